@@ -1,0 +1,335 @@
+"""Aggregator base classes.
+
+``Aggregator`` keeps the reference contract (reference aggregators/base.py:11-103):
+``aggregate(gradients) -> tensor`` plus the ``Operator`` interface with
+``input_key = "gradients"``.  Two family bases carry the B200-native structure:
+
+* :class:`CoordinateWiseAggregator` -- one streaming selection-network pass
+  (``ops.cw_select``); shards over the feature dimension.
+* :class:`GramAggregator` -- Gram pass, n-space solve, weighted-sum pass
+  (``ops.gram`` -> ``ops.nspace`` -> ``ops.weighted_sum``); the Gram shards over the
+  feature dimension (split-K) and the solve never touches the data.
+
+Both expose ``fused_plan()`` so the device parameter server can fold the operator
+into its fused cross-GPU kernel, and both are stateless across calls (re-entrant).
+Inputs may be tensors, ndarrays, ``SharedTensorHandle`` s or handle dicts.
+"""
+from __future__ import annotations
+
+from abc import ABC, abstractmethod
+from typing import Any, Iterable, List, Mapping, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .. import ops
+from ..engine.graph.operator import OpContext, Operator
+from ..engine.graph.subtask import SubTask
+from ..engine.storage.shared_store import (SharedTensorHandle, cleanup_tensor, is_handle,
+                                           materialize, open_tensor, register_tensor)
+from ._chunking import select_adaptive_chunk_size
+
+
+class Aggregator(Operator, ABC):
+    """Base class of every gradient aggregator."""
+
+    name = "aggregator"
+    input_key = "gradients"
+
+    def compute(self, inputs: Mapping[str, Any], *, context: OpContext) -> Any:
+        if self.input_key not in inputs:
+            raise KeyError(f"{self.name} expects input key {self.input_key!r}")
+        grads = inputs[self.input_key]
+        if not isinstance(grads, Sequence):
+            raise TypeError(f"{self.name} expects a sequence at {self.input_key!r}")
+        return self.aggregate(grads)
+
+    @abstractmethod
+    def aggregate(self, gradients: Sequence[Any]) -> Any:
+        ...
+
+    def fused_plan(self, n: int):
+        """Plan object for :class:`byzpy_b200.parallel.device_ps.DeviceRound` (or None)."""
+        return None
+
+
+# --------------------------------------------------------------------------- helpers
+def prepare_rows(gradients: Sequence[Any], what: str = "gradients") -> Tuple[List[torch.Tensor], torch.Tensor]:
+    """Materialise inputs -> (flat row tensors, template tensor for shape/dtype/device)."""
+    if gradients is None or len(gradients) == 0:
+        raise ValueError(f"{what} must be a non-empty sequence")
+    tensors = [materialize(g) for g in gradients]
+    like = tensors[0]
+    dev = like.device
+    rows = []
+    for t in tensors:
+        if t.device != dev:
+            t = t.to(dev)
+        if not t.dtype.is_floating_point:
+            t = t.to(torch.float32)
+        rows.append(t.reshape(-1))
+    d = rows[0].numel()
+    for r in rows:
+        if r.numel() != d:
+            raise ValueError("all gradients must have the same number of elements")
+    if not like.dtype.is_floating_point:
+        like = like.to(torch.float32)
+    return rows, like
+
+
+def finish(vec: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
+    """Reshape / cast a flat result to the template's shape, dtype and device."""
+    return vec.reshape(like.shape).to(dtype=like.dtype, device=like.device)
+
+
+def _kernel_rows(rows: List[torch.Tensor]) -> List[torch.Tensor]:
+    """CUDA rows are fed to the kernels as fp32 (upcast copies for bf16/fp16/fp64)."""
+    if rows[0].is_cuda:
+        return [r if r.dtype == torch.float32 else r.float() for r in rows]
+    return rows
+
+
+def pool_size_of(context: Optional[OpContext]) -> int:
+    meta = (context.metadata if context is not None else None) or {}
+    return int(meta.get("pool_size") or 0)
+
+
+class _Packed:
+    """Rows packaged for subtasks: one host shm matrix, or in-process device rows."""
+
+    __slots__ = ("handle", "rows")
+
+    def __init__(self, handle: Optional[SharedTensorHandle], rows: Optional[List[torch.Tensor]]):
+        self.handle = handle
+        self.rows = rows
+
+    @classmethod
+    def pack(cls, rows: List[torch.Tensor]) -> "_Packed":
+        if rows[0].is_cuda:
+            return cls(None, rows)
+        mat = torch.stack([r.to(torch.float64 if r.dtype == torch.float64 else torch.float32)
+                           for r in rows], dim=0)
+        return cls(register_tensor(mat.numpy()), None)
+
+    def slice(self, start: int, end: int) -> List[torch.Tensor]:
+        if self.rows is not None:
+            return [r[start:end] for r in self.rows]
+        with open_tensor(self.handle) as arr:
+            chunk = torch.from_numpy(np.array(arr[:, start:end], copy=True))
+        return [chunk[i] for i in range(chunk.shape[0])]
+
+    def release(self) -> None:
+        if self.handle is not None:
+            cleanup_tensor(self.handle)
+
+    def __getstate__(self):
+        return (self.handle, self.rows)
+
+    def __setstate__(self, st):
+        self.handle, self.rows = st
+
+
+def feature_chunks(d: int, chunk: int) -> Iterable[Tuple[int, int]]:
+    for s in range(0, d, chunk):
+        yield s, min(d, s + chunk)
+
+
+# --------------------------------------------------------------- coordinate-wise family
+def _cw_chunk(packed: _Packed, start: int, end: int, mode: int, f: int):
+    rows = packed.slice(start, end)
+    out = ops.cw_select(_kernel_rows(rows), mode, f)
+    return start, out
+
+
+class CoordinateWiseAggregator(Aggregator):
+    """Per-coordinate selection over the n inputs (median / trimmed mean / meamed)."""
+
+    supports_subtasks = True
+    max_subtasks_inflight = 0
+    _mode: int = ops.MODE_MEDIAN
+    chunk_size: int = 8192
+
+    def _f(self, n: int) -> int:
+        return 0
+
+    def _validate(self, n: int) -> None:
+        pass
+
+    def aggregate(self, gradients: Sequence[Any]) -> Any:
+        rows, like = prepare_rows(gradients)
+        self._validate(len(rows))
+        out = ops.cw_select(_kernel_rows(rows), self._mode, self._f(len(rows)))
+        return finish(out, like)
+
+    def fused_plan(self, n: int):
+        from ..parallel.device_ps import CwPlan
+
+        self._validate(n)
+        return CwPlan(self._mode, self._f(n))
+
+    def create_subtasks(self, inputs, *, context):
+        grads = inputs.get(self.input_key)
+        if not isinstance(grads, Sequence) or not grads:
+            return []
+        rows, _ = prepare_rows(grads)
+        n, d = len(rows), rows[0].numel()
+        self._validate(n)
+        chunk = select_adaptive_chunk_size(d, self.chunk_size, pool_size=pool_size_of(context))
+        packed = _Packed.pack(rows)
+        mode, f = self._mode, self._f(n)
+
+        def gen():
+            for k, (s, e) in enumerate(feature_chunks(d, chunk)):
+                yield SubTask(fn=_cw_chunk, args=(packed, s, e, mode, f), name=f"{self.name}_chunk_{k}")
+
+        _hold_packed(self, inputs, packed)
+        return gen()
+
+    def reduce_subtasks(self, partials, inputs, *, context):
+        try:
+            if not partials:
+                return self.compute(inputs, context=context)
+            _, like = prepare_rows(inputs[self.input_key])
+            parts = sorted(partials, key=lambda p: p[0])
+            vec = torch.cat([torch.as_tensor(p[1]).reshape(-1).to(like.device) for p in parts])
+            return finish(vec, like)
+        finally:
+            _release_packed(self, inputs)
+
+
+def _hold_packed(op, inputs, packed) -> None:
+    """Keep the shm package alive until ``reduce_subtasks`` for THIS invocation (keyed by the
+    identity of the per-run inputs mapping, so one operator instance stays re-entrant)."""
+    op.__dict__.setdefault("_live_packages", {})[id(inputs)] = packed
+
+
+def _release_packed(op, inputs) -> None:
+    packed = op.__dict__.get("_live_packages", {}).pop(id(inputs), None)
+    if packed is not None:
+        packed.release()
+
+
+# --------------------------------------------------------------------------- Gram family
+def _gram_chunk(packed: _Packed, start: int, end: int):
+    rows = packed.slice(start, end)
+    G = ops.gram(_kernel_rows(rows), want64=True)
+    return G.detach().cpu().numpy()
+
+
+class GramAggregator(Aggregator):
+    """Distance/norm based aggregators: Gram pass -> n-space solve -> weighted sum."""
+
+    supports_subtasks = True
+    max_subtasks_inflight = 0
+    chunk_size: int = 8192      # feature-dimension chunk of the split-K Gram subtasks
+    _gram_chunk_elems: int = 1 << 16
+
+    # -- hooks ---------------------------------------------------------------------
+    def _validate(self, n: int) -> None:
+        pass
+
+    def _aux_rows(self, rows: List[torch.Tensor]) -> List[torch.Tensor]:
+        """Extra rows appended to the Gram (e.g. the median start point of Weiszfeld)."""
+        return []
+
+    @abstractmethod
+    def _solve(self, G: np.ndarray, n: int) -> np.ndarray:
+        """Host solve: fp64 Gram of (rows + aux rows) -> weights over (rows + aux rows)."""
+
+    def _solve_device(self, G: torch.Tensor, n: int) -> Optional[torch.Tensor]:
+        """Optional sync-free device solve (CUDA n-space kernels); None -> host solve."""
+        return None
+
+    # -- direct path ---------------------------------------------------------------
+    def _weights(self, all_rows: List[torch.Tensor], n: int, G: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if G is None:
+            G = ops.gram(all_rows, want64=True)
+        if G.is_cuda:
+            w = self._solve_device(G, n)
+            if w is not None:
+                return w
+        w_np = self._solve(G.detach().cpu().numpy().astype(np.float64), n)
+        return torch.from_numpy(np.asarray(w_np, dtype=np.float32)).to(all_rows[0].device)
+
+    def aggregate(self, gradients: Sequence[Any]) -> Any:
+        rows, like = prepare_rows(gradients)
+        n = len(rows)
+        self._validate(n)
+        krows = _kernel_rows(rows)
+        all_rows = krows + self._aux_rows(krows)
+        w = self._weights(all_rows, n)
+        out = ops.weighted_sum(all_rows, w.reshape(-1))
+        return finish(out, like)
+
+    def fused_plan(self, n: int):
+        from ..parallel.device_ps import GramPlan
+
+        self._validate(n)
+        if type(self)._aux_rows is not GramAggregator._aux_rows:
+            return None
+
+        def solver(G: torch.Tensor) -> torch.Tensor:
+            w = self._solve_device(G.double(), n) if G.is_cuda else None
+            if w is None:
+                w = torch.from_numpy(np.asarray(
+                    self._solve(G.detach().double().cpu().numpy(), n), dtype=np.float32)).to(G.device)
+            return w
+
+        return GramPlan(solver, self.name)
+
+    # -- subtask path: split-K partial Grams -------------------------------------------
+    def _gram_subtasks(self, all_rows: List[torch.Tensor], context) -> Tuple[_Packed, List[SubTask]]:
+        d = all_rows[0].numel()
+        chunk = select_adaptive_chunk_size(d, max(self.chunk_size, 1), pool_size=pool_size_of(context))
+        packed = _Packed.pack(all_rows)
+        tasks = [SubTask(fn=_gram_chunk, args=(packed, s, e), name=f"{self.name}_gram_{k}")
+                 for k, (s, e) in enumerate(feature_chunks(d, chunk))]
+        return packed, tasks
+
+    def create_subtasks(self, inputs, *, context):
+        grads = inputs.get(self.input_key)
+        if not isinstance(grads, Sequence) or not grads:
+            return []
+        rows, _ = prepare_rows(grads)
+        self._validate(len(rows))
+        krows = _kernel_rows(rows)
+        packed, tasks = self._gram_subtasks(krows + self._aux_rows(krows), context)
+        _hold_packed(self, inputs, packed)
+        return tasks
+
+    def _finish_from_partials(self, partials, gradients):
+        rows, like = prepare_rows(gradients)
+        n = len(rows)
+        krows = _kernel_rows(rows)
+        all_rows = krows + self._aux_rows(krows)
+        G = np.zeros((len(all_rows), len(all_rows)), dtype=np.float64)
+        for p in partials:
+            G += np.asarray(p, dtype=np.float64)
+        w = self._weights(all_rows, n, torch.from_numpy(G))
+        return finish(ops.weighted_sum(all_rows, w.reshape(-1)), like)
+
+    def reduce_subtasks(self, partials, inputs, *, context):
+        try:
+            if not partials:
+                return self.compute(inputs, context=context)
+            return self._finish_from_partials(partials, inputs[self.input_key])
+        finally:
+            _release_packed(self, inputs)
+
+    async def run_barriered_subtasks(self, inputs, *, context, pool):
+        """One barrier: fan out the split-K Gram, then solve + weighted sum locally."""
+        grads = inputs.get(self.input_key)
+        if not isinstance(grads, Sequence) or not grads:
+            raise ValueError(f"{self.name} requires a non-empty gradient list.")
+        rows, _ = prepare_rows(grads)
+        self._validate(len(rows))
+        krows = _kernel_rows(rows)
+        packed, tasks = self._gram_subtasks(krows + self._aux_rows(krows), context)
+        try:
+            partials = await self._run_subtasks(pool, tasks, self.max_subtasks_inflight, context)
+            return self._finish_from_partials(partials, grads)
+        finally:
+            packed.release()
+
+
+__all__ = ["Aggregator", "CoordinateWiseAggregator", "GramAggregator", "prepare_rows", "finish"]

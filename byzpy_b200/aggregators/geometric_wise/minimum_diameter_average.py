@@ -1,0 +1,33 @@
+"""Minimum Diameter Averaging: mean of the (n-f)-subset with the smallest diameter
+(max pairwise squared distance); ties resolve to the lexicographically first subset, as the
+reference's seeded DFS does (reference
+aggregators/geometric_wise/minimum_diameter_average.py:328-386).  The search runs on the
+(n, n) distance matrix only (threshold bisection + bitset clique search)."""
+from __future__ import annotations
+
+import numpy as np
+
+from ...ops import nspace
+from ..base import GramAggregator
+
+
+class MinimumDiameterAveraging(GramAggregator):
+    name = "minimum-diameter-averaging"
+
+    def __init__(self, f: int, *, chunk_size: int = 256) -> None:
+        if f < 0:
+            raise ValueError("f must be >= 0")
+        if chunk_size <= 0:
+            raise ValueError("chunk_size must be > 0")
+        self.f = int(f)
+        self.chunk_size = int(chunk_size)
+
+    def _validate(self, n: int) -> None:
+        if not (0 <= self.f < n):
+            raise ValueError(f"f must satisfy 0 <= f < n (got n={n}, f={self.f})")
+
+    def _solve(self, G: np.ndarray, n: int) -> np.ndarray:
+        return nspace.mda_weights(G, self.f)
+
+
+__all__ = ["MinimumDiameterAveraging"]

@@ -1,0 +1,35 @@
+"""MoNNA: mean of the n-f vectors nearest to a trusted reference vector
+(reference aggregators/geometric_wise/monna.py:36-178)."""
+from __future__ import annotations
+
+import numpy as np
+
+from ...ops import nspace
+from ..base import GramAggregator
+
+
+class MoNNA(GramAggregator):
+    name = "monna"
+
+    def __init__(self, f: int, *, reference_index: int = 0, chunk_size: int = 32) -> None:
+        if f < 0:
+            raise ValueError("f must be >= 0")
+        if reference_index < 0:
+            raise ValueError("reference_index must be >= 0")
+        if chunk_size <= 0:
+            raise ValueError("chunk_size must be > 0")
+        self.f = int(f)
+        self.reference_index = int(reference_index)
+        self.chunk_size = int(chunk_size)
+
+    def _validate(self, n: int) -> None:
+        if not (0 <= 2 * self.f < n):
+            raise ValueError(f"2f must be < n (got n={n}, f={self.f})")
+        if self.reference_index >= n:
+            raise ValueError(f"reference_index {self.reference_index} out of range for n={n}")
+
+    def _solve(self, G: np.ndarray, n: int) -> np.ndarray:
+        return nspace.monna_weights(G, self.f, self.reference_index)
+
+
+__all__ = ["MoNNA"]

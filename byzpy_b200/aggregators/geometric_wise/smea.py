@@ -1,0 +1,31 @@
+"""SMEA (smallest maximum eigenvalue averaging): among all (n-f)-subsets pick the one whose
+empirical covariance has the smallest top eigenvalue, computed on the centred m x m Gram
+blocks (reference aggregators/geometric_wise/smea.py:63-88), batched over subsets."""
+from __future__ import annotations
+
+import numpy as np
+
+from ...ops import nspace
+from ..base import GramAggregator
+
+
+class SMEA(GramAggregator):
+    name = "smea"
+
+    def __init__(self, f: int, *, chunk_size: int = 256) -> None:
+        if f < 0:
+            raise ValueError("f must be >= 0")
+        if chunk_size <= 0:
+            raise ValueError("chunk_size must be > 0")
+        self.f = int(f)
+        self.chunk_size = int(chunk_size)
+
+    def _validate(self, n: int) -> None:
+        if not (0 <= 2 * self.f < n):
+            raise ValueError(f"2f must be < n (got n={n}, f={self.f})")
+
+    def _solve(self, G: np.ndarray, n: int) -> np.ndarray:
+        return nspace.smea_weights(G, self.f)
+
+
+__all__ = ["SMEA"]

@@ -1,0 +1,30 @@
+"""CGE: drop the f largest-norm gradients, average the rest (reference
+aggregators/norm_wise/comparative_gradient_elimination.py:28-154).  Only diag(G) is needed."""
+from __future__ import annotations
+
+import numpy as np
+
+from ...ops import nspace
+from ..base import GramAggregator
+
+
+class ComparativeGradientElimination(GramAggregator):
+    name = "comparative-gradient-elimination"
+
+    def __init__(self, f: int, *, chunk_size: int = 8192) -> None:
+        if f < 0:
+            raise ValueError("f must be >= 0")
+        if chunk_size <= 0:
+            raise ValueError("chunk_size must be > 0")
+        self.f = int(f)
+        self.chunk_size = int(chunk_size)
+
+    def _validate(self, n: int) -> None:
+        if not (0 <= self.f < n):
+            raise ValueError(f"f must satisfy 0 <= f < n (got n={n}, f={self.f})")
+
+    def _solve(self, G: np.ndarray, n: int) -> np.ndarray:
+        return nspace.cge_weights(G, self.f)
+
+
+__all__ = ["ComparativeGradientElimination"]

@@ -1,0 +1,186 @@
+// pybind11 bindings for the byzpy_b200 kernel library.
+//
+// Deliberately torch-free: tensors cross the boundary as raw device addresses
+// (tensor.data_ptr()) and the CUDA stream as an integer handle
+// (torch.cuda.current_stream().cuda_stream), so this file compiles in seconds
+// and the .so has no libtorch ABI dependency.
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "api.h"
+#include "runtime.h"
+
+namespace py = pybind11;
+
+namespace {
+
+void check(int err, const char* what) {
+  if (err != 0) {
+    throw std::runtime_error(std::string(what) + ": CUDA error " + std::to_string(err) + " (" +
+                             cudaGetErrorString((cudaError_t)err) + ")");
+  }
+}
+
+template <typename T>
+T* as_ptr(uint64_t v) {
+  return reinterpret_cast<T*>(static_cast<uintptr_t>(v));
+}
+
+void fill_rows(RowTable& rt, ScaleTable& st, const std::vector<uint64_t>& rows,
+               const std::vector<float>& scales) {
+  if (rows.empty() || rows.size() > BZ_MAXN) throw std::invalid_argument("need 1..128 rows");
+  if (!scales.empty() && scales.size() != rows.size())
+    throw std::invalid_argument("scales must match rows");
+  for (size_t i = 0; i < BZ_MAXN; ++i) {
+    rt.p[i] = i < rows.size() ? as_ptr<const float>(rows[i]) : nullptr;
+    st.s[i] = (i < rows.size() && !scales.empty()) ? scales[i] : 1.0f;
+  }
+}
+
+void fill_upd(UpdTable& u, const std::vector<uint64_t>& params, const std::vector<uint64_t>& moms,
+              float lr, float mu, float wd) {
+  if (params.size() > BZ_MAXR) throw std::invalid_argument("too many replicas (max 16)");
+  if (!moms.empty() && moms.size() != params.size())
+    throw std::invalid_argument("moms must match params");
+  std::memset(&u, 0, sizeof(u));
+  u.count = (int)params.size();
+  for (size_t r = 0; r < params.size(); ++r) {
+    u.param[r] = as_ptr<float>(params[r]);
+    u.mom[r] = moms.empty() ? nullptr : as_ptr<float>(moms[r]);
+  }
+  u.lr = lr;
+  u.mu = mu;
+  u.wd = wd;
+}
+
+cudaStream_t as_stream(uint64_t s) { return reinterpret_cast<cudaStream_t>(static_cast<uintptr_t>(s)); }
+
+}  // namespace
+
+PYBIND11_MODULE(_C, m) {
+  m.doc() = "byzpy_b200 sm_100a kernel library";
+  m.attr("MAXN") = BZ_MAXN;
+  m.attr("MAXR") = BZ_MAXR;
+  m.attr("ARCH") = "sm_100a";
+
+  m.def(
+      "cw_select",
+      [](const std::vector<uint64_t>& rows, const std::vector<float>& scales, int mode, int f,
+         int n_virtual, int n_honest, float va, float vb, long long off, long long len,
+         uint64_t out, const std::vector<uint64_t>& upd_params,
+         const std::vector<uint64_t>& upd_moms, float lr, float mu, float wd, int sm_count,
+         uint64_t stream) {
+        BzCwArgs a;
+        std::memset(&a, 0, sizeof(a));
+        fill_rows(a.rows, a.scales, rows, scales);
+        a.n = (int)rows.size();
+        a.virt.count = n_virtual;
+        a.virt.n_honest = n_honest;
+        a.virt.a = va;
+        a.virt.b = vb;
+        a.f = f;
+        a.mode = mode;
+        a.off = off;
+        a.len = len;
+        a.out = as_ptr<float>(out);
+        fill_upd(a.upd, upd_params, upd_moms, lr, mu, wd);
+        check(bz_cw_select(&a, sm_count, as_stream(stream)), "cw_select");
+      },
+      py::arg("rows"), py::arg("scales"), py::arg("mode"), py::arg("f"), py::arg("n_virtual"),
+      py::arg("n_honest"), py::arg("va"), py::arg("vb"), py::arg("off"), py::arg("len"),
+      py::arg("out"), py::arg("upd_params"), py::arg("upd_moms"), py::arg("lr"), py::arg("mu"),
+      py::arg("wd"), py::arg("sm_count"), py::arg("stream"));
+
+  m.def(
+      "wsum",
+      [](const std::vector<uint64_t>& rows, const std::vector<float>& scales, uint64_t W, int mrows,
+         long long off, long long len, const std::vector<uint64_t>& outs,
+         const std::vector<uint64_t>& upd_params, const std::vector<uint64_t>& upd_moms, float lr,
+         float mu, float wd, int sm_count, uint64_t stream) {
+        BzWsumArgs a;
+        std::memset(&a, 0, sizeof(a));
+        fill_rows(a.rows, a.scales, rows, scales);
+        a.n = (int)rows.size();
+        a.m = mrows;
+        a.W = as_ptr<const float>(W);
+        a.off = off;
+        a.len = len;
+        if ((int)outs.size() != mrows || mrows > 8) throw std::invalid_argument("outs must have m<=8 entries");
+        for (int r = 0; r < mrows; ++r) a.out[r] = as_ptr<float>(outs[r]);
+        fill_upd(a.upd, upd_params, upd_moms, lr, mu, wd);
+        check(bz_wsum(&a, sm_count, as_stream(stream)), "wsum");
+      },
+      py::arg("rows"), py::arg("scales"), py::arg("W"), py::arg("m"), py::arg("off"),
+      py::arg("len"), py::arg("outs"), py::arg("upd_params"), py::arg("upd_moms"), py::arg("lr"),
+      py::arg("mu"), py::arg("wd"), py::arg("sm_count"), py::arg("stream"));
+
+  m.def("gram_partials_needed", &bz_gram_partials_needed);
+  m.def(
+      "gram",
+      [](const std::vector<uint64_t>& rows, const std::vector<float>& scales, long long off,
+         long long len, uint64_t partials, int num_partials, uint64_t G, uint64_t G64, int sm_count,
+         uint64_t stream) {
+        BzGramArgs a;
+        std::memset(&a, 0, sizeof(a));
+        fill_rows(a.rows, a.scales, rows, scales);
+        a.n = (int)rows.size();
+        a.off = off;
+        a.len = len;
+        a.partials = as_ptr<float>(partials);
+        a.num_partials = num_partials;
+        a.G = as_ptr<float>(G);
+        a.G64 = as_ptr<double>(G64);
+        check(bz_gram(&a, sm_count, as_stream(stream)), "gram");
+      },
+      py::arg("rows"), py::arg("scales"), py::arg("off"), py::arg("len"), py::arg("partials"),
+      py::arg("num_partials"), py::arg("G"), py::arg("G64"), py::arg("sm_count"),
+      py::arg("stream"));
+
+  m.def(
+      "colstat",
+      [](const std::vector<uint64_t>& rows, const std::vector<float>& scales, float a_, float b_,
+         long long off, long long len, uint64_t out, int sm_count, uint64_t stream) {
+        BzColStatArgs a;
+        std::memset(&a, 0, sizeof(a));
+        fill_rows(a.rows, a.scales, rows, scales);
+        a.n = (int)rows.size();
+        a.a = a_;
+        a.b = b_;
+        a.off = off;
+        a.len = len;
+        a.out = as_ptr<float>(out);
+        check(bz_colstat(&a, sm_count, as_stream(stream)), "colstat");
+      },
+      py::arg("rows"), py::arg("scales"), py::arg("a"), py::arg("b"), py::arg("off"),
+      py::arg("len"), py::arg("out"), py::arg("sm_count"), py::arg("stream"));
+
+  m.def("scale_copy", [](uint64_t src, uint64_t dst, float scale, long long len, int sm_count,
+                         uint64_t stream) {
+    check(bz_scale_copy(as_ptr<const float>(src), as_ptr<float>(dst), scale, len, sm_count,
+                        as_stream(stream)),
+          "scale_copy");
+  });
+  m.def("fill", [](uint64_t dst, float value, long long len, int sm_count, uint64_t stream) {
+    check(bz_fill(as_ptr<float>(dst), value, len, sm_count, as_stream(stream)), "fill");
+  });
+  m.def("gaussian", [](uint64_t dst, float mu, float sigma, unsigned long long seed,
+                       unsigned long long offset, long long len, int sm_count, uint64_t stream) {
+    check(bz_gaussian(as_ptr<float>(dst), mu, sigma, seed, offset, len, sm_count,
+                      as_stream(stream)),
+          "gaussian");
+  });
+  m.def("sgd", [](uint64_t grad, const std::vector<uint64_t>& params,
+                  const std::vector<uint64_t>& moms, float lr, float mu, float wd, long long len,
+                  int sm_count, uint64_t stream) {
+    UpdTable u;
+    fill_upd(u, params, moms, lr, mu, wd);
+    check(bz_sgd(as_ptr<const float>(grad), &u, len, sm_count, as_stream(stream)), "sgd");
+  });
+
+  bz_bind_runtime(m);
+}

@@ -1,0 +1,122 @@
+// Shared device helpers for the byzpy_b200 sm_100a kernels.
+//
+// Conventions used by every kernel in this directory:
+//   * a "row" is one flattened gradient / parameter vector of length d (fp32);
+//   * the n rows of the logical (n, d) matrix are NOT required to be contiguous:
+//     kernels take a RowTable of n base pointers, so rows may live in different
+//     allocations, in a flat arena, or in a *peer GPU's* HBM mapped over NVLink;
+//   * per-row scale factors (sign-flip, clipping, ...) are folded into the load.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define BZ_MAXN 128   // max rows handled by the register / smem resident kernels
+#define BZ_MAXR 16    // max model replicas updated by a fused optimizer epilogue
+
+struct RowTable {
+  const float* p[BZ_MAXN];
+};
+struct ScaleTable {
+  float s[BZ_MAXN];
+};
+
+// Optional fused SGD(+momentum, +weight-decay) epilogue applied to `count`
+// local model replicas with the freshly aggregated gradient.
+struct UpdTable {
+  float* param[BZ_MAXR];
+  float* mom[BZ_MAXR];
+  int count;
+  float lr, mu, wd;
+};
+
+// Virtual (synthesised) rows: `count` identical rows whose value per coordinate
+// is a*mean(h) + b*std(h) over the first `n_honest` real rows.  Little ("a
+// little is enough") and Empire attacks are exactly this, so the
+// omniscient adversary never materialises its vector.
+struct VirtRows {
+  int count;
+  int n_honest;
+  float a, b;
+};
+
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float2 ldg_stream2(const float* p) {
+  float2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];"
+               : "=f"(r.x), "=f"(r.y)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float ldg_stream1(const float* p) {
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+// Coherent (L2) loads for data produced by a peer GPU *during* this kernel.
+__device__ __forceinline__ float4 ldg_cg4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float ldg_cg1(const float* p) {
+  float r;
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream4(float* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void stg_stream1(float* p, float v) {
+  asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+// NaN is canonicalised to +inf on load: a NaN coordinate is treated as an
+// extreme outlier (sorts last, like torch.sort) instead of poisoning min/max.
+__device__ __forceinline__ float canon(float x) { return (x != x) ? __int_as_float(0x7f800000) : x; }
+
+// Fully unrolled bitonic sorting network over a register array (ascending).
+// All indices are compile-time after unrolling, so v[] stays in registers, and
+// the compiler dead-code-eliminates compare-exchanges whose outputs are unused
+// (e.g. when only the median slot is read).
+template <int NP>
+__device__ __forceinline__ void bitonic_sort(float (&v)[NP]) {
+#pragma unroll
+  for (int k = 2; k <= NP; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        const int l = i ^ j;
+        if (l > i) {
+          const bool up = ((i & k) == 0);
+          const float a = v[i], b = v[l];
+          const float lo = fminf(a, b), hi = fmaxf(a, b);
+          v[i] = up ? lo : hi;
+          v[l] = up ? hi : lo;
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+#define BZ_CUDA_CHECK(expr)                                   \
+  do {                                                        \
+    cudaError_t _e = (expr);                                  \
+    if (_e != cudaSuccess) return (int)_e;                    \
+  } while (0)

@@ -1,0 +1,204 @@
+// Fused cross-GPU parameter-server round for the coordinate-wise family.
+//
+// ONE persistent kernel per rank replaces  all_gather -> aggregate -> broadcast
+// -> optimizer.step()  of the reference round (reference
+// engine/parameter_server/ps.py:103-144) with no NCCL call on the path:
+//
+//   phase 0  publish "my gradient rows for epoch e are ready" to every peer's
+//            signal pad (st.release.sys over NVLink);
+//   phase 1  this rank owns the coordinate shard [shard_off, shard_off+shard_len):
+//            for each tile it LOADS the n gradient rows directly from the owning
+//            GPUs' HBM (plain 16-byte P2P ld.global through NVSwitch), runs the
+//            register selection network (median / trimmed mean / mean-of-medians,
+//            attack rows folded in), and STORES the aggregated tile into every
+//            rank's `agg` buffer (P2P st.global) -- gather, math and broadcast in
+//            one pass, tile by tile;
+//   phase 2  after every peer signalled "my shard is delivered", the kernel
+//            applies SGD(+momentum) to all local model replicas from the local
+//            `agg` buffer.
+//
+// Synchronisation is device-side only: monotonically increasing epoch numbers in
+// per-rank signal pads written with release semantics at system scope and polled
+// with acquire loads.  Safety argument (no host barrier needed between rounds):
+//   * a peer can only overwrite my agg buffer for epoch e+1 after it saw my
+//     ready[e+1] flag, which I publish at the start of kernel e+1, i.e. after
+//     my kernel e finished reading agg;
+//   * I only finish kernel e after all peers' done[e] flags, which they publish
+//     after they finished reading my gradient rows, so my next backward may
+//     overwrite them.
+// Every spin loop has a wall-clock budget; on expiry the kernel records an
+// error code in `status` and exits instead of hanging the GPU.
+#include "cw_core.cuh"
+#include "fused_ps.h"
+
+namespace {
+using namespace bzcw;
+
+constexpr unsigned long long kSpinBudgetNs = 20ull * 1000ull * 1000ull * 1000ull;  // 20 s
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Block-wide wait until flags[0..world) have all reached `epoch`.
+// Returns false on timeout (uniform across the block).
+__device__ bool wait_all(const uint32_t* flags, int world, uint32_t epoch, int* status, int code) {
+  __shared__ int s_ok;
+  if (threadIdx.x == 0) s_ok = 1;
+  __syncthreads();
+  if ((int)threadIdx.x < world) {
+    const unsigned long long t0 = globaltimer_ns();
+    while ((int32_t)(ld_acquire_sys(flags + threadIdx.x) - epoch) < 0) {
+      __nanosleep(64);
+      if (globaltimer_ns() - t0 > kSpinBudgetNs) {
+        s_ok = 0;
+        atomicExch(status, code);
+        break;
+      }
+      if (*((volatile int*)status) != 0) {
+        s_ok = 0;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  const bool ok = s_ok != 0;
+  __syncthreads();
+  return ok;
+}
+
+template <int NP, int V, int MODE>
+__global__ void __launch_bounds__(kThreads) fused_ps_cw_kernel(const __grid_constant__ BzFusedPsArgs a) {
+  uint32_t* my_pad = a.pad[a.rank];
+  const uint32_t epoch = a.epoch_ptr ? *a.epoch_ptr : a.epoch;
+  // ---- phase 0: publish readiness of my gradient rows ------------------------
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    __threadfence_system();
+    for (int p = 0; p < a.world; ++p) st_release_sys(a.pad[p] + BZ_PAD_READY + a.rank, epoch);
+  }
+  // ---- phase 1: gather + select + broadcast my shard ---------------------------
+  if (!wait_all(my_pad + BZ_PAD_READY, a.world, epoch, a.status, 1)) return;
+  {
+    const long long nvec = a.shard_len / V;
+    const long long stride = (long long)gridDim.x * kThreads;
+    for (long long u = (long long)blockIdx.x * kThreads + threadIdx.x; u < nvec; u += stride) {
+      const long long base = a.shard_off + u * V;
+      float res[V];
+      cw_unit<NP, V, MODE>(a.rows, a.scales, a.n, a.virt, a.f, base, res);
+      for (int p = 0; p < a.world; ++p) {
+        float* dst = a.agg[p] + base;
+        if constexpr (V == 4) {
+          stg_stream4(dst, make_float4(res[0], res[1], res[2], res[3]));
+        } else {
+#pragma unroll
+          for (int c = 0; c < V; ++c) stg_stream1(dst + c, res[c]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const unsigned int prev = atomicAdd(a.counter, 1u);
+    if (prev == gridDim.x - 1) {
+      // last CTA of this rank: my shard has been delivered everywhere
+      *a.counter = 0u;
+      __threadfence_system();
+      for (int p = 0; p < a.world; ++p) st_release_sys(a.pad[p] + BZ_PAD_DONE + a.rank, epoch);
+    }
+  }
+  // ---- phase 2: optimizer step on the local replicas ---------------------------
+  if (a.upd.count <= 0 && a.world == 1) return;
+  if (!wait_all(my_pad + BZ_PAD_DONE, a.world, epoch, a.status, 2)) return;
+  if (a.upd.count > 0) {
+    const float* agg = a.agg[a.rank];
+    const long long nvec4 = a.d / 4;
+    const long long stride = (long long)gridDim.x * kThreads;
+    for (long long u = (long long)blockIdx.x * kThreads + threadIdx.x; u < nvec4; u += stride) {
+      const float4 g4 = ldg_cg4(agg + u * 4);
+      const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+      sgd_apply<4>(a.upd, u * 4, g);
+    }
+    const long long t0 = nvec4 * 4;
+    const long long j = t0 + (long long)blockIdx.x * kThreads + threadIdx.x;
+    if (j < a.d) {
+      const float g[1] = {ldg_cg1(agg + j)};
+      sgd_apply<1>(a.upd, j, g);
+    }
+  }
+}
+
+template <int NP, int MODE>
+int launch_np(const BzFusedPsArgs& a, int grid, cudaStream_t stream) {
+  constexpr int V = (NP <= 16) ? 4 : (NP == 32 ? 2 : 1);
+  fused_ps_cw_kernel<NP, V, MODE><<<grid, kThreads, 0, stream>>>(a);
+  return (int)cudaGetLastError();
+}
+
+template <int NP, int MODE>
+int max_grid_np(int sm_count) {
+  constexpr int V = (NP <= 16) ? 4 : (NP == 32 ? 2 : 1);
+  int per_sm = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+      &per_sm, fused_ps_cw_kernel<NP, V, MODE>, kThreads, 0);
+  if (e != cudaSuccess || per_sm < 1) per_sm = 1;
+  if (per_sm > 4) per_sm = 4;
+  return per_sm * sm_count;
+}
+
+template <int MODE>
+int dispatch_mode(const BzFusedPsArgs& a, int sm_count, cudaStream_t stream, bool query) {
+  const int nt = a.n + a.virt.count;
+#define BZ_CASE(NP)                                                   \
+  if (nt <= NP) {                                                     \
+    const int g = max_grid_np<NP, MODE>(sm_count);                    \
+    if (query) return g;                                              \
+    return launch_np<NP, MODE>(a, g, stream);                         \
+  }
+  BZ_CASE(2) BZ_CASE(4) BZ_CASE(8) BZ_CASE(16) BZ_CASE(32) BZ_CASE(64)
+#undef BZ_CASE
+  return query ? 0 : (int)cudaErrorInvalidValue;
+}
+
+__global__ void bump_u32_kernel(uint32_t* p) { *p = *p + 1u; }
+
+}  // namespace
+
+int bz_bump_u32(uint32_t* p, cudaStream_t stream) {
+  bump_u32_kernel<<<1, 1, 0, stream>>>(p);
+  return (int)cudaGetLastError();
+}
+
+int bz_fused_ps_cw(const BzFusedPsArgs* args, int sm_count, cudaStream_t stream) {
+  const BzFusedPsArgs& a = *args;
+  const int nt = a.n + a.virt.count;
+  if (a.n < 1 || nt > 64 || a.world < 1 || a.world > BZ_MAXW || a.rank < 0 || a.rank >= a.world)
+    return (int)cudaErrorInvalidValue;
+  // the fused kernel is vector-only: arenas are 16-byte aligned and padded by construction
+  if ((a.shard_off % 4) != 0 || (a.shard_len % 4) != 0) return (int)cudaErrorInvalidValue;
+  for (int i = 0; i < a.n; ++i)
+    if (((uintptr_t)a.rows.p[i] % 16) != 0) return (int)cudaErrorInvalidValue;
+  for (int p = 0; p < a.world; ++p)
+    if (((uintptr_t)a.agg[p] % 16) != 0) return (int)cudaErrorInvalidValue;
+  for (int r = 0; r < a.upd.count; ++r)
+    if (((uintptr_t)a.upd.param[r] % 16) != 0 ||
+        (a.upd.mom[r] && ((uintptr_t)a.upd.mom[r] % 16) != 0))
+      return (int)cudaErrorInvalidValue;
+  switch (a.mode) {
+    case BZ_CW_MEDIAN: return dispatch_mode<BZ_CW_MEDIAN>(a, sm_count, stream, false);
+    case BZ_CW_TRMEAN: return dispatch_mode<BZ_CW_TRMEAN>(a, sm_count, stream, false);
+    case BZ_CW_MEAMED: return dispatch_mode<BZ_CW_MEAMED>(a, sm_count, stream, false);
+    case BZ_CW_MEAN: return dispatch_mode<BZ_CW_MEAN>(a, sm_count, stream, false);
+    default: return (int)cudaErrorInvalidValue;
+  }
+}

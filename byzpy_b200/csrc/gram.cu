@@ -1,0 +1,246 @@
+// Gram matrix  G = (S X)(S X)^T  on CUDA cores, exact fp32 products with a
+// deterministic two-stage split-K reduction (fp64 final accumulation).
+//
+// This is the reference-precision path and the fallback for the tcgen05
+// kernel in gram_umma.cu.  "Pass 1" of every Gram-family operator (Krum,
+// Multi-Krum, MoNNA, CGE, NNM, ARC, Clipping, MDA, SMEA, and the Gram-space
+// Weiszfeld / centered-clipping / CAF solves): one read of n*d*4
+// bytes, (n, n) result.
+// Parity: reference krum.py:31-44 (pairwise squared distances via Gram).
+#include "api.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+// ---------------------------------------------------------------- small n --
+// n <= 16: every thread streams V consecutive coordinates of all rows and keeps
+// the upper triangle of the outer product in registers.
+template <int NS, int V>
+__global__ void __launch_bounds__(kThreads) gram_small_kernel(const __grid_constant__ BzGramArgs a) {
+  constexpr int T = NS * (NS + 1) / 2;
+  float acc[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) acc[t] = 0.f;
+  const int n = a.n;
+  const long long nvec = a.len / V;
+  const long long stride = (long long)gridDim.x * kThreads;
+  for (long long u = (long long)blockIdx.x * kThreads + threadIdx.x; u < nvec; u += stride) {
+    const long long base = a.off + u * V;
+    float x[NS][V];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      if (i < n) {
+        if constexpr (V == 4) {
+          const float4 t = ldg_stream4(a.rows.p[i] + base);
+          x[i][0] = t.x; x[i][1] = t.y; x[i][2] = t.z; x[i][3] = t.w;
+        } else if constexpr (V == 2) {
+          const float2 t = ldg_stream2(a.rows.p[i] + base);
+          x[i][0] = t.x; x[i][1] = t.y;
+        } else {
+          x[i][0] = ldg_stream1(a.rows.p[i] + base);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < V; ++c) x[i][c] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < V; ++c) {
+      int t = 0;
+#pragma unroll
+      for (int i = 0; i < NS; ++i)
+#pragma unroll
+        for (int k = i; k < NS; ++k) {
+          acc[t] = fmaf(x[i][c], x[k][c], acc[t]);
+          ++t;
+        }
+    }
+  }
+  // scalar tail (len % V) handled by block 0
+  if (V > 1 && blockIdx.x == 0) {
+    const long long tail0 = a.off + nvec * V;
+    const long long tail = a.len - nvec * V;
+    if ((long long)threadIdx.x < tail) {
+      float x1[NS];
+#pragma unroll
+      for (int i = 0; i < NS; ++i) x1[i] = (i < n) ? a.rows.p[i][tail0 + threadIdx.x] : 0.f;
+      int t = 0;
+#pragma unroll
+      for (int i = 0; i < NS; ++i)
+#pragma unroll
+        for (int k = i; k < NS; ++k) {
+          acc[t] = fmaf(x1[i], x1[k], acc[t]);
+          ++t;
+        }
+    }
+  }
+  __shared__ float red[kWarps][T];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const float s = warp_sum(acc[t]);
+    if (lane == 0) red[warp][t] = s;
+  }
+  __syncthreads();
+  float* part = a.partials + (size_t)blockIdx.x * n * n;
+  for (int t = threadIdx.x; t < T; t += kThreads) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) s += red[w][t];
+    // decode t -> (i, k), i <= k
+    int i = 0, rem = t;
+    while (rem >= NS - i) {
+      rem -= NS - i;
+      ++i;
+    }
+    const int k = i + rem;
+    if (i < n && k < n) {
+      part[i * n + k] = s;
+      part[k * n + i] = s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- tiled n --
+// 16 < n <= 128: 32-column tiles staged (transposed) in shared memory with a
+// register prefetch double buffer; 16x16 threads each own an RB x RB block.
+template <int RB>
+__global__ void __launch_bounds__(kThreads) gram_tiled_kernel(const __grid_constant__ BzGramArgs a) {
+  constexpr int NPAD = 16 * RB, TJ = 32, LD = NPAD + 1;
+  constexpr int RPW = NPAD / kWarps;  // rows per warp
+  __shared__ float Xs[2][TJ][LD];
+  const int n = a.n;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  const long long nchunks = (a.len + TJ - 1) / TJ;
+  float acc[RB][RB];
+#pragma unroll
+  for (int p = 0; p < RB; ++p)
+#pragma unroll
+    for (int q = 0; q < RB; ++q) acc[p][q] = 0.f;
+
+  float pref[RPW];
+  auto gload = [&](long long chunk) {
+    const long long col = chunk * TJ + lane;
+    const bool ok = col < a.len;
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      const int i = warp + kWarps * r;
+      pref[r] = (ok && i < n) ? ldg_stream1(a.rows.p[i] + a.off + col) : 0.f;
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) Xs[buf][lane][warp + kWarps * r] = pref[r];
+  };
+
+  long long chunk = blockIdx.x;
+  int buf = 0;
+  if (chunk < nchunks) {
+    gload(chunk);
+    sstore(0);
+  }
+  __syncthreads();
+  for (; chunk < nchunks; chunk += gridDim.x) {
+    const long long next = chunk + gridDim.x;
+    if (next < nchunks) gload(next);
+#pragma unroll 8
+    for (int j = 0; j < TJ; ++j) {
+      float av[RB], bv[RB];
+#pragma unroll
+      for (int p = 0; p < RB; ++p) av[p] = Xs[buf][j][ty + 16 * p];
+#pragma unroll
+      for (int q = 0; q < RB; ++q) bv[q] = Xs[buf][j][tx + 16 * q];
+#pragma unroll
+      for (int p = 0; p < RB; ++p)
+#pragma unroll
+        for (int q = 0; q < RB; ++q) acc[p][q] = fmaf(av[p], bv[q], acc[p][q]);
+    }
+    if (next < nchunks) sstore(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+  float* part = a.partials + (size_t)blockIdx.x * n * n;
+#pragma unroll
+  for (int p = 0; p < RB; ++p)
+#pragma unroll
+    for (int q = 0; q < RB; ++q) {
+      const int i = ty + 16 * p, k = tx + 16 * q;
+      if (i < n && k < n) part[i * n + k] = acc[p][q];
+    }
+}
+
+__global__ void gram_reduce_kernel(const float* __restrict__ partials, int num_partials, int n,
+                                   ScaleTable scales, float* __restrict__ G,
+                                   double* __restrict__ G64) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * n) return;
+  double s = 0.0;
+  for (int c = 0; c < num_partials; ++c) s += (double)partials[(size_t)c * n * n + t];
+  const int i = t / n, k = t % n;
+  s *= (double)scales.s[i] * (double)scales.s[k];
+  G[t] = (float)s;
+  if (G64) G64[t] = s;
+}
+
+int grid_for(int n, long long len, int sm_count) {
+  long long blocks;
+  if (n <= 16) {
+    const int V = (n <= 8) ? 4 : 2;
+    const long long nvec = len / V;
+    blocks = (nvec + kThreads - 1) / kThreads;
+    const long long cap = (long long)sm_count * 4;
+    if (blocks > cap) blocks = cap;
+  } else {
+    blocks = (len + 31) / 32;
+    const long long cap = (long long)sm_count * 2;
+    if (blocks > cap) blocks = cap;
+  }
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace
+
+int bz_gram_partials_needed(int n, int sm_count) { return sm_count * 4 * n * n; }
+
+int bz_gram(const BzGramArgs* args, int sm_count, cudaStream_t stream) {
+  const BzGramArgs& a0 = *args;
+  if (a0.n < 1 || a0.n > BZ_MAXN || a0.len < 0) return (int)cudaErrorInvalidValue;
+  BzGramArgs a = a0;
+  const int n = a.n;
+  const int grid = grid_for(n, a.len, sm_count);
+  if (grid > a.num_partials) return (int)cudaErrorInvalidValue;
+  bool al16 = (a.off % 4) == 0, al8 = (a.off % 2) == 0;
+  for (int i = 0; i < n; ++i) {
+    al16 = al16 && ((uintptr_t)a.rows.p[i] % 16) == 0;
+    al8 = al8 && ((uintptr_t)a.rows.p[i] % 8) == 0;
+  }
+  if (n <= 2) {
+    if (al16) gram_small_kernel<2, 4><<<grid, kThreads, 0, stream>>>(a);
+    else gram_small_kernel<2, 1><<<grid, kThreads, 0, stream>>>(a);
+  } else if (n <= 4) {
+    if (al16) gram_small_kernel<4, 4><<<grid, kThreads, 0, stream>>>(a);
+    else gram_small_kernel<4, 1><<<grid, kThreads, 0, stream>>>(a);
+  } else if (n <= 8) {
+    if (al16) gram_small_kernel<8, 4><<<grid, kThreads, 0, stream>>>(a);
+    else gram_small_kernel<8, 1><<<grid, kThreads, 0, stream>>>(a);
+  } else if (n <= 16) {
+    if (al8) gram_small_kernel<16, 2><<<grid, kThreads, 0, stream>>>(a);
+    else gram_small_kernel<16, 1><<<grid, kThreads, 0, stream>>>(a);
+  } else if (n <= 32) {
+    gram_tiled_kernel<2><<<grid, kThreads, 0, stream>>>(a);
+  } else if (n <= 64) {
+    gram_tiled_kernel<4><<<grid, kThreads, 0, stream>>>(a);
+  } else {
+    gram_tiled_kernel<8><<<grid, kThreads, 0, stream>>>(a);
+  }
+  int e = (int)cudaGetLastError();
+  if (e) return e;
+  const int rt = 128;
+  gram_reduce_kernel<<<(n * n + rt - 1) / rt, rt, 0, stream>>>(a.partials, grid, n, a.scales, a.G,
+                                                               a.G64);
+  return (int)cudaGetLastError();
+}

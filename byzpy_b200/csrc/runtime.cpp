@@ -1,0 +1,162 @@
+// Native runtime of byzpy_b200 (host side, C++17).
+//
+// Symmetric memory: every rank cudaMalloc's identically sized arenas, exports
+// them as CUDA IPC handles, and maps every peer's arena into its own address
+// space.  The kernels in fused_ps.cu then address peer HBM directly
+// (ld.global / st.global over NVLink 5 through NVSwitch); NCCL/Gloo are used
+// only to exchange the 64-byte handles at start-up.  This replaces the
+// reference's POSIX-shm store (reference engine/storage/shared_store.py:21-54)
+// and its pickle/UCX tensor transport (engine/actor/transports/ucx.py:225-270).
+#include "runtime.h"
+
+#include <pybind11/stl.h>
+
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "fused_ps.h"
+
+namespace py = pybind11;
+
+namespace {
+
+void check(cudaError_t e, const char* what) {
+  if (e != cudaSuccess)
+    throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+template <typename T>
+T* as_ptr(uint64_t v) {
+  return reinterpret_cast<T*>(static_cast<uintptr_t>(v));
+}
+cudaStream_t as_stream(uint64_t s) { return reinterpret_cast<cudaStream_t>(static_cast<uintptr_t>(s)); }
+
+}  // namespace
+
+void bz_bind_runtime(py::module_& m) {
+  m.def("device_count", [] {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+  });
+  m.def("sm_count", [](int device) {
+    int v = 0;
+    check(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device), "sm_count");
+    return v;
+  });
+  m.def("raw_alloc", [](size_t bytes) {
+    void* p = nullptr;
+    check(cudaMalloc(&p, bytes), "cudaMalloc");
+    check(cudaMemset(p, 0, bytes), "cudaMemset");
+    return (uint64_t)(uintptr_t)p;
+  });
+  m.def("raw_free", [](uint64_t p) { check(cudaFree(as_ptr<void>(p)), "cudaFree"); });
+  m.def("ipc_export", [](uint64_t p) {
+    cudaIpcMemHandle_t h;
+    check(cudaIpcGetMemHandle(&h, as_ptr<void>(p)), "cudaIpcGetMemHandle");
+    return py::bytes(reinterpret_cast<const char*>(&h), sizeof(h));
+  });
+  m.def("ipc_open", [](const std::string& handle) {
+    if (handle.size() != sizeof(cudaIpcMemHandle_t)) throw std::invalid_argument("bad IPC handle");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle.data(), sizeof(h));
+    void* p = nullptr;
+    check(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+    return (uint64_t)(uintptr_t)p;
+  });
+  m.def("ipc_close", [](uint64_t p) { check(cudaIpcCloseMemHandle(as_ptr<void>(p)), "cudaIpcCloseMemHandle"); });
+  m.def("can_access_peer", [](int dev, int peer) {
+    int ok = 0;
+    check(cudaDeviceCanAccessPeer(&ok, dev, peer), "cudaDeviceCanAccessPeer");
+    return ok != 0;
+  });
+  m.def("enable_peer_access", [](int peer) {
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+      cudaGetLastError();
+      return;
+    }
+    check(e, "cudaDeviceEnablePeerAccess");
+  });
+  m.def("memset32_async", [](uint64_t p, uint32_t value, size_t words, uint64_t stream) {
+    if (value == 0) {
+      check(cudaMemsetAsync(as_ptr<void>(p), 0, words * 4, as_stream(stream)), "cudaMemsetAsync");
+    } else {
+      std::vector<uint32_t> host(words, value);
+      check(cudaMemcpyAsync(as_ptr<void>(p), host.data(), words * 4, cudaMemcpyHostToDevice,
+                            as_stream(stream)),
+            "cudaMemcpyAsync");
+      check(cudaStreamSynchronize(as_stream(stream)), "cudaStreamSynchronize");
+    }
+  });
+  m.def("read_i32", [](uint64_t p) {
+    int v = 0;
+    check(cudaMemcpy(&v, as_ptr<void>(p), 4, cudaMemcpyDeviceToHost), "cudaMemcpy");
+    return v;
+  });
+
+  m.def("bump_u32", [](uint64_t p, uint64_t stream) {
+    int e = bz_bump_u32(as_ptr<uint32_t>(p), as_stream(stream));
+    if (e != 0) throw std::runtime_error("bump_u32 failed");
+  });
+  m.attr("PAD_WORDS") = BZ_PAD_WORDS;
+  m.attr("MAXW") = BZ_MAXW;
+
+  m.def(
+      "fused_ps_cw",
+      [](const std::vector<uint64_t>& rows, const std::vector<float>& scales, int mode, int f,
+         int n_virtual, int n_honest, float va, float vb, long long d, long long shard_off,
+         long long shard_len, int rank, const std::vector<uint64_t>& agg,
+         const std::vector<uint64_t>& pads, uint32_t epoch, uint64_t epoch_ptr, uint64_t counter, uint64_t status,
+         const std::vector<uint64_t>& upd_params, const std::vector<uint64_t>& upd_moms, float lr,
+         float mu, float wd, int sm_count, uint64_t stream) {
+        BzFusedPsArgs a;
+        std::memset(&a, 0, sizeof(a));
+        if (rows.empty() || rows.size() > BZ_MAXN) throw std::invalid_argument("rows");
+        if (agg.size() != pads.size() || agg.empty() || agg.size() > BZ_MAXW)
+          throw std::invalid_argument("agg/pads");
+        for (size_t i = 0; i < BZ_MAXN; ++i) {
+          a.rows.p[i] = i < rows.size() ? as_ptr<const float>(rows[i]) : nullptr;
+          a.scales.s[i] = (i < scales.size()) ? scales[i] : 1.0f;
+        }
+        a.n = (int)rows.size();
+        a.virt.count = n_virtual;
+        a.virt.n_honest = n_honest;
+        a.virt.a = va;
+        a.virt.b = vb;
+        a.f = f;
+        a.mode = mode;
+        a.d = d;
+        a.shard_off = shard_off;
+        a.shard_len = shard_len;
+        a.rank = rank;
+        a.world = (int)agg.size();
+        for (size_t p = 0; p < agg.size(); ++p) {
+          a.agg[p] = as_ptr<float>(agg[p]);
+          a.pad[p] = as_ptr<uint32_t>(pads[p]);
+        }
+        a.epoch = epoch;
+        a.epoch_ptr = as_ptr<const uint32_t>(epoch_ptr);
+        a.counter = as_ptr<unsigned int>(counter);
+        a.status = as_ptr<int>(status);
+        if (upd_params.size() > BZ_MAXR) throw std::invalid_argument("too many replicas");
+        a.upd.count = (int)upd_params.size();
+        for (size_t r = 0; r < upd_params.size(); ++r) {
+          a.upd.param[r] = as_ptr<float>(upd_params[r]);
+          a.upd.mom[r] = upd_moms.empty() ? nullptr : as_ptr<float>(upd_moms[r]);
+        }
+        a.upd.lr = lr;
+        a.upd.mu = mu;
+        a.upd.wd = wd;
+        int e = bz_fused_ps_cw(&a, sm_count, as_stream(stream));
+        if (e != 0)
+          throw std::runtime_error(std::string("fused_ps_cw: CUDA error ") +
+                                   cudaGetErrorString((cudaError_t)e));
+      },
+      py::arg("rows"), py::arg("scales"), py::arg("mode"), py::arg("f"), py::arg("n_virtual"),
+      py::arg("n_honest"), py::arg("va"), py::arg("vb"), py::arg("d"), py::arg("shard_off"),
+      py::arg("shard_len"), py::arg("rank"), py::arg("agg"), py::arg("pads"), py::arg("epoch"), py::arg("epoch_ptr"),
+      py::arg("counter"), py::arg("status"), py::arg("upd_params"), py::arg("upd_moms"),
+      py::arg("lr"), py::arg("mu"), py::arg("wd"), py::arg("sm_count"), py::arg("stream"));
+}

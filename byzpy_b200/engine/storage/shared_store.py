@@ -1,0 +1,97 @@
+"""Host shared-memory tensor store (CPU plumbing path).
+
+API-compatible with the reference store (reference
+engine/storage/shared_store.py:11-54): ``register_tensor`` copies an array into a
+named POSIX shm segment and returns a picklable ``SharedTensorHandle``;
+``open_tensor`` maps it as a NumPy view; ``cleanup_tensor`` unlinks it.
+
+On the B200 path this store is bypassed entirely: device tensors are shared as
+``DeviceTensorHandle`` s (CUDA-IPC addresses, see ``byzpy_b200.parallel.symmetric``)
+and never bounce through the host.  Unlike the reference, ``handle.dtype`` being
+a string is handled everywhere (``materialize`` below), so aggregators accept
+handles directly (fixes the reference's ``ParameterServer`` + median TypeError,
+SURVEY 0.4).
+"""
+from __future__ import annotations
+
+from contextlib import contextmanager
+from dataclasses import dataclass
+from multiprocessing import shared_memory
+from typing import Any, Iterator, Tuple, Union
+
+import numpy as np
+import torch
+
+
+@dataclass(frozen=True)
+class SharedTensorHandle:
+    name: str
+    shape: Tuple[int, ...]
+    dtype: str
+
+
+SharedHandleLike = Union[SharedTensorHandle, dict]
+
+
+def _coerce(handle: SharedHandleLike) -> SharedTensorHandle:
+    if isinstance(handle, SharedTensorHandle):
+        return handle
+    if isinstance(handle, dict):
+        return SharedTensorHandle(name=handle["name"], shape=tuple(handle["shape"]),
+                                  dtype=str(handle["dtype"]))
+    raise TypeError(f"not a shared tensor handle: {type(handle)!r}")
+
+
+def is_handle(obj: Any) -> bool:
+    return isinstance(obj, SharedTensorHandle) or (
+        isinstance(obj, dict) and {"name", "shape", "dtype"} <= set(obj.keys()))
+
+
+def register_tensor(array: Any) -> SharedTensorHandle:
+    if isinstance(array, torch.Tensor):
+        array = array.detach().cpu().numpy()
+    arr = np.ascontiguousarray(array)
+    seg = shared_memory.SharedMemory(create=True, size=max(1, arr.nbytes))
+    try:
+        np.ndarray(arr.shape, dtype=arr.dtype, buffer=seg.buf)[...] = arr
+    finally:
+        seg.close()
+    return SharedTensorHandle(name=seg.name, shape=tuple(arr.shape), dtype=str(arr.dtype))
+
+
+@contextmanager
+def open_tensor(handle: SharedHandleLike) -> Iterator[np.ndarray]:
+    h = _coerce(handle)
+    seg = shared_memory.SharedMemory(name=h.name)
+    try:
+        yield np.ndarray(h.shape, dtype=np.dtype(h.dtype), buffer=seg.buf)
+    finally:
+        seg.close()
+
+
+def cleanup_tensor(handle: SharedHandleLike) -> None:
+    h = _coerce(handle)
+    try:
+        seg = shared_memory.SharedMemory(name=h.name)
+    except FileNotFoundError:
+        return
+    try:
+        seg.unlink()
+    finally:
+        seg.close()
+
+
+def materialize(obj: Any) -> torch.Tensor:
+    """Tensor / ndarray / handle / handle-dict / sequence -> ``torch.Tensor`` (copies out of shm)."""
+    if isinstance(obj, torch.Tensor):
+        return obj
+    if is_handle(obj):
+        with open_tensor(obj) as arr:
+            return torch.from_numpy(np.array(arr, copy=True))
+    if isinstance(obj, np.ndarray):
+        return torch.from_numpy(obj)
+    return torch.as_tensor(obj)
+
+
+__all__ = ["SharedTensorHandle", "register_tensor", "open_tensor", "cleanup_tensor", "is_handle",
+           "materialize"]

@@ -1,0 +1,117 @@
+"""ResNet-18/34/50 (He et al.) written against plain ``torch.nn``.
+
+The heavy lifting (convolutions, batch-norm) stays in cuDNN/cuBLAS via PyTorch
+(model fwd/bwd is library territory); the framework's own kernels
+take over at the gradient arena.  Module and parameter names follow the
+torchvision layout (``conv1, bn1, layer1.0.conv1, ..., fc``) so a reference
+``state_dict`` checkpoint loads with ``strict=True``.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Type, Union
+
+import torch
+import torch.nn as nn
+
+
+def _conv3x3(cin: int, cout: int, stride: int = 1) -> nn.Conv2d:
+    return nn.Conv2d(cin, cout, 3, stride=stride, padding=1, bias=False)
+
+
+def _conv1x1(cin: int, cout: int, stride: int = 1) -> nn.Conv2d:
+    return nn.Conv2d(cin, cout, 1, stride=stride, bias=False)
+
+
+class BasicBlock(nn.Module):
+    expansion = 1
+
+    def __init__(self, cin: int, width: int, stride: int = 1, downsample: nn.Module | None = None):
+        super().__init__()
+        self.conv1 = _conv3x3(cin, width, stride)
+        self.bn1 = nn.BatchNorm2d(width)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2 = _conv3x3(width, width)
+        self.bn2 = nn.BatchNorm2d(width)
+        self.downsample = downsample
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        idt = x if self.downsample is None else self.downsample(x)
+        y = self.relu(self.bn1(self.conv1(x)))
+        y = self.bn2(self.conv2(y))
+        return self.relu(y + idt)
+
+
+class Bottleneck(nn.Module):
+    expansion = 4
+
+    def __init__(self, cin: int, width: int, stride: int = 1, downsample: nn.Module | None = None):
+        super().__init__()
+        self.conv1 = _conv1x1(cin, width)
+        self.bn1 = nn.BatchNorm2d(width)
+        self.conv2 = _conv3x3(width, width, stride)
+        self.bn2 = nn.BatchNorm2d(width)
+        self.conv3 = _conv1x1(width, width * 4)
+        self.bn3 = nn.BatchNorm2d(width * 4)
+        self.relu = nn.ReLU(inplace=True)
+        self.downsample = downsample
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        idt = x if self.downsample is None else self.downsample(x)
+        y = self.relu(self.bn1(self.conv1(x)))
+        y = self.relu(self.bn2(self.conv2(y)))
+        y = self.bn3(self.conv3(y))
+        return self.relu(y + idt)
+
+
+class ResNet(nn.Module):
+    def __init__(self, block: Type[Union[BasicBlock, Bottleneck]], depths: Sequence[int],
+                 num_classes: int = 1000, in_channels: int = 3, small_input: bool = False):
+        super().__init__()
+        self._cin = 64
+        if small_input:  # CIFAR-style stem
+            self.conv1 = nn.Conv2d(in_channels, 64, 3, stride=1, padding=1, bias=False)
+            self.maxpool = nn.Identity()
+        else:
+            self.conv1 = nn.Conv2d(in_channels, 64, 7, stride=2, padding=3, bias=False)
+            self.maxpool = nn.MaxPool2d(3, stride=2, padding=1)
+        self.bn1 = nn.BatchNorm2d(64)
+        self.relu = nn.ReLU(inplace=True)
+        self.layer1 = self._stage(block, 64, depths[0], 1)
+        self.layer2 = self._stage(block, 128, depths[1], 2)
+        self.layer3 = self._stage(block, 256, depths[2], 2)
+        self.layer4 = self._stage(block, 512, depths[3], 2)
+        self.avgpool = nn.AdaptiveAvgPool2d(1)
+        self.fc = nn.Linear(512 * block.expansion, num_classes)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.ones_(m.weight)
+                nn.init.zeros_(m.bias)
+
+    def _stage(self, block, width: int, depth: int, stride: int) -> nn.Sequential:
+        down = None
+        if stride != 1 or self._cin != width * block.expansion:
+            down = nn.Sequential(_conv1x1(self._cin, width * block.expansion, stride),
+                                 nn.BatchNorm2d(width * block.expansion))
+        layers: List[nn.Module] = [block(self._cin, width, stride, down)]
+        self._cin = width * block.expansion
+        layers += [block(self._cin, width) for _ in range(1, depth)]
+        return nn.Sequential(*layers)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+        x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
+        return self.fc(torch.flatten(self.avgpool(x), 1))
+
+
+def resnet18(num_classes: int = 1000, **kw) -> ResNet:
+    return ResNet(BasicBlock, (2, 2, 2, 2), num_classes, **kw)
+
+
+def resnet34(num_classes: int = 1000, **kw) -> ResNet:
+    return ResNet(BasicBlock, (3, 4, 6, 3), num_classes, **kw)
+
+
+def resnet50(num_classes: int = 1000, **kw) -> ResNet:
+    return ResNet(Bottleneck, (3, 4, 6, 3), num_classes, **kw)

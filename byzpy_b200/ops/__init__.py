@@ -1,0 +1,386 @@
+"""Functional front-end of the sm_100a kernel library.
+
+Every function takes the logical ``(n, d)`` gradient matrix as a *list of n
+row tensors* (or one 2-D tensor): rows are addressed through a pointer table,
+so nothing is ever ``torch.stack``-ed on the GPU path -- rows may live in
+different allocations, in a flat arena, or in a peer GPU's memory.
+
+Dispatch rule (no silent fallbacks on a GPU box):
+  * CUDA fp32 rows, ``n <= 128``  -> hand-written kernels in ``byzpy_b200._C``;
+    if the extension cannot be imported a ``RuntimeError`` is raised.
+  * CPU tensors (and exotic dtypes / n > 128) -> the plain PyTorch reference
+    implementations in :mod:`byzpy_b200.ops.reference`, which are also the
+    oracle the GPU numerics tests compare against.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple, Union
+
+import torch
+
+from . import reference as ref
+
+MODE_MEDIAN, MODE_TRMEAN, MODE_MEAMED, MODE_MEAN = 0, 1, 2, 3
+MAXN = 128
+MAXR = 16
+
+_C = None
+_C_err: Optional[BaseException] = None
+
+
+def _load_ext():
+    global _C, _C_err
+    if _C is not None:
+        return _C
+    try:
+        from .. import _C as ext  # type: ignore[attr-defined]
+
+        _C = ext
+    except Exception as exc:  # pragma: no cover - exercised only on broken installs
+        _C_err = exc
+        _C = None
+    return _C
+
+
+def extension_available() -> bool:
+    return _load_ext() is not None
+
+
+def require_ext():
+    ext = _load_ext()
+    if ext is None:
+        raise RuntimeError(
+            "byzpy_b200._C (sm_100a kernel library) is not built/importable; run "
+            "`python -m byzpy_b200._build`. Refusing to fall back to PyTorch on a CUDA device. "
+            f"Import error: {_C_err!r}"
+        )
+    return ext
+
+
+_SM_COUNT: dict = {}
+
+
+def sm_count(device: torch.device) -> int:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _SM_COUNT:
+        _SM_COUNT[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
+    return _SM_COUNT[idx]
+
+
+def _stream(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+Rows = Union[torch.Tensor, Sequence[torch.Tensor]]
+
+
+def as_rows(x: Rows) -> List[torch.Tensor]:
+    """Normalise the input into a list of 1-D tensors (views, no copy)."""
+    if isinstance(x, torch.Tensor):
+        if x.dim() == 1:
+            return [x]
+        flat = x.reshape(x.shape[0], -1)
+        return [flat[i] for i in range(flat.shape[0])]
+    rows = []
+    for r in x:
+        if not isinstance(r, torch.Tensor):
+            r = torch.as_tensor(r)
+        rows.append(r.reshape(-1))
+    if not rows:
+        raise ValueError("need at least one row")
+    d = rows[0].numel()
+    for r in rows:
+        if r.numel() != d:
+            raise ValueError("all rows must have the same number of elements")
+    return rows
+
+
+def _kernel_ok(rows: List[torch.Tensor]) -> bool:
+    r0 = rows[0]
+    if not r0.is_cuda or len(rows) > MAXN:
+        return False
+    return all(r.is_cuda and r.dtype == torch.float32 and r.device == r0.device for r in rows)
+
+
+def _prep(rows: List[torch.Tensor]) -> List[torch.Tensor]:
+    return [r if r.is_contiguous() else r.contiguous() for r in rows]
+
+
+def _scales(scales, n) -> List[float]:
+    if scales is None:
+        return []
+    s = [float(v) for v in scales]
+    if len(s) != n:
+        raise ValueError("scales must have one entry per row")
+    return s
+
+
+# ----------------------------------------------------------------------------
+# coordinate-wise family
+# ----------------------------------------------------------------------------
+def cw_select(
+    rows: Rows,
+    mode: int,
+    f: int = 0,
+    *,
+    scales: Optional[Sequence[float]] = None,
+    virtual: Optional[Tuple[int, int, float, float]] = None,
+    out: Optional[torch.Tensor] = None,
+    update: Optional[dict] = None,
+) -> torch.Tensor:
+    """Coordinate-wise select over n rows.
+
+    ``virtual=(count, n_honest, a, b)`` appends ``count`` synthesised rows equal
+    to ``a*mean + b*std`` of the first ``n_honest`` rows (Little / Empire).
+    ``update=dict(params=[...], moms=[...]|None, lr=, momentum=, weight_decay=)``
+    fuses an SGD step on flat replicas into the same kernel.
+    """
+    rows = as_rows(rows)
+    n = len(rows)
+    d = rows[0].numel()
+    nv, nh, va, vb = virtual if virtual is not None else (0, 0, 0.0, 0.0)
+    nt = n + nv
+    if mode == MODE_TRMEAN and not (0 <= 2 * f < nt):
+        raise ValueError("f must satisfy 0 <= 2f < n")
+    if mode == MODE_MEAMED and not (0 <= f < nt):
+        raise ValueError("f must satisfy 0 <= f < n")
+    if _kernel_ok(rows) and nt <= MAXN:
+        ext = require_ext()
+        rows = _prep(rows)
+        dev = rows[0].device
+        if out is None:
+            out = torch.empty(d, dtype=torch.float32, device=dev)
+        params, moms, lr, mu, wd = _unpack_update(update)
+        ext.cw_select(
+            [r.data_ptr() for r in rows], _scales(scales, n), mode, int(f), int(nv), int(nh),
+            float(va), float(vb), 0, d, out.data_ptr(),
+            [p.data_ptr() for p in params], [m.data_ptr() for m in moms],
+            lr, mu, wd, sm_count(dev), _stream(dev),
+        )
+        return out
+    res = ref.cw_select(rows, mode, f, scales=scales, virtual=virtual)
+    if out is not None:
+        out.copy_(res)
+        res = out
+    if update is not None:
+        ref.sgd_step(res, **update)
+    return res
+
+
+def _unpack_update(update: Optional[dict]):
+    if not update:
+        return [], [], 0.0, 0.0, 0.0
+    params = list(update["params"])
+    moms = list(update.get("moms") or [])
+    return (params, moms, float(update.get("lr", 0.0)), float(update.get("momentum", 0.0)),
+            float(update.get("weight_decay", 0.0)))
+
+
+def cw_median(rows: Rows, **kw) -> torch.Tensor:
+    return cw_select(rows, MODE_MEDIAN, 0, **kw)
+
+
+def cw_trimmed_mean(rows: Rows, f: int, **kw) -> torch.Tensor:
+    return cw_select(rows, MODE_TRMEAN, f, **kw)
+
+
+def cw_meamed(rows: Rows, f: int, **kw) -> torch.Tensor:
+    return cw_select(rows, MODE_MEAMED, f, **kw)
+
+
+def cw_mean(rows: Rows, **kw) -> torch.Tensor:
+    return cw_select(rows, MODE_MEAN, 0, **kw)
+
+
+# ----------------------------------------------------------------------------
+# Gram family
+# ----------------------------------------------------------------------------
+_GRAM_SCRATCH: dict = {}
+
+
+def _gram_scratch(dev: torch.device, n: int) -> torch.Tensor:
+    ext = require_ext()
+    need = ext.gram_partials_needed(n, sm_count(dev))
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    buf = _GRAM_SCRATCH.get(key)
+    if buf is None or buf.numel() < need:
+        buf = torch.empty(need, dtype=torch.float32, device=dev)
+        _GRAM_SCRATCH[key] = buf
+    return buf
+
+
+def gram(rows: Rows, *, scales: Optional[Sequence[float]] = None, want64: bool = False,
+         impl: str = "auto") -> torch.Tensor:
+    """``G = (S X)(S X)^T`` as an ``(n, n)`` tensor on the rows' device.
+
+    ``impl``: ``"auto"`` | ``"fp32"`` (CUDA-core exact) | ``"umma"`` (tcgen05 3xTF32).
+    """
+    rows = as_rows(rows)
+    n = len(rows)
+    d = rows[0].numel()
+    if _kernel_ok(rows):
+        ext = require_ext()
+        rows = _prep(rows)
+        dev = rows[0].device
+        use_umma = impl == "umma" or (impl == "auto" and hasattr(ext, "gram_umma") and n > 16
+                                      and d >= 4096)
+        G = torch.empty((n, n), dtype=torch.float32, device=dev)
+        G64 = torch.empty((n, n), dtype=torch.float64, device=dev) if want64 else None
+        if use_umma:
+            from . import umma
+
+            umma.gram_umma(rows, _scales(scales, n), G, G64)
+        else:
+            scratch = _gram_scratch(dev, n)
+            ext.gram(
+                [r.data_ptr() for r in rows], _scales(scales, n), 0, d, scratch.data_ptr(),
+                scratch.numel() // (n * n), G.data_ptr(), G64.data_ptr() if want64 else 0,
+                sm_count(dev), _stream(dev),
+            )
+        return G64 if want64 else G
+    return ref.gram(rows, scales=scales, want64=want64)
+
+
+def sqdist_from_gram(G: torch.Tensor) -> torch.Tensor:
+    """Pairwise squared distances ``D_ij = G_ii + G_jj - 2 G_ij`` clamped at 0."""
+    diag = torch.diagonal(G)
+    D = diag[:, None] + diag[None, :] - 2.0 * G
+    D = torch.clamp(D, min=0.0)
+    D = torch.nan_to_num(D, nan=float("inf"))
+    D.fill_diagonal_(0.0)
+    return D
+
+
+def weighted_sum(
+    rows: Rows,
+    W: torch.Tensor,
+    *,
+    scales: Optional[Sequence[float]] = None,
+    out: Optional[torch.Tensor] = None,
+    update: Optional[dict] = None,
+) -> torch.Tensor:
+    """``Y = W (S X)`` with ``W`` an ``(m, n)`` (or ``(n,)``) weight tensor on the device.
+
+    Returns ``(m, d)`` (or ``(d,)`` for 1-D ``W``).  For ``m <= 8`` this is the
+    streaming pointer-table kernel; larger ``m`` uses one cuBLAS GEMM.
+    """
+    rows = as_rows(rows)
+    n = len(rows)
+    d = rows[0].numel()
+    squeeze = W.dim() == 1
+    W2 = W.reshape(1, -1) if squeeze else W
+    m = W2.shape[0]
+    if W2.shape[1] != n:
+        raise ValueError("W must have one column per row")
+    if _kernel_ok(rows) and m <= 8:
+        ext = require_ext()
+        rows = _prep(rows)
+        dev = rows[0].device
+        Wd = W2.to(device=dev, dtype=torch.float32).contiguous()
+        if out is None:
+            out2 = torch.empty((m, d), dtype=torch.float32, device=dev)
+        else:
+            out2 = out.reshape(m, d)
+        params, moms, lr, mu, wd = _unpack_update(update)
+        ext.wsum(
+            [r.data_ptr() for r in rows], _scales(scales, n), Wd.data_ptr(), m, 0, d,
+            [out2[r].data_ptr() for r in range(m)],
+            [p.data_ptr() for p in params], [mm.data_ptr() for mm in moms],
+            lr, mu, wd, sm_count(dev), _stream(dev),
+        )
+        return out2[0] if squeeze else out2
+    res = ref.weighted_sum(rows, W2, scales=scales)
+    if out is not None:
+        out.reshape(m, d).copy_(res)
+        res = out.reshape(m, d)
+    if update is not None:
+        ref.sgd_step(res[0], **update)
+    return res[0] if squeeze else res
+
+
+def colstat(rows: Rows, a: float, b: float, *, scales=None, out=None) -> torch.Tensor:
+    """``a*mean + b*std`` (population std) per coordinate."""
+    rows = as_rows(rows)
+    n = len(rows)
+    d = rows[0].numel()
+    if _kernel_ok(rows):
+        ext = require_ext()
+        rows = _prep(rows)
+        dev = rows[0].device
+        if out is None:
+            out = torch.empty(d, dtype=torch.float32, device=dev)
+        ext.colstat([r.data_ptr() for r in rows], _scales(scales, n), float(a), float(b), 0, d,
+                    out.data_ptr(), sm_count(dev), _stream(dev))
+        return out
+    res = ref.colstat(rows, a, b, scales=scales)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
+# ----------------------------------------------------------------------------
+# element-wise helpers
+# ----------------------------------------------------------------------------
+def scale_copy(src: torch.Tensor, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    flat = src.reshape(-1)
+    if flat.is_cuda and flat.dtype == torch.float32:
+        ext = require_ext()
+        flat = flat.contiguous()
+        if out is None:
+            out = torch.empty_like(flat)
+        ext.scale_copy(flat.data_ptr(), out.data_ptr(), float(scale), flat.numel(),
+                       sm_count(flat.device), _stream(flat.device))
+        return out.reshape(src.shape)
+    res = src * scale
+    if out is not None:
+        out.copy_(res.reshape(out.shape))
+        return out
+    return res
+
+
+def fill_(dst: torch.Tensor, value: float) -> torch.Tensor:
+    if dst.is_cuda and dst.dtype == torch.float32 and dst.is_contiguous():
+        ext = require_ext()
+        ext.fill(dst.data_ptr(), float(value), dst.numel(), sm_count(dst.device),
+                 _stream(dst.device))
+        return dst
+    return dst.fill_(value)
+
+
+def gaussian_(dst: torch.Tensor, mu: float, sigma: float, seed: int, offset: int = 0) -> torch.Tensor:
+    """Fill ``dst`` with N(mu, sigma^2) samples (Philox4x32-10 counter RNG on CUDA)."""
+    if dst.is_cuda and dst.dtype == torch.float32 and dst.is_contiguous():
+        ext = require_ext()
+        ext.gaussian(dst.data_ptr(), float(mu), float(sigma), int(seed) & (2**64 - 1),
+                     int(offset), dst.numel(), sm_count(dst.device), _stream(dst.device))
+        return dst
+    gen = torch.Generator(device="cpu")
+    gen.manual_seed(int(seed) & (2**63 - 1))
+    vals = torch.randn(dst.numel() + offset, generator=gen, dtype=torch.float32)[offset:]
+    dst.copy_((vals * sigma + mu).reshape(dst.shape).to(dst.dtype))
+    return dst
+
+
+def sgd_step(grad: torch.Tensor, params: Sequence[torch.Tensor],
+             moms: Optional[Sequence[torch.Tensor]] = None, *, lr: float, momentum: float = 0.0,
+             weight_decay: float = 0.0) -> None:
+    """Fused SGD(+momentum) over flat replicas: one kernel for all of them."""
+    params = list(params)
+    moms = list(moms) if moms else []
+    if grad.is_cuda and grad.dtype == torch.float32 and len(params) <= MAXR:
+        ext = require_ext()
+        ext.sgd(grad.data_ptr(), [p.data_ptr() for p in params], [m.data_ptr() for m in moms],
+                float(lr), float(momentum), float(weight_decay), grad.numel(),
+                sm_count(grad.device), _stream(grad.device))
+        return
+    ref.sgd_step(grad, params=params, moms=moms or None, lr=lr, momentum=momentum,
+                 weight_decay=weight_decay)
+
+
+__all__ = [
+    "MODE_MEDIAN", "MODE_TRMEAN", "MODE_MEAMED", "MODE_MEAN", "as_rows", "cw_select", "cw_median",
+    "cw_trimmed_mean", "cw_meamed", "cw_mean", "gram", "sqdist_from_gram", "weighted_sum",
+    "colstat", "scale_copy", "fill_", "gaussian_", "sgd_step", "extension_available",
+    "require_ext", "sm_count",
+]

@@ -1,0 +1,66 @@
+"""Device-side n-space solvers (single-CTA CUDA kernels in ``csrc/nspace.cu``).
+
+Each function takes the fp64 Gram matrix ON THE DEVICE and returns the weight /
+coefficient vector ON THE DEVICE without any host synchronisation, so a
+Gram-family aggregation is three back-to-back launches (gram -> solve ->
+weighted sum).  Returns ``None`` when the extension lacks the kernel, in which
+case the caller falls back to the host solver in :mod:`byzpy_b200.ops.nspace`.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _load_ext, _stream
+
+
+def _ready(G: torch.Tensor, name: str):
+    ext = _load_ext()
+    if ext is None or not hasattr(ext, name) or not G.is_cuda or G.shape[0] > 128:
+        return None
+    return ext
+
+
+def krum_weights(G: torch.Tensor, f: int, q: int) -> Optional[torch.Tensor]:
+    ext = _ready(G, "nspace_krum")
+    if ext is None:
+        return None
+    n = G.shape[0]
+    G = G.contiguous().double()
+    w = torch.empty(n, dtype=torch.float32, device=G.device)
+    ext.nspace_krum(G.data_ptr(), n, int(f), int(q), w.data_ptr(), _stream(G.device))
+    return w
+
+
+def weiszfeld_coeffs(G: torch.Tensor, n_real: int, a0: np.ndarray, *, tol: float, max_iter: int,
+                     eps: float) -> Optional[torch.Tensor]:
+    ext = _ready(G, "nspace_weiszfeld")
+    if ext is None:
+        return None
+    nt = G.shape[0]
+    G = G.contiguous().double()
+    a = torch.from_numpy(np.asarray(a0, dtype=np.float64)).to(G.device, non_blocking=True)
+    w = torch.empty(nt, dtype=torch.float32, device=G.device)
+    iters = torch.zeros(1, dtype=torch.int32, device=G.device)
+    ext.nspace_weiszfeld(G.data_ptr(), nt, int(n_real), a.data_ptr(), float(tol), int(max_iter),
+                         float(eps), w.data_ptr(), iters.data_ptr(), _stream(G.device))
+    return w
+
+
+def centered_clip_coeffs(G: torch.Tensor, n_real: int, a0: np.ndarray, *, c_tau: float, M: int,
+                         eps: float) -> Optional[torch.Tensor]:
+    ext = _ready(G, "nspace_cclip")
+    if ext is None:
+        return None
+    nt = G.shape[0]
+    G = G.contiguous().double()
+    a = torch.from_numpy(np.asarray(a0, dtype=np.float64)).to(G.device, non_blocking=True)
+    w = torch.empty(nt, dtype=torch.float32, device=G.device)
+    ext.nspace_cclip(G.data_ptr(), nt, int(n_real), a.data_ptr(), float(c_tau), int(M), float(eps),
+                     w.data_ptr(), _stream(G.device))
+    return w
+
+
+__all__ = ["krum_weights", "weiszfeld_coeffs", "centered_clip_coeffs"]

@@ -1,0 +1,377 @@
+"""B200-native parameter-server round: the CUDA runtime behind
+:class:`byzpy_b200.engine.parameter_server.ps.ParameterServer` when its nodes
+are device-resident (:class:`DeviceWorker`).
+
+One process per GPU.  A rank hosts ``L = n / world`` worker replicas; every
+replica's parameters, momentum and gradient live in flat fp32 arenas, and the
+gradient rows sit in CUDA-IPC symmetric memory so that any rank's kernel can
+read them over NVLink.  A training round is
+
+    for each local worker:  H2D batch -> fwd/bwd (PyTorch / cuDNN, bf16 autocast)
+    ONE fused kernel:       gather(P2P ld) + robust aggregate + broadcast(P2P st)
+                            + SGD(momentum) on all local replicas
+
+captured end-to-end in a CUDA graph (epoch counter lives on the device), so the
+steady state is a single ``cudaGraphLaunch`` per round per rank and there is no
+NCCL call on the path.  Semantics mirror the reference round (reference
+engine/parameter_server/ps.py:103-144): honest gradients, then Byzantine
+vectors appended after them, aggregate, apply to every
+honest node (and Byzantine ones when ``update_byzantines``).
+"""
+from __future__ import annotations
+
+import contextlib
+from dataclasses import dataclass, field
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from .. import ops
+from .arena import ParamArena, padded_size
+from .symmetric import SymmetricBuffer, _dist_on
+
+
+# --------------------------------------------------------------------------- plans
+@dataclass
+class CwPlan:
+    """Coordinate-wise aggregation plan (median / trimmed mean / meamed / mean)."""
+
+    mode: int
+    f: int = 0
+
+
+@dataclass
+class GramPlan:
+    """Gram-family plan: pass 1 Gram, n-space solve -> weights, pass 2 weighted sum."""
+
+    solver: Callable[[torch.Tensor], torch.Tensor]  # (n,n) Gram on device -> (n,) weights
+    name: str = "gram"
+
+
+@dataclass
+class RowFold:
+    """How a Byzantine row is produced without materialising it."""
+
+    kind: str  # "scale" (own gradient * scale) | "virtual" (a*mean+b*std of honest rows) | "alias"
+    scale: float = 1.0
+    a: float = 0.0
+    b: float = 0.0
+    index: int = 0
+
+
+# ------------------------------------------------------------------------- workers
+class DeviceWorker:
+    """One model replica resident on the local GPU.
+
+    ``role``: ``"honest"`` or ``"byzantine"``; a Byzantine worker with a
+    ``scale`` fold (SignFlip) still computes its own gradient (its ``base_grad``)
+    and the sign/scale is folded into the aggregation kernel's row load.
+    """
+
+    def __init__(self, model: nn.Module, loss_fn: Callable, *, role: str = "honest",
+                 fold: Optional[RowFold] = None, name: Optional[str] = None,
+                 preprocess: Optional[Callable[[torch.Tensor], torch.Tensor]] = None,
+                 data: Optional[Callable[[], Tuple[torch.Tensor, torch.Tensor]]] = None):
+        self.model = model
+        self.loss_fn = loss_fn
+        self.role = role
+        self.fold = fold
+        self.name = name or role
+        self.preprocess = preprocess
+        self.data = data
+        self.arena: Optional[ParamArena] = None
+        self.mom: Optional[torch.Tensor] = None
+        self.static_x: Optional[torch.Tensor] = None
+        self.static_y: Optional[torch.Tensor] = None
+        self.loss_slot: Optional[torch.Tensor] = None
+
+    # filled in by the engine
+    def bind(self, flat_params: torch.Tensor, flat_grads: torch.Tensor, mom: Optional[torch.Tensor],
+             loss_slot: torch.Tensor) -> None:
+        self.arena = ParamArena(self.model, flat_params=flat_params, flat_grads=flat_grads)
+        self.mom = mom
+        self.loss_slot = loss_slot
+
+    def stage_batch(self, x: torch.Tensor, y: torch.Tensor) -> None:
+        """Copy this step's inputs (typically pinned host tensors) into static device buffers."""
+        dev = self.arena.flat_params.device
+        if self.static_x is None or self.static_x.shape != x.shape or self.static_x.dtype != x.dtype:
+            self.static_x = torch.empty(x.shape, dtype=x.dtype, device=dev)
+            self.static_y = torch.empty(y.shape, dtype=y.dtype, device=dev)
+        self.static_x.copy_(x, non_blocking=True)
+        self.static_y.copy_(y, non_blocking=True)
+
+    def forward_backward(self, amp_dtype: Optional[torch.dtype]) -> None:
+        self.arena.flat_grads.zero_()
+        x = self.static_x
+        if self.preprocess is not None:
+            x = self.preprocess(x)
+        ctx = (torch.autocast("cuda", dtype=amp_dtype) if amp_dtype is not None
+               else contextlib.nullcontext())
+        with ctx:
+            out = self.model(x)
+            loss = self.loss_fn(out, self.static_y)
+        loss.backward()
+        self.loss_slot.copy_(loss.detach().float())
+
+    def state_dict_cpu(self):
+        """Checkpoint mapping, identical to the reference nodes' ``dump_state_dict``
+        (reference examples/ps/nodes.py:127-128)."""
+        return {k: v.detach().cpu() for k, v in self.model.state_dict().items()}
+
+
+# -------------------------------------------------------------------------- layout
+@dataclass
+class RowLayout:
+    """Global row order of a round: honest workers first, then Byzantine ones."""
+
+    n_honest: int
+    n_byz_workers: int          # Byzantine rows backed by a worker replica (scale folds)
+    n_virtual: int = 0          # synthesised Byzantine rows (Little / Empire)
+    world: int = 1
+    rank_of: List[int] = field(default_factory=list)
+    slot_of: List[int] = field(default_factory=list)
+
+    @property
+    def n_workers(self) -> int:
+        return self.n_honest + self.n_byz_workers
+
+    @classmethod
+    def block(cls, n_honest: int, n_byz_workers: int, world: int, n_virtual: int = 0) -> "RowLayout":
+        n = n_honest + n_byz_workers
+        if n % world != 0:
+            raise ValueError(f"{n} workers do not divide evenly over {world} ranks")
+        per = n // world
+        return cls(n_honest, n_byz_workers, n_virtual, world,
+                   [g // per for g in range(n)], [g % per for g in range(n)])
+
+    def local_ids(self, rank: int) -> List[int]:
+        return [g for g in range(self.n_workers) if self.rank_of[g] == rank]
+
+
+# -------------------------------------------------------------------------- engine
+class DeviceRound:
+    """Owns the symmetric arenas and launches the fused round on this rank."""
+
+    def __init__(self, workers: Sequence[DeviceWorker], layout: RowLayout, plan, *,
+                 lr: float, momentum: float = 0.0, weight_decay: float = 0.0,
+                 update_byzantines: bool = False, device: Optional[torch.device] = None,
+                 group=None, amp_dtype: Optional[torch.dtype] = torch.bfloat16,
+                 use_cuda_graph: bool = True, worker_streams: int = 1,
+                 virtual_fold: Optional[RowFold] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("DeviceRound needs a CUDA device (B200)")
+        self.ext = ops.require_ext()
+        self.workers = list(workers)
+        self.layout = layout
+        self.plan = plan
+        self.lr, self.momentum, self.weight_decay = float(lr), float(momentum), float(weight_decay)
+        self.update_byzantines = update_byzantines
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.group = group
+        self.amp_dtype = amp_dtype
+        self.use_cuda_graph = use_cuda_graph
+        self.virtual_fold = virtual_fold
+        self.rank = dist.get_rank(group) if _dist_on() else 0
+        self.world = dist.get_world_size(group) if _dist_on() else 1
+        if layout.world != self.world:
+            raise ValueError("layout.world does not match the process group")
+        self.local_ids = layout.local_ids(self.rank)
+        if len(self.local_ids) != len(self.workers):
+            raise ValueError(f"rank {self.rank} hosts {len(self.local_ids)} rows but got "
+                             f"{len(self.workers)} workers")
+        L = len(self.workers)
+        self.L = L
+        d = sum(p.numel() for p in self.workers[0].model.parameters())
+        self.d = d
+        # shards must be multiples of 4 elements on every rank
+        self.d_pad = padded_size(d, 1024)
+        self.sm = ops.sm_count(self.device)
+
+        # --- symmetric region: [grads L*d_pad | agg d_pad | pad words | counter,status,epoch]
+        f4 = 4
+        self._off_grads = 0
+        self._off_agg = L * self.d_pad * f4
+        self._off_pad = self._off_agg + self.d_pad * f4
+        self._off_ctl = self._off_pad + 256
+        nbytes = self._off_ctl + 256
+        self.sym = SymmetricBuffer(nbytes, self.device, group)
+        self.grads = self.sym.view(torch.float32, L * self.d_pad, self._off_grads).view(L, self.d_pad)
+        self.agg = self.sym.view(torch.float32, self.d_pad, self._off_agg)
+        self.pad = self.sym.view(torch.int32, 64, self._off_pad)
+        self.ctl = self.sym.view(torch.int32, 64, self._off_ctl)  # [0]=counter [1]=status [2]=epoch
+        # local (non-symmetric) replica state
+        self.params = torch.zeros((L, self.d_pad), dtype=torch.float32, device=self.device)
+        self.moms = (torch.zeros((L, self.d_pad), dtype=torch.float32, device=self.device)
+                     if self.momentum != 0.0 else None)
+        self.losses = torch.zeros(L, dtype=torch.float32, device=self.device)
+        self.losses_host = torch.zeros(L, dtype=torch.float32).pin_memory()
+        for i, w in enumerate(self.workers):
+            w.model.to(self.device)
+            w.bind(self.params[i], self.grads[i], None if self.moms is None else self.moms[i],
+                   self.losses[i])
+        self._rows, self._scales = self._row_table()
+        self._upd_params, self._upd_moms = self._update_table()
+        sh = self.d_pad // self.world
+        sh -= sh % 4
+        self.shard_off = self.rank * sh
+        self.shard_len = sh if self.rank < self.world - 1 else self.d_pad - sh * (self.world - 1)
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._side_streams = [torch.cuda.Stream(self.device) for _ in range(max(0, worker_streams - 1))]
+        self._gram_ws = None
+        self.launches_per_step = 0
+        if self.world > 1:
+            dist.barrier(group=group)
+        torch.cuda.synchronize(self.device)
+
+    # ------------------------------------------------------------------ tables
+    def _row_table(self) -> Tuple[List[int], List[float]]:
+        lay = self.layout
+        rows, scales = [], []
+        for g in range(lay.n_workers):
+            r, s = lay.rank_of[g], lay.slot_of[g]
+            rows.append(self.sym.peer_ptr(r, self._off_grads + s * self.d_pad * 4))
+            scales.append(1.0)
+        # folds of Byzantine workers hosted anywhere: every rank derives the same scale
+        # from the (replicated) fold description of its local workers; remote ones are exchanged.
+        local = {g: (w.fold.scale if (w.fold is not None and w.fold.kind == "scale") else 1.0)
+                 for g, w in zip(self.local_ids, self.workers)}
+        if self.world > 1:
+            allf: List[Optional[dict]] = [None] * self.world
+            dist.all_gather_object(allf, local, group=self.group)
+            for part in allf:
+                for g, sc in part.items():
+                    scales[g] = sc
+        else:
+            for g, sc in local.items():
+                scales[g] = sc
+        return rows, scales
+
+    def _update_table(self) -> Tuple[List[int], List[int]]:
+        ps, ms = [], []
+        for i, w in enumerate(self.workers):
+            if w.role == "honest" or self.update_byzantines:
+                ps.append(self.params[i].data_ptr())
+                if self.moms is not None:
+                    ms.append(self.moms[i].data_ptr())
+        return ps, ms
+
+    # ------------------------------------------------------------------- launch
+    def _virtual(self) -> Tuple[int, int, float, float]:
+        lay = self.layout
+        if lay.n_virtual and self.virtual_fold is not None:
+            return lay.n_virtual, lay.n_honest, self.virtual_fold.a, self.virtual_fold.b
+        return 0, 0, 0.0, 0.0
+
+    def launch_aggregate(self) -> None:
+        """Enqueue the fused gather+aggregate+broadcast+update on the current stream."""
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        ctl = self.ctl.data_ptr()
+        self.ext.bump_u32(ctl + 8, stream)
+        plan = self.plan
+        nv, nh, va, vb = self._virtual()
+        if isinstance(plan, CwPlan):
+            self.ext.fused_ps_cw(
+                self._rows, self._scales, plan.mode, plan.f, nv, nh, va, vb, self.d_pad,
+                self.shard_off, self.shard_len, self.rank,
+                [self.sym.peer_ptr(r, self._off_agg) for r in range(self.world)],
+                [self.sym.peer_ptr(r, self._off_pad) for r in range(self.world)],
+                0, ctl + 8, ctl + 0, ctl + 4,
+                self._upd_params, self._upd_moms, self.lr, self.momentum, self.weight_decay,
+                self.sm, stream,
+            )
+            self.launches_per_step = 2
+        elif isinstance(plan, GramPlan):
+            if self.world != 1:
+                raise NotImplementedError("Gram-family fused round is single-rank in this build")
+            rows = [self.grads[i] for i in range(self.L)]
+            G = ops.gram(rows, scales=self._scales)
+            w = plan.solver(G)
+            ops.weighted_sum(rows, w.reshape(1, -1), scales=self._scales, out=self.agg.view(1, -1),
+                             update=dict(params=[self.params[i] for i in self._upd_index()],
+                                         moms=None if self.moms is None else
+                                         [self.moms[i] for i in self._upd_index()],
+                                         lr=self.lr, momentum=self.momentum,
+                                         weight_decay=self.weight_decay))
+            self.launches_per_step = 4
+        else:
+            raise TypeError(f"unsupported plan {plan!r}")
+
+    def _upd_index(self) -> List[int]:
+        return [i for i, w in enumerate(self.workers) if w.role == "honest" or self.update_byzantines]
+
+    def _body(self) -> None:
+        main = torch.cuda.current_stream(self.device)
+        if self._side_streams:
+            streams = [main] + self._side_streams
+            for s in self._side_streams:
+                s.wait_stream(main)
+            for i, w in enumerate(self.workers):
+                with torch.cuda.stream(streams[i % len(streams)]):
+                    w.forward_backward(self.amp_dtype)
+            for s in self._side_streams:
+                main.wait_stream(s)
+        else:
+            for w in self.workers:
+                w.forward_backward(self.amp_dtype)
+        self.launch_aggregate()
+
+    def capture(self, warmup: int = 2) -> None:
+        """Warm up eagerly on a side stream, then capture the whole round in a CUDA graph."""
+        for w in self.workers:
+            if w.static_x is None:
+                raise RuntimeError("stage a batch on every worker before capture()")
+        s = torch.cuda.Stream(self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._body()
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._body()
+        self._graph = g
+
+    # --------------------------------------------------------------------- step
+    def step(self, batches: Optional[Sequence[Tuple[torch.Tensor, torch.Tensor]]] = None) -> torch.Tensor:
+        """One training round.  ``batches[i]`` = this step's (x, y) for local worker i
+        (pinned host tensors are copied H2D asynchronously).  Returns the device
+        tensor of per-worker losses."""
+        if batches is None:
+            batches = [w.data() for w in self.workers]
+        for w, (x, y) in zip(self.workers, batches):
+            w.stage_batch(x, y)
+        if self.use_cuda_graph:
+            if self._graph is None:
+                self.capture()
+            self._graph.replay()
+        else:
+            self._body()
+        return self.losses
+
+    def read_losses(self) -> torch.Tensor:
+        """Device->host read of the round's losses (synchronises the stream)."""
+        self.losses_host.copy_(self.losses, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self.losses_host
+
+    def check_status(self) -> None:
+        st = int(self.ctl[1].item())
+        if st != 0:
+            raise RuntimeError(f"fused PS kernel reported error {st} (1=gradient-ready timeout, "
+                               f"2=delivery timeout)")
+
+    def aggregated(self) -> torch.Tensor:
+        return self.agg[: self.d]
+
+    def close(self) -> None:
+        self._graph = None
+        self.sym.close()
+
+
+__all__ = ["CwPlan", "GramPlan", "RowFold", "DeviceWorker", "RowLayout", "DeviceRound"]
