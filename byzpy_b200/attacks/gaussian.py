@@ -1,0 +1,47 @@
+"""Gaussian attack: an i.i.d. N(mu, sigma^2) vector shaped like a gradient, re-seeded every call
+so a fixed ``seed`` reproduces the same vector (reference attacks/gaussian.py:38-139).
+
+CPU inputs use ``numpy.random.default_rng(seed)`` exactly like the reference (bit-identical);
+CUDA inputs are sampled on the device with a Philox4x32-10 kernel (statistically equivalent,
+SURVEY K18)."""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .. import ops
+from ..aggregators.base import finish, prepare_rows
+from .base import Attack
+
+
+class GaussianAttack(Attack):
+    name = "gaussian"
+    uses_honest_grads = True
+    supports_subtasks = False
+
+    def __init__(self, mu: float = 0.0, sigma: float = 1.0, *, seed: Optional[int] = None,
+                 chunk_size: int = 8192) -> None:
+        if sigma < 0:
+            raise ValueError("sigma must be >= 0")
+        if chunk_size <= 0:
+            raise ValueError("chunk_size must be > 0")
+        self.mu, self.sigma, self.seed = float(mu), float(sigma), seed
+        self.chunk_size = int(chunk_size)
+
+    def apply(self, *, model=None, x=None, y=None, honest_grads=None, base_grad=None):
+        if not honest_grads:
+            raise ValueError("GaussianAttack requires honest_grads.")
+        rows, like = prepare_rows([honest_grads[0]], "honest_grads")
+        d = rows[0].numel()
+        if like.is_cuda:
+            seed = self.seed if self.seed is not None else int(np.random.SeedSequence().entropy % (2 ** 63))
+            out = torch.empty(d, dtype=torch.float32, device=like.device)
+            ops.gaussian_(out, self.mu, self.sigma, seed)
+            return finish(out, like)
+        sample = np.random.default_rng(self.seed).normal(loc=self.mu, scale=self.sigma, size=d)
+        return finish(torch.from_numpy(sample), like)
+
+
+__all__ = ["GaussianAttack"]

@@ -161,7 +161,8 @@ int dispatch_mode(const BzFusedPsArgs& a, int sm_count, cudaStream_t stream, boo
   const int nt = a.n + a.virt.count;
 #define BZ_CASE(NP)                                                   \
   if (nt <= NP) {                                                     \
-    const int g = max_grid_np<NP, MODE>(sm_count);                    \
+    int g = max_grid_np<NP, MODE>(sm_count);                          \
+    if (a.grid_limit > 0 && a.grid_limit < g) g = a.grid_limit;       \
     if (query) return g;                                              \
     return launch_np<NP, MODE>(a, g, stream);                         \
   }

@@ -25,6 +25,7 @@ struct BzFusedPsArgs {
   unsigned int* counter;    // local CTA arrival counter (zero-initialised)
   int* status;              // local error word (0 == ok)
   UpdTable upd;             // local replicas to update in phase 2
+  int grid_limit;           // 0 = one full co-resident wave; >0 caps the CTA count
 };
 
 int bz_fused_ps_cw(const BzFusedPsArgs* args, int sm_count, cudaStream_t stream);

@@ -110,7 +110,7 @@ void bz_bind_runtime(py::module_& m) {
          long long shard_len, int rank, const std::vector<uint64_t>& agg,
          const std::vector<uint64_t>& pads, uint32_t epoch, uint64_t epoch_ptr, uint64_t counter, uint64_t status,
          const std::vector<uint64_t>& upd_params, const std::vector<uint64_t>& upd_moms, float lr,
-         float mu, float wd, int sm_count, uint64_t stream) {
+         float mu, float wd, int sm_count, uint64_t stream, int grid_limit) {
         BzFusedPsArgs a;
         std::memset(&a, 0, sizeof(a));
         if (rows.empty() || rows.size() > BZ_MAXN) throw std::invalid_argument("rows");
@@ -149,6 +149,7 @@ void bz_bind_runtime(py::module_& m) {
         a.upd.lr = lr;
         a.upd.mu = mu;
         a.upd.wd = wd;
+        a.grid_limit = grid_limit;
         int e = bz_fused_ps_cw(&a, sm_count, as_stream(stream));
         if (e != 0)
           throw std::runtime_error(std::string("fused_ps_cw: CUDA error ") +
@@ -158,5 +159,6 @@ void bz_bind_runtime(py::module_& m) {
       py::arg("n_honest"), py::arg("va"), py::arg("vb"), py::arg("d"), py::arg("shard_off"),
       py::arg("shard_len"), py::arg("rank"), py::arg("agg"), py::arg("pads"), py::arg("epoch"), py::arg("epoch_ptr"),
       py::arg("counter"), py::arg("status"), py::arg("upd_params"), py::arg("upd_moms"),
-      py::arg("lr"), py::arg("mu"), py::arg("wd"), py::arg("sm_count"), py::arg("stream"));
+      py::arg("lr"), py::arg("mu"), py::arg("wd"), py::arg("sm_count"), py::arg("stream"),
+      py::arg("grid_limit") = 0);
 }

@@ -1,0 +1,136 @@
+"""Device-resident nodes: the ``"gpu"`` actor backend of this framework is a CUDA runtime.
+
+A ``DeviceHonestNode`` / ``DeviceByzantineNode`` satisfies the ordinary node contract
+(``next_batch`` / ``honest_gradient`` / ``apply_server_gradient``), so it works with the generic
+actor-based :class:`ParameterServer` path, and additionally exposes a :class:`DeviceWorker` so
+that a ``ParameterServer`` made only of device nodes runs its round as ONE fused kernel over
+flat arenas (see :mod:`byzpy_b200.parallel.device_ps`).
+
+Reference analogue: the example node classes (reference examples/ps/nodes.py:64-161) hosted on
+``GPUActorBackend`` (reference engine/actor/backends/gpu.py:23-200), which contains no CUDA code.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from ...attacks.base import Attack
+from ...parallel.arena import flatten_grads, write_vector_to_grads_
+from ...parallel.device_ps import DeviceWorker, RowFold
+from .base import ByzantineNode, HonestNode
+
+BatchSource = Callable[[], Tuple[torch.Tensor, torch.Tensor]]
+
+
+class DeviceHonestNode(HonestNode):
+    def __init__(self, model: nn.Module, loss_fn: Optional[Callable] = None, *,
+                 data: Optional[BatchSource] = None, lr: float = 0.05, momentum: float = 0.9,
+                 weight_decay: float = 0.0, device: Optional[str] = None,
+                 preprocess: Optional[Callable] = None, name: str = "honest"):
+        self.device = torch.device(device or ("cuda" if torch.cuda.is_available() else "cpu"))
+        self.model = model.to(self.device)
+        self.loss_fn = loss_fn or nn.CrossEntropyLoss()
+        self.data = data
+        self.lr, self.momentum, self.weight_decay = lr, momentum, weight_decay
+        self.preprocess = preprocess
+        self.name = name
+        self._opt: Optional[torch.optim.Optimizer] = None
+        self.worker = DeviceWorker(self.model, self.loss_fn, role="honest", name=name,
+                                   preprocess=preprocess, data=data)
+
+    # ---- generic node contract (used by the actor-based round) ----------------------------
+    def next_batch(self):
+        if self.data is None:
+            raise RuntimeError("DeviceHonestNode has no data source")
+        x, y = self.data()
+        return x.to(self.device, non_blocking=True), y.to(self.device, non_blocking=True)
+
+    def honest_gradient(self, x, y):
+        self.model.zero_grad(set_to_none=False)
+        xin = self.preprocess(x) if self.preprocess is not None else x
+        loss = self.loss_fn(self.model(xin), y)
+        loss.backward()
+        return flatten_grads(self.model)
+
+    def apply_server_gradient(self, grad_vec):
+        if self._opt is None:
+            self._opt = torch.optim.SGD(self.model.parameters(), lr=self.lr, momentum=self.momentum,
+                                        weight_decay=self.weight_decay)
+        write_vector_to_grads_(self.model, grad_vec.to(self.device))
+        self._opt.step()
+
+    def dump_state_dict(self):
+        return {k: v.detach().cpu() for k, v in self.model.state_dict().items()}
+
+
+class DeviceByzantineNode(ByzantineNode):
+    """Byzantine node driven by an :class:`Attack`.
+
+    Attacks that need the node's own gradient (``uses_base_grad``, e.g. SignFlip) require a
+    ``model`` + ``data``; omniscient attacks (Little, Empire, Mimic) need neither and become
+    virtual/alias rows of the fused kernel.
+    """
+
+    def __init__(self, attack: Attack, *, model: Optional[nn.Module] = None,
+                 loss_fn: Optional[Callable] = None, data: Optional[BatchSource] = None,
+                 lr: float = 0.05, momentum: float = 0.9, weight_decay: float = 0.0,
+                 device: Optional[str] = None, preprocess: Optional[Callable] = None,
+                 name: str = "byzantine"):
+        self.attack = attack
+        self.device = torch.device(device or ("cuda" if torch.cuda.is_available() else "cpu"))
+        self.model = model.to(self.device) if model is not None else None
+        self.loss_fn = loss_fn or nn.CrossEntropyLoss()
+        self.data = data
+        self.lr, self.momentum, self.weight_decay = lr, momentum, weight_decay
+        self.preprocess = preprocess
+        self.name = name
+        self._opt = None
+        self.worker: Optional[DeviceWorker] = None
+        if attack.uses_base_grad or attack.uses_model_batch:
+            if model is None:
+                raise ValueError(f"{type(attack).__name__} needs the node's own model/batch")
+            self.worker = DeviceWorker(self.model, self.loss_fn, role="byzantine", name=name,
+                                       preprocess=preprocess, data=data)
+
+    def fold(self, n_honest: int) -> Optional[RowFold]:
+        return self.attack.fold(n_honest)
+
+    def next_batch(self):
+        if self.data is None:
+            return torch.empty(0), torch.empty(0, dtype=torch.long)
+        x, y = self.data()
+        return x.to(self.device, non_blocking=True), y.to(self.device, non_blocking=True)
+
+    def _own_gradient(self, x, y):
+        self.model.zero_grad(set_to_none=False)
+        xin = self.preprocess(x) if self.preprocess is not None else x
+        self.loss_fn(self.model(xin), y).backward()
+        return flatten_grads(self.model)
+
+    def byzantine_gradient(self, x, y, honest_grads=None):
+        kw = {}
+        if self.attack.uses_model_batch:
+            if x.numel() == 0:
+                x, y = self.next_batch()
+            kw.update(model=self.model, x=self.preprocess(x) if self.preprocess else x, y=y)
+        if self.attack.uses_base_grad:
+            if x.numel() == 0:
+                x, y = self.next_batch()
+            kw["base_grad"] = self._own_gradient(x, y)
+        if self.attack.uses_honest_grads:
+            kw["honest_grads"] = list(honest_grads or [])
+        return self.attack.apply(**kw)
+
+    def apply_server_gradient(self, grad_vec):
+        if self.model is None:
+            return
+        if self._opt is None:
+            self._opt = torch.optim.SGD(self.model.parameters(), lr=self.lr, momentum=self.momentum,
+                                        weight_decay=self.weight_decay)
+        write_vector_to_grads_(self.model, grad_vec.to(self.device))
+        self._opt.step()
+
+
+__all__ = ["DeviceHonestNode", "DeviceByzantineNode"]

@@ -1,0 +1,187 @@
+"""Synchronous Byzantine-robust parameter server.
+
+Same constructor and ``round()/shutdown()`` contract as the reference
+(reference engine/parameter_server/ps.py:18-158): collect honest gradients, let every
+Byzantine node see them and emit its vector (appended after the honest ones), optional
+pre-aggregation, robust aggregation, fan the aggregate out to the honest nodes (and the
+Byzantine ones if ``update_byzantines``).
+
+Two execution paths:
+
+* **device path** -- when every node is a device node (``DeviceHonestNode`` /
+  ``DeviceByzantineNode``) on CUDA and the aggregator has a fused plan, the whole round is
+  :class:`byzpy_b200.parallel.device_ps.DeviceRound`: fwd/bwd per replica, then ONE fused
+  sm_100a kernel doing gather (P2P loads over NVLink) + aggregation + broadcast + SGD, replayed
+  as a CUDA graph.  Multi-GPU: one process per GPU, each constructs a ParameterServer over its
+  LOCAL nodes and passes ``layout=RowLayout.block(...)``; ``round()`` is then collective.
+* **generic path** -- arbitrary node actors (thread / process / tcp backends): gradients are
+  gathered through actor RPCs like the reference, in *submission* order (deterministic row
+  order; the reference uses completion order).  Aggregators accept
+  tensors and shm handles alike, so -- unlike the reference at this commit --
+  every aggregator works here, with or without an ``actor_pool``.
+"""
+from __future__ import annotations
+
+import asyncio
+import inspect
+from typing import Any, List, Optional, Sequence
+
+import torch
+
+from ...aggregators.base import Aggregator
+from ...pre_aggregators.base import PreAggregator
+
+
+async def _call(obj: Any, method: str, *args, **kwargs) -> Any:
+    res = getattr(obj, method)(*args, **kwargs)
+    if inspect.isawaitable(res):
+        res = await res
+    return res
+
+
+def _is_device_node(node: Any) -> bool:
+    try:
+        from ..node.device import DeviceByzantineNode, DeviceHonestNode
+    except Exception:  # pragma: no cover
+        return False
+    return isinstance(node, (DeviceHonestNode, DeviceByzantineNode))
+
+
+class ParameterServer:
+    def __init__(self, honest_nodes: List[Any], byzantine_nodes: List[Any], aggregator: Aggregator,
+                 pre_aggregator: Optional[PreAggregator] = None, update_byzantines: bool = False, *,
+                 actor_pool=None, scheduler_metadata: Optional[dict] = None, layout=None,
+                 process_group=None, lr: Optional[float] = None, momentum: Optional[float] = None,
+                 weight_decay: Optional[float] = None, amp_dtype: Optional[torch.dtype] = torch.bfloat16,
+                 use_cuda_graph: bool = True, worker_streams: int = 1, fused: Optional[bool] = None):
+        self.hon = list(honest_nodes)
+        self.byz = list(byzantine_nodes)
+        self.agg = aggregator
+        self.pre = pre_aggregator
+        self.update_byz = update_byzantines
+        self.pool = actor_pool
+        self.scheduler = None
+        self.rounds = 0
+        if actor_pool is not None:
+            from ..graph.ops import make_single_operator_graph
+            from ..graph.scheduler import NodeScheduler
+
+            graph = make_single_operator_graph(node_name="agg", operator=self.agg,
+                                               input_keys=("gradients",))
+            self.scheduler = NodeScheduler(graph, pool=actor_pool, metadata=scheduler_metadata)
+        self.device_round = None
+        want_fused = fused if fused is not None else True
+        if want_fused and actor_pool is None:
+            self.device_round = self._try_build_device_round(
+                layout, process_group, lr, momentum, weight_decay, amp_dtype, use_cuda_graph,
+                worker_streams)
+        if fused and self.device_round is None:
+            raise RuntimeError("fused=True requested but the configuration has no fused device path")
+
+    # ------------------------------------------------------------------ device path
+    def _try_build_device_round(self, layout, group, lr, momentum, weight_decay, amp_dtype,
+                                use_cuda_graph, worker_streams):
+        nodes = self.hon + self.byz
+        if not nodes or not all(_is_device_node(n) for n in nodes):
+            return None
+        if not torch.cuda.is_available() or any(n.device.type != "cuda" for n in nodes):
+            return None
+        if self.pre is not None:
+            return None  # pre-aggregated rounds use the generic path in this build
+        from ...parallel.device_ps import DeviceRound, RowFold, RowLayout
+
+        import torch.distributed as dist
+
+        world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        workers = [n.worker for n in self.hon]
+        virtual_fold = None
+        n_virtual_local = 0
+        for b in self.byz:
+            fold = b.fold(0)
+            if b.worker is not None:
+                if fold is None or fold.kind != "scale":
+                    return None
+                b.worker.fold = fold
+                workers.append(b.worker)
+            else:
+                if fold is None or fold.kind != "virtual":
+                    return None
+                n_virtual_local += 1
+        if layout is None:
+            if world != 1:
+                raise ValueError("multi-rank ParameterServer needs an explicit layout=RowLayout...")
+            layout = RowLayout.block(len(self.hon), len(workers) - len(self.hon), 1, n_virtual_local)
+        if layout.n_virtual:
+            virt = [b for b in self.byz if b.worker is None]
+            if not virt:
+                return None
+            f0 = virt[0].attack.fold(layout.n_honest)
+            virtual_fold = RowFold("virtual", a=f0.a, b=f0.b)
+        n_rows = layout.n_workers + layout.n_virtual
+        plan = self.agg.fused_plan(n_rows)
+        if plan is None:
+            return None
+        first = self.hon[0] if self.hon else self.byz[0]
+        return DeviceRound(
+            workers, layout, plan,
+            lr=first.lr if lr is None else lr,
+            momentum=first.momentum if momentum is None else momentum,
+            weight_decay=first.weight_decay if weight_decay is None else weight_decay,
+            update_byzantines=self.update_byz, device=first.device, group=group,
+            amp_dtype=amp_dtype, use_cuda_graph=use_cuda_graph, worker_streams=worker_streams,
+            virtual_fold=virtual_fold)
+
+    def step(self, batches=None) -> torch.Tensor:
+        """Device path: one fused round, asynchronous on the current CUDA stream.
+        Returns the device tensor of local per-worker losses."""
+        if self.device_round is None:
+            raise RuntimeError("step() is only available on the fused device path; use round()")
+        self.rounds += 1
+        return self.device_round.step(batches)
+
+    # ------------------------------------------------------------------- generic path
+    async def _gather_honest(self) -> List[torch.Tensor]:
+        return list(await asyncio.gather(
+            *[_call(h, "honest_gradient_for_next_batch") for h in self.hon]))
+
+    async def _gather_byzantine(self, honest: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+        if not self.byz:
+            return []
+        return list(await asyncio.gather(
+            *[_call(b, "byzantine_gradient_for_next_batch", honest) for b in self.byz]))
+
+    async def round(self) -> torch.Tensor:
+        if self.device_round is not None:
+            self.step()
+            return self.device_round.aggregated()
+        grads = await self._gather_honest()
+        grads += await self._gather_byzantine(tuple(grads))
+        if self.pre is not None:
+            grads = list(self.pre.pre_aggregate(grads))
+        if self.scheduler is not None:
+            g = (await self.scheduler.run({"gradients": grads}))["agg"]
+        else:
+            g = self.agg.aggregate(grads)
+        targets = self.hon + (self.byz if self.update_byz else [])
+        await asyncio.gather(*[_call(n, "apply_server_gradient", g) for n in targets])
+        self.rounds += 1
+        return g
+
+    def round_sync(self) -> torch.Tensor:
+        return asyncio.run(self.round())
+
+    async def shutdown(self) -> None:
+        if self.device_round is not None:
+            self.device_round.close()
+            self.device_round = None
+        closers = []
+        for n in self.hon + self.byz:
+            ref = getattr(n, "_ref", None)
+            backend = getattr(ref, "_backend", None)
+            if backend is not None:
+                closers.append(backend.close())
+        if closers:
+            await asyncio.gather(*closers)
+
+
+__all__ = ["ParameterServer"]

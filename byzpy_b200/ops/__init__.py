@@ -272,7 +272,7 @@ def weighted_sum(
     m = W2.shape[0]
     if W2.shape[1] != n:
         raise ValueError("W must have one column per row")
-    if _kernel_ok(rows) and m <= 8:
+    if _kernel_ok(rows):
         ext = require_ext()
         rows = _prep(rows)
         dev = rows[0].device
@@ -282,12 +282,19 @@ def weighted_sum(
         else:
             out2 = out.reshape(m, d)
         params, moms, lr, mu, wd = _unpack_update(update)
-        ext.wsum(
-            [r.data_ptr() for r in rows], _scales(scales, n), Wd.data_ptr(), m, 0, d,
-            [out2[r].data_ptr() for r in range(m)],
-            [p.data_ptr() for p in params], [mm.data_ptr() for mm in moms],
-            lr, mu, wd, sm_count(dev), _stream(dev),
-        )
+        ptrs = [r.data_ptr() for r in rows]
+        sc = _scales(scales, n)
+        # the streaming kernel emits up to 8 output rows per pass over the inputs
+        for r0 in range(0, m, 8):
+            mb = min(8, m - r0)
+            first = r0 == 0
+            ext.wsum(
+                ptrs, sc, Wd[r0:r0 + mb].data_ptr(), mb, 0, d,
+                [out2[r0 + r].data_ptr() for r in range(mb)],
+                [p.data_ptr() for p in params] if first else [],
+                [mm.data_ptr() for mm in moms] if first else [],
+                lr, mu, wd, sm_count(dev), _stream(dev),
+            )
         return out2[0] if squeeze else out2
     res = ref.weighted_sum(rows, W2, scales=scales)
     if out is not None:

@@ -1,0 +1,104 @@
+"""Pre-aggregator base (reference pre_aggregators/base.py:9-96): ``Sequence[vec] -> List[vec]``.
+
+Every pre-aggregator in this library is a *linear row map* ``X' = W X`` whose matrix ``W``
+(m x n) depends only on the Gram matrix of the inputs (norms, pairwise distances) or on nothing
+at all (bucketing).  ``row_map`` exposes ``W`` so that a following Gram-family aggregator can be
+composed in n-space -- ``G' = W G W^T``, final weights ``w_agg @ W`` -- and the pre-aggregated
+vectors are never materialised.  ``pre_aggregate`` materialises them for API parity.
+"""
+from __future__ import annotations
+
+from abc import ABC, abstractmethod
+from typing import Any, List, Mapping, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .. import ops
+from ..aggregators._chunking import select_adaptive_chunk_size
+from ..aggregators.base import (_Packed, _gram_chunk, _hold_packed, _kernel_rows, _release_packed,
+                                feature_chunks, finish, pool_size_of, prepare_rows)
+from ..engine.graph.operator import OpContext, Operator
+from ..engine.graph.subtask import SubTask
+
+
+class PreAggregator(Operator, ABC):
+    name = "pre-aggregator"
+    input_key = "vectors"
+
+    def compute(self, inputs: Mapping[str, Any], *, context: OpContext) -> Any:
+        if self.input_key not in inputs:
+            raise KeyError(f"{self.name} expects input key {self.input_key!r}")
+        xs = inputs[self.input_key]
+        if not isinstance(xs, Sequence):
+            raise TypeError(f"{self.name} expects a sequence at {self.input_key!r}")
+        return self.pre_aggregate(xs)
+
+    @abstractmethod
+    def pre_aggregate(self, xs: Sequence[Any]) -> List[Any]:
+        ...
+
+
+class LinearPreAggregator(PreAggregator):
+    """Pre-aggregators expressible as ``X' = W X``."""
+
+    supports_subtasks = True
+    max_subtasks_inflight = 0
+    needs_gram: bool = True
+    feature_chunk_size: int = 8192
+
+    def _validate(self, n: int) -> None:
+        pass
+
+    @abstractmethod
+    def row_map(self, G: Optional[np.ndarray], n: int) -> np.ndarray:
+        """(m, n) mixing matrix from the fp64 Gram matrix (``G`` is None when ``needs_gram`` is False)."""
+
+    def _materialise(self, rows: List[torch.Tensor], W: np.ndarray, like: torch.Tensor) -> List[torch.Tensor]:
+        krows = _kernel_rows(rows)
+        Wt = torch.from_numpy(np.asarray(W, dtype=np.float32)).to(rows[0].device)
+        if W.shape[0] == W.shape[1] and np.count_nonzero(W - np.diag(np.diagonal(W))) == 0:
+            # diagonal map (clipping): n independent scaled copies
+            diag = np.diagonal(W)
+            return [finish(ops.scale_copy(krows[i], float(diag[i])), like) for i in range(len(rows))]
+        Y = ops.weighted_sum(krows, Wt)
+        return [finish(Y[i], like) for i in range(Y.shape[0])]
+
+    def pre_aggregate(self, xs: Sequence[Any]) -> List[Any]:
+        rows, like = prepare_rows(xs, "xs")
+        n = len(rows)
+        self._validate(n)
+        G = None
+        if self.needs_gram:
+            G = ops.gram(_kernel_rows(rows), want64=True).detach().cpu().numpy()
+        return self._materialise(rows, self.row_map(G, n), like)
+
+    # -- subtask path: split-K Gram over feature chunks, then one local materialisation ----
+    def create_subtasks(self, inputs, *, context):
+        xs = inputs.get(self.input_key)
+        if not isinstance(xs, Sequence) or not xs or not self.needs_gram:
+            return []
+        rows, _ = prepare_rows(xs, "xs")
+        self._validate(len(rows))
+        d = rows[0].numel()
+        chunk = select_adaptive_chunk_size(d, self.feature_chunk_size, pool_size=pool_size_of(context))
+        packed = _Packed.pack(_kernel_rows(rows))
+        _hold_packed(self, inputs, packed)
+        return [SubTask(fn=_gram_chunk, args=(packed, s, e), name=f"{self.name}_gram_{k}")
+                for k, (s, e) in enumerate(feature_chunks(d, chunk))]
+
+    def reduce_subtasks(self, partials, inputs, *, context):
+        try:
+            if not partials:
+                return self.compute(inputs, context=context)
+            rows, like = prepare_rows(inputs[self.input_key], "xs")
+            n = len(rows)
+            G = np.zeros((n, n), dtype=np.float64)
+            for p in partials:
+                G += np.asarray(p, dtype=np.float64)
+            return self._materialise(rows, self.row_map(G, n), like)
+        finally:
+            _release_packed(self, inputs)
+
+
+__all__ = ["PreAggregator", "LinearPreAggregator"]

@@ -1,0 +1,26 @@
+"""Static norm clipping: ``x_i <- x_i * min(1, tau / max(||x_i||, 1e-12))``
+(reference pre_aggregators/clipping.py:35-130)."""
+from __future__ import annotations
+
+import numpy as np
+
+from ..ops import nspace
+from .base import LinearPreAggregator
+
+
+class Clipping(LinearPreAggregator):
+    name = "pre-agg/clipping"
+
+    def __init__(self, threshold: float = 2.0, *, chunk_size: int = 32) -> None:
+        if threshold < 0:
+            raise ValueError("threshold must be >= 0")
+        if chunk_size <= 0:
+            raise ValueError("chunk_size must be > 0")
+        self.threshold = float(threshold)
+        self.chunk_size = int(chunk_size)
+
+    def row_map(self, G, n):
+        return np.diag(nspace.clip_scales(G, self.threshold))
+
+
+__all__ = ["Clipping"]

@@ -1,0 +1,200 @@
+"""GPU integration: operator classes on CUDA, the fused parameter-server kernel (incl. a
+"two ranks on one GPU" protocol test) and the device round vs a plain PyTorch reference loop."""
+import asyncio
+
+import pytest
+import torch
+import torch.nn as nn
+
+pytestmark = pytest.mark.gpu
+
+from byzpy_b200 import ops
+from byzpy_b200.aggregators.coordinate_wise import (CoordinateWiseMedian, CoordinateWiseTrimmedMean,
+                                                     MeanOfMedians)
+from byzpy_b200.aggregators.geometric_wise import (SMEA, GeometricMedian, Krum,
+                                                    MinimumDiameterAveraging, MoNNA, MultiKrum)
+from byzpy_b200.aggregators.norm_wise import CAF, CenteredClipping, ComparativeGradientElimination
+from byzpy_b200.attacks import (EmpireAttack, GaussianAttack, InfAttack, LittleAttack, MimicAttack,
+                                SignFlipAttack)
+from byzpy_b200.pre_aggregators import ARC, Bucketing, Clipping, NearestNeighborMixing
+
+DEV = "cuda:0"
+
+
+def grads(n, d, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.randn(d, generator=g) + (4.0 if i < 2 else 0.0) for i in range(n)]
+
+
+AGGS = [
+    lambda: CoordinateWiseMedian(), lambda: CoordinateWiseTrimmedMean(f=2), lambda: MeanOfMedians(f=2),
+    lambda: MultiKrum(f=2, q=3), lambda: Krum(f=2), lambda: GeometricMedian(),
+    lambda: GeometricMedian(init="mean"), lambda: MinimumDiameterAveraging(f=2), lambda: MoNNA(f=2),
+    lambda: SMEA(f=2), lambda: CenteredClipping(c_tau=1.0), lambda: CenteredClipping(c_tau=0.5, init="median"),
+    lambda: ComparativeGradientElimination(f=2), lambda: CAF(f=2),
+]
+
+
+@pytest.mark.parametrize("mk", AGGS)
+def test_aggregators_cuda_match_cpu(mk):
+    g = grads(11, 3001, seed=4)
+    cpu = mk().aggregate(g)
+    gpu = mk().aggregate([x.to(DEV) for x in g])
+    assert gpu.is_cuda and gpu.shape == cpu.shape and gpu.dtype == cpu.dtype
+    torch.testing.assert_close(gpu.cpu(), cpu, rtol=2e-4, atol=2e-4)
+
+
+@pytest.mark.parametrize("mk", [lambda: Clipping(threshold=30.0), lambda: ARC(f=3),
+                                lambda: NearestNeighborMixing(f=3),
+                                lambda: Bucketing(bucket_size=4, perm=[3, 1, 0, 2, 5, 4, 7, 6, 9, 8, 10])])
+def test_pre_aggregators_cuda_match_cpu(mk):
+    g = grads(11, 2049, seed=5)
+    cpu = mk().pre_aggregate(g)
+    gpu = mk().pre_aggregate([x.to(DEV) for x in g])
+    assert len(cpu) == len(gpu)
+    for a, b in zip(gpu, cpu):
+        torch.testing.assert_close(a.cpu(), b, rtol=1e-4, atol=1e-4)
+
+
+def test_attacks_cuda():
+    g = grads(7, 4097, seed=6)
+    gd = [x.to(DEV) for x in g]
+    for mk, kw in [(lambda: SignFlipAttack(scale=-2.0), dict(base_grad=0)),
+                   (lambda: EmpireAttack(scale=-1.1), dict(honest_grads=1)),
+                   (lambda: LittleAttack(f=2), dict(honest_grads=1)),
+                   (lambda: MimicAttack(epsilon=3), dict(honest_grads=1)),
+                   (lambda: InfAttack(), dict(honest_grads=1))]:
+        kc = {k: (g[0] if v == 0 else g) for k, v in kw.items()}
+        kg = {k: (gd[0] if v == 0 else gd) for k, v in kw.items()}
+        a, b = mk().apply(**kc), mk().apply(**kg)
+        assert b.is_cuda
+        torch.testing.assert_close(b.cpu(), a, rtol=1e-5, atol=1e-5)
+    z = GaussianAttack(mu=0.5, sigma=3.0, seed=1).apply(honest_grads=[torch.zeros(1 << 18, device=DEV)])
+    assert abs(z.mean().item() - 0.5) < 0.05 and abs(z.std().item() - 3.0) < 0.05
+
+
+def _fused(ext, rows, scales, mode, f, d, off, ln, rank, aggs, pads, epoch, ctl, upd_p, upd_m,
+           stream, grid_limit=0, virt=(0, 0, 0.0, 0.0)):
+    ext.fused_ps_cw(rows, scales, mode, f, virt[0], virt[1], virt[2], virt[3], d, off, ln, rank,
+                    aggs, pads, epoch, 0, ctl.data_ptr(), ctl.data_ptr() + 4, upd_p, upd_m,
+                    0.1, 0.9, 0.0, ops.sm_count(torch.device(DEV)), stream, grid_limit)
+
+
+def test_fused_ps_single_rank_matches_unfused():
+    ext = ops.require_ext()
+    n, d = 8, 8192
+    X = torch.randn(n, d, device=DEV)
+    agg = torch.zeros(d, device=DEV)
+    pad = torch.zeros(64, dtype=torch.int32, device=DEV)
+    ctl = torch.zeros(8, dtype=torch.int32, device=DEV)
+    params = [torch.randn(d, device=DEV) for _ in range(2)]
+    moms = [torch.zeros(d, device=DEV) for _ in range(2)]
+    p0 = [p.clone() for p in params]
+    scales = [1.0] * 6 + [-1.0, -1.0]
+    s = torch.cuda.current_stream().cuda_stream
+    _fused(ext, [X[i].data_ptr() for i in range(n)], scales, ops.MODE_MEDIAN, 0, d, 0, d, 0,
+           [agg.data_ptr()], [pad.data_ptr()], 1, ctl, [p.data_ptr() for p in params],
+           [m.data_ptr() for m in moms], s)
+    torch.cuda.synchronize()
+    assert ctl[1].item() == 0
+    exp = (X * torch.tensor(scales, device=DEV)[:, None]).median(dim=0).values
+    torch.testing.assert_close(agg, exp, rtol=0, atol=0)
+    for r in range(2):
+        torch.testing.assert_close(moms[r], exp)
+        torch.testing.assert_close(params[r], p0[r] - 0.1 * exp, rtol=1e-6, atol=1e-6)
+    assert pad[0].item() == 1 and pad[16].item() == 1  # ready / done flags carry the epoch
+
+
+def test_fused_ps_two_ranks_on_one_gpu_protocol():
+    """Both 'ranks' live on one device: exercises flags, sharding and the cross-rank stores."""
+    ext = ops.require_ext()
+    n, d = 8, 1 << 16
+    X = torch.randn(n, d, device=DEV)
+    aggs = [torch.zeros(d, device=DEV) for _ in range(2)]
+    pads = [torch.zeros(64, dtype=torch.int32, device=DEV) for _ in range(2)]
+    ctls = [torch.zeros(8, dtype=torch.int32, device=DEV) for _ in range(2)]
+    params = [[torch.zeros(d, device=DEV)] for _ in range(2)]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    half = d // 2
+    limit = max(1, ops.sm_count(torch.device(DEV)) // 2)
+    torch.cuda.synchronize()
+    for epoch in (1, 2, 3):
+        for r in range(2):
+            with torch.cuda.stream(streams[r]):
+                _fused(ext, [X[i].data_ptr() for i in range(n)], [1.0] * n, ops.MODE_TRMEAN, 2, d,
+                       r * half, half, r, [a.data_ptr() for a in aggs], [p.data_ptr() for p in pads],
+                       epoch, ctls[r], [params[r][0].data_ptr()], [], streams[r].cuda_stream,
+                       grid_limit=limit)
+        torch.cuda.synchronize()
+        assert ctls[0][1].item() == 0 and ctls[1][1].item() == 0
+    exp = X.sort(dim=0).values[2:6].mean(dim=0)
+    for r in range(2):
+        torch.testing.assert_close(aggs[r], exp, rtol=1e-6, atol=1e-6)
+        torch.testing.assert_close(params[r][0], -0.1 * 3 * exp, rtol=1e-5, atol=1e-6)
+
+
+class TinyNet(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.a = nn.Linear(20, 33)
+        self.b = nn.Linear(33, 5)
+
+    def forward(self, x):
+        return self.b(torch.relu(self.a(x)))
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_device_round_matches_manual_loop(graph):
+    from byzpy_b200.engine.node.device import DeviceByzantineNode, DeviceHonestNode
+    from byzpy_b200.engine.parameter_server.ps import ParameterServer
+
+    torch.manual_seed(0)
+    n_h, n_b, steps = 4, 1, 3
+    data = [[(torch.randn(16, 20), torch.randint(0, 5, (16,))) for _ in range(steps + 4)]
+            for _ in range(n_h + n_b)]
+    init = TinyNet().state_dict()
+
+    def mk():
+        m = TinyNet()
+        m.load_state_dict(init)
+        return m
+
+    hon = [DeviceHonestNode(mk(), lr=0.1, momentum=0.9, device=DEV) for _ in range(n_h)]
+    byz = [DeviceByzantineNode(SignFlipAttack(), model=mk(), lr=0.1, momentum=0.9, device=DEV)]
+    ps = ParameterServer(hon, byz, CoordinateWiseMedian(), update_byzantines=True, fused=True,
+                         amp_dtype=None, use_cuda_graph=graph)
+    warm = 0
+    # manual reference
+    models = [mk().to(DEV) for _ in range(n_h + n_b)]
+    opts = [torch.optim.SGD(m.parameters(), lr=0.1, momentum=0.9) for m in models]
+    lossf = nn.CrossEntropyLoss()
+    for t in range(steps):
+        batches = [(data[w][t][0].pin_memory(), data[w][t][1].pin_memory()) for w in range(n_h + n_b)]
+        ps.step(batches)
+        gs = []
+        for w, m in enumerate(models):
+            m.zero_grad()
+            lossf(m(batches[w][0].to(DEV)), batches[w][1].to(DEV)).backward()
+            g = torch.cat([p.grad.reshape(-1) for p in m.parameters()])
+            gs.append(-g if w >= n_h else g)
+        agg = torch.stack(gs).median(dim=0).values
+        for m, o in zip(models, opts):
+            off = 0
+            for p in m.parameters():
+                p.grad.copy_(agg[off:off + p.numel()].view_as(p))
+                off += p.numel()
+            o.step()
+    ps.device_round.check_status()
+    torch.testing.assert_close(ps.device_round.aggregated(), agg, rtol=1e-4, atol=1e-5)
+    mine = torch.cat([p.detach().reshape(-1) for p in hon[0].model.parameters()])
+    theirs = torch.cat([p.detach().reshape(-1) for p in models[0].parameters()])
+    torch.testing.assert_close(mine, theirs, rtol=1e-4, atol=1e-5)
+    sd = hon[0].dump_state_dict()
+    TinyNet().load_state_dict(sd, strict=True)
+    asyncio.run(ps.shutdown())
+
+
+def test_smoke_entry():
+    import __graft_entry__ as g
+
+    g.smoke()

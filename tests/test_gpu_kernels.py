@@ -1,0 +1,170 @@
+"""GPU numerics: every hand-written kernel vs a plain PyTorch fp32/fp64 reference of the same op."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from byzpy_b200 import ops
+from byzpy_b200.ops import reference as ref
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+def rows_of(n, d, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    X = torch.randn(n, d, generator=g) * scale
+    return [X[i].to(dev()).contiguous() for i in range(n)], X
+
+
+def test_extension_is_loaded():
+    ext = ops.require_ext()
+    assert ext.ARCH == "sm_100a"
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 8, 9, 16, 17, 31, 33, 64, 65, 100, 128])
+@pytest.mark.parametrize("mode", [ops.MODE_MEDIAN, ops.MODE_TRMEAN, ops.MODE_MEAMED, ops.MODE_MEAN])
+def test_cw_select_matches_reference(n, mode):
+    d = 4096 + 37
+    rows, X = rows_of(n, d, seed=n)
+    f = 0 if n < 3 else max(1, n // 5)
+    if mode == ops.MODE_TRMEAN and 2 * f >= n:
+        f = 0
+    out = ops.cw_select(rows, mode, f)
+    exp = ref.cw_select([X[i] for i in range(n)], mode, f)
+    torch.testing.assert_close(out.cpu(), exp, rtol=1e-5, atol=1e-5)
+
+
+def test_cw_median_is_lower_median_and_matches_torch():
+    rows, X = rows_of(8, 10000, seed=3)
+    out = ops.cw_median(rows)
+    torch.testing.assert_close(out.cpu(), X.median(dim=0).values, rtol=0, atol=0)
+
+
+def test_cw_select_unaligned_rows_and_tail():
+    base = torch.randn(7 * 1001 + 3, device=dev())
+    rows = [base[1 + i * 1001: 1 + i * 1001 + 999] for i in range(7)]  # misaligned views
+    out = ops.cw_median(rows)
+    exp = torch.stack(rows).median(dim=0).values
+    torch.testing.assert_close(out, exp, rtol=0, atol=0)
+
+
+def test_cw_select_inf_and_nan_rows():
+    rows, X = rows_of(9, 2048, seed=5)
+    rows[0].fill_(float("inf"))
+    rows[1][::2] = float("nan")
+    X[0] = float("inf")
+    X[1, ::2] = float("nan")
+    for mode, f in [(ops.MODE_MEDIAN, 0), (ops.MODE_TRMEAN, 2)]:
+        out = ops.cw_select(rows, mode, f)
+        exp = ref.cw_select([X[i] for i in range(9)], mode, f)
+        torch.testing.assert_close(out.cpu(), exp, rtol=1e-5, atol=1e-5, equal_nan=True)
+        assert torch.isfinite(out).all()
+
+
+def test_cw_select_scales_and_virtual_rows():
+    rows, X = rows_of(6, 5000, seed=7)
+    scales = [1, 1, 1, 1, -1, -2.5]
+    out = ops.cw_select(rows, ops.MODE_MEDIAN, 0, scales=scales)
+    exp = ref.cw_select([X[i] for i in range(6)], ops.MODE_MEDIAN, 0, scales=scales)
+    torch.testing.assert_close(out.cpu(), exp, rtol=1e-6, atol=1e-6)
+    virt = (2, 6, 1.0, 1.5)  # two Little rows built from all six honest ones
+    out = ops.cw_select(rows, ops.MODE_TRMEAN, 1, virtual=virt)
+    exp = ref.cw_select([X[i] for i in range(6)], ops.MODE_TRMEAN, 1, virtual=virt)
+    torch.testing.assert_close(out.cpu(), exp, rtol=1e-5, atol=1e-5)
+
+
+def test_cw_select_fused_sgd_update():
+    rows, X = rows_of(8, 3000, seed=11)
+    params = [torch.randn(3000, device=dev()) for _ in range(3)]
+    moms = [torch.randn(3000, device=dev()) for _ in range(3)]
+    p0 = [p.clone().cpu() for p in params]
+    m0 = [m.clone().cpu() for m in moms]
+    g = ops.cw_select(rows, ops.MODE_MEDIAN, 0,
+                      update=dict(params=params, moms=moms, lr=0.1, momentum=0.9, weight_decay=1e-3))
+    gexp = X.median(dim=0).values
+    torch.testing.assert_close(g.cpu(), gexp)
+    for r in range(3):
+        gg = gexp + 1e-3 * p0[r]
+        m = 0.9 * m0[r] + gg
+        torch.testing.assert_close(moms[r].cpu(), m, rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(params[r].cpu(), p0[r] - 0.1 * m, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("n", [2, 4, 7, 8, 12, 16, 20, 33, 64, 100, 128])
+def test_gram_fp32_matches_fp64(n):
+    d = 20000 + 13
+    rows, X = rows_of(n, d, seed=100 + n)
+    G = ops.gram(rows, impl="fp32")
+    exp = (X.double() @ X.double().T)
+    torch.testing.assert_close(G.cpu().double(), exp, rtol=2e-5, atol=2e-3)
+    G64 = ops.gram(rows, want64=True, impl="fp32")
+    torch.testing.assert_close(G64.cpu(), exp, rtol=2e-5, atol=2e-3)
+
+
+def test_gram_scales():
+    rows, X = rows_of(5, 7000, seed=9)
+    s = [1.0, -1.0, 0.5, 2.0, 0.0]
+    G = ops.gram(rows, scales=s, impl="fp32")
+    Xs = X * torch.tensor(s)[:, None]
+    torch.testing.assert_close(G.cpu(), Xs @ Xs.T, rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("m", [1, 2, 3, 8, 11])
+def test_weighted_sum(m):
+    n, d = 13, 9001
+    rows, X = rows_of(n, d, seed=21)
+    W = torch.randn(m, n)
+    W[:, 3] = 0.0
+    rows[3].fill_(float("inf"))  # zero-weight rows must not poison the output
+    Y = ops.weighted_sum(rows, W.to(dev()))
+    Xc = X.clone()
+    Xc[3] = 0.0
+    torch.testing.assert_close(Y.cpu(), W @ Xc, rtol=1e-4, atol=1e-4)
+
+
+def test_colstat_little():
+    rows, X = rows_of(10, 6000, seed=31)
+    out = ops.colstat(rows, 1.0, 1.7)
+    exp = X.mean(0) + 1.7 * X.std(0, unbiased=False)
+    torch.testing.assert_close(out.cpu(), exp, rtol=1e-5, atol=1e-5)
+
+
+def test_sgd_step_multi_replica():
+    d = 10007
+    g = torch.randn(d, device=dev())
+    ps = [torch.randn(d, device=dev()) for _ in range(4)]
+    ms = [torch.zeros(d, device=dev()) for _ in range(4)]
+    ref_p = [p.clone() for p in ps]
+    ref_m = [m.clone() for m in ms]
+    for _ in range(3):
+        ops.sgd_step(g, ps, ms, lr=0.05, momentum=0.9, weight_decay=0.0)
+        ref.sgd_step(g, params=ref_p, moms=ref_m, lr=0.05, momentum=0.9)
+    for a, b in zip(ps, ref_p):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)
+
+
+def test_gaussian_statistics_and_determinism():
+    a = torch.empty(1 << 20, device=dev())
+    b = torch.empty(1 << 20, device=dev())
+    ops.gaussian_(a, 1.0, 2.0, seed=7)
+    ops.gaussian_(b, 1.0, 2.0, seed=7)
+    assert torch.equal(a, b)
+    assert abs(a.mean().item() - 1.0) < 0.02
+    assert abs(a.std().item() - 2.0) < 0.02
+    z = (a - 1.0) / 2.0
+    assert abs((z ** 3).mean().item()) < 0.05           # skewness
+    assert abs((z ** 4).mean().item() - 3.0) < 0.1      # kurtosis
+    ops.gaussian_(b, 1.0, 2.0, seed=8)
+    assert not torch.equal(a, b)
+
+
+def test_scale_fill():
+    x = torch.randn(5001, device=dev())
+    torch.testing.assert_close(ops.scale_copy(x, -1.0), -x)
+    y = torch.empty(77, device=dev())
+    ops.fill_(y, float("inf"))
+    assert torch.isinf(y).all()
