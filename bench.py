@@ -253,14 +253,14 @@ def run_reference(args, rank, world, device):
     classes, lr = args.classes, args.lr
 
     def flatten(model):
-        return torch.cat([(torch.zeros_like(p) if p.grad is None else p.grad).view(-1)
+        return torch.cat([(torch.zeros_like(p) if p.grad is None else p.grad).reshape(-1)
                           for p in model.parameters()])
 
     def write_grads(model, vec):
         off = 0
         for p in model.parameters():
             n = p.numel()
-            chunk = vec[off:off + n].view_as(p)
+            chunk = vec[off:off + n].view(p.shape)
             if p.grad is None:
                 p.grad = chunk.clone()
             else:

@@ -1,0 +1,34 @@
+"""Length-prefixed object framing for the TCP control plane: 4-byte big-endian length +
+cloudpickle body (frame layout of reference engine/actor/_wire.py:5-18; cloudpickle instead of
+pickle so classes/closures defined in ``__main__`` travel by value)."""
+from __future__ import annotations
+
+import asyncio
+import pickle
+import struct
+from typing import Any
+
+import cloudpickle
+
+_HDR = struct.Struct(">I")
+MAX_FRAME = (1 << 32) - 1
+
+
+def encode(obj: Any) -> bytes:
+    body = cloudpickle.dumps(obj, protocol=pickle.HIGHEST_PROTOCOL)
+    if len(body) > MAX_FRAME:
+        raise ValueError("frame too large")
+    return _HDR.pack(len(body)) + body
+
+
+async def send_obj(writer: asyncio.StreamWriter, obj: Any) -> None:
+    writer.write(encode(obj))
+    await writer.drain()
+
+
+async def recv_obj(reader: asyncio.StreamReader) -> Any:
+    (n,) = _HDR.unpack(await reader.readexactly(_HDR.size))
+    return cloudpickle.loads(await reader.readexactly(n))
+
+
+__all__ = ["send_obj", "recv_obj", "encode"]

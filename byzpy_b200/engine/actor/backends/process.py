@@ -1,0 +1,128 @@
+"""Process actor: the object lives in a ``spawn``-ed child process behind a duplex pipe
+(reference engine/actor/backends/process.py:19-321).
+
+The class/factory travels by value (cloudpickle); tensor arguments and results cross the
+boundary through POSIX shared memory (``wrap_payload`` / ``unwrap_payload``), one copy each way.
+A lock serialises request/response pairs on the pipe; the blocking pipe I/O runs in the default
+executor.  Mailboxes stay on the parent side (they are only read by the coordinator).
+This is the CPU plumbing path; device-resident work uses the ``gpu`` backend instead.
+"""
+from __future__ import annotations
+
+import asyncio
+import multiprocessing as mp
+import threading
+import traceback
+from typing import Any
+
+import cloudpickle
+
+from ..ipc import unwrap_payload, wrap_payload
+from ._local import LocalMailboxBackend
+
+
+def _child_main(conn) -> None:
+    import asyncio as _aio
+    import inspect as _inspect
+
+    obj = None
+    while True:
+        try:
+            msg = conn.recv()
+        except (EOFError, OSError):
+            break
+        op = msg.get("op")
+        try:
+            if op == "stop":
+                conn.send({"ok": True, "payload": None})
+                break
+            if op == "construct":
+                target = cloudpickle.loads(msg["cls"])
+                obj = target(*unwrap_payload(msg["args"]), **unwrap_payload(msg["kwargs"]))
+                conn.send({"ok": True, "payload": None})
+            elif op == "call":
+                fn = getattr(obj, msg["method"])
+                out = fn(*unwrap_payload(msg["args"]), **unwrap_payload(msg["kwargs"]))
+                if _inspect.isawaitable(out):
+                    out = _aio.run(_await(out))
+                conn.send({"ok": True, "payload": wrap_payload(out)})
+            else:
+                conn.send({"ok": False, "error": f"unknown op {op!r}"})
+        except BaseException as exc:  # noqa: BLE001 - everything goes back to the parent
+            try:
+                conn.send({"ok": False, "error": f"{exc!r}\n{traceback.format_exc()}"})
+            except Exception:
+                break
+    try:
+        conn.close()
+    except Exception:
+        pass
+
+
+async def _await(x):
+    return await x
+
+
+class ProcessActorBackend(LocalMailboxBackend):
+    scheme = "process"
+
+    def __init__(self) -> None:
+        super().__init__()
+        ctx = mp.get_context("spawn")
+        self._conn, child = ctx.Pipe(duplex=True)
+        self._proc = ctx.Process(target=_child_main, args=(child,), daemon=True)
+        self._proc.start()
+        child.close()
+        self._io_lock = threading.Lock()
+        self._closed = False
+
+    async def start(self) -> None:
+        if self._loop is None:
+            self._loop = asyncio.get_running_loop()
+
+    def _roundtrip(self, msg: dict) -> Any:
+        with self._io_lock:
+            if self._closed:
+                raise RuntimeError("process actor is closed")
+            try:
+                self._conn.send(msg)
+                reply = self._conn.recv()
+            except (EOFError, OSError, BrokenPipeError) as exc:
+                raise RuntimeError(f"process actor died (pipe error: {exc!r}); the child may have "
+                                   "crashed or been closed concurrently") from exc
+        if not reply.get("ok", False):
+            raise RuntimeError(f"process actor error: {reply.get('error')}")
+        return reply.get("payload")
+
+    async def _send(self, msg: dict) -> Any:
+        loop = asyncio.get_running_loop()
+        return await loop.run_in_executor(None, self._roundtrip, msg)
+
+    async def construct(self, cls_or_factory: Any, *, args: tuple, kwargs: dict) -> None:
+        await self._send({"op": "construct", "cls": cloudpickle.dumps(cls_or_factory),
+                          "args": wrap_payload(tuple(args)), "kwargs": wrap_payload(dict(kwargs))})
+
+    async def call(self, method: str, *args, **kwargs) -> Any:
+        out = await self._send({"op": "call", "method": method, "args": wrap_payload(tuple(args)),
+                                "kwargs": wrap_payload(dict(kwargs))})
+        return unwrap_payload(out)
+
+    async def close(self) -> None:
+        if self._closed:
+            return
+        self._unregister()
+        try:
+            await self._send({"op": "stop"})
+        except Exception:
+            pass
+        self._closed = True
+        try:
+            self._conn.close()
+        except Exception:
+            pass
+        self._proc.join(timeout=5)
+        if self._proc.is_alive():
+            self._proc.terminate()
+
+
+__all__ = ["ProcessActorBackend"]

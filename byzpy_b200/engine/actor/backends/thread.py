@@ -1,0 +1,46 @@
+"""Thread actor: the object lives on a dedicated single-thread executor, so its methods never
+run concurrently with each other (reference engine/actor/backends/thread.py:14-171)."""
+from __future__ import annotations
+
+import asyncio
+import concurrent.futures
+import inspect
+from typing import Any
+
+from ._local import LocalMailboxBackend
+
+
+class ThreadActorBackend(LocalMailboxBackend):
+    scheme = "thread"
+
+    def __init__(self) -> None:
+        super().__init__()
+        self._pool = concurrent.futures.ThreadPoolExecutor(max_workers=1,
+                                                           thread_name_prefix="byz-actor")
+        self._obj: Any = None
+
+    async def start(self) -> None:
+        if self._loop is None:
+            self._loop = asyncio.get_running_loop()
+
+    async def _in_thread(self, fn, *args, **kwargs):
+        loop = asyncio.get_running_loop()
+        return await loop.run_in_executor(self._pool, lambda: fn(*args, **kwargs))
+
+    async def construct(self, cls_or_factory: Any, *, args: tuple, kwargs: dict) -> None:
+        self._obj = await self._in_thread(cls_or_factory, *args, **kwargs)
+
+    async def call(self, method: str, *args, **kwargs) -> Any:
+        if self._obj is None:
+            raise RuntimeError("actor not constructed")
+        fn = getattr(self._obj, method)
+        if inspect.iscoroutinefunction(fn):
+            return await fn(*args, **kwargs)
+        return await self._in_thread(fn, *args, **kwargs)
+
+    async def close(self) -> None:
+        self._unregister()
+        self._pool.shutdown(wait=True)
+
+
+__all__ = ["ThreadActorBackend"]

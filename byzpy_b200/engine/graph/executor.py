@@ -1,0 +1,128 @@
+"""One-operator convenience runner (reference engine/graph/executor.py:33-294).
+
+``OperatorExecutor(op, input_keys=None, pool_config=None, node_name=None)`` builds the
+single-node graph + ``NodeScheduler`` (and lazily owns an ``ActorPool`` when ``pool_config`` is
+given); ``run_operator`` is the one-shot form.  Input keys are auto-detected for aggregators and
+pre-aggregators; attacks need explicit ``input_keys``.  A custom single key different from the
+operator's ``input_key`` is transparently renamed.
+"""
+from __future__ import annotations
+
+from typing import Any, Mapping, Optional, Sequence, Union
+
+from .operator import OpContext, Operator
+from .ops import make_single_operator_graph
+from .pool import ActorPool, ActorPoolConfig
+from .scheduler import NodeScheduler
+
+
+def _detect_input_keys(operator: Operator) -> Sequence[str]:
+    from ...aggregators.base import Aggregator
+    from ...attacks.base import Attack
+    from ...pre_aggregators.base import PreAggregator
+
+    if isinstance(operator, (Aggregator, PreAggregator)):
+        return (operator.input_key,)
+    if isinstance(operator, Attack):
+        raise ValueError(
+            f"Cannot auto-detect input keys for Attack {type(operator).__name__}. "
+            "Attacks have variable input requirements. Please specify input_keys explicitly.")
+    raise ValueError(f"Cannot auto-detect input keys for operator {type(operator).__name__}. "
+                     "Please specify input_keys explicitly.")
+
+
+class _RenamedInput(Operator):
+    """Presents ``inputs[custom_key]`` to the wrapped operator under its own ``input_key``."""
+
+    def __init__(self, wrapped: Operator, custom_key: str, op_key: str) -> None:
+        self.wrapped_op = wrapped
+        self.custom_key, self.op_key = custom_key, op_key
+        self.name = wrapped.name
+        self.supports_subtasks = wrapped.supports_subtasks
+        self.supports_barriered_subtasks = wrapped.supports_barriered_subtasks
+        self.max_subtasks_inflight = wrapped.max_subtasks_inflight
+
+    def _remap(self, inputs: Mapping[str, Any]) -> dict:
+        if self.custom_key not in inputs:
+            raise KeyError(f"Missing input key {self.custom_key!r}")
+        return {self.op_key: inputs[self.custom_key]}
+
+    def compute(self, inputs, *, context: OpContext):
+        return self.wrapped_op.compute(self._remap(inputs), context=context)
+
+    async def run(self, inputs, *, context: OpContext, pool):
+        # remap once so the wrapped operator sees ONE inputs mapping for the whole invocation
+        return await self.wrapped_op.run(self._remap(inputs), context=context, pool=pool)
+
+
+class OperatorExecutor:
+    def __init__(self, operator: Operator, *, input_keys: Optional[Sequence[str]] = None,
+                 pool_config: Union[ActorPoolConfig, Sequence[ActorPoolConfig], None] = None,
+                 node_name: Optional[str] = None):
+        if not isinstance(operator, Operator):
+            raise TypeError(f"operator must be an Operator instance, got {type(operator)}")
+        self.operator = operator
+        self.pool_config = pool_config
+        self.node_name = node_name or operator.name
+        self.input_keys = tuple(input_keys) if input_keys is not None else tuple(_detect_input_keys(operator))
+        self._operator_input_key = getattr(operator, "input_key", None) if len(self.input_keys) == 1 else None
+        self._needs_input_mapping = (self._operator_input_key is not None
+                                     and self.input_keys[0] != self._operator_input_key)
+        self._pool: Optional[ActorPool] = None
+        self._pool_managed = False
+        self._graph = None
+        self._scheduler: Optional[NodeScheduler] = None
+
+    async def __aenter__(self):
+        if self.pool_config is not None:
+            await self._ensure_pool()
+        return self
+
+    async def __aexit__(self, exc_type, exc_val, exc_tb):
+        await self._cleanup_pool()
+
+    async def _ensure_pool(self) -> None:
+        if self._pool is not None:
+            return
+        cfgs = [self.pool_config] if isinstance(self.pool_config, ActorPoolConfig) else list(self.pool_config)
+        self._pool = ActorPool(cfgs)
+        await self._pool.start()
+        self._pool_managed = True
+
+    async def _cleanup_pool(self) -> None:
+        if self._pool is not None and self._pool_managed:
+            await self._pool.shutdown()
+            self._pool = None
+            self._pool_managed = False
+            self._scheduler = None
+
+    def _make_scheduler(self) -> NodeScheduler:
+        op = self.operator
+        if self._needs_input_mapping:
+            op = _RenamedInput(op, self.input_keys[0], self._operator_input_key)
+        graph = make_single_operator_graph(node_name=self.node_name, operator=op,
+                                           input_keys=self.input_keys)
+        self._graph = graph
+        return NodeScheduler(graph, pool=self._pool)
+
+    async def run(self, inputs: Mapping[str, Any]) -> Any:
+        if self.pool_config is not None:
+            await self._ensure_pool()
+        reuse = self.pool_config is not None
+        sched = self._scheduler if (reuse and self._scheduler is not None
+                                    and self._scheduler.pool is self._pool) else None
+        if sched is None:
+            sched = self._make_scheduler()
+            if reuse:
+                self._scheduler = sched
+        return (await sched.run(inputs))[self.node_name]
+
+
+async def run_operator(operator: Operator, inputs: Mapping[str, Any], *,
+                       pool_config: Union[ActorPoolConfig, Sequence[ActorPoolConfig], None] = None,
+                       input_keys: Optional[Sequence[str]] = None) -> Any:
+    async with OperatorExecutor(operator, pool_config=pool_config, input_keys=input_keys) as ex:
+        return await ex.run(inputs)
+
+
+__all__ = ["OperatorExecutor", "run_operator"]

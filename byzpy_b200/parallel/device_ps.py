@@ -323,6 +323,11 @@ class DeviceRound:
         for w in self.workers:
             if w.static_x is None:
                 raise RuntimeError("stage a batch on every worker before capture()")
+        # Warm-up rounds are real rounds: snapshot the training state and restore it afterwards
+        # so that capture() is invisible to the optimisation trajectory.
+        snap_p = self.params.clone()
+        snap_m = None if self.moms is None else self.moms.clone()
+        snap_b = [[b.clone() for b in w.model.buffers()] for w in self.workers]
         s = torch.cuda.Stream(self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
@@ -336,6 +341,14 @@ class DeviceRound:
         with torch.cuda.graph(g):
             self._body()
         self._graph = g
+        with torch.no_grad():
+            self.params.copy_(snap_p)
+            if snap_m is not None:
+                self.moms.copy_(snap_m)
+            for w, bufs in zip(self.workers, snap_b):
+                for b, saved in zip(w.model.buffers(), bufs):
+                    b.copy_(saved)
+        torch.cuda.synchronize(self.device)
 
     # --------------------------------------------------------------------- step
     def step(self, batches: Optional[Sequence[Tuple[torch.Tensor, torch.Tensor]]] = None) -> torch.Tensor:

@@ -1,0 +1,124 @@
+"""Multi-rank correctness check of the fused cross-GPU parameter-server round.
+
+Launch:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+             --master-port 29533 tests/multi_gpu/check_fused_round.py [--agg median|trmean|meamed]
+
+Every rank hosts 8/N TinyNet replicas; after each round the fused kernel's aggregate (delivered
+into every rank's buffer by peer stores) is compared with an NCCL all_gather + PyTorch reference
+of the same math, and the updated parameters with a plain torch SGD loop.
+"""
+import argparse
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+
+from byzpy_b200.aggregators.coordinate_wise import (CoordinateWiseMedian, CoordinateWiseTrimmedMean,  # noqa: E402
+                                                     MeanOfMedians)
+from byzpy_b200.attacks import SignFlipAttack  # noqa: E402
+from byzpy_b200.engine.node.device import DeviceByzantineNode, DeviceHonestNode  # noqa: E402
+from byzpy_b200.engine.parameter_server.ps import ParameterServer  # noqa: E402
+from byzpy_b200.ops import reference as ref  # noqa: E402
+from byzpy_b200.parallel.device_ps import RowLayout  # noqa: E402
+
+
+class TinyNet(nn.Module):
+    def __init__(self, width=257):
+        super().__init__()
+        self.a = nn.Linear(64, width)
+        self.b = nn.Linear(width, width)
+        self.c = nn.Linear(width, 10)
+
+    def forward(self, x):
+        return self.c(torch.relu(self.b(torch.relu(self.a(x)))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--agg", default="median")
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--graph", type=int, default=1)
+    a = ap.parse_args()
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    n_total, n_byz = 8, 2
+    n_h = n_total - n_byz
+    layout = RowLayout.block(n_h, n_byz, world)
+    gids = layout.local_ids(rank)
+    torch.manual_seed(0)
+    init = TinyNet().state_dict()
+    hon, byz, mirror = [], [], []
+    for g in gids:
+        m = TinyNet()
+        m.load_state_dict(init)
+        m2 = TinyNet()
+        m2.load_state_dict(init)
+        mirror.append(m2.to(dev))
+        kw = dict(lr=0.1, momentum=0.9, device=str(dev))
+        if g < n_h:
+            hon.append(DeviceHonestNode(m, **kw))
+        else:
+            byz.append(DeviceByzantineNode(SignFlipAttack(), model=m, **kw))
+    agg = {"median": CoordinateWiseMedian(), "trmean": CoordinateWiseTrimmedMean(f=2),
+           "meamed": MeanOfMedians(f=2)}[a.agg]
+    mode, f = {"median": (0, 0), "trmean": (1, 2), "meamed": (2, 2)}[a.agg]
+    ps = ParameterServer(hon, byz, agg, update_byzantines=True, layout=layout, amp_dtype=None,
+                         use_cuda_graph=bool(a.graph), fused=True)
+    opts = [torch.optim.SGD(m.parameters(), lr=0.1, momentum=0.9) for m in mirror]
+    lossf = nn.CrossEntropyLoss()
+    ok = True
+    for t in range(a.steps):
+        gen = torch.Generator().manual_seed(1000 * t + rank)
+        batches = [(torch.randn(32, 64, generator=gen).pin_memory(),
+                    torch.randint(0, 10, (32,), generator=gen).pin_memory()) for _ in gids]
+        ps.step(batches)
+        # reference: local grads on the mirrors, NCCL all_gather, torch aggregate, torch SGD
+        local_rows = []
+        for (x, y), m, g in zip(batches, mirror, gids):
+            m.zero_grad()
+            lossf(m(x.to(dev)), y.to(dev)).backward()
+            v = torch.cat([p.grad.reshape(-1) for p in m.parameters()])
+            local_rows.append(-v if g >= n_h else v)
+        loc = torch.stack(local_rows)
+        full = torch.empty((world,) + tuple(loc.shape), device=dev)
+        dist.all_gather_into_tensor(full.view(-1), loc.view(-1))
+        rows = list(full.view(n_total, -1).unbind(0))
+        expect = ref.cw_select(rows, mode, f)
+        for m, o in zip(mirror, opts):
+            off = 0
+            for p in m.parameters():
+                p.grad.copy_(expect[off:off + p.numel()].view_as(p))
+                off += p.numel()
+            o.step()
+        torch.cuda.synchronize()
+        ps.device_round.check_status()
+        got = ps.device_round.aggregated()
+        e1 = (got - expect).abs().max().item()
+        mine = torch.cat([p.detach().reshape(-1) for p in (hon[0].model if hon else byz[0].model).parameters()])
+        theirs = torch.cat([p.detach().reshape(-1) for p in mirror[0].parameters()])
+        e2 = (mine - theirs).abs().max().item()
+        good = e1 < 1e-5 and e2 < 1e-4
+        ok = ok and good
+        print(f"[rank {rank}] step {t}: |agg-ref|={e1:.2e} |param-ref|={e2:.2e} {'OK' if good else 'MISMATCH'}",
+              flush=True)
+    flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("MULTI_GPU_FUSED_ROUND", "PASS" if flag.item() == 1.0 else "FAIL", f"world={world} agg={a.agg}", flush=True)
+    import asyncio
+
+    asyncio.run(ps.shutdown())
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1.0 else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,25 @@
+"""Multi-GPU tests (skipped unless >= 2 CUDA devices): launch torchrun subprocesses."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("agg", ["median", "trmean"])
+def test_fused_round_two_ranks(agg):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29533",
+           os.path.join(ROOT, "tests", "multi_gpu", "check_fused_round.py"), "--agg", agg]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert res.returncode == 0 and "MULTI_GPU_FUSED_ROUND PASS" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
