@@ -1,0 +1,38 @@
+"""Array-backend selection (reference configs/backend.py:12-49).
+
+The reference's ``get_backend()`` unconditionally returns a fresh torch backend, so
+``set_backend`` / ``use_backend`` are inert there.  The API is kept; here the
+selection is honoured: ``"torch"`` (default) or ``"numpy"``.
+"""
+from __future__ import annotations
+
+from contextlib import contextmanager
+from typing import Iterator
+
+from ..engine.backend.ndarray import get_array_backend
+
+_current = "torch"
+
+
+def set_backend(name: str) -> None:
+    global _current
+    get_array_backend(name)  # validates
+    _current = name
+
+
+def get_backend():
+    return get_array_backend(_current)
+
+
+@contextmanager
+def use_backend(name: str) -> Iterator[None]:
+    global _current
+    prev = _current
+    set_backend(name)
+    try:
+        yield
+    finally:
+        _current = prev
+
+
+__all__ = ["set_backend", "get_backend", "use_backend"]
