@@ -88,6 +88,15 @@ class RemoteActorBackend:
         return await self.get_endpoint()
 
     async def chan_put(self, *, from_ep: Endpoint, to_ep: Endpoint, name: str, payload: Any) -> None:
+        if to_ep.scheme in ("thread", "process", "gpu"):
+            # the target lives in THIS (client) process: deliver through the local router
+            from ..router import channel_router
+
+            peer = channel_router.resolve(to_ep.scheme, to_ep.actor_id)
+            if peer is None:
+                raise RuntimeError(f"no local {to_ep.scheme} actor {to_ep.actor_id}")
+            await peer._deliver_local(name, from_ep, payload)
+            return
         await self._rpc({"op": "chan_put", "actor_id": to_ep.actor_id, "name": name,
                          "to": (to_ep.scheme, to_ep.address, to_ep.actor_id),
                          "payload": self._pack(payload)})

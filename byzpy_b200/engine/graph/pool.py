@@ -151,6 +151,13 @@ class ActorPool:
         self._channel_cache: Dict[str, ActorPoolChannel] = {}
         self._worker_affinity_caps: List[str] = []
 
+    # a pool travels between processes as its configuration only (workers are re-created there)
+    def __getstate__(self):
+        return {"configs": self.configs}
+
+    def __setstate__(self, state):
+        self.__init__(state["configs"])
+
     @property
     def size(self) -> int:
         return len(self._workers) if self._started else sum(c.count for c in self.configs)

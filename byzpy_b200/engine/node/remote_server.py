@@ -1,0 +1,139 @@
+"""Hub server hosting decentralized nodes and relaying between remote clients
+(reference engine/node/remote_server.py:15-274).
+
+Nodes registered on the server use ``ServerNodeContext``: local delivery goes through the
+in-process registry, anything else is forwarded to the remote client that announced the target
+id with a ``_register_node`` handshake.  Remote clients address any node id; the server delivers
+locally or relays to the owning client.
+"""
+from __future__ import annotations
+
+import asyncio
+from typing import Any, Dict, Optional
+
+from .context import InProcessContext, NodeContext
+from .remote_client import read_frame, write_frame
+
+
+class ServerNodeContext(NodeContext):
+    def __init__(self, server: "RemoteNodeServer", in_process_context: InProcessContext):
+        self.server = server
+        self.inner = in_process_context
+        self._node = None
+
+    async def start(self, node) -> None:
+        self._node = node
+        await self.inner.start(node)
+
+    async def send_message(self, to_node_id, message_type: str, payload: Any) -> None:
+        if to_node_id in InProcessContext._registry:
+            await self.inner.send_message(to_node_id, message_type, payload)
+            return
+        await self.server.send_message_to_client(
+            to_node_id, {"from": self._node.node_id if self._node else "unknown",
+                         "type": message_type, "payload": payload})
+
+    async def receive_messages(self):
+        async for msg in self.inner.receive_messages():
+            yield msg
+
+    async def shutdown(self) -> None:
+        await self.inner.shutdown()
+
+
+class RemoteNodeServer:
+    def __init__(self, host: str = "localhost", port: int = 8888, *, gpu_direct: bool = False):
+        self.host, self.port = host, int(port)
+        self.gpu_direct = gpu_direct
+        self._nodes: Dict[Any, Any] = {}
+        self._clients: Dict[Any, asyncio.StreamWriter] = {}
+        self._server: Optional[asyncio.AbstractServer] = None
+        self._running = False
+
+    async def register_node(self, node) -> None:
+        if node.node_id in self._nodes:
+            raise ValueError(f"Node {node.node_id!r} already registered")
+        inner = node.context if isinstance(node.context, InProcessContext) else InProcessContext()
+        node.context = ServerNodeContext(self, inner)
+        self._nodes[node.node_id] = node
+        await node.start()
+
+    async def start(self) -> None:
+        if self._server is None:
+            self._server = await asyncio.start_server(self._handle_client, self.host, self.port)
+            self.port = self._server.sockets[0].getsockname()[1]
+            self._running = True
+
+    async def serve(self) -> None:
+        await self.start()
+        async with self._server:
+            await self._server.serve_forever()
+
+    async def _deliver(self, msg: Dict[str, Any]) -> None:
+        target = msg.get("to")
+        node = self._nodes.get(target)
+        if node is not None:
+            await node.handle_incoming_message(msg.get("from", "unknown"), msg.get("type", "unknown"),
+                                               msg.get("payload"))
+            return
+        await self.send_message_to_client(target, {"from": msg.get("from", "unknown"),
+                                                   "type": msg.get("type"), "payload": msg.get("payload")})
+
+    async def _handle_client(self, reader: asyncio.StreamReader, writer: asyncio.StreamWriter) -> None:
+        owned = []
+        try:
+            while True:
+                try:
+                    msg = await read_frame(reader)
+                except (asyncio.IncompleteReadError, ConnectionError, OSError):
+                    break
+                if msg.get("type") == "_register_node":
+                    nid = msg.get("node_id")
+                    self._clients[nid] = writer
+                    owned.append(nid)
+                    continue
+                try:
+                    await self._deliver(msg)
+                except Exception:
+                    continue
+        finally:
+            for nid in owned:
+                if self._clients.get(nid) is writer:
+                    self._clients.pop(nid, None)
+            try:
+                writer.close()
+            except Exception:
+                pass
+
+    async def send_message_to_client(self, node_id, msg: Dict[str, Any]) -> None:
+        writer = self._clients.get(node_id)
+        if writer is None or writer.is_closing():
+            raise ValueError(f"Target node {node_id} not found on server or among clients")
+        out = dict(msg)
+        out.setdefault("to", node_id)
+        await write_frame(writer, out, gpu_direct=self.gpu_direct)
+
+    async def shutdown(self) -> None:
+        self._running = False
+        for node in list(self._nodes.values()):
+            try:
+                await node.shutdown()
+            except Exception:
+                pass
+        self._nodes.clear()
+        for w in list(self._clients.values()):
+            try:
+                w.close()
+            except Exception:
+                pass
+        self._clients.clear()
+        if self._server is not None:
+            self._server.close()
+            try:
+                await self._server.wait_closed()
+            except Exception:
+                pass
+            self._server = None
+
+
+__all__ = ["RemoteNodeServer", "ServerNodeContext"]

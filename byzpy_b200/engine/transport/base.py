@@ -1,0 +1,14 @@
+"""``Transport`` protocol: ``register(node_id, handler)`` / ``send(to_id, payload)``
+(reference engine/transport/base.py:9-16)."""
+from __future__ import annotations
+
+from typing import Any, Callable, Protocol
+
+
+class Transport(Protocol):
+    def register(self, node_id: str, handler: Callable[[Any], None]) -> None: ...
+
+    def send(self, to_id: str, payload: Any) -> None: ...
+
+
+__all__ = ["Transport"]

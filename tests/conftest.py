@@ -24,7 +24,7 @@ def pytest_collection_modifyitems(config, items):
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:
-        if "gpu" in item.keywords:
+        if item.get_closest_marker("gpu") is not None:
             item.add_marker(skip)
 
 

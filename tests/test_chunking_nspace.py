@@ -1,0 +1,117 @@
+import itertools
+
+import numpy as np
+import pytest
+
+from byzpy_b200.aggregators._chunking import select_adaptive_chunk_size
+from byzpy_b200.ops import nspace
+
+
+def test_chunking_basic_and_degenerate():
+    assert select_adaptive_chunk_size(0, 10) == 0
+    assert select_adaptive_chunk_size(5, 10) == 5
+    assert select_adaptive_chunk_size(100, 32, pool_size=1) == 32
+    assert select_adaptive_chunk_size(65536, 8192, pool_size=6) == 2731
+    assert select_adaptive_chunk_size(65536, 8192, pool_size=2) == 8192
+    assert select_adaptive_chunk_size(1000, 100, pool_size=4) == 63
+
+
+def test_chunking_env_overrides(monkeypatch):
+    base = select_adaptive_chunk_size(10**6, 4096, pool_size=6)
+    monkeypatch.setenv("BYZPY_CHUNK_MIN_PER_WORKER", "64")
+    more = select_adaptive_chunk_size(10**6, 4096, pool_size=6)
+    assert more < base
+    monkeypatch.setenv("BYZPY_CHUNK_MAX_SHRINK", "2")
+    assert select_adaptive_chunk_size(10**6, 4096, pool_size=6) >= 2048
+    monkeypatch.setenv("BYZPY_CHUNK_TARGET_FACTOR", "not-a-number")
+    select_adaptive_chunk_size(10**6, 4096, pool_size=6)  # bad values are ignored
+
+
+def _X(n, d, seed):
+    return np.random.default_rng(seed).normal(size=(n, d))
+
+
+def test_sqdist_and_krum_bruteforce():
+    X = _X(9, 20, 0)
+    G = X @ X.T
+    D = nspace.sqdist(G)
+    ref = ((X[:, None, :] - X[None, :, :]) ** 2).sum(-1)
+    assert np.allclose(D, ref, atol=1e-9)
+    f, q = 2, 3
+    scores = np.array([np.sort(np.delete(ref[i], i))[: 9 - f - 1].sum() for i in range(9)])
+    assert np.allclose(nspace.krum_scores(G, f), scores)
+    w = nspace.krum_weights(G, f, q)
+    assert set(np.nonzero(w)[0]) == set(np.argsort(scores)[:q]) and np.isclose(w.sum(), 1.0)
+
+
+def test_mda_subset_is_lexicographically_first_minimiser():
+    for seed in range(5):
+        X = _X(8, 3, seed)
+        D = nspace.sqdist(X @ X.T)
+        m = 5
+        best, best_combo = None, None
+        for combo in itertools.combinations(range(8), m):
+            diam = max(D[i, j] for i in combo for j in combo)
+            if best is None or diam < best:
+                best, best_combo = diam, combo
+        assert nspace.mda_subset(D, m) == best_combo
+
+
+def test_mda_tie_breaks_to_first_subset():
+    D = np.ones((5, 5)) - np.eye(5)
+    assert nspace.mda_subset(D, 3) == (0, 1, 2)
+
+
+def test_smea_subset_bruteforce():
+    X = _X(7, 10, 4)
+    G = X @ X.T
+    m = 5
+    best, best_combo = None, None
+    for combo in itertools.combinations(range(7), m):
+        sub = X[list(combo)]
+        cov = np.cov(sub.T, bias=True)
+        lam = np.linalg.eigvalsh(cov)[-1]
+        if best is None or lam < best - 1e-12:
+            best, best_combo = lam, combo
+    assert nspace.smea_subset(G, m) == best_combo
+
+
+def test_weiszfeld_coeffs_match_data_space_iteration():
+    X = _X(8, 30, 7)
+    G = X @ X.T
+    a0 = np.full(8, 1 / 8)
+    a, iters = nspace.weiszfeld_coeffs(G, 8, a0, tol=1e-10, max_iter=300, eps=1e-12)
+    z = X.mean(0)
+    for _ in range(300):
+        dist = np.maximum(np.linalg.norm(X - z, axis=1), 1e-12)
+        w = 1 / dist
+        z_new = (w[:, None] * X).sum(0) / w.sum()
+        if np.linalg.norm(z_new - z) <= 1e-10:
+            z = z_new
+            break
+        z = z_new
+    assert np.allclose(a @ X, z, atol=1e-7) and 1 <= iters <= 300
+
+
+def test_centered_clip_coeffs_match_data_space():
+    X = _X(6, 12, 9)
+    G = X @ X.T
+    a = nspace.centered_clip_coeffs(G, 6, np.zeros(6), c_tau=0.8, M=5, eps=1e-12)
+    v = np.zeros(12)
+    for _ in range(5):
+        diff = X - v
+        dist = np.maximum(np.linalg.norm(diff, axis=1), 1e-12)
+        v = v + (np.minimum(1.0, 0.8 / dist)[:, None] * diff).sum(0) / 6
+    assert np.allclose(a @ X, v, atol=1e-9)
+
+
+def test_selection_validation():
+    G = np.eye(4)
+    with pytest.raises(ValueError):
+        nspace.krum_weights(G, 3, 1)
+    with pytest.raises(ValueError):
+        nspace.monna_weights(G, 2)
+    with pytest.raises(ValueError):
+        nspace.cge_weights(G, 4)
+    with pytest.raises(ValueError):
+        nspace.bucket_matrix(4, 2, [0, 1, 2, 2])

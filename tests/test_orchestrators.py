@@ -1,0 +1,257 @@
+"""Orchestrators: ParameterServer (generic actor path, every aggregator, with and without a
+pool -- the reference fails here for Median/TrimmedMean/GeometricMedian/CenteredClipping),
+PeerToPeer, legacy runners/transports, CLI, utils, shared store, arenas."""
+import asyncio
+import json
+
+import pytest
+import torch
+import torch.nn as nn
+
+from byzpy_b200.aggregators.coordinate_wise import CoordinateWiseMedian, CoordinateWiseTrimmedMean
+from byzpy_b200.aggregators.geometric_wise import GeometricMedian, MultiKrum
+from byzpy_b200.aggregators.norm_wise import CenteredClipping
+from byzpy_b200.attacks import EmpireAttack, SignFlipAttack
+from byzpy_b200.cli import main as cli_main
+from byzpy_b200.engine.graph.pool import ActorPool, ActorPoolConfig
+from byzpy_b200.engine.node.actors import ByzantineNodeActor, HonestNodeActor
+from byzpy_b200.engine.node.base import ByzantineNode, HonestNode
+from byzpy_b200.engine.node.device import DeviceByzantineNode, DeviceHonestNode
+from byzpy_b200.engine.node.mixin import P2PByzantineMixin, P2PHonestMixin
+from byzpy_b200.engine.parameter_server.ps import ParameterServer
+from byzpy_b200.engine.parameter_server.runner import ParameterServerRunner
+from byzpy_b200.engine.peer_to_peer.topology import Topology
+from byzpy_b200.engine.peer_to_peer.train import PeerToPeer
+from byzpy_b200.engine.storage.shared_store import (SharedTensorHandle, cleanup_tensor, materialize,
+                                                    open_tensor, register_tensor)
+from byzpy_b200.engine.transport import LocalTransport, TcpTransport
+from byzpy_b200.parallel.arena import ParamArena, flatten_grads, flatten_params
+from byzpy_b200.pre_aggregators import Bucketing
+from byzpy_b200.utils import train_with_progress
+
+
+def run(coro):
+    return asyncio.run(coro)
+
+
+class Hon(HonestNode):
+    def __init__(self, seed, d=12):
+        self.g = torch.Generator().manual_seed(seed)
+        self.d = d
+        self.applied = []
+
+    def next_batch(self):
+        return torch.randn(self.d, generator=self.g), torch.zeros(1)
+
+    def honest_gradient(self, x, y):
+        return x + 1.0
+
+    def apply_server_gradient(self, g):
+        self.applied.append(g.clone())
+
+    def history(self):
+        return self.applied
+
+
+class Byz(ByzantineNode):
+    def __init__(self):
+        self.attack = EmpireAttack(scale=-3.0)
+        self.applied = []
+
+    def next_batch(self):
+        return torch.empty(0), torch.empty(0)
+
+    def byzantine_gradient(self, x, y, honest_grads=None):
+        return self.attack.apply(honest_grads=list(honest_grads))
+
+    def apply_server_gradient(self, g):
+        self.applied.append(g)
+
+    def history(self):
+        return self.applied
+
+
+AGGS = [lambda: CoordinateWiseMedian(), lambda: CoordinateWiseTrimmedMean(f=1), lambda: GeometricMedian(),
+        lambda: CenteredClipping(c_tau=1.0), lambda: MultiKrum(f=1, q=2)]
+
+
+@pytest.mark.parametrize("mk", AGGS)
+@pytest.mark.parametrize("use_pool", [False, True])
+def test_parameter_server_round_generic_path(mk, use_pool):
+    async def scenario():
+        hon = [await HonestNodeActor.spawn(Hon, backend="thread", args=(i,)) for i in range(4)]
+        byz = [await ByzantineNodeActor.spawn(Byz, backend="thread")]
+        pool = None
+        if use_pool:
+            pool = ActorPool([ActorPoolConfig(backend="thread", count=2)])
+            await pool.start()
+        ps = ParameterServer(hon, byz, mk(), update_byzantines=False, actor_pool=pool)
+        g = await ps.round()
+        # deterministic (submission-order) gather: recompute what the PS saw
+        mirrors = [Hon(i) for i in range(4)]
+        rows = [m.honest_gradient_for_next_batch() for m in mirrors]
+        rows.append(Byz().byzantine_gradient_for_next_batch(rows))
+        assert torch.allclose(g, mk().aggregate(rows), rtol=1e-5, atol=1e-6)
+        for h in hon:
+            assert len(await h.history()) == 1
+        assert len(await byz[0].history()) == 0
+        await ps.shutdown()
+        if pool is not None:
+            await pool.shutdown()
+
+    run(scenario())
+
+
+def test_parameter_server_pre_aggregator_and_update_byzantines_plain_objects():
+    hon, byz = [Hon(i) for i in range(4)], [Byz()]
+    ps = ParameterServer(hon, byz, CoordinateWiseMedian(), pre_aggregator=Bucketing(2, perm=[0, 1, 2, 3, 4]),
+                         update_byzantines=True)
+    g = ps.round_sync()
+    assert g.shape == (12,) and len(byz[0].applied) == 1 and ps.rounds == 1
+    assert ps.device_round is None
+    with pytest.raises(RuntimeError):
+        ps.step()
+
+
+def test_device_nodes_fall_back_to_generic_round_on_cpu():
+    torch.manual_seed(0)
+
+    def src():
+        return torch.randn(8, 6), torch.randint(0, 3, (8,))
+
+    hon = [DeviceHonestNode(nn.Linear(6, 3), data=src, lr=0.1, momentum=0.0, device="cpu") for _ in range(3)]
+    byz = [DeviceByzantineNode(SignFlipAttack(), model=nn.Linear(6, 3), data=src, device="cpu")]
+    ps = ParameterServer(hon, byz, CoordinateWiseMedian(), update_byzantines=True)
+    assert ps.device_round is None
+    before = flatten_params(hon[0].model).clone()
+    g = ps.round_sync()
+    after = flatten_params(hon[0].model)
+    assert torch.allclose(after, before - 0.1 * g, atol=1e-6)
+    with pytest.raises(RuntimeError):
+        ParameterServer(hon, byz, CoordinateWiseMedian(), fused=True)
+    sd = hon[0].dump_state_dict()
+    nn.Linear(6, 3).load_state_dict(sd, strict=True)
+
+
+class PH(P2PHonestMixin):
+    def __init__(self, seed):
+        torch.manual_seed(0)
+        self.model = nn.Linear(5, 2)
+        self.device = torch.device("cpu")
+        self.criterion = nn.CrossEntropyLoss()
+        self.p2p_agg = CoordinateWiseTrimmedMean(f=1)
+        self.g = torch.Generator().manual_seed(seed)
+
+    def next_batch(self):
+        return torch.randn(16, 5, generator=self.g), torch.randint(0, 2, (16,), generator=self.g)
+
+    def params(self):
+        return self.get_param_vector()
+
+
+class PB(P2PByzantineMixin):
+    def __init__(self):
+        self.device = torch.device("cpu")
+        self.attack = EmpireAttack(scale=-5.0)
+
+
+def test_peer_to_peer_round_writes_back_robust_aggregate():
+    async def scenario():
+        hon = [await HonestNodeActor.spawn(PH, backend="thread", args=(i,)) for i in range(4)]
+        byz = [await ByzantineNodeActor.spawn(PB, backend="thread")]
+        p2p = PeerToPeer(hon, byz, Topology.complete(5), lr=0.1)
+        await p2p.bootstrap()
+        p0 = await hon[0].params()
+        await p2p.round()
+        p1 = await hon[0].params()
+        # manual expectation for node 0
+        mirrors = [PH(i) for i in range(4)]
+        halves = [m.p2p_half_step(0.1) for m in mirrors]
+        mal = PB().p2p_broadcast_vector(neighbor_vectors=halves, like=halves[0])
+        exp = CoordinateWiseTrimmedMean(f=1).aggregate([halves[0]] + halves[1:] + [mal])
+        assert not torch.equal(p0, p1) and torch.allclose(p1, exp, atol=1e-6)
+        assert p2p.runner.rounds == 1
+        await p2p.shutdown()
+        for a in hon + byz:
+            await a.close()
+
+    run(scenario())
+
+
+def g1():
+    return torch.tensor([1.0, 2.0])
+
+
+def g2():
+    return torch.tensor([3.0, 4.0])
+
+
+@pytest.mark.parametrize("transport", [None, LocalTransport, TcpTransport])
+def test_parameter_server_runner_mean_round(transport):
+    tr = transport() if transport else None
+    r = ParameterServerRunner([g1, g2], transport=tr)
+    r.start()
+    try:
+        assert torch.equal(r.run_round(), torch.tensor([2.0, 3.0]))
+        assert torch.equal(r.run_round(), torch.tensor([2.0, 3.0]))
+    finally:
+        r.stop()
+        if hasattr(tr, "close"):
+            tr.close()
+
+
+def test_local_transport_unknown_node():
+    with pytest.raises(KeyError):
+        LocalTransport().send("nobody", 1)
+
+
+def test_cli(capsys):
+    assert cli_main(["version"]) == 0
+    assert capsys.readouterr().out.strip()
+    assert cli_main(["doctor", "--format", "json"]) == 0
+    rep = json.loads(capsys.readouterr().out)
+    assert rep["torch"]["available"] and "kernels" in rep
+    assert cli_main(["list", "aggregators", "--format", "json"]) == 0
+    items = json.loads(capsys.readouterr().out)["items"]
+    assert {"CoordinateWiseMedian", "MultiKrum", "Krum", "CAF", "SMEA", "MoNNA"} <= set(items)
+    assert "CoordinateWiseAggregator" not in items
+    assert cli_main(["list", "attacks"]) == 0 and "LittleAttack" in capsys.readouterr().out
+    assert cli_main(["list", "pre-aggregators"]) == 0 and "Bucketing" in capsys.readouterr().out
+
+
+def test_train_with_progress():
+    class FakePS:
+        n = 0
+
+        async def round(self):
+            self.n += 1
+
+    evals = []
+    ps = FakePS()
+    run(train_with_progress(ps, 10, eval_callback=lambda: evals.append(ps.n) or {"acc": 0.5}, eval_interval=5))
+    assert ps.n == 10 and evals == [5, 10]
+
+
+def test_shared_store_roundtrip():
+    x = torch.arange(12.0).reshape(3, 4)
+    h = register_tensor(x)
+    assert isinstance(h, SharedTensorHandle) and h.shape == (3, 4) and h.dtype == "float32"
+    with open_tensor(h) as arr:
+        assert arr[2, 3] == 11.0
+    assert torch.equal(materialize({"name": h.name, "shape": h.shape, "dtype": h.dtype}), x)
+    cleanup_tensor(h)
+    cleanup_tensor(h)  # idempotent
+
+
+def test_param_arena_views_and_layout():
+    m = nn.Sequential(nn.Linear(3, 4), nn.Linear(4, 2))
+    ref = flatten_params(m).clone()
+    arena = ParamArena(m)
+    assert arena.d == ref.numel() and arena.d_pad % 1024 == 0 and arena.check_bound()
+    assert torch.equal(arena.param_vector(), ref)
+    m(torch.randn(5, 3)).sum().backward()
+    assert torch.equal(arena.grad_vector(), flatten_grads(m)) and arena.check_bound()
+    arena.flat_params[:3] = 7.0
+    assert torch.equal(next(m.parameters()).reshape(-1)[:3], torch.full((3,), 7.0))
+    arena.zero_grad()
+    assert all(p.grad.abs().sum() == 0 for p in m.parameters())

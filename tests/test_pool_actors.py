@@ -1,0 +1,269 @@
+"""ActorPool logic (fake backend) and real actor backends (thread / process / gpu / tcp) incl. the
+cross-backend channel matrix."""
+import asyncio
+import socket
+import threading
+
+import pytest
+import torch
+
+from byzpy_b200.aggregators.coordinate_wise import CoordinateWiseMedian, CoordinateWiseTrimmedMean
+from byzpy_b200.aggregators.geometric_wise import GeometricMedian, MultiKrum
+from byzpy_b200.configs.actor import set_actor
+from byzpy_b200.engine.actor.backends.gpu import GPUActorBackend, UCXRemoteActorBackend
+from byzpy_b200.engine.actor.backends.process import ProcessActorBackend
+from byzpy_b200.engine.actor.backends.remote import RemoteActorBackend, RemoteActorServer
+from byzpy_b200.engine.actor.backends.thread import ThreadActorBackend
+from byzpy_b200.engine.actor.base import ActorRef
+from byzpy_b200.engine.actor.channels import Endpoint
+from byzpy_b200.engine.actor.factory import resolve_backend
+from byzpy_b200.engine.actor.ipc import unwrap_payload, wrap_payload
+from byzpy_b200.engine.graph import pool as pool_mod
+from byzpy_b200.engine.graph.ops import make_single_operator_graph
+from byzpy_b200.engine.graph.pool import ActorPool, ActorPoolConfig
+from byzpy_b200.engine.graph.scheduler import NodeScheduler
+from byzpy_b200.engine.graph.subtask import SubTask
+
+
+def run(coro):
+    return asyncio.run(coro)
+
+
+class _FakeBackend:
+    """Runs the worker object inline; records calls (reference test technique)."""
+
+    instances = []
+
+    def __init__(self, fail_first=0):
+        self.obj = None
+        self.calls = 0
+        self.fail_first = fail_first
+        self.closed = False
+        _FakeBackend.instances.append(self)
+
+    async def start(self):
+        pass
+
+    async def construct(self, cls, *, args, kwargs):
+        self.obj = cls(*args, **kwargs)
+
+    async def call(self, method, *args, **kwargs):
+        self.calls += 1
+        if self.calls <= self.fail_first:
+            raise RuntimeError("injected failure")
+        await asyncio.sleep(0.005)
+        return getattr(self.obj, method)(*args, **kwargs)
+
+    async def close(self):
+        self.closed = True
+
+    async def get_endpoint(self):
+        return Endpoint("fake", "", str(id(self)))
+
+    async def chan_open(self, name):
+        return await self.get_endpoint()
+
+
+@pytest.fixture
+def fake_backends(monkeypatch):
+    _FakeBackend.instances.clear()
+    monkeypatch.setattr(pool_mod, "resolve_backend", lambda spec: spec if not isinstance(spec, str) else _FakeBackend())
+    return _FakeBackend
+
+
+def sq(x):
+    return x * x
+
+
+def test_pool_size_capabilities_and_affinity(fake_backends):
+    async def scenario():
+        pool = ActorPool([ActorPoolConfig("thread", count=2, name="cpu"), ActorPoolConfig("gpu", count=1, name="g")])
+        assert pool.size == 3
+        await pool.start()
+        assert pool.worker_affinities() == ("worker::cpu-0", "worker::cpu-1", "worker::g-0")
+        assert await pool.run_many([SubTask(sq, (i,)) for i in range(6)]) == [i * i for i in range(6)]
+        gpu_worker = [w for w in pool._workers if "gpu" in w.capabilities][0]
+        before = gpu_worker.backend.calls
+        await asyncio.gather(*[pool.run_subtask(SubTask(sq, (3,), affinity="gpu")) for _ in range(4)])
+        assert gpu_worker.backend.calls == before + 4
+        assert await pool.run_subtask(SubTask(sq, (5,), affinity="worker::cpu-1")) == 25
+        with pytest.raises(RuntimeError, match="No actor in the pool"):
+            await pool.run_subtask(SubTask(sq, (1,), affinity="tpu"))
+        await pool.shutdown()
+        assert all(b.closed for b in fake_backends.instances)
+
+    run(scenario())
+
+
+def test_pool_retries(fake_backends):
+    async def scenario():
+        be = _FakeBackend(fail_first=2)
+        pool = ActorPool([ActorPoolConfig(be, count=1)])
+        await pool.start()
+        assert await pool.run_subtask(SubTask(sq, (4,), max_retries=2)) == 16
+        be.calls, be.fail_first = 0, 5
+        with pytest.raises(RuntimeError):
+            await pool.run_subtask(SubTask(sq, (4,), max_retries=1))
+        await pool.shutdown()
+
+    run(scenario())
+
+
+def test_explicit_capabilities_and_infer():
+    assert ActorPoolConfig("gpu").resolved_capabilities() == ("gpu",)
+    assert ActorPoolConfig("ucx://h:1").resolved_capabilities() == ("gpu",)
+    assert ActorPoolConfig("thread").resolved_capabilities() == ("cpu",)
+    assert ActorPoolConfig("thread", capabilities=("x",)).resolved_capabilities() == ("x",)
+    assert isinstance(resolve_backend("tcp://127.0.0.1:1"), RemoteActorBackend)
+    assert isinstance(resolve_backend("ucx://127.0.0.1:1"), UCXRemoteActorBackend)
+    assert isinstance(set_actor("thread"), ThreadActorBackend)
+    with pytest.raises(ValueError):
+        resolve_backend("carrier-pigeon")
+
+
+class Counter:
+    def __init__(self, start=0):
+        self.v = start
+
+    def add(self, k):
+        self.v += k
+        return self.v
+
+    async def aadd(self, k):
+        self.v += k
+        return self.v
+
+    def echo(self, t):
+        return t * 2
+
+
+@pytest.mark.parametrize("spec", ["thread", "gpu", "process"])
+def test_actor_backends_call_and_tensors(spec):
+    async def scenario():
+        be = resolve_backend(spec)
+        async with ActorRef(be) as ref:
+            await be.construct(Counter, args=(10,), kwargs={})
+            assert await ref.add(5) == 15
+            assert await ref.aadd(1) == 16
+            out = await ref.echo(torch.arange(4.0))
+            assert torch.equal(out, torch.arange(4.0) * 2)
+            with pytest.raises(Exception):
+                await ref.nope()
+
+    run(scenario())
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+class _ServerThread:
+    """Actor server on a background thread with its own event loop."""
+
+    def __init__(self, cls=RemoteActorServer):
+        self.port = _free_port()
+        self.server = cls("127.0.0.1", self.port)
+        self.loop = asyncio.new_event_loop()
+        self.ready = threading.Event()
+        self.thread = threading.Thread(target=self._main, daemon=True)
+        self.thread.start()
+        assert self.ready.wait(5)
+
+    def _main(self):
+        asyncio.set_event_loop(self.loop)
+        self.loop.run_until_complete(self.server.start())
+        self.ready.set()
+        self.loop.run_forever()
+
+    def stop(self):
+        fut = asyncio.run_coroutine_threadsafe(self.server.stop(), self.loop)
+        fut.result(5)
+        self.loop.call_soon_threadsafe(self.loop.stop)
+        self.thread.join(5)
+
+
+def test_tcp_actor_server_roundtrip():
+    srv = _ServerThread()
+    try:
+        async def scenario():
+            be = resolve_backend(f"tcp://127.0.0.1:{srv.port}")
+            async with ActorRef(be) as ref:
+                await be.construct(Counter, args=(), kwargs={"start": 2})
+                assert await ref.add(3) == 5
+                assert torch.equal(await ref.echo(torch.ones(3)), torch.full((3,), 2.0))
+                ep = await ref.endpoint()
+                assert ep.scheme == "tcp" and ep.address.endswith(str(srv.port))
+                with pytest.raises(RuntimeError):
+                    await ref.missing_method()
+
+        run(scenario())
+    finally:
+        srv.stop()
+
+
+def test_cross_backend_channel_matrix():
+    srv = _ServerThread()
+    try:
+        async def scenario():
+            specs = ["thread", "gpu", "process", f"tcp://127.0.0.1:{srv.port}"]
+            backends = []
+            for s in specs:
+                be = resolve_backend(s)
+                await be.start()
+                await be.construct(Counter, args=(), kwargs={})
+                backends.append(be)
+            refs = [ActorRef(b) for b in backends]
+            chans = [await r.open_channel("grads") for r in refs]
+            eps = [await r.endpoint() for r in refs]
+            for i, src in enumerate(chans):
+                for j, dst in enumerate(eps):
+                    if i == j:
+                        continue
+                    payload = {"from": i, "t": torch.full((2,), float(10 * i + j))}
+                    await src.send(dst, payload)
+                    got = await chans[j].recv(timeout=2.0)
+                    assert got["from"] == i and torch.equal(got["t"], payload["t"]), (specs[i], specs[j])
+            assert await chans[0].recv(timeout=0.05) is None
+            for b in backends:
+                await b.close()
+
+        run(scenario())
+    finally:
+        srv.stop()
+
+
+def test_ipc_wrap_unwrap_roundtrip():
+    payload = {"a": torch.arange(6.0).reshape(2, 3), "b": [torch.ones(2), 7], "c": ("x", torch.zeros(1))}
+    back = unwrap_payload(wrap_payload(payload))
+    assert torch.equal(back["a"], payload["a"]) and torch.equal(back["b"][0], payload["b"][0]) and back["b"][1] == 7
+    assert isinstance(back["c"], tuple) and torch.equal(back["c"][1], torch.zeros(1))
+
+
+@pytest.mark.real_actor_backends
+@pytest.mark.parametrize("backend", ["thread", "gpu", "process"])
+def test_operators_through_real_pools(backend):
+    async def scenario():
+        g = [torch.randn(500) for _ in range(10)]
+        pool = ActorPool([ActorPoolConfig(backend=backend, count=3)])
+        await pool.start()
+        try:
+            for mk in (lambda: CoordinateWiseMedian(chunk_size=64), lambda: CoordinateWiseTrimmedMean(f=2, chunk_size=64),
+                       lambda: MultiKrum(f=2, q=3), lambda: GeometricMedian()):
+                graph = make_single_operator_graph(node_name="agg", operator=mk(), input_keys=("gradients",))
+                out = (await NodeScheduler(graph, pool=pool).run({"gradients": g}))["agg"]
+                assert torch.allclose(out, mk().aggregate(g), rtol=1e-5, atol=1e-6)
+            ch = await pool.open_channel("c")
+            a, b = ch.workers[0], ch.workers[1]
+            await ch.send(a, b, {"v": torch.ones(3)})
+            assert torch.equal((await ch.recv(b, timeout=2.0))["v"], torch.ones(3))
+            assert (await pool.open_channel("c")) is ch
+            with pytest.raises(KeyError):
+                ch.channel("nobody")
+        finally:
+            await pool.shutdown()
+
+    run(scenario())
