@@ -13,6 +13,8 @@
 #include <vector>
 
 #include "api.h"
+#include "gram_umma.h"
+#include "nspace.h"
 #include "runtime.h"
 
 namespace py = pybind11;
@@ -180,6 +182,46 @@ PYBIND11_MODULE(_C, m) {
     UpdTable u;
     fill_upd(u, params, moms, lr, mu, wd);
     check(bz_sgd(as_ptr<const float>(grad), &u, len, sm_count, as_stream(stream)), "sgd");
+  });
+
+  m.def("gram_umma_grid", &bz_gram_umma_grid);
+  m.def(
+      "gram_umma",
+      [](const std::vector<uint64_t>& rows, const std::vector<float>& scales, long long off,
+         long long len, uint64_t partials, int num_partials, uint64_t tail64, uint64_t G,
+         uint64_t G64, int sm_count, uint64_t stream) {
+        BzGramUmmaArgs a;
+        std::memset(&a, 0, sizeof(a));
+        fill_rows(a.rows, a.scales, rows, scales);
+        a.n = (int)rows.size();
+        a.off = off;
+        a.len = len;
+        a.partials = as_ptr<float>(partials);
+        a.num_partials = num_partials;
+        a.tail64 = as_ptr<const double>(tail64);
+        a.G = as_ptr<float>(G);
+        a.G64 = as_ptr<double>(G64);
+        check(bz_gram_umma(&a, sm_count, as_stream(stream)), "gram_umma");
+      },
+      py::arg("rows"), py::arg("scales"), py::arg("off"), py::arg("len"), py::arg("partials"),
+      py::arg("num_partials"), py::arg("tail64"), py::arg("G"), py::arg("G64"),
+      py::arg("sm_count"), py::arg("stream"));
+  m.def("nspace_krum", [](uint64_t G, int n, int f, int q, uint64_t w, uint64_t stream) {
+    check(bz_nspace_krum(as_ptr<const double>(G), n, f, q, as_ptr<float>(w), as_stream(stream)),
+          "nspace_krum");
+  });
+  m.def("nspace_weiszfeld", [](uint64_t G, int nt, int n_real, uint64_t a0, double tol, int max_iter,
+                               double eps, uint64_t out, uint64_t iters, uint64_t stream) {
+    check(bz_nspace_weiszfeld(as_ptr<const double>(G), nt, n_real, as_ptr<const double>(a0), tol,
+                              max_iter, eps, as_ptr<float>(out), as_ptr<int>(iters),
+                              as_stream(stream)),
+          "nspace_weiszfeld");
+  });
+  m.def("nspace_cclip", [](uint64_t G, int nt, int n_real, uint64_t a0, double c_tau, int M,
+                           double eps, uint64_t out, uint64_t stream) {
+    check(bz_nspace_cclip(as_ptr<const double>(G), nt, n_real, as_ptr<const double>(a0), c_tau, M,
+                          eps, as_ptr<float>(out), as_stream(stream)),
+          "nspace_cclip");
   });
 
   bz_bind_runtime(m);

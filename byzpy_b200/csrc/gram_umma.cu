@@ -1,0 +1,350 @@
+// Gram matrix  G = (S X)(S X)^T  on the 5th-generation tensor cores (tcgen05 / UMMA),
+// with TMEM accumulators and TMA bulk loads.  sm_100a only.
+//
+// Shape: M = N = n <= 128 rows (padded to M = 128, N = round_up(n, 16)), K = d (huge):
+// a split-K skinny GEMM whose cost is ONE read of the n*d matrix.  Each persistent CTA owns a
+// strided set of 64-column K chunks and accumulates all of them into the SAME TMEM
+// accumulators; per-CTA partial results are reduced in fp64 by a second tiny kernel
+// (deterministic two-stage split-K, no atomics).
+//
+// Precision (SURVEY 7.1 "precision hazard"): kind::tf32 keeps 10 mantissa bits, which is not
+// enough for G_ii + G_jj - 2 G_ij when gradients are close.  Every fp32 value is split
+// x = hi + lo with hi = rna_tf32(x); the kernel accumulates  HH = hi hi^T  and  HL = hi lo^T
+// in two TMEM accumulators, and the reduction forms  G = HH + HL + HL^T  (the dropped lo lo^T
+// term is 2^-22 relative).  Two MMAs per k-step instead of three because A == B == X.
+//
+// Warp roles (192 threads):
+//   warp 0      TMA producer: per K chunk one cp.async.bulk (global -> smem, 256 B) per row,
+//               straight from the row pointer table (rows may live in peer HBM), completion
+//               tracked by an mbarrier transaction count;
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit releases the
+//               operand stage / signals the epilogue;
+//   warps 2..5  converters: read the raw fp32 tile, split hi/lo, write the two K-major
+//               SWIZZLE_128B operand tiles (conflict-free both ways), fence.proxy.async, arrive;
+//               afterwards the same warps are the epilogue (tcgen05.ld TMEM -> registers ->
+//               per-CTA partial in global memory).
+// Three mbarrier rings: raw full/empty (TMA <-> converters), operand full/empty
+// (converters <-> MMA), accumulator full (MMA -> epilogue).
+#include "api.h"
+#include "gram_umma.h"
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kRawCols = 64;                  // fp32 columns per TMA chunk (256 B per row)
+constexpr int kOpCols = 32;                   // columns per operand tile (128 B swizzle row)
+constexpr int kRows = 128;                    // padded M
+constexpr int kRawStages = 3;
+constexpr int kOpStages = 3;
+constexpr int kRawStageBytes = kRows * kRawCols * 4;          // 32 KB
+constexpr int kOpTileBytes = kRows * kOpCols * 4;             // 16 KB (hi) ; lo follows
+constexpr int kOpStageBytes = 2 * kOpTileBytes;               // 32 KB
+constexpr int kTmemCols = 256;                // D_hh at column 0, D_hl at column 128
+constexpr int kSmemBytes = 1024 /*align slack*/ + kRawStages * kRawStageBytes +
+                           kOpStages * kOpStageBytes + 256 /*barriers*/;
+constexpr unsigned long long kWaitBudgetCycles = 4000000000ull;  // ~2 s: trap instead of hanging
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const unsigned long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > kWaitBudgetCycles) __trap();
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
+//   start address >> 4 | LBO (unused for swizzled K-major, set to 1) | SBO = 1024 B between
+//   8-row groups | layout type 2 (SWIZZLE_128B) in bits [61, 64).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);          // bits [0, 14)
+  d |= (uint64_t)1 << 16;                            // leading byte offset (16 B units)
+  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset
+  d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+  return d;
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = n_pad.
+__device__ __forceinline__ uint32_t make_idesc(int n_pad) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_pad >> 3) << 17) |
+         ((uint32_t)(kRows >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+               ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1) gram_umma_kernel(const __grid_constant__ BzGramUmmaArgs a) {
+  extern __shared__ uint8_t smem_raw_[];
+  // SWIZZLE_128B operand tiles need 1024-byte alignment
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw_ + 1023) & ~(uintptr_t)1023);
+  uint8_t* op_base = smem;                                         // kOpStages x (hi | lo)
+  uint8_t* raw_base = smem + kOpStages * kOpStageBytes;            // kRawStages x [128][64] fp32
+  uint64_t* bars = (uint64_t*)(raw_base + kRawStages * kRawStageBytes);
+  uint64_t* raw_full = bars;                    // [kRawStages]
+  uint64_t* raw_empty = bars + kRawStages;      // [kRawStages]
+  uint64_t* op_full = bars + 2 * kRawStages;    // [kOpStages]
+  uint64_t* op_empty = op_full + kOpStages;     // [kOpStages]
+  uint64_t* acc_full = op_empty + kOpStages;    // [1]
+  uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = a.n;
+  const int n_pad = (n + 15) & ~15;
+  const long long nchunks = a.len / kRawCols;                      // full 64-column chunks only
+  long long my_chunks = 0;
+  if ((long long)blockIdx.x < nchunks) my_chunks = (nchunks - 1 - blockIdx.x) / gridDim.x + 1;
+
+  // ---- one-time setup ------------------------------------------------------------------
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kRawStages; ++s) {
+      mbar_init(smem_u32(&raw_full[s]), 1);
+      mbar_init(smem_u32(&raw_empty[s]), 128);
+    }
+    for (int s = 0; s < kOpStages; ++s) {
+      mbar_init(smem_u32(&op_full[s]), 128);
+      mbar_init(smem_u32(&op_empty[s]), 1);
+    }
+    mbar_init(smem_u32(acc_full), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // rows >= n of every operand tile stay zero for the whole kernel
+  for (int i = threadIdx.x; i < kOpStages * kOpStageBytes / 16; i += kThreads)
+    reinterpret_cast<uint4*>(op_base)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================== TMA producer ===================================
+    for (long long k = 0; k < my_chunks; ++k) {
+      const int rs = (int)(k % kRawStages);
+      const uint32_t ph = (uint32_t)((k / kRawStages) & 1);
+      mbar_wait(smem_u32(&raw_empty[rs]), ph ^ 1u);
+      const long long col = a.off + ((long long)blockIdx.x + k * gridDim.x) * kRawCols;
+      if (lane == 0) mbar_arrive_expect_tx(smem_u32(&raw_full[rs]), (uint32_t)n * kRawCols * 4);
+      __syncwarp();
+      for (int r = lane; r < n; r += 32) {
+        bulk_g2s(smem_u32(raw_base + rs * kRawStageBytes + r * (kRawCols * 4)), a.rows.p[r] + col,
+                 kRawCols * 4, smem_u32(&raw_full[rs]));
+      }
+    }
+  } else if (warp == 1) {
+    // ====================================== MMA issuer ====================================
+    const uint32_t idesc = make_idesc(n_pad);
+    const uint32_t d_hh = tmem_base, d_hl = tmem_base + 128;
+    const long long nops = my_chunks * (kRawCols / kOpCols);
+    for (long long t = 0; t < nops; ++t) {
+      const int os = (int)(t % kOpStages);
+      const uint32_t ph = (uint32_t)((t / kOpStages) & 1);
+      mbar_wait(smem_u32(&op_full[os]), ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t hi = smem_u32(op_base + os * kOpStageBytes);
+        const uint32_t lo = hi + kOpTileBytes;
+#pragma unroll
+        for (int kk = 0; kk < kOpCols / 8; ++kk) {   // K = 8 tf32 (32 bytes) per instruction
+          const uint64_t dh = make_desc(hi + kk * 32);
+          const uint64_t dl = make_desc(lo + kk * 32);
+          const uint32_t acc = (t > 0 || kk > 0) ? 1u : 0u;
+          umma_tf32(d_hh, dh, dh, idesc, acc);
+          umma_tf32(d_hl, dh, dl, idesc, acc);
+        }
+        umma_commit(smem_u32(&op_empty[os]));         // frees the operand stage when MMAs retire
+        if (t == nops - 1) umma_commit(smem_u32(acc_full));
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================================== converters / epilogue =============================
+    const int cw = warp - 2;                          // 0..3
+    const int c = lane & 7, rr = lane >> 3;           // 16-byte chunk within a 128 B row, row in quad
+    long long t = 0;                                  // operand-tile counter (2 per raw chunk)
+    for (long long k = 0; k < my_chunks; ++k) {
+      const int rs = (int)(k % kRawStages);
+      mbar_wait(smem_u32(&raw_full[rs]), (uint32_t)((k / kRawStages) & 1));
+      const uint8_t* raw = raw_base + rs * kRawStageBytes;
+#pragma unroll
+      for (int h = 0; h < kRawCols / kOpCols; ++h, ++t) {
+        const int os = (int)(t % kOpStages);
+        mbar_wait(smem_u32(&op_empty[os]), (uint32_t)(((t / kOpStages) & 1) ^ 1));
+        uint8_t* hi = op_base + os * kOpStageBytes;
+        uint8_t* lo = hi + kOpTileBytes;
+#pragma unroll
+        for (int it = 0; it < kRows / 16; ++it) {
+          const int row = it * 16 + cw * 4 + rr;
+          if (row < n) {
+            const float4 x = *reinterpret_cast<const float4*>(raw + row * (kRawCols * 4) + h * 128 + c * 16);
+            const float xs[4] = {x.x, x.y, x.z, x.w};      // row scales are applied in the reduce
+            uint32_t hh[4], ll[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              hh[e] = to_tf32(xs[e]);
+              ll[e] = __float_as_uint(xs[e] - __uint_as_float(hh[e]));
+            }
+            const int off = (row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4);
+            *reinterpret_cast<uint4*>(hi + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+            *reinterpret_cast<uint4*>(lo + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+          }
+        }
+        fence_proxy_async();                           // generic-proxy writes -> async proxy (UMMA)
+        mbar_arrive(smem_u32(&op_full[os]));
+      }
+      mbar_arrive(smem_u32(&raw_empty[rs]));
+    }
+    // ---- epilogue: TMEM -> registers -> per-CTA partials --------------------------------
+    if (my_chunks > 0) {
+      mbar_wait(smem_u32(acc_full), 0);
+      tc_fence_after();
+      const int quad = warp & 3;                       // TMEM lane partition of this warp
+      const int row = quad * 32 + lane;
+      float* PA = a.partials + (size_t)blockIdx.x * 2 * n * n;
+      float* PB = PA + (size_t)n * n;
+      for (int c0 = 0; c0 < n_pad; c0 += 16) {
+        uint32_t va[16], vb[16];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0;
+        tmem_ld16(taddr, va);
+        tmem_ld16(taddr + 128, vb);
+        if (row < n) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (c0 + j < n) {
+              PA[row * n + c0 + j] = __uint_as_float(va[j]);
+              PB[row * n + c0 + j] = __uint_as_float(vb[j]);
+            }
+          }
+        }
+      }
+    }
+  }
+  // ---- teardown ------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+  }
+}
+
+// G_ij = s_i s_j * ( sum_c HH_c[i][j] + HL_c[i][j] + HL_c[j][i] ) + G_tail[i][j]
+__global__ void gram_umma_reduce_kernel(const float* __restrict__ partials, int num_partials, int n,
+                                        ScaleTable scales, const double* __restrict__ tail64,
+                                        float* __restrict__ G, double* __restrict__ G64) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * n) return;
+  const int i = t / n, j = t % n;
+  double s = 0.0;
+  for (int c = 0; c < num_partials; ++c) {
+    const float* PA = partials + (size_t)c * 2 * n * n;
+    const float* PB = PA + (size_t)n * n;
+    s += (double)PA[i * n + j] + (double)PB[i * n + j] + (double)PB[j * n + i];
+  }
+  s *= (double)scales.s[i] * (double)scales.s[j];
+  if (tail64) s += tail64[t];
+  G[t] = (float)s;
+  if (G64) G64[t] = s;
+}
+
+}  // namespace
+
+int bz_gram_umma_grid(long long len, int sm_count) {
+  const long long nchunks = len / kRawCols;
+  if (nchunks <= 0) return 0;
+  return (int)(nchunks < sm_count ? nchunks : sm_count);
+}
+
+int bz_gram_umma(const BzGramUmmaArgs* args, int sm_count, cudaStream_t stream) {
+  const BzGramUmmaArgs& a = *args;
+  if (a.n < 1 || a.n > BZ_MAXN) return (int)cudaErrorInvalidValue;
+  if ((a.off % 4) != 0) return (int)cudaErrorInvalidValue;
+  for (int i = 0; i < a.n; ++i)
+    if (((uintptr_t)a.rows.p[i] % 16) != 0) return (int)cudaErrorInvalidValue;
+  const int grid = bz_gram_umma_grid(a.len, sm_count);
+  if (grid > a.num_partials) return (int)cudaErrorInvalidValue;
+  if (grid > 0) {
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(gram_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           kSmemBytes);
+      if (e != cudaSuccess) return (int)e;
+      configured = true;
+    }
+    gram_umma_kernel<<<grid, kThreads, kSmemBytes, stream>>>(a);
+    int e = (int)cudaGetLastError();
+    if (e) return e;
+  }
+  const int rt = 128;
+  gram_umma_reduce_kernel<<<(a.n * a.n + rt - 1) / rt, rt, 0, stream>>>(
+      a.partials, grid, a.n, a.scales, a.tail64, a.G, a.G64);
+  return (int)cudaGetLastError();
+}

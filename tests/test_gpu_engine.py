@@ -73,6 +73,39 @@ def test_attacks_cuda():
     assert abs(z.mean().item() - 0.5) < 0.05 and abs(z.std().item() - 3.0) < 0.05
 
 
+def test_nspace_cuda_solvers_match_host():
+    import numpy as np
+
+    from byzpy_b200.ops import nspace, nspace_cuda
+
+    torch.manual_seed(3)
+    for n, d in [(9, 500), (33, 2000), (128, 4096)]:
+        X = torch.randn(n, d, dtype=torch.float64)
+        X[: n // 4] += 3.0
+        G = (X @ X.T)
+        Gd = G.to(DEV)
+        f = n // 4
+        w = nspace_cuda.krum_weights(Gd, f, 3)
+        assert w is not None
+        np.testing.assert_allclose(w.cpu().numpy(), nspace.krum_weights(G.numpy(), f, 3), atol=1e-7)
+        a0 = np.full(n, 1.0 / n)
+        a = nspace_cuda.weiszfeld_coeffs(Gd, n, a0, tol=1e-8, max_iter=200, eps=1e-12)
+        ah, _ = nspace.weiszfeld_coeffs(G.numpy(), n, a0, tol=1e-8, max_iter=200, eps=1e-12)
+        np.testing.assert_allclose(a.cpu().numpy(), ah, atol=1e-5)
+        c = nspace_cuda.centered_clip_coeffs(Gd, n, np.zeros(n), c_tau=5.0, M=10, eps=1e-12)
+        ch = nspace.centered_clip_coeffs(G.numpy(), n, np.zeros(n), c_tau=5.0, M=10, eps=1e-12)
+        np.testing.assert_allclose(c.cpu().numpy(), ch, atol=1e-6)
+    # augmented start row (median init): n_real < nt
+    X = torch.randn(12, 300, dtype=torch.float64)
+    Xa = torch.cat([X, X.median(0).values[None]], 0)
+    G = Xa @ Xa.T
+    a0 = np.zeros(13)
+    a0[12] = 1.0
+    a = nspace_cuda.weiszfeld_coeffs(G.to(DEV), 12, a0, tol=1e-9, max_iter=256, eps=1e-12)
+    ah, _ = nspace.weiszfeld_coeffs(G.numpy(), 12, a0, tol=1e-9, max_iter=256, eps=1e-12)
+    np.testing.assert_allclose(a.cpu().numpy(), ah, atol=1e-5)
+
+
 def _fused(ext, rows, scales, mode, f, d, off, ln, rank, aggs, pads, epoch, ctl, upd_p, upd_m,
            stream, grid_limit=0, virt=(0, 0, 0.0, 0.0)):
     ext.fused_ps_cw(rows, scales, mode, f, virt[0], virt[1], virt[2], virt[3], d, off, ln, rank,

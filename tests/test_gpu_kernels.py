@@ -105,6 +105,42 @@ def test_gram_fp32_matches_fp64(n):
     torch.testing.assert_close(G64.cpu(), exp, rtol=2e-5, atol=2e-3)
 
 
+@pytest.mark.parametrize("n,d", [(8, 4096), (16, 8192 + 40), (17, 64 * 300), (33, 100000), (64, 65536),
+                                 (100, 50000 + 3), (128, 65536), (128, 64), (5, 200)])
+def test_gram_umma_tcgen05_matches_fp64(n, d):
+    rows, X = rows_of(n, d, seed=500 + n)
+    exp = X.double() @ X.double().T
+    G64 = ops.gram(rows, want64=True, impl="umma")
+    # 3xTF32 split: error ~ 2^-21 relative per product, fp32 accumulation in TMEM
+    torch.testing.assert_close(G64.cpu(), exp, rtol=5e-5, atol=5e-3 * (d / 65536) ** 0.5 + 1e-3)
+    G = ops.gram(rows, impl="umma")
+    torch.testing.assert_close(G.cpu().double(), exp, rtol=5e-5, atol=5e-3 * (d / 65536) ** 0.5 + 1e-3)
+
+
+def test_gram_umma_close_vectors_keep_distance_ranking():
+    """The precision hazard: nearly identical rows; plain TF32 would lose the ordering."""
+    torch.manual_seed(0)
+    base = torch.randn(1 << 16) * 10
+    X = torch.stack([base + 1e-3 * (i + 1) * torch.randn(1 << 16) for i in range(24)])
+    rows = [X[i].to(dev()).contiguous() for i in range(24)]
+    D = ops.sqdist_from_gram(ops.gram(rows, want64=True, impl="umma")).cpu()
+    Dref = torch.cdist(X.double(), X.double()) ** 2
+    # distances are ~1e-6 of |x|^2; require 1 % agreement on them
+    off = ~torch.eye(24, dtype=torch.bool)
+    rel = ((D - Dref).abs() / Dref.clamp_min(1e-30))[off]
+    assert rel.max().item() < 0.05, rel.max().item()
+
+
+def test_gram_umma_scales_and_repeat_determinism():
+    rows, X = rows_of(20, 64 * 777, seed=77)
+    s = [1.0] * 18 + [-1.0, 0.5]
+    a = ops.gram(rows, scales=s, want64=True, impl="umma")
+    b = ops.gram(rows, scales=s, want64=True, impl="umma")
+    assert torch.equal(a, b)
+    Xs = X.double() * torch.tensor(s, dtype=torch.float64)[:, None]
+    torch.testing.assert_close(a.cpu(), Xs @ Xs.T, rtol=5e-5, atol=5e-3)
+
+
 def test_gram_scales():
     rows, X = rows_of(5, 7000, seed=9)
     s = [1.0, -1.0, 0.5, 2.0, 0.0]
