@@ -261,21 +261,34 @@ class GramAggregator(Aggregator):
         out = ops.weighted_sum(all_rows, w.reshape(-1))
         return finish(out, like)
 
+    # fused device round: auxiliary rows the solver expects after the real ones, and whether a
+    # sync-free device solver exists (otherwise the round does one host round trip on G)
+    fused_aux: Tuple[str, ...] = ()
+    device_solve: bool = False
+
+    def _fused_aux(self) -> Optional[Tuple[str, ...]]:
+        """Aux rows as understood by DeviceRound, or None if this instance cannot be fused."""
+        if type(self)._aux_rows is GramAggregator._aux_rows:
+            return ()
+        return None
+
     def fused_plan(self, n: int):
         from ..parallel.device_ps import GramPlan
 
         self._validate(n)
-        if type(self)._aux_rows is not GramAggregator._aux_rows:
+        aux = self._fused_aux()
+        if aux is None:
             return None
 
         def solver(G: torch.Tensor) -> torch.Tensor:
-            w = self._solve_device(G.double(), n) if G.is_cuda else None
-            if w is None:
-                w = torch.from_numpy(np.asarray(
-                    self._solve(G.detach().double().cpu().numpy(), n), dtype=np.float32)).to(G.device)
-            return w
+            if self.device_solve and G.is_cuda:
+                w = self._solve_device(G.double(), n)
+                if w is not None:
+                    return w
+            w_np = self._solve(G.detach().double().cpu().numpy(), n)
+            return torch.from_numpy(np.asarray(w_np, dtype=np.float32)).to(G.device)
 
-        return GramPlan(solver, self.name)
+        return GramPlan(solver, self.name, aux=tuple(aux), capturable=bool(self.device_solve))
 
     # -- subtask path: split-K partial Grams -------------------------------------------
     def _gram_subtasks(self, all_rows: List[torch.Tensor], context) -> Tuple[_Packed, List[SubTask]]:

@@ -22,6 +22,10 @@ from ..base import GramAggregator
 class GeometricMedian(GramAggregator):
     name = "geometric-median"
     supports_barriered_subtasks = True
+    device_solve = True
+
+    def _fused_aux(self):
+        return ("median",) if self.init == "median" else ()
 
     def __init__(self, *, tol: float = 1e-6, max_iter: int = 256, eps: float = 1e-12,
                  init: str = "median", chunk_size: int = 32) -> None:

@@ -17,6 +17,10 @@ from ..base import GramAggregator
 class CenteredClipping(GramAggregator):
     name = "centered-clipping"
     supports_barriered_subtasks = True
+    device_solve = True
+
+    def _fused_aux(self):
+        return ("median",) if self.init == "median" else ()
 
     def __init__(self, *, c_tau: float, M: int = 10, eps: float = 1e-12, init: str = "mean",
                  chunk_size: int = 32) -> None:

@@ -138,6 +138,108 @@ __global__ void __launch_bounds__(kThreads) fused_ps_cw_kernel(const __grid_cons
   }
 }
 
+// ---------------------------------------------------------------- Gram-family pass 2 --
+__global__ void __launch_bounds__(kThreads) fused_ps_wsum_kernel(const __grid_constant__ BzFusedPsArgs a) {
+  __shared__ float ws[BZ_MAXN];
+  uint32_t* my_pad = a.pad[a.rank];
+  const uint32_t epoch = a.epoch_ptr ? *a.epoch_ptr : a.epoch;
+  const int n = a.n;
+  for (int i = threadIdx.x; i < BZ_MAXN; i += kThreads) ws[i] = (i < n) ? a.W[i] * a.scales.s[i] : 0.f;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    __threadfence_system();
+    for (int p = 0; p < a.world; ++p) st_release_sys(a.pad[p] + BZ_PAD_READY + a.rank, epoch);
+  }
+  if (!wait_all(my_pad + BZ_PAD_READY, a.world, epoch, a.status, 1)) return;
+  {
+    const long long nvec = a.shard_len / 4;
+    const long long stride = (long long)gridDim.x * kThreads;
+    for (long long u = (long long)blockIdx.x * kThreads + threadIdx.x; u < nvec; u += stride) {
+      const long long base = a.shard_off + u * 4;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int i0 = 0; i0 < n; i0 += 8) {
+        float4 x[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int i = i0 + k;
+          x[k] = (i < n && ws[i] != 0.f) ? ldg_stream4(a.rows.p[i] + base) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int i = i0 + k;
+          if (i < n) {
+            const float w = ws[i];
+            if (w != 0.f) {
+              acc[0] = fmaf(w, x[k].x, acc[0]);
+              acc[1] = fmaf(w, x[k].y, acc[1]);
+              acc[2] = fmaf(w, x[k].z, acc[2]);
+              acc[3] = fmaf(w, x[k].w, acc[3]);
+            }
+          }
+        }
+      }
+      for (int p = 0; p < a.world; ++p)
+        stg_stream4(a.agg[p] + base, make_float4(acc[0], acc[1], acc[2], acc[3]));
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const unsigned int prev = atomicAdd(a.counter, 1u);
+    if (prev == gridDim.x - 1) {
+      *a.counter = 0u;
+      __threadfence_system();
+      for (int p = 0; p < a.world; ++p) st_release_sys(a.pad[p] + BZ_PAD_DONE + a.rank, epoch);
+    }
+  }
+  if (a.upd.count <= 0 && a.world == 1) return;
+  if (!wait_all(my_pad + BZ_PAD_DONE, a.world, epoch, a.status, 2)) return;
+  if (a.upd.count > 0) {
+    const float* agg = a.agg[a.rank];
+    const long long nvec4 = a.d / 4;
+    const long long stride = (long long)gridDim.x * kThreads;
+    for (long long u = (long long)blockIdx.x * kThreads + threadIdx.x; u < nvec4; u += stride) {
+      const float4 g4 = ldg_cg4(agg + u * 4);
+      const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+      sgd_apply<4>(a.upd, u * 4, g);
+    }
+  }
+}
+
+__global__ void flag_barrier_kernel(const __grid_constant__ BzFlagBarrierArgs a) {
+  const uint32_t epoch = *a.epoch_ptr;
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    for (int p = 0; p < a.world; ++p) st_release_sys(a.pad[p] + a.slot + a.rank, epoch);
+  }
+  wait_all(a.pad[a.rank] + a.slot, a.world, epoch, a.status, 3);
+}
+
+__global__ void gram_exchange_kernel(const __grid_constant__ BzGramExchangeArgs a) {
+  const uint32_t epoch = *a.epoch_ptr;
+  const int nn = a.n * a.n;
+  for (int p = 0; p < a.world; ++p) {
+    double* dst = a.slots[p] + (size_t)a.rank * nn;
+    for (int t = threadIdx.x; t < nn; t += blockDim.x) dst[t] = a.local[t];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    for (int p = 0; p < a.world; ++p) st_release_sys(a.pad[p] + BZ_PAD_GRAM + a.rank, epoch);
+  }
+  if (!wait_all(a.pad[a.rank] + BZ_PAD_GRAM, a.world, epoch, a.status, 4)) return;
+  const double* mine = a.slots[a.rank];
+  for (int t = threadIdx.x; t < nn; t += blockDim.x) {
+    double s = 0.0;
+    for (int r = 0; r < a.world; ++r) {
+      double v;
+      asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(mine + (size_t)r * nn + t));
+      s += v;
+    }
+    a.out64[t] = s;
+    if (a.out32) a.out32[t] = (float)s;
+  }
+}
+
 template <int NP, int MODE>
 int launch_np(const BzFusedPsArgs& a, int grid, cudaStream_t stream) {
   constexpr int V = (NP <= 16) ? 4 : (NP == 32 ? 2 : 1);
@@ -177,6 +279,37 @@ __global__ void bump_u32_kernel(uint32_t* p) { *p = *p + 1u; }
 
 int bz_bump_u32(uint32_t* p, cudaStream_t stream) {
   bump_u32_kernel<<<1, 1, 0, stream>>>(p);
+  return (int)cudaGetLastError();
+}
+
+int bz_fused_ps_wsum(const BzFusedPsArgs* args, int sm_count, cudaStream_t stream) {
+  const BzFusedPsArgs& a = *args;
+  if (a.n < 1 || a.n > BZ_MAXN || a.W == nullptr || a.world < 1 || a.world > BZ_MAXW)
+    return (int)cudaErrorInvalidValue;
+  if ((a.shard_off % 4) != 0 || (a.shard_len % 4) != 0 || (a.d % 4) != 0) return (int)cudaErrorInvalidValue;
+  for (int i = 0; i < a.n; ++i)
+    if (((uintptr_t)a.rows.p[i] % 16) != 0) return (int)cudaErrorInvalidValue;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_ps_wsum_kernel, kThreads, 0) != cudaSuccess ||
+      per_sm < 1)
+    per_sm = 1;
+  if (per_sm > 4) per_sm = 4;
+  int g = per_sm * sm_count;
+  if (a.grid_limit > 0 && a.grid_limit < g) g = a.grid_limit;
+  fused_ps_wsum_kernel<<<g, kThreads, 0, stream>>>(a);
+  return (int)cudaGetLastError();
+}
+
+int bz_flag_barrier(const BzFlagBarrierArgs* args, cudaStream_t stream) {
+  if (args->world < 1 || args->world > BZ_MAXW) return (int)cudaErrorInvalidValue;
+  flag_barrier_kernel<<<1, 32, 0, stream>>>(*args);
+  return (int)cudaGetLastError();
+}
+
+int bz_gram_exchange(const BzGramExchangeArgs* args, cudaStream_t stream) {
+  if (args->world < 1 || args->world > BZ_MAXW || args->n < 1 || args->n > BZ_MAXN + 8)
+    return (int)cudaErrorInvalidValue;
+  gram_exchange_kernel<<<1, 256, 0, stream>>>(*args);
   return (int)cudaGetLastError();
 }
 

@@ -26,7 +26,36 @@ struct BzFusedPsArgs {
   int* status;              // local error word (0 == ok)
   UpdTable upd;             // local replicas to update in phase 2
   int grid_limit;           // 0 = one full co-resident wave; >0 caps the CTA count
+  const float* W;           // wsum mode: n weights on the device (output of the n-space solve)
 };
 
 int bz_fused_ps_cw(const BzFusedPsArgs* args, int sm_count, cudaStream_t stream);
 int bz_bump_u32(uint32_t* p, cudaStream_t stream);
+
+// Gram-family round pieces -------------------------------------------------------------
+// Fused  Y = W (S X)  on this rank's shard + broadcast + SGD (same protocol as bz_fused_ps_cw).
+int bz_fused_ps_wsum(const BzFusedPsArgs* args, int sm_count, cudaStream_t stream);
+
+// Device-side flag barrier: publish pad[slot + rank] = epoch on every rank, wait for all.
+struct BzFlagBarrierArgs {
+  uint32_t* pad[BZ_MAXW];
+  int rank, world;
+  int slot;                  // BZ_PAD_READY / BZ_PAD_GRAM / ...
+  const uint32_t* epoch_ptr;
+  int* status;
+};
+int bz_flag_barrier(const BzFlagBarrierArgs* args, cudaStream_t stream);
+
+// All-reduce of the (n, n) fp64 partial Gram through peer stores: write my partial into
+// slot[rank] of every rank, flag, wait, sum the `world` slots locally.
+struct BzGramExchangeArgs {
+  const double* local;       // (n, n) partial of this rank
+  double* slots[BZ_MAXW];    // per rank: world x n x n doubles (peer-mapped)
+  uint32_t* pad[BZ_MAXW];
+  int rank, world, n;
+  const uint32_t* epoch_ptr;
+  int* status;
+  double* out64;             // (n, n) total
+  float* out32;              // (n, n) total (optional)
+};
+int bz_gram_exchange(const BzGramExchangeArgs* args, cudaStream_t stream);

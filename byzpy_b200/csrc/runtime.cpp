@@ -96,6 +96,98 @@ void bz_bind_runtime(py::module_& m) {
     return v;
   });
 
+  m.def(
+      "fused_ps_wsum",
+      [](const std::vector<uint64_t>& rows, const std::vector<float>& scales, uint64_t W, long long d,
+         long long shard_off, long long shard_len, int rank, const std::vector<uint64_t>& agg,
+         const std::vector<uint64_t>& pads, uint64_t epoch_ptr, uint64_t counter, uint64_t status,
+         const std::vector<uint64_t>& upd_params, const std::vector<uint64_t>& upd_moms, float lr,
+         float mu, float wd, int sm_count, uint64_t stream, int grid_limit) {
+        BzFusedPsArgs a;
+        std::memset(&a, 0, sizeof(a));
+        if (rows.empty() || rows.size() > BZ_MAXN) throw std::invalid_argument("rows");
+        if (agg.size() != pads.size() || agg.empty() || agg.size() > BZ_MAXW)
+          throw std::invalid_argument("agg/pads");
+        for (size_t i = 0; i < BZ_MAXN; ++i) {
+          a.rows.p[i] = i < rows.size() ? as_ptr<const float>(rows[i]) : nullptr;
+          a.scales.s[i] = (i < scales.size()) ? scales[i] : 1.0f;
+        }
+        a.n = (int)rows.size();
+        a.W = as_ptr<const float>(W);
+        a.d = d;
+        a.shard_off = shard_off;
+        a.shard_len = shard_len;
+        a.rank = rank;
+        a.world = (int)agg.size();
+        for (size_t p = 0; p < agg.size(); ++p) {
+          a.agg[p] = as_ptr<float>(agg[p]);
+          a.pad[p] = as_ptr<uint32_t>(pads[p]);
+        }
+        a.epoch_ptr = as_ptr<const uint32_t>(epoch_ptr);
+        a.counter = as_ptr<unsigned int>(counter);
+        a.status = as_ptr<int>(status);
+        if (upd_params.size() > BZ_MAXR) throw std::invalid_argument("too many replicas");
+        a.upd.count = (int)upd_params.size();
+        for (size_t r = 0; r < upd_params.size(); ++r) {
+          a.upd.param[r] = as_ptr<float>(upd_params[r]);
+          a.upd.mom[r] = upd_moms.empty() ? nullptr : as_ptr<float>(upd_moms[r]);
+        }
+        a.upd.lr = lr;
+        a.upd.mu = mu;
+        a.upd.wd = wd;
+        a.grid_limit = grid_limit;
+        int e = bz_fused_ps_wsum(&a, sm_count, as_stream(stream));
+        if (e != 0)
+          throw std::runtime_error(std::string("fused_ps_wsum: CUDA error ") +
+                                   cudaGetErrorString((cudaError_t)e));
+      },
+      py::arg("rows"), py::arg("scales"), py::arg("W"), py::arg("d"), py::arg("shard_off"),
+      py::arg("shard_len"), py::arg("rank"), py::arg("agg"), py::arg("pads"), py::arg("epoch_ptr"),
+      py::arg("counter"), py::arg("status"), py::arg("upd_params"), py::arg("upd_moms"),
+      py::arg("lr"), py::arg("mu"), py::arg("wd"), py::arg("sm_count"), py::arg("stream"),
+      py::arg("grid_limit") = 0);
+
+  m.def("flag_barrier", [](const std::vector<uint64_t>& pads, int rank, int slot, uint64_t epoch_ptr,
+                           uint64_t status, uint64_t stream) {
+    BzFlagBarrierArgs a;
+    std::memset(&a, 0, sizeof(a));
+    if (pads.empty() || pads.size() > BZ_MAXW) throw std::invalid_argument("pads");
+    a.world = (int)pads.size();
+    a.rank = rank;
+    a.slot = slot;
+    for (size_t p = 0; p < pads.size(); ++p) a.pad[p] = as_ptr<uint32_t>(pads[p]);
+    a.epoch_ptr = as_ptr<const uint32_t>(epoch_ptr);
+    a.status = as_ptr<int>(status);
+    int e = bz_flag_barrier(&a, as_stream(stream));
+    if (e != 0) throw std::runtime_error("flag_barrier failed");
+  });
+
+  m.def("gram_exchange", [](uint64_t local, const std::vector<uint64_t>& slots,
+                            const std::vector<uint64_t>& pads, int rank, int n, uint64_t epoch_ptr,
+                            uint64_t status, uint64_t out64, uint64_t out32, uint64_t stream) {
+    BzGramExchangeArgs a;
+    std::memset(&a, 0, sizeof(a));
+    if (slots.size() != pads.size() || slots.empty() || slots.size() > BZ_MAXW)
+      throw std::invalid_argument("slots/pads");
+    a.local = as_ptr<const double>(local);
+    a.world = (int)slots.size();
+    a.rank = rank;
+    a.n = n;
+    for (size_t p = 0; p < slots.size(); ++p) {
+      a.slots[p] = as_ptr<double>(slots[p]);
+      a.pad[p] = as_ptr<uint32_t>(pads[p]);
+    }
+    a.epoch_ptr = as_ptr<const uint32_t>(epoch_ptr);
+    a.status = as_ptr<int>(status);
+    a.out64 = as_ptr<double>(out64);
+    a.out32 = as_ptr<float>(out32);
+    int e = bz_gram_exchange(&a, as_stream(stream));
+    if (e != 0) throw std::runtime_error("gram_exchange failed");
+  });
+  m.attr("PAD_READY") = BZ_PAD_READY;
+  m.attr("PAD_DONE") = BZ_PAD_DONE;
+  m.attr("PAD_GRAM") = BZ_PAD_GRAM;
+
   m.def("bump_u32", [](uint64_t p, uint64_t stream) {
     int e = bz_bump_u32(as_ptr<uint32_t>(p), as_stream(stream));
     if (e != 0) throw std::runtime_error("bump_u32 failed");

@@ -86,8 +86,6 @@ class ParameterServer:
             return None
         if not torch.cuda.is_available() or any(n.device.type != "cuda" for n in nodes):
             return None
-        if self.pre is not None:
-            return None  # pre-aggregated rounds use the generic path in this build
         from ...parallel.device_ps import DeviceRound, RowFold, RowLayout
 
         import torch.distributed as dist
@@ -118,7 +116,7 @@ class ParameterServer:
             f0 = virt[0].attack.fold(layout.n_honest)
             virtual_fold = RowFold("virtual", a=f0.a, b=f0.b)
         n_rows = layout.n_workers + layout.n_virtual
-        plan = self.agg.fused_plan(n_rows)
+        plan = self._fused_plan(n_rows)
         if plan is None:
             return None
         first = self.hon[0] if self.hon else self.byz[0]
@@ -130,6 +128,52 @@ class ParameterServer:
             update_byzantines=self.update_byz, device=first.device, group=group,
             amp_dtype=amp_dtype, use_cuda_graph=use_cuda_graph, worker_streams=worker_streams,
             virtual_fold=virtual_fold)
+
+    def _fused_plan(self, n_rows: int):
+        """Aggregator plan, composed in n-space with a linear pre-aggregator when present:
+        ``X' = W_p X``  =>  ``G' = W_p G W_p^T`` and final weights ``w_agg @ W_p`` -- the
+        pre-aggregated vectors are never materialised."""
+        if self.pre is None:
+            return self.agg.fused_plan(n_rows)
+        from ...parallel.device_ps import GramPlan
+        from ...pre_aggregators.base import LinearPreAggregator
+
+        if not isinstance(self.pre, LinearPreAggregator):
+            return None
+        import numpy as np
+
+        pre = self.pre
+        pre._validate(n_rows)
+        probe = pre.row_map(np.eye(n_rows) if pre.needs_gram else None, n_rows)
+        m = probe.shape[0]
+        inner = self.agg.fused_plan(m)
+        if not isinstance(inner, GramPlan) or inner.aux:
+            return None
+        state = {"W": None}
+
+        def refresh():
+            if not pre.needs_gram:
+                Wn = np.asarray(pre.row_map(None, n_rows), dtype=np.float64)
+                if state["W"] is None:
+                    state["W"] = torch.from_numpy(Wn).to(self.hon[0].device if self.hon else "cuda")
+                else:
+                    state["W"].copy_(torch.from_numpy(Wn), non_blocking=True)
+
+        def solver(G: torch.Tensor) -> torch.Tensor:
+            if pre.needs_gram:
+                Wp = torch.from_numpy(np.asarray(pre.row_map(G.detach().double().cpu().numpy(), n_rows),
+                                                 dtype=np.float64)).to(G.device)
+            else:
+                if state["W"] is None:
+                    refresh()
+                Wp = state["W"]
+            G2 = Wp @ G.double() @ Wp.T
+            w2 = inner.solver(G2)
+            return (w2.double() @ Wp).float()
+
+        return GramPlan(solver, f"{pre.name}+{inner.name}", aux=(),
+                        capturable=inner.capturable and not pre.needs_gram,
+                        refresh=None if pre.needs_gram else refresh)
 
     def step(self, batches=None) -> torch.Tensor:
         """Device path: one fused round, asynchronous on the current CUDA stream.

@@ -44,10 +44,21 @@ class CwPlan:
 
 @dataclass
 class GramPlan:
-    """Gram-family plan: pass 1 Gram, n-space solve -> weights, pass 2 weighted sum."""
+    """Gram-family plan: pass 1 Gram, n-space solve -> weights, pass 2 weighted sum.
 
-    solver: Callable[[torch.Tensor], torch.Tensor]  # (n,n) Gram on device -> (n,) weights
+    ``solver(G)`` maps the fp64 Gram of (real rows + aux rows) ON THE DEVICE to the fp32 weight
+    vector over the same rows.  ``aux`` lists auxiliary rows the solver expects after the real
+    ones (``"median"`` = coordinate-wise median of the real rows, the Weiszfeld / centered-clipping
+    start point).  ``capturable`` is False when the solver synchronises with the host (MDA, SMEA,
+    CAF searches), which rules out CUDA-graph capture of the round.  ``refresh`` (optional) is
+    called on the host before every round (e.g. to draw a new bucketing permutation).
+    """
+
+    solver: Callable[[torch.Tensor], torch.Tensor]
     name: str = "gram"
+    aux: Tuple[str, ...] = ()
+    capturable: bool = True
+    refresh: Optional[Callable[[], None]] = None
 
 
 @dataclass
@@ -196,7 +207,10 @@ class DeviceRound:
         self._off_agg = L * self.d_pad * f4
         self._off_pad = self._off_agg + self.d_pad * f4
         self._off_ctl = self._off_pad + 256
-        nbytes = self._off_ctl + 256
+        self._off_gslots = self._off_ctl + 256
+        self.nt_max = 144                       # rows + auxiliary rows of a Gram plan
+        gram_bytes = self.world * self.nt_max * self.nt_max * 8 if isinstance(plan, GramPlan) else 0
+        nbytes = self._off_gslots + gram_bytes
         self.sym = SymmetricBuffer(nbytes, self.device, group)
         self.grads = self.sym.view(torch.float32, L * self.d_pad, self._off_grads).view(L, self.d_pad)
         self.agg = self.sym.view(torch.float32, self.d_pad, self._off_agg)
@@ -222,6 +236,10 @@ class DeviceRound:
         self._side_streams = [torch.cuda.Stream(self.device) for _ in range(max(0, worker_streams - 1))]
         self._gram_ws = None
         self.launches_per_step = 0
+        if isinstance(plan, GramPlan):
+            self._setup_gram_plan()
+            if not plan.capturable:
+                self.use_cuda_graph = False
         if self.world > 1:
             dist.barrier(group=group)
         torch.cuda.synchronize(self.device)
@@ -284,20 +302,99 @@ class DeviceRound:
             )
             self.launches_per_step = 2
         elif isinstance(plan, GramPlan):
-            if self.world != 1:
-                raise NotImplementedError("Gram-family fused round is single-rank in this build")
-            rows = [self.grads[i] for i in range(self.L)]
-            G = ops.gram(rows, scales=self._scales)
-            w = plan.solver(G)
-            ops.weighted_sum(rows, w.reshape(1, -1), scales=self._scales, out=self.agg.view(1, -1),
-                             update=dict(params=[self.params[i] for i in self._upd_index()],
-                                         moms=None if self.moms is None else
-                                         [self.moms[i] for i in self._upd_index()],
-                                         lr=self.lr, momentum=self.momentum,
-                                         weight_decay=self.weight_decay))
-            self.launches_per_step = 4
+            self._launch_gram_round(stream, ctl)
         else:
             raise TypeError(f"unsupported plan {plan!r}")
+
+    # ------------------------------------------------------------- Gram-family round
+    def _setup_gram_plan(self) -> None:
+        """Static buffers of the Gram-family round (addresses must not change under graph replay)."""
+        lay = self.layout
+        dev = self.device
+        self._n_real = lay.n_workers + lay.n_virtual
+        self._n_aux = len(self.plan.aux)
+        nt = self._n_real + self._n_aux
+        if nt > self.nt_max or nt > ops.MAXN:
+            raise ValueError("too many rows for the fused Gram round")
+        self._nt = nt
+        self._virt_buf = (torch.zeros(self.d_pad, dtype=torch.float32, device=dev)
+                          if lay.n_virtual else None)
+        self._aux_bufs = [torch.zeros(self.d_pad, dtype=torch.float32, device=dev)
+                          for _ in range(self._n_aux)]
+        self._g_local64 = torch.zeros((nt, nt), dtype=torch.float64, device=dev)
+        self._g_local32 = torch.zeros((nt, nt), dtype=torch.float32, device=dev)
+        self._g_tail64 = torch.zeros((nt, nt), dtype=torch.float64, device=dev)
+        self._g_tail32 = torch.zeros((nt, nt), dtype=torch.float32, device=dev)
+        self._g_total64 = torch.zeros((nt, nt), dtype=torch.float64, device=dev)
+        self._w_dev = torch.zeros(nt, dtype=torch.float32, device=dev)
+        need = self.ext.gram_partials_needed(nt, self.sm)
+        self._gram_scratch = torch.empty(need, dtype=torch.float32, device=dev)
+        self._umma_scratch = torch.empty(self.sm * 2 * nt * nt, dtype=torch.float32, device=dev)
+        # row tables: workers (peer pointers) + virtual rows + aux rows (both local, shard-valid)
+        rows = list(self._rows)
+        scales = list(self._scales)
+        if lay.n_virtual:
+            rows += [self._virt_buf.data_ptr()] * lay.n_virtual
+            scales += [1.0] * lay.n_virtual
+        self._real_rows, self._real_scales = list(rows), list(scales)
+        for b in self._aux_bufs:
+            rows.append(b.data_ptr())
+            scales.append(1.0)
+        self._all_rows, self._all_scales = rows, scales
+
+    def _launch_gram_round(self, stream: int, ctl: int) -> None:
+        ext, lay, plan = self.ext, self.layout, self.plan
+        pads = [self.sym.peer_ptr(r, self._off_pad) for r in range(self.world)]
+        off, ln = self.shard_off, self.shard_len
+        nt = self._nt
+        launches = 1
+        # every rank's gradient rows must be complete before anybody reads them
+        ext.flag_barrier(pads, self.rank, ext.PAD_READY, ctl + 8, ctl + 4, stream)
+        launches += 1
+        if lay.n_virtual:
+            nh = lay.n_honest
+            ext.colstat(self._rows[:nh], self._scales[:nh], float(self.virtual_fold.a),
+                        float(self.virtual_fold.b), off, ln, self._virt_buf.data_ptr(), self.sm, stream)
+            launches += 1
+        for kind, buf in zip(plan.aux, self._aux_bufs):
+            if kind != "median":
+                raise ValueError(f"unknown aux row {kind!r}")
+            ext.cw_select(self._real_rows, self._real_scales, ops.MODE_MEDIAN, 0, 0, 0, 0.0, 0.0, off, ln,
+                          buf.data_ptr(), [], [], 0.0, 0.0, 0.0, self.sm, stream)
+            launches += 1
+        # pass 1: partial Gram over my coordinate shard (tcgen05 for n > 16, exact fp32 otherwise)
+        main = (ln // 64) * 64 if nt > 16 else 0
+        if main > 0:
+            tail_ptr = 0
+            if main < ln:
+                ext.gram(self._all_rows, self._all_scales, off + main, ln - main, self._gram_scratch.data_ptr(),
+                         self._gram_scratch.numel() // (nt * nt), self._g_tail32.data_ptr(),
+                         self._g_tail64.data_ptr(), self.sm, stream)
+                tail_ptr = self._g_tail64.data_ptr()
+                launches += 2
+            ext.gram_umma(self._all_rows, self._all_scales, off, main, self._umma_scratch.data_ptr(),
+                          self._umma_scratch.numel() // (2 * nt * nt), tail_ptr,
+                          self._g_local32.data_ptr(), self._g_local64.data_ptr(), self.sm, stream)
+        else:
+            ext.gram(self._all_rows, self._all_scales, off, ln, self._gram_scratch.data_ptr(),
+                     self._gram_scratch.numel() // (nt * nt), self._g_local32.data_ptr(),
+                     self._g_local64.data_ptr(), self.sm, stream)
+        launches += 2
+        # all-reduce the (nt, nt) partials through peer stores
+        ext.gram_exchange(self._g_local64.data_ptr(),
+                          [self.sym.peer_ptr(r, self._off_gslots) for r in range(self.world)], pads,
+                          self.rank, nt, ctl + 8, ctl + 4, self._g_total64.data_ptr(), 0, stream)
+        launches += 1
+        # n-space solve (device side) -> weights
+        w = plan.solver(self._g_total64)
+        self._w_dev.copy_(w.reshape(-1).to(torch.float32), non_blocking=True)
+        launches += 2
+        # pass 2: weighted sum on my shard + broadcast + SGD
+        ext.fused_ps_wsum(self._all_rows, self._all_scales, self._w_dev.data_ptr(), self.d_pad, off, ln,
+                          self.rank, [self.sym.peer_ptr(r, self._off_agg) for r in range(self.world)], pads,
+                          ctl + 8, ctl + 0, ctl + 4, self._upd_params, self._upd_moms, self.lr,
+                          self.momentum, self.weight_decay, self.sm, stream)
+        self.launches_per_step = launches + 1
 
     def _upd_index(self) -> List[int]:
         return [i for i, w in enumerate(self.workers) if w.role == "honest" or self.update_byzantines]
@@ -359,6 +456,9 @@ class DeviceRound:
             batches = [w.data() for w in self.workers]
         for w, (x, y) in zip(self.workers, batches):
             w.stage_batch(x, y)
+        refresh = getattr(self.plan, "refresh", None)
+        if refresh is not None:
+            refresh()
         if self.use_cuda_graph:
             if self._graph is None:
                 self.capture()

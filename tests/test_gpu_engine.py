@@ -227,6 +227,77 @@ def test_device_round_matches_manual_loop(graph):
     asyncio.run(ps.shutdown())
 
 
+def _run_device_vs_mirror(mk_agg, pre=None, attack="signflip", graph=True, steps=3, n_h=6, n_b=2):
+    from byzpy_b200.attacks import LittleAttack
+    from byzpy_b200.engine.node.device import DeviceByzantineNode, DeviceHonestNode
+    from byzpy_b200.engine.parameter_server.ps import ParameterServer
+
+    torch.manual_seed(1)
+    init = TinyNet().state_dict()
+
+    def mk():
+        m = TinyNet()
+        m.load_state_dict(init)
+        return m
+
+    virtual = attack == "little"
+    n_workers = n_h if virtual else n_h + n_b
+    data = [[(torch.randn(16, 20), torch.randint(0, 5, (16,))) for _ in range(steps)] for _ in range(n_workers)]
+    hon = [DeviceHonestNode(mk(), lr=0.1, momentum=0.9, device=DEV) for _ in range(n_h)]
+    if virtual:
+        byz = [DeviceByzantineNode(LittleAttack(f=n_b), device=DEV) for _ in range(n_b)]
+    else:
+        byz = [DeviceByzantineNode(SignFlipAttack(), model=mk(), lr=0.1, momentum=0.9, device=DEV) for _ in range(n_b)]
+    ps = ParameterServer(hon, byz, mk_agg(), pre_aggregator=pre, update_byzantines=True, fused=True,
+                         amp_dtype=None, use_cuda_graph=graph)
+    models = [mk().to(DEV) for _ in range(n_workers)]
+    opts = [torch.optim.SGD(m.parameters(), lr=0.1, momentum=0.9) for m in models]
+    lossf = nn.CrossEntropyLoss()
+    for t in range(steps):
+        batches = [(data[w][t][0].pin_memory(), data[w][t][1].pin_memory()) for w in range(n_workers)]
+        ps.step(batches)
+        rows = []
+        for w, m in enumerate(models):
+            m.zero_grad()
+            lossf(m(batches[w][0].to(DEV)), batches[w][1].to(DEV)).backward()
+            g = torch.cat([p.grad.reshape(-1) for p in m.parameters()])
+            rows.append(-g if (w >= n_h and not virtual) else g)
+        if virtual:
+            rows = rows + [LittleAttack(f=n_b).apply(honest_grads=rows)] * n_b
+        agg = mk_agg().aggregate(pre.pre_aggregate(rows) if pre is not None else rows)
+        for m, o in zip(models, opts):
+            off = 0
+            for p in m.parameters():
+                p.grad.copy_(agg[off:off + p.numel()].view_as(p))
+                off += p.numel()
+            o.step()
+        ps.device_round.check_status()
+        torch.testing.assert_close(ps.device_round.aggregated(), agg, rtol=2e-4, atol=2e-5)
+    mine = torch.cat([p.detach().reshape(-1) for p in hon[0].model.parameters()])
+    theirs = torch.cat([p.detach().reshape(-1) for p in models[0].parameters()])
+    torch.testing.assert_close(mine, theirs, rtol=5e-4, atol=5e-5)
+    asyncio.run(ps.shutdown())
+
+
+@pytest.mark.parametrize("name", ["multikrum", "krum", "gm_median", "gm_mean", "cclip", "cge_host", "trmean_little",
+                                  "krum_little", "bucket_krum"])
+def test_device_round_gram_family_and_folds(name):
+    from byzpy_b200.pre_aggregators import Bucketing
+
+    cases = {
+        "multikrum": dict(mk_agg=lambda: MultiKrum(f=2, q=4)),
+        "krum": dict(mk_agg=lambda: Krum(f=2)),
+        "gm_median": dict(mk_agg=lambda: GeometricMedian(tol=1e-7)),
+        "gm_mean": dict(mk_agg=lambda: GeometricMedian(init="mean", tol=1e-7)),
+        "cclip": dict(mk_agg=lambda: CenteredClipping(c_tau=0.5, M=8)),
+        "cge_host": dict(mk_agg=lambda: ComparativeGradientElimination(f=2)),       # host solve, no graph
+        "trmean_little": dict(mk_agg=lambda: CoordinateWiseTrimmedMean(f=2), attack="little"),
+        "krum_little": dict(mk_agg=lambda: MultiKrum(f=2, q=3), attack="little"),
+        "bucket_krum": dict(mk_agg=lambda: MultiKrum(f=1, q=2), pre=Bucketing(2, perm=[3, 0, 6, 1, 7, 2, 5, 4])),
+    }
+    _run_device_vs_mirror(**cases[name])
+
+
 def test_smoke_entry():
     import __graft_entry__ as g
 

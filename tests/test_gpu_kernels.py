@@ -118,17 +118,23 @@ def test_gram_umma_tcgen05_matches_fp64(n, d):
 
 
 def test_gram_umma_close_vectors_keep_distance_ranking():
-    """The precision hazard: nearly identical rows; plain TF32 would lose the ordering."""
+    """The precision hazard: clustered rows whose pairwise distances are ~1e-3 of |x|^2.  A single
+    TF32 pass (2^-11 relative error on G) would scramble them; the hi/lo split must not."""
     torch.manual_seed(0)
-    base = torch.randn(1 << 16) * 10
-    X = torch.stack([base + 1e-3 * (i + 1) * torch.randn(1 << 16) for i in range(24)])
+    base = torch.randn(1 << 16)
+    X = torch.stack([base + 0.02 * (i + 1) * torch.randn(1 << 16) for i in range(24)])
     rows = [X[i].to(dev()).contiguous() for i in range(24)]
     D = ops.sqdist_from_gram(ops.gram(rows, want64=True, impl="umma")).cpu()
     Dref = torch.cdist(X.double(), X.double()) ** 2
-    # distances are ~1e-6 of |x|^2; require 1 % agreement on them
     off = ~torch.eye(24, dtype=torch.bool)
     rel = ((D - Dref).abs() / Dref.clamp_min(1e-30))[off]
-    assert rel.max().item() < 0.05, rel.max().item()
+    assert rel.max().item() < 1e-2, rel.max().item()
+    # Krum's ranking of the rows is preserved
+    from byzpy_b200.ops import nspace
+
+    G = ops.gram(rows, want64=True, impl="umma").cpu().numpy()
+    ref_scores = nspace.krum_scores((X.double() @ X.double().T).numpy(), 4)
+    assert (nspace.krum_scores(G, 4).argsort() == ref_scores.argsort()).all()
 
 
 def test_gram_umma_scales_and_repeat_determinism():
