@@ -1,9 +1,9 @@
 // Gram matrix  G = (S X)(S X)^T  on the 5th-generation tensor cores (tcgen05 / UMMA),
-// with TMEM accumulators and TMA bulk loads.  sm_100a only.
+// with TMEM accumulators.  sm_100a only.
 //
 // Shape: M = N = n <= 128 rows (padded to M = 128, N = round_up(n, 16)), K = d (huge):
 // a split-K skinny GEMM whose cost is ONE read of the n*d matrix.  Each persistent CTA owns a
-// strided set of 64-column K chunks and accumulates all of them into the SAME TMEM
+// strided set of 32-column K tiles and accumulates all of them into the SAME TMEM
 // accumulators; per-CTA partial results are reduced in fp64 by a second tiny kernel
 // (deterministic two-stage split-K, no atomics).
 //
@@ -13,35 +13,40 @@
 // in two TMEM accumulators, and the reduction forms  G = HH + HL + HL^T  (the dropped lo lo^T
 // term is 2^-22 relative).  Two MMAs per k-step instead of three because A == B == X.
 //
-// Warp roles (192 threads):
-//   warp 0      TMA producer: per K chunk one cp.async.bulk (global -> smem, 256 B) per row,
-//               straight from the row pointer table (rows may live in peer HBM), completion
-//               tracked by an mbarrier transaction count;
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit releases the
+// Warp roles (288 threads):
+//   warp 0      TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit releases the
 //               operand stage / signals the epilogue;
-//   warps 2..5  converters: read the raw fp32 tile, split hi/lo, write the two K-major
-//               SWIZZLE_128B operand tiles (conflict-free both ways), fence.proxy.async, arrive;
-//               afterwards the same warps are the epilogue (tcgen05.ld TMEM -> registers ->
-//               per-CTA partial in global memory).
-// Three mbarrier rings: raw full/empty (TMA <-> converters), operand full/empty
-// (converters <-> MMA), accumulator full (MMA -> epilogue).
+//   warps 1..8  loaders + converters: 16-byte ld.global.nc straight from the row pointer table
+//               (rows may live in peer HBM), kept 3 tiles ahead in registers (12 x 16 B in flight
+//               per thread, ~49 KB per SM); split hi/lo; write the two K-major SWIZZLE_128B operand
+//               tiles (conflict-free), fence.proxy.async, arrive on the stage's mbarrier.
+//               Warps 1..4 are also the epilogue (tcgen05.ld TMEM -> registers -> per-CTA partial).
+// Two mbarrier rings: operand full/empty (converters <-> MMA) and accumulator full.
+//
+// Measured design note (profiles/gram_umma.md): the first version fed the converters with one
+// cp.async.bulk (TMA, UBLKCP) per row per 64-column chunk.  Bulk copies are issued through the
+// uniform datapath, ~80 cycles each, so 256-byte copies cap a CTA at ~3 B/clk (0.9 TB/s chip-wide,
+// ncu: dram 11 %, tensor 10 %).  A pointer-table of rows cannot use one 2-D tensor map, so the
+// loads moved to the LSU path above.
 #include "api.h"
 #include "gram_umma.h"
 
 namespace {
 
-constexpr int kThreads = 192;
-constexpr int kRawCols = 64;                  // fp32 columns per TMA chunk (256 B per row)
+constexpr int kConvWarps = 8;                 // converter warps (also: first 4 = epilogue)
+constexpr int kConvThreads = kConvWarps * 32;
+constexpr int kThreads = 32 + kConvThreads;   // warp 0 = TMEM allocator + MMA issuer
 constexpr int kOpCols = 32;                   // columns per operand tile (128 B swizzle row)
 constexpr int kRows = 128;                    // padded M
-constexpr int kRawStages = 3;
-constexpr int kOpStages = 3;
-constexpr int kRawStageBytes = kRows * kRawCols * 4;          // 32 KB
+constexpr int kOpStages = 4;
 constexpr int kOpTileBytes = kRows * kOpCols * 4;             // 16 KB (hi) ; lo follows
 constexpr int kOpStageBytes = 2 * kOpTileBytes;               // 32 KB
+constexpr int kPrefetch = 3;                  // operand tiles of global loads kept in flight per thread
+constexpr int kChunksPerThread = kRows * 8 / kConvThreads;    // 16-byte chunks per thread per tile (4)
 constexpr int kTmemCols = 256;                // D_hh at column 0, D_hl at column 128
-constexpr int kSmemBytes = 1024 /*align slack*/ + kRawStages * kRawStageBytes +
-                           kOpStages * kOpStageBytes + 256 /*barriers*/;
+constexpr int kPartialStageBytes = 0;
+constexpr int kSmemBytes = 1024 /*align slack*/ + kOpStages * kOpStageBytes + 256 /*barriers*/ +
+                           kPartialStageBytes;
 constexpr unsigned long long kWaitBudgetCycles = 4000000000ull;  // ~2 s: trap instead of hanging
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -52,10 +57,6 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-               : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -74,12 +75,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > kWaitBudgetCycles) __trap();
   }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
-      : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -141,32 +136,24 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 __global__ void __launch_bounds__(kThreads, 1) gram_umma_kernel(const __grid_constant__ BzGramUmmaArgs a) {
   extern __shared__ uint8_t smem_raw_[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw_ + 1023) & ~(uintptr_t)1023);
-  uint8_t* op_base = smem;                                         // kOpStages x (hi | lo)
-  uint8_t* raw_base = smem + kOpStages * kOpStageBytes;            // kRawStages x [128][64] fp32
-  uint64_t* bars = (uint64_t*)(raw_base + kRawStages * kRawStageBytes);
-  uint64_t* raw_full = bars;                    // [kRawStages]
-  uint64_t* raw_empty = bars + kRawStages;      // [kRawStages]
-  uint64_t* op_full = bars + 2 * kRawStages;    // [kOpStages]
-  uint64_t* op_empty = op_full + kOpStages;     // [kOpStages]
-  uint64_t* acc_full = op_empty + kOpStages;    // [1]
+  uint8_t* op_base = (uint8_t*)(((uintptr_t)smem_raw_ + 1023) & ~(uintptr_t)1023);   // kOpStages x (hi | lo)
+  uint64_t* bars = (uint64_t*)(op_base + kOpStages * kOpStageBytes);
+  uint64_t* op_full = bars;                     // [kOpStages]  converters -> MMA
+  uint64_t* op_empty = bars + kOpStages;        // [kOpStages]  MMA (tcgen05.commit) -> converters
+  uint64_t* acc_full = op_empty + kOpStages;    // [1]          MMA -> epilogue
   uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = a.n;
   const int n_pad = (n + 15) & ~15;
-  const long long nchunks = a.len / kRawCols;                      // full 64-column chunks only
-  long long my_chunks = 0;
-  if ((long long)blockIdx.x < nchunks) my_chunks = (nchunks - 1 - blockIdx.x) / gridDim.x + 1;
+  const long long ntiles = a.len / kOpCols;                       // full 32-column tiles only
+  long long my_tiles = 0;
+  if ((long long)blockIdx.x < ntiles) my_tiles = (ntiles - 1 - blockIdx.x) / gridDim.x + 1;
 
   // ---- one-time setup ------------------------------------------------------------------
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kRawStages; ++s) {
-      mbar_init(smem_u32(&raw_full[s]), 1);
-      mbar_init(smem_u32(&raw_empty[s]), 128);
-    }
     for (int s = 0; s < kOpStages; ++s) {
-      mbar_init(smem_u32(&op_full[s]), 128);
+      mbar_init(smem_u32(&op_full[s]), kConvThreads);
       mbar_init(smem_u32(&op_empty[s]), 1);
     }
     mbar_init(smem_u32(acc_full), 1);
@@ -176,7 +163,7 @@ __global__ void __launch_bounds__(kThreads, 1) gram_umma_kernel(const __grid_con
   for (int i = threadIdx.x; i < kOpStages * kOpStageBytes / 16; i += kThreads)
     reinterpret_cast<uint4*>(op_base)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async();
-  if (warp == 1) {
+  if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                  ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -187,28 +174,12 @@ __global__ void __launch_bounds__(kThreads, 1) gram_umma_kernel(const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================================== TMA producer ===================================
-    for (long long k = 0; k < my_chunks; ++k) {
-      const int rs = (int)(k % kRawStages);
-      const uint32_t ph = (uint32_t)((k / kRawStages) & 1);
-      mbar_wait(smem_u32(&raw_empty[rs]), ph ^ 1u);
-      const long long col = a.off + ((long long)blockIdx.x + k * gridDim.x) * kRawCols;
-      if (lane == 0) mbar_arrive_expect_tx(smem_u32(&raw_full[rs]), (uint32_t)n * kRawCols * 4);
-      __syncwarp();
-      for (int r = lane; r < n; r += 32) {
-        bulk_g2s(smem_u32(raw_base + rs * kRawStageBytes + r * (kRawCols * 4)), a.rows.p[r] + col,
-                 kRawCols * 4, smem_u32(&raw_full[rs]));
-      }
-    }
-  } else if (warp == 1) {
     // ====================================== MMA issuer ====================================
     const uint32_t idesc = make_idesc(n_pad);
     const uint32_t d_hh = tmem_base, d_hl = tmem_base + 128;
-    const long long nops = my_chunks * (kRawCols / kOpCols);
-    for (long long t = 0; t < nops; ++t) {
+    for (long long t = 0; t < my_tiles; ++t) {
       const int os = (int)(t % kOpStages);
-      const uint32_t ph = (uint32_t)((t / kOpStages) & 1);
-      mbar_wait(smem_u32(&op_full[os]), ph);
+      mbar_wait(smem_u32(&op_full[os]), (uint32_t)((t / kOpStages) & 1));
       tc_fence_after();
       if (lane == 0) {
         const uint32_t hi = smem_u32(op_base + os * kOpStageBytes);
@@ -221,50 +192,70 @@ __global__ void __launch_bounds__(kThreads, 1) gram_umma_kernel(const __grid_con
           umma_tf32(d_hh, dh, dh, idesc, acc);
           umma_tf32(d_hl, dh, dl, idesc, acc);
         }
-        umma_commit(smem_u32(&op_empty[os]));         // frees the operand stage when MMAs retire
-        if (t == nops - 1) umma_commit(smem_u32(acc_full));
+        umma_commit(smem_u32(&op_empty[os]));         // frees the operand stage when the MMAs retire
+        if (t == my_tiles - 1) umma_commit(smem_u32(acc_full));
       }
       __syncwarp();
     }
   } else {
-    // ================================== converters / epilogue =============================
-    const int cw = warp - 2;                          // 0..3
-    const int c = lane & 7, rr = lane >> 3;           // 16-byte chunk within a 128 B row, row in quad
-    long long t = 0;                                  // operand-tile counter (2 per raw chunk)
-    for (long long k = 0; k < my_chunks; ++k) {
-      const int rs = (int)(k % kRawStages);
-      mbar_wait(smem_u32(&raw_full[rs]), (uint32_t)((k / kRawStages) & 1));
-      const uint8_t* raw = raw_base + rs * kRawStageBytes;
+    // ========================= loaders / converters / epilogue ============================
+    // Each thread owns kChunksPerThread 16-byte chunks of every 128 x 32 tile: chunk q covers
+    // row q / 8, 16-byte column group q % 8.  Loads go straight from the row pointer table
+    // (local or peer HBM) into registers, kPrefetch tiles ahead of their use.
+    const int ct = threadIdx.x - 32;
+    int rows_[kChunksPerThread], cs_[kChunksPerThread];
+    const float* src_[kChunksPerThread];
 #pragma unroll
-      for (int h = 0; h < kRawCols / kOpCols; ++h, ++t) {
-        const int os = (int)(t % kOpStages);
-        mbar_wait(smem_u32(&op_empty[os]), (uint32_t)(((t / kOpStages) & 1) ^ 1));
-        uint8_t* hi = op_base + os * kOpStageBytes;
-        uint8_t* lo = hi + kOpTileBytes;
-#pragma unroll
-        for (int it = 0; it < kRows / 16; ++it) {
-          const int row = it * 16 + cw * 4 + rr;
-          if (row < n) {
-            const float4 x = *reinterpret_cast<const float4*>(raw + row * (kRawCols * 4) + h * 128 + c * 16);
-            const float xs[4] = {x.x, x.y, x.z, x.w};      // row scales are applied in the reduce
-            uint32_t hh[4], ll[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              hh[e] = to_tf32(xs[e]);
-              ll[e] = __float_as_uint(xs[e] - __uint_as_float(hh[e]));
-            }
-            const int off = (row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4);
-            *reinterpret_cast<uint4*>(hi + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-            *reinterpret_cast<uint4*>(lo + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
-          }
-        }
-        fence_proxy_async();                           // generic-proxy writes -> async proxy (UMMA)
-        mbar_arrive(smem_u32(&op_full[os]));
-      }
-      mbar_arrive(smem_u32(&raw_empty[rs]));
+    for (int j = 0; j < kChunksPerThread; ++j) {
+      const int q = j * kConvThreads + ct;
+      rows_[j] = q >> 3;
+      cs_[j] = q & 7;
+      src_[j] = (rows_[j] < n) ? a.rows.p[rows_[j]] + a.off + cs_[j] * 4 : nullptr;
     }
-    // ---- epilogue: TMEM -> registers -> per-CTA partials --------------------------------
-    if (my_chunks > 0) {
+    float4 buf[kPrefetch][kChunksPerThread];
+    auto issue = [&](long long t, int slot) {
+      const long long col = ((long long)blockIdx.x + t * gridDim.x) * kOpCols;
+#pragma unroll
+      for (int j = 0; j < kChunksPerThread; ++j)
+        if (src_[j] != nullptr) buf[slot][j] = ldg_stream4(src_[j] + col);
+    };
+#pragma unroll
+    for (int pf = 0; pf < kPrefetch; ++pf)
+      if (pf < my_tiles) issue(pf, pf);
+    for (long long t0 = 0; t0 < my_tiles; t0 += kPrefetch) {
+#pragma unroll
+      for (int slot = 0; slot < kPrefetch; ++slot) {
+        const long long t = t0 + slot;
+        if (t < my_tiles) {
+          const int os = (int)(t % kOpStages);
+          mbar_wait(smem_u32(&op_empty[os]), (uint32_t)(((t / kOpStages) & 1) ^ 1));
+          uint8_t* hi = op_base + os * kOpStageBytes;
+          uint8_t* lo = hi + kOpTileBytes;
+#pragma unroll
+          for (int j = 0; j < kChunksPerThread; ++j) {
+            if (src_[j] != nullptr) {
+              const float4 x = buf[slot][j];
+              const float xs[4] = {x.x, x.y, x.z, x.w};      // row scales are applied in the reduce
+              uint32_t hh[4], ll[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                hh[e] = to_tf32(xs[e]);
+                ll[e] = __float_as_uint(xs[e] - __uint_as_float(hh[e]));
+              }
+              const int row = rows_[j];
+              const int off = (row >> 3) * 1024 + (row & 7) * 128 + ((cs_[j] ^ (row & 7)) << 4);
+              *reinterpret_cast<uint4*>(hi + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+              *reinterpret_cast<uint4*>(lo + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+            }
+          }
+          fence_proxy_async();                         // generic-proxy writes -> async proxy (UMMA)
+          mbar_arrive(smem_u32(&op_full[os]));
+          if (t + kPrefetch < my_tiles) issue(t + kPrefetch, slot);
+        }
+      }
+    }
+    // ---- epilogue: TMEM -> registers -> per-CTA partials (first 4 converter warps) -------
+    if (my_tiles > 0 && warp <= 4) {
       mbar_wait(smem_u32(acc_full), 0);
       tc_fence_after();
       const int quad = warp & 3;                       // TMEM lane partition of this warp
@@ -291,7 +282,7 @@ __global__ void __launch_bounds__(kThreads, 1) gram_umma_kernel(const __grid_con
   // ---- teardown ------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
   }
 }
@@ -318,9 +309,9 @@ __global__ void gram_umma_reduce_kernel(const float* __restrict__ partials, int 
 }  // namespace
 
 int bz_gram_umma_grid(long long len, int sm_count) {
-  const long long nchunks = len / kRawCols;
-  if (nchunks <= 0) return 0;
-  return (int)(nchunks < sm_count ? nchunks : sm_count);
+  const long long ntiles = len / kOpCols;
+  if (ntiles <= 0) return 0;
+  return (int)(ntiles < sm_count ? ntiles : sm_count);
 }
 
 int bz_gram_umma(const BzGramUmmaArgs* args, int sm_count, cudaStream_t stream) {

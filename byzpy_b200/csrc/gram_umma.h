@@ -6,7 +6,7 @@ struct BzGramUmmaArgs {
   RowTable rows;
   ScaleTable scales;
   int n;
-  long long off, len;      // the kernel consumes floor(len / 64) * 64 columns starting at off
+  long long off, len;      // the kernel consumes floor(len / 32) * 32 columns starting at off
   float* partials;         // num_partials x 2 x n x n floats
   int num_partials;
   const double* tail64;    // optional (n, n) fp64 Gram of the remaining columns, added in the reduce

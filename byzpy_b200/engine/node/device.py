@@ -20,6 +20,7 @@ from ...attacks.base import Attack
 from ...parallel.arena import flatten_grads, write_vector_to_grads_
 from ...parallel.device_ps import DeviceWorker, RowFold
 from .base import ByzantineNode, HonestNode
+from .mixin import P2PByzantineMixin, P2PHonestMixin
 
 BatchSource = Callable[[], Tuple[torch.Tensor, torch.Tensor]]
 
@@ -133,4 +134,36 @@ class DeviceByzantineNode(ByzantineNode):
         self._opt.step()
 
 
-__all__ = ["DeviceHonestNode", "DeviceByzantineNode"]
+class DeviceP2PHonestNode(P2PHonestMixin):
+    """Honest gossip node.  Generic path: the ``P2PHonestMixin`` step functions.  Device path:
+    :class:`byzpy_b200.parallel.device_p2p.DeviceP2PRound` (fused, peer rows read over NVLink)."""
+
+    def __init__(self, model: nn.Module, aggregator, *, loss_fn: Optional[Callable] = None,
+                 pre_aggregator=None, data: Optional[BatchSource] = None, device: Optional[str] = None,
+                 preprocess: Optional[Callable] = None, name: str = "p2p-honest"):
+        self.device = torch.device(device or ("cuda" if torch.cuda.is_available() else "cpu"))
+        self.model = model.to(self.device)
+        self.criterion = loss_fn or nn.CrossEntropyLoss()
+        self.p2p_agg = aggregator
+        self.p2p_pre = pre_aggregator
+        self.data = data
+        self.preprocess = preprocess
+        self.name = name
+
+    def next_batch(self):
+        x, y = self.data()
+        x, y = x.to(self.device, non_blocking=True), y.to(self.device, non_blocking=True)
+        return (self.preprocess(x) if self.preprocess is not None else x), y
+
+    def dump_state_dict(self):
+        return {k: v.detach().cpu() for k, v in self.model.state_dict().items()}
+
+
+class DeviceP2PByzantineNode(P2PByzantineMixin):
+    def __init__(self, attack: Attack, *, device: Optional[str] = None, name: str = "p2p-byz"):
+        self.device = torch.device(device or ("cuda" if torch.cuda.is_available() else "cpu"))
+        self.attack = attack
+        self.name = name
+
+
+__all__ = ["DeviceHonestNode", "DeviceByzantineNode", "DeviceP2PHonestNode", "DeviceP2PByzantineNode"]

@@ -16,6 +16,23 @@ import torch
 from . import _load_ext, _stream
 
 
+_CONST_CACHE: dict = {}
+
+
+def _device_const(a0: np.ndarray, device: torch.device) -> torch.Tensor:
+    """Start-coefficient vectors are tiny constants: upload once per (device, value) so that no
+    host->device copy happens inside a CUDA-graph capture."""
+    arr = np.ascontiguousarray(np.asarray(a0, dtype=np.float64))
+    key = (str(device), arr.tobytes())
+    t = _CONST_CACHE.get(key)
+    if t is None:
+        if len(_CONST_CACHE) > 256:
+            _CONST_CACHE.clear()
+        t = torch.from_numpy(arr.copy()).to(device)
+        _CONST_CACHE[key] = t
+    return t
+
+
 def _ready(G: torch.Tensor, name: str):
     ext = _load_ext()
     if ext is None or not hasattr(ext, name) or not G.is_cuda or G.shape[0] > 128:
@@ -41,7 +58,7 @@ def weiszfeld_coeffs(G: torch.Tensor, n_real: int, a0: np.ndarray, *, tol: float
         return None
     nt = G.shape[0]
     G = G.contiguous().double()
-    a = torch.from_numpy(np.asarray(a0, dtype=np.float64)).to(G.device, non_blocking=True)
+    a = _device_const(a0, G.device)
     w = torch.empty(nt, dtype=torch.float32, device=G.device)
     iters = torch.zeros(1, dtype=torch.int32, device=G.device)
     ext.nspace_weiszfeld(G.data_ptr(), nt, int(n_real), a.data_ptr(), float(tol), int(max_iter),
@@ -56,7 +73,7 @@ def centered_clip_coeffs(G: torch.Tensor, n_real: int, a0: np.ndarray, *, c_tau:
         return None
     nt = G.shape[0]
     G = G.contiguous().double()
-    a = torch.from_numpy(np.asarray(a0, dtype=np.float64)).to(G.device, non_blocking=True)
+    a = _device_const(a0, G.device)
     w = torch.empty(nt, dtype=torch.float32, device=G.device)
     ext.nspace_cclip(G.data_ptr(), nt, int(n_real), a.data_ptr(), float(c_tau), int(M), float(eps),
                      w.data_ptr(), _stream(G.device))

@@ -1,7 +1,7 @@
 """Front-end of the tcgen05 / TMEM / TMA Gram kernel (``csrc/gram_umma.cu``).
 
-The tensor-core kernel consumes the first ``floor(d / 64) * 64`` columns (TMA bulk copies need
-16-byte aligned 256-byte row segments); the < 64 column tail goes through the exact fp32
+The tensor-core kernel consumes the first ``floor(d / 32) * 32`` columns (16-byte aligned 128-byte row
+segments); the < 32 column tail goes through the exact fp32
 CUDA-core kernel and is added in the fp64 reduction.  Rows that are not 16-byte aligned fall
 back to the CUDA-core kernel entirely.
 """
@@ -39,12 +39,12 @@ def gram_umma(rows: List[torch.Tensor], scales: List[float], G: torch.Tensor,
     ptrs = [r.data_ptr() for r in rows]
     sms = sm_count(dev)
     stream = _stream(dev)
-    if not supported(rows) or d < 64:
+    if not supported(rows) or d < 32:
         scratch = _gram_scratch(dev, n)
         ext.gram(ptrs, scales, 0, d, scratch.data_ptr(), scratch.numel() // (n * n), G.data_ptr(),
                  G64.data_ptr() if G64 is not None else 0, sms, stream)
         return
-    main = (d // 64) * 64
+    main = (d // 32) * 32
     tail64 = None
     if main < d:
         scratch = _gram_scratch(dev, n)

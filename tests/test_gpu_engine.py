@@ -298,6 +298,64 @@ def test_device_round_gram_family_and_folds(name):
     _run_device_vs_mirror(**cases[name])
 
 
+@pytest.mark.parametrize("name", ["trmean", "gm", "multikrum"])
+@pytest.mark.parametrize("topo", ["complete", "ring"])
+def test_device_p2p_round_matches_mixin_semantics(name, topo):
+    from byzpy_b200.engine.node.device import DeviceP2PByzantineNode, DeviceP2PHonestNode
+    from byzpy_b200.engine.node.mixin import P2PByzantineMixin
+    from byzpy_b200.engine.peer_to_peer.topology import Topology
+    from byzpy_b200.engine.peer_to_peer.train import PeerToPeer
+
+    mk_agg = {"trmean": lambda: CoordinateWiseTrimmedMean(f=1), "gm": lambda: GeometricMedian(tol=1e-7),
+              "multikrum": lambda: MultiKrum(f=1, q=2)}[name]
+    n_h, n_b, steps, lr = 5, 1, 2, 0.1
+    n = n_h + n_b
+    topology = Topology.complete(n) if topo == "complete" else Topology.ring(n, 2)
+    torch.manual_seed(2)
+    init = TinyNet().state_dict()
+
+    def mk():
+        m = TinyNet()
+        m.load_state_dict(init)
+        return m
+
+    data = [[(torch.randn(16, 20), torch.randint(0, 5, (16,))) for _ in range(steps)] for _ in range(n_h)]
+    hon = [DeviceP2PHonestNode(mk(), mk_agg(), device=DEV) for _ in range(n_h)]
+    byz = [DeviceP2PByzantineNode(EmpireAttack(scale=-2.0), device=DEV) for _ in range(n_b)]
+    p2p = PeerToPeer(hon, byz, topology, lr=lr, fused=True, amp_dtype=None, use_cuda_graph=True)
+    assert p2p.device_round is not None
+    mirrors = [mk().to(DEV) for _ in range(n_h)]
+    lossf = nn.CrossEntropyLoss()
+    for t in range(steps):
+        batches = [(data[i][t][0].pin_memory(), data[i][t][1].pin_memory()) for i in range(n_h)] + [None] * n_b
+        p2p.step(batches)
+        halves = []
+        for i, m in enumerate(mirrors):
+            m.zero_grad()
+            lossf(m(batches[i][0].to(DEV)), batches[i][1].to(DEV)).backward()
+            with torch.no_grad():
+                for p in m.parameters():
+                    p.add_(p.grad, alpha=-lr)
+            halves.append(torch.cat([p.detach().reshape(-1) for p in m.parameters()]))
+        vec = {i: halves[i] for i in range(n_h)}
+        for j in range(n_h, n):
+            seen = [halves[k] for k in dict.fromkeys(topology.in_[j]) if k < n_h]
+            vec[j] = EmpireAttack(scale=-2.0).apply(honest_grads=seen)
+        for i, m in enumerate(mirrors):
+            rows = [vec[i]] + [vec[k] for k in dict.fromkeys(topology.in_[i]) if k != i]
+            new = mk_agg().aggregate(rows)
+            off = 0
+            with torch.no_grad():
+                for p in m.parameters():
+                    p.copy_(new[off:off + p.numel()].view_as(p))
+                    off += p.numel()
+        p2p.device_round.check_status()
+        for i, m in enumerate(mirrors):
+            theirs = torch.cat([p.detach().reshape(-1) for p in m.parameters()])
+            torch.testing.assert_close(p2p.device_round.param_vector(i), theirs, rtol=2e-4, atol=2e-5)
+    asyncio.run(p2p.shutdown())
+
+
 def test_smoke_entry():
     import __graft_entry__ as g
 
