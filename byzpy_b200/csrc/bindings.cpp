@@ -185,6 +185,8 @@ PYBIND11_MODULE(_C, m) {
   });
 
   m.def("gram_umma_grid", &bz_gram_umma_grid);
+  m.def("gram_umma_tile_cols", &bz_gram_umma_tile_cols);
+  m.def("gram_umma_partials", &bz_gram_umma_partials);
   m.def(
       "gram_umma",
       [](const std::vector<uint64_t>& rows, const std::vector<float>& scales, long long off,

@@ -7,6 +7,12 @@
 // accumulators; per-CTA partial results are reduced in fp64 by a second tiny kernel
 // (deterministic two-stage split-K, no atomics).
 //
+// Block-diagonal packing: the MMA atom is always M = N = 128.  For n < 128 the 128 operand rows hold
+// B = 128 / n_pad different 32-column blocks of the SAME n rows (n_pad = n rounded up to 16/32/64/128),
+// i.e. one tile covers 32*B columns.  The 128 x 128 product then contains the B partial Grams on
+// its diagonal n_pad x n_pad blocks (off-diagonal blocks are cross terms and are ignored), so the
+// bytes moved per MMA are the same 16 KB for every n and the kernel runs at the n = 128 rate.
+//
 // Precision (SURVEY 7.1 "precision hazard"): kind::tf32 keeps 10 mantissa bits, which is not
 // enough for G_ii + G_jj - 2 G_ij when gradients are close.  Every fp32 value is split
 // x = hi + lo with hi = rna_tf32(x); the kernel accumulates  HH = hi hi^T  and  HL = hi lo^T
@@ -145,15 +151,17 @@ __global__ void __launch_bounds__(kThreads, 1) gram_umma_kernel(const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = a.n;
-  const int n_pad = (n + 15) & ~15;
-  const long long ntiles = a.len / kOpCols;                       // full 32-column tiles only
+  const int n_pad = a.n_pad;                                      // 16 / 32 / 64 / 128
+  const int nblk = kRows / n_pad;                                 // column blocks packed per tile
+  const int tile_cols = kOpCols * nblk;
+  const long long ntiles = a.len / tile_cols;                     // full tiles only
   long long my_tiles = 0;
   if ((long long)blockIdx.x < ntiles) my_tiles = (ntiles - 1 - blockIdx.x) / gridDim.x + 1;
 
   // ---- one-time setup ------------------------------------------------------------------
   if (threadIdx.x == 0) {
     for (int s = 0; s < kOpStages; ++s) {
-      mbar_init(smem_u32(&op_full[s]), kConvThreads);
+      mbar_init(smem_u32(&op_full[s]), kConvWarps);
       mbar_init(smem_u32(&op_empty[s]), 1);
     }
     mbar_init(smem_u32(acc_full), 1);
@@ -175,7 +183,7 @@ __global__ void __launch_bounds__(kThreads, 1) gram_umma_kernel(const __grid_con
 
   if (warp == 0) {
     // ====================================== MMA issuer ====================================
-    const uint32_t idesc = make_idesc(n_pad);
+    const uint32_t idesc = make_idesc(kRows);
     const uint32_t d_hh = tmem_base, d_hl = tmem_base + 128;
     for (long long t = 0; t < my_tiles; ++t) {
       const int os = (int)(t % kOpStages);
@@ -208,13 +216,14 @@ __global__ void __launch_bounds__(kThreads, 1) gram_umma_kernel(const __grid_con
 #pragma unroll
     for (int j = 0; j < kChunksPerThread; ++j) {
       const int q = j * kConvThreads + ct;
-      rows_[j] = q >> 3;
+      rows_[j] = q >> 3;                               // tile row = block * n_pad + data row
       cs_[j] = q & 7;
-      src_[j] = (rows_[j] < n) ? a.rows.p[rows_[j]] + a.off + cs_[j] * 4 : nullptr;
+      const int blk = rows_[j] / n_pad, drow = rows_[j] % n_pad;
+      src_[j] = (drow < n) ? a.rows.p[drow] + a.off + blk * kOpCols + cs_[j] * 4 : nullptr;
     }
     float4 buf[kPrefetch][kChunksPerThread];
     auto issue = [&](long long t, int slot) {
-      const long long col = ((long long)blockIdx.x + t * gridDim.x) * kOpCols;
+      const long long col = ((long long)blockIdx.x + t * gridDim.x) * tile_cols;
 #pragma unroll
       for (int j = 0; j < kChunksPerThread; ++j)
         if (src_[j] != nullptr) buf[slot][j] = ldg_stream4(src_[j] + col);
@@ -249,7 +258,8 @@ __global__ void __launch_bounds__(kThreads, 1) gram_umma_kernel(const __grid_con
             }
           }
           fence_proxy_async();                         // generic-proxy writes -> async proxy (UMMA)
-          mbar_arrive(smem_u32(&op_full[os]));
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&op_full[os]));   // one arrival per converter warp
           if (t + kPrefetch < my_tiles) issue(t + kPrefetch, slot);
         }
       }
@@ -259,20 +269,22 @@ __global__ void __launch_bounds__(kThreads, 1) gram_umma_kernel(const __grid_con
       mbar_wait(smem_u32(acc_full), 0);
       tc_fence_after();
       const int quad = warp & 3;                       // TMEM lane partition of this warp
-      const int row = quad * 32 + lane;
-      float* PA = a.partials + (size_t)blockIdx.x * 2 * n * n;
+      const int trow = quad * 32 + lane;               // accumulator row owned by this thread
+      const int blk = trow / n_pad, drow = trow % n_pad;
+      // partial layout: [cta][block][HH | HL][n][n]
+      float* PA = a.partials + ((size_t)blockIdx.x * nblk + blk) * 2 * n * n;
       float* PB = PA + (size_t)n * n;
       for (int c0 = 0; c0 < n_pad; c0 += 16) {
         uint32_t va[16], vb[16];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(blk * n_pad + c0);
         tmem_ld16(taddr, va);
         tmem_ld16(taddr + 128, vb);
-        if (row < n) {
+        if (drow < n) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             if (c0 + j < n) {
-              PA[row * n + c0 + j] = __uint_as_float(va[j]);
-              PB[row * n + c0 + j] = __uint_as_float(vb[j]);
+              PA[drow * n + c0 + j] = __uint_as_float(va[j]);
+              PB[drow * n + c0 + j] = __uint_as_float(vb[j]);
             }
           }
         }
@@ -308,11 +320,17 @@ __global__ void gram_umma_reduce_kernel(const float* __restrict__ partials, int 
 
 }  // namespace
 
-int bz_gram_umma_grid(long long len, int sm_count) {
-  const long long ntiles = len / kOpCols;
+int bz_gram_umma_npad(int n) { return n <= 16 ? 16 : (n <= 32 ? 32 : (n <= 64 ? 64 : 128)); }
+
+int bz_gram_umma_tile_cols(int n) { return kOpCols * (kRows / bz_gram_umma_npad(n)); }
+
+int bz_gram_umma_grid(int n, long long len, int sm_count) {
+  const long long ntiles = len / bz_gram_umma_tile_cols(n);
   if (ntiles <= 0) return 0;
   return (int)(ntiles < sm_count ? ntiles : sm_count);
 }
+
+int bz_gram_umma_partials(int n, int grid) { return grid * (kRows / bz_gram_umma_npad(n)); }
 
 int bz_gram_umma(const BzGramUmmaArgs* args, int sm_count, cudaStream_t stream) {
   const BzGramUmmaArgs& a = *args;
@@ -320,8 +338,11 @@ int bz_gram_umma(const BzGramUmmaArgs* args, int sm_count, cudaStream_t stream) 
   if ((a.off % 4) != 0) return (int)cudaErrorInvalidValue;
   for (int i = 0; i < a.n; ++i)
     if (((uintptr_t)a.rows.p[i] % 16) != 0) return (int)cudaErrorInvalidValue;
-  const int grid = bz_gram_umma_grid(a.len, sm_count);
-  if (grid > a.num_partials) return (int)cudaErrorInvalidValue;
+  BzGramUmmaArgs b = *args;
+  b.n_pad = bz_gram_umma_npad(a.n);
+  const int grid = bz_gram_umma_grid(a.n, a.len, sm_count);
+  const int nparts = bz_gram_umma_partials(a.n, grid);
+  if (nparts > a.num_partials) return (int)cudaErrorInvalidValue;
   if (grid > 0) {
     static bool configured = false;
     if (!configured) {
@@ -330,12 +351,12 @@ int bz_gram_umma(const BzGramUmmaArgs* args, int sm_count, cudaStream_t stream) 
       if (e != cudaSuccess) return (int)e;
       configured = true;
     }
-    gram_umma_kernel<<<grid, kThreads, kSmemBytes, stream>>>(a);
+    gram_umma_kernel<<<grid, kThreads, kSmemBytes, stream>>>(b);
     int e = (int)cudaGetLastError();
     if (e) return e;
   }
   const int rt = 128;
   gram_umma_reduce_kernel<<<(a.n * a.n + rt - 1) / rt, rt, 0, stream>>>(
-      a.partials, grid, a.n, a.scales, a.tail64, a.G, a.G64);
+      a.partials, nparts, a.n, a.scales, a.tail64, a.G, a.G64);
   return (int)cudaGetLastError();
 }

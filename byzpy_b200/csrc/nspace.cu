@@ -43,27 +43,35 @@ __device__ __forceinline__ double sqdist_entry(const double* G, int nt, int i, i
   return d < 0.0 ? 0.0 : d;
 }
 
-__global__ void __launch_bounds__(kT) krum_kernel(const double* __restrict__ G, int n, int f, int q,
-                                                 float* __restrict__ w) {
-  __shared__ double score[kT];
-  const int i = threadIdx.x;
-  const int keep = n - f;  // entries of the sorted row (self included) that are summed, minus self
-  double s = 0.0;
-  if (i < n) {
-    for (int j = 0; j < n; ++j) {
-      const double dj = sqdist_entry(G, n, i, j);
-      int rank = 0;
-      for (int k = 0; k < n; ++k) {
-        const double dk = sqdist_entry(G, n, i, k);
-        rank += (dk < dj || (dk == dj && k < j)) ? 1 : 0;
-      }
-      // sorted positions 1 .. n-f-1 (position 0 is the zero self-distance)
-      if (rank >= 1 && rank < keep) s += dj;
-    }
-  }
-  score[i] = s;
+// 1024 threads; D (n x n, fp64) and the scores live in dynamic shared memory.
+//   phase 1: D_ij from the Gram matrix;
+//   phase 2: one (i, j) pair per thread-iteration: rank of D_ij inside row i by counting
+//            (ties -> lower index first), entries of rank 1 .. n-f-1 are added to score_i;
+//   phase 3: rank of score_i among the scores; the q best get weight 1/q.
+__global__ void __launch_bounds__(1024) krum_kernel(const double* __restrict__ G, int n, int f, int q,
+                                                   float* __restrict__ w) {
+  extern __shared__ double sm[];
+  double* D = sm;                 // n * n
+  double* score = sm + n * n;     // n
+  const int nn = n * n;
+  for (int t = threadIdx.x; t < nn; t += blockDim.x) D[t] = sqdist_entry(G, n, t / n, t % n);
+  for (int t = threadIdx.x; t < n; t += blockDim.x) score[t] = 0.0;
   __syncthreads();
-  if (i < n) {
+  const int keep = n - f;         // sorted positions 1 .. n-f-1 are summed (position 0 = self)
+  for (int t = threadIdx.x; t < nn; t += blockDim.x) {
+    const int i = t / n, j = t % n;
+    const double* row = D + i * n;
+    const double dj = row[j];
+    int rank = 0;
+    for (int k = 0; k < n; ++k) {
+      const double dk = row[k];
+      rank += (dk < dj || (dk == dj && k < j)) ? 1 : 0;
+    }
+    if (rank >= 1 && rank < keep) atomicAdd(&score[i], dj);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double s = score[i];
     int rank = 0;
     for (int k = 0; k < n; ++k) rank += (score[k] < s || (score[k] == s && k < i)) ? 1 : 0;
     w[i] = rank < q ? (float)(1.0 / (double)q) : 0.f;
@@ -147,7 +155,15 @@ __global__ void __launch_bounds__(kT) cclip_kernel(const double* __restrict__ G,
 
 int bz_nspace_krum(const double* G, int n, int f, int q, float* w, cudaStream_t stream) {
   if (n < 1 || n > BZ_MAXN || f < 0 || q < 1) return (int)cudaErrorInvalidValue;
-  krum_kernel<<<1, kT, 0, stream>>>(G, n, f, q, w);
+  const int smem = (n * n + n) * (int)sizeof(double);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(krum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (BZ_MAXN * BZ_MAXN + BZ_MAXN) * (int)sizeof(double));
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  krum_kernel<<<1, 1024, smem, stream>>>(G, n, f, q, w);
   return (int)cudaGetLastError();
 }
 

@@ -105,8 +105,12 @@ class ParallelScheduler:
         tensors: List[Any] = []
         if use_streams:
             _cuda_tensors(inputs, tensors)
+        tracer = base_metadata.get("tracer")
         if not tensors:
-            return node_name, await node.op.run(inputs, context=ctx, pool=self.pool)
+            if tracer is None:
+                return node_name, await node.op.run(inputs, context=ctx, pool=self.pool)
+            with tracer.span(f"node:{node_name}", op=node.op.name):
+                return node_name, await node.op.run(inputs, context=ctx, pool=self.pool)
         import torch
 
         dev = tensors[0].device

@@ -67,10 +67,15 @@ class NodeScheduler:
     async def run(self, inputs: Mapping[str, Any]) -> Dict[str, Any]:
         self._check_inputs(inputs)
         cache: Dict[str, Any] = dict(inputs)
+        tracer = self.metadata.get("tracer")
         for node in self.graph.nodes_in_order():
             ctx = OpContext(node_name=node.name, metadata=self._node_metadata())
-            cache[node.name] = await node.op.run(self._resolve_inputs(node, cache), context=ctx,
-                                                 pool=self.pool)
+            bound = self._resolve_inputs(node, cache)
+            if tracer is None:
+                cache[node.name] = await node.op.run(bound, context=ctx, pool=self.pool)
+            else:
+                with tracer.span(f"node:{node.name}", op=node.op.name):
+                    cache[node.name] = await node.op.run(bound, context=ctx, pool=self.pool)
         return {name: cache[name] for name in self.graph.outputs}
 
 

@@ -53,7 +53,8 @@ class ParameterServer:
                  actor_pool=None, scheduler_metadata: Optional[dict] = None, layout=None,
                  process_group=None, lr: Optional[float] = None, momentum: Optional[float] = None,
                  weight_decay: Optional[float] = None, amp_dtype: Optional[torch.dtype] = torch.bfloat16,
-                 use_cuda_graph: bool = True, worker_streams: int = 1, fused: Optional[bool] = None):
+                 use_cuda_graph: bool = True, worker_streams: int = 1, fused: Optional[bool] = None,
+                 node_timeout: Optional[float] = None, tolerate_failures: bool = False):
         self.hon = list(honest_nodes)
         self.byz = list(byzantine_nodes)
         self.agg = aggregator
@@ -62,6 +63,12 @@ class ParameterServer:
         self.pool = actor_pool
         self.scheduler = None
         self.rounds = 0
+        # failure detection (the reference has none: a hung actor hangs the round):
+        # a node that raises or exceeds ``node_timeout`` is treated as silent for that round when
+        # ``tolerate_failures`` is set; ``failed`` records (round, node index, reason).
+        self.node_timeout = node_timeout
+        self.tolerate_failures = tolerate_failures
+        self.failed: List[tuple] = []
         if actor_pool is not None:
             from ..graph.ops import make_single_operator_graph
             from ..graph.scheduler import NodeScheduler
@@ -184,15 +191,29 @@ class ParameterServer:
         return self.device_round.step(batches)
 
     # ------------------------------------------------------------------- generic path
+    async def _guarded(self, kind: str, idx: int, node: Any, method: str, *args):
+        try:
+            coro = _call(node, method, *args)
+            if self.node_timeout is not None:
+                return await asyncio.wait_for(coro, timeout=self.node_timeout)
+            return await coro
+        except Exception as exc:  # noqa: BLE001
+            if not self.tolerate_failures:
+                raise
+            self.failed.append((self.rounds, f"{kind}:{idx}", repr(exc)))
+            return None
+
     async def _gather_honest(self) -> List[torch.Tensor]:
-        return list(await asyncio.gather(
-            *[_call(h, "honest_gradient_for_next_batch") for h in self.hon]))
+        got = await asyncio.gather(*[self._guarded("honest", i, h, "honest_gradient_for_next_batch")
+                                     for i, h in enumerate(self.hon)])
+        return [g for g in got if g is not None]
 
     async def _gather_byzantine(self, honest: Sequence[torch.Tensor]) -> List[torch.Tensor]:
         if not self.byz:
             return []
-        return list(await asyncio.gather(
-            *[_call(b, "byzantine_gradient_for_next_batch", honest) for b in self.byz]))
+        got = await asyncio.gather(*[self._guarded("byzantine", i, b, "byzantine_gradient_for_next_batch", honest)
+                                     for i, b in enumerate(self.byz)])
+        return [g for g in got if g is not None]
 
     async def round(self) -> torch.Tensor:
         if self.device_round is not None:
@@ -200,14 +221,19 @@ class ParameterServer:
             return self.device_round.aggregated()
         grads = await self._gather_honest()
         grads += await self._gather_byzantine(tuple(grads))
+        if not grads:
+            raise RuntimeError("no gradients were collected this round (all nodes failed)")
         if self.pre is not None:
             grads = list(self.pre.pre_aggregate(grads))
         if self.scheduler is not None:
             g = (await self.scheduler.run({"gradients": grads}))["agg"]
         else:
             g = self.agg.aggregate(grads)
+        if not grads:
+            raise RuntimeError("no gradients were collected this round (all nodes failed)")
         targets = self.hon + (self.byz if self.update_byz else [])
-        await asyncio.gather(*[_call(n, "apply_server_gradient", g) for n in targets])
+        await asyncio.gather(*[self._guarded("apply", i, n, "apply_server_gradient", g)
+                               for i, n in enumerate(targets)])
         self.rounds += 1
         return g
 

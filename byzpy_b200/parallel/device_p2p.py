@@ -165,7 +165,7 @@ class DeviceP2PRound:
             ws["T64"] = torch.zeros((nt, nt), dtype=torch.float64, device=dev)
             ws["W"] = torch.zeros(nt, dtype=torch.float32, device=dev)
             ws["scratch"] = torch.empty(self.ext.gram_partials_needed(nt, self.sm), dtype=torch.float32, device=dev)
-            ws["umma"] = torch.empty(self.sm * 2 * nt * nt, dtype=torch.float32, device=dev)
+            ws["umma"] = torch.empty(self.sm * 8 * 2 * nt * nt, dtype=torch.float32, device=dev)
             ws["nt"] = nt
         return ws
 
@@ -210,7 +210,8 @@ class DeviceP2PRound:
                           0.0, 0.0, self.sm, stream)
             all_rows.append(buf.data_ptr())
         nt = ws["nt"]
-        main = (d // 64) * 64 if nt > 16 else 0
+        tc = ext.gram_umma_tile_cols(nt)
+        main = (d // tc) * tc if nt > 16 else 0
         if main > 0:
             tail = 0
             if main < d:

@@ -329,7 +329,7 @@ class DeviceRound:
         self._w_dev = torch.zeros(nt, dtype=torch.float32, device=dev)
         need = self.ext.gram_partials_needed(nt, self.sm)
         self._gram_scratch = torch.empty(need, dtype=torch.float32, device=dev)
-        self._umma_scratch = torch.empty(self.sm * 2 * nt * nt, dtype=torch.float32, device=dev)
+        self._umma_scratch = torch.empty(self.sm * 8 * 2 * nt * nt, dtype=torch.float32, device=dev)
         # row tables: workers (peer pointers) + virtual rows + aux rows (both local, shard-valid)
         rows = list(self._rows)
         scales = list(self._scales)
@@ -363,7 +363,8 @@ class DeviceRound:
                           buf.data_ptr(), [], [], 0.0, 0.0, 0.0, self.sm, stream)
             launches += 1
         # pass 1: partial Gram over my coordinate shard (tcgen05 for n > 16, exact fp32 otherwise)
-        main = (ln // 64) * 64 if nt > 16 else 0
+        tc = ext.gram_umma_tile_cols(nt)
+        main = (ln // tc) * tc if nt > 16 else 0
         if main > 0:
             tail_ptr = 0
             if main < ln:

@@ -255,3 +255,84 @@ def test_param_arena_views_and_layout():
     assert torch.equal(next(m.parameters()).reshape(-1)[:3], torch.full((3,), 7.0))
     arena.zero_grad()
     assert all(p.grad.abs().sum() == 0 for p in m.parameters())
+
+
+class Flaky(Hon):
+    def __init__(self, seed, mode):
+        super().__init__(seed)
+        self.mode = mode
+
+    def honest_gradient(self, x, y):
+        if self.mode == "raise":
+            raise RuntimeError("node crashed")
+        if self.mode == "hang":
+            import time
+
+            time.sleep(1.0)
+        return super().honest_gradient(x, y)
+
+
+def test_parameter_server_failure_detection_and_fault_injection():
+    async def scenario():
+        hon = [await HonestNodeActor.spawn(Hon, backend="thread", args=(i,)) for i in range(3)]
+        hon.append(await HonestNodeActor.spawn(Flaky, backend="thread", args=(7, "raise")))
+        hon.append(await HonestNodeActor.spawn(Flaky, backend="thread", args=(8, "hang")))
+        strict = ParameterServer(hon[:4], [], CoordinateWiseMedian())
+        with pytest.raises(Exception):
+            await strict.round()
+        ps = ParameterServer(hon, [], CoordinateWiseMedian(), node_timeout=0.2, tolerate_failures=True)
+        g = await ps.round()
+        rows = [Hon(i).honest_gradient_for_next_batch() for i in range(3)]
+        # the strict server consumed one batch of nodes 0..2 already: regenerate their second batch
+        mirrors = [Hon(i) for i in range(3)]
+        for m in mirrors:
+            m.honest_gradient_for_next_batch()
+        rows = [m.honest_gradient_for_next_batch() for m in mirrors]
+        assert torch.allclose(g, CoordinateWiseMedian().aggregate(rows))
+        kinds = sorted(f[1] for f in ps.failed if f[1].startswith("honest"))
+        assert kinds == ["honest:3", "honest:4"]
+        await asyncio.sleep(1.0)
+        for a in hon:
+            await a.close()
+
+    run(scenario())
+
+
+def test_checkpoint_roundtrip_generic_nodes(tmp_path):
+    from byzpy_b200.utils.checkpoint import load_checkpoint, save_checkpoint
+
+    torch.manual_seed(0)
+
+    def src():
+        return torch.randn(8, 6), torch.randint(0, 3, (8,))
+
+    def build():
+        hon = [DeviceHonestNode(nn.Linear(6, 3), data=src, lr=0.1, momentum=0.9, device="cpu") for _ in range(3)]
+        return ParameterServer(hon, [], CoordinateWiseMedian())
+
+    ps = build()
+    for _ in range(3):
+        ps.round_sync()
+    path = str(tmp_path / "ck.pt")
+    save_checkpoint(path, ps)
+    ps2 = build()
+    assert load_checkpoint(path, ps2) == 3 and ps2.rounds == 3
+    for a, b in zip(ps.hon, ps2.hon):
+        assert torch.equal(flatten_params(a.model), flatten_params(b.model))
+    blob = torch.load(path, weights_only=False)
+    # the per-node snapshot is exactly the reference's dump_state_dict() mapping
+    nn.Linear(6, 3).load_state_dict(blob["nodes"][0]["state_dict"], strict=True)
+
+
+def test_tracer_records_graph_nodes():
+    from byzpy_b200.engine.graph.ops import make_single_operator_graph
+    from byzpy_b200.engine.graph.scheduler import NodeScheduler
+    from byzpy_b200.utils.tracing import Tracer, nvtx_range
+
+    tr = Tracer(cuda=False)
+    g = make_single_operator_graph(node_name="agg", operator=CoordinateWiseMedian(), input_keys=("gradients",))
+    run(NodeScheduler(g, metadata={"tracer": tr}).run({"gradients": [torch.randn(5) for _ in range(3)]}))
+    summ = tr.summary()
+    assert summ["node:agg"]["calls"] == 1 and summ["node:agg"]["host_ms"] > 0
+    with nvtx_range("noop"):
+        pass
