@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "api.h"
+#include "bn.h"
 #include "gram_umma.h"
 #include "nspace.h"
 #include "runtime.h"
@@ -184,6 +185,57 @@ PYBIND11_MODULE(_C, m) {
     check(bz_sgd(as_ptr<const float>(grad), &u, len, sm_count, as_stream(stream)), "sgd");
   });
 
+  m.def("bn_partial_blocks", &bz_bn_partial_blocks);
+  m.def(
+      "bn_forward",
+      [](uint64_t x, uint64_t y, long long R, int C, uint64_t gamma, uint64_t beta, uint64_t rmean,
+         uint64_t rvar, uint64_t mean, uint64_t invstd, uint64_t scale, uint64_t shift, uint64_t partial,
+         float eps, float momentum, int relu, int training, int sm_count, uint64_t stream) {
+        BzBnArgs a;
+        std::memset(&a, 0, sizeof(a));
+        a.x = as_ptr<const void>(x);
+        a.y = as_ptr<void>(y);
+        a.R = R;
+        a.C = C;
+        a.gamma = as_ptr<const float>(gamma);
+        a.beta = as_ptr<const float>(beta);
+        a.running_mean = as_ptr<float>(rmean);
+        a.running_var = as_ptr<float>(rvar);
+        a.mean = as_ptr<float>(mean);
+        a.invstd = as_ptr<float>(invstd);
+        a.scale = as_ptr<float>(scale);
+        a.shift = as_ptr<float>(shift);
+        a.partial = as_ptr<float>(partial);
+        a.eps = eps;
+        a.momentum = momentum;
+        a.relu = relu;
+        a.training = training;
+        check(bz_bn_forward(&a, sm_count, as_stream(stream)), "bn_forward");
+      });
+  m.def(
+      "bn_backward",
+      [](uint64_t x, uint64_t dy, uint64_t dx, long long R, int C, uint64_t gamma, uint64_t mean,
+         uint64_t invstd, uint64_t scale, uint64_t shift, uint64_t partial, uint64_t dgamma,
+         uint64_t dbeta, uint64_t coef, int relu, int sm_count, uint64_t stream) {
+        BzBnArgs a;
+        std::memset(&a, 0, sizeof(a));
+        a.x = as_ptr<const void>(x);
+        a.dy = as_ptr<const void>(dy);
+        a.dx = as_ptr<void>(dx);
+        a.R = R;
+        a.C = C;
+        a.gamma = as_ptr<const float>(gamma);
+        a.mean = as_ptr<float>(mean);
+        a.invstd = as_ptr<float>(invstd);
+        a.scale = as_ptr<float>(scale);
+        a.shift = as_ptr<float>(shift);
+        a.partial = as_ptr<float>(partial);
+        a.dgamma = as_ptr<float>(dgamma);
+        a.dbeta = as_ptr<float>(dbeta);
+        a.coef = as_ptr<float>(coef);
+        a.relu = relu;
+        check(bz_bn_backward(&a, sm_count, as_stream(stream)), "bn_backward");
+      });
   m.def("gram_umma_grid", &bz_gram_umma_grid);
   m.def("gram_umma_tile_cols", &bz_gram_umma_tile_cols);
   m.def("gram_umma_partials", &bz_gram_umma_partials);

@@ -1,0 +1,270 @@
+// Fused training-mode BatchNorm(+ReLU) for NHWC bf16 activations (fp32 statistics / parameters).
+//
+// Why it is in this library: in the headline workload (ResNet-18 replicas, per-worker batch 32)
+// ATen's channels-last batch-norm kernels are 37 % of the device time of a parameter-server round
+// (profiles/bench_log.md): PyTorch routes bf16 NHWC batch norm to its native kernels (cuDNN's fused
+// NHWC path is fp16-only there), which are latency bound at ~25 us per call on 13-50 MB
+// activations that stream in 2-8 us.  The kernels below are plain streaming kernels:
+//
+//   forward   stats_partial  : per-CTA partial (sum, sum of squares) per channel, 16-byte loads
+//             stats_finalize : mean / invstd / running statistics, fused scale+shift
+//             apply          : y = [relu](x * scale[c] + shift[c])
+//   backward  bwd_partial    : per-CTA partial (sum dy', sum dy' * xhat), dy' = dy * [z > 0] (ReLU
+//                              mask recomputed from x, the forward output is not needed)
+//             bwd_finalize   : dgamma, dbeta, per-channel coefficients
+//             bwd_apply      : dx = a * (dy' - c1 - xhat * c2)
+//
+// Activations are [R = N*H*W rows][C channels] with C % 8 == 0 (every ResNet width).
+#include <cuda_bf16.h>
+
+#include "bn.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct alignas(16) Bf8 {
+  __nv_bfloat162 v[4];
+};
+
+__device__ __forceinline__ void unpack(const Bf8& p, float (&f)[8]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 t = __bfloat1622float2(p.v[k]);
+    f[2 * k] = t.x;
+    f[2 * k + 1] = t.y;
+  }
+}
+__device__ __forceinline__ Bf8 pack(const float (&f)[8]) {
+  Bf8 p;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) p.v[k] = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+  return p;
+}
+
+// Thread layout shared by the two reduction kernels: cg = C / 8 channel groups along x,
+// rows_per_iter = kThreads / cg row lanes; each CTA owns a contiguous slab of rows.
+template <bool BWD>
+__global__ void __launch_bounds__(kThreads) reduce_partial_kernel(
+    const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, long long R, int C,
+    const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+    const float* __restrict__ invstd, int relu, float* __restrict__ partial) {
+  extern __shared__ float red[];  // [rows_per_iter][C][2]
+  const int cg = C >> 3;
+  const int lanes = kThreads / cg;
+  const int g = threadIdx.x % cg, rl = threadIdx.x / cg;
+  const long long per = (R + gridDim.x - 1) / gridDim.x;
+  const long long r0 = (long long)blockIdx.x * per;
+  const long long r1 = (r0 + per < R) ? r0 + per : R;
+  float a0[8], a1[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a0[k] = a1[k] = 0.f;
+  float sc[8], sh[8], mu[8], is[8];
+  if (BWD) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      sc[k] = scale[g * 8 + k];
+      sh[k] = shift[g * 8 + k];
+      mu[k] = mean[g * 8 + k];
+      is[k] = invstd[g * 8 + k];
+    }
+  }
+  if (rl < lanes) {
+#pragma unroll 4
+    for (long long r = r0 + rl; r < r1; r += lanes) {
+      const Bf8 px = *reinterpret_cast<const Bf8*>(x + r * C + g * 8);
+      float xf[8];
+      unpack(px, xf);
+      if (!BWD) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          a0[k] += xf[k];
+          a1[k] = fmaf(xf[k], xf[k], a1[k]);
+        }
+      } else {
+        const Bf8 pd = *reinterpret_cast<const Bf8*>(dy + r * C + g * 8);
+        float df[8];
+        unpack(pd, df);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float d = df[k];
+          if (relu && fmaf(xf[k], sc[k], sh[k]) <= 0.f) d = 0.f;
+          a0[k] += d;
+          a1[k] = fmaf(d, (xf[k] - mu[k]) * is[k], a1[k]);
+        }
+      }
+    }
+  }
+  // reduce across row lanes through shared memory
+  float* mine = red + ((size_t)rl * C + g * 8) * 2;
+  if (rl < lanes) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      mine[2 * k] = a0[k];
+      mine[2 * k + 1] = a1[k];
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < C * 2; t += kThreads) {
+    float s = 0.f;
+    for (int l = 0; l < lanes; ++l) s += red[(size_t)l * C * 2 + t];
+    partial[(size_t)blockIdx.x * C * 2 + t] = s;
+  }
+}
+
+__global__ void stats_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, long long R,
+                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      float eps, float momentum, float* __restrict__ running_mean,
+                                      float* __restrict__ running_var, float* __restrict__ mean,
+                                      float* __restrict__ invstd, float* __restrict__ scale,
+                                      float* __restrict__ shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int b = 0; b < nblocks; ++b) {
+    s += (double)partial[((size_t)b * C + c) * 2];
+    q += (double)partial[((size_t)b * C + c) * 2 + 1];
+  }
+  const double m = s / (double)R;
+  double var = q / (double)R - m * m;
+  if (var < 0.0) var = 0.0;
+  const float is = (float)(1.0 / sqrt(var + (double)eps));
+  mean[c] = (float)m;
+  invstd[c] = is;
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  scale[c] = g * is;
+  shift[c] = b - (float)m * g * is;
+  if (running_mean) {
+    const double unbiased = R > 1 ? var * (double)R / (double)(R - 1) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) apply_kernel(const __nv_bfloat16* __restrict__ x,
+                                                        __nv_bfloat16* __restrict__ y, long long total8,
+                                                        int C, const float* __restrict__ scale,
+                                                        const float* __restrict__ shift, int relu) {
+  const int cg = C >> 3;
+  const long long stride = (long long)gridDim.x * kThreads;
+  for (long long u = (long long)blockIdx.x * kThreads + threadIdx.x; u < total8; u += stride) {
+    const int g = (int)(u % cg);
+    const Bf8 px = reinterpret_cast<const Bf8*>(x)[u];
+    float f[8];
+    unpack(px, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float v = fmaf(f[k], __ldg(scale + g * 8 + k), __ldg(shift + g * 8 + k));
+      f[k] = (relu && v < 0.f) ? 0.f : v;
+    }
+    reinterpret_cast<Bf8*>(y)[u] = pack(f);
+  }
+}
+
+__global__ void bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, long long R,
+                                    const float* __restrict__ gamma, const float* __restrict__ invstd,
+                                    float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                    float* __restrict__ coef /* [3][C]: a, c1, c2 */) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int b = 0; b < nblocks; ++b) {
+    s += (double)partial[((size_t)b * C + c) * 2];
+    q += (double)partial[((size_t)b * C + c) * 2 + 1];
+  }
+  if (dbeta) dbeta[c] = (float)s;
+  if (dgamma) dgamma[c] = (float)q;
+  const float g = gamma ? gamma[c] : 1.f;
+  coef[c] = g * invstd[c];
+  coef[C + c] = (float)(s / (double)R);
+  coef[2 * C + c] = (float)(q / (double)R);
+}
+
+__global__ void __launch_bounds__(kThreads) bwd_apply_kernel(
+    const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+    __nv_bfloat16* __restrict__ dx, long long total8, int C, const float* __restrict__ scale,
+    const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
+    const float* __restrict__ coef, int relu) {
+  const int cg = C >> 3;
+  const long long stride = (long long)gridDim.x * kThreads;
+  for (long long u = (long long)blockIdx.x * kThreads + threadIdx.x; u < total8; u += stride) {
+    const int g = (int)(u % cg);
+    float xf[8], df[8];
+    unpack(reinterpret_cast<const Bf8*>(x)[u], xf);
+    unpack(reinterpret_cast<const Bf8*>(dy)[u], df);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = g * 8 + k;
+      float d = df[k];
+      if (relu && fmaf(xf[k], __ldg(scale + c), __ldg(shift + c)) <= 0.f) d = 0.f;
+      const float xhat = (xf[k] - __ldg(mean + c)) * __ldg(invstd + c);
+      df[k] = __ldg(coef + c) * (d - __ldg(coef + C + c) - xhat * __ldg(coef + 2 * C + c));
+    }
+    reinterpret_cast<Bf8*>(dx)[u] = pack(df);
+  }
+}
+
+int reduce_blocks(long long R, int sm_count) {
+  long long b = (long long)sm_count * 4;
+  if (b > R / 64) b = R / 64;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+int stream_blocks(long long total8, int sm_count) {
+  long long b = (total8 + kThreads - 1) / kThreads;
+  const long long cap = (long long)sm_count * 8;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace
+
+int bz_bn_partial_blocks(long long R, int sm_count) { return reduce_blocks(R, sm_count); }
+
+static int check_shape(long long R, int C) {
+  if (C < 8 || (C % 8) != 0 || C > 4096 || R < 1) return (int)cudaErrorInvalidValue;
+  if (kThreads / (C >> 3) < 1) return (int)cudaErrorInvalidValue;  // C <= 2048
+  return 0;
+}
+
+int bz_bn_forward(const BzBnArgs* a, int sm_count, cudaStream_t stream) {
+  if (int e = check_shape(a->R, a->C)) return e;
+  const auto* x = reinterpret_cast<const __nv_bfloat16*>(a->x);
+  auto* y = reinterpret_cast<__nv_bfloat16*>(a->y);
+  const int C = a->C;
+  if (a->training) {
+    const int nb = reduce_blocks(a->R, sm_count);
+    const int lanes = kThreads / (C >> 3);
+    const size_t smem = (size_t)lanes * C * 2 * sizeof(float);
+    reduce_partial_kernel<false><<<nb, kThreads, smem, stream>>>(x, nullptr, a->R, C, nullptr, nullptr,
+                                                                nullptr, nullptr, 0, a->partial);
+    stats_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(
+        a->partial, nb, C, a->R, a->gamma, a->beta, a->eps, a->momentum, a->running_mean,
+        a->running_var, a->mean, a->invstd, a->scale, a->shift);
+  }
+  const long long total8 = a->R * (C >> 3);
+  apply_kernel<<<stream_blocks(total8, sm_count), kThreads, 0, stream>>>(x, y, total8, C, a->scale,
+                                                                       a->shift, a->relu);
+  return (int)cudaGetLastError();
+}
+
+int bz_bn_backward(const BzBnArgs* a, int sm_count, cudaStream_t stream) {
+  if (int e = check_shape(a->R, a->C)) return e;
+  const auto* x = reinterpret_cast<const __nv_bfloat16*>(a->x);
+  const auto* dy = reinterpret_cast<const __nv_bfloat16*>(a->dy);
+  auto* dx = reinterpret_cast<__nv_bfloat16*>(a->dx);
+  const int C = a->C;
+  const int nb = reduce_blocks(a->R, sm_count);
+  const int lanes = kThreads / (C >> 3);
+  const size_t smem = (size_t)lanes * C * 2 * sizeof(float);
+  reduce_partial_kernel<true><<<nb, kThreads, smem, stream>>>(x, dy, a->R, C, a->scale, a->shift, a->mean,
+                                                             a->invstd, a->relu, a->partial);
+  bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(a->partial, nb, C, a->R, a->gamma, a->invstd,
+                                                          a->dgamma, a->dbeta, a->coef);
+  const long long total8 = a->R * (C >> 3);
+  bwd_apply_kernel<<<stream_blocks(total8, sm_count), kThreads, 0, stream>>>(
+      x, dy, dx, total8, C, a->scale, a->shift, a->mean, a->invstd, a->coef, a->relu);
+  return (int)cudaGetLastError();
+}

@@ -22,21 +22,30 @@ def _conv1x1(cin: int, cout: int, stride: int = 1) -> nn.Conv2d:
     return nn.Conv2d(cin, cout, 1, stride=stride, bias=False)
 
 
+def _bn(channels: int, relu: bool = False) -> nn.BatchNorm2d:
+    """BatchNorm2d with the following ReLU folded in.  ``FusedBatchNorm2d`` runs the hand-written
+    sm_100a NHWC bf16 kernels on CUDA and falls back to ``F.batch_norm`` (+ relu) elsewhere; its
+    parameters / buffers / state_dict keys are those of ``nn.BatchNorm2d``."""
+    from ..ops.fused_bn import FusedBatchNorm2d
+
+    return FusedBatchNorm2d(channels, relu=relu)
+
+
 class BasicBlock(nn.Module):
     expansion = 1
 
     def __init__(self, cin: int, width: int, stride: int = 1, downsample: nn.Module | None = None):
         super().__init__()
         self.conv1 = _conv3x3(cin, width, stride)
-        self.bn1 = nn.BatchNorm2d(width)
+        self.bn1 = _bn(width, relu=True)
         self.relu = nn.ReLU(inplace=True)
         self.conv2 = _conv3x3(width, width)
-        self.bn2 = nn.BatchNorm2d(width)
+        self.bn2 = _bn(width)
         self.downsample = downsample
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         idt = x if self.downsample is None else self.downsample(x)
-        y = self.relu(self.bn1(self.conv1(x)))
+        y = self.bn1(self.conv1(x))          # ReLU fused into bn1
         y = self.bn2(self.conv2(y))
         return self.relu(y + idt)
 
@@ -47,18 +56,18 @@ class Bottleneck(nn.Module):
     def __init__(self, cin: int, width: int, stride: int = 1, downsample: nn.Module | None = None):
         super().__init__()
         self.conv1 = _conv1x1(cin, width)
-        self.bn1 = nn.BatchNorm2d(width)
+        self.bn1 = _bn(width, relu=True)
         self.conv2 = _conv3x3(width, width, stride)
-        self.bn2 = nn.BatchNorm2d(width)
+        self.bn2 = _bn(width, relu=True)
         self.conv3 = _conv1x1(width, width * 4)
-        self.bn3 = nn.BatchNorm2d(width * 4)
+        self.bn3 = _bn(width * 4)
         self.relu = nn.ReLU(inplace=True)
         self.downsample = downsample
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         idt = x if self.downsample is None else self.downsample(x)
-        y = self.relu(self.bn1(self.conv1(x)))
-        y = self.relu(self.bn2(self.conv2(y)))
+        y = self.bn1(self.conv1(x))          # ReLU fused
+        y = self.bn2(self.conv2(y))          # ReLU fused
         y = self.bn3(self.conv3(y))
         return self.relu(y + idt)
 
@@ -74,7 +83,7 @@ class ResNet(nn.Module):
         else:
             self.conv1 = nn.Conv2d(in_channels, 64, 7, stride=2, padding=3, bias=False)
             self.maxpool = nn.MaxPool2d(3, stride=2, padding=1)
-        self.bn1 = nn.BatchNorm2d(64)
+        self.bn1 = _bn(64, relu=True)
         self.relu = nn.ReLU(inplace=True)
         self.layer1 = self._stage(block, 64, depths[0], 1)
         self.layer2 = self._stage(block, 128, depths[1], 2)
@@ -93,14 +102,14 @@ class ResNet(nn.Module):
         down = None
         if stride != 1 or self._cin != width * block.expansion:
             down = nn.Sequential(_conv1x1(self._cin, width * block.expansion, stride),
-                                 nn.BatchNorm2d(width * block.expansion))
+                                 _bn(width * block.expansion))
         layers: List[nn.Module] = [block(self._cin, width, stride, down)]
         self._cin = width * block.expansion
         layers += [block(self._cin, width) for _ in range(1, depth)]
         return nn.Sequential(*layers)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+        x = self.maxpool(self.bn1(self.conv1(x)))   # ReLU fused into bn1
         x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
         return self.fc(torch.flatten(self.avgpool(x), 1))
 

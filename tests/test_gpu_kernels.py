@@ -210,3 +210,69 @@ def test_scale_fill():
     y = torch.empty(77, device=dev())
     ops.fill_(y, float("inf"))
     assert torch.isinf(y).all()
+
+
+@pytest.mark.parametrize("shape", [(32, 64, 56, 56), (8, 128, 28, 28), (4, 512, 7, 7), (3, 24, 5, 9)])
+@pytest.mark.parametrize("relu", [False, True])
+def test_fused_batchnorm_matches_torch(shape, relu):
+    import torch.nn.functional as F
+
+    from byzpy_b200.ops.fused_bn import FusedBatchNorm2d
+
+    torch.manual_seed(0)
+    N, C, H, W = shape
+    x32 = (torch.randn(shape, device=dev()) * 2.0 + 0.5)
+    xb = x32.to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    bn = FusedBatchNorm2d(C, relu=relu).to(dev())
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.uniform_(-0.5, 0.5)
+    y = bn(xb)
+    assert y.dtype == torch.bfloat16 and y.is_contiguous(memory_format=torch.channels_last)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    # fp32 reference on the same bf16-rounded inputs
+    xr = xb.detach().float().requires_grad_(True)
+    w = bn.weight.detach().clone().requires_grad_(True)
+    b = bn.bias.detach().clone().requires_grad_(True)
+    rm, rv = torch.zeros(C, device=dev()), torch.ones(C, device=dev())
+    yr = F.batch_norm(xr, rm, rv, w, b, True, 0.1, 1e-5)
+    if relu:
+        yr = F.relu(yr)
+    yr.backward(gy.float())
+    torch.testing.assert_close(y.float(), yr, rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(xb.grad.float(), xr.grad, rtol=3e-2, atol=3e-2)
+    torch.testing.assert_close(bn.weight.grad, w.grad, rtol=2e-2, atol=2e-2 * (N * H * W) ** 0.5)
+    torch.testing.assert_close(bn.bias.grad, b.grad, rtol=2e-2, atol=2e-2 * (N * H * W) ** 0.5)
+    torch.testing.assert_close(bn.running_mean, rm, rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(bn.running_var, rv, rtol=1e-3, atol=1e-3)
+    assert int(bn.num_batches_tracked) == 1
+    # eval mode uses the running statistics
+    bn.eval()
+    ye = bn(xb.detach())
+    yre = F.batch_norm(xb.detach().float(), rm, rv, w.detach(), b.detach(), False, 0.1, 1e-5)
+    torch.testing.assert_close(ye.float(), F.relu(yre) if relu else yre, rtol=2e-2, atol=2e-2)
+
+
+def test_resnet18_fused_bn_trains_like_torchvision():
+    import torchvision
+
+    from byzpy_b200.models import resnet18
+
+    torch.manual_seed(0)
+    ref = torchvision.models.resnet18(num_classes=10).to(dev())
+    mine = resnet18(num_classes=10).to(dev())
+    mine.load_state_dict(ref.state_dict(), strict=True)
+    x = torch.randn(16, 3, 64, 64, device=dev()).contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, 10, (16,), device=dev())
+    losses = []
+    for m in (ref, mine):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = torch.nn.functional.cross_entropy(m(x), y)
+        loss.backward()
+        losses.append(loss.item())
+    assert abs(losses[0] - losses[1]) < 0.05
+    ga = torch.cat([p.grad.reshape(-1) for p in ref.parameters()])
+    gb = torch.cat([p.grad.reshape(-1) for p in mine.parameters()])
+    cos = torch.nn.functional.cosine_similarity(ga, gb, dim=0).item()
+    assert cos > 0.98, cos
