@@ -1,0 +1,33 @@
+"""Runtime dependency report (the reference's ``_dependencies.py`` selects cupy/ucxx extras at
+install time via ``BYZPY_FORCE_GPU`` / ``BYZPY_FORCE_CPU``, reference _dependencies.py:34-77).
+This framework has no optional GPU wheels -- its kernels are built in-tree -- so the same
+environment variables only steer :func:`preferred_device`."""
+from __future__ import annotations
+
+import os
+
+
+def _flag(name: str) -> bool:
+    return os.environ.get(name, "").strip().lower() in ("1", "true", "yes", "on")
+
+
+def preferred_device() -> str:
+    if _flag("BYZPY_FORCE_CPU"):
+        return "cpu"
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            return "cuda"
+    except Exception:
+        pass
+    if _flag("BYZPY_FORCE_GPU"):
+        raise RuntimeError("BYZPY_FORCE_GPU is set but no CUDA device is available")
+    return "cpu"
+
+
+def base_requirements():
+    return ["torch>=2.6", "numpy>=1.24", "cloudpickle>=2.2", "tqdm>=4.65", "pybind11>=2.11"]
+
+
+__all__ = ["preferred_device", "base_requirements"]

@@ -112,19 +112,34 @@ __global__ void __launch_bounds__(kThreads) reduce_partial_kernel(
   }
 }
 
-__global__ void stats_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, long long R,
-                                      const float* __restrict__ gamma, const float* __restrict__ beta,
-                                      float eps, float momentum, float* __restrict__ running_mean,
-                                      float* __restrict__ running_var, float* __restrict__ mean,
-                                      float* __restrict__ invstd, float* __restrict__ scale,
-                                      float* __restrict__ shift) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0, q = 0.0;
-  for (int b = 0; b < nblocks; ++b) {
-    s += (double)partial[((size_t)b * C + c) * 2];
-    q += (double)partial[((size_t)b * C + c) * 2 + 1];
+// One warp per channel: lanes stride over the per-CTA partials, shuffle-reduce in fp64.
+__device__ __forceinline__ void reduce_channel(const float* __restrict__ partial, int nblocks, int C, int c,
+                                               double& s, double& q) {
+  const int lane = threadIdx.x & 31;
+  double ls = 0.0, lq = 0.0;
+  for (int b = lane; b < nblocks; b += 32) {
+    ls += (double)partial[((size_t)b * C + c) * 2];
+    lq += (double)partial[((size_t)b * C + c) * 2 + 1];
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ls += __shfl_xor_sync(0xffffffffu, ls, o);
+    lq += __shfl_xor_sync(0xffffffffu, lq, o);
+  }
+  s = ls;
+  q = lq;
+}
+
+__global__ void __launch_bounds__(kThreads) stats_finalize_kernel(
+    const float* __restrict__ partial, int nblocks, int C, long long R, const float* __restrict__ gamma,
+    const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
+    float* __restrict__ running_var, float* __restrict__ mean, float* __restrict__ invstd,
+    float* __restrict__ scale, float* __restrict__ shift) {
+  const int c = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  if (c >= C) return;
+  double s, q;
+  reduce_channel(partial, nblocks, C, c, s, q);
+  if ((threadIdx.x & 31) != 0) return;
   const double m = s / (double)R;
   double var = q / (double)R - m * m;
   if (var < 0.0) var = 0.0;
@@ -141,64 +156,97 @@ __global__ void stats_finalize_kernel(const float* __restrict__ partial, int nbl
   }
 }
 
+// The grid-stride (gridDim * 256) is a multiple of cg whenever cg divides 256 (every power-of-two
+// width), so a thread always sees the same channel group and keeps its constants in registers.
 __global__ void __launch_bounds__(kThreads) apply_kernel(const __nv_bfloat16* __restrict__ x,
                                                         __nv_bfloat16* __restrict__ y, long long total8,
                                                         int C, const float* __restrict__ scale,
                                                         const float* __restrict__ shift, int relu) {
   const int cg = C >> 3;
   const long long stride = (long long)gridDim.x * kThreads;
-  for (long long u = (long long)blockIdx.x * kThreads + threadIdx.x; u < total8; u += stride) {
-    const int g = (int)(u % cg);
-    const Bf8 px = reinterpret_cast<const Bf8*>(x)[u];
-    float f[8];
-    unpack(px, f);
+  const long long u0 = (long long)blockIdx.x * kThreads + threadIdx.x;
+  const bool fixed = (kThreads % cg) == 0;
+  float sc[8], sh[8];
+  if (fixed) {
+    const int g = (int)(u0 % cg);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      float v = fmaf(f[k], __ldg(scale + g * 8 + k), __ldg(shift + g * 8 + k));
+      sc[k] = scale[g * 8 + k];
+      sh[k] = shift[g * 8 + k];
+    }
+  }
+  for (long long u = u0; u < total8; u += stride) {
+    if (!fixed) {
+      const int g = (int)(u % cg);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        sc[k] = __ldg(scale + g * 8 + k);
+        sh[k] = __ldg(shift + g * 8 + k);
+      }
+    }
+    float f[8];
+    unpack(reinterpret_cast<const Bf8*>(x)[u], f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float v = fmaf(f[k], sc[k], sh[k]);
       f[k] = (relu && v < 0.f) ? 0.f : v;
     }
     reinterpret_cast<Bf8*>(y)[u] = pack(f);
   }
 }
 
-__global__ void bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, long long R,
-                                    const float* __restrict__ gamma, const float* __restrict__ invstd,
-                                    float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                    float* __restrict__ coef /* [3][C]: a, c1, c2 */) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// coef[3][C]:  dx = P * dy' + Q * x + S   with  P = gamma*invstd,  Q = -P*c2*invstd,
+//               S = -P*c1 + P*c2*invstd*mean   (c1 = sum dy'/R, c2 = sum dy' xhat / R)
+__global__ void __launch_bounds__(kThreads) bwd_finalize_kernel(
+    const float* __restrict__ partial, int nblocks, int C, long long R, const float* __restrict__ gamma,
+    const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ dgamma,
+    float* __restrict__ dbeta, float* __restrict__ coef) {
+  const int c = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   if (c >= C) return;
-  double s = 0.0, q = 0.0;
-  for (int b = 0; b < nblocks; ++b) {
-    s += (double)partial[((size_t)b * C + c) * 2];
-    q += (double)partial[((size_t)b * C + c) * 2 + 1];
-  }
+  double s, q;
+  reduce_channel(partial, nblocks, C, c, s, q);
+  if ((threadIdx.x & 31) != 0) return;
   if (dbeta) dbeta[c] = (float)s;
   if (dgamma) dgamma[c] = (float)q;
-  const float g = gamma ? gamma[c] : 1.f;
-  coef[c] = g * invstd[c];
-  coef[C + c] = (float)(s / (double)R);
-  coef[2 * C + c] = (float)(q / (double)R);
+  const double g = gamma ? (double)gamma[c] : 1.0;
+  const double is = (double)invstd[c], mu = (double)mean[c];
+  const double P = g * is, c1 = s / (double)R, c2 = q / (double)R;
+  coef[c] = (float)P;
+  coef[C + c] = (float)(-P * c2 * is);
+  coef[2 * C + c] = (float)(-P * c1 + P * c2 * is * mu);
 }
 
 __global__ void __launch_bounds__(kThreads) bwd_apply_kernel(
     const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
     __nv_bfloat16* __restrict__ dx, long long total8, int C, const float* __restrict__ scale,
-    const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
-    const float* __restrict__ coef, int relu) {
+    const float* __restrict__ shift, const float* __restrict__ coef, int relu) {
   const int cg = C >> 3;
   const long long stride = (long long)gridDim.x * kThreads;
-  for (long long u = (long long)blockIdx.x * kThreads + threadIdx.x; u < total8; u += stride) {
-    const int g = (int)(u % cg);
+  const long long u0 = (long long)blockIdx.x * kThreads + threadIdx.x;
+  const bool fixed = (kThreads % cg) == 0;
+  float sc[8], sh[8], P[8], Q[8], S[8];
+  auto load_consts = [&](int g) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = g * 8 + k;
+      sc[k] = __ldg(scale + c);
+      sh[k] = __ldg(shift + c);
+      P[k] = __ldg(coef + c);
+      Q[k] = __ldg(coef + C + c);
+      S[k] = __ldg(coef + 2 * C + c);
+    }
+  };
+  if (fixed) load_consts((int)(u0 % cg));
+  for (long long u = u0; u < total8; u += stride) {
+    if (!fixed) load_consts((int)(u % cg));
     float xf[8], df[8];
     unpack(reinterpret_cast<const Bf8*>(x)[u], xf);
     unpack(reinterpret_cast<const Bf8*>(dy)[u], df);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const int c = g * 8 + k;
       float d = df[k];
-      if (relu && fmaf(xf[k], __ldg(scale + c), __ldg(shift + c)) <= 0.f) d = 0.f;
-      const float xhat = (xf[k] - __ldg(mean + c)) * __ldg(invstd + c);
-      df[k] = __ldg(coef + c) * (d - __ldg(coef + C + c) - xhat * __ldg(coef + 2 * C + c));
+      if (relu && fmaf(xf[k], sc[k], sh[k]) <= 0.f) d = 0.f;
+      df[k] = fmaf(P[k], d, fmaf(Q[k], xf[k], S[k]));
     }
     reinterpret_cast<Bf8*>(dx)[u] = pack(df);
   }
@@ -240,7 +288,7 @@ int bz_bn_forward(const BzBnArgs* a, int sm_count, cudaStream_t stream) {
     const size_t smem = (size_t)lanes * C * 2 * sizeof(float);
     reduce_partial_kernel<false><<<nb, kThreads, smem, stream>>>(x, nullptr, a->R, C, nullptr, nullptr,
                                                                 nullptr, nullptr, 0, a->partial);
-    stats_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(
+    stats_finalize_kernel<<<(C + 7) / 8, kThreads, 0, stream>>>(
         a->partial, nb, C, a->R, a->gamma, a->beta, a->eps, a->momentum, a->running_mean,
         a->running_var, a->mean, a->invstd, a->scale, a->shift);
   }
@@ -261,10 +309,10 @@ int bz_bn_backward(const BzBnArgs* a, int sm_count, cudaStream_t stream) {
   const size_t smem = (size_t)lanes * C * 2 * sizeof(float);
   reduce_partial_kernel<true><<<nb, kThreads, smem, stream>>>(x, dy, a->R, C, a->scale, a->shift, a->mean,
                                                              a->invstd, a->relu, a->partial);
-  bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(a->partial, nb, C, a->R, a->gamma, a->invstd,
-                                                          a->dgamma, a->dbeta, a->coef);
+  bwd_finalize_kernel<<<(C + 7) / 8, kThreads, 0, stream>>>(a->partial, nb, C, a->R, a->gamma, a->mean,
+                                                           a->invstd, a->dgamma, a->dbeta, a->coef);
   const long long total8 = a->R * (C >> 3);
   bwd_apply_kernel<<<stream_blocks(total8, sm_count), kThreads, 0, stream>>>(
-      x, dy, dx, total8, C, a->scale, a->shift, a->mean, a->invstd, a->coef, a->relu);
+      x, dy, dx, total8, C, a->scale, a->shift, a->coef, a->relu);
   return (int)cudaGetLastError();
 }

@@ -270,21 +270,28 @@ __global__ void __launch_bounds__(kThreads, 1) gram_umma_kernel(const __grid_con
       tc_fence_after();
       const int quad = warp & 3;                       // TMEM lane partition of this warp
       const int trow = quad * 32 + lane;               // accumulator row owned by this thread
-      const int blk = trow / n_pad, drow = trow % n_pad;
-      // partial layout: [cta][block][HH | HL][n][n]
-      float* PA = a.partials + ((size_t)blockIdx.x * nblk + blk) * 2 * n * n;
-      float* PB = PA + (size_t)n * n;
-      for (int c0 = 0; c0 < n_pad; c0 += 16) {
-        uint32_t va[16], vb[16];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(blk * n_pad + c0);
-        tmem_ld16(taddr, va);
-        tmem_ld16(taddr + 128, vb);
-        if (drow < n) {
+      const int my_blk = trow / n_pad, drow = trow % n_pad;
+      // tcgen05.ld is warp-collective: the TMEM address must be warp-uniform.  A warp's 32 rows
+      // span max(1, 32 / n_pad) diagonal blocks; load each block's columns with a uniform address
+      // and let the lanes that belong to that block keep the data.
+      const int blk_first = (quad * 32) / n_pad;
+      const int blk_last = (quad * 32 + 31) / n_pad;
+      for (int blk = blk_first; blk <= blk_last; ++blk) {
+        // partial layout: [cta][block][HH | HL][n][n]
+        float* PA = a.partials + ((size_t)blockIdx.x * nblk + blk) * 2 * n * n;
+        float* PB = PA + (size_t)n * n;
+        for (int c0 = 0; c0 < n_pad; c0 += 16) {
+          uint32_t va[16], vb[16];
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(blk * n_pad + c0);
+          tmem_ld16(taddr, va);
+          tmem_ld16(taddr + 128, vb);
+          if (blk == my_blk && drow < n) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if (c0 + j < n) {
-              PA[drow * n + c0 + j] = __uint_as_float(va[j]);
-              PB[drow * n + c0 + j] = __uint_as_float(vb[j]);
+            for (int j = 0; j < 16; ++j) {
+              if (c0 + j < n) {
+                PA[drow * n + c0 + j] = __uint_as_float(va[j]);
+                PB[drow * n + c0 + j] = __uint_as_float(vb[j]);
+              }
             }
           }
         }

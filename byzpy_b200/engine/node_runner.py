@@ -22,6 +22,7 @@ def _runner_main(cmd_conn, inbox_conn, blob: bytes) -> None:
     step_fn, msg_handler, init_state = cloudpickle.loads(blob)
     state = init_state if init_state is not None else {}
     auto, interval, last = False, 0.0, time.monotonic()
+    cmd_conn.send(("ready", None))  # handshake: the interpreter and the callables are loaded
 
     def drain() -> None:
         nonlocal state
@@ -81,10 +82,15 @@ class NodeRunner:
         self._pump_thread: Optional[threading.Thread] = None
         self._pump_stop = threading.Event()
 
-    def start(self) -> None:
+    def start(self, ready_timeout: float = 120.0) -> None:
         self._proc.start()
         for c in self._children:
             c.close()
+        # a spawned interpreter may take seconds to import its dependencies; commands carry short
+        # timeouts, so wait for the child's handshake once instead of padding every timeout
+        if not self._cmd.poll(ready_timeout):
+            raise TimeoutError("NodeRunner child did not come up")
+        self._cmd.recv()
 
     def _command(self, op: str, payload: Any = None, timeout: float = 5.0):
         with self._lock:

@@ -265,6 +265,10 @@ def test_resnet18_fused_bn_trains_like_torchvision():
     mine.load_state_dict(ref.state_dict(), strict=True)
     x = torch.randn(16, 3, 64, 64, device=dev()).contiguous(memory_format=torch.channels_last)
     y = torch.randint(0, 10, (16,), device=dev())
+    import copy
+
+    exact = copy.deepcopy(ref)  # fp32, no autocast: the yardstick for bf16 noise
+    torch.nn.functional.cross_entropy(exact(x), y).backward()
     losses = []
     for m in (ref, mine):
         with torch.autocast("cuda", dtype=torch.bfloat16):
@@ -272,7 +276,13 @@ def test_resnet18_fused_bn_trains_like_torchvision():
         loss.backward()
         losses.append(loss.item())
     assert abs(losses[0] - losses[1]) < 0.05
-    ga = torch.cat([p.grad.reshape(-1) for p in ref.parameters()])
-    gb = torch.cat([p.grad.reshape(-1) for p in mine.parameters()])
-    cos = torch.nn.functional.cosine_similarity(ga, gb, dim=0).item()
-    assert cos > 0.98, cos
+
+    def flat(m):
+        return torch.cat([p.grad.reshape(-1).float() for p in m.parameters()])
+
+    g_exact, g_tv, g_mine = flat(exact), flat(ref), flat(mine)
+    cos_tv = torch.nn.functional.cosine_similarity(g_tv, g_exact, dim=0).item()
+    cos_mine = torch.nn.functional.cosine_similarity(g_mine, g_exact, dim=0).item()
+    # the fused BN path must be as faithful to the fp32 gradient as torchvision-under-autocast is
+    assert cos_mine > cos_tv - 0.03, (cos_mine, cos_tv)
+    assert cos_mine > 0.9, cos_mine

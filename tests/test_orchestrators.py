@@ -336,3 +336,94 @@ def test_tracer_records_graph_nodes():
     assert summ["node:agg"]["calls"] == 1 and summ["node:agg"]["host_ms"] > 0
     with nvtx_range("noop"):
         pass
+
+
+def test_byzpy_import_alias_maps_reference_paths():
+    import sys
+
+    from byzpy_b200 import compat
+
+    saved = {k: v for k, v in sys.modules.items() if k == "byzpy" or k.startswith("byzpy.")}
+    for k in saved:
+        del sys.modules[k]
+    compat.install_alias()
+    try:
+        from byzpy.aggregators.coordinate_wise import CoordinateWiseMedian as A  # type: ignore
+        from byzpy.engine.graph.pool import ActorPoolConfig as P  # type: ignore
+        from byzpy.engine.peer_to_peer.topology import Topology as T  # type: ignore
+        import byzpy  # type: ignore
+
+        from byzpy_b200.aggregators.coordinate_wise import CoordinateWiseMedian
+        from byzpy_b200.engine.graph.pool import ActorPoolConfig
+        from byzpy_b200.engine.peer_to_peer.topology import Topology
+
+        assert A is CoordinateWiseMedian and P is ActorPoolConfig and T is Topology
+        assert hasattr(byzpy, "run_operator")
+    finally:
+        compat.uninstall_alias()
+        sys.modules.update(saved)
+
+
+def test_public_api_surface_of_the_reference_is_importable():
+    import importlib
+
+    surface = {
+        "byzpy_b200": ["run_operator", "OperatorExecutor", "__version__"],
+        "byzpy_b200.aggregators": ["Aggregator"],
+        "byzpy_b200.aggregators.coordinate_wise": ["MeanOfMedians", "CoordinateWiseMedian", "CoordinateWiseTrimmedMean"],
+        "byzpy_b200.aggregators.geometric_wise": ["GeometricMedian", "Krum", "MultiKrum", "MinimumDiameterAveraging", "MoNNA", "SMEA"],
+        "byzpy_b200.aggregators.norm_wise": ["CAF", "CenteredClipping", "ComparativeGradientElimination"],
+        "byzpy_b200.aggregators._chunking": ["select_adaptive_chunk_size"],
+        "byzpy_b200.aggregators.coordinate_wise._tiling": ["flatten_gradients"],
+        "byzpy_b200.pre_aggregators": ["PreAggregator", "Bucketing", "NearestNeighborMixing", "Clipping", "ARC"],
+        "byzpy_b200.attacks": ["Attack", "EmpireAttack", "LittleAttack", "SignFlipAttack", "LabelFlipAttack", "GaussianAttack", "InfAttack", "MimicAttack"],
+        "byzpy_b200.configs.actor": ["set_actor"],
+        "byzpy_b200.configs.backend": ["set_backend", "get_backend", "use_backend"],
+        "byzpy_b200.engine": ["CallableOp", "RemoteCallableOp", "make_single_operator_graph", "NodeCluster", "NodeRunner"],
+        "byzpy_b200.engine.graph.graph": ["ComputationGraph", "GraphInput", "GraphNode", "graph_input"],
+        "byzpy_b200.engine.graph.operator": ["OpContext", "Operator", "MessageTriggerOp"],
+        "byzpy_b200.engine.graph.subtask": ["SubTask"],
+        "byzpy_b200.engine.graph.scheduler": ["NodeScheduler", "MessageAwareNodeScheduler", "MessageSource"],
+        "byzpy_b200.engine.graph.parallel_scheduler": ["ParallelScheduler"],
+        "byzpy_b200.engine.graph.pool": ["ActorPool", "ActorPoolConfig", "ActorPoolChannel"],
+        "byzpy_b200.engine.graph.ops": ["CallableOp", "RemoteCallableOp", "make_single_operator_graph"],
+        "byzpy_b200.engine.graph.lazy": ["GraphBuilder", "LazyNode"],
+        "byzpy_b200.engine.graph.session": ["ExecutionSession", "ExecutionFuture"],
+        "byzpy_b200.engine.graph.executor": ["OperatorExecutor", "run_operator"],
+        "byzpy_b200.engine.actor.base": ["ActorBackend", "ActorRef"],
+        "byzpy_b200.engine.actor.channels": ["Endpoint", "ChannelRef", "open_channel"],
+        "byzpy_b200.engine.actor.factory": ["resolve_backend"],
+        "byzpy_b200.engine.actor.router": ["ChannelRouter", "channel_router"],
+        "byzpy_b200.engine.actor.ipc": ["wrap_payload", "unwrap_payload"],
+        "byzpy_b200.engine.actor.backends.thread": ["ThreadActorBackend"],
+        "byzpy_b200.engine.actor.backends.process": ["ProcessActorBackend"],
+        "byzpy_b200.engine.actor.backends.gpu": ["GPUActorBackend", "UCXRemoteActorBackend", "UCXRemoteActorServer", "start_ucx_actor_server"],
+        "byzpy_b200.engine.actor.backends.remote": ["RemoteActorBackend", "RemoteActorServer", "start_actor_server"],
+        "byzpy_b200.engine.actor.transports.tcp": ["chan_put", "chan_get"],
+        "byzpy_b200.engine.actor.transports.ucx": ["have_ucx"],
+        "byzpy_b200.engine.node": ["NodeApplication", "NodePipeline", "HonestNodeApplication", "ByzantineNodeApplication", "CallableOp",
+                                   "RemoteCallableOp", "make_single_operator_graph", "NodeContext", "InProcessContext", "ProcessContext",
+                                   "RemoteContext", "DecentralizedNode", "DistributedHonestNode", "DistributedByzantineNode",
+                                   "DecentralizedCluster", "MessageRouter", "RemoteNodeServer", "RemoteNodeClient", "serialize_message",
+                                   "deserialize_message"],
+        "byzpy_b200.engine.node.context": ["MeshRemoteContext"],
+        "byzpy_b200.engine.node.actors": ["HonestNodeActor", "ByzantineNodeActor"],
+        "byzpy_b200.engine.node.base": ["Node", "HonestNode", "ByzantineNode"],
+        "byzpy_b200.engine.node.mixin": ["P2PHonestMixin", "P2PByzantineMixin"],
+        "byzpy_b200.engine.node.remote_server": ["ServerNodeContext"],
+        "byzpy_b200.engine.parameter_server.ps": ["ParameterServer"],
+        "byzpy_b200.engine.parameter_server.runner": ["ParameterServerRunner"],
+        "byzpy_b200.engine.parameter_server.decentralized": ["DecentralizedParameterServer"],
+        "byzpy_b200.engine.peer_to_peer.topology": ["Topology", "Edge"],
+        "byzpy_b200.engine.peer_to_peer.train": ["PeerToPeer"],
+        "byzpy_b200.engine.peer_to_peer.runner": ["DecentralizedPeerToPeer"],
+        "byzpy_b200.engine.storage.shared_store": ["SharedTensorHandle", "register_tensor", "open_tensor", "cleanup_tensor"],
+        "byzpy_b200.engine.transport": ["Transport", "LocalTransport", "TcpTransport", "TcpMailbox", "send_message"],
+        "byzpy_b200.engine.backend.ndarray": ["get_array_backend"],
+        "byzpy_b200.utils": ["train_with_progress"],
+        "byzpy_b200.cli": ["main"],
+    }
+    for mod, names in surface.items():
+        m = importlib.import_module(mod)
+        for n in names:
+            assert hasattr(m, n), f"{mod}.{n} missing"
