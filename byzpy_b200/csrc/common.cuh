@@ -90,19 +90,20 @@ __device__ __forceinline__ float canon(float x) { return (x != x) ? __int_as_flo
 // (e.g. when only the median slot is read).
 template <int NP>
 __device__ __forceinline__ void bitonic_sort(float (&v)[NP]) {
+  // Batcher's odd-even merge sort (19 / 63 / 191 / 543 / 1471 compare-exchanges for
+  // NP = 8 / 16 / 32 / 64 / 128, ~20 % fewer than the bitonic network the name recalls).
+  // Every comparator sorts ascending, so each is exactly one FMNMX pair on the alu pipe.
 #pragma unroll
-  for (int k = 2; k <= NP; k <<= 1) {
+  for (int p = 1; p < NP; p <<= 1) {
 #pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) {
+    for (int k = p; k >= 1; k >>= 1) {
 #pragma unroll
-      for (int i = 0; i < NP; ++i) {
-        const int l = i ^ j;
-        if (l > i) {
-          const bool up = ((i & k) == 0);
-          const float a = v[i], b = v[l];
-          const float lo = fminf(a, b), hi = fmaxf(a, b);
-          v[i] = up ? lo : hi;
-          v[l] = up ? hi : lo;
+      for (int x = 0; x < NP; ++x) {
+        const int r = k % p;
+        if (x >= r && ((x - r) % (2 * k)) < k && x + k < NP && (x / (2 * p)) == ((x + k) / (2 * p))) {
+          const float a = v[x], b = v[x + k];
+          v[x] = fminf(a, b);
+          v[x + k] = fmaxf(a, b);
         }
       }
     }

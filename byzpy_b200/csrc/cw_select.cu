@@ -44,8 +44,17 @@ int launch_one(const BzCwArgs& a, int sm_count, cudaStream_t stream) {
   const long long nvec = a.len / V;
   if (nvec <= 0) return 0;
   long long blocks = (nvec + kThreads - 1) / kThreads;
-  // persistent-ish grid: a multiple of the SM count (148 on B200), capped.
-  const long long cap = (long long)sm_count * (NP >= 64 ? 4 : 8);
+  // persistent grid: exactly the number of CTAs the device can keep resident (148 SMs x the
+  // occupancy of this instantiation), so the grid-stride loop has no partial last wave.
+  static int occ = 0;
+  if (occ == 0) {
+    int o = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, cw_select_kernel<NP, V, MODE>, kThreads, 0) !=
+            cudaSuccess || o < 1)
+      o = 2;
+    occ = o;
+  }
+  const long long cap = (long long)sm_count * occ;
   if (blocks > cap) blocks = cap;
   cw_select_kernel<NP, V, MODE><<<(unsigned)blocks, kThreads, 0, stream>>>(a);
   return (int)cudaGetLastError();
