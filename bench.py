@@ -174,7 +174,8 @@ def run_ours(args, rank, world, device):
             byz.append(DeviceByzantineNode(SignFlipAttack(), model=model, name=f"byz{g}", **kw))
     ps = ParameterServer(honest, byz, CoordinateWiseMedian(), update_byzantines=True,
                          layout=layout, amp_dtype=torch.bfloat16, use_cuda_graph=not args.no_graph,
-                         worker_streams=args.worker_streams, fused=True)
+                         worker_streams=args.worker_streams, fused=True,
+                         direct_grads=not args.no_direct_grads, overlap_wgrad=not args.no_overlap_wgrad)
     rnd = ps.device_round
 
     def batches(i):
@@ -222,7 +223,7 @@ def run_ours(args, rank, world, device):
         dist.all_reduce(tot)
         h2d, d2h = int(tot[0].item()), int(tot[1].item())
     result = dict(ms=ms, e2e_s=e2e_s, h2d=h2d, d2h=d2h, clocks=clk.summary(),
-                  launches=rnd.launches_per_step * args.steps,
+                  launches=(rnd.launches_per_step + rnd.model_launches_per_step) * args.steps,
                   loss=float(losses.mean().item()), d=rnd.d)
     asyncio.run(ps.shutdown())
     return result
@@ -397,6 +398,10 @@ def main():
     ap.add_argument("--lr", type=float, default=0.05)
     ap.add_argument("--worker-streams", type=int, default=4)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-direct-grads", action="store_true",
+                    help="A/B: stock autograd gradient accumulation instead of in-place arena gradients")
+    ap.add_argument("--no-overlap-wgrad", action="store_true",
+                    help="A/B: weight-gradient GEMMs on the worker stream instead of a side stream")
     args = ap.parse_args()
 
     world = env_int("WORLD_SIZE", 1)

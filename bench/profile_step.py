@@ -15,6 +15,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--streams", type=int, default=1)
     ap.add_argument("--out", default="gpurun_out/profile_step.txt")
+    ap.add_argument("--no-direct-grads", action="store_true")
+    ap.add_argument("--no-overlap-wgrad", action="store_true")
     a = ap.parse_args()
     from byzpy_b200.aggregators.coordinate_wise import CoordinateWiseMedian
     from byzpy_b200.attacks import SignFlipAttack
@@ -35,7 +37,8 @@ def main():
         else:
             byz.append(DeviceByzantineNode(SignFlipAttack(), model=m, **kw))
     ps = ParameterServer(hon, byz, CoordinateWiseMedian(), update_byzantines=True, fused=True,
-                         use_cuda_graph=False, worker_streams=a.streams)
+                         use_cuda_graph=False, worker_streams=a.streams,
+                         direct_grads=not a.no_direct_grads, overlap_wgrad=not a.no_overlap_wgrad)
     bt = [(xs[s][0], ys[s][0]) for s in range(a.workers)]
     for _ in range(3):
         ps.step(bt)

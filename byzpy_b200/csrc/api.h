@@ -20,6 +20,7 @@ struct BzCwArgs {
   long long len;      // number of coordinates
   float* out;         // aggregated vector (may be nullptr when only updating)
   UpdTable upd;       // optional fused optimizer step
+  int impl;           // 0 = auto, 1 = direct register loads, 2 = cp.async-staged pipeline
 };
 
 // Coordinate-wise family (median / trimmed mean / mean-of-medians / mean).

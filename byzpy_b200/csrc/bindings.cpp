@@ -14,6 +14,7 @@
 
 #include "api.h"
 #include "bn.h"
+#include "pool.h"
 #include "gram_umma.h"
 #include "nspace.h"
 #include "runtime.h"
@@ -77,7 +78,7 @@ PYBIND11_MODULE(_C, m) {
          int n_virtual, int n_honest, float va, float vb, long long off, long long len,
          uint64_t out, const std::vector<uint64_t>& upd_params,
          const std::vector<uint64_t>& upd_moms, float lr, float mu, float wd, int sm_count,
-         uint64_t stream) {
+         uint64_t stream, int impl) {
         BzCwArgs a;
         std::memset(&a, 0, sizeof(a));
         fill_rows(a.rows, a.scales, rows, scales);
@@ -92,12 +93,13 @@ PYBIND11_MODULE(_C, m) {
         a.len = len;
         a.out = as_ptr<float>(out);
         fill_upd(a.upd, upd_params, upd_moms, lr, mu, wd);
+        a.impl = impl;
         check(bz_cw_select(&a, sm_count, as_stream(stream)), "cw_select");
       },
       py::arg("rows"), py::arg("scales"), py::arg("mode"), py::arg("f"), py::arg("n_virtual"),
       py::arg("n_honest"), py::arg("va"), py::arg("vb"), py::arg("off"), py::arg("len"),
       py::arg("out"), py::arg("upd_params"), py::arg("upd_moms"), py::arg("lr"), py::arg("mu"),
-      py::arg("wd"), py::arg("sm_count"), py::arg("stream"));
+      py::arg("wd"), py::arg("sm_count"), py::arg("stream"), py::arg("impl") = 0);
 
   m.def(
       "wsum",
@@ -190,7 +192,8 @@ PYBIND11_MODULE(_C, m) {
       "bn_forward",
       [](uint64_t x, uint64_t y, long long R, int C, uint64_t gamma, uint64_t beta, uint64_t rmean,
          uint64_t rvar, uint64_t mean, uint64_t invstd, uint64_t scale, uint64_t shift, uint64_t partial,
-         float eps, float momentum, int relu, int training, int sm_count, uint64_t stream) {
+         float eps, float momentum, int relu, int training, uint64_t res, uint64_t counter, int sm_count,
+         uint64_t stream) {
         BzBnArgs a;
         std::memset(&a, 0, sizeof(a));
         a.x = as_ptr<const void>(x);
@@ -210,13 +213,16 @@ PYBIND11_MODULE(_C, m) {
         a.momentum = momentum;
         a.relu = relu;
         a.training = training;
+        a.res = as_ptr<const void>(res);
+        a.counter = as_ptr<unsigned>(counter);
         check(bz_bn_forward(&a, sm_count, as_stream(stream)), "bn_forward");
       });
   m.def(
       "bn_backward",
       [](uint64_t x, uint64_t dy, uint64_t dx, long long R, int C, uint64_t gamma, uint64_t mean,
          uint64_t invstd, uint64_t scale, uint64_t shift, uint64_t partial, uint64_t dgamma,
-         uint64_t dbeta, uint64_t coef, int relu, int sm_count, uint64_t stream) {
+         uint64_t dbeta, uint64_t coef, int relu, uint64_t ymask, uint64_t dres, uint64_t counter,
+         int sm_count, uint64_t stream) {
         BzBnArgs a;
         std::memset(&a, 0, sizeof(a));
         a.x = as_ptr<const void>(x);
@@ -234,7 +240,24 @@ PYBIND11_MODULE(_C, m) {
         a.dbeta = as_ptr<float>(dbeta);
         a.coef = as_ptr<float>(coef);
         a.relu = relu;
+        a.ymask = as_ptr<const void>(ymask);
+        a.dres = as_ptr<void>(dres);
+        a.counter = as_ptr<unsigned>(counter);
         check(bz_bn_backward(&a, sm_count, as_stream(stream)), "bn_backward");
+      });
+  m.def(
+      "maxpool_forward",
+      [](uint64_t x, uint64_t y, uint64_t idx, int N, int H, int W, int C, int sm_count, uint64_t stream) {
+        check(bz_maxpool3x3s2_forward(as_ptr<const void>(x), as_ptr<void>(y), as_ptr<void>(idx), N, H, W, C,
+                                      sm_count, as_stream(stream)),
+              "maxpool_forward");
+      });
+  m.def(
+      "maxpool_backward",
+      [](uint64_t dy, uint64_t idx, uint64_t dx, int N, int H, int W, int C, int sm_count, uint64_t stream) {
+        check(bz_maxpool3x3s2_backward(as_ptr<const void>(dy), as_ptr<const void>(idx), as_ptr<void>(dx), N, H,
+                                       W, C, sm_count, as_stream(stream)),
+              "maxpool_backward");
       });
   m.def("gram_umma_grid", &bz_gram_umma_grid);
   m.def("gram_umma_tile_cols", &bz_gram_umma_tile_cols);

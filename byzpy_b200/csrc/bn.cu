@@ -6,13 +6,16 @@
 // NHWC path is fp16-only there), which are latency bound at ~25 us per call on 13-50 MB
 // activations that stream in 2-8 us.  The kernels below are plain streaming kernels:
 //
-//   forward   stats_partial  : per-CTA partial (sum, sum of squares) per channel, 16-byte loads
-//             stats_finalize : mean / invstd / running statistics, fused scale+shift
-//             apply          : y = [relu](x * scale[c] + shift[c])
-//   backward  bwd_partial    : per-CTA partial (sum dy', sum dy' * xhat), dy' = dy * [z > 0] (ReLU
-//                              mask recomputed from x, the forward output is not needed)
-//             bwd_finalize   : dgamma, dbeta, per-channel coefficients
-//             bwd_apply      : dx = a * (dy' - c1 - xhat * c2)
+//   forward   reduce<false>  : per-CTA partial (sum, sum of squares) per channel, 16-byte loads; the
+//                              LAST CTA to finish (device counter) folds the partials in fp64 into
+//                              mean / invstd / running statistics / fused scale+shift
+//             apply          : y = [relu](x * scale[c] + shift[c] [+ residual])
+//   backward  reduce<true>   : per-CTA partial (sum dy', sum dy' * xhat), dy' = dy * [y > 0] (mask
+//                              from the saved output when a residual was added, else recomputed
+//                              from x); last CTA: dgamma, dbeta (written straight into the gradient
+//                              arena) and the per-channel coefficients
+//             bwd_apply      : dx = P * dy' + Q * x + S, optionally d(residual) = dy'
+// Two launches per direction; no atomics on data, deterministic summation order.
 //
 // Activations are [R = N*H*W rows][C channels] with C % 8 == 0 (every ResNet width).
 #include <cuda_bf16.h>
@@ -42,13 +45,79 @@ __device__ __forceinline__ Bf8 pack(const float (&f)[8]) {
   return p;
 }
 
+// One warp per channel: lanes stride over the per-CTA partials, shuffle-reduce in fp64.
+// (volatile loads: the partials were written by other CTAs of this launch.)
+__device__ __forceinline__ void reduce_channel(const float* partial, int nblocks, int C, int c, double& s,
+                                               double& q) {
+  const int lane = threadIdx.x & 31;
+  double ls = 0.0, lq = 0.0;
+  for (int b = lane; b < nblocks; b += 32) {
+    const float2 t = __ldcg(reinterpret_cast<const float2*>(partial + ((size_t)b * C + c) * 2));
+    ls += (double)t.x;
+    lq += (double)t.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ls += __shfl_xor_sync(0xffffffffu, ls, o);
+    lq += __shfl_xor_sync(0xffffffffu, lq, o);
+  }
+  s = ls;
+  q = lq;
+}
+
+// Per-channel epilogues executed by the last CTA of a reduction.
+struct Finalize {
+  const float* gamma;
+  const float* beta;
+  float* running_mean;
+  float* running_var;
+  float* mean;
+  float* invstd;
+  float* scale;
+  float* shift;
+  float* dgamma;
+  float* dbeta;
+  float* coef;   // [3][C]:  dx = P * dy' + Q * x + S
+  float eps, momentum;
+
+  __device__ __forceinline__ void forward(int c, long long R, double s, double q) const {
+    const double m = s / (double)R;
+    double var = q / (double)R - m * m;
+    if (var < 0.0) var = 0.0;
+    const float is = (float)(1.0 / sqrt(var + (double)eps));
+    mean[c] = (float)m;
+    invstd[c] = is;
+    const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+    scale[c] = g * is;
+    shift[c] = b - (float)m * g * is;
+    if (running_mean) {
+      const double unbiased = R > 1 ? var * (double)R / (double)(R - 1) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+  }
+  // P = gamma*invstd,  Q = -P*c2*invstd,  S = -P*c1 + P*c2*invstd*mean
+  // (c1 = sum dy'/R, c2 = sum dy' xhat / R)
+  __device__ __forceinline__ void backward(int c, int C, long long R, double s, double q) const {
+    if (dbeta) dbeta[c] = (float)s;
+    if (dgamma) dgamma[c] = (float)q;
+    const double g = gamma ? (double)gamma[c] : 1.0;
+    const double is = (double)invstd[c], mu = (double)mean[c];
+    const double P = g * is, c1 = s / (double)R, c2 = q / (double)R;
+    coef[c] = (float)P;
+    coef[C + c] = (float)(-P * c2 * is);
+    coef[2 * C + c] = (float)(-P * c1 + P * c2 * is * mu);
+  }
+};
+
 // Thread layout shared by the two reduction kernels: cg = C / 8 channel groups along x,
 // rows_per_iter = kThreads / cg row lanes; each CTA owns a contiguous slab of rows.
 template <bool BWD>
 __global__ void __launch_bounds__(kThreads) reduce_partial_kernel(
     const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, long long R, int C,
     const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
-    const float* __restrict__ invstd, int relu, float* __restrict__ partial) {
+    const float* __restrict__ invstd, int relu, const __nv_bfloat16* __restrict__ ymask,
+    float* __restrict__ partial, unsigned* __restrict__ counter, const Finalize fin) {
   extern __shared__ float red[];  // [rows_per_iter][C][2]
   const int cg = C >> 3;
   const int lanes = kThreads / cg;
@@ -85,12 +154,19 @@ __global__ void __launch_bounds__(kThreads) reduce_partial_kernel(
         const Bf8 pd = *reinterpret_cast<const Bf8*>(dy + r * C + g * 8);
         float df[8];
         unpack(pd, df);
+        if (ymask != nullptr) {
+          float yf[8];
+          unpack(*reinterpret_cast<const Bf8*>(ymask + r * C + g * 8), yf);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) df[k] = yf[k] > 0.f ? df[k] : 0.f;
+        } else if (relu) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) df[k] = fmaf(xf[k], sc[k], sh[k]) > 0.f ? df[k] : 0.f;
+        }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          float d = df[k];
-          if (relu && fmaf(xf[k], sc[k], sh[k]) <= 0.f) d = 0.f;
-          a0[k] += d;
-          a1[k] = fmaf(d, (xf[k] - mu[k]) * is[k], a1[k]);
+          a0[k] += df[k];
+          a1[k] = fmaf(df[k], (xf[k] - mu[k]) * is[k], a1[k]);
         }
       }
     }
@@ -110,49 +186,25 @@ __global__ void __launch_bounds__(kThreads) reduce_partial_kernel(
     for (int l = 0; l < lanes; ++l) s += red[(size_t)l * C * 2 + t];
     partial[(size_t)blockIdx.x * C * 2 + t] = s;
   }
-}
-
-// One warp per channel: lanes stride over the per-CTA partials, shuffle-reduce in fp64.
-__device__ __forceinline__ void reduce_channel(const float* __restrict__ partial, int nblocks, int C, int c,
-                                               double& s, double& q) {
-  const int lane = threadIdx.x & 31;
-  double ls = 0.0, lq = 0.0;
-  for (int b = lane; b < nblocks; b += 32) {
-    ls += (double)partial[((size_t)b * C + c) * 2];
-    lq += (double)partial[((size_t)b * C + c) * 2 + 1];
+  // ---- last CTA folds the partials (threadfence-reduction pattern; the counter resets itself)
+  __shared__ bool last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(counter, 1u);
+    last = (prev == gridDim.x - 1);
+    if (last) *counter = 0u;
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    ls += __shfl_xor_sync(0xffffffffu, ls, o);
-    lq += __shfl_xor_sync(0xffffffffu, lq, o);
-  }
-  s = ls;
-  q = lq;
-}
-
-__global__ void __launch_bounds__(kThreads) stats_finalize_kernel(
-    const float* __restrict__ partial, int nblocks, int C, long long R, const float* __restrict__ gamma,
-    const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
-    float* __restrict__ running_var, float* __restrict__ mean, float* __restrict__ invstd,
-    float* __restrict__ scale, float* __restrict__ shift) {
-  const int c = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-  if (c >= C) return;
-  double s, q;
-  reduce_channel(partial, nblocks, C, c, s, q);
-  if ((threadIdx.x & 31) != 0) return;
-  const double m = s / (double)R;
-  double var = q / (double)R - m * m;
-  if (var < 0.0) var = 0.0;
-  const float is = (float)(1.0 / sqrt(var + (double)eps));
-  mean[c] = (float)m;
-  invstd[c] = is;
-  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
-  scale[c] = g * is;
-  shift[c] = b - (float)m * g * is;
-  if (running_mean) {
-    const double unbiased = R > 1 ? var * (double)R / (double)(R - 1) : var;
-    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
-    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  for (int c = threadIdx.x >> 5; c < C; c += kThreads / 32) {
+    double s, q;
+    reduce_channel(partial, (int)gridDim.x, C, c, s, q);
+    if ((threadIdx.x & 31) == 0) {
+      if (BWD) fin.backward(c, C, R, s, q);
+      else fin.forward(c, R, s, q);
+    }
   }
 }
 
@@ -161,7 +213,8 @@ __global__ void __launch_bounds__(kThreads) stats_finalize_kernel(
 __global__ void __launch_bounds__(kThreads) apply_kernel(const __nv_bfloat16* __restrict__ x,
                                                         __nv_bfloat16* __restrict__ y, long long total8,
                                                         int C, const float* __restrict__ scale,
-                                                        const float* __restrict__ shift, int relu) {
+                                                        const float* __restrict__ shift, int relu,
+                                                        const __nv_bfloat16* __restrict__ res) {
   const int cg = C >> 3;
   const long long stride = (long long)gridDim.x * kThreads;
   const long long u0 = (long long)blockIdx.x * kThreads + threadIdx.x;
@@ -184,42 +237,28 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(const __nv_bfloat16* __
         sh[k] = __ldg(shift + g * 8 + k);
       }
     }
-    float f[8];
+    float f[8], rf[8];
     unpack(reinterpret_cast<const Bf8*>(x)[u], f);
+    if (res != nullptr) {
+      unpack(reinterpret_cast<const Bf8*>(res)[u], rf);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) rf[k] = 0.f;
+    }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float v = fmaf(f[k], sc[k], sh[k]);
+      const float v = fmaf(f[k], sc[k], sh[k]) + rf[k];
       f[k] = (relu && v < 0.f) ? 0.f : v;
     }
     reinterpret_cast<Bf8*>(y)[u] = pack(f);
   }
 }
 
-// coef[3][C]:  dx = P * dy' + Q * x + S   with  P = gamma*invstd,  Q = -P*c2*invstd,
-//               S = -P*c1 + P*c2*invstd*mean   (c1 = sum dy'/R, c2 = sum dy' xhat / R)
-__global__ void __launch_bounds__(kThreads) bwd_finalize_kernel(
-    const float* __restrict__ partial, int nblocks, int C, long long R, const float* __restrict__ gamma,
-    const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ dgamma,
-    float* __restrict__ dbeta, float* __restrict__ coef) {
-  const int c = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-  if (c >= C) return;
-  double s, q;
-  reduce_channel(partial, nblocks, C, c, s, q);
-  if ((threadIdx.x & 31) != 0) return;
-  if (dbeta) dbeta[c] = (float)s;
-  if (dgamma) dgamma[c] = (float)q;
-  const double g = gamma ? (double)gamma[c] : 1.0;
-  const double is = (double)invstd[c], mu = (double)mean[c];
-  const double P = g * is, c1 = s / (double)R, c2 = q / (double)R;
-  coef[c] = (float)P;
-  coef[C + c] = (float)(-P * c2 * is);
-  coef[2 * C + c] = (float)(-P * c1 + P * c2 * is * mu);
-}
-
 __global__ void __launch_bounds__(kThreads) bwd_apply_kernel(
     const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
     __nv_bfloat16* __restrict__ dx, long long total8, int C, const float* __restrict__ scale,
-    const float* __restrict__ shift, const float* __restrict__ coef, int relu) {
+    const float* __restrict__ shift, const float* __restrict__ coef, int relu,
+    const __nv_bfloat16* __restrict__ ymask, __nv_bfloat16* __restrict__ dres) {
   const int cg = C >> 3;
   const long long stride = (long long)gridDim.x * kThreads;
   const long long u0 = (long long)blockIdx.x * kThreads + threadIdx.x;
@@ -242,12 +281,18 @@ __global__ void __launch_bounds__(kThreads) bwd_apply_kernel(
     float xf[8], df[8];
     unpack(reinterpret_cast<const Bf8*>(x)[u], xf);
     unpack(reinterpret_cast<const Bf8*>(dy)[u], df);
+    if (ymask != nullptr) {
+      float yf[8];
+      unpack(reinterpret_cast<const Bf8*>(ymask)[u], yf);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float d = df[k];
-      if (relu && fmaf(xf[k], sc[k], sh[k]) <= 0.f) d = 0.f;
-      df[k] = fmaf(P[k], d, fmaf(Q[k], xf[k], S[k]));
+      for (int k = 0; k < 8; ++k) df[k] = yf[k] > 0.f ? df[k] : 0.f;
+    } else if (relu) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) df[k] = fmaf(xf[k], sc[k], sh[k]) > 0.f ? df[k] : 0.f;
     }
+    if (dres != nullptr) reinterpret_cast<Bf8*>(dres)[u] = pack(df);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) df[k] = fmaf(P[k], df[k], fmaf(Q[k], xf[k], S[k]));
     reinterpret_cast<Bf8*>(dx)[u] = pack(df);
   }
 }
@@ -277,42 +322,61 @@ static int check_shape(long long R, int C) {
   return 0;
 }
 
+static Finalize make_finalize(const BzBnArgs* a) {
+  Finalize f;
+  f.gamma = a->gamma;
+  f.beta = a->beta;
+  f.running_mean = a->running_mean;
+  f.running_var = a->running_var;
+  f.mean = a->mean;
+  f.invstd = a->invstd;
+  f.scale = a->scale;
+  f.shift = a->shift;
+  f.dgamma = a->dgamma;
+  f.dbeta = a->dbeta;
+  f.coef = a->coef;
+  f.eps = a->eps;
+  f.momentum = a->momentum;
+  return f;
+}
+
 int bz_bn_forward(const BzBnArgs* a, int sm_count, cudaStream_t stream) {
   if (int e = check_shape(a->R, a->C)) return e;
   const auto* x = reinterpret_cast<const __nv_bfloat16*>(a->x);
   auto* y = reinterpret_cast<__nv_bfloat16*>(a->y);
   const int C = a->C;
   if (a->training) {
+    if (a->counter == nullptr) return (int)cudaErrorInvalidValue;
     const int nb = reduce_blocks(a->R, sm_count);
     const int lanes = kThreads / (C >> 3);
     const size_t smem = (size_t)lanes * C * 2 * sizeof(float);
-    reduce_partial_kernel<false><<<nb, kThreads, smem, stream>>>(x, nullptr, a->R, C, nullptr, nullptr,
-                                                                nullptr, nullptr, 0, a->partial);
-    stats_finalize_kernel<<<(C + 7) / 8, kThreads, 0, stream>>>(
-        a->partial, nb, C, a->R, a->gamma, a->beta, a->eps, a->momentum, a->running_mean,
-        a->running_var, a->mean, a->invstd, a->scale, a->shift);
+    reduce_partial_kernel<false><<<nb, kThreads, smem, stream>>>(
+        x, nullptr, a->R, C, nullptr, nullptr, nullptr, nullptr, 0, nullptr, a->partial, a->counter,
+        make_finalize(a));
   }
   const long long total8 = a->R * (C >> 3);
-  apply_kernel<<<stream_blocks(total8, sm_count), kThreads, 0, stream>>>(x, y, total8, C, a->scale,
-                                                                       a->shift, a->relu);
+  apply_kernel<<<stream_blocks(total8, sm_count), kThreads, 0, stream>>>(
+      x, y, total8, C, a->scale, a->shift, a->relu, reinterpret_cast<const __nv_bfloat16*>(a->res));
   return (int)cudaGetLastError();
 }
 
 int bz_bn_backward(const BzBnArgs* a, int sm_count, cudaStream_t stream) {
   if (int e = check_shape(a->R, a->C)) return e;
+  if (a->counter == nullptr) return (int)cudaErrorInvalidValue;
   const auto* x = reinterpret_cast<const __nv_bfloat16*>(a->x);
   const auto* dy = reinterpret_cast<const __nv_bfloat16*>(a->dy);
+  const auto* ymask = reinterpret_cast<const __nv_bfloat16*>(a->ymask);
   auto* dx = reinterpret_cast<__nv_bfloat16*>(a->dx);
   const int C = a->C;
   const int nb = reduce_blocks(a->R, sm_count);
   const int lanes = kThreads / (C >> 3);
   const size_t smem = (size_t)lanes * C * 2 * sizeof(float);
   reduce_partial_kernel<true><<<nb, kThreads, smem, stream>>>(x, dy, a->R, C, a->scale, a->shift, a->mean,
-                                                             a->invstd, a->relu, a->partial);
-  bwd_finalize_kernel<<<(C + 7) / 8, kThreads, 0, stream>>>(a->partial, nb, C, a->R, a->gamma, a->mean,
-                                                           a->invstd, a->dgamma, a->dbeta, a->coef);
+                                                             a->invstd, a->relu, ymask, a->partial,
+                                                             a->counter, make_finalize(a));
   const long long total8 = a->R * (C >> 3);
   bwd_apply_kernel<<<stream_blocks(total8, sm_count), kThreads, 0, stream>>>(
-      x, dy, dx, total8, C, a->scale, a->shift, a->coef, a->relu);
+      x, dy, dx, total8, C, a->scale, a->shift, a->coef, a->relu, ymask,
+      reinterpret_cast<__nv_bfloat16*>(a->dres));
   return (int)cudaGetLastError();
 }

@@ -150,25 +150,13 @@ __device__ __forceinline__ void sgd_apply(const UpdTable& upd, long long idx, co
 }
 
 
-// Load the n real values of V consecutive coordinates, synthesise virtual
-// rows, run the selection network; returns V results in res[].
+// Values of V coordinates are in v[c][0..n); synthesise virtual rows, run the selection network.
 template <int NP, int V, int MODE>
-__device__ __forceinline__ void cw_unit(const RowTable& rows, const ScaleTable& scales, int n,
-                                        const VirtRows& virt, int f, long long base,
-                                        float (&res)[V]) {
+__device__ __forceinline__ void cw_finish(float (&v)[V][NP], int n, const VirtRows& virt, int f,
+                                          float (&res)[V]) {
   const int nv = virt.count;
   const int nt = n + nv;
   const int apad = NP / 2 - 1 - (nt - 1) / 2;
-  float v[V][NP];
-#pragma unroll
-  for (int i = 0; i < NP; ++i) {
-    if (i < n) {
-      VecIO<NP, V>::load(rows.p[i] + base, v, i, scales.s[i]);
-    } else {
-#pragma unroll
-      for (int c = 0; c < V; ++c) v[c][i] = 0.f;
-    }
-  }
 #pragma unroll
   for (int c = 0; c < V; ++c) {
     if (nv > 0) {
@@ -191,6 +179,82 @@ __device__ __forceinline__ void cw_unit(const RowTable& rows, const ScaleTable& 
       }
     }
     res[c] = cw_pick<NP, MODE>(v[c], nt, f, apad);
+  }
+}
+
+// Load the n real values of V consecutive coordinates straight from the row
+// buffers, then finish; returns V results in res[].
+template <int NP, int V, int MODE>
+__device__ __forceinline__ void cw_unit(const RowTable& rows, const ScaleTable& scales, int n,
+                                        const VirtRows& virt, int f, long long base,
+                                        float (&res)[V]) {
+  float v[V][NP];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    if (i < n) {
+      VecIO<NP, V>::load(rows.p[i] + base, v, i, scales.s[i]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < V; ++c) v[c][i] = 0.f;
+    }
+  }
+  cw_finish<NP, V, MODE>(v, n, virt, f, res);
+}
+
+// ---- cp.async staging: every thread streams ITS OWN next tiles into a private shared-memory
+// slot (so no block barrier is needed, only cp.async.wait_group), which keeps two tiles of loads
+// in flight per thread while the selection network of the current tile runs, at zero register
+// cost.  Slot layout [stage][row][thread][V] is bank-conflict free for both the async writes and
+// the read-back.
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  if constexpr (BYTES == 16) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+  } else {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(s), "l"(gmem), "n"(BYTES) : "memory");
+  }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int NP, int V>
+__device__ __forceinline__ void cw_stage_issue(float* stage, int threads, const RowTable& rows, int n,
+                                               long long base) {
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    if (i < n) cp_async<V * 4>(stage + ((size_t)i * threads + threadIdx.x) * V, rows.p[i] + base);
+  }
+}
+
+template <int NP, int V>
+__device__ __forceinline__ void cw_stage_read(const float* stage, int threads, const ScaleTable& scales,
+                                              int n, float (&v)[V][NP]) {
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    if (i < n) {
+      const float* p = stage + ((size_t)i * threads + threadIdx.x) * V;
+      const float sc = scales.s[i];
+      if constexpr (V == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(p);
+        v[0][i] = canon(t.x * sc);
+        v[1][i] = canon(t.y * sc);
+        v[2][i] = canon(t.z * sc);
+        v[3][i] = canon(t.w * sc);
+      } else if constexpr (V == 2) {
+        const float2 t = *reinterpret_cast<const float2*>(p);
+        v[0][i] = canon(t.x * sc);
+        v[1][i] = canon(t.y * sc);
+      } else {
+        v[0][i] = canon(p[0] * sc);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < V; ++c) v[c][i] = 0.f;
+    }
   }
 }
 

@@ -39,8 +39,54 @@ __global__ void __launch_bounds__(kThreads) cw_select_kernel(const __grid_consta
   }
 }
 
+// Software-pipelined variant: kStages-deep cp.async ring of thread-private tiles.
+constexpr int kStages = 3;
+
+template <int NP, int V, int MODE, int THREADS>
+__global__ void __launch_bounds__(THREADS) cw_select_staged_kernel(const __grid_constant__ BzCwArgs a) {
+  extern __shared__ __align__(16) float stage_mem[];
+  const int n = a.n;
+  const size_t stage_elems = (size_t)n * THREADS * V;
+  const long long nvec = a.len / V;
+  const long long stride = (long long)gridDim.x * THREADS;
+  const long long u0 = (long long)blockIdx.x * THREADS + threadIdx.x;
+#pragma unroll
+  for (int s = 0; s < kStages - 1; ++s) {
+    const long long u = u0 + s * stride;
+    if (u < nvec) cw_stage_issue<NP, V>(stage_mem + s * stage_elems, THREADS, a.rows, n, a.off + u * V);
+    cp_async_commit();
+  }
+  int slot = 0;
+  for (long long u = u0; u < nvec; u += stride) {
+    {
+      const long long un = u + (kStages - 1) * stride;
+      int sn = slot + kStages - 1;
+      if (sn >= kStages) sn -= kStages;
+      if (un < nvec) cw_stage_issue<NP, V>(stage_mem + sn * stage_elems, THREADS, a.rows, n, a.off + un * V);
+      cp_async_commit();
+    }
+    cp_async_wait<kStages - 1>();
+    float v[V][NP];
+    cw_stage_read<NP, V>(stage_mem + slot * stage_elems, THREADS, a.scales, n, v);
+    float res[V];
+    cw_finish<NP, V, MODE>(v, n, a.virt, a.f, res);
+    const long long base = a.off + u * V;
+    if (a.out != nullptr) {
+      if constexpr (V == 4) {
+        stg_stream4(a.out + base, make_float4(res[0], res[1], res[2], res[3]));
+      } else {
+#pragma unroll
+        for (int c = 0; c < V; ++c) a.out[base + c] = res[c];
+      }
+    }
+    if (a.upd.count > 0) sgd_apply<V>(a.upd, base, res);
+    if (++slot == kStages) slot = 0;
+  }
+  cp_async_wait<0>();
+}
+
 template <int NP, int V, int MODE>
-int launch_one(const BzCwArgs& a, int sm_count, cudaStream_t stream) {
+int launch_direct(const BzCwArgs& a, int sm_count, cudaStream_t stream) {
   const long long nvec = a.len / V;
   if (nvec <= 0) return 0;
   long long blocks = (nvec + kThreads - 1) / kThreads;
@@ -58,6 +104,45 @@ int launch_one(const BzCwArgs& a, int sm_count, cudaStream_t stream) {
   if (blocks > cap) blocks = cap;
   cw_select_kernel<NP, V, MODE><<<(unsigned)blocks, kThreads, 0, stream>>>(a);
   return (int)cudaGetLastError();
+}
+
+template <int NP, int V, int MODE>
+int launch_staged(const BzCwArgs& a, int sm_count, cudaStream_t stream) {
+  constexpr int THREADS = (NP >= 128) ? 128 : 256;
+  const long long nvec = a.len / V;
+  if (nvec <= 0) return 0;
+  const size_t smem = (size_t)kStages * a.n * THREADS * V * sizeof(float);
+  if (smem > 220 * 1024) return launch_direct<NP, V, MODE>(a, sm_count, stream);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(cw_select_staged_kernel<NP, V, MODE, THREADS>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cw_select_staged_kernel<NP, V, MODE, THREADS>,
+                                                    THREADS, smem) != cudaSuccess || occ < 1)
+    occ = 1;
+  long long blocks = (nvec + THREADS - 1) / THREADS;
+  const long long cap = (long long)sm_count * occ;
+  if (blocks > cap) blocks = cap;
+  cw_select_staged_kernel<NP, V, MODE, THREADS><<<(unsigned)blocks, THREADS, smem, stream>>>(a);
+  return (int)cudaGetLastError();
+}
+
+template <int NP, int V, int MODE>
+int launch_one(const BzCwArgs& a, int sm_count, cudaStream_t stream) {
+  // auto: the direct kernel is at the HBM roofline for the pruned median network up to 8 rows and
+  // for the plain mean; everything with a longer ALU phase per tile is latency bound without the
+  // cp.async pipeline (profiles/cw_select.md).
+  bool staged = (MODE == BZ_CW_TRMEAN || MODE == BZ_CW_MEAMED || (MODE == BZ_CW_MEDIAN && NP >= 16));
+  if (a.impl == 1) staged = false;
+  if (a.impl == 2) staged = true;
+  // short vectors: one tile per thread, nothing to pipeline
+  if (a.impl == 0 && a.len / V < (long long)sm_count * kThreads * 2) staged = false;
+  return staged ? launch_staged<NP, V, MODE>(a, sm_count, stream)
+                : launch_direct<NP, V, MODE>(a, sm_count, stream);
 }
 
 template <int NP, int MODE>

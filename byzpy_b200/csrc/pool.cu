@@ -1,0 +1,164 @@
+// 3x3 / stride 2 / pad 1 max pooling for NHWC bf16 activations (the ResNet stem pool).
+//
+// ATen's max_pool_{forward,backward}_nhwc take 107 us / 227 us on the 32x64x112x112 stem activation
+// (profiles/bench_log.md) -- the backward alone is 6 % of a replica's step.  Both directions here
+// are pure streaming kernels with 16-byte accesses (8 channels per thread):
+//   forward   y = max over the window, plus a one-byte window position (kh*3+kw) per output element;
+//             scan order and the strict '>' (NaN propagates) match ATen, so ties pick the same element
+//   backward  GATHER form: each input element looks at the <= 4 windows that contain it and sums the
+//             dy whose recorded position is this element -- no atomics, deterministic.
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "pool.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct alignas(16) Bf8 {
+  __nv_bfloat162 v[4];
+};
+struct alignas(8) Idx8 {
+  uint8_t b[8];
+};
+
+__device__ __forceinline__ void unpack(const Bf8& p, float (&f)[8]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 t = __bfloat1622float2(p.v[k]);
+    f[2 * k] = t.x;
+    f[2 * k + 1] = t.y;
+  }
+}
+__device__ __forceinline__ Bf8 pack(const float (&f)[8]) {
+  Bf8 p;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) p.v[k] = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+  return p;
+}
+
+__global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                              __nv_bfloat16* __restrict__ y,
+                                                              uint8_t* __restrict__ idx, int N, int H, int W,
+                                                              int C, int Ho, int Wo) {
+  const int cg = C >> 3;
+  const long long total = (long long)N * Ho * Wo * cg;
+  const long long stride = (long long)gridDim.x * kThreads;
+  for (long long u = (long long)blockIdx.x * kThreads + threadIdx.x; u < total; u += stride) {
+    const int g = (int)(u % cg);
+    long long t = u / cg;
+    const int ow = (int)(t % Wo);
+    t /= Wo;
+    const int oh = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    float m[8];
+    uint8_t am[8];
+    bool first = true;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int ih = 2 * oh - 1 + kh;
+      if (ih < 0 || ih >= H) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int iw = 2 * ow - 1 + kw;
+        if (iw < 0 || iw >= W) continue;
+        float f[8];
+        unpack(*reinterpret_cast<const Bf8*>(x + (((long long)n * H + ih) * W + iw) * C + g * 8), f);
+        const uint8_t code = (uint8_t)(kh * 3 + kw);
+        if (first) {
+          // ATen starts from -inf with the first in-range position as the index
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            m[k] = -__builtin_huge_valf();
+            am[k] = code;
+          }
+          first = false;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (f[k] > m[k] || f[k] != f[k]) {
+            m[k] = f[k];
+            am[k] = code;
+          }
+        }
+      }
+    }
+    *reinterpret_cast<Bf8*>(y + u * 8) = pack(m);
+    Idx8 o;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o.b[k] = am[k];
+    *reinterpret_cast<Idx8*>(idx + u * 8) = o;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                              const uint8_t* __restrict__ idx,
+                                                              __nv_bfloat16* __restrict__ dx, int N, int H,
+                                                              int W, int C, int Ho, int Wo) {
+  const int cg = C >> 3;
+  const long long total = (long long)N * H * W * cg;
+  const long long stride = (long long)gridDim.x * kThreads;
+  for (long long u = (long long)blockIdx.x * kThreads + threadIdx.x; u < total; u += stride) {
+    const int g = (int)(u % cg);
+    long long t = u / cg;
+    const int iw = (int)(t % W);
+    t /= W;
+    const int ih = (int)(t % H);
+    const int n = (int)(t / H);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    // windows containing row ih: oh with 2*oh-1 <= ih <= 2*oh+1
+    const int oh0 = ih >> 1, oh1 = (ih + 1) >> 1;
+    const int ow0 = iw >> 1, ow1 = (iw + 1) >> 1;
+    for (int oh = oh0; oh <= oh1; ++oh) {
+      if (oh >= Ho) continue;
+      const int kh = ih - (2 * oh - 1);
+      for (int ow = ow0; ow <= ow1; ++ow) {
+        if (ow >= Wo) continue;
+        const int kw = iw - (2 * ow - 1);
+        const uint8_t code = (uint8_t)(kh * 3 + kw);
+        const long long o = (((long long)n * Ho + oh) * Wo + ow) * cg + g;
+        const Idx8 id = *reinterpret_cast<const Idx8*>(idx + o * 8);
+        float d[8];
+        unpack(*reinterpret_cast<const Bf8*>(dy + o * 8), d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += (id.b[k] == code) ? d[k] : 0.f;
+      }
+    }
+    *reinterpret_cast<Bf8*>(dx + u * 8) = pack(acc);
+  }
+}
+
+int blocks_for(long long total, int sm_count) {
+  long long b = (total + kThreads - 1) / kThreads;
+  const long long cap = (long long)sm_count * 8;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace
+
+int bz_maxpool3x3s2_forward(const void* x, void* y, void* idx, int N, int H, int W, int C, int sm_count,
+                            cudaStream_t stream) {
+  if (N < 1 || H < 1 || W < 1 || C < 8 || (C % 8) != 0) return (int)cudaErrorInvalidValue;
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;  // floor((H + 2 - 3) / 2) + 1
+  const long long total = (long long)N * Ho * Wo * (C >> 3);
+  maxpool_fwd_kernel<<<blocks_for(total, sm_count), kThreads, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y),
+      reinterpret_cast<uint8_t*>(idx), N, H, W, C, Ho, Wo);
+  return (int)cudaGetLastError();
+}
+
+int bz_maxpool3x3s2_backward(const void* dy, const void* idx, void* dx, int N, int H, int W, int C,
+                             int sm_count, cudaStream_t stream) {
+  if (N < 1 || H < 1 || W < 1 || C < 8 || (C % 8) != 0) return (int)cudaErrorInvalidValue;
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const long long total = (long long)N * H * W * (C >> 3);
+  maxpool_bwd_kernel<<<blocks_for(total, sm_count), kThreads, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const uint8_t*>(idx),
+      reinterpret_cast<__nv_bfloat16*>(dx), N, H, W, C, Ho, Wo);
+  return (int)cudaGetLastError();
+}

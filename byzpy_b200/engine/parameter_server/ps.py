@@ -54,7 +54,9 @@ class ParameterServer:
                  process_group=None, lr: Optional[float] = None, momentum: Optional[float] = None,
                  weight_decay: Optional[float] = None, amp_dtype: Optional[torch.dtype] = torch.bfloat16,
                  use_cuda_graph: bool = True, worker_streams: int = 1, fused: Optional[bool] = None,
-                 node_timeout: Optional[float] = None, tolerate_failures: bool = False):
+                 node_timeout: Optional[float] = None, tolerate_failures: bool = False,
+                 direct_grads: bool = True, overlap_wgrad: bool = True):
+        self._device_opts = dict(direct_grads=direct_grads, overlap_wgrad=overlap_wgrad)
         self.hon = list(honest_nodes)
         self.byz = list(byzantine_nodes)
         self.agg = aggregator
@@ -134,7 +136,7 @@ class ParameterServer:
             weight_decay=first.weight_decay if weight_decay is None else weight_decay,
             update_byzantines=self.update_byz, device=first.device, group=group,
             amp_dtype=amp_dtype, use_cuda_graph=use_cuda_graph, worker_streams=worker_streams,
-            virtual_fold=virtual_fold)
+            virtual_fold=virtual_fold, **self._device_opts)
 
     def _fused_plan(self, n_rows: int):
         """Aggregator plan, composed in n-space with a linear pre-aggregator when present:

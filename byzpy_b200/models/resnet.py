@@ -14,12 +14,21 @@ import torch
 import torch.nn as nn
 
 
+def _conv(cin: int, cout: int, k: int, stride: int = 1, padding: int = 0) -> nn.Conv2d:
+    """``nn.Conv2d`` subclass that can produce its weight gradient in place in the gradient arena,
+    on a side stream (ops/fused_layers.py); identical to ``nn.Conv2d`` until a device worker
+    switches that mode on."""
+    from ..ops.fused_layers import ArenaConv2d
+
+    return ArenaConv2d(cin, cout, k, stride=stride, padding=padding, bias=False)
+
+
 def _conv3x3(cin: int, cout: int, stride: int = 1) -> nn.Conv2d:
-    return nn.Conv2d(cin, cout, 3, stride=stride, padding=1, bias=False)
+    return _conv(cin, cout, 3, stride, 1)
 
 
 def _conv1x1(cin: int, cout: int, stride: int = 1) -> nn.Conv2d:
-    return nn.Conv2d(cin, cout, 1, stride=stride, bias=False)
+    return _conv(cin, cout, 1, stride)
 
 
 def _bn(channels: int, relu: bool = False) -> nn.BatchNorm2d:
@@ -40,14 +49,13 @@ class BasicBlock(nn.Module):
         self.bn1 = _bn(width, relu=True)
         self.relu = nn.ReLU(inplace=True)
         self.conv2 = _conv3x3(width, width)
-        self.bn2 = _bn(width)
+        self.bn2 = _bn(width, relu=True)     # relu(bn2(.) + identity) in one kernel
         self.downsample = downsample
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         idt = x if self.downsample is None else self.downsample(x)
         y = self.bn1(self.conv1(x))          # ReLU fused into bn1
-        y = self.bn2(self.conv2(y))
-        return self.relu(y + idt)
+        return self.bn2(self.conv2(y), idt)  # residual add + ReLU fused into bn2
 
 
 class Bottleneck(nn.Module):
@@ -60,7 +68,7 @@ class Bottleneck(nn.Module):
         self.conv2 = _conv3x3(width, width, stride)
         self.bn2 = _bn(width, relu=True)
         self.conv3 = _conv1x1(width, width * 4)
-        self.bn3 = _bn(width * 4)
+        self.bn3 = _bn(width * 4, relu=True)  # relu(bn3(.) + identity) in one kernel
         self.relu = nn.ReLU(inplace=True)
         self.downsample = downsample
 
@@ -68,8 +76,7 @@ class Bottleneck(nn.Module):
         idt = x if self.downsample is None else self.downsample(x)
         y = self.bn1(self.conv1(x))          # ReLU fused
         y = self.bn2(self.conv2(y))          # ReLU fused
-        y = self.bn3(self.conv3(y))
-        return self.relu(y + idt)
+        return self.bn3(self.conv3(y), idt)  # residual add + ReLU fused
 
 
 class ResNet(nn.Module):
@@ -78,11 +85,13 @@ class ResNet(nn.Module):
         super().__init__()
         self._cin = 64
         if small_input:  # CIFAR-style stem
-            self.conv1 = nn.Conv2d(in_channels, 64, 3, stride=1, padding=1, bias=False)
+            self.conv1 = _conv(in_channels, 64, 3, 1, 1)
             self.maxpool = nn.Identity()
         else:
-            self.conv1 = nn.Conv2d(in_channels, 64, 7, stride=2, padding=3, bias=False)
-            self.maxpool = nn.MaxPool2d(3, stride=2, padding=1)
+            from ..ops.fused_layers import FusedMaxPool2d
+
+            self.conv1 = _conv(in_channels, 64, 7, 2, 3)
+            self.maxpool = FusedMaxPool2d(3, stride=2, padding=1)
         self.bn1 = _bn(64, relu=True)
         self.relu = nn.ReLU(inplace=True)
         self.layer1 = self._stage(block, 64, depths[0], 1)
@@ -90,7 +99,9 @@ class ResNet(nn.Module):
         self.layer3 = self._stage(block, 256, depths[2], 2)
         self.layer4 = self._stage(block, 512, depths[3], 2)
         self.avgpool = nn.AdaptiveAvgPool2d(1)
-        self.fc = nn.Linear(512 * block.expansion, num_classes)
+        from ..ops.fused_layers import ArenaLinear
+
+        self.fc = ArenaLinear(512 * block.expansion, num_classes)
         for m in self.modules():
             if isinstance(m, nn.Conv2d):
                 nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")

@@ -42,6 +42,19 @@ def _load_ext():
     return _C
 
 
+# Kernel launches issued from Python-side layer wrappers (fused BN / pooling), so the training engine
+# can report how many of this library's kernels a step contains (bench.py "gpu_launches").
+_LAUNCHES = [0]
+
+
+def count_launch(k: int = 1) -> None:
+    _LAUNCHES[0] += k
+
+
+def launches() -> int:
+    return _LAUNCHES[0]
+
+
 def extension_available() -> bool:
     return _load_ext() is not None
 
@@ -127,8 +140,12 @@ def cw_select(
     virtual: Optional[Tuple[int, int, float, float]] = None,
     out: Optional[torch.Tensor] = None,
     update: Optional[dict] = None,
+    impl: str = "auto",
 ) -> torch.Tensor:
     """Coordinate-wise select over n rows.
+
+    ``impl``: ``"auto"`` | ``"direct"`` (register loads) | ``"staged"`` (cp.async pipeline); the
+    two CUDA variants are bit-identical, the knob exists for benchmarking.
 
     ``virtual=(count, n_honest, a, b)`` appends ``count`` synthesised rows equal
     to ``a*mean + b*std`` of the first ``n_honest`` rows (Little / Empire).
@@ -155,7 +172,7 @@ def cw_select(
             [r.data_ptr() for r in rows], _scales(scales, n), mode, int(f), int(nv), int(nh),
             float(va), float(vb), 0, d, out.data_ptr(),
             [p.data_ptr() for p in params], [m.data_ptr() for m in moms],
-            lr, mu, wd, sm_count(dev), _stream(dev),
+            lr, mu, wd, sm_count(dev), _stream(dev), {"auto": 0, "direct": 1, "staged": 2}[impl],
         )
         return out
     res = ref.cw_select(rows, mode, f, scales=scales, virtual=virtual)

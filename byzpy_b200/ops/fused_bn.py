@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import _stream, require_ext, sm_count
+from . import _stream, count_launch, require_ext, sm_count
 
 
 def _eligible(x: torch.Tensor) -> bool:
@@ -23,9 +23,22 @@ def _eligible(x: torch.Tensor) -> bool:
             and x.numel() > 0)
 
 
+def _direct_grad_ptrs(mod, weight, bias):
+    """Arena pointers for dgamma / dbeta when the layer is in direct-gradient mode: the backward
+    kernel then writes the parameter gradients in place (no AccumulateGrad add, no temporaries)."""
+    if mod is None or not getattr(mod, "_direct_grad", False) or weight is None or bias is None:
+        return None
+    gw, gb = weight.grad, bias.grad
+    if (gw is None or gb is None or gw.dtype != torch.float32 or gb.dtype != torch.float32
+            or not gw.is_contiguous() or not gb.is_contiguous() or gw.device != weight.device):
+        return None
+    return gw.data_ptr(), gb.data_ptr()
+
+
 class _FusedBN(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, running_mean, running_var, training, momentum, eps, relu):
+    def forward(ctx, x, weight, bias, residual, running_mean, running_var, training, momentum, eps, relu,
+                ctr, mod):
         ext = require_ext()
         N, C, H, W = x.shape
         R = N * H * W
@@ -52,16 +65,24 @@ class _FusedBN(torch.autograd.Function):
                        running_mean.data_ptr() if (training and running_mean is not None) else 0,
                        running_var.data_ptr() if (training and running_var is not None) else 0,
                        mean.data_ptr(), invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(), pptr,
-                       float(eps), float(momentum), int(relu), int(training), sms, _stream(dev))
-        ctx.save_for_backward(x, weight, stats)
+                       float(eps), float(momentum), int(relu), int(training),
+                       residual.data_ptr() if residual is not None else 0, ctr[0:1].data_ptr(),
+                       sms, _stream(dev))
+        count_launch(2 if training else 1)
+        ctx.has_res = residual is not None
+        # with a residual the ReLU mask cannot be recomputed from x alone: keep the output (the next
+        # layer saves it anyway, so this costs no memory)
+        ctx.save_for_backward(x, weight, stats, ctr, y if (ctx.has_res and relu) else None)
         ctx.relu = bool(relu)
         ctx.training = bool(training)
+        ctx.mod = mod
+        ctx.bias = bias
         return y
 
     @staticmethod
     def backward(ctx, dy):
         ext = require_ext()
-        x, weight, stats = ctx.saved_tensors
+        x, weight, stats, ctr, ysaved = ctx.saved_tensors
         N, C, H, W = x.shape
         R = N * H * W
         dev = x.device
@@ -69,49 +90,76 @@ class _FusedBN(torch.autograd.Function):
         dy = dy.contiguous(memory_format=torch.channels_last)
         if dy.dtype != torch.bfloat16:
             dy = dy.to(torch.bfloat16)
-        dx = torch.empty_like(x, memory_format=torch.channels_last)
         mean, invstd, scale, shift = stats[0], stats[1], stats[2], stats[3]
+        nones = (None,) * 8
         if not ctx.training:
             # eval mode: statistics are constants -> dx = dy' * scale
-            z = x.float() * scale.view(1, C, 1, 1) + shift.view(1, C, 1, 1)
-            d = dy.float() * ((z > 0) if ctx.relu else 1.0)
+            d = dy.float()
+            if ctx.relu:
+                if ysaved is not None:
+                    d = d * (ysaved > 0)
+                else:
+                    d = d * ((x.float() * scale.view(1, C, 1, 1) + shift.view(1, C, 1, 1)) > 0)
             dxe = (d * scale.view(1, C, 1, 1)).to(torch.bfloat16)
             xhat = (x.float() - mean.view(1, C, 1, 1)) * invstd.view(1, C, 1, 1)
             dg = (d * xhat).sum(dim=(0, 2, 3)) if weight is not None else None
             db = d.sum(dim=(0, 2, 3)) if weight is not None else None
-            return dxe, dg, db, None, None, None, None, None, None
+            dres = d.to(torch.bfloat16) if ctx.has_res else None
+            return (dxe, dg, db, dres) + nones
+        dx = torch.empty_like(x, memory_format=torch.channels_last)
         nb = ext.bn_partial_blocks(R, sms)
         partial = torch.empty((nb, C, 2), dtype=torch.float32, device=dev)
-        grads = torch.empty((5, C), dtype=torch.float32, device=dev)  # dgamma, dbeta, coef[3]
+        direct = _direct_grad_ptrs(ctx.mod, weight, ctx.bias)
+        grads = torch.empty((3 if direct else 5, C), dtype=torch.float32, device=dev)  # coef[3] (+ dgamma, dbeta)
+        if direct:
+            dg_ptr, db_ptr = direct
+        else:
+            dg_ptr, db_ptr = grads[3].data_ptr(), grads[4].data_ptr()
+        dres = None
+        dres_ptr = 0
+        if ctx.has_res:
+            if ctx.relu:
+                dres = torch.empty_like(x, memory_format=torch.channels_last)
+                dres_ptr = dres.data_ptr()
+            else:
+                dres = dy
         ext.bn_backward(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), R, C,
                         weight.data_ptr() if weight is not None else 0, mean.data_ptr(), invstd.data_ptr(),
-                        scale.data_ptr(), shift.data_ptr(), partial.data_ptr(), grads[0].data_ptr(),
-                        grads[1].data_ptr(), grads[2].data_ptr(), int(ctx.relu), sms, _stream(dev))
-        dg = grads[0] if weight is not None else None
-        db = grads[1] if weight is not None else None
-        return dx, dg, db, None, None, None, None, None, None
+                        scale.data_ptr(), shift.data_ptr(), partial.data_ptr(), dg_ptr, db_ptr,
+                        grads[0].data_ptr(), int(ctx.relu), ysaved.data_ptr() if ysaved is not None else 0,
+                        dres_ptr, ctr[1:2].data_ptr(), sms, _stream(dev))
+        count_launch(2)
+        if direct or weight is None:
+            return (dx, None, None, dres) + nones
+        return (dx, grads[3], grads[4], dres) + nones
 
 
 class FusedBatchNorm2d(nn.BatchNorm2d):
-    """``nn.BatchNorm2d`` with an optional fused ReLU and hand-written sm_100a kernels."""
+    """``nn.BatchNorm2d`` with an optional fused residual add + ReLU and hand-written sm_100a
+    kernels: ``forward(x, residual=None)`` returns ``[relu](bn(x) [+ residual])``."""
 
     def __init__(self, num_features: int, eps: float = 1e-5, momentum: float = 0.1, affine: bool = True,
                  track_running_stats: bool = True, relu: bool = False, device=None, dtype=None):
         super().__init__(num_features, eps=eps, momentum=momentum, affine=affine,
                          track_running_stats=track_running_stats, device=device, dtype=dtype)
         self.fused_relu = relu
+        # last-CTA detection words of the forward / backward reductions (self-resetting)
+        self.register_buffer("_ctr", torch.zeros(2, dtype=torch.int32, device=device), persistent=False)
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
         use_batch_stats = self.training or not self.track_running_stats
-        if (_eligible(x) and self.momentum is not None
-                and (use_batch_stats or self.running_mean is not None)):
+        if (_eligible(x) and self.momentum is not None and self._ctr.device == x.device
+                and (use_batch_stats or self.running_mean is not None)
+                and (residual is None or (_eligible(residual) and residual.shape == x.shape))):
             if self.training and self.track_running_stats and self.num_batches_tracked is not None:
                 self.num_batches_tracked.add_(1)
-            return _FusedBN.apply(x, self.weight, self.bias,
+            return _FusedBN.apply(x, self.weight, self.bias, residual,
                                   self.running_mean if self.track_running_stats else None,
                                   self.running_var if self.track_running_stats else None,
-                                  use_batch_stats, self.momentum, self.eps, self.fused_relu)
+                                  use_batch_stats, self.momentum, self.eps, self.fused_relu, self._ctr, self)
         y = super().forward(x)
+        if residual is not None:
+            y = y + residual
         return F.relu(y) if self.fused_relu else y
 
 

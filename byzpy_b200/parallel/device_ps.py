@@ -97,6 +97,7 @@ class DeviceWorker:
         self.static_x: Optional[torch.Tensor] = None
         self.static_y: Optional[torch.Tensor] = None
         self.loss_slot: Optional[torch.Tensor] = None
+        self.sink = None            # ops.fused_layers.GradSink once direct gradients are on
 
     # filled in by the engine
     def bind(self, flat_params: torch.Tensor, flat_grads: torch.Tensor, mom: Optional[torch.Tensor],
@@ -104,6 +105,13 @@ class DeviceWorker:
         self.arena = ParamArena(self.model, flat_params=flat_params, flat_grads=flat_grads)
         self.mom = mom
         self.loss_slot = loss_slot
+
+    def enable_direct_grads(self, side_stream: Optional["torch.cuda.Stream"] = None) -> None:
+        """Let the replica's own layer types (models/resnet.py) write their parameter gradients
+        straight into the arena row, weight gradients on ``side_stream`` (ops/fused_layers.py)."""
+        from ..ops.fused_layers import enable_direct_grads
+
+        self.sink = enable_direct_grads(self.model, side_stream=side_stream)
 
     def stage_batch(self, x: torch.Tensor, y: torch.Tensor) -> None:
         """Copy this step's inputs (typically pinned host tensors) into static device buffers."""
@@ -125,6 +133,8 @@ class DeviceWorker:
             out = self.model(x)
             loss = self.loss_fn(out, self.static_y)
         loss.backward()
+        if self.sink is not None:
+            self.sink.join()        # weight gradients produced on the side stream are now ordered
         self.loss_slot.copy_(loss.detach().float())
 
     def state_dict_cpu(self):
@@ -171,7 +181,8 @@ class DeviceRound:
                  update_byzantines: bool = False, device: Optional[torch.device] = None,
                  group=None, amp_dtype: Optional[torch.dtype] = torch.bfloat16,
                  use_cuda_graph: bool = True, worker_streams: int = 1,
-                 virtual_fold: Optional[RowFold] = None):
+                 virtual_fold: Optional[RowFold] = None, direct_grads: bool = True,
+                 overlap_wgrad: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("DeviceRound needs a CUDA device (B200)")
         self.ext = ops.require_ext()
@@ -234,8 +245,17 @@ class DeviceRound:
         self.shard_len = sh if self.rank < self.world - 1 else self.d_pad - sh * (self.world - 1)
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._side_streams = [torch.cuda.Stream(self.device) for _ in range(max(0, worker_streams - 1))]
+        # one weight-gradient stream per worker stream: backward's dgrad chain stays on the worker
+        # stream, the wgrad GEMMs of the same replica overlap with it
+        self._wgrad_streams = ([torch.cuda.Stream(self.device) for _ in range(1 + len(self._side_streams))]
+                               if (direct_grads and overlap_wgrad) else [])
+        if direct_grads:
+            for i, w in enumerate(self.workers):
+                w.enable_direct_grads(self._wgrad_streams[i % len(self._wgrad_streams)]
+                                      if self._wgrad_streams else None)
         self._gram_ws = None
         self.launches_per_step = 0
+        self.model_launches_per_step = 0
         if isinstance(plan, GramPlan):
             self._setup_gram_plan()
             if not plan.capturable:
@@ -402,6 +422,7 @@ class DeviceRound:
 
     def _body(self) -> None:
         main = torch.cuda.current_stream(self.device)
+        l0 = ops.launches()
         if self._side_streams:
             streams = [main] + self._side_streams
             for s in self._side_streams:
@@ -414,6 +435,7 @@ class DeviceRound:
         else:
             for w in self.workers:
                 w.forward_backward(self.amp_dtype)
+        self.model_launches_per_step = ops.launches() - l0   # this library's BN / pooling kernels
         self.launch_aggregate()
 
     def capture(self, warmup: int = 2) -> None:
