@@ -31,7 +31,7 @@ def main():
     for g in range(a.workers):
         torch.manual_seed(0)
         m = build_model("resnet18", num_classes=1000)
-        kw = dict(lr=0.05, momentum=0.9, device=str(dev), preprocess=B.preprocess_uint8_nhwc)
+        kw = dict(lr=0.05, momentum=0.9, device=str(dev), preprocess=B.preprocess_fused)
         if g < a.workers - 2:
             hon.append(DeviceHonestNode(m, **kw))
         else:

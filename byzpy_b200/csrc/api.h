@@ -74,3 +74,7 @@ int bz_gaussian(float* dst, float mu, float sigma, unsigned long long seed,
                 unsigned long long offset, long long len, int sm_count, cudaStream_t stream);
 int bz_sgd(const float* grad, const UpdTable* upd, long long len, int sm_count,
            cudaStream_t stream);
+
+// uint8 [..., C] -> bf16 (x - mean[c]) * scale[c], same element order (C <= 8, 16-byte aligned buffers).
+int bz_u8_affine(const void* in, void* out, long long n, int C, const float* mean, const float* scale,
+                 int sm_count, cudaStream_t stream);

@@ -13,8 +13,12 @@
 #include <vector>
 
 #include "api.h"
+#include <algorithm>
+#include <stdexcept>
+
 #include "bn.h"
 #include "pool.h"
+#include "layout.h"
 #include "gram_umma.h"
 #include "nspace.h"
 #include "runtime.h"
@@ -164,6 +168,13 @@ PYBIND11_MODULE(_C, m) {
       py::arg("rows"), py::arg("scales"), py::arg("a"), py::arg("b"), py::arg("off"),
       py::arg("len"), py::arg("out"), py::arg("sm_count"), py::arg("stream"));
 
+  m.def("u8_affine", [](uint64_t in, uint64_t out, long long n, int C, const std::vector<float>& mean,
+                        const std::vector<float>& scale, int sm_count, uint64_t stream) {
+    if ((int)mean.size() < C || (int)scale.size() < C) throw std::invalid_argument("u8_affine: mean/scale");
+    check(bz_u8_affine(as_ptr<const void>(in), as_ptr<void>(out), n, C, mean.data(), scale.data(), sm_count,
+                       as_stream(stream)),
+          "u8_affine");
+  });
   m.def("scale_copy", [](uint64_t src, uint64_t dst, float scale, long long len, int sm_count,
                          uint64_t stream) {
     check(bz_scale_copy(as_ptr<const float>(src), as_ptr<float>(dst), scale, len, sm_count,
@@ -192,7 +203,7 @@ PYBIND11_MODULE(_C, m) {
       "bn_forward",
       [](uint64_t x, uint64_t y, long long R, int C, uint64_t gamma, uint64_t beta, uint64_t rmean,
          uint64_t rvar, uint64_t mean, uint64_t invstd, uint64_t scale, uint64_t shift, uint64_t partial,
-         float eps, float momentum, int relu, int training, uint64_t res, uint64_t counter, int sm_count,
+         float eps, float momentum, int relu, int training, uint64_t res, int sm_count,
          uint64_t stream) {
         BzBnArgs a;
         std::memset(&a, 0, sizeof(a));
@@ -214,15 +225,14 @@ PYBIND11_MODULE(_C, m) {
         a.relu = relu;
         a.training = training;
         a.res = as_ptr<const void>(res);
-        a.counter = as_ptr<unsigned>(counter);
         check(bz_bn_forward(&a, sm_count, as_stream(stream)), "bn_forward");
       });
   m.def(
       "bn_backward",
       [](uint64_t x, uint64_t dy, uint64_t dx, long long R, int C, uint64_t gamma, uint64_t mean,
          uint64_t invstd, uint64_t scale, uint64_t shift, uint64_t partial, uint64_t dgamma,
-         uint64_t dbeta, uint64_t coef, int relu, uint64_t ymask, uint64_t dres, uint64_t counter,
-         int sm_count, uint64_t stream) {
+         uint64_t dbeta, uint64_t coef, int relu, uint64_t ymask, uint64_t dres, int sm_count,
+         uint64_t stream) {
         BzBnArgs a;
         std::memset(&a, 0, sizeof(a));
         a.x = as_ptr<const void>(x);
@@ -242,7 +252,6 @@ PYBIND11_MODULE(_C, m) {
         a.relu = relu;
         a.ymask = as_ptr<const void>(ymask);
         a.dres = as_ptr<void>(dres);
-        a.counter = as_ptr<unsigned>(counter);
         check(bz_bn_backward(&a, sm_count, as_stream(stream)), "bn_backward");
       });
   m.def(
@@ -258,6 +267,35 @@ PYBIND11_MODULE(_C, m) {
         check(bz_maxpool3x3s2_backward(as_ptr<const void>(dy), as_ptr<const void>(idx), as_ptr<void>(dx), N, H,
                                        W, C, sm_count, as_stream(stream)),
               "maxpool_backward");
+      });
+  m.def(
+      "krsc_cast",
+      [](const std::vector<uint64_t>& src, const std::vector<uint64_t>& dst, const std::vector<int>& K,
+         const std::vector<int>& C, const std::vector<int>& RS, int to_grad, uint64_t stream) {
+        const size_t n = src.size();
+        if (dst.size() != n || K.size() != n || C.size() != n || RS.size() != n)
+          throw std::invalid_argument("krsc_cast: list lengths differ");
+        int launches = 0;
+        for (size_t base = 0; base < n; base += BZ_CAST_MAX) {
+          BzCastTable t;
+          std::memset(&t, 0, sizeof(t));
+          int total = 0;
+          const size_t end = std::min(n, base + (size_t)BZ_CAST_MAX);
+          for (size_t i = base; i < end; ++i) {
+            BzCastEntry& e = t.e[i - base];
+            e.src = as_ptr<const void>(src[i]);
+            e.dst = as_ptr<void>(dst[i]);
+            e.K = K[i];
+            e.C = C[i];
+            e.RS = RS[i];
+            e.cta_start = total;
+            total += bz_krsc_cast_ctas(K[i], C[i], RS[i]);
+          }
+          t.count = (int)(end - base);
+          check(bz_krsc_cast(&t, to_grad, as_stream(stream)), "krsc_cast");
+          ++launches;
+        }
+        return launches;
       });
   m.def("gram_umma_grid", &bz_gram_umma_grid);
   m.def("gram_umma_tile_cols", &bz_gram_umma_tile_cols);

@@ -6,16 +6,18 @@
 // NHWC path is fp16-only there), which are latency bound at ~25 us per call on 13-50 MB
 // activations that stream in 2-8 us.  The kernels below are plain streaming kernels:
 //
-//   forward   reduce<false>  : per-CTA partial (sum, sum of squares) per channel, 16-byte loads; the
-//                              LAST CTA to finish (device counter) folds the partials in fp64 into
-//                              mean / invstd / running statistics / fused scale+shift
+//   forward   reduce<false>  : per-CTA partial (sum, sum of squares) per channel, 16-byte loads
+//             finalize<false>: one warp per channel folds the partials in fp64 into mean / invstd /
+//                              running statistics / fused scale+shift
 //             apply          : y = [relu](x * scale[c] + shift[c] [+ residual])
 //   backward  reduce<true>   : per-CTA partial (sum dy', sum dy' * xhat), dy' = dy * [y > 0] (mask
 //                              from the saved output when a residual was added, else recomputed
-//                              from x); last CTA: dgamma, dbeta (written straight into the gradient
-//                              arena) and the per-channel coefficients
+//                              from x)
+//             finalize<true> : dgamma, dbeta (written straight into the gradient arena when the
+//                              layer is in direct-gradient mode) and the per-channel coefficients
 //             bwd_apply      : dx = P * dy' + Q * x + S, optionally d(residual) = dy'
-// Two launches per direction; no atomics on data, deterministic summation order.
+// No atomics, deterministic summation order.  (A last-CTA-finalizes variant that saves the middle
+// launch was measured 10x slower: one CTA walking 592 x C partials is L2-latency bound, ~70 us.)
 //
 // Activations are [R = N*H*W rows][C channels] with C % 8 == 0 (every ResNet width).
 #include <cuda_bf16.h>
@@ -46,13 +48,13 @@ __device__ __forceinline__ Bf8 pack(const float (&f)[8]) {
 }
 
 // One warp per channel: lanes stride over the per-CTA partials, shuffle-reduce in fp64.
-// (volatile loads: the partials were written by other CTAs of this launch.)
 __device__ __forceinline__ void reduce_channel(const float* partial, int nblocks, int C, int c, double& s,
                                                double& q) {
   const int lane = threadIdx.x & 31;
   double ls = 0.0, lq = 0.0;
+#pragma unroll 4
   for (int b = lane; b < nblocks; b += 32) {
-    const float2 t = __ldcg(reinterpret_cast<const float2*>(partial + ((size_t)b * C + c) * 2));
+    const float2 t = __ldg(reinterpret_cast<const float2*>(partial + ((size_t)b * C + c) * 2));
     ls += (double)t.x;
     lq += (double)t.y;
   }
@@ -65,7 +67,7 @@ __device__ __forceinline__ void reduce_channel(const float* partial, int nblocks
   q = lq;
 }
 
-// Per-channel epilogues executed by the last CTA of a reduction.
+// Per-channel epilogues of the two reductions.
 struct Finalize {
   const float* gamma;
   const float* beta;
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(kThreads) reduce_partial_kernel(
     const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, long long R, int C,
     const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
     const float* __restrict__ invstd, int relu, const __nv_bfloat16* __restrict__ ymask,
-    float* __restrict__ partial, unsigned* __restrict__ counter, const Finalize fin) {
+    float* __restrict__ partial) {
   extern __shared__ float red[];  // [rows_per_iter][C][2]
   const int cg = C >> 3;
   const int lanes = kThreads / cg;
@@ -139,7 +141,7 @@ __global__ void __launch_bounds__(kThreads) reduce_partial_kernel(
     }
   }
   if (rl < lanes) {
-#pragma unroll 4
+#pragma unroll 8
     for (long long r = r0 + rl; r < r1; r += lanes) {
       const Bf8 px = *reinterpret_cast<const Bf8*>(x + r * C + g * 8);
       float xf[8];
@@ -186,26 +188,19 @@ __global__ void __launch_bounds__(kThreads) reduce_partial_kernel(
     for (int l = 0; l < lanes; ++l) s += red[(size_t)l * C * 2 + t];
     partial[(size_t)blockIdx.x * C * 2 + t] = s;
   }
-  // ---- last CTA folds the partials (threadfence-reduction pattern; the counter resets itself)
-  __shared__ bool last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned prev = atomicAdd(counter, 1u);
-    last = (prev == gridDim.x - 1);
-    if (last) *counter = 0u;
-  }
-  __syncthreads();
-  if (!last) return;
-  __threadfence();
-  for (int c = threadIdx.x >> 5; c < C; c += kThreads / 32) {
-    double s, q;
-    reduce_channel(partial, (int)gridDim.x, C, c, s, q);
-    if ((threadIdx.x & 31) == 0) {
-      if (BWD) fin.backward(c, C, R, s, q);
-      else fin.forward(c, R, s, q);
-    }
-  }
+}
+
+// One warp per channel; partial loads of a lane are independent (unrolled), the fold is fp64.
+template <bool BWD>
+__global__ void __launch_bounds__(kThreads) finalize_kernel(const float* __restrict__ partial, int nblocks,
+                                                           int C, long long R, const Finalize fin) {
+  const int c = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  if (c >= C) return;
+  double s, q;
+  reduce_channel(partial, nblocks, C, c, s, q);
+  if ((threadIdx.x & 31) != 0) return;
+  if (BWD) fin.backward(c, C, R, s, q);
+  else fin.forward(c, R, s, q);
 }
 
 // The grid-stride (gridDim * 256) is a multiple of cg whenever cg divides 256 (every power-of-two
@@ -298,7 +293,9 @@ __global__ void __launch_bounds__(kThreads) bwd_apply_kernel(
 }
 
 int reduce_blocks(long long R, int sm_count) {
-  long long b = (long long)sm_count * 4;
+  // two resident CTAs per SM saturate HBM with the 8-deep unrolled 16-byte loads; more CTAs only
+  // lengthen the finalize
+  long long b = (long long)sm_count * 2;
   if (b > R / 64) b = R / 64;
   if (b < 1) b = 1;
   return (int)b;
@@ -346,13 +343,12 @@ int bz_bn_forward(const BzBnArgs* a, int sm_count, cudaStream_t stream) {
   auto* y = reinterpret_cast<__nv_bfloat16*>(a->y);
   const int C = a->C;
   if (a->training) {
-    if (a->counter == nullptr) return (int)cudaErrorInvalidValue;
     const int nb = reduce_blocks(a->R, sm_count);
     const int lanes = kThreads / (C >> 3);
     const size_t smem = (size_t)lanes * C * 2 * sizeof(float);
-    reduce_partial_kernel<false><<<nb, kThreads, smem, stream>>>(
-        x, nullptr, a->R, C, nullptr, nullptr, nullptr, nullptr, 0, nullptr, a->partial, a->counter,
-        make_finalize(a));
+    reduce_partial_kernel<false><<<nb, kThreads, smem, stream>>>(x, nullptr, a->R, C, nullptr, nullptr, nullptr,
+                                                                nullptr, 0, nullptr, a->partial);
+    finalize_kernel<false><<<(C + 7) / 8, kThreads, 0, stream>>>(a->partial, nb, C, a->R, make_finalize(a));
   }
   const long long total8 = a->R * (C >> 3);
   apply_kernel<<<stream_blocks(total8, sm_count), kThreads, 0, stream>>>(
@@ -362,7 +358,6 @@ int bz_bn_forward(const BzBnArgs* a, int sm_count, cudaStream_t stream) {
 
 int bz_bn_backward(const BzBnArgs* a, int sm_count, cudaStream_t stream) {
   if (int e = check_shape(a->R, a->C)) return e;
-  if (a->counter == nullptr) return (int)cudaErrorInvalidValue;
   const auto* x = reinterpret_cast<const __nv_bfloat16*>(a->x);
   const auto* dy = reinterpret_cast<const __nv_bfloat16*>(a->dy);
   const auto* ymask = reinterpret_cast<const __nv_bfloat16*>(a->ymask);
@@ -372,8 +367,8 @@ int bz_bn_backward(const BzBnArgs* a, int sm_count, cudaStream_t stream) {
   const int lanes = kThreads / (C >> 3);
   const size_t smem = (size_t)lanes * C * 2 * sizeof(float);
   reduce_partial_kernel<true><<<nb, kThreads, smem, stream>>>(x, dy, a->R, C, a->scale, a->shift, a->mean,
-                                                             a->invstd, a->relu, ymask, a->partial,
-                                                             a->counter, make_finalize(a));
+                                                             a->invstd, a->relu, ymask, a->partial);
+  finalize_kernel<true><<<(C + 7) / 8, kThreads, 0, stream>>>(a->partial, nb, C, a->R, make_finalize(a));
   const long long total8 = a->R * (C >> 3);
   bwd_apply_kernel<<<stream_blocks(total8, sm_count), kThreads, 0, stream>>>(
       x, dy, dx, total8, C, a->scale, a->shift, a->coef, a->relu, ymask,

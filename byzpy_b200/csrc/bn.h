@@ -24,7 +24,6 @@ struct BzBnArgs {
   const void* res;        // bf16 [R][C] residual added before the ReLU (forward, may be null)
   const void* ymask;      // bf16 [R][C] forward output; ReLU mask source in backward (null: recompute)
   void* dres;             // bf16 [R][C] gradient of the residual = masked dy (backward, may be null)
-  unsigned* counter;      // one zero-initialised word owned by the layer (last-CTA detection)
   float eps, momentum;
   int relu;
   int training;

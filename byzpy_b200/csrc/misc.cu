@@ -4,8 +4,11 @@
 //   fill      : constant (+inf)           -> InfAttack
 //   gaussian  : Philox4x32-10 + Box-Muller N(mu, sigma^2)  -> GaussianAttack (K18)
 //   sgd       : fused SGD(+momentum,+wd) over a flat arena for several replicas (K20)
+//   u8_affine : uint8 NHWC image batch -> (x - mean[c]) * scale[c] in bf16, one pass (input pipeline)
 // Parity: reference attacks/little.py:113-131, empire.py:85-92, sign_flip.py:47-52,
 //         inf.py:61-65, gaussian.py:78-83, examples/ps/nodes.py:123-125.
+#include <cuda_bf16.h>
+
 #include "api.h"
 
 namespace {
@@ -164,6 +167,46 @@ __global__ void __launch_bounds__(kThreads) sgd_kernel(const float* __restrict__
   }
 }
 
+// 16 pixels-components per thread: one 16-byte load, two 16-byte stores.
+struct AffineC {
+  float mean[8];
+  float scale[8];
+};
+
+__global__ void __launch_bounds__(kThreads) u8_affine_kernel(const uint8_t* __restrict__ in,
+                                                            __nv_bfloat16* __restrict__ out, long long n,
+                                                            int C, const AffineC k) {
+  const long long nvec = n >> 4;
+  const long long stride = (long long)gridDim.x * kThreads;
+  for (long long u = (long long)blockIdx.x * kThreads + threadIdx.x; u < nvec; u += stride) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(in + (u << 4));
+    const unsigned w[4] = {raw.x, raw.y, raw.z, raw.w};
+    int c = (int)((u << 4) % C);
+    __nv_bfloat162 o[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float f[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int b = 2 * q + h;
+        const float v = (float)((w[b >> 2] >> (8 * (b & 3))) & 0xffu);
+        f[h] = (v - k.mean[c]) * k.scale[c];
+        c = (c + 1 == C) ? 0 : c + 1;
+      }
+      o[q] = __floats2bfloat162_rn(f[0], f[1]);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + (u << 4));
+    dst[0] = *reinterpret_cast<const uint4*>(&o[0]);
+    dst[1] = *reinterpret_cast<const uint4*>(&o[4]);
+  }
+  // scalar tail
+  const long long t0 = nvec << 4;
+  for (long long i = t0 + (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    const int c = (int)(i % C);
+    out[i] = __float2bfloat16_rn(((float)in[i] - k.mean[c]) * k.scale[c]);
+  }
+}
+
 }  // namespace
 
 int bz_colstat(const BzColStatArgs* args, int sm_count, cudaStream_t stream) {
@@ -207,5 +250,20 @@ int bz_sgd(const float* grad, const UpdTable* upd, long long len, int sm_count,
   const long long units = vec ? (len + 3) / 4 : len;
   // the vector path's tail needs at least one thread per tail element: grid >= 1 is enough (tail < 4)
   sgd_kernel<<<grid_for(units, sm_count), kThreads, 0, stream>>>(grad, *upd, len, vec ? 1 : 0);
+  return (int)cudaGetLastError();
+}
+
+int bz_u8_affine(const void* in, void* out, long long n, int C, const float* mean, const float* scale,
+                 int sm_count, cudaStream_t stream) {
+  if (n < 0 || C < 1 || C > 8) return (int)cudaErrorInvalidValue;
+  if (n == 0) return 0;
+  if (((uintptr_t)in % 16) != 0 || ((uintptr_t)out % 16) != 0) return (int)cudaErrorMisalignedAddress;
+  AffineC k;
+  for (int c = 0; c < 8; ++c) {
+    k.mean[c] = c < C ? mean[c] : 0.f;
+    k.scale[c] = c < C ? scale[c] : 1.f;
+  }
+  u8_affine_kernel<<<grid_for((n >> 4) + 1, sm_count), kThreads, 0, stream>>>(
+      reinterpret_cast<const uint8_t*>(in), reinterpret_cast<__nv_bfloat16*>(out), n, C, k);
   return (int)cudaGetLastError();
 }

@@ -386,6 +386,31 @@ def gaussian_(dst: torch.Tensor, mu: float, sigma: float, seed: int, offset: int
     return dst
 
 
+def normalize_uint8_nhwc(x: torch.Tensor, mean: Union[float, Sequence[float]] = 127.5,
+                         std: Union[float, Sequence[float]] = 127.5) -> torch.Tensor:
+    """uint8 image batch ``[N, H, W, C]`` -> ``(x - mean[c]) / std[c]`` as a bf16 ``[N, C, H, W]`` tensor
+    with channels-last strides (the same memory order, no transpose): the whole input pipeline of a
+    replica step in one streaming kernel instead of float() / sub / mul / cast passes."""
+    if x.dtype != torch.uint8 or x.dim() != 4:
+        raise TypeError("expected a uint8 [N, H, W, C] tensor")
+    C = x.shape[3]
+    mean = [float(mean)] * C if not isinstance(mean, (list, tuple)) else [float(v) for v in mean]
+    std = [float(std)] * C if not isinstance(std, (list, tuple)) else [float(v) for v in std]
+    if len(mean) != C or len(std) != C:
+        raise ValueError("mean / std must have one entry per channel")
+    scale = [1.0 / v for v in std]
+    if x.is_cuda and x.is_contiguous() and C <= 8 and x.data_ptr() % 16 == 0:
+        ext = require_ext()
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+        ext.u8_affine(x.data_ptr(), out.data_ptr(), x.numel(), C, mean, scale, sm_count(x.device),
+                      _stream(x.device))
+        count_launch()
+        return out.permute(0, 3, 1, 2)
+    m = torch.tensor(mean, dtype=torch.float32, device=x.device)
+    s = torch.tensor(scale, dtype=torch.float32, device=x.device)
+    return ((x.float() - m) * s).to(torch.bfloat16).permute(0, 3, 1, 2)
+
+
 def sgd_step(grad: torch.Tensor, params: Sequence[torch.Tensor],
              moms: Optional[Sequence[torch.Tensor]] = None, *, lr: float, momentum: float = 0.0,
              weight_decay: float = 0.0) -> None:
@@ -406,5 +431,5 @@ __all__ = [
     "MODE_MEDIAN", "MODE_TRMEAN", "MODE_MEAMED", "MODE_MEAN", "as_rows", "cw_select", "cw_median",
     "cw_trimmed_mean", "cw_meamed", "cw_mean", "gram", "sqdist_from_gram", "weighted_sum",
     "colstat", "scale_copy", "fill_", "gaussian_", "sgd_step", "extension_available",
-    "require_ext", "sm_count",
+    "require_ext", "sm_count", "normalize_uint8_nhwc", "count_launch", "launches",
 ]

@@ -38,7 +38,7 @@ def _direct_grad_ptrs(mod, weight, bias):
 class _FusedBN(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, residual, running_mean, running_var, training, momentum, eps, relu,
-                ctr, mod):
+                mod):
         ext = require_ext()
         N, C, H, W = x.shape
         R = N * H * W
@@ -66,13 +66,12 @@ class _FusedBN(torch.autograd.Function):
                        running_var.data_ptr() if (training and running_var is not None) else 0,
                        mean.data_ptr(), invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(), pptr,
                        float(eps), float(momentum), int(relu), int(training),
-                       residual.data_ptr() if residual is not None else 0, ctr[0:1].data_ptr(),
-                       sms, _stream(dev))
-        count_launch(2 if training else 1)
+                       residual.data_ptr() if residual is not None else 0, sms, _stream(dev))
+        count_launch(3 if training else 1)
         ctx.has_res = residual is not None
         # with a residual the ReLU mask cannot be recomputed from x alone: keep the output (the next
         # layer saves it anyway, so this costs no memory)
-        ctx.save_for_backward(x, weight, stats, ctr, y if (ctx.has_res and relu) else None)
+        ctx.save_for_backward(x, weight, stats, y if (ctx.has_res and relu) else None)
         ctx.relu = bool(relu)
         ctx.training = bool(training)
         ctx.mod = mod
@@ -82,7 +81,7 @@ class _FusedBN(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         ext = require_ext()
-        x, weight, stats, ctr, ysaved = ctx.saved_tensors
+        x, weight, stats, ysaved = ctx.saved_tensors
         N, C, H, W = x.shape
         R = N * H * W
         dev = x.device
@@ -91,7 +90,7 @@ class _FusedBN(torch.autograd.Function):
         if dy.dtype != torch.bfloat16:
             dy = dy.to(torch.bfloat16)
         mean, invstd, scale, shift = stats[0], stats[1], stats[2], stats[3]
-        nones = (None,) * 8
+        nones = (None,) * 7
         if not ctx.training:
             # eval mode: statistics are constants -> dx = dy' * scale
             d = dy.float()
@@ -127,8 +126,8 @@ class _FusedBN(torch.autograd.Function):
                         weight.data_ptr() if weight is not None else 0, mean.data_ptr(), invstd.data_ptr(),
                         scale.data_ptr(), shift.data_ptr(), partial.data_ptr(), dg_ptr, db_ptr,
                         grads[0].data_ptr(), int(ctx.relu), ysaved.data_ptr() if ysaved is not None else 0,
-                        dres_ptr, ctr[1:2].data_ptr(), sms, _stream(dev))
-        count_launch(2)
+                        dres_ptr, sms, _stream(dev))
+        count_launch(3)
         if direct or weight is None:
             return (dx, None, None, dres) + nones
         return (dx, grads[3], grads[4], dres) + nones
@@ -143,12 +142,10 @@ class FusedBatchNorm2d(nn.BatchNorm2d):
         super().__init__(num_features, eps=eps, momentum=momentum, affine=affine,
                          track_running_stats=track_running_stats, device=device, dtype=dtype)
         self.fused_relu = relu
-        # last-CTA detection words of the forward / backward reductions (self-resetting)
-        self.register_buffer("_ctr", torch.zeros(2, dtype=torch.int32, device=device), persistent=False)
 
     def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
         use_batch_stats = self.training or not self.track_running_stats
-        if (_eligible(x) and self.momentum is not None and self._ctr.device == x.device
+        if (_eligible(x) and self.momentum is not None
                 and (use_batch_stats or self.running_mean is not None)
                 and (residual is None or (_eligible(residual) and residual.shape == x.shape))):
             if self.training and self.track_running_stats and self.num_batches_tracked is not None:
@@ -156,7 +153,7 @@ class FusedBatchNorm2d(nn.BatchNorm2d):
             return _FusedBN.apply(x, self.weight, self.bias, residual,
                                   self.running_mean if self.track_running_stats else None,
                                   self.running_var if self.track_running_stats else None,
-                                  use_batch_stats, self.momentum, self.eps, self.fused_relu, self._ctr, self)
+                                  use_batch_stats, self.momentum, self.eps, self.fused_relu, self)
         y = super().forward(x)
         if residual is not None:
             y = y + residual

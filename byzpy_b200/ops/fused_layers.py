@@ -39,6 +39,22 @@ class GradSink:
         self.side_stream = side_stream
         self.keep: List[object] = []
         self._forked = False
+        self.convs: List["ArenaConv2d"] = []
+        self.shadows_fresh = False
+
+    def refresh_shadows(self) -> None:
+        """Refresh the bf16 channels-last shadow of EVERY conv weight with one launch
+        (``csrc/layout.cu``); the forward passes of this step then skip their own refresh."""
+        convs = [m for m in self.convs if m._direct_grad and m.weight.is_cuda]
+        if not convs:
+            return
+        ext = require_ext()
+        dev = convs[0].weight.device
+        n = ext.krsc_cast([m.weight.data_ptr() for m in convs], [m._shadow().data_ptr() for m in convs],
+                          [m.weight.shape[0] for m in convs], [m.weight.shape[1] for m in convs],
+                          [m.weight.shape[2] * m.weight.shape[3] for m in convs], 0, _stream(dev))
+        count_launch(n)
+        self.shadows_fresh = True
 
     def fork(self) -> Optional["torch.cuda.Stream"]:
         """Make the side stream wait for everything enqueued on the current stream so far."""
@@ -55,6 +71,7 @@ class GradSink:
             torch.cuda.current_stream().wait_stream(self.side_stream)
             self._forked = False
         self.keep.clear()
+        self.shadows_fresh = False
 
 
 def _bf16_autocast_on() -> bool:
@@ -70,11 +87,26 @@ def _grad_view_ok(p: Optional[torch.Tensor]) -> bool:
 
 
 # --------------------------------------------------------------------------- convolution
+def _krsc_cast(src: torch.Tensor, dst: torch.Tensor, *, to_grad: bool) -> None:
+    """fp32 OIHW <-> bf16 channels-last for one filter bank, coalesced on both sides."""
+    K, C, R, S = dst.shape
+    cl = src if to_grad else dst
+    if not cl.is_contiguous(memory_format=torch.channels_last) or (dst if to_grad else src).stride() != (
+            C * R * S, R * S, S, 1):
+        dst.copy_(src)          # unusual strides (e.g. a 1-channel filter): ATen's strided copy
+        return
+    ext = require_ext()
+    count_launch(ext.krsc_cast([src.data_ptr()], [dst.data_ptr()], [K], [C], [R * S], int(to_grad),
+                               _stream(dst.device)))
+
+
 class _ConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, mod):
         w16 = mod._shadow()
-        w16.copy_(weight)                      # one kernel: fp32 OIHW -> bf16 channels-last
+        sink = mod._sink
+        if sink is None or not sink.shadows_fresh:
+            _krsc_cast(weight, w16, to_grad=False)   # fp32 OIHW -> bf16 channels-last
         with torch.autocast("cuda", enabled=False):
             y = _aten.convolution(x, w16, None, mod.stride, mod.padding, mod.dilation, False, (0, 0),
                                   mod.groups)
@@ -96,13 +128,13 @@ class _ConvFn(torch.autograd.Function):
         if side is not None:
             with torch.cuda.stream(side):
                 gw = _aten.convolution_backward(dy, x, w16, *args, [False, True, False])[1]
-                weight.grad.copy_(gw)          # cast + layout change straight into the arena row
+                _krsc_cast(gw, weight.grad, to_grad=True)   # cast + layout change into the arena row
             sink.keep.append((dy, x, gw))      # alive until GradSink.join()
             dx = (_aten.convolution_backward(dy, x, w16, *args, [True, False, False])[0]
                   if need_dx else None)
         else:
             dx, gw, _ = _aten.convolution_backward(dy, x, w16, *args, [need_dx, True, False])
-            weight.grad.copy_(gw)
+            _krsc_cast(gw, weight.grad, to_grad=True)
         return dx, None, None
 
 
@@ -264,6 +296,8 @@ def enable_direct_grads(module: nn.Module, *, side_stream: Optional["torch.cuda.
         if isinstance(m, (ArenaConv2d, ArenaLinear)):
             m._direct_grad = enabled
             m._sink = sink if enabled else None
+            if isinstance(m, ArenaConv2d) and enabled:
+                sink.convs.append(m)
         elif isinstance(m, FusedBatchNorm2d):
             m._direct_grad = enabled
     return sink

@@ -129,6 +129,8 @@ class DeviceWorker:
             x = self.preprocess(x)
         ctx = (torch.autocast("cuda", dtype=amp_dtype) if amp_dtype is not None
                else contextlib.nullcontext())
+        if self.sink is not None and amp_dtype == torch.bfloat16:
+            self.sink.refresh_shadows()     # all conv weights -> bf16 channels-last, one launch
         with ctx:
             out = self.model(x)
             loss = self.loss_fn(out, self.static_y)
