@@ -203,7 +203,7 @@ PYBIND11_MODULE(_C, m) {
       "bn_forward",
       [](uint64_t x, uint64_t y, long long R, int C, uint64_t gamma, uint64_t beta, uint64_t rmean,
          uint64_t rvar, uint64_t mean, uint64_t invstd, uint64_t scale, uint64_t shift, uint64_t partial,
-         float eps, float momentum, int relu, int training, uint64_t res, int sm_count,
+         float eps, float momentum, int relu, int training, uint64_t res, uint64_t nbt, int sm_count,
          uint64_t stream) {
         BzBnArgs a;
         std::memset(&a, 0, sizeof(a));
@@ -225,6 +225,7 @@ PYBIND11_MODULE(_C, m) {
         a.relu = relu;
         a.training = training;
         a.res = as_ptr<const void>(res);
+        a.num_batches_tracked = as_ptr<long long>(nbt);
         check(bz_bn_forward(&a, sm_count, as_stream(stream)), "bn_forward");
       });
   m.def(

@@ -80,6 +80,7 @@ struct Finalize {
   float* dgamma;
   float* dbeta;
   float* coef;   // [3][C]:  dx = P * dy' + Q * x + S
+  long long* num_batches_tracked;  // incremented once per training forward (may be null)
   float eps, momentum;
 
   __device__ __forceinline__ void forward(int c, long long R, double s, double q) const {
@@ -97,6 +98,7 @@ struct Finalize {
       running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
       running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
     }
+    if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
   }
   // P = gamma*invstd,  Q = -P*c2*invstd,  S = -P*c1 + P*c2*invstd*mean
   // (c1 = sum dy'/R, c2 = sum dy' xhat / R)
@@ -332,6 +334,7 @@ static Finalize make_finalize(const BzBnArgs* a) {
   f.dgamma = a->dgamma;
   f.dbeta = a->dbeta;
   f.coef = a->coef;
+  f.num_batches_tracked = a->num_batches_tracked;
   f.eps = a->eps;
   f.momentum = a->momentum;
   return f;

@@ -24,6 +24,7 @@ struct BzBnArgs {
   const void* res;        // bf16 [R][C] residual added before the ReLU (forward, may be null)
   const void* ymask;      // bf16 [R][C] forward output; ReLU mask source in backward (null: recompute)
   void* dres;             // bf16 [R][C] gradient of the residual = masked dy (backward, may be null)
+  long long* num_batches_tracked;  // int64 scalar bumped by the training forward (may be null)
   float eps, momentum;
   int relu;
   int training;

@@ -38,7 +38,7 @@ def _direct_grad_ptrs(mod, weight, bias):
 class _FusedBN(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, residual, running_mean, running_var, training, momentum, eps, relu,
-                mod):
+                mod, nbt):
         ext = require_ext()
         N, C, H, W = x.shape
         R = N * H * W
@@ -66,7 +66,8 @@ class _FusedBN(torch.autograd.Function):
                        running_var.data_ptr() if (training and running_var is not None) else 0,
                        mean.data_ptr(), invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(), pptr,
                        float(eps), float(momentum), int(relu), int(training),
-                       residual.data_ptr() if residual is not None else 0, sms, _stream(dev))
+                       residual.data_ptr() if residual is not None else 0,
+                       nbt.data_ptr() if (training and nbt is not None) else 0, sms, _stream(dev))
         count_launch(3 if training else 1)
         ctx.has_res = residual is not None
         # with a residual the ReLU mask cannot be recomputed from x alone: keep the output (the next
@@ -90,7 +91,7 @@ class _FusedBN(torch.autograd.Function):
         if dy.dtype != torch.bfloat16:
             dy = dy.to(torch.bfloat16)
         mean, invstd, scale, shift = stats[0], stats[1], stats[2], stats[3]
-        nones = (None,) * 7
+        nones = (None,) * 8
         if not ctx.training:
             # eval mode: statistics are constants -> dx = dy' * scale
             d = dy.float()
@@ -148,12 +149,14 @@ class FusedBatchNorm2d(nn.BatchNorm2d):
         if (_eligible(x) and self.momentum is not None
                 and (use_batch_stats or self.running_mean is not None)
                 and (residual is None or (_eligible(residual) and residual.shape == x.shape))):
-            if self.training and self.track_running_stats and self.num_batches_tracked is not None:
-                self.num_batches_tracked.add_(1)
+            # num_batches_tracked is bumped inside the statistics kernel (no extra launch)
+            nbt = (self.num_batches_tracked
+                   if (self.training and self.track_running_stats and self.num_batches_tracked is not None
+                       and self.num_batches_tracked.dtype == torch.int64) else None)
             return _FusedBN.apply(x, self.weight, self.bias, residual,
                                   self.running_mean if self.track_running_stats else None,
                                   self.running_var if self.track_running_stats else None,
-                                  use_batch_stats, self.momentum, self.eps, self.fused_relu, self)
+                                  use_batch_stats, self.momentum, self.eps, self.fused_relu, self, nbt)
         y = super().forward(x)
         if residual is not None:
             y = y + residual
