@@ -53,6 +53,29 @@ def main():
     with open(a.out, "w") as f:
         f.write(txt)
     print(txt[-3000:])
+    # stream occupancy: how much of the wall span do kernels cover (gaps = launch / dependency latency)
+    ks = []
+    for e in prof.events():
+        if getattr(e, "device_type", None) is not None and "cuda" in str(e.device_type).lower():
+            ks.append((float(e.time_range.start), float(e.time_range.end), e.name))
+    if ks:
+        ks.sort()
+        span = ks[-1][1] - ks[0][0]
+        busy = sum(k[1] - k[0] for k in ks)
+        # union of intervals (kernels on different streams overlap)
+        cover, cur_s, cur_e = 0.0, ks[0][0], ks[0][1]
+        for s_, e_, _ in ks[1:]:
+            if s_ > cur_e:
+                cover += cur_e - cur_s
+                cur_s, cur_e = s_, e_
+            else:
+                cur_e = max(cur_e, e_)
+        cover += cur_e - cur_s
+        line = (f"device activities: {len(ks)}  span {span / 1e3:.3f} ms  sum of durations {busy / 1e3:.3f} ms  "
+                f"covered {cover / 1e3:.3f} ms  idle {100 * (1 - cover / span):.1f} %")
+        print(line)
+        with open(a.out, "a") as f:
+            f.write("\n" + line + "\n")
 
 
 if __name__ == "__main__":

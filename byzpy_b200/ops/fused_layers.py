@@ -148,8 +148,7 @@ class ArenaConv2d(nn.Conv2d):
         w = self.weight
         s = getattr(self, "_w16", None)
         if s is None or s.device != w.device or s.shape != w.shape:
-            s = torch.empty(w.shape, dtype=torch.bfloat16, device=w.device).contiguous(
-                memory_format=torch.channels_last)
+            s = torch.empty(w.shape, dtype=torch.bfloat16, device=w.device, memory_format=torch.channels_last)
             self._w16 = s
         return s
 
@@ -235,7 +234,7 @@ class _MaxPoolFn(torch.autograd.Function):
         N, C, H, W = x.shape
         Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
         dev = x.device
-        y = torch.empty((N, C, Ho, Wo), dtype=x.dtype, device=dev).contiguous(memory_format=torch.channels_last)
+        y = torch.empty((N, C, Ho, Wo), dtype=x.dtype, device=dev, memory_format=torch.channels_last)
         idx = torch.empty((N, Ho, Wo, C), dtype=torch.uint8, device=dev)
         ext.maxpool_forward(x.data_ptr(), y.data_ptr(), idx.data_ptr(), N, H, W, C, sm_count(dev), _stream(dev))
         count_launch()
@@ -252,8 +251,7 @@ class _MaxPoolFn(torch.autograd.Function):
         dy = dy.contiguous(memory_format=torch.channels_last)
         if dy.dtype != torch.bfloat16:
             dy = dy.to(torch.bfloat16)
-        dx = torch.empty((N, C, H, W), dtype=torch.bfloat16, device=dev).contiguous(
-            memory_format=torch.channels_last)
+        dx = torch.empty((N, C, H, W), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
         ext.maxpool_backward(dy.data_ptr(), idx.data_ptr(), dx.data_ptr(), N, H, W, C, sm_count(dev),
                              _stream(dev))
         count_launch()
