@@ -221,7 +221,12 @@ class GramAggregator(Aggregator):
 
     supports_subtasks = True
     max_subtasks_inflight = 0
-    chunk_size: int = 8192      # feature-dimension chunk of the split-K Gram subtasks
+    # ``chunk_size`` keeps the reference's constructor meaning (rows / pairs / combinations per
+    # subtask) and only matters to subclasses that chunk a combinatorial search; the split-K Gram
+    # subtasks chunk the FEATURE dimension and use ``gram_feature_chunk`` (adapted to the pool size):
+    # a 32-feature chunk would turn a 1.2 M-parameter gradient into 37 500 subtasks.
+    chunk_size: int = 8192
+    gram_feature_chunk: int = 1 << 16
     _gram_chunk_elems: int = 1 << 16
 
     # -- hooks ---------------------------------------------------------------------
@@ -293,7 +298,8 @@ class GramAggregator(Aggregator):
     # -- subtask path: split-K partial Grams -------------------------------------------
     def _gram_subtasks(self, all_rows: List[torch.Tensor], context) -> Tuple[_Packed, List[SubTask]]:
         d = all_rows[0].numel()
-        chunk = select_adaptive_chunk_size(d, max(self.chunk_size, 1), pool_size=pool_size_of(context))
+        chunk = select_adaptive_chunk_size(d, max(int(self.gram_feature_chunk), 1),
+                                           pool_size=pool_size_of(context))
         packed = _Packed.pack(all_rows)
         tasks = [SubTask(fn=_gram_chunk, args=(packed, s, e), name=f"{self.name}_gram_{k}")
                  for k, (s, e) in enumerate(feature_chunks(d, chunk))]
