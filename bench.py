@@ -137,7 +137,7 @@ def preprocess_fused(x: torch.Tensor) -> torch.Tensor:
     # same map, one streaming kernel of this library, bf16 output (what the first conv consumes)
     from byzpy_b200.ops import normalize_uint8_nhwc
 
-    return normalize_uint8_nhwc(x, 127.5, 127.5)
+    return normalize_uint8_nhwc(x, 127.5, 127.5, s2d=True)
 
 
 def max_over_ranks(value: float, device) -> float:

@@ -42,15 +42,17 @@ for shape in [(32, 64, 112, 112), (32, 64, 56, 56), (32, 128, 28, 28), (32, 256,
         x, r, gy = mk().requires_grad_(True), mk().requires_grad_(True), mk()
         bn = FusedBatchNorm2d(C, relu=True).to(dev)
         mb = x.numel() * 2 / 1e6
+        with torch.no_grad():
+            pass
         fwd = timeit(lambda: bn(x, r if res else None))
-        y = bn(x, r if res else None)
 
-        def bwd():
-            y.backward(gy, retain_graph=True)
+        def both():          # autograd runs backward on the forward's stream: capture them together
+            y = bn(x, r if res else None)
+            y.backward(gy)
             x.grad = None
             r.grad = None
 
-        b = timeit(bwd)
+        b = timeit(both) - fwd
         fwd_bytes = mb * (3 + (1 if res else 0))            # x twice, y once (+ residual)
         bwd_bytes = mb * (5 + (3 if res else 0))            # x, dy twice, dx (+ y twice, dres)
         print(f"shape={shape} residual={res} act={mb:.1f}MB  fwd {fwd:6.1f} us ({fwd_bytes / fwd / 1e3 / PEAK * 1e3:.2f} of HBM peak)"

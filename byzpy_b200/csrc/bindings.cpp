@@ -298,6 +298,19 @@ PYBIND11_MODULE(_C, m) {
         }
         return launches;
       });
+  m.def("s2d_pack", [](uint64_t x, int x_is_u8, uint64_t out, int N, int H, int W, const std::vector<float>& mean,
+                       const std::vector<float>& scale, uint64_t stream) {
+    if (mean.size() < 3 || scale.size() < 3) throw std::invalid_argument("s2d_pack: mean/scale need 3 entries");
+    check(bz_s2d_pack(as_ptr<const void>(x), x_is_u8, as_ptr<void>(out), N, H, W, mean.data(), scale.data(),
+                      as_stream(stream)),
+          "s2d_pack");
+  });
+  m.def("stem_weight_pack", [](uint64_t w, uint64_t wp, int K, uint64_t stream) {
+    check(bz_stem_weight_pack(as_ptr<const float>(w), as_ptr<void>(wp), K, as_stream(stream)), "stem_weight_pack");
+  });
+  m.def("stem_grad_unpack", [](uint64_t gp, uint64_t g, int K, uint64_t stream) {
+    check(bz_stem_grad_unpack(as_ptr<const void>(gp), as_ptr<float>(g), K, as_stream(stream)), "stem_grad_unpack");
+  });
   m.def("gram_umma_grid", &bz_gram_umma_grid);
   m.def("gram_umma_tile_cols", &bz_gram_umma_tile_cols);
   m.def("gram_umma_partials", &bz_gram_umma_partials);

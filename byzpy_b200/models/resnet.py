@@ -88,9 +88,10 @@ class ResNet(nn.Module):
             self.conv1 = _conv(in_channels, 64, 3, 1, 1)
             self.maxpool = nn.Identity()
         else:
-            from ..ops.fused_layers import FusedMaxPool2d
+            from ..ops.fused_layers import FusedMaxPool2d, S2DStemConv2d
 
-            self.conv1 = _conv(in_channels, 64, 7, 2, 3)
+            # 7x7/s2 stem: runs as a space-to-depth 4x4 conv on B200 when in_channels == 3
+            self.conv1 = S2DStemConv2d(in_channels, 64, 7, stride=2, padding=3, bias=False)
             self.maxpool = FusedMaxPool2d(3, stride=2, padding=1)
         self.bn1 = _bn(64, relu=True)
         self.relu = nn.ReLU(inplace=True)

@@ -387,7 +387,7 @@ def gaussian_(dst: torch.Tensor, mu: float, sigma: float, seed: int, offset: int
 
 
 def normalize_uint8_nhwc(x: torch.Tensor, mean: Union[float, Sequence[float]] = 127.5,
-                         std: Union[float, Sequence[float]] = 127.5) -> torch.Tensor:
+                         std: Union[float, Sequence[float]] = 127.5, *, s2d: bool = False):
     """uint8 image batch ``[N, H, W, C]`` -> ``(x - mean[c]) / std[c]`` as a bf16 ``[N, C, H, W]`` tensor
     with channels-last strides (the same memory order, no transpose): the whole input pipeline of a
     replica step in one streaming kernel instead of float() / sub / mul / cast passes."""
@@ -398,6 +398,12 @@ def normalize_uint8_nhwc(x: torch.Tensor, mean: Union[float, Sequence[float]] = 
     std = [float(std)] * C if not isinstance(std, (list, tuple)) else [float(v) for v in std]
     if len(mean) != C or len(std) != C:
         raise ValueError("mean / std must have one entry per channel")
+    if s2d and x.is_cuda and x.is_contiguous() and C == 3:
+        # ``s2d=True``: emit the 2x2 space-to-depth packed, zero-padded form consumed by
+        # ``ops.fused_layers.S2DStemConv2d`` (the ResNet stem) -- same single pass over the bytes
+        from .fused_layers import pack_stem_input
+
+        return pack_stem_input(x, mean, std)
     scale = [1.0 / v for v in std]
     if x.is_cuda and x.is_contiguous() and C <= 8 and x.data_ptr() % 16 == 0:
         ext = require_ext()

@@ -20,6 +20,7 @@ Off (the default) they behave exactly like ``nn.Conv2d`` / ``nn.Linear`` / ``nn.
 """
 from __future__ import annotations
 
+import contextlib
 from typing import List, Optional
 
 import torch
@@ -41,11 +42,13 @@ class GradSink:
         self._forked = False
         self.convs: List["ArenaConv2d"] = []
         self.shadows_fresh = False
+        self.pending: List[tuple] = []      # (bf16 channels-last wgrad, fp32 arena view) awaiting the cast
 
     def refresh_shadows(self) -> None:
         """Refresh the bf16 channels-last shadow of EVERY conv weight with one launch
         (``csrc/layout.cu``); the forward passes of this step then skip their own refresh."""
-        convs = [m for m in self.convs if m._direct_grad and m.weight.is_cuda]
+        convs = [m for m in self.convs if m._direct_grad and m.weight.is_cuda
+                 and not (isinstance(m, S2DStemConv2d) and m._s2d_ok())]   # the stem packs its own weight
         if not convs:
             return
         ext = require_ext()
@@ -54,6 +57,8 @@ class GradSink:
                           [m.weight.shape[0] for m in convs], [m.weight.shape[1] for m in convs],
                           [m.weight.shape[2] * m.weight.shape[3] for m in convs], 0, _stream(dev))
         count_launch(n)
+        for m in convs:
+            m._shadow_fresh = True
         self.shadows_fresh = True
 
     def fork(self) -> Optional["torch.cuda.Stream"]:
@@ -67,10 +72,20 @@ class GradSink:
 
     def join(self) -> None:
         """Order the current stream after all side-stream work of this backward pass."""
+        if self.pending:
+            # one multi-tensor launch casts every weight gradient of this backward pass into the arena
+            # row (issued where the wgrad GEMMs ran, so stream order already covers the dependency)
+            ctx = torch.cuda.stream(self.side_stream) if self._forked else contextlib.nullcontext()
+            with ctx:
+                _krsc_cast_many([g for g, _ in self.pending], [d for _, d in self.pending], to_grad=True)
+            self.pending.clear()
         if self._forked:
             torch.cuda.current_stream().wait_stream(self.side_stream)
             self._forked = False
         self.keep.clear()
+        if self.shadows_fresh:
+            for m in self.convs:
+                m._shadow_fresh = False
         self.shadows_fresh = False
 
 
@@ -100,12 +115,29 @@ def _krsc_cast(src: torch.Tensor, dst: torch.Tensor, *, to_grad: bool) -> None:
                                _stream(dst.device)))
 
 
+def _krsc_cast_many(srcs, dsts, *, to_grad: bool) -> None:
+    ok = []
+    for src, dst in zip(srcs, dsts):
+        K, C, R, S = dst.shape
+        cl = src if to_grad else dst
+        if cl.is_contiguous(memory_format=torch.channels_last) and (dst if to_grad else src).stride() == (
+                C * R * S, R * S, S, 1):
+            ok.append((src, dst))
+        else:
+            dst.copy_(src)
+    if ok:
+        ext = require_ext()
+        count_launch(ext.krsc_cast([s.data_ptr() for s, _ in ok], [d.data_ptr() for _, d in ok],
+                                   [d.shape[0] for _, d in ok], [d.shape[1] for _, d in ok],
+                                   [d.shape[2] * d.shape[3] for _, d in ok], int(to_grad),
+                                   _stream(ok[0][1].device)))
+
+
 class _ConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, mod):
         w16 = mod._shadow()
-        sink = mod._sink
-        if sink is None or not sink.shadows_fresh:
+        if not getattr(mod, "_shadow_fresh", False):
             _krsc_cast(weight, w16, to_grad=False)   # fp32 OIHW -> bf16 channels-last
         with torch.autocast("cuda", enabled=False):
             y = _aten.convolution(x, w16, None, mod.stride, mod.padding, mod.dilation, False, (0, 0),
@@ -128,13 +160,16 @@ class _ConvFn(torch.autograd.Function):
         if side is not None:
             with torch.cuda.stream(side):
                 gw = _aten.convolution_backward(dy, x, w16, *args, [False, True, False])[1]
-                _krsc_cast(gw, weight.grad, to_grad=True)   # cast + layout change into the arena row
+            sink.pending.append((gw, weight.grad))   # cast into the arena row by GradSink.join()
             sink.keep.append((dy, x, gw))      # alive until GradSink.join()
             dx = (_aten.convolution_backward(dy, x, w16, *args, [True, False, False])[0]
                   if need_dx else None)
         else:
             dx, gw, _ = _aten.convolution_backward(dy, x, w16, *args, [need_dx, True, False])
-            _krsc_cast(gw, weight.grad, to_grad=True)
+            if sink is not None:
+                sink.pending.append((gw, weight.grad))
+            else:
+                _krsc_cast(gw, weight.grad, to_grad=True)
         return dx, None, None
 
 
@@ -164,6 +199,129 @@ class ArenaConv2d(nn.Conv2d):
             x = x.to(torch.bfloat16)
         x = x.contiguous(memory_format=torch.channels_last)
         return _ConvFn.apply(x, self.weight, self)
+
+
+# --------------------------------------------------------------------------- space-to-depth stem
+class PackedStemInput:
+    """A 2x2 space-to-depth packed, zero-padded image batch for :class:`S2DStemConv2d`:
+    ``data`` is bf16 ``[N, 16, (H-1)//2 + 4, (W-1)//2 + 4]`` channels-last (``csrc/layout.cu``)."""
+
+    __slots__ = ("data", "hw")
+
+    def __init__(self, data: torch.Tensor, hw):
+        self.data, self.hw = data, tuple(hw)
+
+    @property
+    def shape(self):
+        return torch.Size((self.data.shape[0], 3) + self.hw)
+
+    @property
+    def device(self):
+        return self.data.device
+
+
+def pack_stem_input(x: torch.Tensor, mean=None, std=None) -> PackedStemInput:
+    """uint8 ``[N, H, W, 3]`` (normalised with ``mean`` / ``std``) or bf16 channels-last ``[N, 3, H, W]``
+    -> :class:`PackedStemInput`, one streaming kernel."""
+    ext = require_ext()
+    if x.dtype == torch.uint8:
+        N, H, W, C = x.shape
+        src, is_u8 = x, 1
+        m = [float(v) for v in (mean if isinstance(mean, (list, tuple)) else [127.5 if mean is None else mean] * 3)]
+        sd = [float(v) for v in (std if isinstance(std, (list, tuple)) else [127.5 if std is None else std] * 3)]
+        sc = [1.0 / v for v in sd]
+    else:
+        N, C, H, W = x.shape
+        src, is_u8 = x, 0
+        m, sc = [0.0] * 3, [1.0] * 3
+        if x.dtype != torch.bfloat16 or not x.is_contiguous(memory_format=torch.channels_last):
+            raise TypeError("pack_stem_input expects uint8 NHWC or bf16 channels-last input")
+    if C != 3 or not src.is_contiguous(memory_format=torch.contiguous_format if is_u8 else torch.channels_last):
+        raise ValueError("pack_stem_input needs a dense 3-channel image batch")
+    Hb, Wb = (H - 1) // 2 + 4, (W - 1) // 2 + 4
+    out = torch.empty((N, 16, Hb, Wb), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    ext.s2d_pack(src.data_ptr(), is_u8, out.data_ptr(), N, H, W, m, sc, _stream(x.device))
+    count_launch()
+    return PackedStemInput(out, (H, W))
+
+
+class _StemFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xp, weight, mod):
+        ext = require_ext()
+        K = weight.shape[0]
+        wp = mod._packed_weight()
+        ext.stem_weight_pack(weight.data_ptr(), wp.data_ptr(), K, _stream(weight.device))
+        count_launch()
+        with torch.autocast("cuda", enabled=False):
+            y = _aten.convolution(xp, wp, None, (1, 1), (0, 0), (1, 1), False, (0, 0), 1)
+        ctx.save_for_backward(xp)
+        ctx.wp, ctx.mod, ctx.weight = wp, mod, weight
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        ext = require_ext()
+        (xp,) = ctx.saved_tensors
+        mod, wp, weight = ctx.mod, ctx.wp, ctx.weight
+        dy = dy.contiguous(memory_format=torch.channels_last)
+        if dy.dtype != torch.bfloat16:
+            dy = dy.to(torch.bfloat16)
+        direct = mod._direct_grad and _grad_view_ok(weight)
+        sink: Optional[GradSink] = getattr(mod, "_sink", None) if direct else None
+        target = weight.grad if direct else torch.empty_like(weight, memory_format=torch.contiguous_format)
+
+        def wgrad():
+            gp = _aten.convolution_backward(dy, xp, wp, None, (1, 1), (0, 0), (1, 1), False, (0, 0), 1,
+                                            [False, True, False])[1]
+            gp = gp.contiguous(memory_format=torch.channels_last)
+            ext.stem_grad_unpack(gp.data_ptr(), target.data_ptr(), weight.shape[0], _stream(weight.device))
+            count_launch()
+            return gp
+
+        side = sink.fork() if sink is not None else None
+        if side is not None:
+            with torch.cuda.stream(side):
+                gp = wgrad()
+            sink.keep.append((dy, xp, gp))
+        else:
+            wgrad()
+        # the image batch needs no gradient; a packed input never requires grad
+        return None, (None if direct else target), None
+
+
+class S2DStemConv2d(ArenaConv2d):
+    """The ResNet stem (7x7 / stride 2 / pad 3 over 3 channels) executed as a 4x4 / stride 1
+    convolution over the 2x2 space-to-depth packed input: same parameters, ``state_dict`` and
+    results, 4-5x faster on B200 because the dense 16-channel form runs on the sm_100 tensor-core
+    kernels (``csrc/layout.cu`` has the index algebra).  Accepts a :class:`PackedStemInput`
+    (from ``ops.normalize_uint8_nhwc(..., s2d=True)``) or an ordinary image batch."""
+
+    def _s2d_ok(self) -> bool:
+        return (self.kernel_size == (7, 7) and self.stride == (2, 2) and self.padding == (3, 3)
+                and self.dilation == (1, 1) and self.groups == 1 and self.in_channels == 3
+                and self.bias is None and self.padding_mode == "zeros")
+
+    def _packed_weight(self) -> torch.Tensor:
+        w = self.weight
+        s = getattr(self, "_wp", None)
+        if s is None or s.device != w.device or s.shape[0] != w.shape[0]:
+            s = torch.empty((w.shape[0], 16, 4, 4), dtype=torch.bfloat16, device=w.device,
+                            memory_format=torch.channels_last)
+            self._wp = s
+        return s
+
+    def forward(self, x):
+        if isinstance(x, PackedStemInput):
+            if not self._s2d_ok():
+                raise TypeError("PackedStemInput needs a 7x7/s2/p3 3-channel stem convolution")
+            return _StemFn.apply(x.data, self.weight, self)
+        if (self._direct_grad and self._s2d_ok() and x.is_cuda and x.dim() == 4 and x.shape[1] == 3
+                and torch.is_grad_enabled() and not x.requires_grad and _bf16_autocast_on()):
+            xb = x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
+            xb = xb.contiguous(memory_format=torch.channels_last)
+            return _StemFn.apply(pack_stem_input(xb).data, self.weight, self)
+        return super().forward(x)
 
 
 # --------------------------------------------------------------------------- linear
@@ -295,10 +453,11 @@ def enable_direct_grads(module: nn.Module, *, side_stream: Optional["torch.cuda.
             m._direct_grad = enabled
             m._sink = sink if enabled else None
             if isinstance(m, ArenaConv2d) and enabled:
-                sink.convs.append(m)
+                sink.convs.append(m)        # (the s2d stem also keeps a KRSC shadow for its fallback path)
         elif isinstance(m, FusedBatchNorm2d):
             m._direct_grad = enabled
     return sink
 
 
-__all__ = ["ArenaConv2d", "ArenaLinear", "FusedMaxPool2d", "GradSink", "enable_direct_grads"]
+__all__ = ["ArenaConv2d", "ArenaLinear", "FusedMaxPool2d", "GradSink", "enable_direct_grads", "S2DStemConv2d",
+           "PackedStemInput", "pack_stem_input"]

@@ -459,3 +459,47 @@ def test_normalize_uint8_nhwc(shape):
     torch.testing.assert_close(y.float(), exp, rtol=1e-2, atol=1e-2)
     z = ops.normalize_uint8_nhwc(x)         # scalar mean / std
     torch.testing.assert_close(z.float(), (x.permute(0, 3, 1, 2).float() - 127.5) / 127.5, rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("hw", [(224, 224), (64, 64), (37, 50)])
+@pytest.mark.parametrize("packed_input", [False, True])
+def test_space_to_depth_stem_matches_plain_convolution(hw, packed_input):
+    """The 7x7/s2/p3 stem run as a 4x4 conv over the 2x2 space-to-depth packed input."""
+    import torch.nn.functional as F
+
+    from byzpy_b200.ops.fused_layers import PackedStemInput, S2DStemConv2d, enable_direct_grads
+
+    torch.manual_seed(4)
+    H, W = hw
+    N = 4
+    img = torch.randint(0, 256, (N, H, W, 3), dtype=torch.uint8, device=dev())
+    conv = S2DStemConv2d(3, 64, 7, stride=2, padding=3, bias=False).to(dev())
+    conv.weight.grad = torch.zeros_like(conv.weight)
+    holder = torch.nn.Sequential(conv)
+    sink = enable_direct_grads(holder, side_stream=torch.cuda.Stream())
+    xn = ops.normalize_uint8_nhwc(img)                          # bf16 [N,3,H,W] channels-last
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        if packed_input:
+            xin = ops.normalize_uint8_nhwc(img, s2d=True)
+            assert isinstance(xin, PackedStemInput) and tuple(xin.shape) == (N, 3, H, W)
+        else:
+            xin = xn
+        y = conv(xin)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    sink.join()
+    torch.cuda.synchronize()
+    wr = conv.weight.detach().to(torch.bfloat16).float().requires_grad_(True)
+    yr = F.conv2d(xn.float(), wr, stride=2, padding=3)
+    yr.backward(gy.float())
+    assert y.shape == yr.shape and y.dtype == torch.bfloat16
+    torch.testing.assert_close(y.float(), yr, rtol=2e-2, atol=2e-2)
+    scale = wr.grad.abs().max().item()
+    torch.testing.assert_close(conv.weight.grad, wr.grad, rtol=2e-2, atol=1e-2 * scale)
+    # autograd mode (direct gradients off): the gradient comes back through autograd
+    enable_direct_grads(holder, enabled=False)
+    conv.weight.grad = None
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y2 = conv(ops.normalize_uint8_nhwc(img, s2d=True))
+    y2.backward(gy)
+    torch.testing.assert_close(conv.weight.grad, wr.grad, rtol=2e-2, atol=1e-2 * scale)

@@ -178,6 +178,49 @@ def test_peer_to_peer_round_writes_back_robust_aggregate():
     run(scenario())
 
 
+def test_decentralized_peer_to_peer_round_matches_manual_expectation():
+    """``DecentralizedPeerToPeer`` over DecentralizedNodes: the round writes the robust aggregate of
+    own + neighbour half-steps back into every honest model (ring topology, message-count driven)."""
+    from byzpy_b200.engine.peer_to_peer.runner import DecentralizedPeerToPeer
+
+    async def scenario():
+        hon = [await HonestNodeActor.spawn(PH, backend="thread", args=(i,)) for i in range(4)]
+        byz = [await ByzantineNodeActor.spawn(PB, backend="thread")]
+        p2p = DecentralizedPeerToPeer(hon, byz, Topology.complete(5), lr=0.1, recv_timeout=10.0)
+        await p2p.start()
+        await p2p.run_round_async()
+        got = [await h.params() for h in hon]
+        mirrors = [PH(i) for i in range(4)]
+        halves = [m.p2p_half_step(0.1) for m in mirrors]
+        mal = PB().p2p_broadcast_vector(neighbor_vectors=halves, like=halves[0])
+        for i in range(4):
+            others = [halves[j] for j in range(4) if j != i] + [mal]
+            exp = CoordinateWiseTrimmedMean(f=1).aggregate([halves[i]] + others)
+            assert torch.allclose(got[i], exp, atol=1e-6)
+        assert p2p.rounds == 1
+        await p2p.run_round_async()
+        assert p2p.rounds == 2
+        await p2p.stop()
+        for a in hon + byz:
+            await a.close()
+
+    run(scenario())
+
+
+def test_gram_family_subtasks_chunk_the_feature_dimension_coarsely():
+    """Regression: the reference's row-chunk default (chunk_size=32) must not be used as a FEATURE
+    chunk -- a 1.2 M-parameter gradient became 37 500 subtasks."""
+    from byzpy_b200.aggregators.geometric_wise import MultiKrum
+    from byzpy_b200.engine.graph.operator import OpContext
+
+    op = MultiKrum(f=1, q=3)
+    grads = [torch.randn(300_000) for _ in range(5)]
+    ctx = OpContext(node_name="agg", metadata={"pool_size": 2})
+    tasks = list(op.create_subtasks({"gradients": grads}, context=ctx))
+    assert 1 <= len(tasks) <= 64
+    op._release_packed(grads) if hasattr(op, "_release_packed") else None
+
+
 def g1():
     return torch.tensor([1.0, 2.0])
 
