@@ -226,7 +226,10 @@ PYBIND11_MODULE(_C, m) {
         a.training = training;
         a.res = as_ptr<const void>(res);
         a.num_batches_tracked = as_ptr<long long>(nbt);
+        int launches = 0;
+        a.launches = &launches;
         check(bz_bn_forward(&a, sm_count, as_stream(stream)), "bn_forward");
+        return launches;
       });
   m.def(
       "bn_backward",
@@ -253,7 +256,10 @@ PYBIND11_MODULE(_C, m) {
         a.relu = relu;
         a.ymask = as_ptr<const void>(ymask);
         a.dres = as_ptr<void>(dres);
+        int launches = 0;
+        a.launches = &launches;
         check(bz_bn_backward(&a, sm_count, as_stream(stream)), "bn_backward");
+        return launches;
       });
   m.def(
       "maxpool_forward",

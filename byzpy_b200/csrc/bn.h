@@ -25,6 +25,7 @@ struct BzBnArgs {
   const void* ymask;      // bf16 [R][C] forward output; ReLU mask source in backward (null: recompute)
   void* dres;             // bf16 [R][C] gradient of the residual = masked dy (backward, may be null)
   long long* num_batches_tracked;  // int64 scalar bumped by the training forward (may be null)
+  int* launches;          // host out-param: kernels launched by this call (may be null)
   float eps, momentum;
   int relu;
   int training;

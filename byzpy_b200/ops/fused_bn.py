@@ -59,7 +59,7 @@ class _FusedBN(torch.autograd.Function):
             scale.copy_(g * invstd)
             shift.copy_(b - running_mean * scale)
             pptr = 0
-        ext.bn_forward(x.data_ptr(), y.data_ptr(), R, C,
+        count_launch(ext.bn_forward(x.data_ptr(), y.data_ptr(), R, C,
                        weight.data_ptr() if weight is not None else 0,
                        bias.data_ptr() if bias is not None else 0,
                        running_mean.data_ptr() if (training and running_mean is not None) else 0,
@@ -67,8 +67,7 @@ class _FusedBN(torch.autograd.Function):
                        mean.data_ptr(), invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(), pptr,
                        float(eps), float(momentum), int(relu), int(training),
                        residual.data_ptr() if residual is not None else 0,
-                       nbt.data_ptr() if (training and nbt is not None) else 0, sms, _stream(dev))
-        count_launch(3 if training else 1)
+                       nbt.data_ptr() if (training and nbt is not None) else 0, sms, _stream(dev)))
         ctx.has_res = residual is not None
         # with a residual the ReLU mask cannot be recomputed from x alone: keep the output (the next
         # layer saves it anyway, so this costs no memory)
@@ -123,12 +122,11 @@ class _FusedBN(torch.autograd.Function):
                 dres_ptr = dres.data_ptr()
             else:
                 dres = dy
-        ext.bn_backward(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), R, C,
+        count_launch(ext.bn_backward(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), R, C,
                         weight.data_ptr() if weight is not None else 0, mean.data_ptr(), invstd.data_ptr(),
                         scale.data_ptr(), shift.data_ptr(), partial.data_ptr(), dg_ptr, db_ptr,
                         grads[0].data_ptr(), int(ctx.relu), ysaved.data_ptr() if ysaved is not None else 0,
-                        dres_ptr, sms, _stream(dev))
-        count_launch(3)
+                        dres_ptr, sms, _stream(dev)))
         if direct or weight is None:
             return (dx, None, None, dres) + nones
         return (dx, grads[3], grads[4], dres) + nones
