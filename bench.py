@@ -171,10 +171,20 @@ def run_ours(args, rank, world, device):
     xs, ys = make_pool(L, args.batch, args.image, args.classes, args.pool, seed=1234 + rank)
     torch.manual_seed(0)  # identical init on every replica, like a PS that broadcasts the model
     honest, byz = [], []
+    cursor = [0] * L
+
+    def source(slot):
+        # the node's data source: this worker's next pinned host batch (cycles through the pool)
+        def nxt():
+            k = cursor[slot] % args.pool
+            cursor[slot] += 1
+            return xs[slot][k], ys[slot][k]
+        return nxt
+
     for slot, g in enumerate(gids):
         torch.manual_seed(0)
         model = build_model(args.model, num_classes=args.classes)
-        kw = dict(lr=args.lr, momentum=0.9, device=str(device), preprocess=preprocess_fused)
+        kw = dict(lr=args.lr, momentum=0.9, device=str(device), preprocess=preprocess_fused, data=source(slot))
         if g < n_honest:
             honest.append(DeviceHonestNode(model, name=f"honest{g}", **kw))
         else:
@@ -214,10 +224,16 @@ def run_ours(args, rank, world, device):
     rnd.check_status()
 
     # ---- end-to-end through the public API: H2D inputs + round + D2H losses every step ----
+    # ps.step() pulls every worker's next pinned host batch from its data source; the H2D copy of
+    # batch k+1 is issued right after round k is launched (double-buffered inputs), the loss of
+    # round k is read back synchronously every step.
+    ps.step()                       # fills the prefetch pipeline (and captures the second graph)
+    ps.step()
+    rnd.read_losses()
     barrier_sync(device)
     t0 = time.perf_counter()
     for i in range(args.steps):
-        ps.step(batches(i))
+        ps.step()
         losses = rnd.read_losses()
     torch.cuda.synchronize(device)
     e2e_s = max_over_ranks(time.perf_counter() - t0, device)

@@ -94,8 +94,10 @@ class DeviceWorker:
         self.data = data
         self.arena: Optional[ParamArena] = None
         self.mom: Optional[torch.Tensor] = None
-        self.static_x: Optional[torch.Tensor] = None
-        self.static_y: Optional[torch.Tensor] = None
+        # two sets of static input buffers: the round engine reads set ``buf`` while the next
+        # step's batch is copied H2D into the other one (DeviceRound.step, double-buffered graphs)
+        self._static: List[Optional[Tuple[torch.Tensor, torch.Tensor]]] = [None, None]
+        self.buf = 0
         self.loss_slot: Optional[torch.Tensor] = None
         self.sink = None            # ops.fused_layers.GradSink once direct gradients are on
 
@@ -113,14 +115,31 @@ class DeviceWorker:
 
         self.sink = enable_direct_grads(self.model, side_stream=side_stream)
 
-    def stage_batch(self, x: torch.Tensor, y: torch.Tensor) -> None:
-        """Copy this step's inputs (typically pinned host tensors) into static device buffers."""
+    @property
+    def static_x(self) -> Optional[torch.Tensor]:
+        cur = self._static[self.buf]
+        return None if cur is None else cur[0]
+
+    @property
+    def static_y(self) -> Optional[torch.Tensor]:
+        cur = self._static[self.buf]
+        return None if cur is None else cur[1]
+
+    def stage_batch(self, x: torch.Tensor, y: torch.Tensor, buf: Optional[int] = None) -> bool:
+        """Copy a step's inputs (typically pinned host tensors) into static device buffer set ``buf``
+        (default: the active one) on the current stream.  Returns True when the buffers had to be
+        (re)allocated -- a captured graph that baked the old addresses is then stale."""
+        b = self.buf if buf is None else buf
         dev = self.arena.flat_params.device
-        if self.static_x is None or self.static_x.shape != x.shape or self.static_x.dtype != x.dtype:
-            self.static_x = torch.empty(x.shape, dtype=x.dtype, device=dev)
-            self.static_y = torch.empty(y.shape, dtype=y.dtype, device=dev)
-        self.static_x.copy_(x, non_blocking=True)
-        self.static_y.copy_(y, non_blocking=True)
+        cur = self._static[b]
+        fresh = (cur is None or cur[0].shape != x.shape or cur[0].dtype != x.dtype
+                 or cur[1].shape != y.shape or cur[1].dtype != y.dtype)
+        if fresh:
+            cur = (torch.empty(x.shape, dtype=x.dtype, device=dev), torch.empty(y.shape, dtype=y.dtype, device=dev))
+            self._static[b] = cur
+        cur[0].copy_(x, non_blocking=True)
+        cur[1].copy_(y, non_blocking=True)
+        return fresh
 
     def forward_backward(self, amp_dtype: Optional[torch.dtype]) -> None:
         self.arena.flat_grads.zero_()
@@ -245,7 +264,13 @@ class DeviceRound:
         sh -= sh % 4
         self.shard_off = self.rank * sh
         self.shard_len = sh if self.rank < self.world - 1 else self.d_pad - sh * (self.world - 1)
-        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        # one captured graph per static input buffer set (they share one memory pool)
+        self._graphs: List[Optional[torch.cuda.CUDAGraph]] = [None, None]
+        self._buf = 0
+        self._copy_stream = torch.cuda.Stream(self.device)
+        self._h2d_done = [torch.cuda.Event(), torch.cuda.Event()]
+        self._consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        self._prefetched = [False, False]
         self._side_streams = [torch.cuda.Stream(self.device) for _ in range(max(0, worker_streams - 1))]
         # one weight-gradient stream per worker stream: backward's dgrad chain stays on the worker
         # stream, the wgrad GEMMs of the same replica overlap with it
@@ -460,9 +485,10 @@ class DeviceRound:
         if self.world > 1:
             dist.barrier(group=self.group)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        other = self._graphs[1 - self._buf]
+        with torch.cuda.graph(g, **({"pool": other.pool()} if other is not None else {})):
             self._body()
-        self._graph = g
+        self._graphs[self._buf] = g
         with torch.no_grad():
             self.params.copy_(snap_p)
             if snap_m is not None:
@@ -473,23 +499,62 @@ class DeviceRound:
         torch.cuda.synchronize(self.device)
 
     # --------------------------------------------------------------------- step
-    def step(self, batches: Optional[Sequence[Tuple[torch.Tensor, torch.Tensor]]] = None) -> torch.Tensor:
-        """One training round.  ``batches[i]`` = this step's (x, y) for local worker i
-        (pinned host tensors are copied H2D asynchronously).  Returns the device
-        tensor of per-worker losses."""
-        if batches is None:
-            batches = [w.data() for w in self.workers]
-        for w, (x, y) in zip(self.workers, batches):
-            w.stage_batch(x, y)
+    @property
+    def _graph(self) -> Optional[torch.cuda.CUDAGraph]:
+        """The captured round reading the ACTIVE input buffer set."""
+        return self._graphs[self._buf]
+
+    def step(self, batches: Optional[Sequence[Tuple[torch.Tensor, torch.Tensor]]] = None, *,
+             prefetch: bool = True) -> torch.Tensor:
+        """One training round.  Returns the device tensor of per-worker losses.
+
+        ``batches[i]`` = this step's (x, y) for local worker i: pinned host tensors are copied H2D
+        asynchronously on the launching stream, then the round runs.
+
+        ``batches=None``: every worker pulls from its ``data`` source.  The inputs are then
+        **double buffered**: as soon as round k is launched, batch k+1 is fetched and copied H2D on a
+        copy stream into the other buffer set (its own captured graph), so the copy overlaps the
+        round instead of preceding it; round k+1 only waits for that copy's event."""
+        main = torch.cuda.current_stream(self.device)
+        explicit = batches is not None
+        b = self._buf
+        for w in self.workers:
+            w.buf = b
+        if explicit or not self._prefetched[b]:
+            if batches is None:
+                batches = [w.data() for w in self.workers]
+            stale = False
+            for w, (x, y) in zip(self.workers, batches):
+                stale |= w.stage_batch(x, y, b)
+            if stale:
+                self._graphs[b] = None
+        else:
+            main.wait_event(self._h2d_done[b])
+        self._prefetched[b] = False
         refresh = getattr(self.plan, "refresh", None)
         if refresh is not None:
             refresh()
         if self.use_cuda_graph:
-            if self._graph is None:
+            if self._graphs[b] is None:
                 self.capture()
-            self._graph.replay()
+            self._graphs[b].replay()
         else:
             self._body()
+        self._consumed[b].record(main)
+        if (not explicit) and prefetch and all(w.data is not None for w in self.workers):
+            nb = 1 - b
+            nxt = [w.data() for w in self.workers]
+            cs = self._copy_stream
+            cs.wait_event(self._consumed[nb])       # the last round that read set nb has finished
+            stale = False
+            with torch.cuda.stream(cs):
+                for w, (x, y) in zip(self.workers, nxt):
+                    stale |= w.stage_batch(x, y, nb)
+            if stale:
+                self._graphs[nb] = None
+            self._h2d_done[nb].record(cs)
+            self._prefetched[nb] = True
+            self._buf = nb
         return self.losses
 
     def read_losses(self) -> torch.Tensor:
@@ -508,7 +573,7 @@ class DeviceRound:
         return self.agg[: self.d]
 
     def close(self) -> None:
-        self._graph = None
+        self._graphs = [None, None]
         self.sym.close()
 
 

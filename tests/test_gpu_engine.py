@@ -227,6 +227,54 @@ def test_device_round_matches_manual_loop(graph):
     asyncio.run(ps.shutdown())
 
 
+@pytest.mark.parametrize("graph", [False, True])
+def test_device_round_prefetch_pipeline_matches_explicit_batches(graph):
+    """ps.step() with data sources double-buffers the inputs (H2D of batch k+1 overlaps round k, one
+    captured graph per buffer set); the trajectory equals feeding the same batches explicitly."""
+    from byzpy_b200.engine.node.device import DeviceByzantineNode, DeviceHonestNode
+    from byzpy_b200.engine.parameter_server.ps import ParameterServer
+
+    torch.manual_seed(3)
+    n_h, n_b, steps = 3, 1, 6
+    data = [[(torch.randn(16, 20).pin_memory(), torch.randint(0, 5, (16,)).pin_memory()) for _ in range(steps + 2)]
+            for _ in range(n_h + n_b)]
+    init = TinyNet().state_dict()
+
+    def mk():
+        m = TinyNet()
+        m.load_state_dict(init)
+        return m
+
+    def build(with_sources):
+        cur = [0] * (n_h + n_b)
+
+        def src(w):
+            def nxt():
+                b = data[w][cur[w]]
+                cur[w] += 1
+                return b
+            return nxt if with_sources else None
+
+        hon = [DeviceHonestNode(mk(), lr=0.1, momentum=0.9, device=DEV, data=src(w)) for w in range(n_h)]
+        byz = [DeviceByzantineNode(SignFlipAttack(), model=mk(), lr=0.1, momentum=0.9, device=DEV, data=src(n_h))]
+        return hon, ParameterServer(hon, byz, CoordinateWiseMedian(), update_byzantines=True, fused=True,
+                                    amp_dtype=None, use_cuda_graph=graph)
+
+    hon_a, ps_a = build(True)
+    hon_b, ps_b = build(False)
+    for t in range(steps):
+        ps_a.step()                                            # prefetching pipeline
+        ps_b.step([data[w][t] for w in range(n_h + n_b)])      # explicit batches
+        la, lb = ps_a.device_round.read_losses().clone(), ps_b.device_round.read_losses().clone()
+        torch.testing.assert_close(la, lb, rtol=1e-5, atol=1e-6)
+    pa = torch.cat([p.detach().reshape(-1) for p in hon_a[0].model.parameters()])
+    pb = torch.cat([p.detach().reshape(-1) for p in hon_b[0].model.parameters()])
+    torch.testing.assert_close(pa, pb, rtol=1e-5, atol=1e-6)
+    assert ps_a.device_round._buf in (0, 1) and ps_a.device_round._prefetched[ps_a.device_round._buf]
+    asyncio.run(ps_a.shutdown())
+    asyncio.run(ps_b.shutdown())
+
+
 def _run_device_vs_mirror(mk_agg, pre=None, attack="signflip", graph=True, steps=3, n_h=6, n_b=2):
     from byzpy_b200.attacks import LittleAttack
     from byzpy_b200.engine.node.device import DeviceByzantineNode, DeviceHonestNode
