@@ -293,7 +293,8 @@ class GramAggregator(Aggregator):
             w_np = self._solve(G.detach().double().cpu().numpy(), n)
             return torch.from_numpy(np.asarray(w_np, dtype=np.float32)).to(G.device)
 
-        return GramPlan(solver, self.name, aux=tuple(aux), capturable=bool(self.device_solve))
+        feasible = getattr(self, "_device_solve_feasible", lambda n_: True)(n)
+        return GramPlan(solver, self.name, aux=tuple(aux), capturable=bool(self.device_solve) and feasible)
 
     # -- subtask path: split-K partial Grams -------------------------------------------
     def _gram_subtasks(self, all_rows: List[torch.Tensor], context) -> Tuple[_Packed, List[SubTask]]:

@@ -27,5 +27,19 @@ class SMEA(GramAggregator):
     def _solve(self, G: np.ndarray, n: int) -> np.ndarray:
         return nspace.smea_weights(G, self.f)
 
+    # exhaustive subset search on the device (csrc/nspace.cu) when C(n, n-f) is small enough;
+    # returns None otherwise and the host search above takes over
+    device_solve = True
+
+    def _solve_device(self, G, n):
+        from ...ops import nspace_cuda
+
+        return nspace_cuda.subset_weights(G, n, n - self.f, "smea")
+
+    def _device_solve_feasible(self, n: int) -> bool:
+        from ...ops import nspace_cuda
+
+        return nspace_cuda.subset_search_feasible(n, n - self.f)
+
 
 __all__ = ["SMEA"]

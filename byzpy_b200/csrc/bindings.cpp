@@ -341,6 +341,14 @@ PYBIND11_MODULE(_C, m) {
       py::arg("rows"), py::arg("scales"), py::arg("off"), py::arg("len"), py::arg("partials"),
       py::arg("num_partials"), py::arg("tail64"), py::arg("G"), py::arg("G64"),
       py::arg("sm_count"), py::arg("stream"));
+  m.def("binomial", &bz_binomial);
+  m.def("nspace_subset_blocks", &bz_nspace_subset_blocks);
+  m.def("nspace_subset", [](uint64_t G, int ldg, int n, int m_, int nt, int mode, uint64_t sscore, uint64_t srank,
+                            uint64_t w, int sm_count, uint64_t stream) {
+    check(bz_nspace_subset(as_ptr<const double>(G), ldg, n, m_, nt, mode, as_ptr<double>(sscore),
+                           as_ptr<unsigned long long>(srank), as_ptr<float>(w), sm_count, as_stream(stream)),
+          "nspace_subset");
+  });
   m.def("nspace_krum", [](uint64_t G, int n, int f, int q, uint64_t w, uint64_t stream) {
     check(bz_nspace_krum(as_ptr<const double>(G), n, f, q, as_ptr<float>(w), as_stream(stream)),
           "nspace_krum");

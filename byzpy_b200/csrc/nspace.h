@@ -7,3 +7,11 @@ int bz_nspace_weiszfeld(const double* G, int nt, int n_real, const double* a0, d
                         int max_iter, double eps, float* out, int* iters, cudaStream_t stream);
 int bz_nspace_cclip(const double* G, int nt, int n_real, const double* a0, double c_tau, int M,
                     double eps, float* out, cudaStream_t stream);
+
+// Exhaustive (n - f)-subset search for MDA (mode 0) / SMEA (mode 1) on the device, n <= 24.
+// G is fp64 with leading dimension ldg; w gets 1/m on the winning rows (nt entries, rest 0).
+// scratch_score / scratch_rank hold bz_nspace_subset_blocks(n, m, sm_count) entries.
+unsigned long long bz_binomial(int n, int k);
+int bz_nspace_subset_blocks(int n, int m, int sm_count);
+int bz_nspace_subset(const double* G, int ldg, int n, int m, int nt, int mode, double* scratch_score,
+                     unsigned long long* scratch_rank, float* w, int sm_count, cudaStream_t stream);

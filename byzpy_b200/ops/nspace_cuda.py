@@ -81,3 +81,37 @@ def centered_clip_coeffs(G: torch.Tensor, n_real: int, a0: np.ndarray, *, c_tau:
 
 
 __all__ = ["krum_weights", "weiszfeld_coeffs", "centered_clip_coeffs"]
+
+
+SUBSET_MAX_N = 24
+SUBSET_MAX_COMBOS = 4_000_000
+
+
+def subset_search_feasible(n: int, m: int) -> bool:
+    """True when the exhaustive device search handles (n, m): n <= 24 and C(n, m) <= 4 M subsets."""
+    ext = _load_ext()
+    if ext is None or not hasattr(ext, "nspace_subset") or not (1 <= m <= n <= SUBSET_MAX_N):
+        return False
+    return ext.binomial(n, m) <= SUBSET_MAX_COMBOS
+
+
+def subset_weights(G: torch.Tensor, n: int, m: int, mode: str) -> Optional[torch.Tensor]:
+    """1/m on the rows of the optimal m-subset of the first ``n`` rows of the fp64 Gram ``G``.
+    ``mode``: ``"mda"`` (minimum diameter) or ``"smea"`` (minimum top covariance eigenvalue); ties go
+    to the lexicographically first subset, like ``ops.nspace.mda_subset`` / ``smea_subset``."""
+    if not G.is_cuda or not subset_search_feasible(n, m):
+        return None
+    from . import sm_count
+
+    ext = _load_ext()
+    G = G.contiguous().double()
+    nt = G.shape[0]
+    dev = G.device
+    sms = sm_count(dev)
+    nb = ext.nspace_subset_blocks(n, m, sms)
+    score = torch.empty(nb, dtype=torch.float64, device=dev)
+    rank = torch.empty(nb, dtype=torch.int64, device=dev)
+    w = torch.empty(nt, dtype=torch.float32, device=dev)
+    ext.nspace_subset(G.data_ptr(), nt, n, m, nt, 0 if mode == "mda" else 1, score.data_ptr(), rank.data_ptr(),
+                      w.data_ptr(), sms, _stream(dev))
+    return w

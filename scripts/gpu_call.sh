@@ -1,9 +1,8 @@
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -x -q -p no:warnings > gpurun_out/pytest17.log 2>&1; echo "pytest rc=$?"
-tail -8 gpurun_out/pytest17.log | cut -c1-300
-timeout 300 python bench.py --steps 20 --warmup 5 > gpurun_out/bench17_n1.log 2>&1; tail -1 gpurun_out/bench17_n1.log | cut -c1-1600
-BYZPY_B200_NO_PDL=1 timeout 300 python bench.py --steps 20 --warmup 5 > gpurun_out/bench17_n1_nopdl.log 2>&1; tail -1 gpurun_out/bench17_n1_nopdl.log | cut -c1-200
-timeout 300 python bench.py --steps 20 --warmup 5 --worker-streams 1 > gpurun_out/bench17_n1_ws1.log 2>&1; tail -1 gpurun_out/bench17_n1_ws1.log | cut -c1-200
-BYZPY_B200_NO_PDL=1 timeout 300 python bench.py --steps 20 --warmup 5 --worker-streams 1 > gpurun_out/bench17_n1_ws1_nopdl.log 2>&1; tail -1 gpurun_out/bench17_n1_ws1_nopdl.log | cut -c1-200
-timeout 300 python bench.py --steps 20 --warmup 5 --worker-streams 8 > gpurun_out/bench17_n1_ws8.log 2>&1; tail -1 gpurun_out/bench17_n1_ws8.log | cut -c1-200
-timeout 200 python bench/bn_layers.py 2>&1 | tail -12
+nvidia-smi -L | head -3
+timeout 1500 python -m pytest tests -m gpu -x -q -p no:warnings > gpurun_out/pytest18.log 2>&1; echo "pytest rc=$?"
+tail -8 gpurun_out/pytest18.log | cut -c1-300
+for agg in median multikrum; do
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/multi_gpu/check_fused_round.py --agg $agg --graph > gpurun_out/mg18_$agg.log 2>&1; echo "check $agg rc=$?"; tail -2 gpurun_out/mg18_$agg.log | cut -c1-200
+done
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/bench18_n2.log 2>&1; tail -1 gpurun_out/bench18_n2.log | cut -c1-1500

@@ -476,3 +476,41 @@ def test_space_to_depth_stem_matches_plain_convolution(hw, packed_input):
         y2 = conv(ops.normalize_uint8_nhwc(img, s2d=True))
     y2.backward(gy)
     torch.testing.assert_close(conv.weight.grad, wr.grad, rtol=2e-2, atol=1e-2 * scale)
+
+
+@pytest.mark.parametrize("n,f", [(6, 1), (10, 3), (13, 4), (16, 5), (20, 3)])
+@pytest.mark.parametrize("mode", ["mda", "smea"])
+def test_device_subset_search_matches_host_oracle(n, f, mode):
+    """Exhaustive (n-f)-subset search on the device (MDA diameter / SMEA top eigenvalue via Jacobi)
+    picks the same subset as the host search, including exact ties (lexicographic order)."""
+    import numpy as np
+
+    from byzpy_b200.ops import nspace, nspace_cuda
+
+    if mode == "smea" and 2 * f >= n:
+        pytest.skip("2f < n required")
+    rng = np.random.default_rng(n * 31 + f)
+    X = rng.standard_normal((n, 40))
+    X[1] = X[0]                              # duplicate rows -> exact ties between subsets
+    X[n - 1] *= 25.0                         # an obvious outlier
+    G = X @ X.T
+    want = nspace.mda_weights(G, f) if mode == "mda" else nspace.smea_weights(G, f)
+    Gd = torch.from_numpy(G).to(dev())
+    assert nspace_cuda.subset_search_feasible(n, n - f)
+    got = nspace_cuda.subset_weights(Gd, n, n - f, mode)
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=0, atol=1e-7)
+    # larger problems fall back to the host search
+    assert not nspace_cuda.subset_search_feasible(64, 56)
+
+
+def test_mda_and_smea_aggregators_use_the_device_solver():
+    from byzpy_b200.aggregators.geometric_wise import SMEA, MinimumDiameterAveraging
+
+    rows, X = rows_of(9, 5000, seed=21)
+    rows[4].mul_(30.0)
+    X[4] *= 30.0
+    for agg in (MinimumDiameterAveraging(f=2), SMEA(f=2)):
+        out = agg.aggregate(rows)
+        exp = agg.aggregate([X[i] for i in range(9)])       # CPU path = host oracle
+        torch.testing.assert_close(out.cpu(), exp, rtol=1e-4, atol=1e-4)
+        assert agg.fused_plan(9).capturable and not agg.fused_plan(64 if agg.name != "smea" else 40).capturable
