@@ -261,8 +261,15 @@ class GramAggregator(Aggregator):
         n = len(rows)
         self._validate(n)
         krows = _kernel_rows(rows)
-        all_rows = krows + self._aux_rows(krows)
-        w = self._weights(all_rows, n)
+        fused = ops.gram_with_median(krows, want64=True) if self._fused_aux() == ("median",) else None
+        if fused is not None:
+            # median start point + Gram matrix in ONE pass over the rows (csrc/gram.cu, AUX variant)
+            G, med = fused
+            all_rows = krows + [med]
+            w = self._weights(all_rows, n, G=G)
+        else:
+            all_rows = krows + self._aux_rows(krows)
+            w = self._weights(all_rows, n)
         out = ops.weighted_sum(all_rows, w.reshape(-1))
         return finish(out, like)
 

@@ -51,6 +51,11 @@ struct BzGramArgs {
   int num_partials;
   double* G64;  // optional fp64 output (may be nullptr)
   float* G;     // fp32 output
+  // Optional fused auxiliary row (n <= 16): the coordinate-wise lower median of the scaled rows is
+  // computed while the rows stream by, written to aux_median (len floats, same offset as the rows)
+  // and appended as row n of the Gram matrix, which is then (n+1) x (n+1).  This is the start point of
+  // Weiszfeld / the centre of centred clipping: fusing it saves a full pass over the n x d matrix.
+  float* aux_median;
 };
 int bz_gram_partials_needed(int n, int sm_count);
 int bz_gram(const BzGramArgs* args, int sm_count, cudaStream_t stream);

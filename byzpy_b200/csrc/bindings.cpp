@@ -133,7 +133,7 @@ PYBIND11_MODULE(_C, m) {
       "gram",
       [](const std::vector<uint64_t>& rows, const std::vector<float>& scales, long long off,
          long long len, uint64_t partials, int num_partials, uint64_t G, uint64_t G64, int sm_count,
-         uint64_t stream) {
+         uint64_t stream, uint64_t aux_median) {
         BzGramArgs a;
         std::memset(&a, 0, sizeof(a));
         fill_rows(a.rows, a.scales, rows, scales);
@@ -144,11 +144,12 @@ PYBIND11_MODULE(_C, m) {
         a.num_partials = num_partials;
         a.G = as_ptr<float>(G);
         a.G64 = as_ptr<double>(G64);
+        a.aux_median = as_ptr<float>(aux_median);
         check(bz_gram(&a, sm_count, as_stream(stream)), "gram");
       },
       py::arg("rows"), py::arg("scales"), py::arg("off"), py::arg("len"), py::arg("partials"),
       py::arg("num_partials"), py::arg("G"), py::arg("G64"), py::arg("sm_count"),
-      py::arg("stream"));
+      py::arg("stream"), py::arg("aux_median") = 0);
 
   m.def(
       "colstat",

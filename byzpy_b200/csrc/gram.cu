@@ -8,6 +8,7 @@
 // bytes, (n, n) result.
 // Parity: reference krum.py:31-44 (pairwise squared distances via Gram).
 #include "api.h"
+#include "cw_core.cuh"
 
 namespace {
 
@@ -17,15 +18,36 @@ constexpr int kWarps = kThreads / 32;
 // ---------------------------------------------------------------- small n --
 // n <= 16: every thread streams V consecutive coordinates of all rows and keeps
 // the upper triangle of the outer product in registers.
-template <int NS, int V>
+// AUX: one more row = the coordinate-wise lower median of the (scaled) rows, computed in registers
+// with the selection network of cw_core.cuh, stored to a.aux_median and included in the products.
+template <int NS, int V, bool AUX>
 __global__ void __launch_bounds__(kThreads) gram_small_kernel(const __grid_constant__ BzGramArgs a) {
-  constexpr int T = NS * (NS + 1) / 2;
+  constexpr int NR = NS + (AUX ? 1 : 0);
+  constexpr int T = NR * (NR + 1) / 2;
   float acc[T];
 #pragma unroll
   for (int t = 0; t < T; ++t) acc[t] = 0.f;
   const int n = a.n;
+  const int ne = n + (AUX ? 1 : 0);
+  const int apad = NS / 2 - 1 - (n - 1) / 2;
   const long long nvec = a.len / V;
   const long long stride = (long long)gridDim.x * kThreads;
+  auto accumulate = [&](const float (&col)[NR]) {
+    int t = 0;
+#pragma unroll
+    for (int i = 0; i < NR; ++i)
+#pragma unroll
+      for (int k = i; k < NR; ++k) {
+        acc[t] = fmaf(col[i], col[k], acc[t]);
+        ++t;
+      }
+  };
+  auto median_of = [&](const float (&col)[NR]) -> float {
+    float v[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) v[i] = (i < n) ? canon(col[i] * a.scales.s[i]) : 0.f;
+    return bzcw::cw_pick<NS, BZ_CW_MEDIAN>(v, n, 0, apad);
+  };
   for (long long u = (long long)blockIdx.x * kThreads + threadIdx.x; u < nvec; u += stride) {
     const long long base = a.off + u * V;
     float x[NS][V];
@@ -46,16 +68,25 @@ __global__ void __launch_bounds__(kThreads) gram_small_kernel(const __grid_const
         for (int c = 0; c < V; ++c) x[i][c] = 0.f;
       }
     }
+    float med[V];
 #pragma unroll
     for (int c = 0; c < V; ++c) {
-      int t = 0;
+      float col[NR];
 #pragma unroll
-      for (int i = 0; i < NS; ++i)
+      for (int i = 0; i < NS; ++i) col[i] = x[i][c];
+      if constexpr (AUX) {
+        med[c] = median_of(col);
+        col[NS] = med[c];
+      }
+      accumulate(col);
+    }
+    if constexpr (AUX) {
+      if constexpr (V == 4) {
+        stg_stream4(a.aux_median + base, make_float4(med[0], med[1], med[2], med[3]));
+      } else {
 #pragma unroll
-        for (int k = i; k < NS; ++k) {
-          acc[t] = fmaf(x[i][c], x[k][c], acc[t]);
-          ++t;
-        }
+        for (int c = 0; c < V; ++c) a.aux_median[base + c] = med[c];
+      }
     }
   }
   // scalar tail (len % V) handled by block 0
@@ -63,17 +94,14 @@ __global__ void __launch_bounds__(kThreads) gram_small_kernel(const __grid_const
     const long long tail0 = a.off + nvec * V;
     const long long tail = a.len - nvec * V;
     if ((long long)threadIdx.x < tail) {
-      float x1[NS];
+      float col[NR];
 #pragma unroll
-      for (int i = 0; i < NS; ++i) x1[i] = (i < n) ? a.rows.p[i][tail0 + threadIdx.x] : 0.f;
-      int t = 0;
-#pragma unroll
-      for (int i = 0; i < NS; ++i)
-#pragma unroll
-        for (int k = i; k < NS; ++k) {
-          acc[t] = fmaf(x1[i], x1[k], acc[t]);
-          ++t;
-        }
+      for (int i = 0; i < NS; ++i) col[i] = (i < n) ? a.rows.p[i][tail0 + threadIdx.x] : 0.f;
+      if constexpr (AUX) {
+        col[NS] = median_of(col);
+        a.aux_median[tail0 + threadIdx.x] = col[NS];
+      }
+      accumulate(col);
     }
   }
   __shared__ float red[kWarps][T];
@@ -84,22 +112,24 @@ __global__ void __launch_bounds__(kThreads) gram_small_kernel(const __grid_const
     if (lane == 0) red[warp][t] = s;
   }
   __syncthreads();
-  float* part = a.partials + (size_t)blockIdx.x * n * n;
+  float* part = a.partials + (size_t)blockIdx.x * ne * ne;
   for (int t = threadIdx.x; t < T; t += kThreads) {
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) s += red[w][t];
-    // decode t -> (i, k), i <= k
+    // decode t -> (i, k), i <= k  (register rows; the aux row NS is logical row n)
     int i = 0, rem = t;
-    while (rem >= NS - i) {
-      rem -= NS - i;
+    while (rem >= NR - i) {
+      rem -= NR - i;
       ++i;
     }
-    const int k = i + rem;
-    if (i < n && k < n) {
-      part[i * n + k] = s;
-      part[k * n + i] = s;
-    }
+    int k = i + rem;
+    if (AUX && i == NS) i = n;
+    else if (i >= n) continue;
+    if (AUX && k == NS) k = n;
+    else if (k >= n) continue;
+    part[i * ne + k] = s;
+    part[k * ne + i] = s;
   }
 }
 
@@ -213,23 +243,37 @@ int bz_gram(const BzGramArgs* args, int sm_count, cudaStream_t stream) {
   const int n = a.n;
   const int grid = grid_for(n, a.len, sm_count);
   if (grid > a.num_partials) return (int)cudaErrorInvalidValue;
+  if (a.aux_median != nullptr && n >= BZ_MAXN) return (int)cudaErrorInvalidValue;
   bool al16 = (a.off % 4) == 0, al8 = (a.off % 2) == 0;
   for (int i = 0; i < n; ++i) {
     al16 = al16 && ((uintptr_t)a.rows.p[i] % 16) == 0;
     al8 = al8 && ((uintptr_t)a.rows.p[i] % 8) == 0;
   }
+  const bool aux = a.aux_median != nullptr;
+  if (aux) {
+    if (n > 16) return (int)cudaErrorInvalidValue;
+    al16 = al16 && ((uintptr_t)a.aux_median % 16) == 0;
+    al8 = al8 && ((uintptr_t)a.aux_median % 8) == 0;
+    a.scales.s[n] = 1.f;           // the median row is built from already-scaled values
+  }
+#define BZ_GRAM_SMALL(NS_, V_)                                                         \
+  do {                                                                                 \
+    if (aux) gram_small_kernel<NS_, V_, true><<<grid, kThreads, 0, stream>>>(a);       \
+    else gram_small_kernel<NS_, V_, false><<<grid, kThreads, 0, stream>>>(a);          \
+  } while (0)
   if (n <= 2) {
-    if (al16) gram_small_kernel<2, 4><<<grid, kThreads, 0, stream>>>(a);
-    else gram_small_kernel<2, 1><<<grid, kThreads, 0, stream>>>(a);
+    if (al16) BZ_GRAM_SMALL(2, 4);
+    else BZ_GRAM_SMALL(2, 1);
   } else if (n <= 4) {
-    if (al16) gram_small_kernel<4, 4><<<grid, kThreads, 0, stream>>>(a);
-    else gram_small_kernel<4, 1><<<grid, kThreads, 0, stream>>>(a);
+    if (al16) BZ_GRAM_SMALL(4, 4);
+    else BZ_GRAM_SMALL(4, 1);
   } else if (n <= 8) {
-    if (al16) gram_small_kernel<8, 4><<<grid, kThreads, 0, stream>>>(a);
-    else gram_small_kernel<8, 1><<<grid, kThreads, 0, stream>>>(a);
+    if (al16) BZ_GRAM_SMALL(8, 4);
+    else BZ_GRAM_SMALL(8, 1);
   } else if (n <= 16) {
-    if (al8) gram_small_kernel<16, 2><<<grid, kThreads, 0, stream>>>(a);
-    else gram_small_kernel<16, 1><<<grid, kThreads, 0, stream>>>(a);
+    if (al8) BZ_GRAM_SMALL(16, 2);
+    else BZ_GRAM_SMALL(16, 1);
+#undef BZ_GRAM_SMALL
   } else if (n <= 32) {
     gram_tiled_kernel<2><<<grid, kThreads, 0, stream>>>(a);
   } else if (n <= 64) {
@@ -240,7 +284,8 @@ int bz_gram(const BzGramArgs* args, int sm_count, cudaStream_t stream) {
   int e = (int)cudaGetLastError();
   if (e) return e;
   const int rt = 128;
-  gram_reduce_kernel<<<(n * n + rt - 1) / rt, rt, 0, stream>>>(a.partials, grid, n, a.scales, a.G,
-                                                               a.G64);
+  const int ne = n + (aux ? 1 : 0);
+  gram_reduce_kernel<<<(ne * ne + rt - 1) / rt, rt, 0, stream>>>(a.partials, grid, ne, a.scales, a.G,
+                                                                 a.G64);
   return (int)cudaGetLastError();
 }

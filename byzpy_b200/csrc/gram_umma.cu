@@ -44,15 +44,16 @@ constexpr int kConvThreads = kConvWarps * 32;
 constexpr int kThreads = 32 + kConvThreads;   // warp 0 = TMEM allocator + MMA issuer
 constexpr int kOpCols = 32;                   // columns per operand tile (128 B swizzle row)
 constexpr int kRows = 128;                    // padded M
-constexpr int kOpStages = 4;
+constexpr int kOpStages = 3;
 constexpr int kOpTileBytes = kRows * kOpCols * 4;             // 16 KB (hi) ; lo follows
 constexpr int kOpStageBytes = 2 * kOpTileBytes;               // 32 KB
-constexpr int kPrefetch = 3;                  // operand tiles of global loads kept in flight per thread
+constexpr int kRawStages = 6;                 // cp.async ring of raw fp32 tiles: 5 tiles (80 KB) in flight per SM
 constexpr int kChunksPerThread = kRows * 8 / kConvThreads;    // 16-byte chunks per thread per tile (4)
+constexpr int kRawStageBytes = kChunksPerThread * kConvThreads * 16;   // 16 KB
 constexpr int kTmemCols = 256;                // D_hh at column 0, D_hl at column 128
 constexpr int kPartialStageBytes = 0;
 constexpr int kSmemBytes = 1024 /*align slack*/ + kOpStages * kOpStageBytes + 256 /*barriers*/ +
-                           kPartialStageBytes;
+                           kRawStages * kRawStageBytes + kPartialStageBytes;
 constexpr unsigned long long kWaitBudgetCycles = 4000000000ull;  // ~2 s: trap instead of hanging
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -208,9 +209,13 @@ __global__ void __launch_bounds__(kThreads, 1) gram_umma_kernel(const __grid_con
   } else {
     // ========================= loaders / converters / epilogue ============================
     // Each thread owns kChunksPerThread 16-byte chunks of every 128 x 32 tile: chunk q covers
-    // row q / 8, 16-byte column group q % 8.  Loads go straight from the row pointer table
-    // (local or peer HBM) into registers, kPrefetch tiles ahead of their use.
+    // row q / 8, 16-byte column group q % 8.  The raw fp32 chunks travel global (local or peer HBM)
+    // -> shared memory with cp.async into a THREAD-PRIVATE slot of a kRawStages-deep ring, so the
+    // bytes in flight are bounded by shared memory (80 KB / SM) instead of registers and nobody
+    // else ever reads the slot (cp.async.wait_group is the only synchronisation); the owner then
+    // splits hi / lo and writes the swizzled operand tiles.
     const int ct = threadIdx.x - 32;
+    uint8_t* raw_base = op_base + kOpStages * kOpStageBytes + 256;
     int rows_[kChunksPerThread], cs_[kChunksPerThread];
     const float* src_[kChunksPerThread];
 #pragma unroll
@@ -221,49 +226,57 @@ __global__ void __launch_bounds__(kThreads, 1) gram_umma_kernel(const __grid_con
       const int blk = rows_[j] / n_pad, drow = rows_[j] % n_pad;
       src_[j] = (drow < n) ? a.rows.p[drow] + a.off + blk * kOpCols + cs_[j] * 4 : nullptr;
     }
-    float4 buf[kPrefetch][kChunksPerThread];
-    auto issue = [&](long long t, int slot) {
-      const long long col = ((long long)blockIdx.x + t * gridDim.x) * tile_cols;
-#pragma unroll
-      for (int j = 0; j < kChunksPerThread; ++j)
-        if (src_[j] != nullptr) buf[slot][j] = ldg_stream4(src_[j] + col);
+    auto raw_slot = [&](int stage, int j) -> uint8_t* {
+      return raw_base + (size_t)stage * kRawStageBytes + ((size_t)j * kConvThreads + ct) * 16;
     };
+    auto issue = [&](long long t) {
+      const long long col = ((long long)blockIdx.x + t * gridDim.x) * tile_cols;
+      const int stage = (int)(t % kRawStages);
 #pragma unroll
-    for (int pf = 0; pf < kPrefetch; ++pf)
-      if (pf < my_tiles) issue(pf, pf);
-    for (long long t0 = 0; t0 < my_tiles; t0 += kPrefetch) {
-#pragma unroll
-      for (int slot = 0; slot < kPrefetch; ++slot) {
-        const long long t = t0 + slot;
-        if (t < my_tiles) {
-          const int os = (int)(t % kOpStages);
-          mbar_wait(smem_u32(&op_empty[os]), (uint32_t)(((t / kOpStages) & 1) ^ 1));
-          uint8_t* hi = op_base + os * kOpStageBytes;
-          uint8_t* lo = hi + kOpTileBytes;
-#pragma unroll
-          for (int j = 0; j < kChunksPerThread; ++j) {
-            if (src_[j] != nullptr) {
-              const float4 x = buf[slot][j];
-              const float xs[4] = {x.x, x.y, x.z, x.w};      // row scales are applied in the reduce
-              uint32_t hh[4], ll[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                hh[e] = to_tf32(xs[e]);
-                ll[e] = __float_as_uint(xs[e] - __uint_as_float(hh[e]));
-              }
-              const int row = rows_[j];
-              const int off = (row >> 3) * 1024 + (row & 7) * 128 + ((cs_[j] ^ (row & 7)) << 4);
-              *reinterpret_cast<uint4*>(hi + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-              *reinterpret_cast<uint4*>(lo + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
-            }
-          }
-          fence_proxy_async();                         // generic-proxy writes -> async proxy (UMMA)
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&op_full[os]));   // one arrival per converter warp
-          if (t + kPrefetch < my_tiles) issue(t + kPrefetch, slot);
+      for (int j = 0; j < kChunksPerThread; ++j) {
+        if (src_[j] != nullptr) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(raw_slot(stage, j))),
+                       "l"(src_[j] + col)
+                       : "memory");
         }
       }
+    };
+#pragma unroll
+    for (int pf = 0; pf < kRawStages - 1; ++pf) {
+      if (pf < my_tiles) issue(pf);
+      asm volatile("cp.async.commit_group;" ::: "memory");
     }
+    for (long long t = 0; t < my_tiles; ++t) {
+      if (t + kRawStages - 1 < my_tiles) issue(t + kRawStages - 1);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group %0;" ::"n"(kRawStages - 1) : "memory");
+      const int os = (int)(t % kOpStages);
+      const int rs = (int)(t % kRawStages);
+      mbar_wait(smem_u32(&op_empty[os]), (uint32_t)(((t / kOpStages) & 1) ^ 1));
+      uint8_t* hi = op_base + os * kOpStageBytes;
+      uint8_t* lo = hi + kOpTileBytes;
+#pragma unroll
+      for (int j = 0; j < kChunksPerThread; ++j) {
+        if (src_[j] != nullptr) {
+          const float4 x = *reinterpret_cast<const float4*>(raw_slot(rs, j));
+          const float xs[4] = {x.x, x.y, x.z, x.w};      // row scales are applied in the reduce
+          uint32_t hh[4], ll[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            hh[e] = to_tf32(xs[e]);
+            ll[e] = __float_as_uint(xs[e] - __uint_as_float(hh[e]));
+          }
+          const int row = rows_[j];
+          const int off = (row >> 3) * 1024 + (row & 7) * 128 + ((cs_[j] ^ (row & 7)) << 4);
+          *reinterpret_cast<uint4*>(hi + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+          *reinterpret_cast<uint4*>(lo + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+        }
+      }
+      fence_proxy_async();                         // generic-proxy writes -> async proxy (UMMA)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&op_full[os]));   // one arrival per converter warp
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     // ---- epilogue: TMEM -> registers -> per-CTA partials (first 4 converter warps) -------
     if (my_tiles > 0 && warp <= 4) {
       mbar_wait(smem_u32(acc_full), 0);

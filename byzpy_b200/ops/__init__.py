@@ -226,6 +226,30 @@ def _gram_scratch(dev: torch.device, n: int) -> torch.Tensor:
     return buf
 
 
+def gram_with_median(rows: Rows, *, scales: Optional[Sequence[float]] = None,
+                     want64: bool = False) -> Optional[Tuple[torch.Tensor, torch.Tensor]]:
+    """One pass over the rows that produces BOTH the coordinate-wise lower median ``m`` of the (scaled)
+    rows and the Gram matrix of ``[rows..., m]`` (``(n+1, n+1)``): the start point of Weiszfeld /
+    centred clipping costs no extra pass over the n x d matrix.  Returns ``None`` when the fused
+    kernel does not apply (CPU tensors, n > 16) -- callers then run the two passes."""
+    rows = as_rows(rows)
+    n = len(rows)
+    if not _kernel_ok(rows) or n > 16:
+        return None
+    ext = require_ext()
+    rows = _prep(rows)
+    d = rows[0].numel()
+    dev = rows[0].device
+    med = torch.empty(d, dtype=torch.float32, device=dev)
+    G = torch.empty((n + 1, n + 1), dtype=torch.float32, device=dev)
+    G64 = torch.empty((n + 1, n + 1), dtype=torch.float64, device=dev) if want64 else None
+    scratch = _gram_scratch(dev, n + 1)
+    ext.gram([r.data_ptr() for r in rows], _scales(scales, n), 0, d, scratch.data_ptr(),
+             scratch.numel() // ((n + 1) * (n + 1)), G.data_ptr(), G64.data_ptr() if want64 else 0,
+             sm_count(dev), _stream(dev), med.data_ptr())
+    return (G64 if want64 else G), med
+
+
 def gram(rows: Rows, *, scales: Optional[Sequence[float]] = None, want64: bool = False,
          impl: str = "auto") -> torch.Tensor:
     """``G = (S X)(S X)^T`` as an ``(n, n)`` tensor on the rows' device.
@@ -435,7 +459,7 @@ def sgd_step(grad: torch.Tensor, params: Sequence[torch.Tensor],
 
 __all__ = [
     "MODE_MEDIAN", "MODE_TRMEAN", "MODE_MEAMED", "MODE_MEAN", "as_rows", "cw_select", "cw_median",
-    "cw_trimmed_mean", "cw_meamed", "cw_mean", "gram", "sqdist_from_gram", "weighted_sum",
+    "cw_trimmed_mean", "cw_meamed", "cw_mean", "gram", "gram_with_median", "sqdist_from_gram", "weighted_sum",
     "colstat", "scale_copy", "fill_", "gaussian_", "sgd_step", "extension_available",
     "require_ext", "sm_count", "normalize_uint8_nhwc", "count_launch", "launches",
 ]

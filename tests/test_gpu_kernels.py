@@ -514,3 +514,28 @@ def test_mda_and_smea_aggregators_use_the_device_solver():
         exp = agg.aggregate([X[i] for i in range(9)])       # CPU path = host oracle
         torch.testing.assert_close(out.cpu(), exp, rtol=1e-4, atol=1e-4)
         assert agg.fused_plan(9).capturable and not agg.fused_plan(64 if agg.name != "smea" else 40).capturable
+
+
+@pytest.mark.parametrize("n,d", [(3, 4096 + 3), (8, 100_003), (9, 50_001), (16, 33_333)])
+def test_gram_with_fused_median_row(n, d):
+    """One pass: lower median of the scaled rows + Gram matrix of [rows..., median]."""
+    rows, X = rows_of(n, d, seed=40 + n)
+    scales = [(-1.0 if i % 3 == 1 else 1.0) * (1.0 + 0.1 * i) for i in range(n)]
+    G, med = ops.gram_with_median(rows, scales=scales, want64=True)
+    Xs = X.double() * torch.tensor(scales, dtype=torch.float64).view(-1, 1)
+    exp_med = ops.cw_median(rows, scales=scales)
+    assert torch.equal(med, exp_med)
+    Xa = torch.cat([Xs, med.cpu().double().view(1, -1)], dim=0)
+    torch.testing.assert_close(G.cpu(), Xa @ Xa.T, rtol=2e-5, atol=2e-5 * d ** 0.5)
+    assert ops.gram_with_median([r.cpu() for r in rows]) is None          # CPU: caller does two passes
+
+
+def test_geometric_median_uses_fused_median_gram_pass():
+    from byzpy_b200.aggregators.geometric_wise import GeometricMedian
+
+    rows, X = rows_of(8, 200_000, seed=77)
+    rows[2].mul_(50.0)
+    X[2] *= 50.0
+    out = GeometricMedian().aggregate(rows)
+    exp = GeometricMedian().aggregate([X[i] for i in range(8)])
+    torch.testing.assert_close(out.cpu(), exp, rtol=1e-3, atol=1e-3)
