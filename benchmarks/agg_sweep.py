@@ -118,7 +118,9 @@ def main():
             ("trimmed_mean", lambda: CoordinateWiseTrimmedMean(f=f).aggregate(rows), lambda: ref_trmean(rows, f), bytes_1pass),
             ("multi_krum", lambda: MultiKrum(f=f, q=n - f).aggregate(rows), lambda: ref_multikrum(rows, f, n - f), bytes_2pass),
             ("centered_clipping", lambda: CenteredClipping(c_tau=1.0, M=10).aggregate(rows), lambda: ref_cclip(rows, 1.0, 10), bytes_2pass),
-            ("geometric_median", lambda: GeometricMedian(max_iter=64).aggregate(rows), lambda: ref_gm(rows, max_iter=64), bytes_2pass + n * d * 4 + d * 4),
+            ("geometric_median", lambda: GeometricMedian(max_iter=64).aggregate(rows), lambda: ref_gm(rows, max_iter=64),
+             # pass 1 reads n rows and writes the median start row, pass 2 reads n + 1 rows and writes the result
+             bytes_2pass + 3 * d * 4),
         ]
         for name, ours, ref, nbytes in ops_list:
             t_ours = timeit(ours, flush=flush)
