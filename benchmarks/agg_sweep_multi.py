@@ -108,9 +108,17 @@ def main():
                 w.arena.flat_grads[:d].copy_(torch.randn(d, device=dev, generator=g))
             ours = timeit(rnd.launch_aggregate, dev)
             rnd.check_status()
+            # bytes one rank moves per round: its coordinate shard of all 8 rows (once for coordinate-wise
+            # aggregators, twice -- Gram pass + weighted-sum pass -- for the Gram family), the aggregate
+            # written into every rank's buffer, and the SGD(+momentum) update of its L local replicas
+            # (read p, m; write p, m -- the aggregate stays in registers)
+            passes = 1 if name in ("median", "trmean") else 2
+            per_gpu = (passes * N_ROWS * d / world + d + L * 4 * d) * 4
             out = dict(agg=name, d=d, n_gpus=world, rows=N_ROWS, ours_ms=round(ours, 4),
                        gathered_GB=round(N_ROWS * d * 4 / 1e9, 3),
-                       ours_GBps_per_gpu=round(N_ROWS * d * 4 / world / ours / 1e6, 1))
+                       bytes_per_gpu_GB=round(per_gpu / 1e9, 3),
+                       ours_GBps_per_gpu=round(per_gpu / ours / 1e6, 1),
+                       frac_of_hbm_peak=round(per_gpu / ours / 1e6 / 6482.7, 3))
             if d <= a.skip_ref_above:
                 rows = torch.stack([w.arena.flat_grads[:d] for w in rnd.workers])
                 params = [torch.zeros(d, device=dev) for _ in range(L)]

@@ -22,18 +22,20 @@
 // Warp roles (288 threads):
 //   warp 0      TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit releases the
 //               operand stage / signals the epilogue;
-//   warps 1..8  loaders + converters: 16-byte ld.global.nc straight from the row pointer table
-//               (rows may live in peer HBM), kept 3 tiles ahead in registers (12 x 16 B in flight
-//               per thread, ~49 KB per SM); split hi/lo; write the two K-major SWIZZLE_128B operand
+//   warps 1..8  loaders + converters: 16-byte cp.async straight from the row pointer table (rows may
+//               live in peer HBM) into a THREAD-PRIVATE slot of a 6-deep shared-memory ring (5 raw
+//               tiles = 80 KB in flight per SM; only cp.async.wait_group, no block barrier); the owner
+//               reads its chunk back, splits hi/lo and writes the two K-major SWIZZLE_128B operand
 //               tiles (conflict-free), fence.proxy.async, arrive on the stage's mbarrier.
 //               Warps 1..4 are also the epilogue (tcgen05.ld TMEM -> registers -> per-CTA partial).
-// Two mbarrier rings: operand full/empty (converters <-> MMA) and accumulator full.
+// Two mbarrier rings: operand full/empty (converters <-> MMA, 3 stages) and accumulator full.
 //
 // Measured design note (profiles/gram_umma.md): the first version fed the converters with one
 // cp.async.bulk (TMA, UBLKCP) per row per 64-column chunk.  Bulk copies are issued through the
 // uniform datapath, ~80 cycles each, so 256-byte copies cap a CTA at ~3 B/clk (0.9 TB/s chip-wide,
 // ncu: dram 11 %, tensor 10 %).  A pointer-table of rows cannot use one 2-D tensor map, so the
-// loads moved to the LSU path above.
+// loads moved to the LSU: first LDG with a 3-tile register prefetch (0.40 of the HBM roofline),
+// then the cp.async ring above (0.52; tensor pipe 41 % busy with two TF32 MMAs per k-step).
 #include "api.h"
 #include "gram_umma.h"
 
