@@ -192,7 +192,8 @@ def run_ours(args, rank, world, device):
     ps = ParameterServer(honest, byz, CoordinateWiseMedian(), update_byzantines=True,
                          layout=layout, amp_dtype=torch.bfloat16, use_cuda_graph=not args.no_graph,
                          worker_streams=args.worker_streams, fused=True,
-                         direct_grads=not args.no_direct_grads, overlap_wgrad=not args.no_overlap_wgrad)
+                         direct_grads=not args.no_direct_grads, overlap_wgrad=not args.no_overlap_wgrad,
+                         branch_streams=not args.no_branch_streams)
     rnd = ps.device_round
 
     def batches(i):
@@ -423,6 +424,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-direct-grads", action="store_true",
                     help="A/B: stock autograd gradient accumulation instead of in-place arena gradients")
+    ap.add_argument("--no-branch-streams", action="store_true",
+                    help="A/B: projection shortcuts of the residual blocks on the worker stream")
     ap.add_argument("--no-overlap-wgrad", action="store_true",
                     help="A/B: weight-gradient GEMMs on the worker stream instead of a side stream")
     args = ap.parse_args()

@@ -55,8 +55,9 @@ class ParameterServer:
                  weight_decay: Optional[float] = None, amp_dtype: Optional[torch.dtype] = torch.bfloat16,
                  use_cuda_graph: bool = True, worker_streams: int = 1, fused: Optional[bool] = None,
                  node_timeout: Optional[float] = None, tolerate_failures: bool = False,
-                 direct_grads: bool = True, overlap_wgrad: bool = True):
-        self._device_opts = dict(direct_grads=direct_grads, overlap_wgrad=overlap_wgrad)
+                 direct_grads: bool = True, overlap_wgrad: bool = True, branch_streams: bool = True):
+        self._device_opts = dict(direct_grads=direct_grads, overlap_wgrad=overlap_wgrad,
+                                 branch_streams=branch_streams)
         self.hon = list(honest_nodes)
         self.byz = list(byzantine_nodes)
         self.agg = aggregator

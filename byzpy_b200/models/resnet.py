@@ -40,8 +40,36 @@ def _bn(channels: int, relu: bool = False) -> nn.BatchNorm2d:
     return FusedBatchNorm2d(channels, relu=relu)
 
 
+def _shortcut(block: nn.Module, x: torch.Tensor):
+    """The block's identity / projection shortcut.  When a device worker has handed the block a
+    ``_branch_stream``, the projection (1x1 conv + BN) runs on that stream concurrently with the main
+    branch -- forward here, and backward too, because autograd replays an op on the stream of its
+    forward.  At one replica per GPU the step is a dependency chain of ~400 short kernels; the three
+    projection branches of a ResNet are ~8 % of it."""
+    if block.downsample is None:
+        return x, None
+    side = getattr(block, "_branch_stream", None)
+    if side is None or not x.is_cuda:
+        return block.downsample(x), None
+    main = torch.cuda.current_stream(x.device)
+    side.wait_stream(main)
+    x.record_stream(side)
+    with torch.cuda.stream(side):
+        idt = block.downsample(x)
+    return idt, (main, side)
+
+
+def _join(idt: torch.Tensor, fork) -> torch.Tensor:
+    if fork is not None:
+        main, side = fork
+        main.wait_stream(side)
+        idt.record_stream(main)
+    return idt
+
+
 class BasicBlock(nn.Module):
     expansion = 1
+    supports_branch_stream = True
 
     def __init__(self, cin: int, width: int, stride: int = 1, downsample: nn.Module | None = None):
         super().__init__()
@@ -53,13 +81,14 @@ class BasicBlock(nn.Module):
         self.downsample = downsample
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        idt = x if self.downsample is None else self.downsample(x)
-        y = self.bn1(self.conv1(x))          # ReLU fused into bn1
-        return self.bn2(self.conv2(y), idt)  # residual add + ReLU fused into bn2
+        idt, fork = _shortcut(self, x)
+        y = self.conv2(self.bn1(self.conv1(x)))          # ReLU fused into bn1
+        return self.bn2(y, _join(idt, fork))             # residual add + ReLU fused into bn2
 
 
 class Bottleneck(nn.Module):
     expansion = 4
+    supports_branch_stream = True
 
     def __init__(self, cin: int, width: int, stride: int = 1, downsample: nn.Module | None = None):
         super().__init__()
@@ -73,10 +102,10 @@ class Bottleneck(nn.Module):
         self.downsample = downsample
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        idt = x if self.downsample is None else self.downsample(x)
+        idt, fork = _shortcut(self, x)
         y = self.bn1(self.conv1(x))          # ReLU fused
-        y = self.bn2(self.conv2(y))          # ReLU fused
-        return self.bn3(self.conv3(y), idt)  # residual add + ReLU fused
+        y = self.conv3(self.bn2(self.conv2(y)))          # ReLU fused
+        return self.bn3(y, _join(idt, fork))             # residual add + ReLU fused
 
 
 class ResNet(nn.Module):

@@ -438,7 +438,7 @@ class FusedMaxPool2d(nn.MaxPool2d):
 
 # --------------------------------------------------------------------------- switch
 def enable_direct_grads(module: nn.Module, *, side_stream: Optional["torch.cuda.Stream"] = None,
-                        enabled: bool = True) -> GradSink:
+                        enabled: bool = True, branch_stream: Optional["torch.cuda.Stream"] = None) -> GradSink:
     """Switch every in-place-gradient layer of ``module`` on (or off).
 
     Call after the parameters' ``.grad`` have been bound to the gradient arena.  In this mode a
@@ -456,6 +456,9 @@ def enable_direct_grads(module: nn.Module, *, side_stream: Optional["torch.cuda.
                 sink.convs.append(m)        # (the s2d stem also keeps a KRSC shadow for its fallback path)
         elif isinstance(m, FusedBatchNorm2d):
             m._direct_grad = enabled
+        if getattr(m, "supports_branch_stream", False):
+            # residual blocks run their projection shortcut on this stream (models/resnet.py)
+            m._branch_stream = branch_stream if enabled else None
     return sink
 
 

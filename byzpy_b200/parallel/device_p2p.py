@@ -132,6 +132,18 @@ class DeviceP2PRound:
                 p.arena = ParamArena(p.model, flat_params=self.params[i], flat_grads=self.grads[i])
         self._pads = [self.sym.peer_ptr(r, self._off_pad) for r in range(self.world)]
         self._has_byz = layout.n_byz > 0
+        # Remote vectors are staged ONCE per round into local HBM (one pass over NVLink): with L local
+        # peers and a 2-3 pass aggregator every remote byte would otherwise cross the link 2-3 x L
+        # times (measured: BERT-base GM at 2 GPUs was NVLink bound, profiles/training_configs.md).
+        needed = []
+        for g in self.local_ids:
+            for j in dict.fromkeys(self.topology.in_.get(g, [])):
+                if self.layout.rank_of(j) != self.rank and j not in needed:
+                    needed.append(j)
+        self._staged_ids = needed
+        self._stage = (torch.empty((len(needed), self.d_pad), dtype=torch.float32, device=self.device)
+                       if needed else None)
+        self._stage_slot = {j: k for k, j in enumerate(needed)}
         self._tables = [self._neighbour_table(g) for g in self.local_ids]
         self._work = [self._workspace(i) for i in range(L)]
         self.use_cuda_graph = use_cuda_graph and all(
@@ -143,8 +155,23 @@ class DeviceP2PRound:
         torch.cuda.synchronize(self.device)
 
     # ---------------------------------------------------------------------------------
-    def _row_ptr(self, g: int) -> int:
+    def _remote_ptr(self, g: int) -> int:
         return self.sym.peer_ptr(self.layout.rank_of(g), self.layout.slot_of(g) * self.d_pad * 4)
+
+    def _row_ptr(self, g: int) -> int:
+        """Where peer g's published vector is read from: its symmetric slot when it lives on this
+        rank, otherwise this rank's staged copy."""
+        k = self._stage_slot.get(g)
+        if k is not None:
+            return self._stage[k].data_ptr()
+        return self._remote_ptr(g)
+
+    def _stage_remote(self, honest: bool, stream: int) -> None:
+        """Pull the remote peers' vectors over NVLink into the local staging rows (P2P loads)."""
+        for j in self._staged_ids:
+            if (j < self.layout.n_honest) == honest:
+                self.ext.scale_copy(self._remote_ptr(j), self._stage[self._stage_slot[j]].data_ptr(), 1.0,
+                                    self.d_pad, self.sm, stream)
 
     def _neighbour_table(self, g: int) -> List[int]:
         ins = list(dict.fromkeys(self.topology.in_.get(g, [])))
@@ -205,14 +232,22 @@ class DeviceP2PRound:
                           self.sm, stream)
             return
         all_rows = list(rows)
-        for kind, buf in zip(plan.aux, ws["aux"]):
-            ext.cw_select(rows, [], ops.MODE_MEDIAN, 0, 0, 0, 0.0, 0.0, 0, d, buf.data_ptr(), [], [], 0.0,
-                          0.0, 0.0, self.sm, stream)
-            all_rows.append(buf.data_ptr())
         nt = ws["nt"]
+        fused_median = tuple(plan.aux) == ("median",) and len(rows) <= 16
+        if not fused_median:
+            for kind, buf in zip(plan.aux, ws["aux"]):
+                ext.cw_select(rows, [], ops.MODE_MEDIAN, 0, 0, 0, 0.0, 0.0, 0, d, buf.data_ptr(), [], [], 0.0,
+                              0.0, 0.0, self.sm, stream)
+                all_rows.append(buf.data_ptr())
         tc = ext.gram_umma_tile_cols(nt)
         main = (d // tc) * tc if nt > 16 else 0
-        if main > 0:
+        if fused_median:
+            # median start row + Gram of [rows..., median] in ONE pass (csrc/gram.cu, AUX variant)
+            med = ws["aux"][0]
+            ext.gram(rows, [], 0, d, ws["scratch"].data_ptr(), ws["scratch"].numel() // (nt * nt),
+                     ws["G32"].data_ptr(), ws["G64"].data_ptr(), self.sm, stream, med.data_ptr())
+            all_rows.append(med.data_ptr())
+        elif main > 0:
             tail = 0
             if main < d:
                 ext.gram(all_rows, [], main, d - main, ws["scratch"].data_ptr(), ws["scratch"].numel() // (nt * nt),
@@ -236,11 +271,13 @@ class DeviceP2PRound:
             if p.role == "honest":
                 self._half_step(i)
         ext.flag_barrier(self._pads, self.rank, ext.PAD_READY, ctl + 8, ctl + 4, stream)
+        self._stage_remote(True, stream)
         if self._has_byz:
             for i, p in enumerate(self.peers):
                 if p.role != "honest":
                     self._attack(i, stream)
             ext.flag_barrier(self._pads, self.rank, PAD_BYZ, ctl + 8, ctl + 4, stream)
+            self._stage_remote(False, stream)
         for i, p in enumerate(self.peers):
             if p.role == "honest":
                 self._aggregate(i, stream)

@@ -108,12 +108,14 @@ class DeviceWorker:
         self.mom = mom
         self.loss_slot = loss_slot
 
-    def enable_direct_grads(self, side_stream: Optional["torch.cuda.Stream"] = None) -> None:
+    def enable_direct_grads(self, side_stream: Optional["torch.cuda.Stream"] = None,
+                            branch_stream: Optional["torch.cuda.Stream"] = None) -> None:
         """Let the replica's own layer types (models/resnet.py) write their parameter gradients
-        straight into the arena row, weight gradients on ``side_stream`` (ops/fused_layers.py)."""
+        straight into the arena row, weight gradients on ``side_stream`` (ops/fused_layers.py);
+        projection shortcuts of residual blocks run on ``branch_stream``."""
         from ..ops.fused_layers import enable_direct_grads
 
-        self.sink = enable_direct_grads(self.model, side_stream=side_stream)
+        self.sink = enable_direct_grads(self.model, side_stream=side_stream, branch_stream=branch_stream)
 
     @property
     def static_x(self) -> Optional[torch.Tensor]:
@@ -203,7 +205,7 @@ class DeviceRound:
                  group=None, amp_dtype: Optional[torch.dtype] = torch.bfloat16,
                  use_cuda_graph: bool = True, worker_streams: int = 1,
                  virtual_fold: Optional[RowFold] = None, direct_grads: bool = True,
-                 overlap_wgrad: bool = True):
+                 overlap_wgrad: bool = True, branch_streams: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("DeviceRound needs a CUDA device (B200)")
         self.ext = ops.require_ext()
@@ -276,10 +278,13 @@ class DeviceRound:
         # stream, the wgrad GEMMs of the same replica overlap with it
         self._wgrad_streams = ([torch.cuda.Stream(self.device) for _ in range(1 + len(self._side_streams))]
                                if (direct_grads and overlap_wgrad) else [])
+        self._branch_streams = ([torch.cuda.Stream(self.device) for _ in range(1 + len(self._side_streams))]
+                                if (direct_grads and branch_streams) else [])
         if direct_grads:
             for i, w in enumerate(self.workers):
-                w.enable_direct_grads(self._wgrad_streams[i % len(self._wgrad_streams)]
-                                      if self._wgrad_streams else None)
+                w.enable_direct_grads(
+                    self._wgrad_streams[i % len(self._wgrad_streams)] if self._wgrad_streams else None,
+                    self._branch_streams[i % len(self._branch_streams)] if self._branch_streams else None)
         self._gram_ws = None
         self.launches_per_step = 0
         self.model_launches_per_step = 0

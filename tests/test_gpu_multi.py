@@ -23,3 +23,15 @@ def test_fused_round_two_ranks(agg):
            os.path.join(ROOT, "tests", "multi_gpu", "check_fused_round.py"), "--agg", agg]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert res.returncode == 0 and "MULTI_GPU_FUSED_ROUND PASS" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("agg,topology", [("trmean", "complete"), ("gm", "complete"), ("trmean", "ring")])
+def test_p2p_round_two_ranks(agg, topology):
+    """Device gossip round across ranks: remote vectors staged over NVLink once per round, robust
+    aggregation per peer, compared with an NCCL all_gather + plain-tensor reference."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29534",
+           os.path.join(ROOT, "tests", "multi_gpu", "check_p2p_round.py"), "--agg", agg, "--topology", topology]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert res.returncode == 0 and "MULTI_GPU_P2P_ROUND PASS" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
