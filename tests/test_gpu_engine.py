@@ -68,7 +68,7 @@ def test_attacks_cuda():
         kg = {k: (gd[0] if v == 0 else gd) for k, v in kw.items()}
         a, b = mk().apply(**kc), mk().apply(**kg)
         assert b.is_cuda
-        torch.testing.assert_close(b.cpu(), a, rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(b.cpu(), a, rtol=1e-5, atol=1e-5, msg=lambda m: f"{type(mk()).__name__}: {m}")
     z = GaussianAttack(mu=0.5, sigma=3.0, seed=1).apply(honest_grads=[torch.zeros(1 << 18, device=DEV)])
     assert abs(z.mean().item() - 0.5) < 0.05 and abs(z.std().item() - 3.0) < 0.05
 
