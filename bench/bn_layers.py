@@ -35,8 +35,11 @@ def timeit(fn, it=50):
     return e0.elapsed_time(e1) / it * 1e3
 
 
-for shape in [(32, 64, 112, 112), (32, 64, 56, 56), (32, 128, 28, 28), (32, 256, 14, 14), (32, 512, 7, 7)]:
-    for res in (False, True):
+SHAPES = [(32, 64, 112, 112), (32, 64, 56, 56), (32, 128, 28, 28), (32, 256, 14, 14), (32, 512, 7, 7)]
+if "--stem-only" in sys.argv:      # for ncu captures of the big-activation kernels
+    SHAPES = SHAPES[:1]
+for shape in SHAPES:
+    for res in ((False,) if "--stem-only" in sys.argv else (False, True)):
         N, C, H, W = shape
         mk = lambda: torch.randn(shape, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         x, r, gy = mk().requires_grad_(True), mk().requires_grad_(True), mk()

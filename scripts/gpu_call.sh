@@ -1,3 +1,5 @@
 mkdir -p gpurun_out
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/bench28_n8.log 2>&1; tail -1 gpurun_out/bench28_n8.log | cut -c1-1500
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus 4 --steps 20 --warmup 5 > gpurun_out/bench28_n4.log 2>&1; tail -1 gpurun_out/bench28_n4.log | cut -c1-1500
+timeout 400 python bench.py --impl reference --gpus 1 --steps 5 --warmup 3 > gpurun_out/bench29_ref.log 2>&1; echo "ref rc=$?"; tail -1 gpurun_out/bench29_ref.log | cut -c1-300
+timeout 1200 python -m pytest tests -m gpu -x -q -p no:warnings > gpurun_out/pytest29.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest29.log | cut -c1-300
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:"reduce_partial|apply_kernel|finalize_kernel" -s 30 -c 6 -f -o gpurun_out/bn_stem python bench/bn_layers.py --stem-only > gpurun_out/ncu_bn.log 2>&1; ls -la gpurun_out/bn_stem.ncu-rep
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
