@@ -120,9 +120,15 @@ int bz_krsc_cast(const BzCastTable* table, int to_grad, cudaStream_t stream) {
 // (bf16, channels-last) and scatter the gradient of w' back into the fp32 OIHW gradient of w.
 namespace {
 
-struct alignas(16) Bf8x {
-  __nv_bfloat162 v[4];
-};
+__device__ __forceinline__ uint4 pack8(const float* f) {     // 8 floats -> 8 bf16 in one 128-bit word
+  uint32_t w[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+    w[k] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
 
 template <typename TIn>
 __device__ __forceinline__ float load_px(const TIn* p);
@@ -162,15 +168,9 @@ __global__ void __launch_bounds__(256) s2d_pack_kernel(const TIn* __restrict__ x
   }
 #pragma unroll
   for (int k = 12; k < 16; ++k) f[k] = 0.f;
-  Bf8x o0, o1;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    o0.v[k] = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
-    o1.v[k] = __floats2bfloat162_rn(f[8 + 2 * k], f[8 + 2 * k + 1]);
-  }
-  Bf8x* dst = reinterpret_cast<Bf8x*>(out + u * 16);
-  dst[0] = o0;
-  dst[1] = o1;
+  uint4* dst = reinterpret_cast<uint4*>(out + u * 16);
+  dst[0] = pack8(f);
+  dst[1] = pack8(f + 8);
 }
 
 // w fp32 [K][3][7][7] -> w' bf16 [K][4][4][16]
