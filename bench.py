@@ -420,7 +420,7 @@ def main():
     ap.add_argument("--classes", type=int, default=1000)
     ap.add_argument("--pool", type=int, default=4, help="distinct pinned host batches per worker")
     ap.add_argument("--lr", type=float, default=0.05)
-    ap.add_argument("--worker-streams", type=int, default=4)
+    ap.add_argument("--worker-streams", type=int, default=8)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-direct-grads", action="store_true",
                     help="A/B: stock autograd gradient accumulation instead of in-place arena gradients")

@@ -68,35 +68,41 @@ __global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(const __nv_bfloat
     t /= Wo;
     const int oh = (int)(t % Ho);
     const int n = (int)(t / Ho);
+    // all (<= 9) window loads are issued before the first compare
+    Bf8 win[9];
+    bool ok[9];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int ih = 2 * oh - 1 + kh, iw = 2 * ow - 1 + kw;
+        const bool in = (ih >= 0 && ih < H && iw >= 0 && iw < W);
+        ok[kh * 3 + kw] = in;
+        win[kh * 3 + kw] = ld8(x + (((long long)n * H + (in ? ih : 0)) * W + (in ? iw : 0)) * C + g * 8);
+      }
+    }
     float m[8];
     uint8_t am[8];
     bool first = true;
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-      const int ih = 2 * oh - 1 + kh;
-      if (ih < 0 || ih >= H) continue;
-#pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const int iw = 2 * ow - 1 + kw;
-        if (iw < 0 || iw >= W) continue;
-        float f[8];
-        unpack(ld8(x + (((long long)n * H + ih) * W + iw) * C + g * 8), f);
-        const uint8_t code = (uint8_t)(kh * 3 + kw);
-        if (first) {
-          // ATen starts from -inf with the first in-range position as the index
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            m[k] = -__builtin_huge_valf();
-            am[k] = code;
-          }
-          first = false;
-        }
+    for (int code = 0; code < 9; ++code) {
+      if (!ok[code]) continue;
+      float f[8];
+      unpack(win[code], f);
+      if (first) {
+        // ATen starts from -inf with the first in-range position as the index
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          if (f[k] > m[k] || f[k] != f[k]) {
-            m[k] = f[k];
-            am[k] = code;
-          }
+          m[k] = -__builtin_huge_valf();
+          am[k] = (uint8_t)code;
+        }
+        first = false;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (f[k] > m[k] || f[k] != f[k]) {
+          m[k] = f[k];
+          am[k] = (uint8_t)code;
         }
       }
     }
@@ -133,18 +139,30 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const __nv_bfloat
       for (int q = 0; q < 2; ++q)
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[p][q][k] = 0.f;
+    // the (<= 4) windows' index + dy loads go out first, then they are routed
+    Idx8 wid[2][2];
+    Bf8 wdy[2][2];
+    bool wok[2][2];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      const int oh = a + i;
-      if (oh >= Ho) continue;
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const int ow = b + j;
-        if (ow >= Wo) continue;
-        const long long o = (((long long)n * Ho + oh) * Wo + ow) * cg + g;
-        const Idx8 id = *reinterpret_cast<const Idx8*>(idx + o * 8);
+        const int oh = a + i, ow = b + j;
+        const bool in = (oh < Ho && ow < Wo);
+        wok[i][j] = in;
+        const long long o = (((long long)n * Ho + (in ? oh : 0)) * Wo + (in ? ow : 0)) * cg + g;
+        wid[i][j] = *reinterpret_cast<const Idx8*>(idx + o * 8);
+        wdy[i][j] = ld8(dy + o * 8);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        if (!wok[i][j]) continue;
+        const Idx8 id = wid[i][j];
         float d[8];
-        unpack(ld8(dy + o * 8), d);
+        unpack(wdy[i][j], d);
         // pixel (p, q) of the block lies in window (oh, ow) iff (i == 0 || p == 1) && (j == 0 || q == 1);
         // its position inside the window is kh = p + 1 - 2i, kw = q + 1 - 2j
 #pragma unroll
