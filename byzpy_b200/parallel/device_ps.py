@@ -273,7 +273,8 @@ class DeviceRound:
         self._h2d_done = [torch.cuda.Event(), torch.cuda.Event()]
         self._consumed = [torch.cuda.Event(), torch.cuda.Event()]
         self._prefetched = [False, False]
-        self._side_streams = [torch.cuda.Stream(self.device) for _ in range(max(0, worker_streams - 1))]
+        worker_streams = max(1, min(int(worker_streams), L))     # never more streams than local replicas
+        self._side_streams = [torch.cuda.Stream(self.device) for _ in range(worker_streams - 1)]
         # one weight-gradient stream per worker stream: backward's dgrad chain stays on the worker
         # stream, the wgrad GEMMs of the same replica overlap with it
         self._wgrad_streams = ([torch.cuda.Stream(self.device) for _ in range(1 + len(self._side_streams))]
