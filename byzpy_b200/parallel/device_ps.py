@@ -208,6 +208,9 @@ class DeviceRound:
                  overlap_wgrad: bool = True, branch_streams: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("DeviceRound needs a CUDA device (B200)")
+        # replica shapes are static for the lifetime of a round engine (they are baked into its CUDA
+        # graphs), so let cuDNN pick its fastest kernels once
+        torch.backends.cudnn.benchmark = True
         self.ext = ops.require_ext()
         self.workers = list(workers)
         self.layout = layout
