@@ -43,6 +43,8 @@ class GradSink:
         self.convs: List["ArenaConv2d"] = []
         self.shadows_fresh = False
         self.pending: List[tuple] = []      # (bf16 channels-last wgrad, fp32 arena view) awaiting the cast
+        self.shadow_event: Optional["torch.cuda.Event"] = None   # refresh issued on the side stream
+        self.flush_every = 6                # wgrads cast per launch while backward is still running
 
     def refresh_shadows(self) -> None:
         """Refresh the bf16 channels-last shadow of EVERY conv weight with one launch
@@ -53,13 +55,41 @@ class GradSink:
             return
         ext = require_ext()
         dev = convs[0].weight.device
-        n = ext.krsc_cast([m.weight.data_ptr() for m in convs], [m._shadow().data_ptr() for m in convs],
-                          [m.weight.shape[0] for m in convs], [m.weight.shape[1] for m in convs],
-                          [m.weight.shape[2] * m.weight.shape[3] for m in convs], 0, _stream(dev))
+        shadows = [m._shadow() for m in convs]          # (allocated on the launching stream, once)
+        side = self.side_stream
+        # With a side stream the cast overlaps the input pipeline and the stem (which packs its own
+        # weight): the first convolution that needs a shadow waits for `shadow_event`.
+        ctx = torch.cuda.stream(side) if side is not None else contextlib.nullcontext()
+        if side is not None:
+            side.wait_stream(torch.cuda.current_stream(dev))     # weights were updated on this stream
+        with ctx:
+            n = ext.krsc_cast([m.weight.data_ptr() for m in convs], [t.data_ptr() for t in shadows],
+                              [m.weight.shape[0] for m in convs], [m.weight.shape[1] for m in convs],
+                              [m.weight.shape[2] * m.weight.shape[3] for m in convs], 0, _stream(dev))
+            if side is not None:
+                self.shadow_event = torch.cuda.Event()
+                self.shadow_event.record(side)
         count_launch(n)
         for m in convs:
             m._shadow_fresh = True
         self.shadows_fresh = True
+
+    def wait_shadows(self) -> None:
+        """Order the current stream after the asynchronous shadow refresh (first consumer only)."""
+        if self.shadow_event is not None:
+            torch.cuda.current_stream().wait_event(self.shadow_event)
+            self.shadow_event = None
+
+    def flush_pending(self, force: bool = False) -> None:
+        """Cast the weight gradients produced so far into the arena row (on the stream that produced
+        them).  Called every few convolutions during backward so that only a short tail is left
+        after the last weight-gradient GEMM."""
+        if not self.pending or (not force and len(self.pending) < self.flush_every):
+            return
+        ctx = torch.cuda.stream(self.side_stream) if self._forked else contextlib.nullcontext()
+        with ctx:
+            _krsc_cast_many([g for g, _ in self.pending], [d for _, d in self.pending], to_grad=True)
+        self.pending.clear()
 
     def fork(self) -> Optional["torch.cuda.Stream"]:
         """Make the side stream wait for everything enqueued on the current stream so far."""
@@ -72,13 +102,8 @@ class GradSink:
 
     def join(self) -> None:
         """Order the current stream after all side-stream work of this backward pass."""
-        if self.pending:
-            # one multi-tensor launch casts every weight gradient of this backward pass into the arena
-            # row (issued where the wgrad GEMMs ran, so stream order already covers the dependency)
-            ctx = torch.cuda.stream(self.side_stream) if self._forked else contextlib.nullcontext()
-            with ctx:
-                _krsc_cast_many([g for g, _ in self.pending], [d for _, d in self.pending], to_grad=True)
-            self.pending.clear()
+        self.flush_pending(force=True)      # the (short) tail of weight gradients still to be cast
+        self.shadow_event = None
         if self._forked:
             torch.cuda.current_stream().wait_stream(self.side_stream)
             self._forked = False
@@ -139,6 +164,8 @@ class _ConvFn(torch.autograd.Function):
         w16 = mod._shadow()
         if not getattr(mod, "_shadow_fresh", False):
             _krsc_cast(weight, w16, to_grad=False)   # fp32 OIHW -> bf16 channels-last
+        elif mod._sink is not None:
+            mod._sink.wait_shadows()                 # refresh runs asynchronously on the side stream
         with torch.autocast("cuda", enabled=False):
             y = _aten.convolution(x, w16, None, mod.stride, mod.padding, mod.dilation, False, (0, 0),
                                   mod.groups)
@@ -160,14 +187,16 @@ class _ConvFn(torch.autograd.Function):
         if side is not None:
             with torch.cuda.stream(side):
                 gw = _aten.convolution_backward(dy, x, w16, *args, [False, True, False])[1]
-            sink.pending.append((gw, weight.grad))   # cast into the arena row by GradSink.join()
+            sink.pending.append((gw, weight.grad))   # cast into the arena row in batches / by join()
             sink.keep.append((dy, x, gw))      # alive until GradSink.join()
+            sink.flush_pending()
             dx = (_aten.convolution_backward(dy, x, w16, *args, [True, False, False])[0]
                   if need_dx else None)
         else:
             dx, gw, _ = _aten.convolution_backward(dy, x, w16, *args, [need_dx, True, False])
             if sink is not None:
                 sink.pending.append((gw, weight.grad))
+                sink.flush_pending()
             else:
                 _krsc_cast(gw, weight.grad, to_grad=True)
         return dx, None, None
