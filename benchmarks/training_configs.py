@@ -70,9 +70,9 @@ def timed(step, steps, warmup, dev):
 
 def config3(a, rank, world, dev):
     n_h, n_virtual = 6, 2
-    if n_h % world:
-        raise SystemExit(f"config 3 hosts {n_h} replicas: run it on 1, 2, 3 or 6 ranks")
-    layout = RowLayout.block(n_h, 0, world, n_virtual=n_virtual)
+    # 6 replicas over any number of ranks up to 8: ranks beyond the sixth host no replica and only take
+    # part in the aggregation of their coordinate shard (RowLayout.spread)
+    layout = RowLayout.spread(n_h, 0, world, n_virtual=n_virtual)
     g = torch.Generator().manual_seed(rank)
     pool = [(torch.randint(0, 256, (a.batch, 224, 224, 3), dtype=torch.uint8, generator=g).pin_memory(),
              torch.randint(0, 1000, (a.batch,), generator=g).pin_memory()) for _ in range(2)]
@@ -91,7 +91,8 @@ def config3(a, rank, world, dev):
     # the two Little rows are virtual (synthesised in-kernel); every rank declares them
     byz = [DeviceByzantineNode(LittleAttack(f=n_virtual), device=str(dev)) for _ in range(n_virtual)]
     ps = ParameterServer(honest, byz, MultiKrum(f=1, q=2), pre_aggregator=Bucketing(bucket_size=2),
-                         update_byzantines=False, layout=layout, fused=True, worker_streams=min(4, len(honest)))
+                         update_byzantines=False, layout=layout, fused=True, worker_streams=4, lr=0.05,
+                         momentum=0.9)
     ms = timed(ps.step, a.steps, a.warmup, dev)
     ps.device_round.check_status()
     d = ps.device_round.d

@@ -92,7 +92,11 @@ class ParameterServer:
     def _try_build_device_round(self, layout, group, lr, momentum, weight_decay, amp_dtype,
                                 use_cuda_graph, worker_streams):
         nodes = self.hon + self.byz
-        if not nodes or not all(_is_device_node(n) for n in nodes):
+        if not nodes:
+            # a rank that hosts no replica (RowLayout.spread) still joins the fused aggregation
+            if layout is None or not torch.cuda.is_available() or lr is None:
+                return None
+        elif not all(_is_device_node(n) for n in nodes):
             return None
         if not torch.cuda.is_available() or any(n.device.type != "cuda" for n in nodes):
             return None
@@ -129,13 +133,15 @@ class ParameterServer:
         plan = self._fused_plan(n_rows)
         if plan is None:
             return None
-        first = self.hon[0] if self.hon else self.byz[0]
+        first = self.hon[0] if self.hon else (self.byz[0] if self.byz else None)
         return DeviceRound(
             workers, layout, plan,
             lr=first.lr if lr is None else lr,
-            momentum=first.momentum if momentum is None else momentum,
-            weight_decay=first.weight_decay if weight_decay is None else weight_decay,
-            update_byzantines=self.update_byz, device=first.device, group=group,
+            momentum=(first.momentum if first is not None else 0.0) if momentum is None else momentum,
+            weight_decay=(first.weight_decay if first is not None else 0.0) if weight_decay is None else weight_decay,
+            update_byzantines=self.update_byz,
+            device=first.device if first is not None else torch.device("cuda", torch.cuda.current_device()),
+            group=group,
             amp_dtype=amp_dtype, use_cuda_graph=use_cuda_graph, worker_streams=worker_streams,
             virtual_fold=virtual_fold, **self._device_opts)
 

@@ -191,8 +191,25 @@ class RowLayout:
         return cls(n_honest, n_byz_workers, n_virtual, world,
                    [g // per for g in range(n)], [g % per for g in range(n)])
 
+    @classmethod
+    def spread(cls, n_honest: int, n_byz_workers: int, world: int, n_virtual: int = 0) -> "RowLayout":
+        """Like :meth:`block` for worker counts that do not divide the world size: contiguous blocks
+        whose sizes differ by at most one; with fewer workers than ranks the trailing ranks host no
+        replica and only take part in the aggregation of their coordinate shard."""
+        n = n_honest + n_byz_workers
+        base, extra = divmod(n, world)
+        rank_of, slot_of = [], []
+        for r in range(world):
+            for s in range(base + (1 if r < extra else 0)):
+                rank_of.append(r)
+                slot_of.append(s)
+        return cls(n_honest, n_byz_workers, n_virtual, world, rank_of, slot_of)
+
     def local_ids(self, rank: int) -> List[int]:
         return [g for g in range(self.n_workers) if self.rank_of[g] == rank]
+
+    def max_local(self) -> int:
+        return max((self.slot_of[g] + 1 for g in range(self.n_workers)), default=0)
 
 
 # -------------------------------------------------------------------------- engine
@@ -232,8 +249,15 @@ class DeviceRound:
                              f"{len(self.workers)} workers")
         L = len(self.workers)
         self.L = L
-        d = sum(p.numel() for p in self.workers[0].model.parameters())
+        d = sum(p.numel() for p in self.workers[0].model.parameters()) if L else 0
+        if self.world > 1:      # ranks without a replica (RowLayout.spread) learn d from the others
+            t = torch.tensor([d], dtype=torch.int64, device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+            d = int(t.item())
+        if d <= 0:
+            raise ValueError("no rank hosts a model replica")
         self.d = d
+        L_sym = max(L, layout.max_local())      # uniform symmetric layout on every rank
         # shards must be multiples of 4 elements on every rank
         self.d_pad = padded_size(d, 1024)
         self.sm = ops.sm_count(self.device)
@@ -241,7 +265,7 @@ class DeviceRound:
         # --- symmetric region: [grads L*d_pad | agg d_pad | pad words | counter,status,epoch]
         f4 = 4
         self._off_grads = 0
-        self._off_agg = L * self.d_pad * f4
+        self._off_agg = L_sym * self.d_pad * f4
         self._off_pad = self._off_agg + self.d_pad * f4
         self._off_ctl = self._off_pad + 256
         self._off_gslots = self._off_ctl + 256
@@ -249,7 +273,7 @@ class DeviceRound:
         gram_bytes = self.world * self.nt_max * self.nt_max * 8 if isinstance(plan, GramPlan) else 0
         nbytes = self._off_gslots + gram_bytes
         self.sym = SymmetricBuffer(nbytes, self.device, group)
-        self.grads = self.sym.view(torch.float32, L * self.d_pad, self._off_grads).view(L, self.d_pad)
+        self.grads = self.sym.view(torch.float32, L_sym * self.d_pad, self._off_grads).view(L_sym, self.d_pad)
         self.agg = self.sym.view(torch.float32, self.d_pad, self._off_agg)
         self.pad = self.sym.view(torch.int32, 64, self._off_pad)
         self.ctl = self.sym.view(torch.int32, 64, self._off_ctl)  # [0]=counter [1]=status [2]=epoch
@@ -276,7 +300,7 @@ class DeviceRound:
         self._h2d_done = [torch.cuda.Event(), torch.cuda.Event()]
         self._consumed = [torch.cuda.Event(), torch.cuda.Event()]
         self._prefetched = [False, False]
-        worker_streams = max(1, min(int(worker_streams), L))     # never more streams than local replicas
+        worker_streams = max(1, min(int(worker_streams), max(L, 1)))   # never more streams than local replicas
         self._side_streams = [torch.cuda.Stream(self.device) for _ in range(worker_streams - 1)]
         # one weight-gradient stream per worker stream: backward's dgrad chain stays on the worker
         # stream, the wgrad GEMMs of the same replica overlap with it

@@ -35,3 +35,14 @@ def test_p2p_round_two_ranks(agg, topology):
            os.path.join(ROOT, "tests", "multi_gpu", "check_p2p_round.py"), "--agg", agg, "--topology", topology]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert res.returncode == 0 and "MULTI_GPU_P2P_ROUND PASS" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("workers,agg", [(7, "multikrum"), (5, "median")])
+def test_fused_round_uneven_worker_counts(workers, agg):
+    """RowLayout.spread: worker counts that do not divide the world size (4 + 3, 3 + 2 replicas)."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29535",
+           os.path.join(ROOT, "tests", "multi_gpu", "check_fused_round.py"), "--agg", agg, "--workers", str(workers)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert res.returncode == 0 and "MULTI_GPU_FUSED_ROUND PASS" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
