@@ -46,3 +46,15 @@ def test_fused_round_uneven_worker_counts(workers, agg):
            os.path.join(ROOT, "tests", "multi_gpu", "check_fused_round.py"), "--agg", agg, "--workers", str(workers)]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert res.returncode == 0 and "MULTI_GPU_FUSED_ROUND PASS" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
+def test_fused_round_rank_without_replica():
+    """One honest replica + two virtual Little rows on two ranks: rank 1 hosts no replica and only takes
+    part in the aggregation of its coordinate shard."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29536",
+           os.path.join(ROOT, "tests", "multi_gpu", "check_fused_round.py"), "--agg", "median", "--workers", "3",
+           "--attack", "little"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert res.returncode == 0 and "MULTI_GPU_FUSED_ROUND PASS" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
