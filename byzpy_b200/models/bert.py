@@ -11,6 +11,8 @@ from dataclasses import dataclass
 
 import torch
 import torch.nn as nn
+
+from ..ops.fused_layers import ArenaLinear as _Linear   # nn.Linear unless a device worker enables direct gradients
 import torch.nn.functional as F
 
 
@@ -31,11 +33,11 @@ class _Block(nn.Module):
     def __init__(self, c: BertConfig):
         super().__init__()
         self.heads = c.heads
-        self.qkv = nn.Linear(c.hidden, 3 * c.hidden)
-        self.proj = nn.Linear(c.hidden, c.hidden)
+        self.qkv = _Linear(c.hidden, 3 * c.hidden)
+        self.proj = _Linear(c.hidden, c.hidden)
         self.ln1 = nn.LayerNorm(c.hidden, eps=c.eps)
-        self.fc1 = nn.Linear(c.hidden, c.ffn)
-        self.fc2 = nn.Linear(c.ffn, c.hidden)
+        self.fc1 = _Linear(c.hidden, c.ffn)
+        self.fc2 = _Linear(c.ffn, c.hidden)
         self.ln2 = nn.LayerNorm(c.hidden, eps=c.eps)
         self.drop = c.dropout
 
@@ -88,7 +90,7 @@ class BertForMaskedLM(nn.Module):
         super().__init__()
         self.bert = BertEncoder(config)
         c = self.bert.config
-        self.transform = nn.Linear(c.hidden, c.hidden)
+        self.transform = _Linear(c.hidden, c.hidden)
         self.ln = nn.LayerNorm(c.hidden, eps=c.eps)
         self.bias = nn.Parameter(torch.zeros(c.vocab_size))
 

@@ -391,7 +391,8 @@ class _LinearFn(torch.autograd.Function):
 
 
 class ArenaLinear(nn.Linear):
-    """``nn.Linear`` with in-place parameter gradients (2-D inputs; see module docstring)."""
+    """``nn.Linear`` with in-place parameter gradients (leading dimensions are flattened; see module
+    docstring)."""
 
     _direct_grad = False
     _sink: Optional[GradSink] = None
@@ -405,12 +406,14 @@ class ArenaLinear(nn.Linear):
         return s
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        if not (self._direct_grad and x.is_cuda and x.dim() == 2 and torch.is_grad_enabled()
+        if not (self._direct_grad and x.is_cuda and x.dim() >= 2 and torch.is_grad_enabled()
                 and _bf16_autocast_on() and _grad_view_ok(self.weight) and _grad_view_ok(self.bias)):
             return super().forward(x)
         if x.dtype != torch.bfloat16:
             x = x.to(torch.bfloat16)
-        return _LinearFn.apply(x.contiguous(), self.weight, self.bias, self)
+        lead = x.shape[:-1]
+        y = _LinearFn.apply(x.reshape(-1, x.shape[-1]).contiguous(), self.weight, self.bias, self)
+        return y.view(*lead, y.shape[-1])
 
 
 # --------------------------------------------------------------------------- max pooling

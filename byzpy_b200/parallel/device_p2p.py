@@ -48,6 +48,7 @@ class DevicePeer:
         self.arena: Optional[ParamArena] = None
         self.static_x = self.static_y = None
         self.loss_slot: Optional[torch.Tensor] = None
+        self.sink = None        # ops.fused_layers.GradSink once direct gradients are enabled
 
     def stage_batch(self, x: torch.Tensor, y: torch.Tensor, dev: torch.device) -> None:
         if self.static_x is None or self.static_x.shape != x.shape or self.static_x.dtype != x.dtype:
@@ -130,6 +131,13 @@ class DeviceP2PRound:
             if p.model is not None:
                 p.model.to(self.device)
                 p.arena = ParamArena(p.model, flat_params=self.params[i], flat_grads=self.grads[i])
+                if amp_dtype == torch.bfloat16:
+                    # in-place parameter gradients + weight-gradient GEMMs on a side stream
+                    from ..ops.fused_layers import enable_direct_grads
+
+                    if not hasattr(self, "_wgrad_stream"):
+                        self._wgrad_stream = torch.cuda.Stream(self.device)
+                    p.sink = enable_direct_grads(p.model, side_stream=self._wgrad_stream)
         self._pads = [self.sym.peer_ptr(r, self._off_pad) for r in range(self.world)]
         self._has_byz = layout.n_byz > 0
         # Remote vectors are staged ONCE per round into local HBM (one pass over NVLink): with L local
@@ -203,9 +211,13 @@ class DeviceP2PRound:
         x = p.preprocess(p.static_x) if p.preprocess is not None else p.static_x
         ctx = (torch.autocast("cuda", dtype=self.amp_dtype) if self.amp_dtype is not None
                else contextlib.nullcontext())
+        if p.sink is not None:
+            p.sink.refresh_shadows()
         with ctx:
             loss = p.loss_fn(p.model(x), p.static_y)
         loss.backward()
+        if p.sink is not None:
+            p.sink.join()
         p.loss_slot.copy_(loss.detach().float())
         ops.sgd_step(self.grads[i], [self.params[i]], None, lr=self.lr)   # theta <- theta - lr * grad
         self.theta[i].copy_(self.params[i])                                # publish

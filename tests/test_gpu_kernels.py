@@ -587,3 +587,36 @@ def test_resnet_branch_stream_gives_identical_gradients():
         outs.append((eager, arena.grad_vector().clone()))
     assert torch.equal(outs[0][0], outs[1][0])          # eager: branch stream == sequential
     assert torch.equal(outs[1][0], outs[1][1])          # graph replay == eager (same BN buffers)
+
+
+def test_bert_direct_gradients_match_autograd():
+    """ArenaLinear on 3-D activations (BERT blocks): in-place gradients == stock autograd accumulation."""
+    import copy
+
+    from byzpy_b200.models import BertConfig, BertForMaskedLM
+    from byzpy_b200.ops.fused_layers import enable_direct_grads
+    from byzpy_b200.parallel.arena import ParamArena
+
+    torch.manual_seed(7)
+    cfg = BertConfig(vocab_size=512, hidden=64, layers=2, heads=4, ffn=128, max_pos=64)
+    base = BertForMaskedLM(cfg).to(dev())
+    ids = torch.randint(0, 512, (4, 32), device=dev())
+    flats = []
+    for direct in (False, True):
+        m = copy.deepcopy(base)
+        arena = ParamArena(m)
+        sink = enable_direct_grads(m, side_stream=torch.cuda.Stream()) if direct else None
+        for _ in range(2):
+            arena.zero_grad()
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out = m(ids)
+                loss = torch.nn.functional.cross_entropy(out.flatten(0, 1), ids.flatten())
+            loss.backward()
+            if sink is not None:
+                sink.join()
+        torch.cuda.synchronize()
+        flats.append(arena.grad_vector().clone())
+    a, b = flats
+    assert torch.isfinite(b).all()
+    assert torch.nn.functional.cosine_similarity(a, b, dim=0).item() > 0.999
+    torch.testing.assert_close(b, a, rtol=5e-2, atol=5e-3 * a.abs().max().item())
