@@ -25,8 +25,8 @@ import torch
 from .. import ops
 from ..engine.graph.operator import OpContext, Operator
 from ..engine.graph.subtask import SubTask
-from ..engine.storage.shared_store import (SharedTensorHandle, cleanup_tensor, is_handle,
-                                           materialize, open_tensor, register_tensor)
+from ..engine.storage.shared_store import (SharedTensorHandle, cleanup_tensor, materialize, open_tensor,
+                                           register_tensor)
 from ._chunking import select_adaptive_chunk_size
 
 

@@ -2,7 +2,6 @@
 device round this is a per-row scale folded into the aggregation kernel's load."""
 from __future__ import annotations
 
-from typing import Sequence
 
 import torch
 

@@ -9,7 +9,7 @@ Duplicate names, unknown dependencies, unknown outputs and cycles raise ``ValueE
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Any, Dict, Iterable, List, Mapping, Optional, Sequence, Set, Union
+from typing import Any, Dict, Iterable, List, Mapping, Optional, Sequence, Set
 
 from .operator import Operator
 

@@ -11,7 +11,7 @@ Reference analogue: the example node classes (reference examples/ps/nodes.py:64-
 """
 from __future__ import annotations
 
-from typing import Callable, List, Optional, Tuple
+from typing import Callable, Optional, Tuple
 
 import torch
 import torch.nn as nn

@@ -11,7 +11,7 @@ tensors to the aggregator directly (no host shm round trip; aggregators accept h
 from __future__ import annotations
 
 import inspect
-from typing import Any, Mapping, Optional, Sequence, Union
+from typing import Mapping, Optional, Sequence, Union
 
 import torch
 

@@ -25,7 +25,6 @@ from typing import List, Optional
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import _stream, count_launch, require_ext, sm_count
 

@@ -13,7 +13,7 @@ engine/actor/ipc.py:20-56, engine/actor/transports/ucx.py:225-270).
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional
+from typing import List, Optional
 
 import torch
 import torch.distributed as dist
