@@ -53,9 +53,8 @@ constexpr int kRawStages = 6;                 // cp.async ring of raw fp32 tiles
 constexpr int kChunksPerThread = kRows * 8 / kConvThreads;    // 16-byte chunks per thread per tile (4)
 constexpr int kRawStageBytes = kChunksPerThread * kConvThreads * 16;   // 16 KB
 constexpr int kTmemCols = 256;                // D_hh at column 0, D_hl at column 128
-constexpr int kPartialStageBytes = 0;
 constexpr int kSmemBytes = 1024 /*align slack*/ + kOpStages * kOpStageBytes + 256 /*barriers*/ +
-                           kRawStages * kRawStageBytes + kPartialStageBytes;
+                           kRawStages * kRawStageBytes;
 constexpr unsigned long long kWaitBudgetCycles = 4000000000ull;  // ~2 s: trap instead of hanging
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
