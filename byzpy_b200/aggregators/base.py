@@ -67,7 +67,7 @@ def prepare_rows(gradients: Sequence[Any], what: str = "gradients") -> Tuple[Lis
             t = t.to(dev)
         if not t.dtype.is_floating_point:
             t = t.to(torch.float32)
-        rows.append(t.reshape(-1))
+        rows.append(t if t.dim() == 1 else t.reshape(-1))
     d = rows[0].numel()
     for r in rows:
         if r.numel() != d:
@@ -94,6 +94,12 @@ def pool_size_of(context: Optional[OpContext]) -> int:
     return int(meta.get("pool_size") or 0)
 
 
+def pool_in_process(context: Optional[OpContext]) -> bool:
+    """Workers share this address space (thread / gpu pools): subtasks can take views of the rows."""
+    meta = (context.metadata if context is not None else None) or {}
+    return bool(meta.get("pool_in_process"))
+
+
 class _Packed:
     """Rows packaged for subtasks: one host shm matrix, or in-process device rows."""
 
@@ -104,9 +110,9 @@ class _Packed:
         self.rows = rows
 
     @classmethod
-    def pack(cls, rows: List[torch.Tensor]) -> "_Packed":
-        if rows[0].is_cuda:
-            return cls(None, rows)
+    def pack(cls, rows: List[torch.Tensor], in_process: bool = False) -> "_Packed":
+        if rows[0].is_cuda or in_process:
+            return cls(None, rows)      # by reference: no POSIX shm round trip for in-process workers
         mat = torch.stack([r.to(torch.float64 if r.dtype == torch.float64 else torch.float32)
                            for r in rows], dim=0)
         return cls(register_tensor(mat.numpy()), None)
@@ -175,7 +181,7 @@ class CoordinateWiseAggregator(Aggregator):
         n, d = len(rows), rows[0].numel()
         self._validate(n)
         chunk = select_adaptive_chunk_size(d, self.chunk_size, pool_size=pool_size_of(context))
-        packed = _Packed.pack(rows)
+        packed = _Packed.pack(rows, in_process=pool_in_process(context))
         mode, f = self._mode, self._f(n)
 
         def gen():
@@ -308,7 +314,7 @@ class GramAggregator(Aggregator):
         d = all_rows[0].numel()
         chunk = select_adaptive_chunk_size(d, max(int(self.gram_feature_chunk), 1),
                                            pool_size=pool_size_of(context))
-        packed = _Packed.pack(all_rows)
+        packed = _Packed.pack(all_rows, in_process=pool_in_process(context))
         tasks = [SubTask(fn=_gram_chunk, args=(packed, s, e), name=f"{self.name}_gram_{k}")
                  for k, (s, e) in enumerate(feature_chunks(d, chunk))]
         return packed, tasks

@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from ..aggregators.base import _Packed, _hold_packed, _kernel_rows, _release_packed, feature_chunks, finish, pool_size_of, prepare_rows
+from ..aggregators.base import _Packed, _hold_packed, _kernel_rows, _release_packed, feature_chunks, finish, pool_in_process, pool_size_of, prepare_rows
 from ..aggregators._chunking import select_adaptive_chunk_size
 from ..engine.graph.operator import OpContext, Operator
 from ..engine.graph.subtask import SubTask
@@ -95,7 +95,7 @@ class ColumnStatAttack(Attack):
         d = rows[0].numel()
         a, b = self._coeffs(len(rows))
         chunk = select_adaptive_chunk_size(d, self.chunk_size, pool_size=pool_size_of(context))
-        packed = _Packed.pack(rows)
+        packed = _Packed.pack(rows, in_process=pool_in_process(context))
         _hold_packed(self, inputs, packed)
         return [SubTask(fn=_colstat_chunk, args=(packed, s, e, a, b), name=f"{self.name}_chunk_{k}")
                 for k, (s, e) in enumerate(feature_chunks(d, chunk))]

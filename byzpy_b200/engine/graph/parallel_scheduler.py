@@ -140,6 +140,7 @@ class ParallelScheduler:
         meta = dict(self.metadata)
         if self.pool is not None:
             meta.setdefault("pool_size", self.pool.size)
+            meta.setdefault("pool_in_process", bool(getattr(self.pool, "in_process", False)))
             meta.setdefault("worker_affinities", tuple(self.pool.worker_affinities()))
         if self.max_pending_subtasks:
             meta["subtask_semaphore"] = asyncio.Semaphore(self.max_pending_subtasks)

@@ -162,6 +162,13 @@ class ActorPool:
     def size(self) -> int:
         return len(self._workers) if self._started else sum(c.count for c in self.configs)
 
+    @property
+    def in_process(self) -> bool:
+        """True when every worker shares this process's address space (thread / gpu backends):
+        operators may then hand subtasks views of their inputs instead of shared-memory copies."""
+        return all(isinstance(c.backend, str) and c.backend.split(":")[0] in ("thread", "gpu")
+                   for c in self.configs)
+
     def worker_affinities(self) -> Sequence[str]:
         return tuple(self._worker_affinity_caps)
 

@@ -50,6 +50,7 @@ class NodeScheduler:
         meta = dict(self.metadata)
         if self.pool is not None:
             meta.setdefault("pool_size", self.pool.size)
+            meta.setdefault("pool_in_process", bool(getattr(self.pool, "in_process", False)))
             meta.setdefault("worker_affinities", tuple(self.pool.worker_affinities()))
         return meta
 

@@ -98,7 +98,7 @@ def as_rows(x: Rows) -> List[torch.Tensor]:
     for r in x:
         if not isinstance(r, torch.Tensor):
             r = torch.as_tensor(r)
-        rows.append(r.reshape(-1))
+        rows.append(r if r.dim() == 1 else r.reshape(-1))
     if not rows:
         raise ValueError("need at least one row")
     d = rows[0].numel()

@@ -17,7 +17,10 @@ MODE_MEDIAN, MODE_TRMEAN, MODE_MEAMED, MODE_MEAN = 0, 1, 2, 3
 def _stack(rows: Sequence[torch.Tensor], scales=None) -> torch.Tensor:
     base = rows[0]
     dtype = base.dtype if base.dtype.is_floating_point else torch.float32
-    X = torch.stack([r.reshape(-1).to(device=base.device, dtype=dtype) for r in rows], dim=0)
+    if all(r.dim() == 1 and r.dtype == dtype and r.device == base.device for r in rows):
+        X = torch.stack(list(rows), dim=0)          # common case: nothing to normalise
+    else:
+        X = torch.stack([r.reshape(-1).to(device=base.device, dtype=dtype) for r in rows], dim=0)
     if scales is not None and len(scales):
         s = torch.as_tensor(list(scales), dtype=X.dtype, device=X.device)
         X = X * s[:, None]
@@ -41,10 +44,12 @@ def cw_select(rows, mode: int, f: int = 0, *, scales=None,
     n = X.shape[0]
     if mode == MODE_MEAN:
         return X.mean(dim=0)
+    if mode == MODE_MEDIAN:
+        # NaN was canonicalised to +inf above, so a k-th value selection (no full sort) has exactly
+        # the kernel's lower-median semantics; kthvalue beats sort / median on CPU for n = 8..64
+        return X.kthvalue((n - 1) // 2 + 1, dim=0).values
     S, _ = torch.sort(X, dim=0)
     mid = (n - 1) // 2
-    if mode == MODE_MEDIAN:
-        return S[mid].clone()
     if mode == MODE_TRMEAN:
         return S[f:n - f].mean(dim=0)
     if mode == MODE_MEAMED:

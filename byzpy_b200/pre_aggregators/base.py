@@ -17,7 +17,7 @@ import torch
 from .. import ops
 from ..aggregators._chunking import select_adaptive_chunk_size
 from ..aggregators.base import (_Packed, _gram_chunk, _hold_packed, _kernel_rows, _release_packed,
-                                feature_chunks, finish, pool_size_of, prepare_rows)
+                                feature_chunks, finish, pool_in_process, pool_size_of, prepare_rows)
 from ..engine.graph.operator import OpContext, Operator
 from ..engine.graph.subtask import SubTask
 
@@ -82,7 +82,7 @@ class LinearPreAggregator(PreAggregator):
         self._validate(len(rows))
         d = rows[0].numel()
         chunk = select_adaptive_chunk_size(d, self.feature_chunk_size, pool_size=pool_size_of(context))
-        packed = _Packed.pack(_kernel_rows(rows))
+        packed = _Packed.pack(_kernel_rows(rows), in_process=pool_in_process(context))
         _hold_packed(self, inputs, packed)
         return [SubTask(fn=_gram_chunk, args=(packed, s, e), name=f"{self.name}_gram_{k}")
                 for k, (s, e) in enumerate(feature_chunks(d, chunk))]
