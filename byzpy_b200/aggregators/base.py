@@ -254,7 +254,7 @@ class GramAggregator(Aggregator):
     # -- direct path ---------------------------------------------------------------
     def _weights(self, all_rows: List[torch.Tensor], n: int, G: Optional[torch.Tensor] = None) -> torch.Tensor:
         if G is None:
-            G = ops.gram(all_rows, want64=True)
+            G = ops.gram(all_rows, want64=True, diag_only=getattr(self, "gram_diag_only", False))
         if G.is_cuda:
             w = self._solve_device(G, n)
             if w is not None:

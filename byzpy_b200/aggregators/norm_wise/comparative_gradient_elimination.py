@@ -10,6 +10,7 @@ from ..base import GramAggregator
 
 class ComparativeGradientElimination(GramAggregator):
     name = "comparative-gradient-elimination"
+    gram_diag_only = True       # only the row norms are used: the torch fallback skips the n^2 d work
 
     def __init__(self, f: int, *, chunk_size: int = 8192) -> None:
         if f < 0:

@@ -251,10 +251,12 @@ def gram_with_median(rows: Rows, *, scales: Optional[Sequence[float]] = None,
 
 
 def gram(rows: Rows, *, scales: Optional[Sequence[float]] = None, want64: bool = False,
-         impl: str = "auto") -> torch.Tensor:
+         impl: str = "auto", diag_only: bool = False) -> torch.Tensor:
     """``G = (S X)(S X)^T`` as an ``(n, n)`` tensor on the rows' device.
 
     ``impl``: ``"auto"`` | ``"fp32"`` (CUDA-core exact) | ``"umma"`` (tcgen05 3xTF32).
+    ``diag_only``: the caller only uses the squared row norms (the torch fallback then skips the
+    off-diagonal work; the CUDA kernels are bandwidth bound and compute the full matrix anyway).
     """
     rows = as_rows(rows)
     n = len(rows)
@@ -279,7 +281,7 @@ def gram(rows: Rows, *, scales: Optional[Sequence[float]] = None, want64: bool =
                 sm_count(dev), _stream(dev),
             )
         return G64 if want64 else G
-    return ref.gram(rows, scales=scales, want64=want64)
+    return ref.gram(rows, scales=scales, want64=want64, diag_only=diag_only)
 
 
 def sqdist_from_gram(G: torch.Tensor) -> torch.Tensor:

@@ -329,13 +329,12 @@ def nnm_matrix(G: np.ndarray, f: int) -> np.ndarray:
     n = G.shape[0]
     if not (0 <= f < n):
         raise ValueError(f"f must satisfy 0 <= f < n (got n={n}, f={f})")
-    D = sqdist(G)
+    D = sqdist(G).copy()
     k = n - f
+    np.fill_diagonal(D, -1.0)                       # self always belongs to its own neighbourhood
+    idx = np.argsort(D, axis=1, kind="stable")[:, :k]   # ties -> lower index, one vectorised sort
     W = np.zeros((n, n))
-    for i in range(n):
-        row = D[i].copy()
-        row[i] = -1.0
-        W[i, _stable_smallest(row, k)] = 1.0 / k
+    W[np.arange(n)[:, None], idx] = 1.0 / k
     return W
 
 

@@ -70,7 +70,8 @@ class LinearPreAggregator(PreAggregator):
         self._validate(n)
         G = None
         if self.needs_gram:
-            G = ops.gram(_kernel_rows(rows), want64=True).detach().cpu().numpy()
+            G = ops.gram(_kernel_rows(rows), want64=True,
+                         diag_only=getattr(self, "gram_diag_only", False)).detach().cpu().numpy()
         return self._materialise(rows, self.row_map(G, n), like)
 
     # -- subtask path: split-K Gram over feature chunks, then one local materialisation ----
