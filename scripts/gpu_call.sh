@@ -1,3 +1,7 @@
+#!/usr/bin/env bash
+# Round-end check on a GPU box:  gpurun --timeout 1800 -- 'bash scripts/gpu_call.sh'
+# (full GPU test-suite, the smoke entry point, the default headline bench; outputs under gpurun_out/)
 mkdir -p gpurun_out
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29552 benchmarks/training_configs.py --config 4 --steps 10 > gpurun_out/cfg4_n4.log 2>&1; echo "cfg4 n4 rc=$?"; tail -1 gpurun_out/cfg4_n4.log | cut -c1-300
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29551 benchmarks/training_configs.py --config 3 --steps 10 > gpurun_out/cfg3_n4.log 2>&1; echo "cfg3 n4 rc=$?"; tail -1 gpurun_out/cfg3_n4.log | cut -c1-300
+timeout 1200 python -m pytest tests -m gpu -x -q -p no:warnings > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_gpu.log | cut -c1-300
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+timeout 300 python bench.py > gpurun_out/bench_n1.log 2>&1; tail -1 gpurun_out/bench_n1.log | cut -c1-1700
