@@ -1,12 +1,21 @@
-"""Byzantine attack simulators (reference package ``byzpy.attacks``)."""
-from .base import Attack
-from .empire import EmpireAttack
-from .gaussian import GaussianAttack
-from .inf import InfAttack
-from .label_flip import LabelFlipAttack
-from .little import LittleAttack
-from .mimic import MimicAttack
-from .sign_flip import SignFlipAttack
+"""Byzantine attack simulators (counterpart of ``byzpy.attacks``).
 
-__all__ = ["Attack", "EmpireAttack", "LittleAttack", "SignFlipAttack", "LabelFlipAttack",
-           "GaussianAttack", "InfAttack", "MimicAttack"]
+Names are resolved from the table below (name -> defining submodule) so that the package namespace
+and ``__all__`` cannot drift apart."""
+from importlib import import_module as _import_module
+
+_WHERE = {
+    "Attack": "base",
+    "EmpireAttack": "empire",
+    "LittleAttack": "little",
+    "SignFlipAttack": "sign_flip",
+    "LabelFlipAttack": "label_flip",
+    "GaussianAttack": "gaussian",
+    "InfAttack": "inf",
+    "MimicAttack": "mimic",
+}
+
+for _name, _module in _WHERE.items():
+    globals()[_name] = getattr(_import_module(f"{__name__}.{_module}"), _name)
+
+__all__ = list(_WHERE)

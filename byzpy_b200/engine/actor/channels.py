@@ -1,49 +1,63 @@
-"""Actor endpoints and channel handles (reference engine/actor/channels.py:13-65)."""
+"""Addresses and mailbox handles of the actor layer (reference engine/actor/channels.py:13-65).
+
+An ``Endpoint`` names an actor globally: the transport scheme, where the hosting process listens
+(empty for in-host schemes) and an id unique there.  A ``ChannelRef`` is a *local* actor's handle on
+one of its named mailboxes: it posts to the same-named mailbox of any other endpoint and receives
+from its own.  Payloads that crossed a process boundary arrive with tensors parked in shared
+memory; ``recv`` materialises them.
+"""
 from __future__ import annotations
 
-from dataclasses import dataclass
-from typing import Any, Optional
+from typing import Any, NamedTuple, Optional
 
 from .ipc import unwrap_payload
 
 
-@dataclass(frozen=True)
-class Endpoint:
-    """Globally addressable actor location."""
+class Endpoint(NamedTuple):
+    scheme: str      # "thread" | "process" | "gpu" | "tcp" | "ucx"
+    address: str     # "host:port" for tcp / ucx, "" otherwise
+    actor_id: str
 
-    scheme: str    # "thread" | "process" | "gpu" | "tcp" | "ucx"
-    address: str   # "" for in-host schemes, "host:port" for tcp / ucx
-    actor_id: str  # unique within (scheme, address)
+    def is_remote(self) -> bool:
+        return self.scheme in ("tcp", "ucx")
+
+    def __str__(self) -> str:
+        where = f"//{self.address}" if self.address else ""
+        return f"{self.scheme}:{where}/{self.actor_id}"
 
 
 class ChannelRef:
-    """Handle on the mailbox ``name`` of a local actor: ``send(to, payload)`` / ``recv(timeout)``."""
-
     __slots__ = ("_backend", "_local", "_name")
 
     def __init__(self, backend, local_ep: Endpoint, name: str):
-        self._backend = backend
-        self._local = local_ep
-        self._name = name
+        self._backend, self._local, self._name = backend, local_ep, name
 
-    @property
-    def endpoint(self) -> Endpoint:
-        return self._local
+    def __repr__(self) -> str:
+        return f"ChannelRef({self._name!r} @ {self._local})"
 
     @property
     def name(self) -> str:
         return self._name
 
+    @property
+    def endpoint(self) -> Endpoint:
+        """Address peers use to reach this mailbox's owner."""
+        return self._local
+
     async def send(self, to: Endpoint, payload: Any) -> None:
+        """Post ``payload`` to mailbox ``name`` of the actor at ``to``."""
         await self._backend.chan_put(from_ep=self._local, to_ep=to, name=self._name, payload=payload)
 
     async def recv(self, *, timeout: Optional[float] = None) -> Any:
-        raw = await self._backend.chan_get(ep=self._local, name=self._name, timeout=timeout)
-        return unwrap_payload(raw)
+        """Next payload from this actor's own mailbox (``asyncio.TimeoutError`` after ``timeout``)."""
+        item = await self._backend.chan_get(ep=self._local, name=self._name, timeout=timeout)
+        return unwrap_payload(item)
 
 
 async def open_channel(backend, name: str) -> ChannelRef:
-    return ChannelRef(backend, await backend.chan_open(name), name)
+    """Open (or attach to) mailbox ``name`` on the actor hosted by ``backend``."""
+    endpoint = await backend.chan_open(name)
+    return ChannelRef(backend, endpoint, name)
 
 
 __all__ = ["Endpoint", "ChannelRef", "open_channel"]

@@ -25,6 +25,8 @@ def wrap_payload(obj: Any) -> Any:
         return (_SHM_MARK, register_tensor(obj))
     if isinstance(obj, tuple) and len(obj) == 2 and obj[0] == _SHM_MARK:
         return obj
+    if isinstance(obj, tuple) and hasattr(obj, "_fields"):      # namedtuple (e.g. an Endpoint)
+        return type(obj)(*(wrap_payload(x) for x in obj))
     if isinstance(obj, (list, tuple)):
         return type(obj)(wrap_payload(x) for x in obj)
     if isinstance(obj, dict):
@@ -44,6 +46,8 @@ def unwrap_payload(obj: Any) -> Any:
         return _take(obj[1])
     if isinstance(obj, list):
         return [unwrap_payload(x) for x in obj]
+    if isinstance(obj, tuple) and hasattr(obj, "_fields"):
+        return type(obj)(*(unwrap_payload(x) for x in obj))
     if isinstance(obj, tuple):
         return tuple(unwrap_payload(x) for x in obj)
     if isinstance(obj, dict):

@@ -1,9 +1,14 @@
-"""``SubTask``: a unit of work schedulable on a pool worker (CPU thread/process
-actor or a CUDA-stream worker).  Field-compatible with the reference dataclass
-(reference engine/graph/subtask.py:7-18)."""
+"""``SubTask`` -- the unit of work an operator hands to an ``ActorPool``.
+
+Field-compatible with the reference dataclass (reference engine/graph/subtask.py:7-18): ``fn(*args,
+**kwargs)`` plus scheduling hints.  ``affinity`` is a capability tag matched against the pool
+workers (``"gpu"``, ``"cpu"``, or a worker tag ``"worker::<pool-name>-<index>"``); ``max_retries``
+is honoured by ``ActorPool`` on worker failure.  On this framework a subtask that touches CUDA
+tensors runs on a CUDA-stream worker with that stream current.
+"""
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass, field, replace
 from typing import Any, Callable, Mapping, Optional, Sequence
 
 
@@ -13,8 +18,27 @@ class SubTask:
     args: Sequence[Any] = field(default_factory=tuple)
     kwargs: Mapping[str, Any] = field(default_factory=dict)
     name: Optional[str] = None
-    affinity: Optional[str] = None  # capability tag, e.g. "gpu" / "cpu" / "worker::<name>-<idx>"
+    affinity: Optional[str] = None
     max_retries: int = 0
+
+    def __post_init__(self) -> None:
+        if not callable(self.fn):
+            raise TypeError("SubTask.fn must be callable")
+        if self.max_retries < 0:
+            raise ValueError("SubTask.max_retries must be >= 0")
+
+    # conveniences used by the schedulers / tests -------------------------------------------
+    def run(self) -> Any:
+        """Execute in the calling thread (what a worker does with the task)."""
+        return self.fn(*self.args, **dict(self.kwargs))
+
+    def pinned_to(self, affinity: Optional[str]) -> "SubTask":
+        """Copy of this task with a different capability / worker tag."""
+        return replace(self, affinity=affinity)
+
+    @property
+    def label(self) -> str:
+        return self.name or getattr(self.fn, "__name__", "subtask")
 
 
 __all__ = ["SubTask"]

@@ -1,55 +1,65 @@
-"""Directed communication graph over nodes ``0..n-1`` (reference
-engine/peer_to_peer/topology.py:13-38).  ``out[i]`` / ``in_[i]`` are the out-/in-neighbour
-lists.  ``ring(n, k)`` adds both directions for every offset ``1..k`` (so duplicates appear when
-``2k >= n``, as in the reference; routers de-duplicate on broadcast).
+"""Directed communication graph over nodes ``0 .. n-1`` (reference
+engine/peer_to_peer/topology.py:13-38).
+
+``out[i]`` / ``in_[i]`` list node i's out- / in-neighbours in insertion order.  ``ring(n, k)`` links
+every node to its ``k`` successors and ``k`` predecessors, so an edge appears twice once ``2k >= n``
+-- the reference keeps those duplicates and lets the routers de-duplicate; ``in_neighbors`` /
+``out_neighbors`` do that here.
 
 On one NVSwitch box every peer is reachable at full NVLink bandwidth, so a topology costs nothing
 to route: it only selects WHICH peer buffers a rank's aggregation kernel loads.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass
-from typing import Dict, Iterable, List, Tuple
+from typing import Dict, Iterable, List, NamedTuple, Tuple
 
 
-@dataclass(frozen=True)
-class Edge:
+class Edge(NamedTuple):
+    """Directed edge ``u -> v``."""
+
     u: int
-    v: int  # directed u -> v
+    v: int
+
+
+def _unique(seq: List[int]) -> List[int]:
+    return list(dict.fromkeys(seq))
 
 
 class Topology:
     def __init__(self, n_nodes: int, edges: Iterable[Tuple[int, int]]):
-        self.n = int(n_nodes)
-        self.out: Dict[int, List[int]] = {i: [] for i in range(self.n)}
-        self.in_: Dict[int, List[int]] = {i: [] for i in range(self.n)}
-        for u, v in edges:
-            if not (0 <= u < self.n and 0 <= v < self.n):
-                raise ValueError(f"edge ({u}, {v}) outside 0..{self.n - 1}")
-            self.out[u].append(v)
-            self.in_[v].append(u)
+        self.n = n = int(n_nodes)
+        self.out: Dict[int, List[int]] = {i: [] for i in range(n)}
+        self.in_: Dict[int, List[int]] = {i: [] for i in range(n)}
+        for src, dst in edges:
+            if min(src, dst) < 0 or max(src, dst) >= n:
+                raise ValueError(f"edge ({src}, {dst}) outside 0..{n - 1}")
+            self.out[src].append(dst)
+            self.in_[dst].append(src)
 
+    # -- constructors -----------------------------------------------------------------------
     @classmethod
     def complete(cls, n: int) -> "Topology":
-        return cls(n, ((i, j) for i in range(n) for j in range(n) if i != j))
+        """Every ordered pair ``i != j``."""
+        return cls(n, [(i, j) for i in range(n) for j in range(n) if j != i])
 
     @classmethod
     def ring(cls, n: int, k: int = 1) -> "Topology":
-        edges = []
+        """Each node talks to its ``k`` nearest neighbours on both sides of a cycle."""
+        pairs: List[Tuple[int, int]] = []
         for i in range(n):
-            for d in range(1, k + 1):
-                edges.append((i, (i + d) % n))
-                edges.append((i, (i - d) % n))
-        return cls(n, edges)
+            for step in range(1, k + 1):
+                pairs += [(i, (i + step) % n), (i, (i - step) % n)]
+        return cls(n, pairs)
 
+    # -- queries ----------------------------------------------------------------------------
     def edges(self) -> List[Edge]:
-        return [Edge(u, v) for u in range(self.n) for v in self.out[u]]
+        return [Edge(u, v) for u, targets in self.out.items() for v in targets]
 
     def in_neighbors(self, i: int, unique: bool = True) -> List[int]:
-        return list(dict.fromkeys(self.in_[i])) if unique else list(self.in_[i])
+        return _unique(self.in_[i]) if unique else list(self.in_[i])
 
     def out_neighbors(self, i: int, unique: bool = True) -> List[int]:
-        return list(dict.fromkeys(self.out[i])) if unique else list(self.out[i])
+        return _unique(self.out[i]) if unique else list(self.out[i])
 
 
 __all__ = ["Topology", "Edge"]

@@ -1,23 +1,42 @@
-"""In-process transport: ``send`` calls the registered handler directly
-(reference engine/transport/local.py:11-22)."""
+"""Same-process transport for the legacy runners (reference engine/transport/local.py:11-22).
+
+A node registers a delivery callback; ``send`` looks the callback up and invokes it synchronously on
+the caller's thread.  It also keeps per-node delivery counters, handy in tests and demos.
+"""
 from __future__ import annotations
 
-from typing import Any, Callable, Dict
+import collections
+import threading
+from typing import Any, Callable, Dict, Iterable
 
 
 class LocalTransport:
     def __init__(self) -> None:
-        self._handlers: Dict[str, Callable[[Any], None]] = {}
+        self._lock = threading.Lock()
+        self._deliver: Dict[str, Callable[[Any], None]] = {}
+        self.delivered: "collections.Counter[str]" = collections.Counter()
 
     def register(self, node_id: str, handler: Callable[[Any], None]) -> None:
-        self._handlers[node_id] = handler
+        if not callable(handler):
+            raise TypeError("handler must be callable")
+        with self._lock:
+            self._deliver[node_id] = handler
+
+    def unregister(self, node_id: str) -> None:
+        with self._lock:
+            self._deliver.pop(node_id, None)
+
+    def known_nodes(self) -> Iterable[str]:
+        with self._lock:
+            return tuple(self._deliver)
 
     def send(self, to_id: str, payload: Any) -> None:
-        try:
-            handler = self._handlers[to_id]
-        except KeyError:
-            raise KeyError(f"Unknown node_id {to_id}") from None
-        handler(payload)
+        with self._lock:
+            callback = self._deliver.get(to_id)
+        if callback is None:
+            raise KeyError(f"Unknown node_id {to_id}")
+        callback(payload)
+        self.delivered[to_id] += 1
 
 
 __all__ = ["LocalTransport"]
