@@ -1,7 +1,16 @@
-"""Peer-to-peer step functions mixed into user node classes
-(reference engine/node/mixin.py:27-105): ``p2p_half_step`` (fwd/bwd + in-place SGD, returns the
-flat parameters), ``p2p_aggregate_and_set`` (optional pre-aggregation, robust aggregation of own +
-neighbour vectors, write back), and the Byzantine ``p2p_broadcast_vector``."""
+"""Gossip step functions mixed into user node classes (reference engine/node/mixin.py:27-105).
+
+``P2PHonestMixin`` expects the host class to provide ``model``, ``device``, ``criterion``,
+``next_batch()`` and a robust ``p2p_agg`` (optionally a ``p2p_pre`` pre-aggregator):
+
+* ``p2p_half_step(lr)``: forward/backward on the next batch, plain SGD step in place, return the
+  flat parameter vector theta^{t+1/2} that gets broadcast to the out-neighbours;
+* ``p2p_aggregate_and_set(own, received)``: robustly aggregate own + received vectors and load the
+  result into the model.
+
+``P2PByzantineMixin.p2p_broadcast_vector`` is the adversary: it runs the node's ``attack`` on the
+vectors it saw from honest neighbours.
+"""
 from __future__ import annotations
 
 from typing import List, Optional, Tuple
@@ -25,30 +34,33 @@ class P2PHonestMixin:
     p2p_agg: Aggregator
     p2p_pre: Optional[PreAggregator] = None
 
-    def next_batch(self) -> Tuple[Tensor, Tensor]:  # provided by the concrete node
+    def next_batch(self) -> Tuple[Tensor, Tensor]:  # supplied by the concrete node
         raise NotImplementedError
 
+    # -- flat view of the model ---------------------------------------------------------------
     def get_param_vector(self) -> Tensor:
         return flatten_params(self.model).to(self.device)
 
     def set_param_vector(self, vec: Tensor) -> None:
         write_vector_to_params_(self.model, vec.to(self.device))
 
+    # -- the two halves of a gossip round -----------------------------------------------------
     def p2p_half_step(self, lr: float) -> Tensor:
-        x, y = self.next_batch()
+        inputs, targets = self.next_batch()
         self.model.zero_grad(set_to_none=True)
-        self.criterion(self.model(x), y).backward()
+        loss = self.criterion(self.model(inputs), targets)
+        loss.backward()
         with torch.no_grad():
             for p in self.model.parameters():
                 if p.grad is not None:
-                    p.add_(p.grad, alpha=-lr)
+                    p.sub_(p.grad, alpha=lr)
         return self.get_param_vector()
 
     def p2p_aggregate_and_set(self, self_theta_half: Tensor, neighbor_vectors: List[Tensor]) -> None:
-        vecs = [self_theta_half] + list(neighbor_vectors)
+        candidates = [self_theta_half, *neighbor_vectors]
         if self.p2p_pre is not None:
-            vecs = self.p2p_pre.pre_aggregate(vecs)
-        self.set_param_vector(self.p2p_agg.aggregate(vecs))
+            candidates = self.p2p_pre.pre_aggregate(candidates)
+        self.set_param_vector(self.p2p_agg.aggregate(candidates))
 
 
 class P2PByzantineMixin:
@@ -57,11 +69,9 @@ class P2PByzantineMixin:
 
     def p2p_broadcast_vector(self, *, neighbor_vectors: Optional[List[Tensor]] = None,
                              like: Optional[Tensor] = None) -> Tensor:
-        out = torch.as_tensor(self.attack.apply(model=None, x=None, y=None,
-                                                honest_grads=neighbor_vectors, base_grad=None))
-        if like is not None:
-            out = out.to(device=like.device, dtype=like.dtype)
-        return out
+        crafted = self.attack.apply(model=None, x=None, y=None, honest_grads=neighbor_vectors, base_grad=None)
+        crafted = torch.as_tensor(crafted)
+        return crafted if like is None else crafted.to(device=like.device, dtype=like.dtype)
 
 
 __all__ = ["P2PHonestMixin", "P2PByzantineMixin"]

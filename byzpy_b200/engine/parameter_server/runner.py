@@ -1,7 +1,15 @@
-"""Prototype parameter server over ``NodeRunner`` processes (reference
-engine/parameter_server/runner.py:49-90): worker runners compute gradients on ``step``, the
-gradients are sent to a server runner which aggregates its inbox on its next ``step``.
-Default aggregator = mean; Byzantine nodes are not modelled here."""
+"""``ParameterServerRunner``: the reference's process-per-node parameter-server prototype
+(reference engine/parameter_server/runner.py:49-90) on top of :class:`NodeCluster`.
+
+One ``NodeRunner`` process per worker plus one for the server.  A round is driven from the parent:
+
+1. every worker executes one ``step`` -> its state holds a fresh gradient;
+2. the parent forwards each gradient to the server's inbox (directly or through the transport);
+3. the server executes one ``step`` -> it folds its inbox with ``aggregator`` (mean by default).
+
+Byzantine behaviour is not modelled at this level (same as the reference); use
+:class:`~byzpy_b200.engine.parameter_server.ps.ParameterServer` for real training.
+"""
 from __future__ import annotations
 
 from typing import Any, Callable, List, Optional, Sequence
@@ -10,49 +18,63 @@ import torch
 
 from ..node_cluster import NodeCluster
 
+GradFn = Callable[[], torch.Tensor]
+AggFn = Callable[[Sequence[torch.Tensor]], torch.Tensor]
 
-def _worker_fns(grad_fn: Callable[[], torch.Tensor]):
-    def step(state: dict) -> dict:
-        state["grad"] = grad_fn()
+SERVER = "server"
+
+
+def mean_aggregate(grads: Sequence[torch.Tensor]) -> torch.Tensor:
+    total = grads[0].clone()
+    for g in grads[1:]:
+        total += g
+    return total / len(grads)
+
+
+class _Worker:
+    """Picklable (step, on_message) pair of a worker runner."""
+
+    def __init__(self, grad_fn: GradFn):
+        self.grad_fn = grad_fn
+
+    def step(self, state: dict) -> dict:
+        state["grad"] = self.grad_fn()
         return state
 
-    def on_msg(state: dict, msg: Any) -> dict:
-        return state
+    @staticmethod
+    def on_message(state: dict, msg: Any) -> dict:
+        return state                      # workers ignore their inbox in this prototype
 
-    return step, on_msg
 
+class _Server:
+    def __init__(self, aggregate: AggFn):
+        self.aggregate = aggregate
 
-def _server_fns(agg: Callable[[Sequence[torch.Tensor]], torch.Tensor]):
-    def step(state: dict) -> dict:
-        pending = state.get("in_msgs") or []
+    def step(self, state: dict) -> dict:
+        pending = state.get("in_msgs")
         if pending:
-            state["out"] = agg(pending)
+            state["out"] = self.aggregate(pending)
             state["in_msgs"] = []
         return state
 
-    def on_msg(state: dict, msg: Any) -> dict:
+    @staticmethod
+    def on_message(state: dict, msg: Any) -> dict:
         state.setdefault("in_msgs", []).append(msg)
         return state
 
-    return step, on_msg
-
-
-def _mean(grads: Sequence[torch.Tensor]) -> torch.Tensor:
-    return sum(grads) / len(grads)
-
 
 class ParameterServerRunner:
-    def __init__(self, worker_grad_fns: List[Callable[[], torch.Tensor]],
-                 aggregator: Optional[Callable[[Sequence[torch.Tensor]], torch.Tensor]] = None, *,
+    def __init__(self, worker_grad_fns: List[GradFn], aggregator: Optional[AggFn] = None, *,
                  transport=None) -> None:
         self.cluster = NodeCluster(transport=transport)
-        self.server_id = "server"
+        self.server_id = SERVER
+        server = _Server(aggregator or mean_aggregate)
+        self.cluster.add_node(SERVER, server.step, server.on_message, init_state={})
         self.worker_ids: List[str] = []
-        self.cluster.add_node(self.server_id, *_server_fns(aggregator or _mean), init_state={})
-        for idx, fn in enumerate(worker_grad_fns):
-            wid = f"w{idx}"
-            self.cluster.add_node(wid, *_worker_fns(fn), init_state={})
-            self.worker_ids.append(wid)
+        for k, fn in enumerate(worker_grad_fns):
+            worker = _Worker(fn)
+            self.cluster.add_node(f"w{k}", worker.step, worker.on_message, init_state={})
+            self.worker_ids.append(f"w{k}")
 
     def start(self) -> None:
         self.cluster.start_all()
@@ -61,13 +83,14 @@ class ParameterServerRunner:
         self.cluster.stop_all()
 
     def run_round(self) -> torch.Tensor:
+        nodes = self.cluster._nodes
         for wid in self.worker_ids:
-            self.cluster._nodes[wid].step()
+            nodes[wid].step()
         for wid in self.worker_ids:
-            self.cluster.send(self.server_id, self.cluster.state(wid).get("grad"))
-        self.cluster.barrier(0.01)  # lets TCP transports land their messages
-        self.cluster._nodes[self.server_id].step()
-        return self.cluster.state(self.server_id).get("out")
+            self.cluster.send(SERVER, self.cluster.state(wid).get("grad"))
+        self.cluster.barrier(0.01)            # lets asynchronous (TCP) transports land their frames
+        nodes[SERVER].step()
+        return self.cluster.state(SERVER).get("out")
 
 
-__all__ = ["ParameterServerRunner"]
+__all__ = ["ParameterServerRunner", "mean_aggregate"]
