@@ -1,5 +1,11 @@
-"""Label-flip attack: gradient of the loss on flipped labels (``y -> K-1-y`` or an explicit
-mapping), scaled; leaves the model's grads zeroed (reference attacks/label_flip.py:35-91)."""
+"""Label-flip (data-poisoning) attack: the Byzantine node trains on corrupted targets and submits
+the resulting gradient (reference attacks/label_flip.py:35-91).
+
+Targets are remapped either with an explicit ``mapping`` {class -> class} or, given
+``num_classes`` = K, by the involution ``y -> K - 1 - y``.  The gradient is returned flat, in
+``model.parameters()`` order, multiplied by ``scale``; the model's ``.grad`` buffers are left zeroed so
+the node's own optimizer state is not polluted.
+"""
 from __future__ import annotations
 
 from typing import Dict, Optional
@@ -11,45 +17,45 @@ from ..parallel.arena import flatten_grads
 from .base import Attack
 
 
-def _flip(y: torch.Tensor, num_classes: Optional[int], mapping: Optional[Dict[int, int]]) -> torch.Tensor:
-    if mapping is not None:
-        out = y.clone()
-        for src, dst in mapping.items():
-            out[y == int(src)] = int(dst)
-        return out
-    return (int(num_classes) - 1) - y
-
-
 class LabelFlipAttack(Attack):
     name = "label-flip"
     uses_model_batch = True
 
     def __init__(self, *, num_classes: Optional[int] = None, mapping: Optional[Dict[int, int]] = None,
                  loss_fn: Optional[nn.Module] = None, scale: float = 1.0) -> None:
-        if mapping is None and num_classes is None:
+        if num_classes is None and mapping is None:
             raise ValueError("Provide either `mapping` or `num_classes`.")
-        self.num_classes = num_classes
-        self.mapping = mapping
-        self.loss_fn = loss_fn or nn.CrossEntropyLoss(reduction="mean")
+        self.num_classes, self.mapping = num_classes, mapping
         self.scale = float(scale)
+        self.loss_fn = loss_fn if loss_fn is not None else nn.CrossEntropyLoss(reduction="mean")
 
-    def apply(self, *, model=None, x=None, y=None, honest_grads=None, base_grad=None):
-        if model is None or x is None or y is None:
-            raise ValueError("LabelFlipAttack requires model, x, y.")
-        y = y.to(dtype=torch.long, device=x.device)
-        y_bad = _flip(y, self.num_classes, self.mapping)
-        for p in model.parameters():
-            if p.grad is not None:
-                p.grad.zero_()
-        model.train(True)
-        loss = self.loss_fn(model(x), y_bad)
-        loss.backward()
-        vec = self.scale * flatten_grads(model).detach()
+    # -- target corruption ----------------------------------------------------------------------
+    def corrupt(self, y: torch.Tensor) -> torch.Tensor:
+        if self.mapping is None:
+            return (int(self.num_classes) - 1) - y
+        lut = torch.arange(int(max(int(y.max().item()) if y.numel() else 0,
+                                   max(self.mapping), max(self.mapping.values()))) + 1, device=y.device)
+        for src, dst in self.mapping.items():
+            lut[int(src)] = int(dst)
+        return lut[y]
+
+    @staticmethod
+    def _zero_grads(model: nn.Module) -> None:
         for p in model.parameters():
             if p.grad is not None:
                 p.grad.detach_()
                 p.grad.zero_()
-        return vec
+
+    def apply(self, *, model=None, x=None, y=None, honest_grads=None, base_grad=None):
+        if model is None or x is None or y is None:
+            raise ValueError("LabelFlipAttack requires model, x, y.")
+        poisoned = self.corrupt(y.to(device=x.device, dtype=torch.long))
+        self._zero_grads(model)
+        model.train(True)
+        self.loss_fn(model(x), poisoned).backward()
+        out = flatten_grads(model).detach() * self.scale
+        self._zero_grads(model)
+        return out
 
 
 __all__ = ["LabelFlipAttack"]

@@ -1,53 +1,63 @@
-"""Transport backed by one :class:`TcpMailbox` + poller thread per registered node
-(reference engine/transport/tcp.py:15-57)."""
+"""``TcpTransport``: every registered node gets a loopback :class:`TcpMailbox` and a pump thread that
+feeds received payloads to the node's handler (reference engine/transport/tcp.py:15-57).  Messages
+therefore really cross a socket even on one host, which is what the legacy runner tests rely on.
+"""
 from __future__ import annotations
 
 import queue
 import threading
-from typing import Any, Callable, Dict
+from typing import Any, Callable, Dict, NamedTuple
 
 from .tcp_simple import TcpMailbox, send_message
 
 
+class _Route(NamedTuple):
+    mailbox: TcpMailbox
+    pump: threading.Thread
+
+
 class TcpTransport:
-    def __init__(self) -> None:
-        self._mailboxes: Dict[str, TcpMailbox] = {}
-        self._threads: Dict[str, threading.Thread] = {}
-        self._stop = threading.Event()
+    def __init__(self, host: str = "127.0.0.1") -> None:
+        self._host = host
+        self._routes: Dict[str, _Route] = {}
+        self._closing = threading.Event()
+
+    def _pump(self, mailbox: TcpMailbox, handler: Callable[[Any], None]) -> None:
+        while not self._closing.is_set():
+            try:
+                payload = mailbox.recv(timeout=0.1)
+            except queue.Empty:
+                continue
+            try:
+                handler(payload)
+            except Exception:       # a failing handler must not kill delivery to the node
+                pass
 
     def register(self, node_id: str, handler: Callable[[Any], None]) -> None:
-        if node_id in self._mailboxes:
+        if node_id in self._routes:
             raise ValueError(f"Node {node_id} already registered")
-        box = TcpMailbox()
-        self._mailboxes[node_id] = box
+        mailbox = TcpMailbox(self._host)
+        pump = threading.Thread(target=self._pump, args=(mailbox, handler), daemon=True,
+                                name=f"tcp-transport-{node_id}")
+        self._routes[node_id] = _Route(mailbox, pump)
+        pump.start()
 
-        def poll() -> None:
-            while not self._stop.is_set():
-                try:
-                    msg = box.recv(timeout=0.1)
-                except queue.Empty:
-                    continue
-                try:
-                    handler(msg)
-                except Exception:
-                    continue
-
-        t = threading.Thread(target=poll, daemon=True)
-        self._threads[node_id] = t
-        t.start()
+    def address_of(self, node_id: str):
+        route = self._routes[node_id]
+        return route.mailbox.host, route.mailbox.port
 
     def send(self, to_id: str, payload: Any) -> None:
-        box = self._mailboxes.get(to_id)
-        if box is None:
+        route = self._routes.get(to_id)
+        if route is None:
             raise KeyError(f"Unknown node_id {to_id}")
-        send_message(("127.0.0.1", box.port), payload)
+        send_message((self._host, route.mailbox.port), payload)
 
     def close(self) -> None:
-        self._stop.set()
-        for box in self._mailboxes.values():
-            box.close()
-        for t in self._threads.values():
-            t.join(timeout=1.0)
+        self._closing.set()
+        for route in self._routes.values():
+            route.mailbox.close()
+        for route in self._routes.values():
+            route.pump.join(timeout=1.0)
 
 
 __all__ = ["TcpTransport"]
