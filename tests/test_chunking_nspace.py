@@ -115,3 +115,63 @@ def test_selection_validation():
         nspace.cge_weights(G, 4)
     with pytest.raises(ValueError):
         nspace.bucket_matrix(4, 2, [0, 1, 2, 2])
+
+
+# ---------------------------------------------------------------- torch fallback fast paths
+def test_reference_gram_variants_agree():
+    import torch
+
+    from byzpy_b200.ops import reference as ref
+
+    torch.manual_seed(0)
+    rows = [torch.randn(20_000) for _ in range(7)]            # > one 8192-column chunk
+    X = torch.stack(rows).double()
+    exact = X @ X.T
+    G = ref.gram(rows, want64=True)
+    assert G.dtype == torch.float64
+    torch.testing.assert_close(G, exact, rtol=1e-6, atol=1e-3)
+    D = ref.gram(rows, want64=True, diag_only=True)
+    torch.testing.assert_close(torch.diagonal(D), torch.diagonal(exact), rtol=1e-9, atol=1e-9)
+    assert float((D - torch.diag(torch.diagonal(D))).abs().max()) == 0.0
+    Ds = ref.gram(rows, want64=True, diag_only=True, scales=[2.0] * 7)
+    torch.testing.assert_close(torch.diagonal(Ds), 4.0 * torch.diagonal(exact), rtol=1e-9, atol=1e-9)
+
+
+def test_reference_weighted_sum_sparse_dense_and_single_row_paths():
+    import torch
+
+    from byzpy_b200.ops import reference as ref
+
+    torch.manual_seed(1)
+    n, d = 32, 500
+    rows = [torch.randn(d) for _ in range(n)]
+    X = torch.stack(rows)
+    W_sparse = torch.zeros(4, n)                               # bucket means: 4 non-zeros per row
+    for r in range(4):
+        W_sparse[r, 8 * r: 8 * r + 4] = 0.25
+    torch.testing.assert_close(ref.weighted_sum(rows, W_sparse), W_sparse @ X)
+    W_dense = torch.rand(5, n)
+    torch.testing.assert_close(ref.weighted_sum(rows, W_dense), W_dense @ X, rtol=1e-5, atol=1e-5)
+    W_diag = torch.diag(torch.rand(n))
+    torch.testing.assert_close(ref.weighted_sum(rows, W_diag), W_diag @ X, rtol=1e-6, atol=1e-6)
+    w1 = torch.rand(n)
+    w1[3] = 0.0
+    rows_inf = list(rows)
+    rows_inf[3] = torch.full((d,), float("inf"))               # zero weight: never touched
+    out = ref.weighted_sum(rows_inf, w1)
+    assert out.shape == (1, d) and torch.isfinite(out).all()
+    torch.testing.assert_close(out[0], (w1[:, None] * torch.stack(rows)).sum(0) - w1[3] * rows[3], rtol=1e-5,
+                               atol=1e-5)
+
+
+def test_stack_cache_is_invalidated_by_in_place_updates():
+    import torch
+
+    from byzpy_b200.ops import reference as ref
+
+    rows = [torch.ones(9000) * (i + 1) for i in range(3)]
+    ref.gram(rows)                                             # remembers the (3, d) stack
+    rows[0].mul_(10.0)                                         # in-place change bumps the version counter
+    W = torch.eye(3)[:2] + 0.5                                 # dense 2 x 3 -> the stacked path
+    out = ref.weighted_sum(rows, W)
+    torch.testing.assert_close(out, W @ torch.stack(rows))

@@ -470,3 +470,39 @@ def test_public_api_surface_of_the_reference_is_importable():
         m = importlib.import_module(mod)
         for n in names:
             assert hasattr(m, n), f"{mod}.{n} missing"
+
+
+def test_row_layout_spread_handles_uneven_and_idle_ranks():
+    from byzpy_b200.parallel.device_ps import RowLayout
+
+    lay = RowLayout.spread(5, 2, 2)                       # 7 workers on 2 ranks: 4 + 3
+    assert [len(lay.local_ids(r)) for r in range(2)] == [4, 3] and lay.max_local() == 4
+    assert sorted(g for r in range(2) for g in lay.local_ids(r)) == list(range(7))
+    idle = RowLayout.spread(6, 0, 8, n_virtual=2)        # 6 replicas on 8 ranks: two ranks host none
+    assert [len(idle.local_ids(r)) for r in range(8)] == [1] * 6 + [0, 0] and idle.n_virtual == 2
+    even = RowLayout.spread(6, 2, 4)
+    blk = RowLayout.block(6, 2, 4)
+    assert even.rank_of == blk.rank_of and even.slot_of == blk.slot_of
+
+
+def test_actor_ref_attribute_calls_are_named_coroutine_functions():
+    import inspect
+
+    from byzpy_b200.engine.actor.base import ActorRef
+
+    class Echo:
+        async def start(self):
+            pass
+
+        async def close(self):
+            pass
+
+        async def call(self, method, *a, **kw):
+            return (method, a, kw)
+
+    ref = ActorRef(Echo())
+    fn = ref.compute
+    assert fn.__name__ == "compute" and inspect.iscoroutinefunction(fn)
+    assert asyncio.run(fn(1, k=2)) == ("compute", (1,), {"k": 2})
+    with pytest.raises(AttributeError):
+        ref.__deepcopy__
