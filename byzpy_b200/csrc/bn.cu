@@ -103,11 +103,20 @@ __device__ __forceinline__ void reduce_channel(const float* partial, int nblocks
                                                double& q) {
   const int lane = threadIdx.x & 31;
   double ls = 0.0, lq = 0.0;
-#pragma unroll 4
-  for (int b = lane; b < nblocks; b += 32) {
-    const float2 t = __ldg(reinterpret_cast<const float2*>(partial + ((size_t)b * C + c) * 2));
-    ls += (double)t.x;
-    lq += (double)t.y;
+  // batches of 8 loads per lane are issued before the first add (same reason as in the reduce kernel)
+  for (int b0 = lane; b0 < nblocks; b0 += 32 * 8) {
+    float2 t[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int b = b0 + 32 * j;
+      t[j] = (b < nblocks) ? __ldg(reinterpret_cast<const float2*>(partial + ((size_t)b * C + c) * 2))
+                           : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      ls += (double)t[j].x;
+      lq += (double)t[j].y;
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
