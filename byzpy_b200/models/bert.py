@@ -3,7 +3,9 @@
 12 layers, hidden 768, 12 heads, FFN 3072, vocab 30522, learned positions,
 post-LayerNorm -- ~110 M parameters with the MLM head tied to the embeddings.
 Used by the P2P GeometricMedian target config (BASELINE.json config 4); random
-init, synthetic token batches (no network for checkpoints/datasets).
+init, synthetic token batches (no network for checkpoints/datasets).  The reference ships no
+transformer (its only model is the SmallCNN of reference examples/ps/nodes.py:46-61); its P2P step
+functions (reference engine/node/mixin.py:59-80) are model-agnostic, which is all this needs.
 """
 from __future__ import annotations
 

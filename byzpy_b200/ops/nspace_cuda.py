@@ -1,4 +1,6 @@
-"""Device-side n-space solvers (single-CTA CUDA kernels in ``csrc/nspace.cu``).
+"""Device-side n-space solvers (single-CTA CUDA kernels in ``csrc/nspace.cu``): the selection /
+iteration logic of reference krum.py:177-194, geometric_median.py:87-102, center_clipping.py:146-154,
+minimum_diameter_average.py:358-386 and smea.py:63-88, evaluated on the (n, n) Gram matrix.
 
 Each function takes the fp64 Gram matrix ON THE DEVICE and returns the weight /
 coefficient vector ON THE DEVICE without any host synchronisation, so a

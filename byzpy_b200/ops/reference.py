@@ -1,5 +1,7 @@
 """Plain PyTorch implementations of every kernel in :mod:`byzpy_b200.ops`.
 
+The math is that of the reference operators (median.py:102-106, trimmed_mean.py:110-115,
+mean_of_medians.py:71-81, krum.py:41-44, little.py:113-131, ...) expressed on a stacked (n, d) matrix.
 They serve two purposes: (1) the CPU execution path of the operator library
 (tests, CPU actor pools), and (2) the fp32/fp64 oracle that GPU numerics tests
 compare the hand-written kernels against.  Semantics follow the kernels

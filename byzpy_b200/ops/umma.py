@@ -1,4 +1,5 @@
-"""Front-end of the tcgen05 / TMEM / TMA Gram kernel (``csrc/gram_umma.cu``).
+"""Front-end of the tcgen05 / TMEM Gram kernel (``csrc/gram_umma.cu``) -- the ``flat @ flat.T`` of
+reference krum.py:41-44 / nnm.py:87-88 on the 5th-generation tensor cores.
 
 The tensor-core kernel consumes whole tiles of ``32 * (128 / n_pad)`` columns (block-diagonal
 packing, 16-byte aligned 128-byte row segments); the tail (< one tile) goes through the exact fp32

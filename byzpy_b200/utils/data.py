@@ -1,6 +1,8 @@
 """Small data helpers for the examples: MNIST when a local copy exists (no download -- the
 build/CI boxes have no network), otherwise a deterministic synthetic stand-in of the same shape
-whose labels are a fixed random linear function of the pixels (so models can actually learn)."""
+whose labels are a fixed random linear function of the pixels (so models can actually learn).
+Counterpart of the data plumbing inside reference examples/ps/thread/mnist.py:30-54 (strided shards,
+``evaluate``)."""
 from __future__ import annotations
 
 import os
