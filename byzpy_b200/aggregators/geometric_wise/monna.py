@@ -10,6 +10,7 @@ from ..base import GramAggregator
 
 class MoNNA(GramAggregator):
     name = "monna"
+    device_solve = True
 
     def __init__(self, f: int, *, reference_index: int = 0, chunk_size: int = 32) -> None:
         if f < 0:
@@ -30,6 +31,11 @@ class MoNNA(GramAggregator):
 
     def _solve(self, G: np.ndarray, n: int) -> np.ndarray:
         return nspace.monna_weights(G, self.f, self.reference_index)
+
+    def _solve_device(self, G, n):
+        from ...ops import nspace_cuda
+
+        return nspace_cuda.monna_weights(G, n, self.f, self.reference_index)
 
 
 __all__ = ["MoNNA"]

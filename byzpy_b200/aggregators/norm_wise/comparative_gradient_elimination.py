@@ -11,6 +11,7 @@ from ..base import GramAggregator
 class ComparativeGradientElimination(GramAggregator):
     name = "comparative-gradient-elimination"
     gram_diag_only = True       # only the row norms are used: the torch fallback skips the n^2 d work
+    device_solve = True
 
     def __init__(self, f: int, *, chunk_size: int = 8192) -> None:
         if f < 0:
@@ -26,6 +27,11 @@ class ComparativeGradientElimination(GramAggregator):
 
     def _solve(self, G: np.ndarray, n: int) -> np.ndarray:
         return nspace.cge_weights(G, self.f)
+
+    def _solve_device(self, G, n):
+        from ...ops import nspace_cuda
+
+        return nspace_cuda.cge_weights(G, n, self.f)
 
 
 __all__ = ["ComparativeGradientElimination"]

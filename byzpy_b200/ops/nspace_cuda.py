@@ -82,7 +82,36 @@ def centered_clip_coeffs(G: torch.Tensor, n_real: int, a0: np.ndarray, *, c_tau:
     return w
 
 
-__all__ = ["krum_weights", "weiszfeld_coeffs", "centered_clip_coeffs"]
+def _uniform_on_smallest(scores: torch.Tensor, k: int) -> torch.Tensor:
+    """fp32 weights 1/k on the k smallest entries of ``scores`` (ties to the lower index), built from
+    sort + index_fill only: no host synchronisation, so the round stays CUDA-graph capturable."""
+    order = torch.sort(scores, stable=True).indices[:k]
+    w = torch.zeros(scores.shape[0], dtype=torch.float32, device=scores.device)
+    return w.index_fill_(0, order, 1.0 / k)
+
+
+def cge_weights(G: torch.Tensor, n: int, f: int) -> torch.Tensor:
+    """Drop the f largest-norm rows among the first ``n`` (``ops.nspace.cge_weights`` on the device)."""
+    g = torch.diagonal(G)[:n].double().clamp_min(0.0)
+    g = torch.where(torch.isnan(g), torch.full_like(g, float("inf")), g)
+    w = torch.zeros(G.shape[0], dtype=torch.float32, device=G.device)
+    w[:n] = _uniform_on_smallest(g, n - f)            # norms and squared norms order identically
+    return w
+
+
+def monna_weights(G: torch.Tensor, n: int, f: int, reference_index: int) -> torch.Tensor:
+    """n-f rows nearest to the trusted row (``ops.nspace.monna_weights`` on the device)."""
+    G = G.double()
+    g = torch.diagonal(G)[:n]
+    d = g + g[reference_index] - 2.0 * G[reference_index, :n]
+    d = torch.where(torch.isnan(d), torch.full_like(d, float("inf")), d).clamp_min(0.0)
+    d[reference_index] = -1.0                          # the trusted row always comes first
+    w = torch.zeros(G.shape[0], dtype=torch.float32, device=G.device)
+    w[:n] = _uniform_on_smallest(d, n - f)
+    return w
+
+
+__all__ = ["krum_weights", "weiszfeld_coeffs", "centered_clip_coeffs", "cge_weights", "monna_weights"]
 
 
 SUBSET_MAX_N = 24

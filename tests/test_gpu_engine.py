@@ -106,6 +106,48 @@ def test_nspace_cuda_solvers_match_host():
     np.testing.assert_allclose(a.cpu().numpy(), ah, atol=1e-5)
 
 
+def test_selection_solvers_on_device_and_under_graph_capture():
+    """CGE / MoNNA weights come from torch sort + index_fill on the device: they must equal the host
+    solvers and be legal inside a CUDA-graph capture (that is what makes their rounds capturable)."""
+    import numpy as np
+
+    from byzpy_b200.aggregators.geometric_wise import MoNNA
+    from byzpy_b200.aggregators.norm_wise import ComparativeGradientElimination
+    from byzpy_b200.ops import nspace, nspace_cuda
+
+    torch.manual_seed(5)
+    X = torch.randn(12, 700, dtype=torch.float64)
+    X[:3] += 4.0
+    G = X @ X.T
+    Gd = G.to(DEV)
+    np.testing.assert_allclose(nspace_cuda.cge_weights(Gd, 12, 3).cpu().numpy(), nspace.cge_weights(G.numpy(), 3), atol=1e-7)
+    np.testing.assert_allclose(nspace_cuda.monna_weights(Gd, 12, 3, 5).cpu().numpy(),
+                               nspace.monna_weights(G.numpy(), 3, 5), atol=1e-7)
+    static = Gd.clone()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):                       # warm the allocator / sort workspaces off-capture
+        nspace_cuda.cge_weights(static, 12, 3)
+        nspace_cuda.monna_weights(static, 12, 3, 5)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        w1 = nspace_cuda.cge_weights(static, 12, 3)
+        w2 = nspace_cuda.monna_weights(static, 12, 3, 5)
+    Y = torch.randn(12, 700, dtype=torch.float64)
+    Y[8:] *= 5.0
+    G2 = Y @ Y.T
+    static.copy_(G2.to(DEV))
+    graph.replay()
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(w1.cpu().numpy(), nspace.cge_weights(G2.numpy(), 3), atol=1e-7)
+    np.testing.assert_allclose(w2.cpu().numpy(), nspace.monna_weights(G2.numpy(), 3, 5), atol=1e-7)
+    g = grads(9, 3001, seed=8)
+    gd = [x.to(DEV) for x in g]
+    for mk in (lambda: ComparativeGradientElimination(f=2), lambda: MoNNA(f=2, reference_index=1)):
+        torch.testing.assert_close(mk().aggregate(gd).cpu(), mk().aggregate(g), rtol=1e-5, atol=1e-5)
+        assert mk().fused_plan(9).capturable
+
+
 def _fused(ext, rows, scales, mode, f, d, off, ln, rank, aggs, pads, epoch, ctl, upd_p, upd_m,
            stream, grid_limit=0, virt=(0, 0, 0.0, 0.0)):
     ext.fused_ps_cw(rows, scales, mode, f, virt[0], virt[1], virt[2], virt[3], d, off, ln, rank,
@@ -327,7 +369,7 @@ def _run_device_vs_mirror(mk_agg, pre=None, attack="signflip", graph=True, steps
     asyncio.run(ps.shutdown())
 
 
-@pytest.mark.parametrize("name", ["multikrum", "krum", "gm_median", "gm_mean", "cclip", "cge_host", "trmean_little",
+@pytest.mark.parametrize("name", ["multikrum", "krum", "gm_median", "gm_mean", "cclip", "cge", "monna", "trmean_little",
                                   "krum_little", "bucket_krum"])
 def test_device_round_gram_family_and_folds(name):
     from byzpy_b200.pre_aggregators import Bucketing
@@ -338,7 +380,8 @@ def test_device_round_gram_family_and_folds(name):
         "gm_median": dict(mk_agg=lambda: GeometricMedian(tol=1e-7)),
         "gm_mean": dict(mk_agg=lambda: GeometricMedian(init="mean", tol=1e-7)),
         "cclip": dict(mk_agg=lambda: CenteredClipping(c_tau=0.5, M=8)),
-        "cge_host": dict(mk_agg=lambda: ComparativeGradientElimination(f=2)),       # host solve, no graph
+        "cge": dict(mk_agg=lambda: ComparativeGradientElimination(f=2)),            # torch-op device solve
+        "monna": dict(mk_agg=lambda: MoNNA(f=2, reference_index=1)),
         "trmean_little": dict(mk_agg=lambda: CoordinateWiseTrimmedMean(f=2), attack="little"),
         "krum_little": dict(mk_agg=lambda: MultiKrum(f=2, q=3), attack="little"),
         "bucket_krum": dict(mk_agg=lambda: MultiKrum(f=1, q=2), pre=Bucketing(2, perm=[3, 0, 6, 1, 7, 2, 5, 4])),
