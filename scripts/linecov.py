@@ -60,9 +60,9 @@ def main():
     for frac, miss, path, missing in rows:
         print(f"{100 * frac:5.1f}%  miss {miss:4d}  {path}")
     print(f"TOTAL {100 * tot_h / max(1, tot_e):.1f}%  ({tot_h}/{tot_e} statements)")
-    if os.environ.get("LINECOV_DETAIL"):
+    for suffix in filter(None, os.environ.get("LINECOV_DETAIL", "").split(",")):   # e.g. "engine/node/context.py,ops/reference.py"
         for frac, miss, path, missing in rows:
-            if path.endswith(os.environ["LINECOV_DETAIL"]):
+            if path.endswith(suffix):
                 print(path, missing)
     return rc
 
