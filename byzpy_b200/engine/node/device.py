@@ -55,12 +55,17 @@ class DeviceHonestNode(HonestNode):
         loss.backward()
         return flatten_grads(self.model)
 
-    def apply_server_gradient(self, grad_vec):
+    def ensure_optimizer(self) -> torch.optim.Optimizer:
+        """The node's SGD optimizer (created on first use; checkpoint loading needs it to exist)."""
         if self._opt is None:
             self._opt = torch.optim.SGD(self.model.parameters(), lr=self.lr, momentum=self.momentum,
                                         weight_decay=self.weight_decay)
+        return self._opt
+
+    def apply_server_gradient(self, grad_vec):
+        opt = self.ensure_optimizer()
         write_vector_to_grads_(self.model, grad_vec.to(self.device))
-        self._opt.step()
+        opt.step()
 
     def dump_state_dict(self):
         return {k: v.detach().cpu() for k, v in self.model.state_dict().items()}
@@ -124,14 +129,18 @@ class DeviceByzantineNode(ByzantineNode):
             kw["honest_grads"] = list(honest_grads or [])
         return self.attack.apply(**kw)
 
+    def ensure_optimizer(self) -> Optional[torch.optim.Optimizer]:
+        if self.model is not None and self._opt is None:
+            self._opt = torch.optim.SGD(self.model.parameters(), lr=self.lr, momentum=self.momentum,
+                                        weight_decay=self.weight_decay)
+        return self._opt
+
     def apply_server_gradient(self, grad_vec):
         if self.model is None:
             return
-        if self._opt is None:
-            self._opt = torch.optim.SGD(self.model.parameters(), lr=self.lr, momentum=self.momentum,
-                                        weight_decay=self.weight_decay)
+        opt = self.ensure_optimizer()
         write_vector_to_grads_(self.model, grad_vec.to(self.device))
-        self._opt.step()
+        opt.step()
 
 
 class DeviceP2PHonestNode(P2PHonestMixin):

@@ -97,6 +97,8 @@ def load_checkpoint(path: str, ps, *, strict: bool = True, restore_rng: bool = T
         for node, rec in zip(targets, nodes):
             node.model.load_state_dict(rec["state_dict"], strict=strict)
             opt = getattr(node, "_opt", None) or getattr(node, "optimizer", None)
+            if opt is None and rec.get("optimizer") is not None and hasattr(node, "ensure_optimizer"):
+                opt = node.ensure_optimizer()      # lazily-built optimizers: momentum must not be dropped on resume
             if opt is not None and rec.get("optimizer") is not None:
                 opt.load_state_dict(rec["optimizer"])
     if restore_rng:
