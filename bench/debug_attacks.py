@@ -1,7 +1,7 @@
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from byzpy_b200.attacks import EmpireAttack, InfAttack, LittleAttack, MimicAttack, SignFlipAttack
+from byzpy_b200.attacks import EmpireAttack, LittleAttack, MimicAttack, SignFlipAttack
 DEV = torch.device("cuda", 0)
 gen = torch.Generator().manual_seed(6)
 g = [torch.randn(4097, generator=gen) for _ in range(7)]

@@ -411,7 +411,6 @@ def test_device_round_gram_family_and_folds(name):
 @pytest.mark.parametrize("topo", ["complete", "ring"])
 def test_device_p2p_round_matches_mixin_semantics(name, topo):
     from byzpy_b200.engine.node.device import DeviceP2PByzantineNode, DeviceP2PHonestNode
-    from byzpy_b200.engine.node.mixin import P2PByzantineMixin
     from byzpy_b200.engine.peer_to_peer.topology import Topology
     from byzpy_b200.engine.peer_to_peer.train import PeerToPeer
 

@@ -1,5 +1,4 @@
 """GPU numerics: every hand-written kernel vs a plain PyTorch fp32/fp64 reference of the same op."""
-import math
 
 import pytest
 import torch

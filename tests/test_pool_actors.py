@@ -10,8 +10,7 @@ import torch
 from byzpy_b200.aggregators.coordinate_wise import CoordinateWiseMedian, CoordinateWiseTrimmedMean
 from byzpy_b200.aggregators.geometric_wise import GeometricMedian, MultiKrum
 from byzpy_b200.configs.actor import set_actor
-from byzpy_b200.engine.actor.backends.gpu import GPUActorBackend, UCXRemoteActorBackend
-from byzpy_b200.engine.actor.backends.process import ProcessActorBackend
+from byzpy_b200.engine.actor.backends.gpu import UCXRemoteActorBackend
 from byzpy_b200.engine.actor.backends.remote import RemoteActorBackend, RemoteActorServer
 from byzpy_b200.engine.actor.backends.thread import ThreadActorBackend
 from byzpy_b200.engine.actor.base import ActorRef
