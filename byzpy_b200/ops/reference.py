@@ -9,6 +9,7 @@ exactly, including NaN canonicalisation (NaN -> +inf before sorting).
 """
 from __future__ import annotations
 
+import weakref
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -30,11 +31,13 @@ def _stack(rows: Sequence[torch.Tensor], scales=None, *, remember: bool = False,
         key = _stack_key(rows, scales)
         if reuse:
             hit = _STACK_CACHE.pop("entry", None)
-            if hit is not None and hit[0] == key:
+            # ids are only unique among LIVE objects: the weak references prove that the remembered rows are
+            # these very tensors and not freed ones whose ids (and version counters) were reused
+            if hit is not None and hit[0] == key and all(ref() is r for ref, r in zip(hit[2], rows)):
                 return hit[1]
     X = _stack_impl(rows, scales)
     if remember and X.numel() <= (1 << 26):
-        _STACK_CACHE["entry"] = (key, X)
+        _STACK_CACHE["entry"] = (key, X, tuple(weakref.ref(r) for r in rows))
     return X
 
 

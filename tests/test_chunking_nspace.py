@@ -175,3 +175,26 @@ def test_stack_cache_is_invalidated_by_in_place_updates():
     W = torch.eye(3)[:2] + 0.5                                 # dense 2 x 3 -> the stacked path
     out = ref.weighted_sum(rows, W)
     torch.testing.assert_close(out, W @ torch.stack(rows))
+
+
+def test_stack_cache_rejects_rows_whose_ids_were_recycled(monkeypatch):
+    import gc
+
+    import torch
+
+    from byzpy_b200.ops import reference as ref
+
+    old = [torch.ones(9000) * (i + 1) for i in range(3)]
+    ref.gram(old)                                              # remembers the stack of `old`
+    del old
+    gc.collect()
+    # worst case of id reuse: the key of the new rows collides with the remembered one
+    monkeypatch.setattr(ref, "_stack_key", lambda rows, scales: "same-key")
+    ref._STACK_CACHE["entry"] = ("same-key",) + ref._STACK_CACHE["entry"][1:]
+    new = [torch.full((9000,), -1.0) * (i + 1) for i in range(3)]
+    W = torch.eye(3)[:2] + 0.5
+    torch.testing.assert_close(ref.weighted_sum(new, W), W @ torch.stack(new))
+    # ... while the very same live tensors do hit
+    ref.gram(new)
+    cached = ref._STACK_CACHE["entry"][1]
+    assert ref._stack(new, None, reuse=True) is cached and "entry" not in ref._STACK_CACHE
