@@ -206,7 +206,11 @@ class CoordinateWiseAggregator(Aggregator):
 def _hold_packed(op, inputs, packed) -> None:
     """Keep the shm package alive until ``reduce_subtasks`` for THIS invocation (keyed by the
     identity of the per-run inputs mapping, so one operator instance stays re-entrant)."""
-    op.__dict__.setdefault("_live_packages", {})[id(inputs)] = packed
+    live = op.__dict__.setdefault("_live_packages", {})
+    stale = live.pop(id(inputs), None)      # an invocation that died before its reduce step: free its segment
+    if stale is not None and stale is not packed:
+        stale.release()
+    live[id(inputs)] = packed
 
 
 def _release_packed(op, inputs) -> None:
