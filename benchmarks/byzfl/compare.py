@@ -34,6 +34,12 @@ BYZFL = {  # op -> (byzfl class name, ctor kwargs builder)
     "arc": ("ARC", lambda n, f: {"f": f}),
     "nnm": ("NNM", lambda n, f: {"f": f}),
     "bucketing": ("Bucketing", lambda n, f: {"s": max(1, n // 16)}),
+    # attacks (ByzFL: callables over the stacked honest matrix)
+    "gaussian": ("Gaussian", lambda n, f: {"mu": 0.0, "sigma": 1.0}),
+    "inf": ("Inf", lambda n, f: {}),
+    "empire": ("InnerProductManipulation", lambda n, f: {"tau": 1.0}),   # IPM == Empire with scale -tau
+    "little": ("ALittleIsEnough", lambda n, f: {"tau": 1.5}),
+    "mimic": ("Mimic", lambda n, f: {"epsilon": 0}),
 }
 
 

@@ -23,7 +23,8 @@ from byzpy_b200.aggregators.coordinate_wise import CoordinateWiseMedian, Coordin
 from byzpy_b200.aggregators.geometric_wise import (SMEA, GeometricMedian, Krum, MinimumDiameterAveraging,  # noqa: E402
                                                     MoNNA, MultiKrum)
 from byzpy_b200.aggregators.norm_wise import CAF, CenteredClipping, ComparativeGradientElimination  # noqa: E402
-from byzpy_b200.attacks import EmpireAttack, GaussianAttack, LittleAttack  # noqa: E402
+from byzpy_b200.attacks import (EmpireAttack, GaussianAttack, InfAttack, LittleAttack, MimicAttack,  # noqa: E402
+                                SignFlipAttack)
 from byzpy_b200.engine.graph.ops import make_single_operator_graph  # noqa: E402
 from byzpy_b200.engine.graph.pool import ActorPool, ActorPoolConfig  # noqa: E402
 from byzpy_b200.engine.graph.scheduler import NodeScheduler  # noqa: E402
@@ -51,6 +52,9 @@ def make(op: str, n: int, f: int):
         "empire": (lambda: EmpireAttack(), "honest_grads"),
         "little": (lambda: LittleAttack(f=f), "honest_grads"),
         "gaussian": (lambda: GaussianAttack(seed=0), "honest_grads"),
+        "inf": (lambda: InfAttack(), "honest_grads"),
+        "mimic": (lambda: MimicAttack(epsilon=0), "honest_grads"),
+        "sign-flip": (lambda: SignFlipAttack(scale=-1.0), "base_grad"),
     }
     if op not in table:
         raise SystemExit(f"unknown --op {op!r}; choose from {sorted(table)}")
@@ -62,6 +66,8 @@ def direct_call(operator, key, data):
         return operator.aggregate(data)
     if key == "vectors":
         return operator.pre_aggregate(data)
+    if key == "base_grad":
+        return operator.apply(base_grad=data)
     return operator.apply(honest_grads=data)
 
 
@@ -94,6 +100,8 @@ async def main():
     data = [torch.randn(a.grad_dim, generator=g).to(dev) for _ in range(a.num_grads)]
     f = min(a.f, max(0, (a.num_grads - 1) // 2 - 1))
     mk, key = make(a.op, a.num_grads, f)
+    if key == "base_grad":  # SignFlip consumes one vector (the Byzantine node's own gradient)
+        data = data[0]
     sync = (lambda: torch.cuda.synchronize()) if dev.type == "cuda" else (lambda: None)
     out = {"op": a.op, "n": a.num_grads, "d": a.grad_dim, "device": a.device, "backend": a.pool_backend}
     out["direct_ms"] = round(timed(lambda: direct_call(mk(), key, data), a.warmup, a.repeat, sync), 3)
