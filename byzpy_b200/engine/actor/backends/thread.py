@@ -7,7 +7,7 @@ import concurrent.futures
 import inspect
 from typing import Any
 
-from ._local import LocalMailboxBackend
+from ._local import LocalMailboxBackend, intra_op_governor
 
 
 class ThreadActorBackend(LocalMailboxBackend):
@@ -25,7 +25,12 @@ class ThreadActorBackend(LocalMailboxBackend):
 
     async def _in_thread(self, fn, *args, **kwargs):
         loop = asyncio.get_running_loop()
-        return await loop.run_in_executor(self._pool, lambda: fn(*args, **kwargs))
+
+        def governed():
+            with intra_op_governor:
+                return fn(*args, **kwargs)
+
+        return await loop.run_in_executor(self._pool, governed)
 
     async def construct(self, cls_or_factory: Any, *, args: tuple, kwargs: dict) -> None:
         self._obj = await self._in_thread(cls_or_factory, *args, **kwargs)

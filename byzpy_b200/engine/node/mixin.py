@@ -8,6 +8,11 @@
 * ``p2p_aggregate_and_set(own, received)``: robustly aggregate own + received vectors and load the
   result into the model.
 
+A host that binds its model to a :class:`~byzpy_b200.parallel.arena.ParamArena` (attribute ``arena``)
+gets the flat fast path: parameters and gradients are views of two flat buffers, so the SGD half
+step is one fused update, the broadcast vector one copy and loading the aggregate one copy,
+instead of one small op per parameter tensor.
+
 ``P2PByzantineMixin.p2p_broadcast_vector`` is the adversary: it runs the node's ``attack`` on the
 vectors it saw from honest neighbours.
 """
@@ -38,15 +43,34 @@ class P2PHonestMixin:
         raise NotImplementedError
 
     # -- flat view of the model ---------------------------------------------------------------
+    def _bound_arena(self):
+        arena = getattr(self, "arena", None)
+        return arena if arena is not None and arena.module is self.model and arena.check_bound() else None
+
     def get_param_vector(self) -> Tensor:
+        arena = self._bound_arena()
+        if arena is not None:
+            return arena.param_vector().detach().clone()
         return flatten_params(self.model).to(self.device)
 
     def set_param_vector(self, vec: Tensor) -> None:
+        arena = self._bound_arena()
+        if arena is not None:
+            with torch.no_grad():
+                arena.param_vector().copy_(torch.as_tensor(vec).reshape(-1))
+            return
         write_vector_to_params_(self.model, vec.to(self.device))
 
     # -- the two halves of a gossip round -----------------------------------------------------
     def p2p_half_step(self, lr: float) -> Tensor:
         inputs, targets = self.next_batch()
+        arena = self._bound_arena()
+        if arena is not None:
+            arena.zero_grad()
+            self.criterion(self.model(inputs), targets).backward()
+            with torch.no_grad():
+                arena.flat_params.sub_(arena.flat_grads, alpha=lr)
+            return arena.param_vector().detach().clone()
         self.model.zero_grad(set_to_none=True)
         loss = self.criterion(self.model(inputs), targets)
         loss.backward()

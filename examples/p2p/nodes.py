@@ -11,6 +11,7 @@ from byzpy_b200.aggregators.coordinate_wise import CoordinateWiseTrimmedMean
 from byzpy_b200.attacks import EmpireAttack
 from byzpy_b200.engine.node.mixin import P2PByzantineMixin, P2PHonestMixin
 from byzpy_b200.models import SmallCNN
+from byzpy_b200.parallel.arena import ParamArena
 from byzpy_b200.utils.data import batch_source, mnist_like
 
 
@@ -22,6 +23,7 @@ class P2PHonestNode(P2PHonestMixin):
         self.device = torch.device(device)
         torch.manual_seed(0)
         self.model = SmallCNN().to(self.device)
+        self.arena = ParamArena(self.model)     # flat parameter / gradient buffers: the mixin's fast path
         self.criterion = nn.CrossEntropyLoss()
         self.optimizer = torch.optim.SGD(self.model.parameters(), lr=0.05)
         self.p2p_agg = CoordinateWiseTrimmedMean(f=f)

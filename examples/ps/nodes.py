@@ -13,7 +13,8 @@ from byzpy_b200.attacks import EmpireAttack
 from byzpy_b200.engine.graph.pool import ActorPoolConfig
 from byzpy_b200.engine.node.distributed import DistributedByzantineNode, DistributedHonestNode
 from byzpy_b200.models import SmallCNN
-from byzpy_b200.parallel.arena import flatten_grads, write_vector_to_grads_
+from byzpy_b200 import ops
+from byzpy_b200.parallel.arena import ParamArena, flatten_grads, write_vector_to_grads_  # noqa: F401  (re-exported)
 from byzpy_b200.utils.data import batch_source, mnist_like
 
 
@@ -36,7 +37,11 @@ class DistributedPSHonestNode(DistributedHonestNode):
         self.device = torch.device(device)
         torch.manual_seed(0)
         self.model = SmallCNN().to(self.device)
-        self.optimizer = torch.optim.SGD(self.model.parameters(), lr=lr, momentum=momentum)
+        # parameters and gradients live as views of two flat buffers: the flat gradient the server wants is
+        # the buffer itself (no per-parameter cat), the aggregate is applied by one flat SGD(+momentum) update
+        self.arena = ParamArena(self.model)
+        self.lr, self.momentum = float(lr), float(momentum)
+        self.velocity = torch.zeros_like(self.arena.flat_params) if momentum else None
         self.criterion = nn.CrossEntropyLoss()
 
     def next_batch(self):
@@ -44,13 +49,15 @@ class DistributedPSHonestNode(DistributedHonestNode):
         return x.to(self.device), y.to(self.device)
 
     def local_honest_gradient(self, *, x, y):
-        self.model.zero_grad(set_to_none=True)
+        self.arena.zero_grad()
         self.criterion(self.model(x.to(self.device)), y.to(self.device)).backward()
-        return flatten_grads(self.model)
+        return self.arena.grad_vector().clone()
 
     def apply_server_gradient(self, aggregated_grad):
-        write_vector_to_grads_(self.model, aggregated_grad.to(self.device))
-        self.optimizer.step()
+        d = self.arena.d
+        g = aggregated_grad.reshape(-1).to(device=self.device, dtype=torch.float32)
+        ops.sgd_step(g, [self.arena.flat_params[:d]], [self.velocity[:d]] if self.velocity is not None else None,
+                     lr=self.lr, momentum=self.momentum)
 
     def dump_state_dict(self):
         return {k: v.detach().cpu() for k, v in self.model.state_dict().items()}

@@ -1,0 +1,174 @@
+"""Host-side fast paths: the intra-op thread governor of the thread actor backend and the flat
+(ParamArena) paths of the example nodes / P2P mixin.  CPU only."""
+from __future__ import annotations
+
+import asyncio
+import os
+import sys
+import threading
+import time
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from byzpy_b200.engine.actor.backends._local import IntraOpGovernor  # noqa: E402
+from byzpy_b200.engine.actor.backends.thread import ThreadActorBackend  # noqa: E402
+from byzpy_b200.engine.actor.base import ActorRef  # noqa: E402
+from byzpy_b200.parallel.arena import ParamArena, flatten_grads, write_vector_to_grads_  # noqa: E402
+
+
+# ------------------------------------------------------------------------------ governor
+def test_governor_alone_keeps_the_full_thread_count():
+    gov = IntraOpGovernor()
+    gov._base = 8
+    seen = {}
+
+    def body():
+        with gov:
+            seen["alone"] = gov._tls.threads
+    t = threading.Thread(target=body)
+    t.start()
+    t.join()
+    assert seen["alone"] == 8
+    assert gov._active == 0
+
+
+def test_governor_splits_threads_between_concurrent_calls_and_restores(monkeypatch):
+    calls = []
+    monkeypatch.setattr(torch, "set_num_threads", lambda k: calls.append((threading.get_ident(), k)))
+    gov = IntraOpGovernor()
+    gov._base = 8
+    inside = threading.Barrier(4)
+    shares = []
+
+    def body():
+        with gov:
+            inside.wait(timeout=10)          # all four are in flight at the same time
+            shares.append(gov._share())
+            inside.wait(timeout=10)
+    ts = [threading.Thread(target=body) for _ in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert shares == [2, 2, 2, 2]            # 8 // 4 once everybody is in
+    assert gov._active == 0
+    assert calls[-1][1] == 8                 # the last one out restores the process default
+    assert min(k for _, k in calls) >= 1
+
+
+def test_governor_remembers_the_recent_peak_then_decays():
+    gov = IntraOpGovernor()
+    gov._base = 8
+    gov.PEAK_WINDOW = 0.05
+    gov._active = 4
+    assert gov._share() == 2
+    gov._active = 1                          # next round's first arrival: sized by the recent peak
+    assert gov._share() == 2
+    time.sleep(0.08)
+    assert gov._share() == 8                 # concurrency stopped: a lone call gets everything again
+
+
+def test_governor_never_goes_below_one_thread_and_can_be_disabled(monkeypatch):
+    gov = IntraOpGovernor()
+    gov._base = 2
+    gov._active = 9
+    assert gov._share() == 1
+    monkeypatch.setenv("BYZPY_INTRAOP_GOVERNOR", "0")
+    off = IntraOpGovernor()
+    assert not off.enabled
+    with off:
+        assert off._active == 0
+
+
+def test_thread_actor_calls_run_under_the_governor():
+    from byzpy_b200.engine.actor.backends import _local
+
+    class Probe:
+        def active(self):
+            return _local.intra_op_governor._active
+
+    async def main():
+        ref = ActorRef(ThreadActorBackend())
+        async with ref:
+            await ref._backend.construct(Probe, args=(), kwargs={})
+            return await ref.active()
+
+    assert asyncio.run(main()) >= 1
+    assert _local.intra_op_governor._active == 0
+
+
+# ------------------------------------------------------------------------------ flat example nodes
+def test_ps_example_node_matches_torch_sgd_bit_for_bit():
+    from examples.ps.nodes import DistributedPSHonestNode, SmallCNN
+
+    node = DistributedPSHonestNode(indices=list(range(256)), batch_size=16)
+    torch.manual_seed(0)
+    twin = SmallCNN()
+    opt = torch.optim.SGD(twin.parameters(), lr=0.05, momentum=0.9)
+    crit = torch.nn.CrossEntropyLoss()
+    for _ in range(3):
+        x, y = node.next_batch()
+        g = node.local_honest_gradient(x=x, y=y)
+        twin.zero_grad(set_to_none=True)
+        crit(twin(x), y).backward()
+        assert torch.equal(g, flatten_grads(twin))
+        node.apply_server_gradient(0.5 * g)
+        write_vector_to_grads_(twin, 0.5 * g)
+        opt.step()
+        for a, b in zip(node.model.parameters(), twin.parameters()):
+            assert torch.equal(a, b)
+    assert node.arena.check_bound()
+    assert set(node.dump_state_dict()) == set(twin.state_dict())
+
+
+def test_returned_gradient_is_a_snapshot_not_a_view_of_the_arena():
+    from examples.ps.nodes import DistributedPSHonestNode
+
+    node = DistributedPSHonestNode(indices=list(range(64)), batch_size=8)
+    x, y = node.next_batch()
+    g1 = node.local_honest_gradient(x=x, y=y)
+    keep = g1.clone()
+    x, y = node.next_batch()
+    node.local_honest_gradient(x=x, y=y)
+    assert torch.equal(g1, keep)
+
+
+def test_p2p_mixin_flat_path_equals_the_per_parameter_path():
+    from examples.p2p.nodes import P2PHonestNode
+
+    fast = P2PHonestNode(indices=list(range(256)), seed=5)
+    slow = P2PHonestNode(indices=list(range(256)), seed=5)
+    slow.arena = None
+    assert fast._bound_arena() is not None and slow._bound_arena() is None
+    for _ in range(3):
+        va, vb = fast.p2p_half_step(0.05), slow.p2p_half_step(0.05)
+        assert torch.equal(va, vb)
+        nb = [va + 0.01, va - 0.02, va * 1.01]
+        fast.p2p_aggregate_and_set(va, nb)
+        slow.p2p_aggregate_and_set(vb, nb)
+        assert torch.equal(fast.get_param_vector(), slow.get_param_vector())
+    assert fast._bound_arena() is not None
+
+
+def test_p2p_mixin_falls_back_when_the_arena_is_unbound():
+    from examples.p2p.nodes import P2PHonestNode
+
+    node = P2PHonestNode(indices=list(range(64)), seed=1)
+    node.model.zero_grad(set_to_none=True)         # user code dropped the gradient views
+    assert node._bound_arena() is None
+    v = node.p2p_half_step(0.05)
+    assert v.numel() == node.arena.d and torch.isfinite(v).all()
+    node.set_param_vector(torch.zeros_like(v))
+    assert float(node.get_param_vector().abs().max()) == 0.0
+
+
+def test_param_arena_on_cpu_keeps_reference_flat_layout():
+    torch.manual_seed(0)
+    m = torch.nn.Sequential(torch.nn.Linear(5, 3), torch.nn.Linear(3, 2))
+    want = torch.cat([p.detach().reshape(-1) for p in m.parameters()])
+    arena = ParamArena(m)
+    assert torch.equal(arena.param_vector(), want)
+    m(torch.randn(4, 5)).sum().backward()
+    assert torch.equal(arena.grad_vector(), flatten_grads(m))
+    assert arena.check_bound()
