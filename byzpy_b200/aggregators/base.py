@@ -103,11 +103,12 @@ def pool_in_process(context: Optional[OpContext]) -> bool:
 class _Packed:
     """Rows packaged for subtasks: one host shm matrix, or in-process device rows."""
 
-    __slots__ = ("handle", "rows")
+    __slots__ = ("handle", "rows", "aux")
 
     def __init__(self, handle: Optional[SharedTensorHandle], rows: Optional[List[torch.Tensor]]):
         self.handle = handle
         self.rows = rows
+        self.aux = None         # coordinator-side only (never pickled): aux rows computed for this invocation
 
     @classmethod
     def pack(cls, rows: List[torch.Tensor], in_process: bool = False) -> "_Packed":
@@ -133,6 +134,7 @@ class _Packed:
 
     def __setstate__(self, st):
         self.handle, self.rows = st
+        self.aux = None
 
 
 def feature_chunks(d: int, chunk: int) -> Iterable[Tuple[int, int]]:
@@ -220,9 +222,16 @@ def _release_packed(op, inputs) -> None:
 
 
 # --------------------------------------------------------------------------- Gram family
-def _gram_chunk(packed: _Packed, start: int, end: int):
-    rows = packed.slice(start, end)
-    G = ops.gram(_kernel_rows(rows), want64=True)
+def _gram_chunk(packed: _Packed, start: int, end: int, with_median: bool = False):
+    """Split-K partial Gram of one feature chunk.  ``with_median``: the coordinate-wise (lower) median of
+    the chunk is computed here too, appended as the last Gram row, and returned with its offset -- the
+    Weiszfeld / centered-clipping start point is then built by the pool, not by the coordinator."""
+    rows = _kernel_rows(packed.slice(start, end))
+    if with_median:
+        med = ops.cw_median(rows).reshape(-1)
+        G = ops.gram(rows + [med], want64=True)
+        return start, G.detach().cpu().numpy(), med.detach()
+    G = ops.gram(rows, want64=True)
     return G.detach().cpu().numpy()
 
 
@@ -314,12 +323,21 @@ class GramAggregator(Aggregator):
         return GramPlan(solver, self.name, aux=tuple(aux), capturable=bool(self.device_solve) and feasible)
 
     # -- subtask path: split-K partial Grams -------------------------------------------
-    def _gram_subtasks(self, all_rows: List[torch.Tensor], context) -> Tuple[_Packed, List[SubTask]]:
+    def _gram_subtasks(self, krows: List[torch.Tensor], context) -> Tuple[_Packed, List[SubTask]]:
+        """Feature-chunk subtasks over the real rows (+ aux rows).  A median aux row is produced by the
+        subtasks themselves; any other aux rows are computed once here and remembered on the package."""
+        with_median = self._fused_aux() == ("median",)
+        aux = [] if with_median else self._aux_rows(krows)
+        all_rows = krows + aux
         d = all_rows[0].numel()
+        # allow_small_chunks: a gradient no longer than one configured chunk still gets split across the
+        # workers (down to chunk / BYZPY_CHUNK_MAX_SHRINK features) instead of becoming a single subtask
         chunk = select_adaptive_chunk_size(d, max(int(self.gram_feature_chunk), 1),
-                                           pool_size=pool_size_of(context))
+                                           pool_size=pool_size_of(context), allow_small_chunks=True)
         packed = _Packed.pack(all_rows, in_process=pool_in_process(context))
-        tasks = [SubTask(fn=_gram_chunk, args=(packed, s, e), name=f"{self.name}_gram_{k}")
+        packed.aux = aux
+        extra = (True,) if with_median else ()
+        tasks = [SubTask(fn=_gram_chunk, args=(packed, s, e) + extra, name=f"{self.name}_gram_{k}")
                  for k, (s, e) in enumerate(feature_chunks(d, chunk))]
         return packed, tasks
 
@@ -330,17 +348,24 @@ class GramAggregator(Aggregator):
         rows, _ = prepare_rows(grads)
         self._validate(len(rows))
         krows = _kernel_rows(rows)
-        packed, tasks = self._gram_subtasks(krows + self._aux_rows(krows), context)
+        packed, tasks = self._gram_subtasks(krows, context)
         _hold_packed(self, inputs, packed)
         return tasks
 
-    def _finish_from_partials(self, partials, gradients):
+    def _finish_from_partials(self, partials, gradients, aux: Optional[List[torch.Tensor]] = None):
         rows, like = prepare_rows(gradients)
         n = len(rows)
         krows = _kernel_rows(rows)
-        all_rows = krows + self._aux_rows(krows)
+        if partials and isinstance(partials[0], tuple):
+            # (offset, partial Gram incl. the median row, median chunk): stitch the start point together
+            parts = sorted(partials, key=lambda p: p[0])
+            med = torch.cat([torch.as_tensor(p[2]).reshape(-1).to(krows[0].device) for p in parts])
+            aux, mats = [med.to(krows[0].dtype)], [p[1] for p in parts]
+        else:
+            aux, mats = (self._aux_rows(krows) if aux is None else aux), partials
+        all_rows = krows + list(aux)
         G = np.zeros((len(all_rows), len(all_rows)), dtype=np.float64)
-        for p in partials:
+        for p in mats:
             G += np.asarray(p, dtype=np.float64)
         w = self._weights(all_rows, n, torch.from_numpy(G))
         return finish(ops.weighted_sum(all_rows, w.reshape(-1)), like)
@@ -349,7 +374,9 @@ class GramAggregator(Aggregator):
         try:
             if not partials:
                 return self.compute(inputs, context=context)
-            return self._finish_from_partials(partials, inputs[self.input_key])
+            packed = self.__dict__.get("_live_packages", {}).get(id(inputs))
+            return self._finish_from_partials(partials, inputs[self.input_key],
+                                              aux=None if packed is None else packed.aux)
         finally:
             _release_packed(self, inputs)
 
@@ -361,10 +388,10 @@ class GramAggregator(Aggregator):
         rows, _ = prepare_rows(grads)
         self._validate(len(rows))
         krows = _kernel_rows(rows)
-        packed, tasks = self._gram_subtasks(krows + self._aux_rows(krows), context)
+        packed, tasks = self._gram_subtasks(krows, context)
         try:
             partials = await self._run_subtasks(pool, tasks, self.max_subtasks_inflight, context)
-            return self._finish_from_partials(partials, grads)
+            return self._finish_from_partials(partials, grads, aux=packed.aux)
         finally:
             packed.release()
 
