@@ -33,13 +33,18 @@ ROWS = [  # (label, module path under aggregators/pre_aggregators/attacks, class
 ]
 
 
-def run(pkg, mod, cls, kw, data, call, repeat=3):
+def run(pkg, mod, cls, kw, data, call, budget_s=1.0, min_repeat=5):
+    """Median of per-call times: at least ``min_repeat`` calls, more until ``budget_s`` is spent (the short
+    workloads are a few ms, where a mean of three calls on a shared box is mostly noise)."""
     C = getattr(importlib.import_module(f"{pkg}.{mod}"), cls)
     getattr(C(**kw), call)(data)                      # warm-up
-    t0 = time.perf_counter()
-    for _ in range(repeat):
+    times, start = [], time.perf_counter()
+    while len(times) < min_repeat or (time.perf_counter() - start < budget_s and len(times) < 200):
+        t0 = time.perf_counter()
         getattr(C(**kw), call)(data)
-    return (time.perf_counter() - t0) / repeat * 1e3
+        times.append((time.perf_counter() - t0) * 1e3)
+    times.sort()
+    return times[len(times) // 2]
 
 
 def main():
@@ -50,13 +55,13 @@ def main():
         data = [torch.randn(d, generator=g) for _ in range(n)]
         ours = run("byzpy_b200", mod, cls, kw, data, call)
         try:
-            ref = run("byzpy", mod, cls, kw, data, call, repeat=2)
+            ref = run("byzpy", mod, cls, kw, data, call)
         except Exception as exc:  # noqa: BLE001
             ref = float("nan")
             print(f"<!-- reference failed on {label}: {exc!r} -->")
         out.append(dict(workload=label, ref_ms=round(ref, 2), ours_ms=round(ours, 2)))
         print(f"| {label} | {ref:.2f} | {ours:.2f} | {ref / ours:.1f}x |", flush=True)
-    with open(os.path.join(ROOT, "gpurun_out", "baseline_table_cpu.json"), "w") as f:
+    with open(os.path.join(ROOT, "profiles", "baseline_table_cpu.json"), "w") as f:
         json.dump(out, f, indent=1)
 
 

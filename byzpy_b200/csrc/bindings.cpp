@@ -22,6 +22,7 @@
 #include "gram_umma.h"
 #include "nspace.h"
 #include "runtime.h"
+#include "host_select.h"
 
 namespace py = pybind11;
 
@@ -128,6 +129,26 @@ PYBIND11_MODULE(_C, m) {
       py::arg("len"), py::arg("outs"), py::arg("upd_params"), py::arg("upd_moms"), py::arg("lr"),
       py::arg("mu"), py::arg("wd"), py::arg("sm_count"), py::arg("stream"));
 
+  m.def("host_network_size", &bz_host_network_size);
+  m.def(
+      "host_cw_select",
+      [](const std::vector<uint64_t>& rows, const std::vector<float>& scales, int mode, int f, long long d,
+         uint64_t out, int threads) {
+        if (rows.empty()) throw std::invalid_argument("need at least one row");
+        if (!scales.empty() && scales.size() != rows.size())
+          throw std::invalid_argument("scales must match rows");
+        std::vector<const float*> ptrs(rows.size());
+        for (size_t i = 0; i < rows.size(); ++i) ptrs[i] = as_ptr<const float>(rows[i]);
+        int rc;
+        {
+          py::gil_scoped_release nogil;   // pure host compute on caller-owned buffers
+          rc = bz_host_cw_select(ptrs.data(), scales.empty() ? nullptr : scales.data(), (int)rows.size(),
+                                 (int64_t)d, mode, f, as_ptr<float>(out), threads);
+        }
+        if (rc != 0) throw std::invalid_argument("host_cw_select: bad arguments (code " + std::to_string(rc) + ")");
+      },
+      py::arg("rows"), py::arg("scales"), py::arg("mode"), py::arg("f"), py::arg("d"), py::arg("out"),
+      py::arg("threads"));
   m.def("gram_partials_needed", &bz_gram_partials_needed);
   m.def(
       "gram",

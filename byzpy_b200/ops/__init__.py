@@ -175,12 +175,40 @@ def cw_select(
             lr, mu, wd, sm_count(dev), _stream(dev), {"auto": 0, "direct": 1, "staged": 2}[impl],
         )
         return out
-    res = ref.cw_select(rows, mode, f, scales=scales, virtual=virtual)
-    if out is not None:
-        out.copy_(res)
-        res = out
+    res = _host_cw_select(rows, mode, f, scales, virtual, out)
+    if res is None:
+        res = ref.cw_select(rows, mode, f, scales=scales, virtual=virtual)
+        if out is not None:
+            out.copy_(res)
+            res = out
     if update is not None:
         ref.sgd_step(res, **update)
+    return res
+
+
+HOST_MAX_ROWS = 1024
+
+
+def _host_cw_select(rows: List[torch.Tensor], mode: int, f: int, scales, virtual, out) -> Optional[torch.Tensor]:
+    """CPU fp32 rows: the native selection-network kernel (csrc/host_select.cpp) -- tiles of the rows are
+    sorted in cache by packed min/max, nothing is stacked.  Returns None when it does not apply (other
+    dtypes / devices, synthesised rows, extension not built), leaving the PyTorch implementation."""
+    if virtual is not None and virtual[0] > 0:
+        return None
+    n = len(rows)
+    if n > HOST_MAX_ROWS or any(r.device.type != "cpu" or r.dtype != torch.float32 for r in rows):
+        return None
+    if out is not None and (out.device.type != "cpu" or out.dtype != torch.float32 or not out.is_contiguous()
+                            or out.numel() != rows[0].numel()):
+        return None
+    ext = _load_ext()
+    if ext is None or not hasattr(ext, "host_cw_select"):
+        return None
+    rows = _prep(rows)
+    d = rows[0].numel()
+    res = out if out is not None else torch.empty(d, dtype=torch.float32)
+    ext.host_cw_select([r.data_ptr() for r in rows], _scales(scales, n), int(mode), int(f), d,
+                       res.data_ptr(), torch.get_num_threads())
     return res
 
 

@@ -332,10 +332,21 @@ def nnm_matrix(G: np.ndarray, f: int) -> np.ndarray:
     D = sqdist(G).copy()
     k = n - f
     np.fill_diagonal(D, -1.0)                       # self always belongs to its own neighbourhood
-    idx = np.argsort(D, axis=1, kind="stable")[:, :k]   # ties -> lower index, one vectorised sort
-    W = np.zeros((n, n))
-    W[np.arange(n)[:, None], idx] = 1.0 / k
-    return W
+    return _k_smallest_mask(D, k) * (1.0 / k)
+
+
+def _k_smallest_mask(D: np.ndarray, k: int) -> np.ndarray:
+    """0/1 matrix marking, per row, the k smallest entries with ties broken by lower index -- what a stable
+    argsort selects, from one O(n) partition per row instead of a full sort."""
+    n = D.shape[1]
+    if k >= n:
+        return np.ones_like(D)
+    thr = np.partition(D, k - 1, axis=1)[:, k - 1: k]          # the k-th smallest value of each row
+    below = D < thr
+    at = D == thr
+    room = k - below.sum(axis=1, keepdims=True)                 # how many entries equal to it still fit
+    keep_at = at & (np.cumsum(at, axis=1) <= room)
+    return (below | keep_at).astype(np.float64)
 
 
 def bucket_matrix(n: int, bucket_size: int, perm: Sequence[int]) -> np.ndarray:

@@ -62,8 +62,12 @@ def _canon(X: torch.Tensor) -> torch.Tensor:
 
 def cw_select(rows, mode: int, f: int = 0, *, scales=None,
               virtual: Optional[Tuple[int, int, float, float]] = None) -> torch.Tensor:
-    X = _canon(_stack(rows, scales))
+    """NaN counts as +inf (the kernels canonicalise on load).  ATen's sort / k-th value already order NaN as
+    the largest value, so instead of scanning the whole (n, d) matrix for NaN up front the clean path runs
+    first and only its (d,)-sized result is inspected."""
+    X = _stack(rows, scales)
     if virtual is not None and virtual[0] > 0:
+        X = _canon(X)
         nv, nh, a, b = virtual
         H = X[:nh]
         mean = H.mean(dim=0)
@@ -72,14 +76,24 @@ def cw_select(rows, mode: int, f: int = 0, *, scales=None,
         X = torch.cat([X, v.unsqueeze(0).expand(nv, -1)], dim=0)
     n = X.shape[0]
     if mode == MODE_MEAN:
-        return X.mean(dim=0)
+        out = X.mean(dim=0)
+        return _canon(X).mean(dim=0) if bool(torch.isnan(out).any()) else out
     if mode == MODE_MEDIAN:
-        # NaN was canonicalised to +inf above, so a k-th value selection (no full sort) has exactly
-        # the kernel's lower-median semantics; kthvalue beats sort / median on CPU for n = 8..64
+        # a k-th value selection (no full sort) has exactly the kernel's lower-median semantics;
+        # kthvalue beats sort / median on CPU for n = 8..64, median wins from n ~ 32 (measured)
+        k = (n - 1) // 2 + 1
         if n >= 32:
-            return X.median(dim=0).values                    # (measured: median wins from n ~ 32 on CPU)
-        return X.kthvalue((n - 1) // 2 + 1, dim=0).values
-    S, _ = torch.sort(X, dim=0)
+            out = X.median(dim=0).values                     # propagates NaN from anywhere in the column
+            bad = torch.isnan(out)
+            if bool(bad.any()):
+                cols = bad.nonzero().flatten()
+                out[cols] = _canon(X[:, cols]).kthvalue(k, dim=0).values
+            return out
+        out = X.kthvalue(k, dim=0).values                    # NaN ranks last: NaN out == +inf canonically
+        return torch.where(torch.isnan(out), torch.full_like(out, float("inf")), out)
+    S, _ = torch.sort(X, dim=0)                              # NaN ranks last here too
+    if bool(torch.isnan(S[-1]).any()):
+        S = torch.nan_to_num(S, nan=float("inf"), posinf=float("inf"), neginf=float("-inf"))
     mid = (n - 1) // 2
     if mode == MODE_TRMEAN:
         return S[f:n - f].mean(dim=0)
@@ -109,7 +123,12 @@ def gram(rows, *, scales=None, want64: bool = False, diag_only: bool = False) ->
         sc = list(scales) if scales is not None and len(scales) else None
         sq = []
         for i, r in enumerate(rows):
-            v = float(torch.linalg.vector_norm(r.reshape(-1), ord=2, dtype=torch.float64)) ** 2
+            r = r.reshape(-1)
+            # BLAS dot: ~10x faster than an fp64-accumulating norm and 1e-7 accurate; squares that overflow
+            # fp32 (a 1e20-sized attack vector) or non-finite entries take the fp64 norm instead
+            v = float(torch.dot(r, r)) if r.dtype in (torch.float32, torch.float64) else float("inf")
+            if not (v < float("inf")):
+                v = float(torch.linalg.vector_norm(r, ord=2, dtype=torch.float64)) ** 2
             sq.append(v * (float(sc[i]) ** 2 if sc is not None else 1.0))
         base = rows[0]
         out_dtype = torch.float64 if want64 else (base.dtype if base.dtype.is_floating_point else torch.float32)
@@ -161,7 +180,7 @@ def weighted_sum(rows, W: torch.Tensor, *, scales=None) -> torch.Tensor:
         return out
     X = _stack(rows, scales, reuse=True)
     W = W.to(device=X.device, dtype=X.dtype)
-    if bool(torch.isfinite(X).all()):
+    if _all_finite(X):
         if m == n and per_row <= 1 and bool((nzmask == torch.eye(n, dtype=torch.bool, device=W.device)).all()):
             return X * torch.diagonal(W)[:, None]            # diagonal map (Clipping / ARC): n d, not n^2 d
         if per_row * 4 <= n:
@@ -182,6 +201,12 @@ def weighted_sum(rows, W: torch.Tensor, *, scales=None) -> torch.Tensor:
         if nz.numel():
             out[r] = (W[r, nz, None] * X[nz]).sum(dim=0)
     return out
+
+
+def _all_finite(X: torch.Tensor) -> bool:
+    """A finite total proves every entry finite (any inf / NaN entry makes the sum non-finite) in one
+    reduction; a non-finite total may just be overflow, so only then pay for the exact element-wise test."""
+    return bool(torch.isfinite(X.sum())) or bool(torch.isfinite(X).all())
 
 
 def colstat(rows, a: float, b: float, *, scales=None) -> torch.Tensor:

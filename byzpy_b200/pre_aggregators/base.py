@@ -62,6 +62,8 @@ class LinearPreAggregator(PreAggregator):
             diag = np.diagonal(W)
             return [finish(ops.scale_copy(krows[i], float(diag[i])), like) for i in range(len(rows))]
         Y = ops.weighted_sum(krows, Wt)
+        if like.dim() == 1 and Y.dtype == like.dtype and Y.device == like.device:
+            return list(Y.unbind(0))                 # already in the caller's shape / dtype / device
         return [finish(Y[i], like) for i in range(Y.shape[0])]
 
     def pre_aggregate(self, xs: Sequence[Any]) -> List[Any]:
