@@ -129,6 +129,25 @@ PYBIND11_MODULE(_C, m) {
       py::arg("len"), py::arg("outs"), py::arg("upd_params"), py::arg("upd_moms"), py::arg("lr"),
       py::arg("mu"), py::arg("wd"), py::arg("sm_count"), py::arg("stream"));
 
+  m.def(
+      "host_colstat",
+      [](const std::vector<uint64_t>& rows, const std::vector<float>& scales, double a, double b, long long d,
+         uint64_t out, int threads) {
+        if (rows.empty()) throw std::invalid_argument("need at least one row");
+        if (!scales.empty() && scales.size() != rows.size())
+          throw std::invalid_argument("scales must match rows");
+        std::vector<const float*> ptrs(rows.size());
+        for (size_t i = 0; i < rows.size(); ++i) ptrs[i] = as_ptr<const float>(rows[i]);
+        int rc;
+        {
+          py::gil_scoped_release nogil;
+          rc = bz_host_colstat(ptrs.data(), scales.empty() ? nullptr : scales.data(), (int)rows.size(),
+                               (int64_t)d, a, b, as_ptr<float>(out), threads);
+        }
+        if (rc != 0) throw std::invalid_argument("host_colstat: bad arguments");
+      },
+      py::arg("rows"), py::arg("scales"), py::arg("a"), py::arg("b"), py::arg("d"), py::arg("out"),
+      py::arg("threads"));
   m.def("host_network_size", &bz_host_network_size);
   m.def(
       "host_cw_select",

@@ -194,7 +194,65 @@ void mean_range(const float* const* rows, const float* scales, int n, float* out
   }
 }
 
+// a * mean + b * (population std) per coordinate, two in-cache sweeps over a block of columns (Little /
+// Empire attacks: reference attacks/little.py:113-131, empire.py:85-92).  No NaN canonicalisation: the
+// statistic of a column holding NaN / inf is NaN / inf as in the PyTorch formula.
+void colstat_range(const float* const* rows, const float* scales, int n, double a, double b, float* out,
+                   int64_t begin, int64_t end) {
+  constexpr int B = 256;
+  double mean[B], var[B];
+  for (int64_t s = begin; s < end; s += B) {
+    const int w = (int)std::min<int64_t>(B, end - s);
+    for (int j = 0; j < w; ++j) mean[j] = var[j] = 0.0;
+    for (int i = 0; i < n; ++i) {
+      const float* r = rows[i] + s;
+      const float sc = scales ? scales[i] : 1.0f;
+      for (int j = 0; j < w; ++j) mean[j] += (double)(r[j] * sc);
+    }
+    for (int j = 0; j < w; ++j) mean[j] /= (double)n;
+    if (b != 0.0) {
+      for (int i = 0; i < n; ++i) {
+        const float* r = rows[i] + s;
+        const float sc = scales ? scales[i] : 1.0f;
+        for (int j = 0; j < w; ++j) {
+          const double c = (double)(r[j] * sc) - mean[j];
+          var[j] += c * c;
+        }
+      }
+      for (int j = 0; j < w; ++j) out[s + j] = (float)(a * mean[j] + b * std::sqrt(var[j] / (double)n));
+    } else {
+      for (int j = 0; j < w; ++j) out[s + j] = (float)(a * mean[j]);
+    }
+  }
+}
+
+template <typename Fn>
+void split_columns(int64_t d, int threads, Fn&& fn) {
+  const int64_t blocks = (d + 4095) / 4096;
+  const int use = (int)std::max<int64_t>(1, std::min<int64_t>(threads, blocks / 4));
+  if (use <= 1) {
+    fn(0, d);
+    return;
+  }
+  std::vector<std::thread> pool;
+  for (int w = 0; w < use; ++w) {
+    const int64_t b = blocks * w / use * 4096, e = std::min<int64_t>(d, blocks * (w + 1) / use * 4096);
+    pool.emplace_back(fn, b, e);
+  }
+  for (auto& th : pool) th.join();
+}
+
 }  // namespace
+
+int bz_host_colstat(const float* const* rows, const float* scales, int n, int64_t d, double a, double b,
+                    float* out, int threads) {
+  if (n < 1 || d < 0) return 1;
+  if (d == 0) return 0;
+  split_columns(d, std::max(1, threads), [=](int64_t lo, int64_t hi) {
+    colstat_range(rows, scales, n, a, b, out, lo, hi);
+  });
+  return 0;
+}
 
 int bz_host_network_size(int n) {
   if (n < 1 || n > MAX_ROWS) return -1;

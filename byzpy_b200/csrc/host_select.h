@@ -10,3 +10,6 @@ int bz_host_cw_select(const float* const* rows, const float* scales, int n, int6
                       float* out, int threads);
 // number of comparators of the merge-exchange network for n rows (-1 if n is out of range)
 int bz_host_network_size(int n);
+// out[j] = a * mean_i(x_ij) + b * population_std_i(x_ij); returns 0 on success.
+int bz_host_colstat(const float* const* rows, const float* scales, int n, int64_t d, double a, double b,
+                    float* out, int threads);

@@ -390,6 +390,17 @@ def colstat(rows: Rows, a: float, b: float, *, scales=None, out=None) -> torch.T
         ext.colstat([r.data_ptr() for r in rows], _scales(scales, n), float(a), float(b), 0, d,
                     out.data_ptr(), sm_count(dev), _stream(dev))
         return out
+    ext = _load_ext()
+    if (ext is not None and hasattr(ext, "host_colstat")
+            and all(r.device.type == "cpu" and r.dtype == torch.float32 for r in rows)
+            and (out is None or (out.device.type == "cpu" and out.dtype == torch.float32
+                                 and out.is_contiguous() and out.numel() == d))):
+        # native two-sweep column statistic over the row pointers (csrc/host_select.cpp): no (n, d) stack
+        rows = _prep(rows)
+        res = out if out is not None else torch.empty(d, dtype=torch.float32)
+        ext.host_colstat([r.data_ptr() for r in rows], _scales(scales, n), float(a), float(b), d,
+                         res.data_ptr(), torch.get_num_threads())
+        return res
     res = ref.colstat(rows, a, b, scales=scales)
     if out is not None:
         out.copy_(res)

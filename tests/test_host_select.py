@@ -159,3 +159,41 @@ def test_aggregators_on_cpu_match_torch_formulas():
     mm = MeanOfMedians(f=3).aggregate(grads).reshape(-1)
     idx = (X - X.median(dim=0).values).abs().argsort(dim=0)[:7]
     assert torch.allclose(mm, torch.take_along_dim(X, idx, dim=0).mean(dim=0), atol=1e-6)
+
+
+# ------------------------------------------------------------------------------ column statistics
+@pytest.mark.parametrize("n,d", [(1, 5), (3, 257), (10, 70001), (64, 4096)])
+@pytest.mark.parametrize("a,b", [(1.0, 0.0), (-1.0, 0.0), (1.0, 1.5), (0.3, -2.0)])
+def test_host_colstat_matches_the_torch_formula(n, d, a, b):
+    torch.manual_seed(n * 31 + d)
+    rows = [torch.randn(d) for _ in range(n)]
+    torch.testing.assert_close(ops.colstat(rows, a, b), ref.colstat(rows, a, b), rtol=1e-5, atol=1e-6)
+    sc = [1.0 + 0.1 * i for i in range(n)]
+    torch.testing.assert_close(ops.colstat(rows, a, b, scales=sc), ref.colstat(rows, a, b, scales=sc),
+                               rtol=1e-5, atol=1e-6)
+
+
+def test_host_colstat_propagates_non_finite_columns_like_torch_and_honours_out():
+    rows = [torch.tensor([1.0, float("inf"), float("nan"), 4.0]), torch.tensor([2.0, 1.0, 1.0, 4.0])]
+    got, want = ops.colstat(rows, 1.0, 1.0), ref.colstat(rows, 1.0, 1.0)
+    assert torch.equal(torch.isnan(got), torch.isnan(want))
+    assert torch.equal(got[~torch.isnan(got)], want[~torch.isnan(want)])
+    out = torch.empty(4)
+    assert ops.colstat(rows, 2.0, 0.0, out=out) is out and out[0] == 3.0 and out[3] == 8.0
+    dbl = [r.double() for r in rows]
+    assert ops.colstat(dbl, 1.0, 0.0).dtype == torch.float64          # other dtypes stay on the torch path
+
+
+def test_little_and_empire_attacks_on_cpu_use_the_same_numbers():
+    from byzpy_b200.attacks import EmpireAttack, LittleAttack
+
+    torch.manual_seed(9)
+    honest = [torch.randn(3, 100) for _ in range(7)]
+    X = torch.stack([h.reshape(-1) for h in honest])
+    emp = EmpireAttack(scale=-2.0).apply(honest_grads=honest)
+    assert emp.shape == (3, 100)
+    torch.testing.assert_close(emp.reshape(-1), -2.0 * X.mean(dim=0), rtol=1e-5, atol=1e-6)
+    lit = LittleAttack(f=2).apply(honest_grads=honest).reshape(-1)
+    mu, sd = X.mean(dim=0), X.std(dim=0, unbiased=False)
+    z = (lit - mu) / sd
+    assert float(z.std()) < 1e-3                                        # one z for every coordinate
