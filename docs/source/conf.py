@@ -14,3 +14,5 @@ exclude_patterns = ["_build"]
 html_theme = "alabaster"
 autodoc_mock_imports = ["byzpy_b200._C"]
 autodoc_default_options = {"members": True, "undoc-members": False, "show-inheritance": True}
+html_static_path = ["_static"]
+html_css_files = ["custom.css"]
