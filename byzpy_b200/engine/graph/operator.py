@@ -147,6 +147,11 @@ class Operator:
                 context)
             if partials:
                 return await _resolve(self.reduce_subtasks(partials, inputs, context=context))
+        if (context.metadata or {}).get("offload_host_compute"):
+            # ParallelScheduler, several nodes in flight: a synchronous compute() would hold the event
+            # loop and serialise the wave, so it runs on a worker thread (torch / the native kernels
+            # release the GIL), sharing the cores with its siblings through the intra-op governor
+            return await _resolve(await asyncio.to_thread(_governed_compute, self, inputs, context))
         return await _resolve(self.compute(inputs, context=context))
 
     async def _run_subtasks(self, pool: "ActorPool", subtasks: Iterable[SubTask],
@@ -156,6 +161,13 @@ class Operator:
         if hints:
             subtasks = _with_affinities(subtasks, tuple(hints))
         return await run_subtasks_windowed(pool, subtasks, limit, meta.get("subtask_semaphore"))
+
+
+def _governed_compute(op: "Operator", inputs: Mapping[str, Any], context: OpContext) -> Any:
+    from ..actor.backends._local import intra_op_governor
+
+    with intra_op_governor:
+        return op.compute(inputs, context=context)
 
 
 class MessageTriggerOp(Operator):

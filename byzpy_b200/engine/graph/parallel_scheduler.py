@@ -97,9 +97,13 @@ class ParallelScheduler:
         return bound
 
     async def _execute_node(self, node_name: str, cache: Dict[str, Any], base_metadata: Dict[str, Any],
-                            events: Optional[Dict[str, Any]] = None) -> Tuple[str, Any]:
+                            events: Optional[Dict[str, Any]] = None, concurrent: bool = False) -> Tuple[str, Any]:
         node = self._node_map[node_name]
         inputs = self._resolve_inputs(node, cache)
+        if concurrent and base_metadata.get("offload_host_compute", True):
+            base_metadata = {**base_metadata, "offload_host_compute": True}
+        elif base_metadata.get("offload_host_compute"):
+            base_metadata = {**base_metadata, "offload_host_compute": False}
         ctx = OpContext(node_name=node.name, metadata=base_metadata)
         use_streams = events is not None and base_metadata.get("cuda_streams", True) and self.pool is None
         tensors: List[Any] = []
@@ -123,6 +127,8 @@ class ParallelScheduler:
                 stream.wait_event(ev)
         for t in tensors:
             t.record_stream(stream)
+        if ctx.metadata.get("offload_host_compute"):     # the stream context is thread-local: stay on this thread
+            ctx = OpContext(node_name=node.name, metadata={**ctx.metadata, "offload_host_compute": False})
         with torch.cuda.stream(stream):
             result = await node.op.run(inputs, context=ctx, pool=self.pool)
             done = torch.cuda.Event()
@@ -148,11 +154,11 @@ class ParallelScheduler:
                 if self.max_concurrent_nodes and self.max_concurrent_nodes > 0 else None)
         events: Dict[str, Any] = {}
 
-        async def guarded(name: str):
+        async def guarded(name: str, concurrent: bool = False):
             if gate is None:
-                return await self._execute_node(name, cache, meta, events)
+                return await self._execute_node(name, cache, meta, events, concurrent)
             async with gate:
-                return await self._execute_node(name, cache, meta, events)
+                return await self._execute_node(name, cache, meta, events, concurrent)
 
         running: set = set()
         ready = [name for name in self._node_map if remaining[name] == 0]
@@ -163,8 +169,10 @@ class ParallelScheduler:
                     name, value = await guarded(ready.pop())
                     finished = [(name, value)]
                 else:
+                    # more than one node in flight: host-side compute() calls go to worker threads
+                    together = len(ready) + len(running) > 1
                     for name in ready:
-                        running.add(asyncio.ensure_future(guarded(name)))
+                        running.add(asyncio.ensure_future(guarded(name, together)))
                     ready = []
                     done, running = await asyncio.wait(running, return_when=asyncio.FIRST_COMPLETED)
                     finished = [t.result() for t in done]

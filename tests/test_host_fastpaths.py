@@ -172,3 +172,84 @@ def test_param_arena_on_cpu_keeps_reference_flat_layout():
     m(torch.randn(4, 5)).sum().backward()
     assert torch.equal(arena.grad_vector(), flatten_grads(m))
     assert arena.check_bound()
+
+
+# ------------------------------------------------------------------------------ ParallelScheduler offload
+def _branch_graph(op_factory, k=3):
+    from byzpy_b200.engine.graph.graph import ComputationGraph, GraphNode, graph_input
+
+    nodes = [GraphNode(f"b{i}", op_factory(i), {"x": graph_input("x")}) for i in range(k)]
+    return ComputationGraph(nodes, outputs=[f"b{i}" for i in range(k)])
+
+
+def test_parallel_scheduler_runs_concurrent_host_computes_on_worker_threads():
+    from byzpy_b200.engine.graph.ops import CallableOp
+    from byzpy_b200.engine.graph.parallel_scheduler import ParallelScheduler
+
+    main_thread = threading.get_ident()
+    seen = {}
+
+    def make(i):
+        def work(x):
+            seen[i] = (threading.get_ident(), time.perf_counter())
+            time.sleep(0.15)                        # a blocking, GIL-releasing compute
+            return x + i
+        return CallableOp(work, input_mapping={"x": "x"})
+
+    t0 = time.perf_counter()
+    out = asyncio.run(ParallelScheduler(_branch_graph(make)).run({"x": 1}))
+    elapsed = time.perf_counter() - t0
+    assert out == {"b0": 1, "b1": 2, "b2": 3}
+    assert all(tid != main_thread for tid, _ in seen.values())      # none of them held the event loop
+    assert elapsed < 0.40                                            # 3 x 0.15 s overlapped
+
+
+def test_parallel_scheduler_offload_can_be_disabled_and_a_lone_node_stays_inline():
+    from byzpy_b200.engine.graph.graph import ComputationGraph, GraphNode, graph_input
+    from byzpy_b200.engine.graph.ops import CallableOp
+    from byzpy_b200.engine.graph.parallel_scheduler import ParallelScheduler
+
+    main_thread = threading.get_ident()
+    tids = []
+
+    def make(i):
+        return CallableOp(lambda x: tids.append(threading.get_ident()) or x, input_mapping={"x": "x"})
+
+    asyncio.run(ParallelScheduler(_branch_graph(make), metadata={"offload_host_compute": False}).run({"x": 0}))
+    assert tids and all(t == main_thread for t in tids)
+    tids.clear()
+    lone = ComputationGraph([GraphNode("only", make(0), {"x": graph_input("x")})])
+    asyncio.run(ParallelScheduler(lone).run({"x": 0}))
+    assert tids == [main_thread]
+
+
+def test_parallel_scheduler_offload_propagates_errors_and_async_results():
+    from byzpy_b200.engine.graph.ops import CallableOp
+    from byzpy_b200.engine.graph.parallel_scheduler import ParallelScheduler
+
+    def make(i):
+        if i == 1:
+            def boom(x):
+                raise ValueError("branch 1 failed")
+            return CallableOp(boom, input_mapping={"x": "x"})
+
+        async def later(x):
+            return x * 10
+
+        return CallableOp(lambda x: later(x), input_mapping={"x": "x"})      # compute() returns an awaitable
+
+    with pytest.raises(ValueError, match="branch 1 failed"):
+        asyncio.run(ParallelScheduler(_branch_graph(make)).run({"x": 2}))
+    ok = asyncio.run(ParallelScheduler(_branch_graph(lambda i: make(0), k=2)).run({"x": 2}))
+    assert ok == {"b0": 20, "b1": 20}
+
+
+def test_node_scheduler_never_offloads():
+    from byzpy_b200.engine.graph.ops import CallableOp
+    from byzpy_b200.engine.graph.scheduler import NodeScheduler
+
+    main_thread = threading.get_ident()
+    tids = []
+    make = lambda i: CallableOp(lambda x: tids.append(threading.get_ident()) or x, input_mapping={"x": "x"})  # noqa: E731
+    asyncio.run(NodeScheduler(_branch_graph(make)).run({"x": 0}))
+    assert tids == [main_thread] * 3
