@@ -100,15 +100,16 @@ class ParallelScheduler:
                             events: Optional[Dict[str, Any]] = None, concurrent: bool = False) -> Tuple[str, Any]:
         node = self._node_map[node_name]
         inputs = self._resolve_inputs(node, cache)
-        if concurrent and base_metadata.get("offload_host_compute", True):
-            base_metadata = {**base_metadata, "offload_host_compute": True}
-        elif base_metadata.get("offload_host_compute"):
-            base_metadata = {**base_metadata, "offload_host_compute": False}
+        device_inputs: List[Any] = []
+        _cuda_tensors(inputs, device_inputs)
+        # worker-thread offload is for host data only: the current CUDA stream is thread-local, so device
+        # work stays on this thread (and goes onto a side stream below when no pool is attached)
+        offload = concurrent and not device_inputs and bool(base_metadata.get("offload_host_compute", True))
+        if offload != bool(base_metadata.get("offload_host_compute")):
+            base_metadata = {**base_metadata, "offload_host_compute": offload}
         ctx = OpContext(node_name=node.name, metadata=base_metadata)
         use_streams = events is not None and base_metadata.get("cuda_streams", True) and self.pool is None
-        tensors: List[Any] = []
-        if use_streams:
-            _cuda_tensors(inputs, tensors)
+        tensors: List[Any] = device_inputs if use_streams else []
         tracer = base_metadata.get("tracer")
         if not tensors:
             if tracer is None:
@@ -127,8 +128,6 @@ class ParallelScheduler:
                 stream.wait_event(ev)
         for t in tensors:
             t.record_stream(stream)
-        if ctx.metadata.get("offload_host_compute"):     # the stream context is thread-local: stay on this thread
-            ctx = OpContext(node_name=node.name, metadata={**ctx.metadata, "offload_host_compute": False})
         with torch.cuda.stream(stream):
             result = await node.op.run(inputs, context=ctx, pool=self.pool)
             done = torch.cuda.Event()
