@@ -12,14 +12,20 @@ import numpy as np
 import torch
 
 from .. import ops
-from ..aggregators.base import finish, prepare_rows
+from ..aggregators._chunking import select_adaptive_chunk_size
+from ..aggregators.base import finish, pool_size_of, prepare_rows
+from ..engine.graph.subtask import SubTask
 from .base import Attack
+
+
+def _span(start: int, end: int):
+    return start, end
 
 
 class GaussianAttack(Attack):
     name = "gaussian"
     uses_honest_grads = True
-    supports_subtasks = False
+    supports_subtasks = True
 
     def __init__(self, mu: float = 0.0, sigma: float = 1.0, *, seed: Optional[int] = None,
                  chunk_size: int = 8192) -> None:
@@ -42,6 +48,29 @@ class GaussianAttack(Attack):
             return finish(out, like)
         sample = np.random.default_rng(self.seed).normal(loc=self.mu, scale=self.sigma, size=d)
         return finish(torch.from_numpy(sample), like)
+
+    # -- subtask path --------------------------------------------------------------------------------
+    # A seeded PCG64 normal stream cannot be entered in the middle (the ziggurat sampler draws a variable
+    # number of words per sample), and "same seed -> same vector" is the contract, so the chunk subtasks
+    # only lay out the output spans (as the reference's no-op chunks do, gaussian.py:33-35, 100-137) and
+    # the vector is drawn once in the reduce step.
+    def create_subtasks(self, inputs, *, context):
+        grads = inputs.get("honest_grads")
+        if not grads:
+            raise ValueError("GaussianAttack requires honest_grads.")
+        rows, _ = prepare_rows([grads[0]], "honest_grads")
+        d = rows[0].numel()
+        chunk = select_adaptive_chunk_size(d, self.chunk_size, pool_size=pool_size_of(context))
+        return [SubTask(fn=_span, args=(s, min(d, s + chunk)), name=f"gaussian_chunk_{k}")
+                for k, s in enumerate(range(0, d, chunk))]
+
+    def reduce_subtasks(self, partials, inputs, *, context):
+        if partials:
+            d = prepare_rows([inputs["honest_grads"][0]], "honest_grads")[0][0].numel()
+            spans = sorted(partials)
+            if spans[0][0] != 0 or spans[-1][1] != d or any(a[1] != b[0] for a, b in zip(spans, spans[1:])):
+                raise ValueError("gaussian chunk spans do not tile the gradient")
+        return self.compute(inputs, context=context)
 
 
 __all__ = ["GaussianAttack"]

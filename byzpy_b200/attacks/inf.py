@@ -4,14 +4,22 @@ from __future__ import annotations
 import torch
 
 from .. import ops
-from ..aggregators.base import finish, prepare_rows
+from ..aggregators._chunking import select_adaptive_chunk_size
+from ..aggregators.base import finish, pool_size_of, prepare_rows
+from ..engine.graph.subtask import SubTask
 from .base import Attack
+
+
+def _inf_chunk(start: int, end: int, device: str):
+    out = torch.empty(end - start, dtype=torch.float32, device=device)
+    ops.fill_(out, float("inf"))
+    return start, out
 
 
 class InfAttack(Attack):
     name = "inf"
     uses_honest_grads = True
-    supports_subtasks = False
+    supports_subtasks = True
 
     def __init__(self, *, chunk_size: int = 8192) -> None:
         if chunk_size <= 0:
@@ -25,6 +33,24 @@ class InfAttack(Attack):
         out = torch.empty(rows[0].numel(), dtype=torch.float32, device=like.device)
         ops.fill_(out, float("inf"))
         return finish(out, like)
+
+    # -- subtask path: every chunk of the output is filled independently (reference inf.py:29-32, 80-117) --
+    def create_subtasks(self, inputs, *, context):
+        grads = inputs.get("honest_grads")
+        if not grads:
+            raise ValueError("InfAttack requires honest_grads.")
+        rows, like = prepare_rows([grads[0]], "honest_grads")
+        d = rows[0].numel()
+        chunk = select_adaptive_chunk_size(d, self.chunk_size, pool_size=pool_size_of(context))
+        return [SubTask(fn=_inf_chunk, args=(s, min(d, s + chunk), str(like.device)), name=f"inf_chunk_{k}")
+                for k, s in enumerate(range(0, d, chunk))]
+
+    def reduce_subtasks(self, partials, inputs, *, context):
+        if not partials:
+            return self.compute(inputs, context=context)
+        _, like = prepare_rows([inputs["honest_grads"][0]], "honest_grads")
+        parts = sorted(partials, key=lambda p: p[0])
+        return finish(torch.cat([torch.as_tensor(p[1]).reshape(-1).to(like.device) for p in parts]), like)
 
 
 __all__ = ["InfAttack"]

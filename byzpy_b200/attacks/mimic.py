@@ -2,15 +2,23 @@
 attacks/mimic.py:35-142).  In the fused device round this is a row *alias* (same pointer twice)."""
 from __future__ import annotations
 
+import torch
+
 from .. import ops
-from ..aggregators.base import finish, prepare_rows
+from ..aggregators._chunking import select_adaptive_chunk_size
+from ..aggregators.base import finish, pool_size_of, prepare_rows
+from ..engine.graph.subtask import SubTask
 from .base import Attack
+
+
+def _copy_chunk(vec: torch.Tensor, start: int, end: int):
+    return start, ops.scale_copy(vec[start:end], 1.0)
 
 
 class MimicAttack(Attack):
     name = "mimic"
     uses_honest_grads = True
-    supports_subtasks = False
+    supports_subtasks = True
 
     def __init__(self, epsilon: int = 0, *, chunk_size: int = 8192) -> None:
         if epsilon < 0:
@@ -27,6 +35,30 @@ class MimicAttack(Attack):
             raise ValueError(f"epsilon={self.epsilon} out of range for {len(honest_grads)} honest gradients")
         rows, like = prepare_rows([honest_grads[self.epsilon]], "honest_grads")
         return finish(ops.scale_copy(rows[0], 1.0), like)
+
+    # -- subtask path: the replayed row is copied chunk by chunk (reference mimic.py:29-32, 100-140) -----
+    def _victim(self, inputs):
+        grads = inputs.get("honest_grads")
+        if not grads:
+            raise ValueError("MimicAttack requires honest_grads.")
+        if self.epsilon >= len(grads):
+            raise ValueError(f"epsilon={self.epsilon} out of range for {len(grads)} honest gradients")
+        return prepare_rows([grads[self.epsilon]], "honest_grads")
+
+    def create_subtasks(self, inputs, *, context):
+        rows, _ = self._victim(inputs)
+        vec = rows[0]
+        d = vec.numel()
+        chunk = select_adaptive_chunk_size(d, self.chunk_size, pool_size=pool_size_of(context))
+        return [SubTask(fn=_copy_chunk, args=(vec, s, min(d, s + chunk)), name=f"mimic_chunk_{k}")
+                for k, s in enumerate(range(0, d, chunk))]
+
+    def reduce_subtasks(self, partials, inputs, *, context):
+        if not partials:
+            return self.compute(inputs, context=context)
+        _, like = self._victim(inputs)
+        parts = sorted(partials, key=lambda p: p[0])
+        return finish(torch.cat([torch.as_tensor(p[1]).reshape(-1).to(like.device) for p in parts]), like)
 
     def fold(self, n_honest: int):
         from ..parallel.device_ps import RowFold

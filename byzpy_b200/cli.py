@@ -2,7 +2,7 @@
 
     byzpy-b200 version
     byzpy-b200 doctor [--format json]          python / torch+CUDA / kernel extension / NVLink peers
-    byzpy-b200 list {aggregators,attacks,pre-aggregators} [--format json]
+    byzpy-b200 list {aggregators,attacks,pre-aggregators} [--format json] [--short]
     byzpy-b200 build [--force]                  compile the sm_100a kernel library in-tree
     byzpy-b200 bench -- <bench.py args>         run the headline benchmark
 """
@@ -23,7 +23,8 @@ from . import __version__
 
 
 def _load_subclasses(package: str, base: type) -> List[str]:
-    """Names of the concrete ``base`` subclasses defined under ``package`` (tests skipped)."""
+    """Fully qualified names (``package.module.Class``, as the reference's CLI prints them) of the concrete
+    ``base`` subclasses defined under ``package`` (test packages and private modules skipped)."""
     pkg = importlib.import_module(package)
     found = set()
     for info in pkgutil.walk_packages(pkg.__path__, prefix=pkg.__name__ + "."):
@@ -37,7 +38,7 @@ def _load_subclasses(package: str, base: type) -> List[str]:
             if issubclass(obj, base) and obj is not base and not inspect.isabstract(obj) \
                     and obj.__module__.startswith(package) \
                     and not obj.__module__.endswith(".base"):
-                found.add(obj.__name__)
+                found.add(f"{obj.__module__}.{obj.__name__}")
     return sorted(found)
 
 
@@ -117,6 +118,8 @@ def _cmd_list(args: argparse.Namespace) -> int:
         from .pre_aggregators.base import PreAggregator as base
 
         items = _load_subclasses("byzpy_b200.pre_aggregators", base)
+    if args.short:
+        items = sorted({name.rsplit(".", 1)[-1] for name in items})
     if args.format == "json":
         print(json.dumps({"component": args.component, "items": items}, indent=2))
     else:
@@ -154,6 +157,7 @@ def build_parser() -> argparse.ArgumentParser:
     lst = sub.add_parser("list", help="List built-in components.")
     lst.add_argument("component", choices=("aggregators", "attacks", "pre-aggregators"))
     lst.add_argument("--format", choices=("human", "json"), default="human")
+    lst.add_argument("--short", action="store_true", help="class names only instead of package.module.Class")
     lst.set_defaults(func=_cmd_list)
     bld = sub.add_parser("build", help="Compile the sm_100a kernel library in-tree.")
     bld.add_argument("--force", action="store_true")

@@ -56,6 +56,10 @@ class _RenamedInput(Operator):
 
 
 class OperatorExecutor:
+    """Reusable single-operator runner: ``async with OperatorExecutor(op, pool_config=...) as ex`` keeps
+    the actor pool, the one-node graph and its scheduler alive across ``await ex.run(inputs)`` calls
+    (reference engine/graph/executor.py:70-294)."""
+
     def __init__(self, operator: Operator, *, input_keys: Optional[Sequence[str]] = None,
                  pool_config: Union[ActorPoolConfig, Sequence[ActorPoolConfig], None] = None,
                  node_name: Optional[str] = None):
@@ -121,6 +125,19 @@ class OperatorExecutor:
 async def run_operator(operator: Operator, inputs: Mapping[str, Any], *,
                        pool_config: Union[ActorPoolConfig, Sequence[ActorPoolConfig], None] = None,
                        input_keys: Optional[Sequence[str]] = None) -> Any:
+    """Run one operator once and return its result.
+
+    ``operator``: an :class:`Aggregator` / :class:`PreAggregator` (its input key -- ``"gradients"`` /
+    ``"vectors"`` -- is detected) or any :class:`Operator` together with ``input_keys``; attacks are refused
+    (they take several differently-routed inputs: wire them into a graph).  ``inputs``: mapping from input
+    key to value, e.g. ``{"gradients": [tensor, ...]}``.  ``pool_config``: one ``ActorPoolConfig`` or a
+    sequence of them; an ``ActorPool`` is started for this call, the operator is decomposed into subtasks
+    over it, and the pool is shut down again (use :class:`OperatorExecutor` to keep the pool across calls).
+    Without ``pool_config`` the operator computes directly in this process.
+
+    Returns whatever the operator returns (a tensor for aggregators, a list of tensors for
+    pre-aggregators) on the input's device.
+    """
     async with OperatorExecutor(operator, pool_config=pool_config, input_keys=input_keys) as ex:
         return await ex.run(inputs)
 

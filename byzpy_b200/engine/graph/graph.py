@@ -65,7 +65,8 @@ class ComputationGraph:
                     if dep not in deps:
                         deps.append(dep)
                 else:
-                    raise ValueError(f"Node {node.name} depends on unknown node {dep!r}")
+                    raise ValueError(f"Node {node.name} depends on unknown node {dep!r}: the graph contains a cycle "
+                                     f"or an unresolved dependency")
             self._edges[node.name] = deps
         self._order = self._toposort([n.name for n in nodes])
         self.outputs: List[str] = list(outputs) if outputs is not None else [self._order[-1]]

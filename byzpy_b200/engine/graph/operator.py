@@ -120,6 +120,11 @@ class Operator:
     supports_subtasks: bool = False
     supports_barriered_subtasks: bool = False
     max_subtasks_inflight: Optional[int] = None
+    # The reference's operators park per-call state on ``self`` between create_subtasks() and
+    # reduce_subtasks() (a shared-memory handle and the flat shape).  Operators here are stateless, the
+    # attributes exist (always None) so callers that inspect or reset them keep working.
+    _active_handle: Any = None
+    _flat_shape: Any = None
 
     # -- to be provided by subclasses -------------------------------------------------
     def compute(self, inputs: Mapping[str, Any], *, context: OpContext) -> Any:

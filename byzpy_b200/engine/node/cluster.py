@@ -17,7 +17,7 @@ class DecentralizedCluster:
         self.nodes: Dict[NodeId, DecentralizedNode] = {}
         self._node_id_map: Dict[int, NodeId] = {}
 
-    async def add_node(self, *, node_id: NodeId, application: NodeApplication, topology: Any = None,
+    async def add_node(self, node_id: NodeId, application: NodeApplication, topology: Any = None,
                        context: Optional[NodeContext] = None,
                        metadata: Optional[Mapping[str, Any]] = None) -> DecentralizedNode:
         if node_id in self.nodes:

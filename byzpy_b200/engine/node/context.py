@@ -28,6 +28,11 @@ if TYPE_CHECKING:  # pragma: no cover
     from .decentralized import DecentralizedNode
 
 
+class PeerUnreachableError(ConnectionError, RuntimeError):
+    """A message could not be handed to a peer: no inbound connection from it and dialling it failed.
+    It is a ``ConnectionError`` (transport layer) and, like the reference's error, a ``RuntimeError``."""
+
+
 class NodeContext(ABC):
     @abstractmethod
     async def start(self, node: "DecentralizedNode") -> None:
@@ -397,6 +402,7 @@ class MeshRemoteContext(NodeContext):
         self._inbound_connections: Dict[Any, asyncio.StreamWriter] = {}
         self._inbox: asyncio.Queue = asyncio.Queue()
         self._monitor_task: Optional[asyncio.Task] = None
+        self._serve_task: Optional[asyncio.Task] = None
 
     async def start(self, node: "DecentralizedNode") -> None:
         if self._running:
@@ -406,6 +412,7 @@ class MeshRemoteContext(NodeContext):
         self._local_server = await asyncio.start_server(self._handle_inbound_connection,
                                                         self.local_host, self.local_port)
         self.local_port = self._local_server.sockets[0].getsockname()[1]
+        self._serve_task = asyncio.ensure_future(self._local_server.serve_forever())
         await self._dial_missing()
         self._monitor_task = asyncio.ensure_future(self._connection_monitor())
 
@@ -497,7 +504,7 @@ class MeshRemoteContext(NodeContext):
             await self._peer_clients[to_node_id].send_message(to_node_id, message_type, payload,
                                                               from_node_id=sender)
             return
-        raise ConnectionError(f"No connection to peer {to_node_id!r}")
+        raise PeerUnreachableError(f"No connection to peer {to_node_id!r}")
 
     async def receive_messages(self) -> AsyncIterator[Any]:
         # outbound clients may also carry replies written on the same socket by the peer
@@ -548,10 +555,17 @@ class MeshRemoteContext(NodeContext):
             except Exception:
                 pass
         self._inbound_connections.clear()
+        if self._serve_task is not None:
+            self._serve_task.cancel()
+            try:
+                await self._serve_task
+            except (asyncio.CancelledError, Exception):
+                pass
+            self._serve_task = None
         if self._local_server is not None:
             self._local_server.close()
             try:
-                await self._local_server.wait_closed()
+                await asyncio.wait_for(self._local_server.wait_closed(), timeout=2.0)
             except Exception:
                 pass
             self._local_server = None
@@ -563,4 +577,5 @@ class MeshRemoteContext(NodeContext):
         return out
 
 
-__all__ = ["NodeContext", "InProcessContext", "ProcessContext", "RemoteContext", "MeshRemoteContext"]
+__all__ = ["NodeContext", "InProcessContext", "ProcessContext", "RemoteContext", "MeshRemoteContext",
+           "PeerUnreachableError"]

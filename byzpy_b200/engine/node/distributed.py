@@ -79,7 +79,11 @@ class DistributedByzantineNode(_DistributedNodeBase, ByzantineNode):
         super().__init_subclass__(**kwargs)
         own = cls.__dict__.get("byzantine_gradient")
         if own is not None and own is not DistributedByzantineNode.byzantine_gradient:
+            # the user's implementation (any signature) becomes the body of the attack pipeline; the public
+            # ``byzantine_gradient(x, y, honest_grads)`` entry point goes back to the dispatcher below, so
+            # the parameter server's calling convention keeps working and the call runs on the node's pool
             cls._distributed_user_bz = own
+            cls.byzantine_gradient = DistributedByzantineNode.byzantine_gradient
         else:
             cls._distributed_user_bz = getattr(cls, "_distributed_user_bz", None)
 

@@ -47,6 +47,7 @@ class RemoteNodeServer:
         self.gpu_direct = gpu_direct
         self._nodes: Dict[Any, Any] = {}
         self._clients: Dict[Any, asyncio.StreamWriter] = {}
+        self._writers: set = set()          # every accepted connection, registered or not
         self._server: Optional[asyncio.AbstractServer] = None
         self._running = False
 
@@ -66,8 +67,22 @@ class RemoteNodeServer:
 
     async def serve(self) -> None:
         await self.start()
-        async with self._server:
+        try:
             await self._server.serve_forever()
+        finally:
+            # cancelled or stopped: also hang up on the clients that are still connected -- since Python
+            # 3.12 ``Server.wait_closed()`` waits for every open connection, so leaving them would block
+            self._running = False
+            self._close_connections()
+            self._server.close()
+
+    def _close_connections(self) -> None:
+        for w in list(self._writers):
+            try:
+                w.close()
+            except Exception:
+                pass
+        self._writers.clear()
 
     async def _deliver(self, msg: Dict[str, Any]) -> None:
         target = msg.get("to")
@@ -81,6 +96,7 @@ class RemoteNodeServer:
 
     async def _handle_client(self, reader: asyncio.StreamReader, writer: asyncio.StreamWriter) -> None:
         owned = []
+        self._writers.add(writer)
         try:
             while True:
                 try:
@@ -100,10 +116,20 @@ class RemoteNodeServer:
             for nid in owned:
                 if self._clients.get(nid) is writer:
                     self._clients.pop(nid, None)
+            self._writers.discard(writer)
             try:
                 writer.close()
             except Exception:
                 pass
+
+    @property
+    def _client_connections(self) -> Dict[Any, asyncio.StreamWriter]:
+        """All open client connections: by node id once a client registered one, by connection identity
+        before that (the reference's attribute name)."""
+        named = {id(w) for w in self._clients.values()}
+        out: Dict[Any, asyncio.StreamWriter] = dict(self._clients)
+        out.update({f"conn-{id(w):x}": w for w in self._writers if id(w) not in named})
+        return out
 
     async def send_message_to_client(self, node_id, msg: Dict[str, Any]) -> None:
         writer = self._clients.get(node_id)
@@ -127,6 +153,7 @@ class RemoteNodeServer:
             except Exception:
                 pass
         self._clients.clear()
+        self._close_connections()
         if self._server is not None:
             self._server.close()
             try:

@@ -77,8 +77,34 @@ def _create_honest_node_application(actor: Any, node_id: str, lr: float) -> Hone
         return await _invoke(key, "p2p_half_step", lr)
 
     async def aggregate_and_set(own, received):
-        await _invoke(key, "p2p_aggregate_and_set", own, list(received))
-        return True
+        """Robust aggregation of own + received, written back into the model.  Nodes built on
+        ``P2PHonestMixin`` provide ``p2p_aggregate_and_set``; duck-typed nodes may only offer the older
+        ``p2p_aggregate(vectors)`` hook, and a node with neither gets the coordinate-wise median of the
+        candidates loaded through ``set_param_vector`` when it has one (the reference computes exactly that
+        median and then drops it)."""
+        received = list(received)
+        local = _NODE_OBJECT_REGISTRY.get(key)
+        if local is None or hasattr(local, "p2p_aggregate_and_set"):
+            try:
+                await _invoke(key, "p2p_aggregate_and_set", own, received)
+                return True
+            except AttributeError:
+                if local is not None:
+                    raise                      # raised inside the node's own method: not a missing hook
+        if local is None or hasattr(local, "p2p_aggregate"):
+            try:
+                return await _invoke(key, "p2p_aggregate", [own, *received])
+            except AttributeError:
+                if local is not None:
+                    raise
+        agg = CoordinateWiseMedian().aggregate([own, *received])
+        if local is None or hasattr(local, "set_param_vector"):
+            try:
+                await _invoke(key, "set_param_vector", agg)
+            except AttributeError:
+                if local is not None:
+                    raise
+        return agg
 
     app.register_pipeline("half_step", make_single_operator_graph(
         node_name="half_step", operator=CallableOp(half_step, input_mapping={"lr": "lr"}),

@@ -39,6 +39,11 @@ class PreAggregator(Operator, ABC):
         ...
 
 
+def _mix_chunk(packed: _Packed, start: int, end: int, W: torch.Tensor):
+    rows = _kernel_rows(packed.slice(start, end))
+    return start, ops.weighted_sum(rows, W.to(rows[0].device))
+
+
 class LinearPreAggregator(PreAggregator):
     """Pre-aggregators expressible as ``X' = W X``."""
 
@@ -77,13 +82,22 @@ class LinearPreAggregator(PreAggregator):
         return self._materialise(rows, self.row_map(G, n), like)
 
     # -- subtask path: split-K Gram over feature chunks, then one local materialisation ----
+    # (maps that need no Gram -- Bucketing -- are materialised by the pool instead: every subtask emits
+    #  the (m, chunk) slab of Y = W X for its feature chunk; the mixing matrix is drawn once, here)
     def create_subtasks(self, inputs, *, context):
         xs = inputs.get(self.input_key)
-        if not isinstance(xs, Sequence) or not xs or not self.needs_gram:
+        if not isinstance(xs, Sequence) or not xs:
             return []
         rows, _ = prepare_rows(xs, "xs")
         self._validate(len(rows))
         d = rows[0].numel()
+        if not self.needs_gram:
+            W = torch.from_numpy(np.asarray(self.row_map(None, len(rows)), dtype=np.float32))
+            chunk = select_adaptive_chunk_size(d, self.feature_chunk_size, pool_size=pool_size_of(context))
+            packed = _Packed.pack(_kernel_rows(rows), in_process=pool_in_process(context))
+            _hold_packed(self, inputs, packed)
+            return [SubTask(fn=_mix_chunk, args=(packed, s, e, W), name=f"{self.name}_mix_{k}")
+                    for k, (s, e) in enumerate(feature_chunks(d, chunk))]
         chunk = select_adaptive_chunk_size(d, self.feature_chunk_size, pool_size=pool_size_of(context))
         packed = _Packed.pack(_kernel_rows(rows), in_process=pool_in_process(context))
         _hold_packed(self, inputs, packed)
@@ -96,6 +110,10 @@ class LinearPreAggregator(PreAggregator):
                 return self.compute(inputs, context=context)
             rows, like = prepare_rows(inputs[self.input_key], "xs")
             n = len(rows)
+            if isinstance(partials[0], tuple):          # (offset, (m, chunk) slab) from _mix_chunk
+                parts = sorted(partials, key=lambda p: p[0])
+                Y = torch.cat([torch.as_tensor(p[1]).to(like.device) for p in parts], dim=1)
+                return [finish(Y[i], like) for i in range(Y.shape[0])]
             G = np.zeros((n, n), dtype=np.float64)
             for p in partials:
                 G += np.asarray(p, dtype=np.float64)

@@ -460,8 +460,10 @@ def test_cli_human_outputs_and_parser(capsys):
     assert "python_version:" in out and "torch:" in out and "  - available: True" in out
     assert cli_main(["list", "pre-aggregators", "--format", "json"]) == 0
     items = json.loads(capsys.readouterr().out)
-    assert items["component"] == "pre-aggregators" and set(items["items"]) == {"ARC", "Bucketing", "Clipping", "NearestNeighborMixing"}
-    assert cli_main(["list", "attacks", "--format", "json"]) == 0
+    assert items["component"] == "pre-aggregators"
+    assert "byzpy_b200.pre_aggregators.bucketing.Bucketing" in items["items"]           # qualified, like the reference
+    assert {n.rsplit(".", 1)[-1] for n in items["items"]} == {"ARC", "Bucketing", "Clipping", "NearestNeighborMixing"}
+    assert cli_main(["list", "attacks", "--format", "json", "--short"]) == 0
     assert {"EmpireAttack", "GaussianAttack", "InfAttack", "LabelFlipAttack", "LittleAttack", "MimicAttack",
             "SignFlipAttack"} <= set(json.loads(capsys.readouterr().out)["items"])
     with pytest.raises(SystemExit):
@@ -475,6 +477,9 @@ def test_cli_human_outputs_and_parser(capsys):
 def test_cli_subclass_discovery_skips_abstract_and_private():
     from byzpy_b200.aggregators.base import Aggregator
 
-    names = _load_subclasses("byzpy_b200.aggregators", Aggregator)
-    assert names == sorted(names) and "Aggregator" not in names and "GramAggregator" not in names
+    qualified = _load_subclasses("byzpy_b200.aggregators", Aggregator)
+    assert "byzpy_b200.aggregators.coordinate_wise.median.CoordinateWiseMedian" in qualified
+    assert not any(".tests" in q for q in qualified)
+    names = [q.rsplit(".", 1)[-1] for q in qualified]
+    assert qualified == sorted(qualified) and "Aggregator" not in names and "GramAggregator" not in names
     assert len(names) >= 12

@@ -255,7 +255,7 @@ def test_cli(capsys):
     rep = json.loads(capsys.readouterr().out)
     assert rep["torch"]["available"] and "kernels" in rep
     assert cli_main(["list", "aggregators", "--format", "json"]) == 0
-    items = json.loads(capsys.readouterr().out)["items"]
+    items = [q.rsplit(".", 1)[-1] for q in json.loads(capsys.readouterr().out)["items"]]
     assert {"CoordinateWiseMedian", "MultiKrum", "Krum", "CAF", "SMEA", "MoNNA"} <= set(items)
     assert "CoordinateWiseAggregator" not in items
     assert cli_main(["list", "attacks"]) == 0 and "LittleAttack" in capsys.readouterr().out
@@ -271,8 +271,16 @@ def test_train_with_progress():
 
     evals = []
     ps = FakePS()
-    run(train_with_progress(ps, 10, eval_callback=lambda: evals.append(ps.n) or {"acc": 0.5}, eval_interval=5))
+    hist = run(train_with_progress(ps, 10, eval_callback=lambda: evals.append(ps.n) or {"acc": 0.5}, eval_interval=5))
     assert ps.n == 10 and evals == [5, 10]
+    assert hist == [{"round": 5, "metrics": {"acc": 0.5}}, {"round": 10, "metrics": {"acc": 0.5}}]
+
+    async def scored(round_num):                                   # the reference's callback shape: async, takes the round
+        return {"acc": round_num / 10}
+
+    hist = run(train_with_progress(FakePS(), 4, eval_callback=scored, eval_interval=2))
+    assert [h["round"] for h in hist] == [2, 4] and hist[1]["metrics"] == {"acc": 0.4}
+    assert run(train_with_progress(FakePS(), 3)) == []
 
 
 def test_shared_store_roundtrip():
