@@ -25,8 +25,8 @@ import torch
 from .. import ops
 from ..engine.graph.operator import OpContext, Operator
 from ..engine.graph.subtask import SubTask
-from ..engine.storage.shared_store import (SharedTensorHandle, cleanup_tensor, materialize, open_tensor,
-                                           register_tensor)
+from ..engine.storage.shared_store import (SharedTensorHandle, attach_cached, cleanup_tensor, materialize,
+                                           register_rows)
 from ._chunking import select_adaptive_chunk_size
 
 
@@ -114,15 +114,15 @@ class _Packed:
     def pack(cls, rows: List[torch.Tensor], in_process: bool = False) -> "_Packed":
         if rows[0].is_cuda or in_process:
             return cls(None, rows)      # by reference: no POSIX shm round trip for in-process workers
-        mat = torch.stack([r.to(torch.float64 if r.dtype == torch.float64 else torch.float32)
-                           for r in rows], dim=0)
-        return cls(register_tensor(mat.numpy()), None)
+        dtype = torch.float64 if rows[0].dtype == torch.float64 else torch.float32
+        return cls(register_rows([r.to(dtype) for r in rows]), None)      # rows copied straight into the segment
 
     def slice(self, start: int, end: int) -> List[torch.Tensor]:
         if self.rows is not None:
             return [r[start:end] for r in self.rows]
-        with open_tensor(self.handle) as arr:
-            chunk = torch.from_numpy(np.array(arr[:, start:end], copy=True))
+        arr = attach_cached(self.handle)                 # mapping reused by this invocation's other subtasks
+        chunk = torch.from_numpy(np.array(arr[:, start:end], copy=True))
+        del arr
         return [chunk[i] for i in range(chunk.shape[0])]
 
     def release(self) -> None:

@@ -14,6 +14,7 @@ SURVEY 0.4).
 """
 from __future__ import annotations
 
+from collections import OrderedDict
 from contextlib import contextmanager
 from dataclasses import dataclass
 from multiprocessing import shared_memory
@@ -59,6 +60,49 @@ def register_tensor(array: Any) -> SharedTensorHandle:
     return SharedTensorHandle(name=seg.name, shape=tuple(arr.shape), dtype=str(arr.dtype))
 
 
+def register_rows(rows) -> SharedTensorHandle:
+    """``n`` equally long 1-D tensors -> one ``(n, d)`` shared segment, each row copied straight into the
+    mapping (one pass over the data; ``register_tensor(torch.stack(rows))`` makes two and a temporary)."""
+    rows = list(rows)
+    n, d = len(rows), int(rows[0].numel())
+    dtype = rows[0].dtype
+    itemsize = torch.empty((), dtype=dtype).element_size()
+    seg = shared_memory.SharedMemory(create=True, size=max(1, n * d * itemsize))
+    try:
+        if n * d:
+            view = torch.frombuffer(seg.buf, dtype=dtype, count=n * d).view(n, d)
+            torch.stack([r.detach().reshape(-1).to(dtype=dtype, device="cpu") for r in rows], dim=0, out=view)
+            del view
+    finally:
+        seg.close()
+    return SharedTensorHandle(name=seg.name, shape=(n, d), dtype=str(torch.empty((), dtype=dtype).numpy().dtype))
+
+
+_ATTACHED: "OrderedDict[str, shared_memory.SharedMemory]" = OrderedDict()
+_ATTACH_LIMIT = 4
+
+
+def attach_cached(handle: SharedHandleLike) -> np.ndarray:
+    """Map a segment and keep the mapping for the next few calls: the subtasks of one operator invocation
+    all read the same segment, and ``shm_open`` + ``mmap`` + page-table population per subtask is most of a
+    small subtask's cost.  At most ``_ATTACH_LIMIT`` mappings stay open per process (oldest closed first);
+    the creator's ``cleanup_tensor`` still unlinks the name, the memory goes when the last mapping closes."""
+    h = _coerce(handle)
+    seg = _ATTACHED.get(h.name)
+    if seg is None:
+        seg = shared_memory.SharedMemory(name=h.name)
+        _ATTACHED[h.name] = seg
+        while len(_ATTACHED) > _ATTACH_LIMIT:
+            _, old = _ATTACHED.popitem(last=False)
+            try:
+                old.close()
+            except BufferError:            # a view is still alive somewhere: let the GC close it
+                pass
+    else:
+        _ATTACHED.move_to_end(h.name)
+    return np.ndarray(h.shape, dtype=np.dtype(h.dtype), buffer=seg.buf)
+
+
 @contextmanager
 def open_tensor(handle: SharedHandleLike) -> Iterator[np.ndarray]:
     h = _coerce(handle)
@@ -93,5 +137,5 @@ def materialize(obj: Any) -> torch.Tensor:
     return torch.as_tensor(obj)
 
 
-__all__ = ["SharedTensorHandle", "register_tensor", "open_tensor", "cleanup_tensor", "is_handle",
-           "materialize"]
+__all__ = ["SharedTensorHandle", "register_tensor", "register_rows", "attach_cached", "open_tensor",
+           "cleanup_tensor", "is_handle", "materialize"]
