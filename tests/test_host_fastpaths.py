@@ -253,3 +253,71 @@ def test_node_scheduler_never_offloads():
     make = lambda i: CallableOp(lambda x: tids.append(threading.get_ident()) or x, input_mapping={"x": "x"})  # noqa: E731
     asyncio.run(NodeScheduler(_branch_graph(make)).run({"x": 0}))
     assert tids == [main_thread] * 3
+
+
+# ------------------------------------------------------------------------------ shared-memory packing
+def test_register_rows_is_one_segment_equal_to_the_stack():
+    from byzpy_b200.engine.storage.shared_store import cleanup_tensor, open_tensor, register_rows
+
+    torch.manual_seed(11)
+    for dtype in (torch.float32, torch.float64):
+        rows = [torch.randn(1000, dtype=dtype) for _ in range(5)]
+        h = register_rows(rows)
+        try:
+            assert h.shape == (5, 1000) and h.dtype == ("float32" if dtype == torch.float32 else "float64")
+            with open_tensor(h) as arr:
+                assert torch.equal(torch.from_numpy(arr.copy()), torch.stack(rows))
+        finally:
+            cleanup_tensor(h)
+    shaped = [torch.arange(6.0).reshape(2, 3) + i for i in range(3)]          # rows are flattened
+    h = register_rows(shaped)
+    try:
+        with open_tensor(h) as arr:
+            assert arr.shape == (3, 6) and arr[2, 5] == 7.0
+    finally:
+        cleanup_tensor(h)
+
+
+def test_attach_cached_reuses_and_bounds_its_mappings():
+    from byzpy_b200.engine.storage import shared_store as ss
+
+    handles = [ss.register_rows([torch.full((16,), float(i))]) for i in range(ss._ATTACH_LIMIT + 2)]
+    try:
+        first = ss.attach_cached(handles[0])
+        assert first[0, 0] == 0.0
+        seg = ss._ATTACHED[handles[0].name]
+        del first
+        assert ss.attach_cached(handles[0]) is not None and ss._ATTACHED[handles[0].name] is seg   # same mapping
+        for h in handles[1:]:
+            assert ss.attach_cached(h)[0, 3] == float(handles.index(h))
+        assert len(ss._ATTACHED) <= ss._ATTACH_LIMIT and handles[0].name not in ss._ATTACHED       # oldest evicted
+        ss.cleanup_tensor(handles[-1])                                   # unlinked name, cached mapping still readable
+        assert ss.attach_cached(handles[-1])[0, 0] == float(len(handles) - 1)
+    finally:
+        for h in handles:
+            ss.cleanup_tensor(h)
+
+
+def _threads_in_worker():
+    import torch as _t
+
+    return _t.get_num_threads()
+
+
+@pytest.mark.real_actor_backends
+def test_process_pool_workers_split_the_cores(monkeypatch):
+    from byzpy_b200.engine.graph.pool import ActorPool, ActorPoolConfig
+    from byzpy_b200.engine.graph.subtask import SubTask
+
+    monkeypatch.setattr(os, "cpu_count", lambda: 8)
+
+    async def main():
+        pool = ActorPool([ActorPoolConfig(backend="process", count=2)])
+        await pool.start()
+        try:
+            return [await pool.run_subtask(SubTask(fn=_threads_in_worker, affinity=a))
+                    for a in pool.worker_affinities()]
+        finally:
+            await pool.shutdown()
+
+    assert asyncio.run(main()) == [4, 4]
