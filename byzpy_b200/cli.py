@@ -74,6 +74,7 @@ def _doctor() -> dict:
             k["arch"] = ext.ARCH
             k["path"] = getattr(ext, "__file__", None)
             k["entry_points"] = sorted(n for n in dir(ext) if not n.startswith("_") and n.islower())
+            k["host_kernels"] = [n for n in ("host_cw_select", "host_colstat") if hasattr(ext, n)]
             if report["torch"].get("cuda"):
                 n = ext.device_count()
                 report["nvlink"]["peer_access"] = [[bool(i == j or ext.can_access_peer(i, j))

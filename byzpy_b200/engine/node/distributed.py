@@ -99,14 +99,17 @@ class DistributedByzantineNode(_DistributedNodeBase, ByzantineNode):
         app = self._app
         if user_impl is not None:
             self._custom_bz_callable = user_impl.__get__(self, type(self))
-            keys, required = [], []
+            keys, required, defaults = [], [], {}
             for pname, param in inspect.signature(self._custom_bz_callable).parameters.items():
                 if pname == "self":
                     continue
                 keys.append(pname)
                 if param.default is inspect.Signature.empty:
                     required.append(pname)
+                else:
+                    defaults[pname] = param.default
             self._custom_input_keys, self._custom_required_keys = tuple(keys), tuple(required)
+            self._custom_defaults = defaults
             op = RemoteCallableOp(self._custom_bz_callable, input_mapping={k: k for k in keys})
             app.register_pipeline(app.ATTACK_PIPELINE, make_single_operator_graph(
                 node_name="attack", operator=op, input_keys=keys))
@@ -161,9 +164,17 @@ class DistributedByzantineNode(_DistributedNodeBase, ByzantineNode):
                 out[key] = value
         return out
 
+    def _complete_custom_inputs(self, inputs: Mapping[str, object]) -> Mapping[str, object]:
+        """The attack pipeline's graph names every parameter of the user's function as an input; optional
+        ones the caller left out are bound to their declared defaults."""
+        out = dict(inputs)
+        for key, default in getattr(self, "_custom_defaults", {}).items():
+            out.setdefault(key, default)
+        return out
+
     def _inputs(self, **data) -> Mapping[str, object]:
         if self._custom_bz_callable is not None:
-            return self._build_custom_inputs(**data)
+            return self._complete_custom_inputs(self._build_custom_inputs(**data))
         return self.prepare_attack_inputs(**data)
 
     async def run_attack(self, *, inputs: Mapping[str, object]) -> torch.Tensor:
