@@ -11,8 +11,10 @@ from __future__ import annotations
 
 import asyncio
 import multiprocessing as mp
+import os
 import threading
 import traceback
+import weakref
 from typing import Any
 
 import cloudpickle
@@ -26,6 +28,7 @@ def _child_main(conn) -> None:
     import inspect as _inspect
 
     obj = None
+    threads = None
     while True:
         try:
             msg = conn.recv()
@@ -33,6 +36,12 @@ def _child_main(conn) -> None:
             break
         op = msg.get("op")
         try:
+            want = msg.get("threads")
+            if want and want != threads:            # this host's process actors split the cores between them
+                import torch as _torch
+
+                _torch.set_num_threads(int(want))
+                threads = want
             if op == "stop":
                 conn.send({"ok": True, "payload": None})
                 break
@@ -63,11 +72,27 @@ async def _await(x):
     return await x
 
 
+_LIVE: "weakref.WeakSet[ProcessActorBackend]" = weakref.WeakSet()
+
+
+def _thread_share() -> int:
+    """Intra-op threads each live process actor of this parent may use: ``cores // actors``.  Five node
+    processes each opening 8-thread OpenMP regions on 8 cores spend their time spinning at barriers (the
+    reference's process examples show exactly that); the share travels with every request, so it follows
+    actors being created and closed.  ``BYZPY_INTRAOP_GOVERNOR=0`` turns it off."""
+    if os.environ.get("BYZPY_INTRAOP_GOVERNOR", "1") in ("0", "false", "False"):
+        return 0
+    live = sum(1 for b in _LIVE if not b._closed)
+    return max(1, (os.cpu_count() or 1) // max(1, live))
+
+
 class ProcessActorBackend(LocalMailboxBackend):
     scheme = "process"
 
     def __init__(self) -> None:
         super().__init__()
+        self._closed = False
+        _LIVE.add(self)
         ctx = mp.get_context("spawn")
         self._conn, child = ctx.Pipe(duplex=True)
         self._proc = ctx.Process(target=_child_main, args=(child,), daemon=True)
@@ -85,6 +110,9 @@ class ProcessActorBackend(LocalMailboxBackend):
             if self._closed:
                 raise RuntimeError("process actor is closed")
             try:
+                share = _thread_share()
+                if share:
+                    msg = {**msg, "threads": share}
                 self._conn.send(msg)
                 reply = self._conn.recv()
             except (EOFError, OSError, BrokenPipeError) as exc:

@@ -12,7 +12,6 @@ deserialised callables (the reference re-unpickles on every call).
 from __future__ import annotations
 
 import asyncio
-import os
 from collections import OrderedDict, defaultdict, deque
 from dataclasses import dataclass
 from typing import Any, Callable, Deque, Dict, List, Mapping, Optional, Sequence, Union
@@ -62,13 +61,6 @@ class _SubTaskWorker:
         else:
             self._fns.move_to_end(payload)
         return fn(*args, **dict(kwargs))
-
-    def set_intra_op_threads(self, count: int) -> int:
-        """Cap this worker's OpenMP / MKL threads (worker processes of one pool share the host's cores)."""
-        import torch
-
-        torch.set_num_threads(max(1, int(count)))
-        return torch.get_num_threads()
 
 
 class _PoolWorker:
@@ -183,7 +175,7 @@ class ActorPool:
     async def start(self) -> None:
         if self._started:
             return
-        fresh, own_process = [], []
+        fresh = []
         for cfg in self.configs:
             for idx in range(cfg.count):
                 label = f"{cfg.name or 'actor'}-{idx}"
@@ -191,16 +183,9 @@ class ActorPool:
                 worker = _PoolWorker(backend=resolve_backend(cfg.backend),
                                      capabilities=set(cfg.resolved_capabilities()) | {pin}, name=label)
                 fresh.append((worker, pin))
-                if isinstance(cfg.backend, str) and cfg.backend == "process":
-                    own_process.append(worker)
-        # workers come up concurrently (a process worker is a fresh interpreter importing torch: seconds each)
+        # workers come up concurrently (a process worker is a fresh interpreter importing torch: seconds each);
+        # process workers split the host's cores between them (ProcessActorBackend sends the share with each call)
         await asyncio.gather(*(w.start() for w, _ in fresh))
-        if len(own_process) > 1 and os.environ.get("BYZPY_INTRAOP_GOVERNOR", "1") not in ("0", "false", "False"):
-            # k worker processes on one host would each open cpu_count-wide OpenMP regions: split the cores
-            # (thread workers are handled dynamically by the in-process governor; the reference does this by
-            # hand inside Multi-Krum's subtasks only, krum.py:461-475)
-            share = max(1, (os.cpu_count() or 1) // len(own_process))
-            await asyncio.gather(*(w._ref.set_intra_op_threads(share) for w in own_process))
         for worker, pin in fresh:
             self._workers.append(worker)
             self._worker_affinity_caps.append(pin)

@@ -34,14 +34,19 @@ def shard_indices(n_items: int, n_shards: int) -> List[List[int]]:
 
 
 def batch_source(x: torch.Tensor, y: torch.Tensor, batch_size: int, *, seed: int = 0,
-                 pin: bool = False) -> Callable[[], Tuple[torch.Tensor, torch.Tensor]]:
-    """Infinite shuffled mini-batch source over in-memory tensors (a DataLoader without workers)."""
+                 pin: bool = False, shuffle: bool = True) -> Callable[[], Tuple[torch.Tensor, torch.Tensor]]:
+    """Infinite mini-batch source over in-memory tensors (a DataLoader without workers): reshuffled every
+    epoch, or cycling in storage order with ``shuffle=False``.  Incomplete trailing batches are dropped."""
     g = torch.Generator().manual_seed(seed)
-    state = {"perm": torch.randperm(x.shape[0], generator=g), "pos": 0}
+
+    def order():
+        return torch.randperm(x.shape[0], generator=g) if shuffle else torch.arange(x.shape[0])
+
+    state = {"perm": order(), "pos": 0}
 
     def next_batch():
         if state["pos"] + batch_size > x.shape[0]:
-            state["perm"] = torch.randperm(x.shape[0], generator=g)
+            state["perm"] = order()
             state["pos"] = 0
         idx = state["perm"][state["pos"]: state["pos"] + batch_size]
         state["pos"] += batch_size

@@ -3,7 +3,7 @@ examples/ps/nodes.py): an honest SmallCNN worker and an Empire-attack Byzantine 
 ``Distributed*Node`` bases, so aggregation / gradient / attack run through per-node pipelines."""
 from __future__ import annotations
 
-from typing import Sequence
+from typing import Sequence, Type
 
 import torch
 import torch.nn as nn
@@ -27,16 +27,18 @@ def select_pool_backend(spec: str) -> str:
 
 
 class DistributedPSHonestNode(DistributedHonestNode):
-    def __init__(self, *, indices: Sequence[int], batch_size: int = 64, lr: float = 0.05,
-                 momentum: float = 0.9, device: str = "cpu", pool_backend: str = "thread", seed: int = 0):
+    def __init__(self, *, indices: Sequence[int], batch_size: int = 64, shuffle: bool = True, lr: float = 0.05,
+                 momentum: float = 0.9, device: str = "cpu", data_root: str = "./data",
+                 pool_backend: str = "thread", model_cls: Type[nn.Module] = SmallCNN, seed: int = 0):
         super().__init__(actor_pool=[ActorPoolConfig(backend=pool_backend, count=1, name="worker")],
-                         aggregator=CoordinateWiseMedian(), name=f"honest-{pool_backend}")
-        x, y = mnist_like(6000)
+                         aggregator=CoordinateWiseMedian(), metadata={"pool_backend": pool_backend},
+                         name=f"honest-{pool_backend}")
+        x, y = mnist_like(6000, root=data_root)
         idx = torch.as_tensor(list(indices))
-        self._next = batch_source(x[idx], y[idx], batch_size, seed=seed)
+        self._next = batch_source(x[idx], y[idx], batch_size, seed=seed, shuffle=shuffle)
         self.device = torch.device(device)
         torch.manual_seed(0)
-        self.model = SmallCNN().to(self.device)
+        self.model = model_cls().to(self.device)
         # parameters and gradients live as views of two flat buffers: the flat gradient the server wants is
         # the buffer itself (no per-parameter cat), the aggregate is applied by one flat SGD(+momentum) update
         self.arena = ParamArena(self.model)
@@ -66,7 +68,8 @@ class DistributedPSHonestNode(DistributedHonestNode):
 class DistributedPSByzNode(DistributedByzantineNode):
     def __init__(self, *, device: str = "cpu", scale: float = -1.0, pool_backend: str = "thread"):
         super().__init__(actor_pool=[ActorPoolConfig(backend=pool_backend, count=1, name="worker")],
-                         attack=EmpireAttack(scale=scale), name=f"byz-{pool_backend}")
+                         attack=EmpireAttack(scale=scale), metadata={"pool_backend": pool_backend},
+                         name=f"byz-{pool_backend}")
         self.device = torch.device(device)
 
     def next_batch(self):

@@ -321,3 +321,33 @@ def test_process_pool_workers_split_the_cores(monkeypatch):
             await pool.shutdown()
 
     assert asyncio.run(main()) == [4, 4]
+
+
+class _ThreadProbe:
+    def threads(self):
+        return torch.get_num_threads()
+
+
+@pytest.mark.real_actor_backends
+def test_process_actors_share_follows_the_number_of_live_actors(monkeypatch):
+    from byzpy_b200.engine.actor.backends import process as proc
+
+    monkeypatch.setattr(os, "cpu_count", lambda: 8)
+    for b in list(proc._LIVE):                    # leftovers of other tests do not count
+        b._closed = True
+
+    async def main():
+        a, b = proc.ProcessActorBackend(), proc.ProcessActorBackend()
+        for be in (a, b):
+            await be.start()
+            await be.construct(_ThreadProbe, args=(), kwargs={})
+        two = [await a.call("threads"), await b.call("threads")]
+        await b.close()
+        one = await a.call("threads")             # b is gone: a gets the whole machine on its next call
+        await a.close()
+        return two, one
+
+    two, one = asyncio.run(main())
+    assert two == [4, 4] and one == 8
+    monkeypatch.setenv("BYZPY_INTRAOP_GOVERNOR", "0")
+    assert proc._thread_share() == 0
