@@ -157,7 +157,25 @@ class ProcessContext(NodeContext):
             value = getattr(node, attr, None)
             if value is not None:
                 config[key] = value
-        blob = cloudpickle.dumps(config)
+        if "_node_objects" in config:
+            # The worker objects behind the pipelines are mirrored into the child so autonomous tasks can run
+            # there; that is an optimisation, not a requirement (driver-paced pipelines execute in this
+            # process).  User nodes holding unpicklable state (a live DataLoader iterator, ...) stay here only.
+            try:
+                cloudpickle.dumps(config["_node_objects"])
+            except Exception:  # noqa: BLE001  (whatever the object's __getstate__ raises)
+                del config["_node_objects"]
+        try:
+            blob = cloudpickle.dumps(config)
+        except Exception as exc:  # noqa: BLE001
+            bad = []
+            for key, value in config.items():
+                try:
+                    cloudpickle.dumps(value)
+                except Exception:  # noqa: BLE001
+                    bad.append(key)
+            raise RuntimeError(f"ProcessContext cannot ship node {node.node_id!r} to its child process: "
+                               f"config entries {bad} are not picklable ({exc!r})") from exc
         ctx = mp.get_context("spawn")
         self._conn, child = ctx.Pipe(duplex=True)
         self._process = ctx.Process(target=_process_node_main, args=(blob, child), daemon=True)
@@ -187,6 +205,23 @@ class ProcessContext(NodeContext):
             backlog.append(msg)
         for msg in backlog:
             self._queue.put_nowait(msg)
+        ProcessContext._rebalance_threads()
+
+    @classmethod
+    def _rebalance_threads(cls) -> None:
+        """Tell every running node process its share of the host's cores (``cores // node processes``): k
+        children each opening full-width OpenMP regions spend their time spinning at barriers."""
+        import os
+
+        if os.environ.get("BYZPY_INTRAOP_GOVERNOR", "1") in ("0", "false", "False"):
+            return
+        running = [c for c in cls._registry.values() if c._running and c._conn is not None]
+        share = max(1, (os.cpu_count() or 1) // max(1, len(running)))
+        for ctx in running:
+            try:
+                ctx._put({"_command": "threads", "value": share})
+            except Exception:
+                pass
 
     async def send_message(self, to_node_id: Any, message_type: str, payload: Any) -> None:
         if not self._running:
@@ -236,6 +271,7 @@ class ProcessContext(NodeContext):
                 await loop.run_in_executor(None, proc.join, 1.0)
         if ProcessContext._registry.get(self._node_id) is self:
             del ProcessContext._registry[self._node_id]
+            ProcessContext._rebalance_threads()
         try:
             self._conn.close()
         except Exception:
@@ -272,6 +308,14 @@ class _SubprocessBridgeContext(NodeContext):
             if msg.get("_command") == "stop":
                 self._running = False
                 break
+            if msg.get("_command") == "threads":       # this host's node processes split the cores
+                try:
+                    import torch
+
+                    torch.set_num_threads(max(1, int(msg.get("value") or 1)))
+                except Exception:
+                    pass
+                continue
             if "_command" in msg:
                 continue
             # tell the parent-side node object about the delivery, then hand it to the mirror

@@ -60,6 +60,13 @@ async def _invoke(node_key: str, method: str, *args, **kwargs) -> Any:
     return out
 
 
+def _local_node(node_key: str) -> Any:
+    """Registry lookup behind a module-level function: the pipeline closures are cloudpickled by value into
+    ``ProcessContext`` children, and a closure naming the registry dict itself would drag every node object
+    along (module-level functions travel by reference)."""
+    return _NODE_OBJECT_REGISTRY.get(node_key)
+
+
 def _register(node_key: str, actor: Any) -> None:
     obj = _local_object(actor)
     if obj is not None:
@@ -83,7 +90,7 @@ def _create_honest_node_application(actor: Any, node_id: str, lr: float) -> Hone
         candidates loaded through ``set_param_vector`` when it has one (the reference computes exactly that
         median and then drops it)."""
         received = list(received)
-        local = _NODE_OBJECT_REGISTRY.get(key)
+        local = _local_node(key)
         if local is None or hasattr(local, "p2p_aggregate_and_set"):
             try:
                 await _invoke(key, "p2p_aggregate_and_set", own, received)
