@@ -105,7 +105,10 @@ def monna_weights(G: torch.Tensor, n: int, f: int, reference_index: int) -> torc
     g = torch.diagonal(G)[:n]
     d = g + g[reference_index] - 2.0 * G[reference_index, :n]
     d = torch.where(torch.isnan(d), torch.full_like(d, float("inf")), d).clamp_min(0.0)
-    d[reference_index] = -1.0                          # the trusted row always comes first
+    # the trusted row always comes first; written as a select (no scalar-into-slice assignment: that path
+    # materialises the Python scalar through a host tensor, which a capturing stream rejects)
+    trusted = torch.arange(n, device=d.device) == int(reference_index)
+    d = torch.where(trusted, torch.full_like(d, -1.0), d)
     w = torch.zeros(G.shape[0], dtype=torch.float32, device=G.device)
     w[:n] = _uniform_on_smallest(d, n - f)
     return w
