@@ -24,6 +24,8 @@ from typing import TYPE_CHECKING, Any, AsyncIterator, Dict, Optional, Tuple
 
 import cloudpickle
 
+from ..actor.backends.process import process_context
+
 if TYPE_CHECKING:  # pragma: no cover
     from .decentralized import DecentralizedNode
 
@@ -145,8 +147,6 @@ class ProcessContext(NodeContext):
             self._conn.send_bytes(blob)
 
     async def start(self, node: "DecentralizedNode") -> None:
-        import multiprocessing as mp
-
         if self._running:
             return
         self._node_id = node.node_id
@@ -176,7 +176,7 @@ class ProcessContext(NodeContext):
                     bad.append(key)
             raise RuntimeError(f"ProcessContext cannot ship node {node.node_id!r} to its child process: "
                                f"config entries {bad} are not picklable ({exc!r})") from exc
-        ctx = mp.get_context("spawn")
+        ctx = process_context()      # fork-server with torch preloaded ("spawn" semantics, fast start)
         self._conn, child = ctx.Pipe(duplex=True)
         self._process = ctx.Process(target=_process_node_main, args=(blob, child), daemon=True)
         self._process.start()

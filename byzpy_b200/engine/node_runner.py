@@ -9,13 +9,14 @@ the time until the next auto-step, instead of a 10 ms polling loop.
 """
 from __future__ import annotations
 
-import multiprocessing as mp
 import threading
 import time
 from multiprocessing.connection import wait as conn_wait
 from typing import Any, Callable, Optional
 
 import cloudpickle
+
+from .actor.backends.process import process_context
 
 
 def _runner_main(cmd_conn, inbox_conn, blob: bytes) -> None:
@@ -71,7 +72,7 @@ def _runner_main(cmd_conn, inbox_conn, blob: bytes) -> None:
 class NodeRunner:
     def __init__(self, step_fn: Callable[[dict], dict], msg_handler: Callable[[dict, Any], dict], *,
                  init_state: Optional[dict] = None) -> None:
-        ctx = mp.get_context("spawn")
+        ctx = process_context()      # fork-server with torch preloaded ("spawn" semantics, fast start)
         self._cmd, child_cmd = ctx.Pipe(duplex=True)
         child_inbox, self._inbox = ctx.Pipe(duplex=False)
         blob = cloudpickle.dumps((step_fn, msg_handler, init_state))
