@@ -13,9 +13,25 @@ from typing import Any
 import numpy as np
 import torch
 
-from ..storage.shared_store import SharedTensorHandle, cleanup_tensor, open_tensor, register_tensor
+from ..storage.shared_store import (SharedTensorHandle, cleanup_tensor, open_tensor, register_rows,
+                                    register_tensor)
 
 _SHM_MARK = "__BYZ_SHARED_TENSOR__"
+_SHM_BATCH_MARK = "__BYZ_SHARED_TENSOR_BATCH__"
+_BATCH_MIN_BYTES = 1 << 16
+
+
+def _batchable(seq) -> bool:
+    """A list / tuple of >= 2 CPU tensors of one shape and dtype (the honest gradients handed to a Byzantine
+    node, the neighbour vectors of a gossip round): they travel as ONE segment instead of one each."""
+    if len(seq) < 2 or not all(isinstance(t, torch.Tensor) for t in seq):
+        return False
+    first = seq[0]
+    if first.is_cuda or first.numel() == 0 or first.numel() * first.element_size() * len(seq) < _BATCH_MIN_BYTES:
+        return False
+    if first.dtype not in (torch.float32, torch.float64, torch.float16, torch.int64, torch.int32, torch.uint8):
+        return False
+    return all(t.shape == first.shape and t.dtype == first.dtype and not t.is_cuda for t in seq)
 
 
 def wrap_payload(obj: Any) -> Any:
@@ -25,13 +41,23 @@ def wrap_payload(obj: Any) -> Any:
         return (_SHM_MARK, register_tensor(obj))
     if isinstance(obj, tuple) and len(obj) == 2 and obj[0] == _SHM_MARK:
         return obj
+    if isinstance(obj, tuple) and len(obj) == 4 and obj[0] == _SHM_BATCH_MARK:
+        return obj
     if isinstance(obj, tuple) and hasattr(obj, "_fields"):      # namedtuple (e.g. an Endpoint)
         return type(obj)(*(wrap_payload(x) for x in obj))
     if isinstance(obj, (list, tuple)):
+        if type(obj) in (list, tuple) and _batchable(obj):
+            return (_SHM_BATCH_MARK, register_rows(obj), type(obj) is tuple, tuple(obj[0].shape))
         return type(obj)(wrap_payload(x) for x in obj)
     if isinstance(obj, dict):
         return {k: wrap_payload(v) for k, v in obj.items()}
     return obj
+
+
+def _take_batch(handle: SharedTensorHandle, as_tuple: bool, shape) -> Any:
+    stacked = _take(handle)                                  # (n, numel): one copy out, one unlink
+    rows = [r.reshape(shape) for r in stacked.unbind(0)]
+    return tuple(rows) if as_tuple else rows
 
 
 def _take(handle: SharedTensorHandle) -> torch.Tensor:
@@ -44,6 +70,8 @@ def _take(handle: SharedTensorHandle) -> torch.Tensor:
 def unwrap_payload(obj: Any) -> Any:
     if isinstance(obj, tuple) and len(obj) == 2 and obj[0] == _SHM_MARK:
         return _take(obj[1])
+    if isinstance(obj, tuple) and len(obj) == 4 and obj[0] == _SHM_BATCH_MARK:
+        return _take_batch(obj[1], obj[2], obj[3])
     if isinstance(obj, list):
         return [unwrap_payload(x) for x in obj]
     if isinstance(obj, tuple) and hasattr(obj, "_fields"):

@@ -351,3 +351,27 @@ def test_process_actors_share_follows_the_number_of_live_actors(monkeypatch):
     assert two == [4, 4] and one == 8
     monkeypatch.setenv("BYZPY_INTRAOP_GOVERNOR", "0")
     assert proc._thread_share() == 0
+
+
+def test_wrap_payload_batches_equal_tensors_into_one_segment_and_round_trips():
+    from byzpy_b200.engine.actor import ipc
+
+    torch.manual_seed(12)
+    grads = [torch.randn(3, 7000) for _ in range(5)]
+    wrapped = ipc.wrap_payload({"honest_grads": grads, "k": 3, "pair": (grads[0], torch.ones(2))})
+    assert wrapped["honest_grads"][0] == ipc._SHM_BATCH_MARK            # one segment for the five gradients
+    assert wrapped["pair"][0][0] == ipc._SHM_MARK and wrapped["k"] == 3
+    assert ipc.wrap_payload(wrapped["honest_grads"]) is wrapped["honest_grads"]   # idempotent
+    back = ipc.unwrap_payload(wrapped)
+    assert isinstance(back["honest_grads"], list) and len(back["honest_grads"]) == 5
+    for a, b in zip(back["honest_grads"], grads):
+        assert a.shape == (3, 7000) and torch.equal(a, b)
+    assert torch.equal(back["pair"][0], grads[0]) and isinstance(back["pair"], tuple)
+    tup = ipc.unwrap_payload(ipc.wrap_payload(tuple(grads)))
+    assert isinstance(tup, tuple) and torch.equal(tup[4], grads[4])
+    # not batched: mixed dtypes / shapes, tiny tensors, single element
+    for payload in ([grads[0], grads[1].double()], [torch.ones(2), torch.ones(3)], [torch.ones(4), torch.ones(4)], [grads[0]]):
+        w = ipc.wrap_payload(payload)
+        assert isinstance(w, list) and all(x[0] == ipc._SHM_MARK for x in w)
+        for a, b in zip(ipc.unwrap_payload(w), payload):
+            assert torch.equal(a, b) and a.dtype == b.dtype
