@@ -411,8 +411,8 @@ def run_reference(args, rank, world, device):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--model", default="resnet18")
     ap.add_argument("--batch", type=int, default=32, help="per-worker batch")

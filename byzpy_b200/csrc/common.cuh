@@ -58,6 +58,28 @@ __device__ __forceinline__ float ldg_stream1(const float* p) {
   asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
   return r;
 }
+// Streaming loads WITHOUT the non-coherent qualifier: for rows that a peer GPU may still have been
+// writing after this kernel became resident (the fused rounds wait for the producer's flag with
+// ld.acquire.sys inside the kernel; PTX only allows .nc on memory that is read-only for the whole
+// kernel).  Same LDG path and L1 policy as the .nc variants.
+__device__ __forceinline__ float4 ldg_weak4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ float2 ldg_weak2(const float* p) {
+  float2 r;
+  asm volatile("ld.global.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ float ldg_weak1(const float* p) {
+  float r;
+  asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p) : "memory");
+  return r;
+}
 // Coherent (L2) loads for data produced by a peer GPU *during* this kernel.
 __device__ __forceinline__ float4 ldg_cg4(const float* p) {
   float4 r;
@@ -75,6 +97,16 @@ __device__ __forceinline__ void stg_stream4(float* p, float4 v) {
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x),
                "f"(v.y), "f"(v.z), "f"(v.w)
                : "memory");
+}
+// NVLS multicast store: one store to the multicast alias lands in every bound GPU's HBM (the
+// NVSwitch replicates it), replacing `world` peer stores.
+__device__ __forceinline__ void stg_multimem4(float* p, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void stg_multimem1(float* p, float v) {
+  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 __device__ __forceinline__ void stg_stream1(float* p, float v) {
   asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");

@@ -80,30 +80,31 @@ __device__ __forceinline__ float cw_pick(float (&v)[NP], const int nt, const int
   }
 }
 
-template <int NP, int V>
+// NC: rows are read-only for the whole kernel (.nc loads); otherwise plain weak loads (see common.cuh)
+template <int NP, int V, bool NC = true>
 struct VecIO;
-template <int NP>
-struct VecIO<NP, 4> {
+template <int NP, bool NC>
+struct VecIO<NP, 4, NC> {
   static __device__ __forceinline__ void load(const float* p, float (&v)[4][NP], int i, float s) {
-    const float4 t = ldg_stream4(p);
+    const float4 t = NC ? ldg_stream4(p) : ldg_weak4(p);
     v[0][i] = canon(t.x * s);
     v[1][i] = canon(t.y * s);
     v[2][i] = canon(t.z * s);
     v[3][i] = canon(t.w * s);
   }
 };
-template <int NP>
-struct VecIO<NP, 2> {
+template <int NP, bool NC>
+struct VecIO<NP, 2, NC> {
   static __device__ __forceinline__ void load(const float* p, float (&v)[2][NP], int i, float s) {
-    const float2 t = ldg_stream2(p);
+    const float2 t = NC ? ldg_stream2(p) : ldg_weak2(p);
     v[0][i] = canon(t.x * s);
     v[1][i] = canon(t.y * s);
   }
 };
-template <int NP>
-struct VecIO<NP, 1> {
+template <int NP, bool NC>
+struct VecIO<NP, 1, NC> {
   static __device__ __forceinline__ void load(const float* p, float (&v)[1][NP], int i, float s) {
-    v[0][i] = canon(ldg_stream1(p) * s);
+    v[0][i] = canon((NC ? ldg_stream1(p) : ldg_weak1(p)) * s);
   }
 };
 
@@ -184,7 +185,7 @@ __device__ __forceinline__ void cw_finish(float (&v)[V][NP], int n, const VirtRo
 
 // Load the n real values of V consecutive coordinates straight from the row
 // buffers, then finish; returns V results in res[].
-template <int NP, int V, int MODE>
+template <int NP, int V, int MODE, bool NC = true>
 __device__ __forceinline__ void cw_unit(const RowTable& rows, const ScaleTable& scales, int n,
                                         const VirtRows& virt, int f, long long base,
                                         float (&res)[V]) {
@@ -192,7 +193,7 @@ __device__ __forceinline__ void cw_unit(const RowTable& rows, const ScaleTable& 
 #pragma unroll
   for (int i = 0; i < NP; ++i) {
     if (i < n) {
-      VecIO<NP, V>::load(rows.p[i] + base, v, i, scales.s[i]);
+      VecIO<NP, V, NC>::load(rows.p[i] + base, v, i, scales.s[i]);
     } else {
 #pragma unroll
       for (int c = 0; c < V; ++c) v[c][i] = 0.f;

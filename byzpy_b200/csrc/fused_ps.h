@@ -16,12 +16,24 @@ struct BzFusedPsArgs {
   int f;
   int mode;            // BzCwMode
   long long d;         // padded arena length (multiple of 4)
-  long long shard_off, shard_len;  // this rank's coordinate shard (multiples of 4)
+  long long shard_off, shard_len;  // this rank's coordinate shard of the launch's range (multiples of 4)
+  // Coordinate range [rng_off, rng_off + rng_len) this launch aggregates and updates: one gradient
+  // BUCKET.  A round is a sequence of bucket launches in reverse-layer order, each enqueued as soon as
+  // the local backward pass has produced the bucket, so aggregation overlaps the rest of backward.
+  long long rng_off, rng_len;
   int rank, world;
+  uint32_t live_mask;       // bit r set: rank r takes part (0 = all `world` ranks); silent ranks are
+                            // neither waited for nor written to
   float* agg[BZ_MAXW];      // aggregated-gradient buffer of every rank (peer-mapped)
+  float* agg_mc;            // NVLS multicast alias of the agg buffers (one multimem.st reaches every
+                            // rank's HBM through the switch); nullptr -> world peer stores
   uint32_t* pad[BZ_MAXW];   // signal pad of every rank (peer-mapped)
   uint32_t epoch;
   const uint32_t* epoch_ptr;  // optional device-resident epoch (CUDA-graph replay); overrides `epoch`
+  // Flag words carry the monotone sequence number  epoch * seq_mul + seq_add  (bucket b of a round
+  // with nb buckets: seq_mul = nb, seq_add = b), so one word per (kind, rank) serves every bucket.
+  uint32_t seq_mul, seq_add;
+  unsigned long long spin_ns;  // wall-clock budget of every flag wait (0 = default 20 s)
   unsigned int* counter;    // local CTA arrival counter (zero-initialised)
   int* status;              // local error word (0 == ok)
   UpdTable upd;             // local replicas to update in phase 2
@@ -43,6 +55,9 @@ struct BzFlagBarrierArgs {
   int slot;                  // BZ_PAD_READY / BZ_PAD_GRAM / ...
   const uint32_t* epoch_ptr;
   int* status;
+  uint32_t live_mask;        // see BzFusedPsArgs
+  uint32_t seq_mul, seq_add; // flag value = epoch * seq_mul + seq_add (seq_mul 0 -> plain epoch)
+  unsigned long long spin_ns;
 };
 int bz_flag_barrier(const BzFlagBarrierArgs* args, cudaStream_t stream);
 
@@ -55,6 +70,8 @@ struct BzGramExchangeArgs {
   int rank, world, n;
   const uint32_t* epoch_ptr;
   int* status;
+  uint32_t live_mask;
+  unsigned long long spin_ns;
   double* out64;             // (n, n) total
   float* out32;              // (n, n) total (optional)
 };

@@ -32,6 +32,54 @@ T* as_ptr(uint64_t v) {
 }
 cudaStream_t as_stream(uint64_t s) { return reinterpret_cast<cudaStream_t>(static_cast<uintptr_t>(s)); }
 
+// The part of the fused-round argument block shared by the coordinate-wise and weighted-sum kernels.
+void fill_common(BzFusedPsArgs& a, const std::vector<uint64_t>& rows, const std::vector<float>& scales,
+                 long long d, long long shard_off, long long shard_len, int rank,
+                 const std::vector<uint64_t>& agg, const std::vector<uint64_t>& pads, uint32_t epoch,
+                 uint64_t epoch_ptr, uint64_t counter, uint64_t status, const std::vector<uint64_t>& upd_params,
+                 const std::vector<uint64_t>& upd_moms, float lr, float mu, float wd, int grid_limit,
+                 long long rng_off, long long rng_len, uint32_t seq_mul, uint32_t seq_add, uint64_t agg_mc,
+                 uint32_t live_mask, double spin_s) {
+  std::memset(&a, 0, sizeof(a));
+  if (rows.empty() || rows.size() > BZ_MAXN) throw std::invalid_argument("rows");
+  if (agg.size() != pads.size() || agg.empty() || agg.size() > BZ_MAXW) throw std::invalid_argument("agg/pads");
+  for (size_t i = 0; i < BZ_MAXN; ++i) {
+    a.rows.p[i] = i < rows.size() ? as_ptr<const float>(rows[i]) : nullptr;
+    a.scales.s[i] = (i < scales.size()) ? scales[i] : 1.0f;
+  }
+  a.n = (int)rows.size();
+  a.d = d;
+  a.shard_off = shard_off;
+  a.shard_len = shard_len;
+  a.rng_off = rng_off;
+  a.rng_len = rng_len;
+  a.rank = rank;
+  a.world = (int)agg.size();
+  a.live_mask = live_mask;
+  for (size_t p = 0; p < agg.size(); ++p) {
+    a.agg[p] = as_ptr<float>(agg[p]);
+    a.pad[p] = as_ptr<uint32_t>(pads[p]);
+  }
+  a.agg_mc = as_ptr<float>(agg_mc);
+  a.epoch = epoch;
+  a.epoch_ptr = as_ptr<const uint32_t>(epoch_ptr);
+  a.seq_mul = seq_mul;
+  a.seq_add = seq_add;
+  a.spin_ns = (unsigned long long)(spin_s * 1e9);
+  a.counter = as_ptr<unsigned int>(counter);
+  a.status = as_ptr<int>(status);
+  if (upd_params.size() > BZ_MAXR) throw std::invalid_argument("too many replicas");
+  a.upd.count = (int)upd_params.size();
+  for (size_t r = 0; r < upd_params.size(); ++r) {
+    a.upd.param[r] = as_ptr<float>(upd_params[r]);
+    a.upd.mom[r] = upd_moms.empty() ? nullptr : as_ptr<float>(upd_moms[r]);
+  }
+  a.upd.lr = lr;
+  a.upd.mu = mu;
+  a.upd.wd = wd;
+  a.grid_limit = grid_limit;
+}
+
 }  // namespace
 
 void bz_bind_runtime(py::module_& m) {
@@ -102,40 +150,14 @@ void bz_bind_runtime(py::module_& m) {
          long long shard_off, long long shard_len, int rank, const std::vector<uint64_t>& agg,
          const std::vector<uint64_t>& pads, uint64_t epoch_ptr, uint64_t counter, uint64_t status,
          const std::vector<uint64_t>& upd_params, const std::vector<uint64_t>& upd_moms, float lr,
-         float mu, float wd, int sm_count, uint64_t stream, int grid_limit) {
+         float mu, float wd, int sm_count, uint64_t stream, int grid_limit, long long rng_off,
+         long long rng_len, uint32_t seq_mul, uint32_t seq_add, uint64_t agg_mc, uint32_t live_mask,
+         double spin_s) {
         BzFusedPsArgs a;
-        std::memset(&a, 0, sizeof(a));
-        if (rows.empty() || rows.size() > BZ_MAXN) throw std::invalid_argument("rows");
-        if (agg.size() != pads.size() || agg.empty() || agg.size() > BZ_MAXW)
-          throw std::invalid_argument("agg/pads");
-        for (size_t i = 0; i < BZ_MAXN; ++i) {
-          a.rows.p[i] = i < rows.size() ? as_ptr<const float>(rows[i]) : nullptr;
-          a.scales.s[i] = (i < scales.size()) ? scales[i] : 1.0f;
-        }
-        a.n = (int)rows.size();
+        fill_common(a, rows, scales, d, shard_off, shard_len, rank, agg, pads, 0u, epoch_ptr, counter, status,
+                    upd_params, upd_moms, lr, mu, wd, grid_limit, rng_off, rng_len, seq_mul, seq_add, agg_mc,
+                    live_mask, spin_s);
         a.W = as_ptr<const float>(W);
-        a.d = d;
-        a.shard_off = shard_off;
-        a.shard_len = shard_len;
-        a.rank = rank;
-        a.world = (int)agg.size();
-        for (size_t p = 0; p < agg.size(); ++p) {
-          a.agg[p] = as_ptr<float>(agg[p]);
-          a.pad[p] = as_ptr<uint32_t>(pads[p]);
-        }
-        a.epoch_ptr = as_ptr<const uint32_t>(epoch_ptr);
-        a.counter = as_ptr<unsigned int>(counter);
-        a.status = as_ptr<int>(status);
-        if (upd_params.size() > BZ_MAXR) throw std::invalid_argument("too many replicas");
-        a.upd.count = (int)upd_params.size();
-        for (size_t r = 0; r < upd_params.size(); ++r) {
-          a.upd.param[r] = as_ptr<float>(upd_params[r]);
-          a.upd.mom[r] = upd_moms.empty() ? nullptr : as_ptr<float>(upd_moms[r]);
-        }
-        a.upd.lr = lr;
-        a.upd.mu = mu;
-        a.upd.wd = wd;
-        a.grid_limit = grid_limit;
         int e = bz_fused_ps_wsum(&a, sm_count, as_stream(stream));
         if (e != 0)
           throw std::runtime_error(std::string("fused_ps_wsum: CUDA error ") +
@@ -145,26 +167,37 @@ void bz_bind_runtime(py::module_& m) {
       py::arg("shard_len"), py::arg("rank"), py::arg("agg"), py::arg("pads"), py::arg("epoch_ptr"),
       py::arg("counter"), py::arg("status"), py::arg("upd_params"), py::arg("upd_moms"),
       py::arg("lr"), py::arg("mu"), py::arg("wd"), py::arg("sm_count"), py::arg("stream"),
-      py::arg("grid_limit") = 0);
+      py::arg("grid_limit") = 0, py::arg("rng_off") = 0, py::arg("rng_len") = 0, py::arg("seq_mul") = 0,
+      py::arg("seq_add") = 0, py::arg("agg_mc") = 0, py::arg("live_mask") = 0, py::arg("spin_s") = 0.0);
 
-  m.def("flag_barrier", [](const std::vector<uint64_t>& pads, int rank, int slot, uint64_t epoch_ptr,
-                           uint64_t status, uint64_t stream) {
-    BzFlagBarrierArgs a;
-    std::memset(&a, 0, sizeof(a));
-    if (pads.empty() || pads.size() > BZ_MAXW) throw std::invalid_argument("pads");
-    a.world = (int)pads.size();
-    a.rank = rank;
-    a.slot = slot;
-    for (size_t p = 0; p < pads.size(); ++p) a.pad[p] = as_ptr<uint32_t>(pads[p]);
-    a.epoch_ptr = as_ptr<const uint32_t>(epoch_ptr);
-    a.status = as_ptr<int>(status);
-    int e = bz_flag_barrier(&a, as_stream(stream));
-    if (e != 0) throw std::runtime_error("flag_barrier failed");
-  });
+  m.def(
+      "flag_barrier",
+      [](const std::vector<uint64_t>& pads, int rank, int slot, uint64_t epoch_ptr, uint64_t status,
+         uint64_t stream, uint32_t seq_mul, uint32_t seq_add, uint32_t live_mask, double spin_s) {
+        BzFlagBarrierArgs a;
+        std::memset(&a, 0, sizeof(a));
+        if (pads.empty() || pads.size() > BZ_MAXW) throw std::invalid_argument("pads");
+        a.world = (int)pads.size();
+        a.rank = rank;
+        a.slot = slot;
+        for (size_t p = 0; p < pads.size(); ++p) a.pad[p] = as_ptr<uint32_t>(pads[p]);
+        a.epoch_ptr = as_ptr<const uint32_t>(epoch_ptr);
+        a.status = as_ptr<int>(status);
+        a.seq_mul = seq_mul;
+        a.seq_add = seq_add;
+        a.live_mask = live_mask;
+        a.spin_ns = (unsigned long long)(spin_s * 1e9);
+        int e = bz_flag_barrier(&a, as_stream(stream));
+        if (e != 0) throw std::runtime_error("flag_barrier failed");
+      },
+      py::arg("pads"), py::arg("rank"), py::arg("slot"), py::arg("epoch_ptr"), py::arg("status"),
+      py::arg("stream"), py::arg("seq_mul") = 0, py::arg("seq_add") = 0, py::arg("live_mask") = 0,
+      py::arg("spin_s") = 0.0);
 
   m.def("gram_exchange", [](uint64_t local, const std::vector<uint64_t>& slots,
                             const std::vector<uint64_t>& pads, int rank, int n, uint64_t epoch_ptr,
-                            uint64_t status, uint64_t out64, uint64_t out32, uint64_t stream) {
+                            uint64_t status, uint64_t out64, uint64_t out32, uint64_t stream,
+                            uint32_t live_mask, double spin_s) {
     BzGramExchangeArgs a;
     std::memset(&a, 0, sizeof(a));
     if (slots.size() != pads.size() || slots.empty() || slots.size() > BZ_MAXW)
@@ -181,9 +214,13 @@ void bz_bind_runtime(py::module_& m) {
     a.status = as_ptr<int>(status);
     a.out64 = as_ptr<double>(out64);
     a.out32 = as_ptr<float>(out32);
+    a.live_mask = live_mask;
+    a.spin_ns = (unsigned long long)(spin_s * 1e9);
     int e = bz_gram_exchange(&a, as_stream(stream));
     if (e != 0) throw std::runtime_error("gram_exchange failed");
-  });
+  }, py::arg("local"), py::arg("slots"), py::arg("pads"), py::arg("rank"), py::arg("n"), py::arg("epoch_ptr"),
+     py::arg("status"), py::arg("out64"), py::arg("out32"), py::arg("stream"), py::arg("live_mask") = 0,
+     py::arg("spin_s") = 0.0);
   m.attr("PAD_READY") = BZ_PAD_READY;
   m.attr("PAD_DONE") = BZ_PAD_DONE;
   m.attr("PAD_GRAM") = BZ_PAD_GRAM;
@@ -202,46 +239,19 @@ void bz_bind_runtime(py::module_& m) {
          long long shard_len, int rank, const std::vector<uint64_t>& agg,
          const std::vector<uint64_t>& pads, uint32_t epoch, uint64_t epoch_ptr, uint64_t counter, uint64_t status,
          const std::vector<uint64_t>& upd_params, const std::vector<uint64_t>& upd_moms, float lr,
-         float mu, float wd, int sm_count, uint64_t stream, int grid_limit) {
+         float mu, float wd, int sm_count, uint64_t stream, int grid_limit, long long rng_off,
+         long long rng_len, uint32_t seq_mul, uint32_t seq_add, uint64_t agg_mc, uint32_t live_mask,
+         double spin_s) {
         BzFusedPsArgs a;
-        std::memset(&a, 0, sizeof(a));
-        if (rows.empty() || rows.size() > BZ_MAXN) throw std::invalid_argument("rows");
-        if (agg.size() != pads.size() || agg.empty() || agg.size() > BZ_MAXW)
-          throw std::invalid_argument("agg/pads");
-        for (size_t i = 0; i < BZ_MAXN; ++i) {
-          a.rows.p[i] = i < rows.size() ? as_ptr<const float>(rows[i]) : nullptr;
-          a.scales.s[i] = (i < scales.size()) ? scales[i] : 1.0f;
-        }
-        a.n = (int)rows.size();
+        fill_common(a, rows, scales, d, shard_off, shard_len, rank, agg, pads, epoch, epoch_ptr, counter, status,
+                    upd_params, upd_moms, lr, mu, wd, grid_limit, rng_off, rng_len, seq_mul, seq_add, agg_mc,
+                    live_mask, spin_s);
         a.virt.count = n_virtual;
         a.virt.n_honest = n_honest;
         a.virt.a = va;
         a.virt.b = vb;
         a.f = f;
         a.mode = mode;
-        a.d = d;
-        a.shard_off = shard_off;
-        a.shard_len = shard_len;
-        a.rank = rank;
-        a.world = (int)agg.size();
-        for (size_t p = 0; p < agg.size(); ++p) {
-          a.agg[p] = as_ptr<float>(agg[p]);
-          a.pad[p] = as_ptr<uint32_t>(pads[p]);
-        }
-        a.epoch = epoch;
-        a.epoch_ptr = as_ptr<const uint32_t>(epoch_ptr);
-        a.counter = as_ptr<unsigned int>(counter);
-        a.status = as_ptr<int>(status);
-        if (upd_params.size() > BZ_MAXR) throw std::invalid_argument("too many replicas");
-        a.upd.count = (int)upd_params.size();
-        for (size_t r = 0; r < upd_params.size(); ++r) {
-          a.upd.param[r] = as_ptr<float>(upd_params[r]);
-          a.upd.mom[r] = upd_moms.empty() ? nullptr : as_ptr<float>(upd_moms[r]);
-        }
-        a.upd.lr = lr;
-        a.upd.mu = mu;
-        a.upd.wd = wd;
-        a.grid_limit = grid_limit;
         int e = bz_fused_ps_cw(&a, sm_count, as_stream(stream));
         if (e != 0)
           throw std::runtime_error(std::string("fused_ps_cw: CUDA error ") +
@@ -252,5 +262,6 @@ void bz_bind_runtime(py::module_& m) {
       py::arg("shard_len"), py::arg("rank"), py::arg("agg"), py::arg("pads"), py::arg("epoch"), py::arg("epoch_ptr"),
       py::arg("counter"), py::arg("status"), py::arg("upd_params"), py::arg("upd_moms"),
       py::arg("lr"), py::arg("mu"), py::arg("wd"), py::arg("sm_count"), py::arg("stream"),
-      py::arg("grid_limit") = 0);
+      py::arg("grid_limit") = 0, py::arg("rng_off") = 0, py::arg("rng_len") = 0, py::arg("seq_mul") = 0,
+      py::arg("seq_add") = 0, py::arg("agg_mc") = 0, py::arg("live_mask") = 0, py::arg("spin_s") = 0.0);
 }

@@ -55,9 +55,15 @@ class ParameterServer:
                  weight_decay: Optional[float] = None, amp_dtype: Optional[torch.dtype] = torch.bfloat16,
                  use_cuda_graph: bool = True, worker_streams: int = 1, fused: Optional[bool] = None,
                  node_timeout: Optional[float] = None, tolerate_failures: bool = False,
-                 direct_grads: bool = True, overlap_wgrad: bool = True, branch_streams: bool = True):
+                 direct_grads: bool = True, overlap_wgrad: bool = True, branch_streams: bool = True,
+                 buckets: Optional[int] = None, multicast: Optional[bool] = None,
+                 device_options: Optional[dict] = None):
+        # ``buckets``: gradient buckets of the fused round (None = automatic, 1 = one launch after
+        # backward); ``multicast``: NVLS multicast broadcast (None = when the heap supports it);
+        # ``device_options``: further DeviceRound keyword arguments (bucket_cuts, spin_seconds, ...)
         self._device_opts = dict(direct_grads=direct_grads, overlap_wgrad=overlap_wgrad,
-                                 branch_streams=branch_streams)
+                                 branch_streams=branch_streams, buckets=buckets, multicast=multicast,
+                                 **(device_options or {}))
         self.hon = list(honest_nodes)
         self.byz = list(byzantine_nodes)
         self.agg = aggregator

@@ -467,6 +467,66 @@ class FusedMaxPool2d(nn.MaxPool2d):
         return super().forward(x)
 
 
+# --------------------------------------------------------------------------- gradient buckets
+class _BucketMark(torch.autograd.Function):
+    """Identity in forward.  Its backward runs when the gradient with respect to this activation
+    exists, i.e. when every layer downstream of it has finished its backward: all parameter
+    gradients of those layers have been issued (AccumulateGrad nodes run before lower-priority
+    nodes, direct-gradient layers enqueue theirs inside their own backward).  The callback turns
+    that moment into CUDA events the round engine's aggregation stream waits on."""
+
+    @staticmethod
+    def forward(ctx, x, callback, index):
+        ctx.callback, ctx.index = callback, index
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        ctx.callback(ctx.index)
+        return g, None, None
+
+
+def install_bucket_marks(marks, callback):
+    """``marks`` = [(module, bucket index)]: wrap each module's first positional input in a
+    :class:`_BucketMark`.  Returns the hook handles (``h.remove()`` uninstalls)."""
+    handles = []
+    for module, index in marks:
+        def pre(mod, args, _i=index):
+            if not args or not isinstance(args[0], torch.Tensor) or not args[0].requires_grad \
+                    or not torch.is_grad_enabled():
+                return None
+            return (_BucketMark.apply(args[0], callback, _i),) + tuple(args[1:])
+        handles.append(module.register_forward_pre_hook(pre))
+    return handles
+
+
+def bucket_candidates(model: nn.Module, offsets) -> list:
+    """[(first flat offset, module)] of the model's blocks in registration (= execution) order: the
+    top-level children, with ``Sequential`` / ``ModuleList`` containers opened one level (residual
+    stages -> blocks, encoder -> layers).  ``offsets`` = ``ParamArena.offsets``."""
+    off_of = {id(p): off for p, (off, _, _) in zip(model.parameters(), offsets)}
+
+    def first(m):
+        for p in m.parameters():
+            return off_of.get(id(p))
+        return None
+
+    out = []
+    for child in model.children():
+        subs = list(child.children()) if isinstance(child, (nn.Sequential, nn.ModuleList)) else []
+        for m in (subs or [child]):
+            fo = first(m)
+            if fo is not None:
+                out.append((fo, m))
+    # keep only a strictly increasing chain (a module registered out of execution order is skipped)
+    chain, last = [], -1
+    for fo, m in out:
+        if fo > last:
+            chain.append((fo, m))
+            last = fo
+    return chain
+
+
 # --------------------------------------------------------------------------- switch
 def enable_direct_grads(module: nn.Module, *, side_stream: Optional["torch.cuda.Stream"] = None,
                         enabled: bool = True, branch_stream: Optional["torch.cuda.Stream"] = None) -> GradSink:
@@ -494,4 +554,4 @@ def enable_direct_grads(module: nn.Module, *, side_stream: Optional["torch.cuda.
 
 
 __all__ = ["ArenaConv2d", "ArenaLinear", "FusedMaxPool2d", "GradSink", "enable_direct_grads", "S2DStemConv2d",
-           "PackedStemInput", "pack_stem_input"]
+           "PackedStemInput", "pack_stem_input", "install_bucket_marks", "bucket_candidates"]

@@ -100,6 +100,8 @@ class DeviceWorker:
         self.buf = 0
         self.loss_slot: Optional[torch.Tensor] = None
         self.sink = None            # ops.fused_layers.GradSink once direct gradients are on
+        self._mark_handles: list = []
+        self._mark_sink: Optional[Callable] = None   # DeviceRound callback (worker, bucket, events)
 
     # filled in by the engine
     def bind(self, flat_params: torch.Tensor, flat_grads: torch.Tensor, mom: Optional[torch.Tensor],
@@ -116,6 +118,44 @@ class DeviceWorker:
         from ..ops.fused_layers import enable_direct_grads
 
         self.sink = enable_direct_grads(self.model, side_stream=side_stream, branch_stream=branch_stream)
+
+    # ---- gradient buckets (DeviceRound overlaps the aggregation of a bucket with the rest of backward)
+    def bucket_candidates(self):
+        from ..ops.fused_layers import bucket_candidates
+
+        return bucket_candidates(self.model, self.arena.offsets)
+
+    def install_marks(self, marks, sink_cb: Callable) -> None:
+        """``marks`` = [(module, bucket index)]; ``sink_cb(worker, bucket, events)`` is invoked from
+        inside backward when every parameter gradient at or beyond the module has been issued."""
+        from ..ops.fused_layers import install_bucket_marks
+
+        self.remove_marks()
+        self._mark_sink = sink_cb
+        self._mark_handles = install_bucket_marks(marks, self._on_mark)
+
+    def remove_marks(self) -> None:
+        for h in self._mark_handles:
+            h.remove()
+        self._mark_handles = []
+        self._mark_sink = None
+
+    def _on_mark(self, index: int) -> None:
+        if self._mark_sink is None:
+            return
+        dev = self.arena.flat_params.device
+        events = []
+        sink = self.sink
+        if sink is not None:
+            sink.flush_pending(force=True)      # weight gradients produced so far -> arena row (side stream)
+            if sink._forked and sink.side_stream is not None:
+                ev = torch.cuda.Event()
+                ev.record(sink.side_stream)
+                events.append(ev)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        events.append(ev)
+        self._mark_sink(self, index, events)
 
     @property
     def static_x(self) -> Optional[torch.Tensor]:
@@ -212,6 +252,45 @@ class RowLayout:
         return max((self.slot_of[g] + 1 for g in range(self.n_workers)), default=0)
 
 
+# ------------------------------------------------------------------------- buckets
+def pick_bucket_offsets(block_offsets: Sequence[int], d: int, cuts: Sequence[float],
+                        buckets: Optional[int] = None) -> List[int]:
+    """Block offsets (descending) at which the gradient arena is cut into buckets.
+
+    ``block_offsets``: first flat offset of every block of the model, ascending (execution order).
+    Walking from the tail of the arena -- the layers backward finishes first -- a cut is placed at
+    the first block input after which at least ``cuts[i]`` of the gradient lies behind it."""
+    offs = list(block_offsets)
+    want = list(cuts)
+    if buckets is not None:
+        want = want[: max(0, buckets - 1)]
+    picks: List[int] = []
+    ci = len(offs) - 1
+    for frac in want:
+        while ci >= 1 and (d - offs[ci]) < frac * d:
+            ci -= 1
+        if ci < 1:
+            break
+        picks.append(offs[ci])
+        ci -= 1
+    return picks
+
+
+def bucket_bounds(cut_offsets: Sequence[int], d_pad: int, min_bucket: int, align: int = 1024) -> List[int]:
+    """``[d_pad, b1, b2, ..., 0]``: bucket k covers ``[bounds[k+1], bounds[k])``.  Cuts are rounded UP
+    to ``align`` elements (the few leading elements of the block at a boundary then belong to the
+    next, later bucket -- always safe); cuts that would leave a bucket under ``min_bucket`` elements
+    are dropped."""
+    bounds = [d_pad]
+    for off in cut_offsets:                                    # descending
+        b = padded_size(off, align)
+        if b <= 0 or bounds[-1] - b < min_bucket or b < min_bucket:
+            continue
+        bounds.append(b)
+    bounds.append(0)
+    return bounds
+
+
 # -------------------------------------------------------------------------- engine
 class DeviceRound:
     """Owns the symmetric arenas and launches the fused round on this rank."""
@@ -222,7 +301,10 @@ class DeviceRound:
                  group=None, amp_dtype: Optional[torch.dtype] = torch.bfloat16,
                  use_cuda_graph: bool = True, worker_streams: int = 1,
                  virtual_fold: Optional[RowFold] = None, direct_grads: bool = True,
-                 overlap_wgrad: bool = True, branch_streams: bool = True):
+                 overlap_wgrad: bool = True, branch_streams: bool = True,
+                 buckets: Optional[int] = None, bucket_cuts: Sequence[float] = (0.40, 0.75, 0.93),
+                 min_bucket: int = 1 << 16, overlap_grid: Optional[int] = None,
+                 spin_seconds: float = 0.0, multicast: Optional[bool] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("DeviceRound needs a CUDA device (B200)")
         # replica shapes are static for the lifetime of a round engine (they are baked into its CUDA
@@ -283,6 +365,10 @@ class DeviceRound:
                      if self.momentum != 0.0 else None)
         self.losses = torch.zeros(L, dtype=torch.float32, device=self.device)
         self.losses_host = torch.zeros(L, dtype=torch.float32).pin_memory()
+        self._status_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._round_launches = 0
+        self._use_buckets = False
+        self._in_round = False
         for i, w in enumerate(self.workers):
             w.model.to(self.device)
             w.bind(self.params[i], self.grads[i], None if self.moms is None else self.moms[i],
@@ -316,6 +402,19 @@ class DeviceRound:
         self._gram_ws = None
         self.launches_per_step = 0
         self.model_launches_per_step = 0
+        self.spin_seconds = float(spin_seconds)
+        self.live_mask = 0                      # 0 = every rank takes part (see recover())
+        self._agg_stream = torch.cuda.Stream(self.device)
+        self._agg_mc = self.sym.mc_ptr(self._off_agg) if (multicast is not False) else 0
+        if multicast and not self._agg_mc:
+            raise RuntimeError("multicast=True but the symmetric heap has no NVLS multicast mapping")
+        # overlapped bucket launches share the SMs with backward: one CTA per SM keeps NVLink busy
+        # (32 KB of 16-byte loads in flight per SM) without taking the register file from cuDNN
+        self.overlap_grid = int(overlap_grid) if overlap_grid is not None else (self.sm if self.world > 1 else 2 * self.sm)
+        self._bounds: List[int] = [0, self.d_pad]     # bucket k = [bounds[k+1], bounds[k]) walking from the tail
+        self._buckets_validated = True
+        if isinstance(plan, CwPlan) and (buckets is None or buckets > 1):
+            self._plan_buckets(buckets, bucket_cuts, min_bucket)
         if isinstance(plan, GramPlan):
             self._setup_gram_plan()
             if not plan.capturable:
@@ -323,6 +422,76 @@ class DeviceRound:
         if self.world > 1:
             dist.barrier(group=group)
         torch.cuda.synchronize(self.device)
+
+    # ----------------------------------------------------------------- buckets
+    @property
+    def n_buckets(self) -> int:
+        return len(self._bounds) - 1
+
+    def bucket_range(self, k: int) -> Tuple[int, int]:
+        """(offset, length) of bucket k; bucket 0 is the TAIL of the arena (the layers whose
+        gradients backward produces first), the last bucket starts at offset 0."""
+        hi, lo = self._bounds[k], self._bounds[k + 1]
+        return lo, hi - lo
+
+    def _plan_buckets(self, buckets: Optional[int], cuts: Sequence[float], min_bucket: int) -> None:
+        """Choose bucket boundaries at block inputs of the replica model and install the backward
+        marks.  ``cuts`` are cumulative fractions of the gradient (from the tail) after which a
+        boundary is placed at the next block input; ``buckets`` caps their number."""
+        local = None
+        if self.L:
+            offs = [fo for fo, _ in self.workers[0].bucket_candidates()]     # ascending block offsets
+            local = pick_bucket_offsets(offs, self.d, cuts, buckets)
+        if self.world > 1:
+            allb: List[Optional[list]] = [None] * self.world
+            dist.all_gather_object(allb, local, group=self.group)
+            known = [b for b in allb if b is not None]
+            if any(b != known[0] for b in known):
+                raise RuntimeError("ranks disagree on gradient bucket boundaries (different replica models?)")
+            chosen = known[0]
+        else:
+            chosen = local or []
+        bounds = bucket_bounds(chosen, self.d_pad, min_bucket)
+        self._bounds = bounds
+        if self.n_buckets > 1:
+            self._buckets_validated = False
+            if self.L:
+                # a mark sits at the input of the FIRST block of a bucket's range: when its backward
+                # fires, everything at or beyond the (rounded-up) boundary has been produced
+                by_bound: dict = {}
+                for fo in chosen:                   # descending: the later block wins a shared boundary
+                    by_bound.setdefault(padded_size(fo, 1024), fo)
+                for w in self.workers:
+                    cw = w.bucket_candidates()
+                    marks = []
+                    for k in range(self.n_buckets - 1):
+                        fo = by_bound[self._bounds[k + 1]]
+                        mod = next(m for off, m in cw if off == fo)
+                        marks.append((mod, k))
+                    w.install_marks(marks, self._on_mark)
+        self._bk_events: List[list] = [[] for _ in range(self.n_buckets)]
+        self._bk_count = [0] * self.n_buckets
+        self._next_bucket = 0
+        self._in_round = False
+        self._use_buckets = self.n_buckets > 1
+
+    def _on_mark(self, worker: DeviceWorker, k: int, events: list) -> None:
+        if not self._in_round or not self._use_buckets:
+            return
+        self._bk_events[k].extend(events)
+        self._bk_count[k] += 1
+        self._launch_ready_buckets()
+
+    def _launch_ready_buckets(self) -> None:
+        """Enqueue, in bucket order, every bucket all local replicas have produced."""
+        agg = self._agg_stream
+        while self._next_bucket < self.n_buckets - 1 and self._bk_count[self._next_bucket] >= self.L:
+            k = self._next_bucket
+            for ev in self._bk_events[k]:
+                agg.wait_event(ev)
+            with torch.cuda.stream(agg):
+                self._launch_cw_bucket(k, self.overlap_grid)
+            self._next_bucket += 1
 
     # ------------------------------------------------------------------ tables
     def _row_table(self) -> Tuple[List[int], List[float]]:
@@ -363,24 +532,54 @@ class DeviceRound:
             return lay.n_virtual, lay.n_honest, self.virtual_fold.a, self.virtual_fold.b
         return 0, 0, 0.0, 0.0
 
+    def _shard(self, off: int, ln: int) -> Tuple[int, int]:
+        """This rank's share of the coordinate range [off, off + ln) (multiples of 4 elements)."""
+        live = [r for r in range(self.world) if self.live_mask == 0 or (self.live_mask >> r) & 1]
+        idx = live.index(self.rank)
+        sh = (ln // len(live)) // 4 * 4
+        s_off = off + idx * sh
+        s_len = sh if idx < len(live) - 1 else ln - sh * (len(live) - 1)
+        return s_off, s_len
+
+    def _launch_cw_bucket(self, k: int, grid_limit: int = 0, *, whole: bool = False) -> None:
+        """One fused launch (gather + select + broadcast + SGD) over bucket k -- or over the whole
+        arena with ``whole`` -- on the current stream.  The epoch word must already be bumped."""
+        plan = self.plan
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        ctl = self.ctl.data_ptr()
+        nv, nh, va, vb = self._virtual()
+        # flag words carry epoch * n_buckets + bucket: the numbering never changes over the life of
+        # the engine (a whole-arena launch counts as the round's last bucket), so sequence numbers
+        # stay monotone when overlapped and single-launch rounds are mixed
+        nb = self.n_buckets
+        if whole or nb == 1:
+            off, ln, k = 0, self.d_pad, nb - 1
+        else:
+            off, ln = self.bucket_range(k)
+        s_off, s_len = self._shard(off, ln)
+        self.ext.fused_ps_cw(
+            self._rows, self._scales, plan.mode, plan.f, nv, nh, va, vb, self.d_pad,
+            s_off, s_len, self.rank,
+            [self.sym.peer_ptr(r, self._off_agg) for r in range(self.world)],
+            [self.sym.peer_ptr(r, self._off_pad) for r in range(self.world)],
+            0, ctl + 8, ctl + 0, ctl + 4,
+            self._upd_params, self._upd_moms, self.lr, self.momentum, self.weight_decay,
+            self.sm, stream, grid_limit, off, ln, nb, k, self._agg_mc,
+            self.live_mask, self.spin_seconds,
+        )
+        self._round_launches += 1
+
     def launch_aggregate(self) -> None:
-        """Enqueue the fused gather+aggregate+broadcast+update on the current stream."""
+        """Enqueue the fused gather+aggregate+broadcast+update on the current stream (one launch
+        over the whole arena for the coordinate-wise family: the non-overlapped form of the round)."""
         stream = torch.cuda.current_stream(self.device).cuda_stream
         ctl = self.ctl.data_ptr()
         self.ext.bump_u32(ctl + 8, stream)
         plan = self.plan
-        nv, nh, va, vb = self._virtual()
         if isinstance(plan, CwPlan):
-            self.ext.fused_ps_cw(
-                self._rows, self._scales, plan.mode, plan.f, nv, nh, va, vb, self.d_pad,
-                self.shard_off, self.shard_len, self.rank,
-                [self.sym.peer_ptr(r, self._off_agg) for r in range(self.world)],
-                [self.sym.peer_ptr(r, self._off_pad) for r in range(self.world)],
-                0, ctl + 8, ctl + 0, ctl + 4,
-                self._upd_params, self._upd_moms, self.lr, self.momentum, self.weight_decay,
-                self.sm, stream,
-            )
-            self.launches_per_step = 2
+            self._round_launches = 1
+            self._launch_cw_bucket(0, whole=True)
+            self.launches_per_step = self._round_launches
         elif isinstance(plan, GramPlan):
             self._launch_gram_round(stream, ctl)
         else:
@@ -483,6 +682,37 @@ class DeviceRound:
     def _body(self) -> None:
         main = torch.cuda.current_stream(self.device)
         l0 = ops.launches()
+        bucketed = isinstance(self.plan, CwPlan) and self._use_buckets
+        if bucketed:
+            # the round's epoch is bumped up front: bucket launches are enqueued from inside backward
+            self.ext.bump_u32(self.ctl.data_ptr() + 8, main.cuda_stream)
+            self._round_launches = 1
+            self._agg_stream.wait_stream(main)
+            self._bk_events = [[] for _ in range(self.n_buckets)]
+            self._bk_count = [0] * self.n_buckets
+            self._next_bucket = 0
+            self._in_round = True
+        try:
+            self._run_replicas(main)
+        finally:
+            self._in_round = False
+        self.model_launches_per_step = ops.launches() - l0   # this library's BN / pooling kernels
+        if not bucketed:
+            self.launch_aggregate()
+            return
+        # buckets whose mark never fired (or ranks without a replica) and the head bucket: after the
+        # whole backward pass, on the aggregation stream, full grid
+        agg = self._agg_stream
+        agg.wait_stream(main)
+        with torch.cuda.stream(agg):
+            while self._next_bucket < self.n_buckets:
+                last = self._next_bucket == self.n_buckets - 1
+                self._launch_cw_bucket(self._next_bucket, 0 if last else self.overlap_grid)
+                self._next_bucket += 1
+        main.wait_stream(agg)
+        self.launches_per_step = self._round_launches
+
+    def _run_replicas(self, main) -> None:
         if self._side_streams:
             streams = [main] + self._side_streams
             for s in self._side_streams:
@@ -495,8 +725,61 @@ class DeviceRound:
         else:
             for w in self.workers:
                 w.forward_backward(self.amp_dtype)
-        self.model_launches_per_step = ops.launches() - l0   # this library's BN / pooling kernels
-        self.launch_aggregate()
+
+    # ---------------------------------------------------------------- bucket validation
+    def _snapshot(self):
+        return (self.params.clone(), None if self.moms is None else self.moms.clone(),
+                [[b.clone() for b in w.model.buffers()] for w in self.workers])
+
+    def _restore(self, snap) -> None:
+        snap_p, snap_m, snap_b = snap
+        with torch.no_grad():
+            self.params.copy_(snap_p)
+            if snap_m is not None:
+                self.moms.copy_(snap_m)
+            for w, bufs in zip(self.workers, snap_b):
+                for b, saved in zip(w.model.buffers(), bufs):
+                    b.copy_(saved)
+
+    def _validate_buckets(self) -> None:
+        """Run the same round twice from the same state -- one launch over the whole arena after
+        backward, then the overlapped bucket sequence -- and compare the aggregates.  A bucket
+        launched before all of its gradients exist (a model whose execution order differs from its
+        registration order) reads the zeroed arena and shows up here; the round then falls back to
+        the single launch.  Both rounds are rolled back."""
+        self._buckets_validated = True
+        if not (isinstance(self.plan, CwPlan) and self._use_buckets):
+            return
+        snap = self._snapshot()
+        s = torch.cuda.Stream(self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            self._use_buckets = False
+            self._body()
+            ref = self.agg.clone()
+            s.synchronize()
+            self._restore(snap)
+            self._use_buckets = True
+            self._body()
+            got = self.agg.clone()
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        self._restore(snap)
+        scale = ref.abs().max().clamp_min(1e-30)
+        bad = torch.tensor([float(not torch.allclose(got, ref, rtol=5e-2, atol=float(scale) * 1e-3))],
+                           device=self.device)
+        if self.world > 1:
+            dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=self.group)
+        if bad.item() != 0.0:
+            import warnings
+
+            warnings.warn("gradient-bucket overlap disabled: the bucketed round did not reproduce the "
+                          "single-launch aggregate (the model's backward order does not follow its "
+                          "parameter order)")
+            self._use_buckets = False
+            for w in self.workers:
+                w.remove_marks()
+        torch.cuda.synchronize(self.device)
 
     def capture(self, warmup: int = 2) -> None:
         """Warm up eagerly on a side stream, then capture the whole round in a CUDA graph."""
@@ -505,9 +788,9 @@ class DeviceRound:
                 raise RuntimeError("stage a batch on every worker before capture()")
         # Warm-up rounds are real rounds: snapshot the training state and restore it afterwards
         # so that capture() is invisible to the optimisation trajectory.
-        snap_p = self.params.clone()
-        snap_m = None if self.moms is None else self.moms.clone()
-        snap_b = [[b.clone() for b in w.model.buffers()] for w in self.workers]
+        if not self._buckets_validated:
+            self._validate_buckets()
+        snap = self._snapshot()
         s = torch.cuda.Stream(self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
@@ -522,13 +805,7 @@ class DeviceRound:
         with torch.cuda.graph(g, **({"pool": other.pool()} if other is not None else {})):
             self._body()
         self._graphs[self._buf] = g
-        with torch.no_grad():
-            self.params.copy_(snap_p)
-            if snap_m is not None:
-                self.moms.copy_(snap_m)
-            for w, bufs in zip(self.workers, snap_b):
-                for b, saved in zip(w.model.buffers(), bufs):
-                    b.copy_(saved)
+        self._restore(snap)
         torch.cuda.synchronize(self.device)
 
     # --------------------------------------------------------------------- step
@@ -572,6 +849,8 @@ class DeviceRound:
                 self.capture()
             self._graphs[b].replay()
         else:
+            if not self._buckets_validated:
+                self._validate_buckets()
             self._body()
         self._consumed[b].record(main)
         if (not explicit) and prefetch and all(w.data is not None for w in self.workers):
@@ -591,16 +870,42 @@ class DeviceRound:
         return self.losses
 
     def read_losses(self) -> torch.Tensor:
-        """Device->host read of the round's losses (synchronises the stream)."""
+        """Device->host read of the round's losses (synchronises the stream).  The fused kernels'
+        status word rides along in the same copy: a flag-wait timeout raises here instead of
+        leaving a training loop running on frozen replicas."""
+        self._status_host.copy_(self.ctl[1:2], non_blocking=True)
         self.losses_host.copy_(self.losses, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
+        self._raise_on_status(int(self._status_host.item()))
         return self.losses_host
 
-    def check_status(self) -> None:
-        st = int(self.ctl[1].item())
+    _STATUS_BITS = {1: "gradient-ready wait", 2: "delivery wait", 4: "flag barrier", 8: "Gram exchange"}
+
+    @staticmethod
+    def decode_status(st: int) -> Tuple[List[str], List[int]]:
+        """(names of the waits that timed out, ranks that did not arrive)."""
+        kinds = [name for bit, name in DeviceRound._STATUS_BITS.items() if st & bit]
+        ranks = [r for r in range(8) if (st >> (8 + r)) & 1]
+        return kinds, ranks
+
+    def _raise_on_status(self, st: int) -> None:
         if st != 0:
-            raise RuntimeError(f"fused PS kernel reported error {st} (1=gradient-ready timeout, "
-                               f"2=delivery timeout)")
+            kinds, ranks = self.decode_status(st)
+            raise RuntimeError(f"fused PS round failed on rank {self.rank}: status {st:#x} "
+                               f"({', '.join(kinds) or 'wait'} timed out; silent ranks {ranks}). The status "
+                               f"is sticky: later rounds skip aggregation until reset_status() or recover().")
+
+    def status(self) -> int:
+        return int(self.ctl[1].item())
+
+    def check_status(self) -> None:
+        self._raise_on_status(self.status())
+
+    def reset_status(self) -> None:
+        """Clear the sticky error word (after the cause of a timeout has been dealt with)."""
+        torch.cuda.synchronize(self.device)
+        self.ctl[0:2].zero_()
+        torch.cuda.synchronize(self.device)
 
     def aggregated(self) -> torch.Tensor:
         return self.agg[: self.d]
@@ -610,4 +915,5 @@ class DeviceRound:
         self.sym.close()
 
 
-__all__ = ["CwPlan", "GramPlan", "RowFold", "DeviceWorker", "RowLayout", "DeviceRound"]
+__all__ = ["CwPlan", "GramPlan", "RowFold", "DeviceWorker", "RowLayout", "DeviceRound", "pick_bucket_offsets",
+           "bucket_bounds"]

@@ -86,6 +86,11 @@ class SymmetricBuffer:
     def peer_ptr(self, rank: int, offset_bytes: int = 0) -> int:
         return self.ptrs[rank] + offset_bytes
 
+    def mc_ptr(self, offset_bytes: int = 0) -> int:
+        """Address of the NVLS multicast alias of the buffer (a ``multimem.st`` there lands in every
+        rank's copy), or 0 when the heap has no multicast mapping."""
+        return (self.mc_base + offset_bytes) if getattr(self, "mc_base", 0) else 0
+
     def close(self) -> None:
         if self._closed:
             return

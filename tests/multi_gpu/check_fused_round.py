@@ -4,8 +4,10 @@ Launch:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-
              --master-port 29533 tests/multi_gpu/check_fused_round.py [--agg median|trmean|meamed]
 
 Every rank hosts 8/N TinyNet replicas; after each round the fused kernel's aggregate (delivered
-into every rank's buffer by peer stores) is compared with an NCCL all_gather + PyTorch reference
-of the same math, and the updated parameters with a plain torch SGD loop.
+into every rank's buffer by peer / multicast stores) is compared with an INDEPENDENT oracle: the
+local gradients of mirror models are exchanged with an NCCL all_gather and aggregated on the host
+in float64 with plain torch algebra (tests/multi_gpu/oracle.py -- none of this repo's operators),
+and the updated parameters with a plain torch SGD loop.
 """
 import argparse
 import os
@@ -16,6 +18,9 @@ import torch.distributed as dist
 import torch.nn as nn
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+import oracle  # noqa: E402
 
 from byzpy_b200.aggregators.coordinate_wise import (CoordinateWiseMedian, CoordinateWiseTrimmedMean,  # noqa: E402
                                                      MeanOfMedians)
@@ -48,6 +53,10 @@ def main():
     ap.add_argument("--attack", default="signflip", choices=["signflip", "little"])
     ap.add_argument("--workers", type=int, default=8,
                     help="total rows; need not divide the world size (RowLayout.spread)")
+    ap.add_argument("--buckets", type=int, default=0,
+                    help="0 = engine default; k > 1 forces small gradient buckets so the overlapped "
+                         "bucket protocol (per-bucket sequence numbers) is exercised across ranks")
+    ap.add_argument("--multicast", type=int, default=-1, help="-1 auto, 0 peer stores, 1 require NVLS multicast")
     a = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -82,8 +91,14 @@ def main():
     pre = Bucketing(2, perm=[3, 0, 6, 1, 7, 2, 5, 4]) if a.agg == "bucket_krum" else None
     if virtual:
         byz = [DeviceByzantineNode(LittleAttack(f=n_byz), device=str(dev)) for _ in range(n_byz)]
+    opts_dev = {}
+    if a.buckets > 1:
+        opts_dev = dict(min_bucket=2048, bucket_cuts=tuple((i + 1) / a.buckets for i in range(a.buckets - 1)))
     ps = ParameterServer(hon, byz, agg, pre_aggregator=pre, update_byzantines=True, layout=layout,
-                         amp_dtype=None, use_cuda_graph=bool(a.graph), fused=True, lr=0.1, momentum=0.9)
+                         amp_dtype=None, use_cuda_graph=bool(a.graph), fused=True, lr=0.1, momentum=0.9,
+                         multicast=None if a.multicast < 0 else bool(a.multicast), device_options=opts_dev)
+    if a.buckets > 1 and a.agg in ("median", "trmean", "meamed"):
+        assert ps.device_round.n_buckets > 1, ps.device_round._bounds
     opts = [torch.optim.SGD(m.parameters(), lr=0.1, momentum=0.9) for m in mirror]
     lossf = nn.CrossEntropyLoss()
     ok = True
@@ -108,10 +123,9 @@ def main():
         dist.all_gather_into_tensor(full.view(-1), loc.view(-1))
         rows = [full[layout.rank_of[g], layout.slot_of[g]] for g in range(layout.n_workers)]
         if virtual:
-            mal = LittleAttack(f=n_byz).apply(honest_grads=rows)
+            mal = oracle.little(rows, n_byz).to(dev, torch.float32)
             rows = rows + [mal] * n_byz
-        ref_agg = mk()
-        expect = ref_agg.aggregate(pre.pre_aggregate(rows) if pre is not None else rows)
+        expect = oracle.aggregate(a.agg, rows).to(dev, torch.float32)     # fp64 host algebra, not this repo's ops
         for m, o in zip(mirror, opts):
             off = 0
             for p in m.parameters():
@@ -132,6 +146,10 @@ def main():
         ok = ok and good
         print(f"[rank {rank}] step {t}: |agg-ref|={e1:.2e} |param-ref|={e2:.2e} {'OK' if good else 'MISMATCH'}",
               flush=True)
+    if rank == 0:
+        r = ps.device_round
+        print(f"[rank 0] buckets={r.n_buckets} overlapped={r._use_buckets} multicast={bool(r._agg_mc)} "
+              f"launches/round={r.launches_per_step}", flush=True)
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

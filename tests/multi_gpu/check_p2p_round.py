@@ -4,8 +4,10 @@ Launch:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-
              --master-port 29534 tests/multi_gpu/check_p2p_round.py [--agg trmean|gm] [--topology complete|ring]
 
 8 peers (7 honest TinyNets + 1 Empire) are block-distributed over the ranks.  After every round each
-local honest peer's parameters are compared with a reference built from an NCCL all_gather of the
-mirrors' half-step vectors and the aggregator run on plain tensors (the P2P mixin semantics).
+local honest peer's parameters are compared with an INDEPENDENT oracle: the mirrors' half-step
+vectors are exchanged with an NCCL all_gather and the Empire vectors / robust aggregates are computed
+on the host in float64 with plain torch algebra (tests/multi_gpu/oracle.py -- none of this repo's
+operators), following the P2P mixin semantics.
 """
 import argparse
 import asyncio
@@ -17,6 +19,9 @@ import torch.distributed as dist
 import torch.nn as nn
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+import oracle  # noqa: E402
 
 from byzpy_b200.aggregators.coordinate_wise import CoordinateWiseTrimmedMean  # noqa: E402
 from byzpy_b200.aggregators.geometric_wise import GeometricMedian  # noqa: E402
@@ -101,14 +106,16 @@ def main():
         vec = {g: full[g // per, g % per] for g in range(peers)}
         for g in range(n_h, peers):       # Empire peers: attack on their honest in-neighbours
             ins = [j for j in dict.fromkeys(topo.in_.get(g, [])) if j < n_h]
-            vec[g] = EmpireAttack(scale=-2.0).apply(honest_grads=[vec[j] for j in ins])
+            vec[g] = oracle.empire([vec[j] for j in ins], scale=-2.0).to(dev, torch.float32)
         torch.cuda.synchronize()
         p2p.device_round.check_status()
         for slot, g in enumerate(gids):
             if g >= n_h:
                 continue
             ins = [j for j in dict.fromkeys(topo.in_.get(g, [])) if j != g]
-            expect = mk_agg().aggregate([vec[g]] + [vec[j] for j in ins])
+            rows_g = [vec[g]] + [vec[j] for j in ins]
+            expect = (oracle.trimmed_mean(rows_g, 1) if a.agg == "trmean"
+                      else oracle.geometric_median(rows_g, tol=1e-7)).to(dev, torch.float32)
             got = p2p.device_round.param_vector(slot)
             err = (got - expect).abs().max().item()
             good = err < 2e-4

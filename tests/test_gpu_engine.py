@@ -287,6 +287,126 @@ def test_device_round_matches_manual_loop(graph):
     asyncio.run(ps.shutdown())
 
 
+class DeepNet(nn.Module):
+    """Four blocks behind a Sequential: enough parameters (and block inputs) for gradient buckets."""
+
+    def __init__(self):
+        super().__init__()
+        self.inp = nn.Linear(20, 64)
+        self.body = nn.Sequential(*[nn.Sequential(nn.Linear(64, 64), nn.ReLU()) for _ in range(3)])
+        self.out = nn.Linear(64, 5)
+
+    def forward(self, x):
+        return self.out(self.body(torch.relu(self.inp(x))))
+
+
+@pytest.mark.parametrize("graph", [False, True])
+@pytest.mark.parametrize("agg_name", ["median", "trmean"])
+def test_device_round_bucketed_overlap_matches_manual_loop(graph, agg_name):
+    """The round as a sequence of bucket launches enqueued from inside backward (reverse-layer order,
+    per-bucket sequence numbers in the flag words) follows the same trajectory as a plain
+    gather -> aggregate -> SGD loop, eagerly and as a captured graph."""
+    from byzpy_b200.aggregators.coordinate_wise import CoordinateWiseTrimmedMean
+    from byzpy_b200.engine.node.device import DeviceByzantineNode, DeviceHonestNode
+    from byzpy_b200.engine.parameter_server.ps import ParameterServer
+
+    torch.manual_seed(0)
+    n_h, n_b, steps = 4, 1, 4
+    data = [[(torch.randn(16, 20), torch.randint(0, 5, (16,))) for _ in range(steps)] for _ in range(n_h + n_b)]
+    init = DeepNet().state_dict()
+
+    def mk():
+        m = DeepNet()
+        m.load_state_dict(init)
+        return m
+
+    def mk_agg():
+        return CoordinateWiseMedian() if agg_name == "median" else CoordinateWiseTrimmedMean(f=1)
+
+    hon = [DeviceHonestNode(mk(), lr=0.1, momentum=0.9, device=DEV) for _ in range(n_h)]
+    byz = [DeviceByzantineNode(SignFlipAttack(), model=mk(), lr=0.1, momentum=0.9, device=DEV)]
+    ps = ParameterServer(hon, byz, mk_agg(), update_byzantines=True, fused=True, amp_dtype=None,
+                         use_cuda_graph=graph, worker_streams=2,
+                         device_options=dict(min_bucket=1024, bucket_cuts=(0.3, 0.6, 0.85)))
+    rnd = ps.device_round
+    assert rnd.n_buckets >= 3, rnd._bounds
+    assert sum(rnd.bucket_range(k)[1] for k in range(rnd.n_buckets)) == rnd.d_pad
+    models = [mk().to(DEV) for _ in range(n_h + n_b)]
+    opts = [torch.optim.SGD(m.parameters(), lr=0.1, momentum=0.9) for m in models]
+    lossf = nn.CrossEntropyLoss()
+    for t in range(steps):
+        batches = [(data[w][t][0].pin_memory(), data[w][t][1].pin_memory()) for w in range(n_h + n_b)]
+        ps.step(batches)
+        gs = []
+        for w, m in enumerate(models):
+            m.zero_grad()
+            lossf(m(batches[w][0].to(DEV)), batches[w][1].to(DEV)).backward()
+            g = torch.cat([p.grad.reshape(-1) for p in m.parameters()])
+            gs.append(-g if w >= n_h else g)
+        agg = mk_agg().aggregate(gs)
+        for m, o in zip(models, opts):
+            off = 0
+            for p in m.parameters():
+                p.grad.copy_(agg[off:off + p.numel()].view_as(p))
+                off += p.numel()
+            o.step()
+        rnd.read_losses()           # raises on a sticky kernel status
+        torch.testing.assert_close(rnd.aggregated(), agg, rtol=1e-4, atol=1e-5)
+    assert rnd._use_buckets, "bucket validation rejected a sequential model"
+    assert rnd.launches_per_step == 1 + rnd.n_buckets
+    mine = torch.cat([p.detach().reshape(-1) for p in hon[0].model.parameters()])
+    theirs = torch.cat([p.detach().reshape(-1) for p in models[0].parameters()])
+    torch.testing.assert_close(mine, theirs, rtol=1e-4, atol=1e-5)
+    asyncio.run(ps.shutdown())
+
+
+class OutOfOrderNet(nn.Module):
+    """Registers its FIRST layer last: ``first`` sits at the highest flat offset but its backward
+    runs at the very end, so a bucket mark at the input of ``c`` (whose range reaches the end of the
+    arena) fires before ``first``'s gradient exists."""
+
+    def __init__(self):
+        super().__init__()
+        self.b = nn.Linear(64, 64)
+        self.c = nn.Linear(64, 64)
+        self.head = nn.Linear(64, 5)
+        self.first = nn.Linear(20, 64)        # registered last, executed first
+
+    def forward(self, x):
+        return self.head(torch.relu(self.c(torch.relu(self.b(torch.relu(self.first(x)))))))
+
+
+def test_bucket_validation_falls_back_for_out_of_order_models():
+    from byzpy_b200.engine.node.device import DeviceHonestNode
+    from byzpy_b200.engine.parameter_server.ps import ParameterServer
+
+    torch.manual_seed(0)
+    init = OutOfOrderNet().state_dict()
+
+    def mk():
+        m = OutOfOrderNet()
+        m.load_state_dict(init)
+        return m
+
+    hon = [DeviceHonestNode(mk(), lr=0.1, momentum=0.0, device=DEV) for _ in range(3)]
+    with pytest.warns(UserWarning, match="bucket overlap disabled"):
+        ps = ParameterServer(hon, [], CoordinateWiseMedian(), fused=True, amp_dtype=None, use_cuda_graph=True,
+                             device_options=dict(min_bucket=1024, bucket_cuts=(0.3, 0.6)))
+        assert ps.device_round.n_buckets >= 2
+        batches = [(torch.randn(8, 20).pin_memory(), torch.randint(0, 5, (8,)).pin_memory()) for _ in range(3)]
+        ps.step(batches)
+    rnd = ps.device_round
+    assert not rnd._use_buckets
+    models = [mk().to(DEV) for _ in range(3)]
+    gs = []
+    for m, (x, y) in zip(models, batches):
+        nn.CrossEntropyLoss()(m(x.to(DEV)), y.to(DEV)).backward()
+        gs.append(torch.cat([p.grad.reshape(-1) for p in m.parameters()]))
+    rnd.read_losses()
+    torch.testing.assert_close(rnd.aggregated(), torch.stack(gs).median(dim=0).values, rtol=1e-4, atol=1e-5)
+    asyncio.run(ps.shutdown())
+
+
 @pytest.mark.parametrize("graph", [False, True])
 def test_device_round_prefetch_pipeline_matches_explicit_batches(graph):
     """ps.step() with data sources double-buffers the inputs (H2D of batch k+1 overlaps round k, one

@@ -58,3 +58,17 @@ def test_fused_round_rank_without_replica():
            "--attack", "little"]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert res.returncode == 0 and "MULTI_GPU_FUSED_ROUND PASS" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("agg,graph", [("median", 1), ("trmean", 0)])
+def test_fused_round_bucketed_overlap_two_ranks(agg, graph):
+    """The round as a sequence of bucket launches enqueued from inside backward, with per-bucket
+    sequence numbers in the cross-GPU flag words, against the independent fp64 oracle."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29537",
+           os.path.join(ROOT, "tests", "multi_gpu", "check_fused_round.py"), "--agg", agg, "--buckets", "3",
+           "--graph", str(graph), "--steps", "5"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert res.returncode == 0 and "MULTI_GPU_FUSED_ROUND PASS" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "buckets=3 overlapped=True" in res.stdout, res.stdout[-1500:]

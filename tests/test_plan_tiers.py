@@ -303,3 +303,67 @@ def test_torch_selection_solvers_treat_nan_rows_as_farthest():
 
 def test_cge_and_monna_plans_are_capturable():
     assert ComparativeGradientElimination(f=1).fused_plan(6).capturable and MoNNA(f=1).fused_plan(6).capturable
+
+
+# ------------------------------------------------------------------ gradient buckets (CPU)
+def test_bucket_planner_cuts_resnet18_at_block_inputs_from_the_tail():
+    import torch
+
+    from byzpy_b200.models import resnet18
+    from byzpy_b200.ops.fused_layers import bucket_candidates
+    from byzpy_b200.parallel.arena import ParamArena
+    from byzpy_b200.parallel.device_ps import bucket_bounds, pick_bucket_offsets
+
+    m = resnet18(num_classes=1000)
+    a = ParamArena(m)
+    cand = bucket_candidates(m, a.offsets)
+    offs = [fo for fo, _ in cand]
+    assert offs == sorted(offs) and len(offs) == 11          # stem conv, bn1, 8 blocks, fc
+    picks = pick_bucket_offsets(offs, a.d, (0.40, 0.75, 0.93))
+    names = {id(mod): n for n, mod in m.named_modules()}
+    assert [names[id(mod)] for fo, mod in cand if fo in picks] == ["layer3.0", "layer4.0", "layer4.1"]
+    b = bucket_bounds(picks, a.d_pad, 1 << 16)
+    assert b[0] == a.d_pad and b[-1] == 0 and b == sorted(b, reverse=True)
+    assert all(x % 1024 == 0 for x in b)
+    assert all(bound >= off for bound, off in zip(b[1:-1], picks))      # rounded UP: never early
+    assert pick_bucket_offsets(offs, a.d, (0.40, 0.75, 0.93), buckets=2) == picks[:1]
+    assert pick_bucket_offsets(offs, a.d, (0.40, 0.75, 0.93), buckets=1) == []
+    # tiny buckets are merged away
+    assert bucket_bounds([5000, 3000, 100], 8192, 4096) == [8192, 0]
+    assert torch.is_tensor(a.flat_grads)
+
+
+def test_bucket_marks_fire_in_reverse_layer_order_with_complete_gradients():
+    import torch
+
+    from byzpy_b200.models import resnet18
+    from byzpy_b200.ops.fused_layers import bucket_candidates, install_bucket_marks
+    from byzpy_b200.parallel.arena import ParamArena
+    from byzpy_b200.parallel.device_ps import pick_bucket_offsets
+
+    torch.manual_seed(0)
+    m = resnet18(num_classes=10, small_input=True)
+    a = ParamArena(m)
+    cand = bucket_candidates(m, a.offsets)
+    picks = pick_bucket_offsets([fo for fo, _ in cand], a.d, (0.40, 0.75, 0.93))
+    seen = []
+
+    def on_mark(k):
+        g = a.flat_grads
+        done = float((g[picks[k]:a.d] != 0).float().mean())
+        early = float((g[:picks[k]] != 0).float().mean())
+        seen.append((k, done, early))
+
+    handles = install_bucket_marks([(next(mod for off, mod in cand if off == fo), k) for k, fo in enumerate(picks)],
+                                   on_mark)
+    a.zero_grad()
+    m(torch.randn(4, 3, 32, 32)).sum().backward()
+    assert [k for k, _, _ in seen] == [0, 1, 2]
+    for _, done, early in seen:
+        assert done > 0.99 and early == 0.0       # everything behind the mark exists, nothing before it
+    for h in handles:
+        h.remove()
+    seen.clear()
+    a.zero_grad()
+    m(torch.randn(4, 3, 32, 32)).sum().backward()
+    assert seen == []
