@@ -193,7 +193,8 @@ def run_ours(args, rank, world, device):
                          layout=layout, amp_dtype=torch.bfloat16, use_cuda_graph=not args.no_graph,
                          worker_streams=args.worker_streams, fused=True,
                          direct_grads=not args.no_direct_grads, overlap_wgrad=not args.no_overlap_wgrad,
-                         branch_streams=not args.no_branch_streams)
+                         branch_streams=not args.no_branch_streams, buckets=args.buckets,
+                         multicast=None if args.multicast < 0 else bool(args.multicast))
     rnd = ps.device_round
 
     def batches(i):
@@ -248,7 +249,9 @@ def run_ours(args, rank, world, device):
         h2d, d2h = int(tot[0].item()), int(tot[1].item())
     result = dict(ms=ms, e2e_s=e2e_s, h2d=h2d, d2h=d2h, clocks=clk.summary(),
                   launches=(rnd.launches_per_step + rnd.model_launches_per_step) * args.steps,
-                  loss=float(losses.mean().item()), d=rnd.d)
+                  loss=float(losses.mean().item()), d=rnd.d,
+                  round=dict(buckets=rnd.n_buckets if rnd._use_buckets else 1, multicast=bool(rnd._agg_mc),
+                             heap=rnd.sym.kind, bounds=list(rnd._bounds)))
     asyncio.run(ps.shutdown())
     return result
 
@@ -422,6 +425,10 @@ def main():
     ap.add_argument("--lr", type=float, default=0.05)
     ap.add_argument("--worker-streams", type=int, default=8)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--buckets", type=int, default=None,
+                    help="gradient buckets of the fused round (default: automatic; 1 = one launch after backward)")
+    ap.add_argument("--multicast", type=int, default=-1,
+                    help="NVLS multicast broadcast: -1 when supported, 0 peer stores, 1 required")
     ap.add_argument("--no-direct-grads", action="store_true",
                     help="A/B: stock autograd gradient accumulation instead of in-place arena gradients")
     ap.add_argument("--no-branch-streams", action="store_true",
@@ -481,6 +488,7 @@ def main():
                 "e2e": {"value": round(e2e, 3), "unit": "steps/s", "h2d_bytes_per_step": res["h2d"],
                         "d2h_bytes_per_step": res["d2h"]},
                 "gpu_launches": res["launches"],
+                "round": res.get("round"),
                 "final_loss": round(res["loss"], 4),
             }
             print(json.dumps(out))

@@ -95,7 +95,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             list(ex.map(_run, jobs))
     out = ext_path()
     if force or jobs or _stale(out, objs):
-        cmd = [nvcc, *ARCH_FLAGS, "-shared", "-o", str(out), *map(str, objs), "-lcudart"]
+        cmd = [nvcc, *ARCH_FLAGS, "-shared", "-o", str(out), *map(str, objs), "-lcudart", "-ldl"]
         if verbose:
             print("[byzpy_b200 build]", " ".join(cmd), flush=True)
         res = subprocess.run(cmd, capture_output=True, text=True)

@@ -409,4 +409,5 @@ PYBIND11_MODULE(_C, m) {
   });
 
   bz_bind_runtime(m);
+  bz_bind_vmm(m);
 }

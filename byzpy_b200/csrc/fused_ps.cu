@@ -251,6 +251,39 @@ __global__ void gram_exchange_kernel(const __grid_constant__ BzGramExchangeArgs 
   }
 }
 
+// (n, n) fp64 all-reduce through the NVLS multicast alias (see BzGramExchangeArgs::slots_mc).
+__global__ void __launch_bounds__(1024) gram_exchange_nvls_kernel(const __grid_constant__ BzGramExchangeArgs a) {
+  const uint32_t epoch = *a.epoch_ptr;
+  const int nn = a.n * a.n;
+  double* mine = a.slots[a.rank];            // slot 0: my partial, slot 1 (at + nn): the total
+  for (int t = threadIdx.x; t < nn; t += blockDim.x) mine[t] = a.local[t];
+  __syncthreads();
+  if (threadIdx.x == 0) publish(a.pad, BZ_PAD_GRAM, a.rank, a.world, a.live_mask, 2u * epoch);
+  if (!wait_all(a.pad[a.rank] + BZ_PAD_GRAM, a.world, a.live_mask, 2u * epoch, a.status, 8, a.spin_ns)) return;
+  // my slice of the matrix: elements t with (t / 32) % live == my index among the live ranks
+  int live = 0, idx = 0;
+  for (int r = 0; r < a.world; ++r) {
+    if (!is_live(a.live_mask, r)) continue;
+    if (r == a.rank) idx = live;
+    ++live;
+  }
+  for (int t = threadIdx.x; t < nn; t += blockDim.x) {
+    if (((t >> 5) % live) != idx) continue;
+    double v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f64 %0, [%1];" : "=d"(v) : "l"(a.slots_mc + t) : "memory");
+    asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(a.slots_mc + nn + t), "d"(v) : "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) publish(a.pad, BZ_PAD_GRAM, a.rank, a.world, a.live_mask, 2u * epoch + 1u);
+  if (!wait_all(a.pad[a.rank] + BZ_PAD_GRAM, a.world, a.live_mask, 2u * epoch + 1u, a.status, 8, a.spin_ns)) return;
+  for (int t = threadIdx.x; t < nn; t += blockDim.x) {
+    double v;
+    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(mine + nn + t));
+    a.out64[t] = v;
+    if (a.out32) a.out32[t] = (float)v;
+  }
+}
+
 template <int NP, int MODE>
 int launch_np(const BzFusedPsArgs& a, int grid, cudaStream_t stream) {
   constexpr int V = (NP <= 16) ? 4 : (NP == 32 ? 2 : 1);
@@ -339,7 +372,10 @@ int bz_flag_barrier(const BzFlagBarrierArgs* args, cudaStream_t stream) {
 int bz_gram_exchange(const BzGramExchangeArgs* args, cudaStream_t stream) {
   if (args->world < 1 || args->world > BZ_MAXW || args->n < 1 || args->n > BZ_MAXN + 16)
     return (int)cudaErrorInvalidValue;
-  gram_exchange_kernel<<<1, 256, 0, stream>>>(*args);
+  if (args->slots_mc != nullptr && args->world > 1)
+    gram_exchange_nvls_kernel<<<1, 1024, 0, stream>>>(*args);
+  else
+    gram_exchange_kernel<<<1, 256, 0, stream>>>(*args);
   return (int)cudaGetLastError();
 }
 

@@ -74,5 +74,11 @@ struct BzGramExchangeArgs {
   unsigned long long spin_ns;
   double* out64;             // (n, n) total
   float* out32;              // (n, n) total (optional)
+  // NVLS form (slots_mc != nullptr): slot 0 of every rank holds its partial, slot 1 receives the total.
+  // Rank r reduces its slice of the matrix INSIDE THE SWITCH with multimem.ld_reduce.add.f64 over the
+  // team's slot-0 copies and multimem.st's the sums into everybody's slot 1 -- one load and one store
+  // per element instead of world peer stores + world local loads, and every rank receives bit-identical
+  // totals (each element is summed once, by one rank), which the n-space selections rely on.
+  double* slots_mc;
 };
 int bz_gram_exchange(const BzGramExchangeArgs* args, cudaStream_t stream);

@@ -197,7 +197,7 @@ void bz_bind_runtime(py::module_& m) {
   m.def("gram_exchange", [](uint64_t local, const std::vector<uint64_t>& slots,
                             const std::vector<uint64_t>& pads, int rank, int n, uint64_t epoch_ptr,
                             uint64_t status, uint64_t out64, uint64_t out32, uint64_t stream,
-                            uint32_t live_mask, double spin_s) {
+                            uint32_t live_mask, double spin_s, uint64_t slots_mc) {
     BzGramExchangeArgs a;
     std::memset(&a, 0, sizeof(a));
     if (slots.size() != pads.size() || slots.empty() || slots.size() > BZ_MAXW)
@@ -216,11 +216,12 @@ void bz_bind_runtime(py::module_& m) {
     a.out32 = as_ptr<float>(out32);
     a.live_mask = live_mask;
     a.spin_ns = (unsigned long long)(spin_s * 1e9);
+    a.slots_mc = as_ptr<double>(slots_mc);
     int e = bz_gram_exchange(&a, as_stream(stream));
     if (e != 0) throw std::runtime_error("gram_exchange failed");
   }, py::arg("local"), py::arg("slots"), py::arg("pads"), py::arg("rank"), py::arg("n"), py::arg("epoch_ptr"),
      py::arg("status"), py::arg("out64"), py::arg("out32"), py::arg("stream"), py::arg("live_mask") = 0,
-     py::arg("spin_s") = 0.0);
+     py::arg("spin_s") = 0.0, py::arg("slots_mc") = 0);
   m.attr("PAD_READY") = BZ_PAD_READY;
   m.attr("PAD_DONE") = BZ_PAD_DONE;
   m.attr("PAD_GRAM") = BZ_PAD_GRAM;

@@ -3,3 +3,5 @@
 #pragma once
 #include <pybind11/pybind11.h>
 void bz_bind_runtime(pybind11::module_& m);
+// symmetric heap on the VMM API + NVLS multicast (vmm.cpp)
+void bz_bind_vmm(pybind11::module_& m);

@@ -352,9 +352,9 @@ class DeviceRound:
         self._off_ctl = self._off_pad + 256
         self._off_gslots = self._off_ctl + 256
         self.nt_max = 144                       # rows + auxiliary rows of a Gram plan
-        gram_bytes = self.world * self.nt_max * self.nt_max * 8 if isinstance(plan, GramPlan) else 0
+        gram_bytes = max(2, self.world) * self.nt_max * self.nt_max * 8 if isinstance(plan, GramPlan) else 0
         nbytes = self._off_gslots + gram_bytes
-        self.sym = SymmetricBuffer(nbytes, self.device, group)
+        self.sym = SymmetricBuffer(nbytes, self.device, group, multicast=multicast)
         self.grads = self.sym.view(torch.float32, L_sym * self.d_pad, self._off_grads).view(L_sym, self.d_pad)
         self.agg = self.sym.view(torch.float32, self.d_pad, self._off_agg)
         self.pad = self.sym.view(torch.int32, 64, self._off_pad)
@@ -628,7 +628,8 @@ class DeviceRound:
         nt = self._nt
         launches = 1
         # every rank's gradient rows must be complete before anybody reads them
-        ext.flag_barrier(pads, self.rank, ext.PAD_READY, ctl + 8, ctl + 4, stream)
+        ext.flag_barrier(pads, self.rank, ext.PAD_READY, ctl + 8, ctl + 4, stream, 0, 0, self.live_mask,
+                         self.spin_seconds)
         launches += 1
         if lay.n_virtual:
             nh = lay.n_honest
@@ -661,9 +662,12 @@ class DeviceRound:
                      self._g_local64.data_ptr(), self.sm, stream)
         launches += 2
         # all-reduce the (nt, nt) partials through peer stores
+        # (NVLS multicast: summed inside the switch by multimem.ld_reduce, broadcast by multimem.st)
         ext.gram_exchange(self._g_local64.data_ptr(),
                           [self.sym.peer_ptr(r, self._off_gslots) for r in range(self.world)], pads,
-                          self.rank, nt, ctl + 8, ctl + 4, self._g_total64.data_ptr(), 0, stream)
+                          self.rank, nt, ctl + 8, ctl + 4, self._g_total64.data_ptr(), 0, stream,
+                          self.live_mask, self.spin_seconds,
+                          self.sym.mc_ptr(self._off_gslots) if self._agg_mc else 0)
         launches += 1
         # n-space solve (device side) -> weights
         w = plan.solver(self._g_total64)
@@ -673,7 +677,8 @@ class DeviceRound:
         ext.fused_ps_wsum(self._all_rows, self._all_scales, self._w_dev.data_ptr(), self.d_pad, off, ln,
                           self.rank, [self.sym.peer_ptr(r, self._off_agg) for r in range(self.world)], pads,
                           ctl + 8, ctl + 0, ctl + 4, self._upd_params, self._upd_moms, self.lr,
-                          self.momentum, self.weight_decay, self.sm, stream)
+                          self.momentum, self.weight_decay, self.sm, stream, 0, 0, 0, 0, 0, self._agg_mc,
+                          self.live_mask, self.spin_seconds)
         self.launches_per_step = launches + 1
 
     def _upd_index(self) -> List[int]:

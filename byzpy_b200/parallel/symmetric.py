@@ -1,18 +1,32 @@
-"""Symmetric device memory over CUDA IPC (one process per GPU).
+"""Symmetric device memory (one process per GPU).
 
-Every rank allocates identically sized raw arenas with ``cudaMalloc`` (through
-the native runtime in ``byzpy_b200._C``), exports them as 64-byte IPC handles,
-and maps every peer's arena into its own address space.  ``torch.distributed``
-(NCCL or Gloo) is used ONLY here, to all-gather the handles at start-up; the
-training hot path then addresses peer HBM directly from inside the fused
-kernels (P2P ``ld.global``/``st.global`` over NVLink 5 / NVSwitch).
+Every rank allocates an identically sized raw arena and maps every peer's arena into its own
+address space; the fused kernels then address peer HBM directly (P2P ``ld.global`` /
+``st.global`` over NVLink 5 / NVSwitch).  Two heaps:
 
-B200-native replacement for the reference's host shared-memory store and
-pickled tensor transport (reference engine/storage/shared_store.py:21-54,
-engine/actor/ipc.py:20-56, engine/actor/transports/ucx.py:225-270).
+* ``"vmm"`` (default where supported) -- CUDA virtual-memory-management allocations
+  (``cuMemCreate``) exported as POSIX file descriptors, exchanged between the ranks over Unix
+  sockets (``SCM_RIGHTS``), and bound to one **NVLS multicast object** for the whole team
+  (``cuMulticastCreate`` / ``AddDevice`` / ``BindMem``).  ``mc_ptr()`` is the multicast alias: a
+  ``multimem.st`` there is replicated by the switch into every rank's copy, a
+  ``multimem.ld_reduce`` sums the copies in the switch (``csrc/vmm.cpp``).
+* ``"ipc"`` -- ``cudaMalloc`` + ``cudaIpc*`` handles (``csrc/runtime.cpp``); no multicast.  The
+  fallback when the driver lacks VMM / fd export, and selectable with ``BYZPY_SYMM=ipc``.
+
+``torch.distributed`` (NCCL or Gloo) is used ONLY here, at start-up, to exchange handles / socket
+paths.
+
+B200-native replacement for the reference's host shared-memory store and pickled tensor
+transport (reference engine/storage/shared_store.py:21-54, engine/actor/ipc.py:20-56,
+engine/actor/transports/ucx.py:225-270).
 """
 from __future__ import annotations
 
+import os
+import socket
+import tempfile
+import threading
+import uuid
 from typing import List, Optional
 
 import torch
@@ -40,41 +54,178 @@ def tensor_from_ptr(ptr: int, nbytes: int, device: torch.device, owner=None) -> 
     return torch.as_tensor(_RawView(ptr, nbytes, owner), device=device)
 
 
+# --------------------------------------------------------------------- fd exchange
+class _FdServer:
+    """Serves this rank's file descriptors to its peers over a Unix socket (``SCM_RIGHTS``).
+    A request is one byte: the index of the wanted descriptor."""
+
+    def __init__(self, fds: List[int]):
+        self.fds = list(fds)
+        self.path = os.path.join(tempfile.gettempdir(), f"byzpy_b200_fd_{uuid.uuid4().hex}.sock")
+        self._sock = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        self._sock.bind(self.path)
+        self._sock.listen(64)
+        self._stop = False
+        self._thr = threading.Thread(target=self._serve, daemon=True)
+        self._thr.start()
+
+    def _serve(self) -> None:
+        while not self._stop:
+            try:
+                conn, _ = self._sock.accept()
+            except OSError:
+                return
+            with conn:
+                try:
+                    idx = conn.recv(1)
+                    if idx:
+                        socket.send_fds(conn, [b"f"], [self.fds[idx[0]]])
+                except OSError:
+                    pass
+
+    def close(self) -> None:
+        self._stop = True
+        try:
+            self._sock.close()
+        finally:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+
+
+def _fetch_fd(path: str, index: int = 0) -> int:
+    with socket.socket(socket.AF_UNIX, socket.SOCK_STREAM) as s:
+        s.connect(path)
+        s.sendall(bytes([index]))
+        _, fds, _, _ = socket.recv_fds(s, 1, 1)
+        if not fds:
+            raise RuntimeError(f"no file descriptor received from {path}")
+        return fds[0]
+
+
+def heap_kind(device: torch.device, world: int) -> str:
+    """``"vmm"`` when the driver supports VMM allocations with POSIX-fd export, else ``"ipc"``."""
+    forced = os.environ.get("BYZPY_SYMM", "").lower()
+    if forced in ("ipc", "vmm"):
+        return forced
+    ext = ops.require_ext()
+    sup = ext.vmm_support(device.index if device.index is not None else torch.cuda.current_device())
+    return "vmm" if (sup["vmm"] and sup["posix_fd"]) else "ipc"
+
+
 class SymmetricBuffer:
     """A raw device allocation mapped on every rank of ``group``.
 
-    ``ptrs[r]`` is the address at which rank ``r``'s copy is visible in THIS
-    process (``ptrs[rank]`` is the local allocation).  ``local`` is a uint8
-    torch tensor over the local copy; use :meth:`view` for typed views.
+    ``ptrs[r]`` is the address at which rank ``r``'s copy is visible in THIS process
+    (``ptrs[rank]`` is the local allocation); ``mc_base`` the address of the NVLS multicast alias
+    (0 without one).  ``local`` is a uint8 torch tensor over the local copy; use :meth:`view` for
+    typed views.
     """
 
-    def __init__(self, nbytes: int, device: torch.device, group=None):
+    def __init__(self, nbytes: int, device: torch.device, group=None, *, kind: Optional[str] = None,
+                 multicast: Optional[bool] = None):
         ext = ops.require_ext()
         self._ext = ext
-        self.nbytes = int((nbytes + 255) // 256 * 256)
         self.device = device
         self.group = group
         self.rank = dist.get_rank(group) if _dist_on() else 0
         self.world = dist.get_world_size(group) if _dist_on() else 1
-        with torch.cuda.device(device):
-            self._ptr = ext.raw_alloc(self.nbytes)
-        self.ptrs: List[int] = [0] * self.world
-        self.ptrs[self.rank] = self._ptr
+        self._dev_index = device.index if device.index is not None else torch.cuda.current_device()
+        self.kind = kind or heap_kind(device, self.world)
+        self.mc_base = 0
+        self._closed = False
         self._opened: List[int] = []
+        self.ptrs: List[int] = [0] * self.world
+        if self.world > 1:      # every rank must take the same path
+            kinds: List[Optional[str]] = [None] * self.world
+            dist.all_gather_object(kinds, self.kind, group=group)
+            if any(k != "vmm" for k in kinds):
+                self.kind = "ipc"
+        if self.kind == "vmm":
+            self._init_vmm(nbytes, multicast)
+        else:
+            if multicast:
+                raise RuntimeError("NVLS multicast needs the VMM symmetric heap")
+            self._init_ipc(nbytes)
+        self.local = tensor_from_ptr(self._ptr, self.nbytes, device, owner=self)
+
+    # ----------------------------------------------------------------- CUDA IPC heap
+    def _init_ipc(self, nbytes: int) -> None:
+        ext = self._ext
+        self.nbytes = int((nbytes + 255) // 256 * 256)
+        with torch.cuda.device(self.device):
+            self._ptr = ext.raw_alloc(self.nbytes)
+        self.ptrs[self.rank] = self._ptr
         if self.world > 1:
             handle = ext.ipc_export(self._ptr)
             handles: List[Optional[bytes]] = [None] * self.world
-            dist.all_gather_object(handles, handle, group=group)
-            with torch.cuda.device(device):
+            dist.all_gather_object(handles, handle, group=self.group)
+            with torch.cuda.device(self.device):
                 for r, h in enumerate(handles):
                     if r == self.rank:
                         continue
                     p = ext.ipc_open(h)
                     self.ptrs[r] = p
                     self._opened.append(p)
-        self.local = tensor_from_ptr(self._ptr, self.nbytes, device, owner=self)
-        self._closed = False
 
+    # ----------------------------------------------------------------- VMM heap (+ multicast)
+    def _init_vmm(self, nbytes: int, multicast: Optional[bool]) -> None:
+        ext, dev = self._ext, self._dev_index
+        sup = ext.vmm_support(dev)
+        want_mc = self.world > 1 and multicast is not False and bool(sup["multicast"])
+        if multicast and self.world > 1 and not sup["multicast"]:
+            raise RuntimeError("multicast=True but this device / driver reports no NVLS multicast support")
+        if self.world > 1:      # all ranks or none
+            flags: List[Optional[bool]] = [None] * self.world
+            dist.all_gather_object(flags, want_mc, group=self.group)
+            want_mc = all(flags)
+        gran = int(ext.vmm_granularity(dev, self.world, want_mc))
+        self._gran = gran
+        self.nbytes = int((nbytes + gran - 1) // gran * gran)
+        self._handle, self._ptr = ext.vmm_alloc(self.nbytes, gran, dev)
+        self.ptrs[self.rank] = self._ptr
+        self._peer_handles: List[int] = []
+        self._mc_handle = 0
+        if self.world == 1:
+            return
+        # ---- exchange the allocation handles as file descriptors
+        my_fd = ext.vmm_export_fd(self._handle)
+        fds = [my_fd]
+        if want_mc and self.rank == 0:
+            self._mc_handle = ext.mc_create(self.world, self.nbytes)
+            fds.append(ext.vmm_export_fd(self._mc_handle))
+        server = _FdServer(fds)
+        try:
+            paths: List[Optional[str]] = [None] * self.world
+            dist.all_gather_object(paths, server.path, group=self.group)
+            for r in range(self.world):
+                if r == self.rank:
+                    continue
+                fd = _fetch_fd(paths[r], 0)
+                h = ext.vmm_import_fd(fd, dev)
+                ext.close_fd(fd)
+                p = ext.vmm_map(h, self.nbytes, gran, dev)
+                self._peer_handles.append(h)
+                self.ptrs[r] = p
+                self._opened.append(p)
+            if want_mc:
+                if self.rank != 0:
+                    fd = _fetch_fd(paths[0], 1)
+                    self._mc_handle = ext.vmm_import_fd(fd, dev)
+                    ext.close_fd(fd)
+                ext.mc_add_device(self._mc_handle, dev)
+                dist.barrier(group=self.group)          # every device is part of the team before anyone binds
+                ext.mc_bind(self._mc_handle, self._handle, self.nbytes)
+                dist.barrier(group=self.group)
+                self.mc_base = ext.vmm_map(self._mc_handle, self.nbytes, gran, dev)
+            dist.barrier(group=self.group)              # nobody tears its server down while peers still fetch
+        finally:
+            server.close()
+            for fd in fds:
+                ext.close_fd(fd)
+
+    # ----------------------------------------------------------------- views
     def view(self, dtype: torch.dtype, numel: Optional[int] = None, offset_bytes: int = 0) -> torch.Tensor:
         itemsize = torch.empty((), dtype=dtype).element_size()
         avail = (self.nbytes - offset_bytes) // itemsize
@@ -89,17 +240,39 @@ class SymmetricBuffer:
     def mc_ptr(self, offset_bytes: int = 0) -> int:
         """Address of the NVLS multicast alias of the buffer (a ``multimem.st`` there lands in every
         rank's copy), or 0 when the heap has no multicast mapping."""
-        return (self.mc_base + offset_bytes) if getattr(self, "mc_base", 0) else 0
+        return (self.mc_base + offset_bytes) if self.mc_base else 0
 
     def close(self) -> None:
         if self._closed:
             return
         self._closed = True
         torch.cuda.synchronize(self.device)
+        ext = self._ext
         with torch.cuda.device(self.device):
+            if self.world > 1 and _dist_on():
+                try:
+                    dist.barrier(group=self.group)      # peers have stopped touching my memory
+                except Exception:
+                    pass
+            if self.kind == "vmm":
+                try:
+                    if self.mc_base:
+                        ext.vmm_unmap(self.mc_base, self.nbytes)
+                    if self._mc_handle:
+                        ext.mc_unbind(self._mc_handle, self._dev_index, self.nbytes)
+                        ext.vmm_release(self._mc_handle)
+                    for p in self._opened:
+                        ext.vmm_unmap(p, self.nbytes)
+                    for h in self._peer_handles:
+                        ext.vmm_release(h)
+                    ext.vmm_unmap(self._ptr, self.nbytes)
+                    ext.vmm_release(self._handle)
+                except Exception:
+                    pass
+                return
             for p in self._opened:
                 try:
-                    self._ext.ipc_close(p)
+                    ext.ipc_close(p)
                 except Exception:
                     pass
             if self.world > 1 and _dist_on():
@@ -108,7 +281,7 @@ class SymmetricBuffer:
                 except Exception:
                     pass
             try:
-                self._ext.raw_free(self._ptr)
+                ext.raw_free(self._ptr)
             except Exception:
                 pass
 
@@ -117,4 +290,4 @@ def _dist_on() -> bool:
     return dist.is_available() and dist.is_initialized()
 
 
-__all__ = ["SymmetricBuffer", "tensor_from_ptr"]
+__all__ = ["SymmetricBuffer", "tensor_from_ptr", "heap_kind"]

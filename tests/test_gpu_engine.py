@@ -588,3 +588,30 @@ def test_smoke_entry():
     import __graft_entry__ as g
 
     g.smoke()
+
+
+def test_symmetric_buffer_on_the_vmm_heap_single_rank():
+    """cuMemCreate-backed symmetric heap (csrc/vmm.cpp): torch views alias the mapping, kernels of
+    this library run on it, close() unmaps and releases."""
+    from byzpy_b200.parallel.symmetric import SymmetricBuffer, heap_kind
+
+    ext = ops.require_ext()
+    sup = ext.vmm_support(0)
+    assert sup["vmm"] and sup["posix_fd"], sup
+    assert heap_kind(torch.device(DEV), 1) == "vmm"
+    buf = SymmetricBuffer(3 * 4096 + 17, torch.device(DEV), kind="vmm")
+    assert buf.kind == "vmm" and buf.nbytes % int(ext.vmm_granularity(0, 1, False)) == 0
+    assert buf.mc_ptr() == 0 and buf.peer_ptr(0, 64) == buf.ptrs[0] + 64
+    v = buf.view(torch.float32, 4096)
+    assert float(v.abs().sum()) == 0.0                  # zero-filled
+    rows = [torch.randn(4096, device=DEV) for _ in range(5)]
+    out = buf.view(torch.float32, 4096, 4096 * 4)
+    ops.cw_select(rows, ops.MODE_MEDIAN, out=out)
+    torch.testing.assert_close(out, torch.stack(rows).median(dim=0).values, rtol=0, atol=0)
+    fd = ext.vmm_export_fd(buf._handle)                 # the handle a peer would receive over the Unix socket
+    assert fd > 2
+    ext.close_fd(fd)
+    buf.close()
+    ipc = SymmetricBuffer(1024, torch.device(DEV), kind="ipc")
+    assert ipc.kind == "ipc" and ipc.mc_ptr() == 0
+    ipc.close()
