@@ -69,22 +69,32 @@ def test_attacks_cuda():
         a, b = mk().apply(**kc), mk().apply(**kg)
         assert b.is_cuda
         if isinstance(mk(), (EmpireAttack, LittleAttack)):
-            # The assertion keeps the 5e-4 band of the aggregator comparisons above.  A rare ~2e-4 CPU/GPU
-            # disagreement was seen on some boxes and never reproduced (bench/debug_little.py: 0 of 400
-            # repeats), so each side is additionally compared with an fp64 oracle built from ITS OWN input
-            # rows and any deviation is reported as a warning naming the side that moved.
+            # The CUDA kernel is held to an fp64 oracle built from the DEVICE rows at 1e-5.  A rare ~2e-4
+            # CPU/GPU disagreement on a quarter of the coordinates was seen on some boxes and never under
+            # repetition (bench/debug_virtual.py: 0 of 2300 repeats, 8 suite runs); when the two fp32
+            # sides disagree, the side that deviates from the oracle is named: the kernel fails the test,
+            # the host implementation is reported (gpurun_out/mismatch_attack.txt) as a warning.
+            import os
             import warnings
 
             ca, cb = mk()._coeffs(len(g))
-            for name, rows, got in (("cpu", g, a), ("gpu", [r.cpu() for r in gd], b.cpu())):
-                X = torch.stack(rows).double()
-                oracle = ca * X.mean(0) + cb * X.std(0, unbiased=False)
-                err = (got.double() - oracle).abs().max().item()
-                if err > 2e-6 * (1.0 + oracle.abs().max().item()):
-                    warnings.warn(f"{type(mk()).__name__}: {name} side deviates from its fp64 oracle by {err:.3e}")
-            if not all(torch.equal(r.cpu(), x) for r, x in zip(gd, g)):
-                warnings.warn(f"{type(mk()).__name__}: device rows differ from the host rows")
-            torch.testing.assert_close(b.cpu(), a, rtol=5e-4, atol=5e-4, msg=lambda m: f"{type(mk()).__name__}: {m}")
+            rows_back = [r.cpu() for r in gd]
+            assert all(torch.equal(r, x) for r, x in zip(rows_back, g)), "device rows differ from the host rows"
+            X = torch.stack(rows_back).double()
+            oracle = (ca * X.mean(0) + cb * X.std(0, unbiased=False)).float()
+            torch.testing.assert_close(b.cpu(), oracle, rtol=1e-5, atol=1e-5,
+                                       msg=lambda m: f"{type(mk()).__name__} kernel vs fp64 oracle: {m}")
+            if not torch.allclose(a, oracle, rtol=1e-5, atol=1e-5):
+                bad = ((a - oracle).abs() > 1e-5 + 1e-5 * oracle.abs()).nonzero().flatten()
+                a2 = mk().apply(**kc)
+                line = (f"{type(mk()).__name__}: HOST side deviates from fp64 oracle by {float((a - oracle).abs().max()):.3e} on "
+                        f"{bad.numel()}/{a.numel()} coordinates, mod 16 {torch.bincount(bad % 16, minlength=16).tolist()}, "
+                        f"first {bad[:12].tolist()}, rerun equal {bool(torch.equal(a2, a))}, rerun vs oracle "
+                        f"{float((a2 - oracle).abs().max()):.3e}, threads {torch.get_num_threads()}")
+                os.makedirs("gpurun_out", exist_ok=True)
+                with open(os.path.join("gpurun_out", "mismatch_attack.txt"), "a") as fh:
+                    fh.write(line + "\n")
+                warnings.warn(line)
             continue
         torch.testing.assert_close(b.cpu(), a, rtol=1e-5, atol=1e-5, msg=lambda m: f"{type(mk()).__name__}: {m}")
     z = GaussianAttack(mu=0.5, sigma=3.0, seed=1).apply(honest_grads=[torch.zeros(1 << 18, device=DEV)])

@@ -102,7 +102,48 @@ def test_cw_select_scales_and_virtual_rows():
     virt = (2, 6, 1.0, 1.5)  # two Little rows built from all six honest ones
     out = ops.cw_select(rows, ops.MODE_TRMEAN, 1, virtual=virt)
     exp = ref.cw_select([X[i] for i in range(6)], ops.MODE_TRMEAN, 1, virtual=virt)
-    torch.testing.assert_close(out.cpu(), exp, rtol=1e-5, atol=1e-5)
+    _assert_close_or_dump("virtual_rows", out, exp, X,
+                          lambda: ops.cw_select(rows, ops.MODE_TRMEAN, 1, virtual=virt),
+                          lambda: ref.cw_select([X[i] for i in range(6)], ops.MODE_TRMEAN, 1, virtual=virt),
+                          lambda Xd: _virtual_trmean_oracle(Xd, virt, 1))
+
+
+def _virtual_trmean_oracle(Xd, virt, f):
+    nv, nh, a, b = virt
+    H = Xd[:nh]
+    v = a * H.mean(0) + b * H.std(0, unbiased=False)
+    S = torch.cat([Xd, v[None].expand(nv, -1)]).sort(dim=0).values
+    return S[f:S.shape[0] - f].mean(0)
+
+
+def _assert_close_or_dump(tag, out, exp, X, rerun_gpu, rerun_cpu, oracle64, rtol=1e-5, atol=1e-5):
+    """The kernel is held to an fp64 host oracle at 1e-5 unconditionally.  The CPU fp32 implementation
+    is compared too; when the two fp32 sides disagree, both are recomputed, each is measured against the
+    oracle and the lane pattern of the bad coordinates is written to gpurun_out/mismatch_<tag>.txt (it
+    travels back from the GPU box), so a disagreement names the side that moved: a GPU deviation fails
+    the test, a CPU-side deviation is reported as a warning."""
+    got = out.cpu()
+    o = oracle64(X.double()).float()
+    torch.testing.assert_close(got, o, rtol=rtol, atol=atol, msg=lambda m: f"{tag}: GPU kernel vs fp64 oracle: {m}")
+    if torch.allclose(got, exp, rtol=rtol, atol=atol):
+        return
+    import os
+    import warnings
+
+    bad = ((got - exp).abs() > atol + rtol * exp.abs()).nonzero().flatten()
+    g2, e2 = rerun_gpu().cpu(), rerun_cpu()
+    lines = [f"{tag}: {bad.numel()} / {got.numel()} coordinates differ; index mod 4 histogram "
+             f"{torch.bincount(bad % 4, minlength=4).tolist()}; mod 16 {torch.bincount(bad % 16, minlength=16).tolist()}; "
+             f"first {bad[:12].tolist()}",
+             f"gpu vs fp64 oracle: max {float((got - o).abs().max()):.3e}; cpu vs fp64 oracle: max {float((exp - o).abs().max()):.3e}",
+             f"gpu rerun equal: {bool(torch.equal(g2, got))} (rerun vs oracle {float((g2 - o).abs().max()):.3e}); "
+             f"cpu rerun equal: {bool(torch.equal(e2, exp))} (rerun vs oracle {float((e2 - o).abs().max()):.3e})",
+             f"torch threads {torch.get_num_threads()} cpu_capability {torch.backends.cpu.get_cpu_capability()} "
+             f"device {torch.cuda.get_device_name(0)}"]
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(os.path.join("gpurun_out", f"mismatch_{tag}.txt"), "a") as fh:
+        fh.write("\n".join(lines) + "\n")
+    warnings.warn("CPU fp32 implementation deviates from the fp64 oracle (the kernel does not): " + " | ".join(lines))
 
 
 def test_cw_select_fused_sgd_update():
