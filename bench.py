@@ -194,7 +194,8 @@ def run_ours(args, rank, world, device):
                          worker_streams=args.worker_streams, fused=True,
                          direct_grads=not args.no_direct_grads, overlap_wgrad=not args.no_overlap_wgrad,
                          branch_streams=not args.no_branch_streams, buckets=args.buckets,
-                         multicast=None if args.multicast < 0 else bool(args.multicast))
+                         multicast=None if args.multicast < 0 else bool(args.multicast),
+                         device_options=dict(trace=args.trace, overlap_grid=args.overlap_grid))
     rnd = ps.device_round
 
     def batches(i):
@@ -224,6 +225,21 @@ def run_ours(args, rank, world, device):
     ms = e0.elapsed_time(e1)
     ms = max_over_ranks(ms, device)
     rnd.check_status()
+    if args.trace:
+        tl = rnd.timeline()
+        allt = [None] * world
+        if dist.is_initialized():
+            dist.all_gather_object(allt, tl)
+        else:
+            allt = [tl]
+        if rank == 0:
+            for r, t in enumerate(allt):
+                print(f"[timeline rank {r}] backward_done={t['backward_done']} round_done={t['round_done']} us", file=sys.stderr)
+                for k, b in enumerate(t["buckets"]):
+                    print(f"    bucket {k} ({b['elements']} el): produced {b['produced']}  start {b['start']}  ready-wait-> "
+                          f"{b['ready_wait_done']}  phase1(block0) {b['block0_phase1_done']}  phase1(all) "
+                          f"{b['all_ctas_phase1_done']}  delivery-wait-> {b['delivery_wait_done']}  sgd {b['sgd_done']}",
+                          file=sys.stderr)
 
     # ---- end-to-end through the public API: H2D inputs + round + D2H losses every step ----
     # ps.step() pulls every worker's next pinned host batch from its data source; the H2D copy of
@@ -427,6 +443,10 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--buckets", type=int, default=None,
                     help="gradient buckets of the fused round (default: automatic; 1 = one launch after backward)")
+    ap.add_argument("--overlap-grid", type=int, default=None,
+                    help="CTAs of a bucket launch that overlaps backward (default: a quarter of the SMs)")
+    ap.add_argument("--trace", action="store_true",
+                    help="print every rank's device-side timeline of the last timed round (stderr)")
     ap.add_argument("--multicast", type=int, default=-1,
                     help="NVLS multicast broadcast: -1 when supported, 0 peer stores, 1 required")
     ap.add_argument("--no-direct-grads", action="store_true",

@@ -52,6 +52,9 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
+__device__ __forceinline__ void stamp(unsigned long long* trace, int slot) {
+  if (trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) trace[slot] = globaltimer_ns();
+}
 __device__ __forceinline__ bool is_live(uint32_t live_mask, int r) {
   return live_mask == 0u || ((live_mask >> r) & 1u) != 0u;
 }
@@ -85,11 +88,22 @@ __device__ bool wait_all(const uint32_t* flags, int world, uint32_t live_mask, u
   return ok;
 }
 
+__device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Publish pad[p][slot + rank] = seq on every live rank p.  Called by ALL threads of a CTA (warp 0
+// does the work): lane p issues ONE system-scope fence followed by a relaxed store to peer p -- a
+// release pattern per lane, so the `world` flag stores leave in parallel behind a single MEMBAR.SYS
+// of the warp.  (One thread looping over st.release.sys paid a fence per peer: measured 2.7 us per
+// peer on an idle fabric and 15 us per peer while the peers' phase-1 traffic was in flight, i.e.
+// >100 us to reach the last rank -- profiles/round_timeline.md.)
 __device__ __forceinline__ void publish(uint32_t* const* pad, int slot, int rank, int world, uint32_t live_mask,
                                         uint32_t seq) {
-  __threadfence_system();
-  for (int p = 0; p < world; ++p)
-    if (is_live(live_mask, p)) st_release_sys(pad[p] + slot + rank, seq);
+  if ((int)threadIdx.x < world && is_live(live_mask, threadIdx.x)) {
+    __threadfence_system();
+    st_relaxed_sys(pad[threadIdx.x] + slot + rank, seq);
+  }
 }
 
 // Deliver V aggregated coordinates to every live rank's agg buffer.
@@ -120,18 +134,24 @@ __device__ __forceinline__ void deliver(const BzFusedPsArgs& a, long long base, 
 // Phase 1 epilogue + phase 2: the last CTA of this rank announces delivery, then every CTA applies
 // the optimizer step over the launch's coordinate range once all ranks have delivered.
 __device__ __forceinline__ void finish_round(const BzFusedPsArgs& a, uint32_t seq, uint32_t* my_pad) {
+  __shared__ int s_last;
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence_system();
+    __threadfence_system();           // this CTA's deliveries are performed system-wide before it is counted
     const unsigned int prev = atomicAdd(a.counter, 1u);
-    if (prev == gridDim.x - 1) {
-      // last CTA of this rank: my shard has been delivered everywhere
-      *a.counter = 0u;
-      publish(a.pad, BZ_PAD_DONE, a.rank, a.world, a.live_mask, seq);
-    }
+    s_last = (prev == gridDim.x - 1);
+    if (s_last) *a.counter = 0u;
   }
+  __syncthreads();
+  if (s_last) {
+    // last CTA of this rank: my shard has been delivered everywhere
+    publish(a.pad, BZ_PAD_DONE, a.rank, a.world, a.live_mask, seq);
+    if (a.trace != nullptr && threadIdx.x == 0) a.trace[3] = globaltimer_ns();
+  }
+  stamp(a.trace, 2);
   if (a.upd.count <= 0 && a.world == 1) return;
   if (!wait_all(my_pad + BZ_PAD_DONE, a.world, a.live_mask, seq, a.status, 2, a.spin_ns)) return;
+  stamp(a.trace, 4);
   if (a.upd.count > 0) {
     const float* agg = a.agg[a.rank];
     const long long nvec4 = a.rng_len / 4;
@@ -148,6 +168,7 @@ __device__ __forceinline__ void finish_round(const BzFusedPsArgs& a, uint32_t se
       sgd_apply<1>(a.upd, j, g);
     }
   }
+  stamp(a.trace, 5);
 }
 
 __device__ __forceinline__ uint32_t flag_seq(const BzFusedPsArgs& a) {
@@ -160,9 +181,11 @@ __global__ void __launch_bounds__(kThreads) fused_ps_cw_kernel(const __grid_cons
   uint32_t* my_pad = a.pad[a.rank];
   const uint32_t seq = flag_seq(a);
   // ---- phase 0: publish readiness of my gradient rows (this bucket) -----------
-  if (blockIdx.x == 0 && threadIdx.x == 0) publish(a.pad, BZ_PAD_READY, a.rank, a.world, a.live_mask, seq);
+  stamp(a.trace, 0);
+  if (blockIdx.x == 0) publish(a.pad, BZ_PAD_READY, a.rank, a.world, a.live_mask, seq);
   // ---- phase 1: gather + select + broadcast my shard ---------------------------
   if (!wait_all(my_pad + BZ_PAD_READY, a.world, a.live_mask, seq, a.status, 1, a.spin_ns)) return;
+  stamp(a.trace, 1);
   {
     const long long nvec = a.shard_len / V;
     const long long stride = (long long)gridDim.x * kThreads;
@@ -184,8 +207,10 @@ __global__ void __launch_bounds__(kThreads) fused_ps_wsum_kernel(const __grid_co
   const uint32_t seq = flag_seq(a);
   const int n = a.n;
   for (int i = threadIdx.x; i < BZ_MAXN; i += kThreads) ws[i] = (i < n) ? a.W[i] * a.scales.s[i] : 0.f;
-  if (blockIdx.x == 0 && threadIdx.x == 0) publish(a.pad, BZ_PAD_READY, a.rank, a.world, a.live_mask, seq);
+  stamp(a.trace, 0);
+  if (blockIdx.x == 0) publish(a.pad, BZ_PAD_READY, a.rank, a.world, a.live_mask, seq);
   if (!wait_all(my_pad + BZ_PAD_READY, a.world, a.live_mask, seq, a.status, 1, a.spin_ns)) return;
+  stamp(a.trace, 1);
   {
     const long long nvec = a.shard_len / 4;
     const long long stride = (long long)gridDim.x * kThreads;
@@ -222,7 +247,7 @@ __global__ void __launch_bounds__(kThreads) fused_ps_wsum_kernel(const __grid_co
 __global__ void flag_barrier_kernel(const __grid_constant__ BzFlagBarrierArgs a) {
   const uint32_t epoch = *a.epoch_ptr;
   const uint32_t seq = a.seq_mul ? epoch * a.seq_mul + a.seq_add : epoch;
-  if (threadIdx.x == 0) publish(a.pad, a.slot, a.rank, a.world, a.live_mask, seq);
+  publish(a.pad, a.slot, a.rank, a.world, a.live_mask, seq);
   wait_all(a.pad[a.rank] + a.slot, a.world, a.live_mask, seq, a.status, 4, a.spin_ns);
 }
 
@@ -235,7 +260,7 @@ __global__ void gram_exchange_kernel(const __grid_constant__ BzGramExchangeArgs 
     for (int t = threadIdx.x; t < nn; t += blockDim.x) dst[t] = a.local[t];
   }
   __syncthreads();
-  if (threadIdx.x == 0) publish(a.pad, BZ_PAD_GRAM, a.rank, a.world, a.live_mask, epoch);
+  publish(a.pad, BZ_PAD_GRAM, a.rank, a.world, a.live_mask, epoch);
   if (!wait_all(a.pad[a.rank] + BZ_PAD_GRAM, a.world, a.live_mask, epoch, a.status, 8, a.spin_ns)) return;
   const double* mine = a.slots[a.rank];
   for (int t = threadIdx.x; t < nn; t += blockDim.x) {
@@ -258,7 +283,7 @@ __global__ void __launch_bounds__(1024) gram_exchange_nvls_kernel(const __grid_c
   double* mine = a.slots[a.rank];            // slot 0: my partial, slot 1 (at + nn): the total
   for (int t = threadIdx.x; t < nn; t += blockDim.x) mine[t] = a.local[t];
   __syncthreads();
-  if (threadIdx.x == 0) publish(a.pad, BZ_PAD_GRAM, a.rank, a.world, a.live_mask, 2u * epoch);
+  publish(a.pad, BZ_PAD_GRAM, a.rank, a.world, a.live_mask, 2u * epoch);
   if (!wait_all(a.pad[a.rank] + BZ_PAD_GRAM, a.world, a.live_mask, 2u * epoch, a.status, 8, a.spin_ns)) return;
   // my slice of the matrix: elements t with (t / 32) % live == my index among the live ranks
   int live = 0, idx = 0;
@@ -274,7 +299,7 @@ __global__ void __launch_bounds__(1024) gram_exchange_nvls_kernel(const __grid_c
     asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(a.slots_mc + nn + t), "d"(v) : "memory");
   }
   __syncthreads();
-  if (threadIdx.x == 0) publish(a.pad, BZ_PAD_GRAM, a.rank, a.world, a.live_mask, 2u * epoch + 1u);
+  publish(a.pad, BZ_PAD_GRAM, a.rank, a.world, a.live_mask, 2u * epoch + 1u);
   if (!wait_all(a.pad[a.rank] + BZ_PAD_GRAM, a.world, a.live_mask, 2u * epoch + 1u, a.status, 8, a.spin_ns)) return;
   for (int t = threadIdx.x; t < nn; t += blockDim.x) {
     double v;
@@ -318,6 +343,7 @@ int dispatch_mode(const BzFusedPsArgs& a, int sm_count, cudaStream_t stream, boo
 }
 
 __global__ void bump_u32_kernel(uint32_t* p) { *p = *p + 1u; }
+__global__ void stamp_kernel(unsigned long long* dst) { *dst = globaltimer_ns(); }
 
 // normalise the optional fields of the argument block (callers from before buckets existed)
 BzFusedPsArgs normalised(const BzFusedPsArgs& in) {
@@ -342,6 +368,11 @@ bool ranges_ok(const BzFusedPsArgs& a) {
 
 int bz_bump_u32(uint32_t* p, cudaStream_t stream) {
   bump_u32_kernel<<<1, 1, 0, stream>>>(p);
+  return (int)cudaGetLastError();
+}
+
+int bz_stamp(unsigned long long* dst, cudaStream_t stream) {
+  stamp_kernel<<<1, 1, 0, stream>>>(dst);
   return (int)cudaGetLastError();
 }
 

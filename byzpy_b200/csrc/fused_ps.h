@@ -34,6 +34,10 @@ struct BzFusedPsArgs {
   // with nb buckets: seq_mul = nb, seq_add = b), so one word per (kind, rank) serves every bucket.
   uint32_t seq_mul, seq_add;
   unsigned long long spin_ns;  // wall-clock budget of every flag wait (0 = default 20 s)
+  // Optional device-side timeline of this launch (nullptr = off): 8 %globaltimer stamps [ns] --
+  // 0 kernel start, 1 ready wait over, 2 block 0 finished phase 1, 3 last CTA finished phase 1,
+  // 4 delivery wait over, 5 block 0 finished the optimizer step (utils/tracing.py renders them).
+  unsigned long long* trace;
   unsigned int* counter;    // local CTA arrival counter (zero-initialised)
   int* status;              // local error word (0 == ok)
   UpdTable upd;             // local replicas to update in phase 2
@@ -43,6 +47,8 @@ struct BzFusedPsArgs {
 
 int bz_fused_ps_cw(const BzFusedPsArgs* args, int sm_count, cudaStream_t stream);
 int bz_bump_u32(uint32_t* p, cudaStream_t stream);
+// *dst = %globaltimer [ns] when the stream reaches this point (round timelines, utils/tracing.py)
+int bz_stamp(unsigned long long* dst, cudaStream_t stream);
 
 // Gram-family round pieces -------------------------------------------------------------
 // Fused  Y = W (S X)  on this rank's shard + broadcast + SGD (same protocol as bz_fused_ps_cw).

@@ -39,7 +39,7 @@ void fill_common(BzFusedPsArgs& a, const std::vector<uint64_t>& rows, const std:
                  uint64_t epoch_ptr, uint64_t counter, uint64_t status, const std::vector<uint64_t>& upd_params,
                  const std::vector<uint64_t>& upd_moms, float lr, float mu, float wd, int grid_limit,
                  long long rng_off, long long rng_len, uint32_t seq_mul, uint32_t seq_add, uint64_t agg_mc,
-                 uint32_t live_mask, double spin_s) {
+                 uint32_t live_mask, double spin_s, uint64_t trace = 0) {
   std::memset(&a, 0, sizeof(a));
   if (rows.empty() || rows.size() > BZ_MAXN) throw std::invalid_argument("rows");
   if (agg.size() != pads.size() || agg.empty() || agg.size() > BZ_MAXW) throw std::invalid_argument("agg/pads");
@@ -66,6 +66,7 @@ void fill_common(BzFusedPsArgs& a, const std::vector<uint64_t>& rows, const std:
   a.seq_mul = seq_mul;
   a.seq_add = seq_add;
   a.spin_ns = (unsigned long long)(spin_s * 1e9);
+  a.trace = as_ptr<unsigned long long>(trace);
   a.counter = as_ptr<unsigned int>(counter);
   a.status = as_ptr<int>(status);
   if (upd_params.size() > BZ_MAXR) throw std::invalid_argument("too many replicas");
@@ -226,6 +227,9 @@ void bz_bind_runtime(py::module_& m) {
   m.attr("PAD_DONE") = BZ_PAD_DONE;
   m.attr("PAD_GRAM") = BZ_PAD_GRAM;
 
+  m.def("stamp", [](uint64_t p, uint64_t stream) {
+    if (bz_stamp(as_ptr<unsigned long long>(p), as_stream(stream)) != 0) throw std::runtime_error("stamp failed");
+  });
   m.def("bump_u32", [](uint64_t p, uint64_t stream) {
     int e = bz_bump_u32(as_ptr<uint32_t>(p), as_stream(stream));
     if (e != 0) throw std::runtime_error("bump_u32 failed");
@@ -242,11 +246,11 @@ void bz_bind_runtime(py::module_& m) {
          const std::vector<uint64_t>& upd_params, const std::vector<uint64_t>& upd_moms, float lr,
          float mu, float wd, int sm_count, uint64_t stream, int grid_limit, long long rng_off,
          long long rng_len, uint32_t seq_mul, uint32_t seq_add, uint64_t agg_mc, uint32_t live_mask,
-         double spin_s) {
+         double spin_s, uint64_t trace) {
         BzFusedPsArgs a;
         fill_common(a, rows, scales, d, shard_off, shard_len, rank, agg, pads, epoch, epoch_ptr, counter, status,
                     upd_params, upd_moms, lr, mu, wd, grid_limit, rng_off, rng_len, seq_mul, seq_add, agg_mc,
-                    live_mask, spin_s);
+                    live_mask, spin_s, trace);
         a.virt.count = n_virtual;
         a.virt.n_honest = n_honest;
         a.virt.a = va;
@@ -264,5 +268,6 @@ void bz_bind_runtime(py::module_& m) {
       py::arg("counter"), py::arg("status"), py::arg("upd_params"), py::arg("upd_moms"),
       py::arg("lr"), py::arg("mu"), py::arg("wd"), py::arg("sm_count"), py::arg("stream"),
       py::arg("grid_limit") = 0, py::arg("rng_off") = 0, py::arg("rng_len") = 0, py::arg("seq_mul") = 0,
-      py::arg("seq_add") = 0, py::arg("agg_mc") = 0, py::arg("live_mask") = 0, py::arg("spin_s") = 0.0);
+      py::arg("seq_add") = 0, py::arg("agg_mc") = 0, py::arg("live_mask") = 0, py::arg("spin_s") = 0.0,
+      py::arg("trace") = 0);
 }

@@ -21,6 +21,7 @@ honest node (and Byzantine ones when ``update_byzantines``).
 from __future__ import annotations
 
 import contextlib
+import os
 from dataclasses import dataclass, field
 from typing import Callable, List, Optional, Sequence, Tuple
 
@@ -304,7 +305,7 @@ class DeviceRound:
                  overlap_wgrad: bool = True, branch_streams: bool = True,
                  buckets: Optional[int] = None, bucket_cuts: Sequence[float] = (0.40, 0.75, 0.93),
                  min_bucket: int = 1 << 16, overlap_grid: Optional[int] = None,
-                 spin_seconds: float = 0.0, multicast: Optional[bool] = None):
+                 spin_seconds: float = 0.0, multicast: Optional[bool] = None, trace: bool = False):
         if not torch.cuda.is_available():
             raise RuntimeError("DeviceRound needs a CUDA device (B200)")
         # replica shapes are static for the lifetime of a round engine (they are baked into its CUDA
@@ -387,12 +388,16 @@ class DeviceRound:
         self._consumed = [torch.cuda.Event(), torch.cuda.Event()]
         self._prefetched = [False, False]
         worker_streams = max(1, min(int(worker_streams), max(L, 1)))   # never more streams than local replicas
-        self._side_streams = [torch.cuda.Stream(self.device) for _ in range(worker_streams - 1)]
+        # model work runs on high-priority streams (the aggregation stream keeps the default, lowest
+        # priority): when both have CTAs pending, the block scheduler serves backward first
+        hp = dict(priority=-1)
+        self._capture_stream = torch.cuda.Stream(self.device, **hp)
+        self._side_streams = [torch.cuda.Stream(self.device, **hp) for _ in range(worker_streams - 1)]
         # one weight-gradient stream per worker stream: backward's dgrad chain stays on the worker
         # stream, the wgrad GEMMs of the same replica overlap with it
-        self._wgrad_streams = ([torch.cuda.Stream(self.device) for _ in range(1 + len(self._side_streams))]
+        self._wgrad_streams = ([torch.cuda.Stream(self.device, **hp) for _ in range(1 + len(self._side_streams))]
                                if (direct_grads and overlap_wgrad) else [])
-        self._branch_streams = ([torch.cuda.Stream(self.device) for _ in range(1 + len(self._side_streams))]
+        self._branch_streams = ([torch.cuda.Stream(self.device, **hp) for _ in range(1 + len(self._side_streams))]
                                 if (direct_grads and branch_streams) else [])
         if direct_grads:
             for i, w in enumerate(self.workers):
@@ -403,14 +408,25 @@ class DeviceRound:
         self.launches_per_step = 0
         self.model_launches_per_step = 0
         self.spin_seconds = float(spin_seconds)
+        # device-side round timeline (%globaltimer stamps written by tiny kernels and by the fused
+        # kernels themselves): [0] round start, [1] backward done, [2] round done, [16+k] bucket k
+        # produced locally, [32+8k ..] the 6 stamps of bucket k's launch (csrc/fused_ps.h)
+        self._trace = torch.zeros(128, dtype=torch.int64, device=self.device) if trace else None
         self.live_mask = 0                      # 0 = every rank takes part (see recover())
         self._agg_stream = torch.cuda.Stream(self.device)
         self._agg_mc = self.sym.mc_ptr(self._off_agg) if (multicast is not False) else 0
         if multicast and not self._agg_mc:
             raise RuntimeError("multicast=True but the symmetric heap has no NVLS multicast mapping")
-        # overlapped bucket launches share the SMs with backward: one CTA per SM keeps NVLink busy
-        # (32 KB of 16-byte loads in flight per SM) without taking the register file from cuDNN
-        self.overlap_grid = int(overlap_grid) if overlap_grid is not None else (self.sm if self.world > 1 else 2 * self.sm)
+        # Overlapped bucket launches share the GPU with backward.  A CTA of the fused kernel parked on
+        # an SM (it waits for the peers' flags, then streams over NVLink) keeps cuDNN kernels that need
+        # a whole SM's registers / shared memory off that SM, so an overlapped launch only takes a
+        # QUARTER of the SMs: one CTA per SM on all of them delayed backward by 250 us per round at
+        # 8 GPUs, more than the overlap saved (profiles/round_timeline.md).  The head bucket, launched
+        # after backward, uses the full grid.
+        env_grid = os.environ.get("BYZPY_OVERLAP_GRID")
+        if overlap_grid is None and env_grid:
+            overlap_grid = int(env_grid)
+        self.overlap_grid = int(overlap_grid) if overlap_grid is not None else max(8, self.sm // 4)
         self._bounds: List[int] = [0, self.d_pad]     # bucket k = [bounds[k+1], bounds[k]) walking from the tail
         self._buckets_validated = True
         if isinstance(plan, CwPlan) and (buckets is None or buckets > 1):
@@ -475,11 +491,37 @@ class DeviceRound:
         self._in_round = False
         self._use_buckets = self.n_buckets > 1
 
+    def _stamp(self, slot: int) -> None:
+        if self._trace is not None:
+            self.ext.stamp(self._trace.data_ptr() + 8 * slot, torch.cuda.current_stream(self.device).cuda_stream)
+
+    def timeline(self) -> dict:
+        """The last round's device timeline in microseconds relative to the round's start
+        (``trace=True``): when backward finished, when each bucket was produced locally, and the
+        phases of every bucket launch."""
+        if self._trace is None:
+            raise RuntimeError("construct the round with trace=True")
+        t = self._trace.cpu().tolist()
+        t0 = t[0]
+        us = lambda v: None if v == 0 else round((v - t0) / 1e3, 1)      # noqa: E731
+        out = {"backward_done": us(t[1]), "round_done": us(t[2]), "buckets": []}
+        nb = self.n_buckets if self._use_buckets else 1
+        for k in range(nb):
+            b = t[32 + 8 * k: 32 + 8 * k + 6]
+            off, ln = self.bucket_range(k) if nb > 1 else (0, self.d_pad)
+            out["buckets"].append({"elements": ln, "produced": us(t[16 + k]) if nb > 1 else us(t[1]),
+                                   "start": us(b[0]), "ready_wait_done": us(b[1]), "block0_phase1_done": us(b[2]),
+                                   "all_ctas_phase1_done": us(b[3]), "delivery_wait_done": us(b[4]),
+                                   "sgd_done": us(b[5])})
+        return out
+
     def _on_mark(self, worker: DeviceWorker, k: int, events: list) -> None:
         if not self._in_round or not self._use_buckets:
             return
         self._bk_events[k].extend(events)
         self._bk_count[k] += 1
+        if self._trace is not None and self._bk_count[k] >= self.L:
+            self._stamp(16 + k)
         self._launch_ready_buckets()
 
     def _launch_ready_buckets(self) -> None:
@@ -566,6 +608,7 @@ class DeviceRound:
             self._upd_params, self._upd_moms, self.lr, self.momentum, self.weight_decay,
             self.sm, stream, grid_limit, off, ln, nb, k, self._agg_mc,
             self.live_mask, self.spin_seconds,
+            0 if self._trace is None else self._trace.data_ptr() + 8 * (32 + 8 * (0 if whole else k)),
         )
         self._round_launches += 1
 
@@ -688,6 +731,7 @@ class DeviceRound:
         main = torch.cuda.current_stream(self.device)
         l0 = ops.launches()
         bucketed = isinstance(self.plan, CwPlan) and self._use_buckets
+        self._stamp(0)
         if bucketed:
             # the round's epoch is bumped up front: bucket launches are enqueued from inside backward
             self.ext.bump_u32(self.ctl.data_ptr() + 8, main.cuda_stream)
@@ -702,8 +746,10 @@ class DeviceRound:
         finally:
             self._in_round = False
         self.model_launches_per_step = ops.launches() - l0   # this library's BN / pooling kernels
+        self._stamp(1)
         if not bucketed:
             self.launch_aggregate()
+            self._stamp(2)
             return
         # buckets whose mark never fired (or ranks without a replica) and the head bucket: after the
         # whole backward pass, on the aggregation stream, full grid
@@ -715,6 +761,7 @@ class DeviceRound:
                 self._launch_cw_bucket(self._next_bucket, 0 if last else self.overlap_grid)
                 self._next_bucket += 1
         main.wait_stream(agg)
+        self._stamp(2)
         self.launches_per_step = self._round_launches
 
     def _run_replicas(self, main) -> None:
@@ -796,7 +843,7 @@ class DeviceRound:
         if not self._buckets_validated:
             self._validate_buckets()
         snap = self._snapshot()
-        s = torch.cuda.Stream(self.device)
+        s = self._capture_stream
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
             for _ in range(warmup):
@@ -807,7 +854,7 @@ class DeviceRound:
             dist.barrier(group=self.group)
         g = torch.cuda.CUDAGraph()
         other = self._graphs[1 - self._buf]
-        with torch.cuda.graph(g, **({"pool": other.pool()} if other is not None else {})):
+        with torch.cuda.graph(g, stream=self._capture_stream, **({"pool": other.pool()} if other is not None else {})):
             self._body()
         self._graphs[self._buf] = g
         self._restore(snap)
