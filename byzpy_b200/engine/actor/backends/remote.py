@@ -126,7 +126,11 @@ class RemoteActorServer:
     scheme = "tcp"
     gpu_direct = False
 
-    def __init__(self, host: str = "0.0.0.0", port: int = 29000) -> None:
+    def __init__(self, host: str = "127.0.0.1", port: int = 29000) -> None:
+        # Frames are unpickled: whoever can reach the port can run code in this process.  The default
+        # therefore binds the loopback interface; pass the interface to expose explicitly
+        # (``host="0.0.0.0"``) on a trusted network only -- the reference has no default and its
+        # examples bind 0.0.0.0 (reference engine/actor/backends/remote.py:264-290).
         self.host, self.port = host, int(port)
         self._actors: Dict[str, Any] = {}
         self._mailboxes: Dict[str, Dict[str, asyncio.Queue]] = {}

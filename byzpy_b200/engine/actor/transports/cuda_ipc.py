@@ -42,6 +42,8 @@ def loads(data: bytes) -> Any:
 def _to_host(obj: Any) -> Any:
     if isinstance(obj, torch.Tensor):
         return obj.detach().cpu()
+    if isinstance(obj, tuple) and hasattr(obj, "_fields"):      # namedtuple (e.g. channels.Endpoint)
+        return type(obj)(*(_to_host(x) for x in obj))
     if isinstance(obj, (list, tuple)):
         return type(obj)(_to_host(x) for x in obj)
     if isinstance(obj, dict):

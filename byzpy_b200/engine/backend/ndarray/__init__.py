@@ -59,8 +59,11 @@ class _TorchBackend:
     def index_select(self, x, axis: int, indices):
         return torch.index_select(x, axis, torch.as_tensor(indices, device=x.device))
 
-    def max(self, x):
-        return x.max()
+    def max(self, x, axis=None):
+        return x.max() if axis is None else torch.amax(x, dim=axis)
+
+    def take_along_axis(self, a, indices, axis: int = 0):
+        return torch.take_along_dim(a, torch.as_tensor(indices, device=a.device), dim=axis)
 
 
 class _NumpyBackend:
@@ -112,8 +115,11 @@ class _NumpyBackend:
     def index_select(self, x, axis: int, indices):
         return np.take(x, np.asarray(indices), axis=axis)
 
-    def max(self, x):
-        return np.max(x)
+    def max(self, x, axis=None):
+        return np.max(x, axis=axis)
+
+    def take_along_axis(self, a, indices, axis: int = 0):
+        return np.take_along_axis(a, np.asarray(indices), axis=axis)
 
 
 _BACKENDS = {"torch": _TorchBackend, "numpy": _NumpyBackend}
@@ -126,4 +132,4 @@ def get_array_backend(name: str = "torch"):
         raise ValueError(f"unknown backend {name!r}; choose 'torch' or 'numpy'") from None
 
 
-__all__ = ["get_array_backend"]
+__all__ = ["get_array_backend", "_TorchBackend", "_NumpyBackend"]

@@ -163,6 +163,17 @@ class ParameterServer:
         if not isinstance(self.pre, LinearPreAggregator):
             return None
         import numpy as np
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 \
+                and getattr(self.pre, "perm", 0) is None and hasattr(self.pre, "rng"):
+            # every rank solves the n-space problem itself, so a randomised map (Bucketing without a
+            # fixed ``perm``) must draw the SAME permutation on every rank: share one seed
+            import random
+
+            box = [random.SystemRandom().getrandbits(63)]
+            dist.broadcast_object_list(box, src=0)
+            self.pre.rng = random.Random(box[0])
 
         pre = self.pre
         pre._validate(n_rows)

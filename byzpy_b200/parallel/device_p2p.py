@@ -333,6 +333,16 @@ class DeviceP2PRound:
             self._body()
         return self.losses
 
+    def replay(self) -> torch.Tensor:
+        """One more round on the batches already staged on the device (no H2D copy)."""
+        if self.use_cuda_graph:
+            if self._graph is None:
+                self.capture()
+            self._graph.replay()
+        else:
+            self._body()
+        return self.losses
+
     def read_losses(self) -> torch.Tensor:
         self.losses_host.copy_(self.losses, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()

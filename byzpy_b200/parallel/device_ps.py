@@ -921,6 +921,22 @@ class DeviceRound:
             self._buf = nb
         return self.losses
 
+    def replay(self) -> torch.Tensor:
+        """Run one more round on the batches already resident in the active input buffers (no H2D
+        copy): the device-only form of :meth:`step`, for kernel-level timing."""
+        refresh = getattr(self.plan, "refresh", None)
+        if refresh is not None:
+            refresh()
+        if self.use_cuda_graph:
+            if self._graphs[self._buf] is None:
+                self.capture()
+            self._graphs[self._buf].replay()
+        else:
+            if not self._buckets_validated:
+                self._validate_buckets()
+            self._body()
+        return self.losses
+
     def read_losses(self) -> torch.Tensor:
         """Device->host read of the round's losses (synchronises the stream).  The fused kernels'
         status word rides along in the same copy: a flag-wait timeout raises here instead of

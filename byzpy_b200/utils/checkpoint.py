@@ -73,7 +73,9 @@ def save_checkpoint(path: str, ps, *, round_index: Optional[int] = None, extra: 
 
 def load_checkpoint(path: str, ps, *, strict: bool = True, restore_rng: bool = True) -> int:
     """Restores models, momentum/optimizer state and RNG; returns the saved round index."""
-    blob = torch.load(path, map_location="cpu", weights_only=False)
+    # the blob holds only tensors, dicts, lists and scalars: the restricted unpickler is enough, and a
+    # checkpoint file obtained from elsewhere cannot run code when loaded
+    blob = torch.load(path, map_location="cpu", weights_only=True)
     if blob.get("format") != FORMAT:
         raise ValueError(f"not a {FORMAT} checkpoint: {blob.get('format')!r}")
     nodes = blob["nodes"]
