@@ -57,5 +57,20 @@ class CAF(GramAggregator):
         w[:n] = nspace.caf_coeffs(G, n, self.f, power_iters=self.power_iters)
         return w
 
+    # ---- sm_100a path: the filter loop is one single-CTA kernel on the device Gram (csrc/nspace_maps.cu)
+    device_solve = True
+
+    def _solve_device(self, G: torch.Tensor, n: int):
+        from ...ops import nspace_cuda
+
+        return nspace_cuda.caf_coeffs(G, n, self.f, power_iters=self.power_iters)
+
+    def _device_solve_feasible(self, n: int) -> bool:
+        return n <= 127
+
+    def _fused_aux(self):
+        # the fused round appends the fixed start direction as a constant auxiliary row
+        return (("const", _start_direction),)
+
 
 __all__ = ["CAF"]

@@ -408,6 +408,17 @@ PYBIND11_MODULE(_C, m) {
           "nspace_cclip");
   });
 
+  m.def("nspace_preagg", [](uint64_t G, int n, int mode, double param, int iparam, uint64_t W, uint64_t W32,
+                            uint64_t stream) {
+    check(bz_nspace_preagg(as_ptr<const double>(G), n, mode, param, iparam, as_ptr<double>(W), as_ptr<float>(W32),
+                           as_stream(stream)),
+          "nspace_preagg");
+  });
+  m.def("nspace_caf", [](uint64_t G, int n, int f, int power_iters, uint64_t out, uint64_t stream) {
+    check(bz_nspace_caf(as_ptr<const double>(G), n, f, power_iters, as_ptr<float>(out), as_stream(stream)),
+          "nspace_caf");
+  });
+
   bz_bind_runtime(m);
   bz_bind_vmm(m);
 }

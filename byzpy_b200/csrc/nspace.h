@@ -15,3 +15,11 @@ unsigned long long bz_binomial(int n, int k);
 int bz_nspace_subset_blocks(int n, int m, int sm_count);
 int bz_nspace_subset(const double* G, int ldg, int n, int m, int nt, int mode, double* scratch_score,
                      unsigned long long* scratch_rank, float* w, int sm_count, cudaStream_t stream);
+
+// nspace_maps.cu -------------------------------------------------------------------------------
+// Row map of a pre-aggregator as an (n, n) fp64 matrix on the device: mode 0 clip (param =
+// threshold), 1 ARC (iparam = f), 2 nearest-neighbour mixing (iparam = f).  W32 (optional): fp32 copy.
+int bz_nspace_preagg(const double* G, int n, int mode, double param, int iparam, double* W, float* W32,
+                     cudaStream_t stream);
+// CAF filter on the (n+1, n+1) Gram of [rows; start direction]; out: n+1 weights.
+int bz_nspace_caf(const double* G, int n, int f, int power_iters, float* out, cudaStream_t stream);

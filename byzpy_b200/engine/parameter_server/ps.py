@@ -192,10 +192,16 @@ class ParameterServer:
                 else:
                     state["W"].copy_(torch.from_numpy(Wn), non_blocking=True)
 
+        device_map = type(pre).row_map_device is not LinearPreAggregator.row_map_device
+
         def solver(G: torch.Tensor) -> torch.Tensor:
             if pre.needs_gram:
-                Wp = torch.from_numpy(np.asarray(pre.row_map(G.detach().double().cpu().numpy(), n_rows),
-                                                 dtype=np.float64)).to(G.device)
+                # the map of Clipping / ARC / NNM is a single-CTA kernel on the device Gram
+                # (csrc/nspace_maps.cu): no host round trip, the round stays CUDA-graph capturable
+                Wp = pre.row_map_device(G.double(), n_rows) if (device_map and G.is_cuda) else None
+                if Wp is None:
+                    Wp = torch.from_numpy(np.asarray(pre.row_map(G.detach().double().cpu().numpy(), n_rows),
+                                                     dtype=np.float64)).to(G.device)
             else:
                 if state["W"] is None:
                     refresh()
@@ -205,7 +211,7 @@ class ParameterServer:
             return (w2.double() @ Wp).float()
 
         return GramPlan(solver, f"{pre.name}+{inner.name}", aux=(),
-                        capturable=inner.capturable and not pre.needs_gram,
+                        capturable=inner.capturable and (device_map or not pre.needs_gram),
                         refresh=None if pre.needs_gram else refresh)
 
     def step(self, batches=None) -> torch.Tensor:
@@ -215,6 +221,15 @@ class ParameterServer:
             raise RuntimeError("step() is only available on the fused device path; use round()")
         self.rounds += 1
         return self.device_round.step(batches)
+
+    def recover(self) -> List[int]:
+        """Device path: after a fused round timed out on a silent rank (``read_losses`` raised), drop
+        that rank's rows, rebuild the aggregation plan for the remaining ones and resynchronise the
+        replicas (:meth:`DeviceRound.recover`).  Returns the dropped ranks.  The generic path handles
+        failures per call (``node_timeout`` / ``tolerate_failures``)."""
+        if self.device_round is None:
+            raise RuntimeError("recover() applies to the fused device path")
+        return self.device_round.recover(self._fused_plan)
 
     # ------------------------------------------------------------------- generic path
     async def _guarded(self, kind: str, idx: int, node: Any, method: str, *args):

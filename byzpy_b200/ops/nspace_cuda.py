@@ -114,7 +114,47 @@ def monna_weights(G: torch.Tensor, n: int, f: int, reference_index: int) -> torc
     return w
 
 
-__all__ = ["krum_weights", "weiszfeld_coeffs", "centered_clip_coeffs", "cge_weights", "monna_weights"]
+def _preagg(G: torch.Tensor, n: int, mode: int, param: float, iparam: int, want32: bool):
+    ext = _ready(G, "nspace_preagg")
+    if ext is None or G.shape[0] != n or G.shape[1] != n:
+        return None
+    G = G.contiguous().double()
+    W = torch.empty((n, n), dtype=torch.float64, device=G.device)
+    W32 = torch.empty((n, n), dtype=torch.float32, device=G.device) if want32 else None
+    ext.nspace_preagg(G.data_ptr(), n, mode, float(param), int(iparam), W.data_ptr(),
+                      W32.data_ptr() if W32 is not None else 0, _stream(G.device))
+    return (W, W32) if want32 else W
+
+
+def clip_matrix(G: torch.Tensor, threshold: float, *, want32: bool = False):
+    """``diag(min(1, threshold / ||x_i||))`` as an (n, n) device matrix (``ops.nspace.clip_scales``)."""
+    return _preagg(G, G.shape[0], 0, threshold, 0, want32)
+
+
+def arc_matrix(G: torch.Tensor, f: int, *, want32: bool = False):
+    """Adaptive robust clipping map (``ops.nspace.arc_scales``) on the device."""
+    return _preagg(G, G.shape[0], 1, 0.0, f, want32)
+
+
+def nnm_matrix(G: torch.Tensor, f: int, *, want32: bool = False):
+    """Nearest-neighbour mixing matrix (``ops.nspace.nnm_matrix``) on the device."""
+    return _preagg(G, G.shape[0], 2, 0.0, f, want32)
+
+
+def caf_coeffs(G: torch.Tensor, n: int, f: int, *, power_iters: int) -> Optional[torch.Tensor]:
+    """CAF weights over the n rows (+ a zero for the start-direction row) from the (n+1, n+1) Gram
+    of ``[rows; r]`` (``ops.nspace.caf_coeffs``) -- the whole filter loop in one single-CTA kernel."""
+    ext = _load_ext()
+    if ext is None or not hasattr(ext, "nspace_caf") or not G.is_cuda or n > 127 or G.shape[0] != n + 1:
+        return None
+    G = G.contiguous().double()
+    w = torch.empty(n + 1, dtype=torch.float32, device=G.device)
+    ext.nspace_caf(G.data_ptr(), int(n), int(f), int(power_iters), w.data_ptr(), _stream(G.device))
+    return w
+
+
+__all__ = ["krum_weights", "weiszfeld_coeffs", "centered_clip_coeffs", "cge_weights", "monna_weights",
+           "clip_matrix", "arc_matrix", "nnm_matrix", "caf_coeffs"]
 
 
 SUBSET_MAX_N = 24

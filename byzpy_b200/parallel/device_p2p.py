@@ -194,6 +194,9 @@ class DeviceP2PRound:
             nt = len(self._tables[i]) + len(p.plan.aux)
             dev = self.device
             ws["aux"] = [torch.zeros(self.d_pad, dtype=torch.float32, device=dev) for _ in p.plan.aux]
+            for kind, buf in zip(p.plan.aux, ws["aux"]):       # constant rows (CAF's start direction): filled once
+                if isinstance(kind, tuple) and kind[0] == "const":
+                    buf[: self.d].copy_(kind[1](self.d, buf).to(torch.float32))
             ws["G32"] = torch.zeros((nt, nt), dtype=torch.float32, device=dev)
             ws["G64"] = torch.zeros((nt, nt), dtype=torch.float64, device=dev)
             ws["T32"] = torch.zeros((nt, nt), dtype=torch.float32, device=dev)
@@ -248,8 +251,9 @@ class DeviceP2PRound:
         fused_median = tuple(plan.aux) == ("median",) and len(rows) <= 16
         if not fused_median:
             for kind, buf in zip(plan.aux, ws["aux"]):
-                ext.cw_select(rows, [], ops.MODE_MEDIAN, 0, 0, 0, 0.0, 0.0, 0, d, buf.data_ptr(), [], [], 0.0,
-                              0.0, 0.0, self.sm, stream)
+                if kind == "median":
+                    ext.cw_select(rows, [], ops.MODE_MEDIAN, 0, 0, 0, 0.0, 0.0, 0, d, buf.data_ptr(), [], [], 0.0,
+                                  0.0, 0.0, self.sm, stream)
                 all_rows.append(buf.data_ptr())
         tc = ext.gram_umma_tile_cols(nt)
         main = (d // tc) * tc if nt > 16 else 0

@@ -31,7 +31,10 @@ import torch.nn as nn
 
 from .. import ops
 from .arena import ParamArena, padded_size
-from .symmetric import SymmetricBuffer, _dist_on
+from .symmetric import SymmetricBuffer, _dist_on, tensor_from_ptr
+
+
+PAD_SYNC = 48       # flag words of the recovery / resynchronisation barriers (csrc/fused_ps.h uses 0-39)
 
 
 # --------------------------------------------------------------------------- plans
@@ -49,8 +52,9 @@ class GramPlan:
 
     ``solver(G)`` maps the fp64 Gram of (real rows + aux rows) ON THE DEVICE to the fp32 weight
     vector over the same rows.  ``aux`` lists auxiliary rows the solver expects after the real
-    ones (``"median"`` = coordinate-wise median of the real rows, the Weiszfeld / centered-clipping
-    start point).  ``capturable`` is False when the solver synchronises with the host (MDA, SMEA,
+    ones: ``"median"`` = coordinate-wise median of the real rows (the Weiszfeld / centered-clipping
+    start point), ``("const", make)`` = a constant vector ``make(d, like)`` resident on the device
+    (CAF's fixed power-iteration start direction).  ``capturable`` is False when the solver synchronises with the host (MDA, SMEA,
     CAF searches), which rules out CUDA-graph capture of the round.  ``refresh`` (optional) is
     called on the host before every round (e.g. to draw a new bucketing permutation).
     """
@@ -367,6 +371,10 @@ class DeviceRound:
         self.losses = torch.zeros(L, dtype=torch.float32, device=self.device)
         self.losses_host = torch.zeros(L, dtype=torch.float32).pin_memory()
         self._status_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._fault: Optional[str] = None
+        self._recoveries = 0
+        self._resync_seq = 0
+        self._resync_ctr = torch.zeros(1, dtype=torch.int32, device=self.device)   # epoch word of the resync barriers (stays 0)
         self._round_launches = 0
         self._use_buckets = False
         self._in_round = False
@@ -643,6 +651,11 @@ class DeviceRound:
                           if lay.n_virtual else None)
         self._aux_bufs = [torch.zeros(self.d_pad, dtype=torch.float32, device=dev)
                           for _ in range(self._n_aux)]
+        for kind, buf in zip(self.plan.aux, self._aux_bufs):
+            if isinstance(kind, tuple) and kind[0] == "const":
+                buf[: self.d].copy_(kind[1](self.d, buf).to(torch.float32))
+            elif kind != "median":
+                raise ValueError(f"unknown aux row {kind!r}")
         self._g_local64 = torch.zeros((nt, nt), dtype=torch.float64, device=dev)
         self._g_local32 = torch.zeros((nt, nt), dtype=torch.float32, device=dev)
         self._g_tail64 = torch.zeros((nt, nt), dtype=torch.float64, device=dev)
@@ -681,7 +694,7 @@ class DeviceRound:
             launches += 1
         for kind, buf in zip(plan.aux, self._aux_bufs):
             if kind != "median":
-                raise ValueError(f"unknown aux row {kind!r}")
+                continue                    # constant rows were filled once at set-up
             ext.cw_select(self._real_rows, self._real_scales, ops.MODE_MEDIAN, 0, 0, 0, 0.0, 0.0, off, ln,
                           buf.data_ptr(), [], [], 0.0, 0.0, 0.0, self.sm, stream)
             launches += 1
@@ -850,7 +863,7 @@ class DeviceRound:
                 self._body()
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
-        if self.world > 1:
+        if self.world > 1 and self._recoveries == 0:      # (after a recovery the process group has a dead member)
             dist.barrier(group=self.group)
         g = torch.cuda.CUDAGraph()
         other = self._graphs[1 - self._buf]
@@ -877,6 +890,8 @@ class DeviceRound:
         **double buffered**: as soon as round k is launched, batch k+1 is fetched and copied H2D on a
         copy stream into the other buffer set (its own captured graph), so the copy overlaps the
         round instead of preceding it; round k+1 only waits for that copy's event."""
+        if self._fault == "silent":
+            return self.losses              # test hook: this rank has stopped taking part (inject_fault)
         main = torch.cuda.current_stream(self.device)
         explicit = batches is not None
         b = self._buf
@@ -974,6 +989,106 @@ class DeviceRound:
         torch.cuda.synchronize(self.device)
         self.ctl[0:2].zero_()
         torch.cuda.synchronize(self.device)
+
+    # ------------------------------------------------------------------ failure handling
+    def inject_fault(self, kind: Optional[str] = "silent") -> None:
+        """Test hook: ``"silent"`` makes this rank stop taking part in rounds -- its
+        ``step()`` returns without launching anything, exactly what its peers see when the process
+        hangs; ``None`` clears it.  The peers' fused kernels then time out (``spin_seconds``),
+        report this rank in their status word and can :meth:`recover`."""
+        self._fault = kind
+
+    def silent_ranks(self) -> List[int]:
+        """Ranks named by the sticky status word of the last failed wait."""
+        return self.decode_status(self.status())[1]
+
+    def recover(self, plan_factory: Optional[Callable[[int], object]] = None) -> List[int]:
+        """Drop the ranks that did not arrive and continue with the remaining rows.
+
+        Every surviving rank calls this after a flag wait timed out (``read_losses`` /
+        ``check_status`` raised).  The silent ranks are read from the status word; their gradient
+        rows leave the row table, their flags are no longer awaited and nothing is delivered to
+        them (``live_mask``); the aggregation plan is rebuilt for the smaller row count by
+        ``plan_factory(n_rows)`` (``ParameterServer`` passes ``aggregator.fused_plan``).  Because a
+        failure in the middle of a round can leave the survivors with different sets of applied
+        buckets, the replicas (parameters and momentum) are re-synchronised from the lowest live
+        rank through the symmetric ``agg`` buffer.  Captured graphs are dropped (row tables and
+        masks are baked into them).  Returns the list of dropped ranks.
+
+        The reference has no failure handling on this path: a hung node actor hangs
+        ``ParameterServer.round()`` (reference engine/parameter_server/ps.py:121-144)."""
+        torch.cuda.synchronize(self.device)
+        st = self.status()
+        _, silent = self.decode_status(st)
+        silent = [r for r in silent if r < self.world]
+        if not silent:
+            self.reset_status()
+            return []
+        if self.rank in silent:
+            raise RuntimeError(f"rank {self.rank} was reported silent by itself; cannot recover")
+        live_before = [r for r in range(self.world) if self.live_mask == 0 or (self.live_mask >> r) & 1]
+        live = [r for r in live_before if r not in silent]
+        if not live:
+            raise RuntimeError("no live rank left")
+        self.live_mask = sum(1 << r for r in live)
+        lay = self.layout
+        keep = [g for g in range(lay.n_workers) if lay.rank_of[g] in live]
+        dropped_honest = sum(1 for g in range(lay.n_honest) if lay.rank_of[g] not in live)
+        new_layout = RowLayout(lay.n_honest - dropped_honest,
+                               lay.n_byz_workers - (lay.n_workers - len(keep) - dropped_honest),
+                               lay.n_virtual, lay.world, [lay.rank_of[g] for g in keep],
+                               [lay.slot_of[g] for g in keep])
+        old_rows, old_scales = self._rows, self._scales
+        self._rows = [old_rows[g] for g in keep]
+        self._scales = [old_scales[g] for g in keep]
+        self.layout = new_layout
+        n_rows = new_layout.n_workers + new_layout.n_virtual
+        if plan_factory is not None:
+            plan = plan_factory(n_rows)
+            if plan is None or type(plan) is not type(self.plan):
+                raise RuntimeError(f"no fused plan of the same family for the remaining {n_rows} rows")
+            self.plan = plan
+        if isinstance(self.plan, GramPlan):
+            self._setup_gram_plan()
+        self._graphs = [None, None]
+        self._prefetched = [False, False]
+        # fresh flag numbering: the survivors agree on a new epoch base above anything published so far
+        self._recoveries += 1
+        self.ctl[0:2].zero_()
+        torch.cuda.synchronize(self.device)
+        self._resync_from_lowest_live(live)
+        return silent
+
+    def _resync_from_lowest_live(self, live: List[int]) -> None:
+        """Copy replica 0 of the lowest live rank (parameters, then momentum) into every replica of
+        every live rank: source -> its symmetric agg buffer, device flag barrier among the live
+        ranks, peers read it over NVLink."""
+        src = live[0]
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        pads = [self.sym.peer_ptr(r, self._off_pad) for r in range(self.world)]
+        ctl = self.ctl.data_ptr()
+        view = tensor_from_ptr(self.sym.peer_ptr(src, self._off_agg), self.d_pad * 4, self.device,
+                               owner=self.sym).view(torch.float32)
+        for which in ("params", "moms"):
+            bank = self.params if which == "params" else self.moms
+            if bank is None:
+                continue
+            has = torch.tensor([1 if self.L else 0], device=self.device)
+            if self.rank == src:
+                if not self.L:
+                    raise RuntimeError("the lowest live rank hosts no replica to resynchronise from")
+                self.agg.copy_(bank[0])
+            # two barriers per bank on their own flag words and sequence numbers (PAD_SYNC)
+            for phase in range(2):
+                self._resync_seq += 1
+                self.ext.flag_barrier(pads, self.rank, PAD_SYNC, self._resync_ctr.data_ptr(), ctl + 4, stream,
+                                      1, self._resync_seq, self.live_mask, max(self.spin_seconds, 5.0))
+                if phase == 0 and self.L:
+                    for i in range(self.L):
+                        bank[i].copy_(view)
+            del has
+        torch.cuda.synchronize(self.device)
+        self.check_status()
 
     def aggregated(self) -> torch.Tensor:
         return self.agg[: self.d]

@@ -28,4 +28,9 @@ class ARC(LinearPreAggregator):
         return np.diag(nspace.arc_scales(G, self.f))
 
 
+    def row_map_device(self, G, n):
+        from ..ops import nspace_cuda
+
+        return nspace_cuda.arc_matrix(G, self.f)
+
 __all__ = ["ARC"]

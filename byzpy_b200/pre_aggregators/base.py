@@ -59,6 +59,11 @@ class LinearPreAggregator(PreAggregator):
     def row_map(self, G: Optional[np.ndarray], n: int) -> np.ndarray:
         """(m, n) mixing matrix from the fp64 Gram matrix (``G`` is None when ``needs_gram`` is False)."""
 
+    def row_map_device(self, G: torch.Tensor, n: int) -> Optional[torch.Tensor]:
+        """The same matrix computed ON THE DEVICE from the device Gram (fp64, (m, n)), without a host
+        round trip -- or None when the map has no device kernel (the caller then uses :meth:`row_map`)."""
+        return None
+
     def _materialise(self, rows: List[torch.Tensor], W: np.ndarray, like: torch.Tensor) -> List[torch.Tensor]:
         krows = _kernel_rows(rows)
         Wt = torch.from_numpy(np.asarray(W, dtype=np.float32)).to(rows[0].device)
@@ -77,8 +82,18 @@ class LinearPreAggregator(PreAggregator):
         self._validate(n)
         G = None
         if self.needs_gram:
-            G = ops.gram(_kernel_rows(rows), want64=True,
-                         diag_only=getattr(self, "gram_diag_only", False)).detach().cpu().numpy()
+            Gd = ops.gram(_kernel_rows(rows), want64=True, diag_only=getattr(self, "gram_diag_only", False))
+            if Gd.is_cuda:
+                # sm_100a path: the n-space map is a single-CTA kernel on the device Gram and feeds the
+                # weighted-sum pass directly -- no host synchronisation (reference nnm.py:82-97 also stays
+                # on the input device; its clipping / ARC go through NumPy, clipping.py:53-62)
+                Wd = self.row_map_device(Gd, n)
+                if Wd is not None:
+                    Y = ops.weighted_sum(_kernel_rows(rows), Wd.to(torch.float32))
+                    if like.dim() == 1 and Y.dtype == like.dtype:
+                        return list(Y.unbind(0))
+                    return [finish(Y[i], like) for i in range(Y.shape[0])]
+            G = Gd.detach().cpu().numpy()
         return self._materialise(rows, self.row_map(G, n), like)
 
     # -- subtask path: split-K Gram over feature chunks, then one local materialisation ----

@@ -24,4 +24,9 @@ class Clipping(LinearPreAggregator):
         return np.diag(nspace.clip_scales(G, self.threshold))
 
 
+    def row_map_device(self, G, n):
+        from ..ops import nspace_cuda
+
+        return nspace_cuda.clip_matrix(G, self.threshold)
+
 __all__ = ["Clipping"]

@@ -25,4 +25,9 @@ class NearestNeighborMixing(LinearPreAggregator):
         return nspace.nnm_matrix(G, self.f)
 
 
+    def row_map_device(self, G, n):
+        from ..ops import nspace_cuda
+
+        return nspace_cuda.nnm_matrix(G, self.f)
+
 __all__ = ["NearestNeighborMixing"]

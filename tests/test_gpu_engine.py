@@ -625,3 +625,140 @@ def test_symmetric_buffer_on_the_vmm_heap_single_rank():
     ipc = SymmetricBuffer(1024, torch.device(DEV), kind="ipc")
     assert ipc.kind == "ipc" and ipc.mc_ptr() == 0
     ipc.close()
+
+
+def test_preagg_maps_and_caf_solver_on_device_match_host_oracles():
+    """Clipping / ARC / NNM row maps and the CAF filter as single-CTA kernels on the device Gram
+    (csrc/nspace_maps.cu) against the host oracles of ops/nspace.py, including duplicated rows (ties),
+    a huge-norm row and an all-inf row; and legal inside a CUDA-graph capture."""
+    import numpy as np
+
+    from byzpy_b200.ops import nspace, nspace_cuda
+
+    torch.manual_seed(11)
+    for n, d in [(5, 300), (12, 900), (33, 2000), (64, 4096), (128, 1024)]:
+        X = torch.randn(n, d, dtype=torch.float64)
+        X[1] = X[0]                                  # exact tie in every distance / norm
+        X[2] *= 40.0
+        G = X @ X.T
+        Gd = G.to(DEV)
+        f = max(1, n // 5)
+        np.testing.assert_allclose(nspace_cuda.clip_matrix(Gd, 3.0).cpu().numpy(),
+                                   np.diag(nspace.clip_scales(G.numpy(), 3.0)), rtol=1e-12, atol=1e-14)
+        for ff in (0, f, n - 1):
+            np.testing.assert_allclose(nspace_cuda.arc_matrix(Gd, ff).cpu().numpy(),
+                                       np.diag(nspace.arc_scales(G.numpy(), ff)), rtol=1e-12, atol=1e-14)
+        for ff in (0, f, n - 1):
+            np.testing.assert_allclose(nspace_cuda.nnm_matrix(Gd, ff).cpu().numpy(), nspace.nnm_matrix(G.numpy(), ff),
+                                       rtol=1e-12, atol=1e-14)
+        W64, W32 = nspace_cuda.nnm_matrix(Gd, f, want32=True)
+        assert W32.dtype == torch.float32 and torch.equal(W32.double(), W64.float().double())
+        if n <= 127:
+            r = torch.randn(d, dtype=torch.float64)
+            Xa = torch.cat([X, r[None]])
+            Ga = Xa @ Xa.T
+            fc = min(f, (n - 1) // 2)
+            got = nspace_cuda.caf_coeffs(Ga.to(DEV), n, fc, power_iters=3).cpu().numpy()
+            want = nspace.caf_coeffs(Ga.numpy(), n, fc, power_iters=3)
+            np.testing.assert_allclose(got[:n], want, rtol=1e-5, atol=1e-7)
+            assert got[n] == 0.0
+    # an all-inf row (InfAttack upstream): scale 0 under clipping, never a neighbour under NNM
+    X = torch.randn(6, 100, dtype=torch.float64)
+    G = X @ X.T
+    G[3, :] = float("inf")
+    G[:, 3] = float("inf")
+    np.testing.assert_allclose(nspace_cuda.clip_matrix(G.to(DEV), 2.0).cpu().numpy(),
+                               np.diag(nspace.clip_scales(G.numpy(), 2.0)))
+    # capture
+    Gs = (torch.randn(16, 500, dtype=torch.float64) @ torch.randn(500, 16, dtype=torch.float64))
+    Gs = (Gs @ Gs.T).to(DEV)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        nspace_cuda.nnm_matrix(Gs, 3)
+        nspace_cuda.caf_coeffs(Gs, 15, 3, power_iters=3)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        a = nspace_cuda.nnm_matrix(Gs, 3)
+        b = nspace_cuda.arc_matrix(Gs, 3)
+        c = nspace_cuda.caf_coeffs(Gs, 15, 3, power_iters=3)
+    graph.replay()
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(a.cpu().numpy(), nspace.nnm_matrix(Gs.cpu().numpy(), 3))
+    np.testing.assert_allclose(b.cpu().numpy(), np.diag(nspace.arc_scales(Gs.cpu().numpy(), 3)))
+    np.testing.assert_allclose(c.cpu().numpy()[:15], nspace.caf_coeffs(Gs.cpu().numpy(), 15, 3, power_iters=3),
+                               rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("pre_name", ["clipping", "arc", "nnm", "bucketing"])
+@pytest.mark.parametrize("agg_name", ["multikrum", "cge", "caf", "gm_mean"])
+def test_every_pre_aggregator_composes_into_a_capturable_fused_plan(pre_name, agg_name):
+    from byzpy_b200.aggregators.norm_wise import CAF, ComparativeGradientElimination
+    from byzpy_b200.engine.node.device import DeviceHonestNode
+    from byzpy_b200.engine.parameter_server.ps import ParameterServer
+    from byzpy_b200.pre_aggregators import ARC, Bucketing, Clipping, NearestNeighborMixing
+
+    pres = {"clipping": lambda: Clipping(0.05), "arc": lambda: ARC(2), "nnm": lambda: NearestNeighborMixing(2),
+            "bucketing": lambda: Bucketing(2, perm=[5, 0, 3, 1, 7, 2, 6, 4])}
+    m = 4 if pre_name == "bucketing" else 8
+    aggs = {"multikrum": lambda: MultiKrum(f=1, q=2), "cge": lambda: ComparativeGradientElimination(f=1),
+            "caf": lambda: CAF(f=1), "gm_mean": lambda: GeometricMedian(init="mean", tol=1e-7)}
+    if agg_name == "caf":
+        # CAF appends a constant aux row: composition with a pre-aggregator is n-space only for aux-free plans
+        ps_kwargs = dict(pre_aggregator=None)
+    else:
+        ps_kwargs = dict(pre_aggregator=pres[pre_name]())
+    torch.manual_seed(2)
+    init = TinyNet().state_dict()
+
+    def mk():
+        net = TinyNet()
+        net.load_state_dict(init)
+        return net
+
+    hon = [DeviceHonestNode(mk(), lr=0.1, momentum=0.9, device=DEV) for _ in range(8)]
+    ps = ParameterServer(hon, [], aggs[agg_name](), fused=True, amp_dtype=None, use_cuda_graph=True, **ps_kwargs)
+    rnd = ps.device_round
+    assert rnd.plan.capturable and rnd.use_cuda_graph, (pre_name, agg_name)
+    models = [mk().to(DEV) for _ in range(8)]
+    lossf = nn.CrossEntropyLoss()
+    for t in range(2):
+        batches = [(torch.randn(16, 20).pin_memory(), torch.randint(0, 5, (16,)).pin_memory()) for _ in range(8)]
+        ps.step(batches)
+        rows = []
+        for mdl, (x, y) in zip(models, batches):
+            mdl.zero_grad()
+            lossf(mdl(x.to(DEV)), y.to(DEV)).backward()
+            rows.append(torch.cat([p.grad.reshape(-1) for p in mdl.parameters()]).cpu())
+        pre = ps_kwargs["pre_aggregator"]
+        if pre is not None:
+            pre_cpu = pres[pre_name]()
+            rows = list(pre_cpu.pre_aggregate(rows))
+            assert len(rows) == m
+        expect = aggs[agg_name]().aggregate(rows)            # CPU path (host oracles)
+        rnd.read_losses()
+        torch.testing.assert_close(rnd.aggregated().cpu(), expect, rtol=2e-4, atol=2e-5)
+        for mdl in models:                                   # keep the mirrors in step
+            off = 0
+            for p in mdl.parameters():
+                p.grad.copy_(expect[off:off + p.numel()].view_as(p).to(DEV))
+                off += p.numel()
+        if t == 0:
+            opts = [torch.optim.SGD(mdl.parameters(), lr=0.1, momentum=0.9) for mdl in models]
+        for o in opts:
+            o.step()
+    asyncio.run(ps.shutdown())
+
+
+def test_pre_aggregate_on_cuda_stays_on_the_device_and_matches_cpu():
+    from byzpy_b200.pre_aggregators import ARC, Clipping, NearestNeighborMixing
+
+    g = grads(12, 5003, seed=21)
+    g[4] = g[4] * 30.0
+    gd = [x.to(DEV) for x in g]
+    for mk in (lambda: Clipping(50.0), lambda: ARC(3), lambda: NearestNeighborMixing(3)):
+        out_d = mk().pre_aggregate(gd)
+        out_c = mk().pre_aggregate(g)
+        assert len(out_d) == len(out_c) and all(o.is_cuda for o in out_d)
+        for a, b in zip(out_d, out_c):
+            torch.testing.assert_close(a.cpu(), b, rtol=1e-5, atol=1e-5)

@@ -72,3 +72,14 @@ def test_fused_round_bucketed_overlap_two_ranks(agg, graph):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert res.returncode == 0 and "MULTI_GPU_FUSED_ROUND PASS" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
     assert "overlapped=True" in res.stdout and "buckets=1 " not in res.stdout, res.stdout[-1500:]
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
+def test_fused_round_survives_a_silent_rank():
+    """Fault injection: a rank stops taking part, the survivor's kernels time out and name
+    it, ParameterServer.recover() drops its rows and training continues on the remaining ones."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29539",
+           os.path.join(ROOT, "tests", "multi_gpu", "check_fault.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert res.returncode == 0 and "MULTI_GPU_FAULT PASS" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
