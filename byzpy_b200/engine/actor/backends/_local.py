@@ -125,9 +125,11 @@ class LocalMailboxBackend:
             await tcp.chan_put(host, port, to_ep.actor_id, name, payload)
             return
         if to_ep.scheme == "ucx":
+            # pooled endpoint per peer, per-peer lock, one retry after eviction; CUDA tensors as IPC handles
+            from ..transports import ucx as ucx_t
+
             host, port = tcp.parse_address(to_ep.address)
-            blob = cuda_ipc.dumps(payload, same_host=host in ("127.0.0.1", "localhost"))
-            await tcp.chan_put(host, port, to_ep.actor_id, name, {"__cuda_ipc__": blob})
+            await ucx_t.chan_put(host, port, to_ep.actor_id, name, payload)
             return
         raise RuntimeError(f"{type(self).__name__} cannot route to {to_ep.scheme!r}")
 
@@ -142,7 +144,12 @@ class LocalMailboxBackend:
                 return payload
             except asyncio.TimeoutError:
                 return None
-        if ep.scheme in ("tcp", "ucx"):
+        if ep.scheme == "ucx":
+            from ..transports import ucx as ucx_t
+
+            host, port = tcp.parse_address(ep.address)
+            return await ucx_t.chan_get(host, port, ep.actor_id, name, timeout)
+        if ep.scheme == "tcp":
             host, port = tcp.parse_address(ep.address)
             got = await tcp.chan_get(host, port, ep.actor_id, name, timeout)
             if isinstance(got, dict) and "__cuda_ipc__" in got:

@@ -1,17 +1,41 @@
-"""Compatibility surface of the reference's UCX transport module
-(reference engine/actor/transports/ucx.py).  There is no UCX dependency here: on one NVSwitch box
-the GPU-direct tensor path of the ``ucx://`` scheme is CUDA IPC (``transports/cuda_ipc.py``)."""
+"""Data plane of the ``ucx://`` scheme on one NVSwitch box.
+
+The reference moves device tensors between actor servers through UCX endpoints: a pooled endpoint
+per ``(host, port)``, one lock per peer so a control message + payload + reply exchange is never
+interleaved, and one retry on a transport error after evicting the endpoint
+(reference engine/actor/transports/ucx.py:110-133), with CUDA payloads sent as raw device buffers
+behind a pickled descriptor (``:186-277``).  On a single B200 node no copy engine is needed in the
+middle: every GPU reaches every other at full NVLink bandwidth, so the payload of a CUDA tensor is
+its 64-byte CUDA-IPC handle (``transports/cuda_ipc.py``) and the receiver maps the sender's memory
+-- zero copy, device to device.  What remains of the transport is the connection management, which
+this module provides with the reference's surface:
+
+* :func:`get_endpoint` / :func:`call` / :func:`clear_pool` -- pooled stream endpoints per peer,
+  per-peer locks, one retry after eviction on a broken connection;
+* :func:`pack_payload` / :func:`unpack_payload` -- ``("cuda" | "pickle", blob)`` payload tagging;
+* :func:`chan_put` / :func:`chan_get` -- mailbox access of a remote ``ucx://`` actor server.
+
+A ``ucx://`` endpoint on ANOTHER host gets by-value payloads (CUDA IPC handles are only valid on the
+box that exported them); ``have_ucx()`` tells whether the GPU-direct path is usable at all.
+"""
 from __future__ import annotations
 
-from typing import Any, Tuple
+import asyncio
+from typing import Any, Awaitable, Callable, Dict, Optional, Tuple
 
+from .._wire import recv_obj, send_obj
 from . import cuda_ipc
+
+Endpoint = Tuple[asyncio.StreamReader, asyncio.StreamWriter]
+
+_EP_CACHE: Dict[Tuple[str, int], Endpoint] = {}
+_EP_LOCKS: Dict[Tuple[str, int], asyncio.Lock] = {}
+_RETRYABLE = (ConnectionError, asyncio.IncompleteReadError, BrokenPipeError, EOFError, OSError)
 
 
 def _ucx_mod():
     """The installed UCX Python binding (``ucxx``, else ``ucp``), or None -- the probe the reference's
-    callers use (reference engine/actor/transports/ucx.py:36-56).  Nothing here needs it: the ``ucx://``
-    scheme moves device tensors as CUDA-IPC handles over the TCP control plane."""
+    callers use (reference engine/actor/transports/ucx.py:36-56).  Nothing here needs it."""
     import importlib
 
     for name in ("ucxx", "ucp"):
@@ -27,8 +51,65 @@ def have_ucx() -> bool:
     return cuda_ipc.available()
 
 
-def pack_payload(obj: Any) -> Tuple[str, bytes]:
-    blob = cuda_ipc.dumps(obj, same_host=True)
+def _key(host: str, port: int) -> Tuple[str, int]:
+    return (host, int(port))
+
+
+def is_same_host(host: str) -> bool:
+    return host in ("127.0.0.1", "localhost", "0.0.0.0", "::1")
+
+
+async def get_endpoint(host: str, port: int) -> Endpoint:
+    """The pooled connection to ``host:port`` (opened on first use, re-opened after eviction)."""
+    key = _key(host, port)
+    ep = _EP_CACHE.get(key)
+    if ep is not None and not ep[1].is_closing():
+        return ep
+    reader, writer = await asyncio.open_connection(host, int(port))
+    _EP_CACHE[key] = (reader, writer)
+    return reader, writer
+
+
+def evict_endpoint(host: str, port: int) -> None:
+    ep = _EP_CACHE.pop(_key(host, port), None)
+    if ep is not None:
+        try:
+            ep[1].close()
+        except Exception:
+            pass
+
+
+async def clear_pool() -> None:
+    for key in list(_EP_CACHE):
+        _, writer = _EP_CACHE.pop(key)
+        try:
+            writer.close()
+            await writer.wait_closed()
+        except Exception:
+            pass
+    _EP_LOCKS.clear()
+
+
+async def call(host: str, port: int, fn: Callable[[Endpoint], Awaitable[Any]]) -> Any:
+    """Run one full exchange ``fn(endpoint)`` on the pooled endpoint of the peer, serialised by the
+    peer's lock; a broken connection evicts the endpoint and the exchange is retried once."""
+    key = _key(host, port)
+    lock = _EP_LOCKS.setdefault(key, asyncio.Lock())
+
+    async def _once():
+        async with lock:
+            ep = await get_endpoint(host, port)
+            return await fn(ep)
+
+    try:
+        return await _once()
+    except _RETRYABLE:
+        evict_endpoint(host, port)
+        return await _once()
+
+
+def pack_payload(obj: Any, *, same_host: bool = True) -> Tuple[str, bytes]:
+    blob = cuda_ipc.dumps(obj, same_host=same_host)
     return ("cuda" if blob[:1] == b"I" else "pickle"), blob
 
 
@@ -36,4 +117,35 @@ def unpack_payload(blob: bytes) -> Any:
     return cuda_ipc.loads(blob)
 
 
-__all__ = ["have_ucx", "pack_payload", "unpack_payload"]
+async def request(host: str, port: int, msg: dict, timeout: Optional[float] = None) -> Any:
+    """One control exchange with a ``ucx://`` actor server over the pooled endpoint."""
+
+    async def _do(ep: Endpoint):
+        reader, writer = ep
+        await send_obj(writer, msg)
+        return await asyncio.wait_for(recv_obj(reader), timeout=timeout)
+
+    reply = await call(host, port, _do)
+    if isinstance(reply, dict) and reply.get("ok") is False:
+        raise RuntimeError(reply.get("error", "remote error"))
+    return reply.get("payload") if isinstance(reply, dict) else reply
+
+
+async def chan_put(host: str, port: int, actor_id: str, name: str, payload: Any) -> None:
+    """Deliver ``payload`` into mailbox ``name`` of a remote ``ucx://`` actor; CUDA tensors travel as
+    CUDA-IPC handles when the server is on this box."""
+    _, blob = pack_payload(payload, same_host=is_same_host(host))
+    await request(host, port, {"op": "chan_put", "actor_id": actor_id, "name": name,
+                               "payload": {"__cuda_ipc__": blob}})
+
+
+async def chan_get(host: str, port: int, actor_id: str, name: str, timeout: Optional[float]) -> Any:
+    out = await request(host, port, {"op": "chan_get", "actor_id": actor_id, "name": name, "timeout": timeout},
+                        timeout=None if timeout is None else timeout + 5.0)
+    if isinstance(out, dict) and "__cuda_ipc__" in out:
+        return unpack_payload(out["__cuda_ipc__"])
+    return out
+
+
+__all__ = ["have_ucx", "pack_payload", "unpack_payload", "get_endpoint", "evict_endpoint", "clear_pool", "call",
+           "request", "chan_put", "chan_get", "is_same_host"]

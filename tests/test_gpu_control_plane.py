@@ -1,0 +1,272 @@
+"""On-device tests of the GPU control plane: graph nodes on CUDA streams (ParallelScheduler), the
+CUDA-stream actor backend, and GPU-direct tensor transport (``ucx://`` actor servers and mesh node
+contexts moving CUDA tensors between PROCESSES as CUDA-IPC handles, zero copy).
+
+Reference counterparts: engine/graph/tests/test_parallel_scheduler.py (concurrency proofs by
+timestamps), engine/actor/tests/test_gpu_backends.py:266-342 (cross-backend matrix + CUDA tensor over
+``ucx://``)."""
+import asyncio
+import os
+import socket
+import subprocess
+import sys
+import time
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DEV = "cuda:0"
+
+
+def _chain(x: torch.Tensor, iters: int = 150) -> torch.Tensor:
+    """A dependent chain of small GEMMs: ~1-2 ms on a handful of SMs, so several chains overlap."""
+    w = torch.eye(x.shape[1], device=x.device) * 0.999
+    for _ in range(iters):
+        x = x @ w
+    return x
+
+
+class _ChainOp:
+    pass
+
+
+def _make_branch_graph(k, stamps):
+    from byzpy_b200.engine.graph.graph import ComputationGraph, GraphNode, graph_input
+    from byzpy_b200.engine.graph.operator import Operator
+
+    class Branch(Operator):
+        name = "branch"
+
+        def __init__(self, idx):
+            self.idx = idx
+
+        def compute(self, inputs, *, context):
+            s = torch.cuda.current_stream()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(s)
+            y = _chain(inputs["x"] + self.idx)
+            b.record(s)
+            stamps[self.idx] = (s.cuda_stream, a, b)
+            return y
+
+    class Join(Operator):
+        name = "join"
+
+        def compute(self, inputs, *, context):
+            return sum(inputs[f"b{i}"] for i in range(k))
+
+    nodes = [GraphNode(name=f"b{i}", op=Branch(i), inputs={"x": graph_input("x")}) for i in range(k)]
+    nodes.append(GraphNode(name="out", op=Join(), inputs={f"b{i}": f"b{i}" for i in range(k)}))
+    return ComputationGraph(nodes, outputs=["out"])
+
+
+def test_parallel_scheduler_runs_cuda_branches_concurrently_on_streams():
+    from byzpy_b200.engine.graph.parallel_scheduler import ParallelScheduler
+    from byzpy_b200.engine.graph.scheduler import NodeScheduler
+
+    k = 4
+    x = torch.randn(64, 64, device=DEV)
+    _chain(x)                                        # warm up cuBLAS
+    torch.cuda.synchronize()
+    stamps_s, stamps_p = {}, {}
+    t0 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    serial = asyncio.run(NodeScheduler(_make_branch_graph(k, stamps_s)).run({"x": x}))["out"]
+    torch.cuda.synchronize()
+    t1 = torch.cuda.Event(enable_timing=True)
+    t1.record()
+    parallel = asyncio.run(ParallelScheduler(_make_branch_graph(k, stamps_p)).run({"x": x}))["out"]
+    torch.cuda.synchronize()
+    torch.testing.assert_close(parallel, serial, rtol=0, atol=0)
+    # serial: one stream, disjoint intervals
+    assert len({s for s, _, _ in stamps_s.values()}) == 1
+    # parallel: the branches ran on distinct side streams ...
+    streams = {s for s, _, _ in stamps_p.values()}
+    assert len(streams) == k and torch.cuda.current_stream().cuda_stream not in streams
+    # ... and overlapped ON THE DEVICE: some branch started before another one finished
+    iv = sorted((t1.elapsed_time(a), t1.elapsed_time(b)) for _, a, b in stamps_p.values())
+    overlaps = sum(1 for i in range(k - 1) if iv[i + 1][0] < iv[i][1])
+    assert overlaps >= 1, iv
+    span_p = max(e for _, e in iv) - min(s for s, _ in iv)
+    iv_s = [(t0.elapsed_time(a), t0.elapsed_time(b)) for _, a, b in stamps_s.values()]
+    span_s = max(e for _, e in iv_s) - min(s for s, _ in iv_s)
+    assert span_p < 0.8 * span_s, (span_p, span_s)
+
+
+def test_gpu_actor_backends_own_streams_overlap_and_order_after_the_caller():
+    from byzpy_b200.engine.actor.base import ActorRef
+    from byzpy_b200.engine.actor.backends.gpu import GPUActorBackend
+
+    class Worker:
+        def __init__(self, bias):
+            self.bias = bias
+
+        def run(self, x):
+            s = torch.cuda.current_stream()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(s)
+            y = _chain(x + self.bias)
+            b.record(s)
+            return y, s.cuda_stream, a, b
+
+    async def main():
+        b1, b2 = GPUActorBackend(0), GPUActorBackend(0)
+        a1, a2 = ActorRef(b1), ActorRef(b2)
+        for a, bias in ((a1, 1.0), (a2, 2.0)):
+            await a._backend.start()
+            await a._backend.construct(Worker, args=(bias,), kwargs={})
+        assert b1.stream.cuda_stream != b2.stream.cuda_stream
+        t0 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        # the input is produced on the CALLER's stream right before the call, with no host sync:
+        # the actor stream must wait for it on the device
+        x = _chain(torch.randn(64, 64, device=DEV), 50)
+        (y1, s1, a1s, a1e), (y2, s2, a2s, a2e) = await asyncio.gather(a1.run(x), a2.run(x))
+        torch.cuda.synchronize()
+        assert s1 == b1.stream.cuda_stream and s2 == b2.stream.cuda_stream
+        torch.testing.assert_close(y1, _chain(x + 1.0), rtol=0, atol=0)
+        torch.testing.assert_close(y2, _chain(x + 2.0), rtol=0, atol=0)
+        i1, i2 = (t0.elapsed_time(a1s), t0.elapsed_time(a1e)), (t0.elapsed_time(a2s), t0.elapsed_time(a2e))
+        assert max(i1[0], i2[0]) < min(i1[1], i2[1]), (i1, i2)          # the two actors overlapped on the device
+        await b1.close()
+        await b2.close()
+
+    asyncio.run(main())
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _wait_port(port, proc, timeout=90.0):
+    t0 = time.time()
+    while time.time() - t0 < timeout:
+        if proc.poll() is not None:
+            raise RuntimeError("server process died: " + (proc.stderr.read() if proc.stderr else ""))
+        try:
+            with socket.create_connection(("127.0.0.1", port), timeout=0.5):
+                return
+        except OSError:
+            time.sleep(0.2)
+    raise TimeoutError("actor server did not come up")
+
+
+def test_cuda_tensor_through_a_ucx_actor_server_in_another_process_is_zero_copy():
+    """A CUDA tensor sent to an actor hosted by a ``ucx://`` server PROCESS arrives as a mapping of the
+    sender's memory (CUDA IPC): the actor's in-place update is visible in the sender's tensor, and a
+    tensor created by the actor comes back as a device tensor.  Also the pooled-endpoint transport:
+    mailbox put/get of a CUDA tensor, and one transparent retry after the connection was dropped."""
+    from byzpy_b200.engine.actor.backends.gpu import UCXRemoteActorBackend
+    from byzpy_b200.engine.actor.transports import ucx as ucx_t
+
+    port = _free_port()
+    code = ("import asyncio, sys; sys.path.insert(0, %r); "
+            "from byzpy_b200.engine.actor.backends.gpu import start_ucx_actor_server; "
+            "asyncio.run(start_ucx_actor_server('127.0.0.1', %d))" % (ROOT, port))
+    proc = subprocess.Popen([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    try:
+        _wait_port(port, proc)
+
+        class Remote:
+            def __init__(self):
+                import os as _os
+
+                self.pid = _os.getpid()
+
+            def touch(self, t):
+                t.add_(1.0)                       # in place, on the mapped memory of the sender
+                torch.cuda.synchronize()
+                return (self.pid, bool(t.is_cuda), float(t.sum().item()))
+
+            def make(self, n):
+                self.keep = torch.arange(n, device="cuda", dtype=torch.float32)
+                return self.keep
+
+        async def main():
+            be = UCXRemoteActorBackend("127.0.0.1", port)
+            await be.start()
+            await be.construct(Remote, args=(), kwargs={})
+            x = torch.zeros(1 << 16, device=DEV)
+            torch.cuda.synchronize()
+            pid, is_cuda, total = await be.call("touch", x)
+            assert pid != os.getpid() and is_cuda and total == float(1 << 16)
+            torch.cuda.synchronize()
+            assert float(x.sum().item()) == float(1 << 16)            # the server wrote into OUR allocation
+            y = await be.call("make", 1000)
+            assert y.is_cuda and torch.equal(y.cpu(), torch.arange(1000, dtype=torch.float32))
+            # mailbox of the remote actor through the pooled ucx transport
+            ep = await be.chan_open("box")
+            z = torch.full((4096,), 3.0, device=DEV)
+            await ucx_t.chan_put("127.0.0.1", port, ep.actor_id, "box", {"v": z, "tag": 7})
+            got = await ucx_t.chan_get("127.0.0.1", port, ep.actor_id, "box", 5.0)
+            assert got["tag"] == 7 and got["v"].is_cuda and torch.equal(got["v"].cpu(), z.cpu())
+            # drop the pooled connection behind the transport's back: the next exchange retries once
+            _, w = await ucx_t.get_endpoint("127.0.0.1", port)
+            w.close()
+            await ucx_t.chan_put("127.0.0.1", port, ep.actor_id, "box", 42)
+            assert await ucx_t.chan_get("127.0.0.1", port, ep.actor_id, "box", 5.0) == 42
+            await ucx_t.clear_pool()
+            await be.close()
+
+        asyncio.run(main())
+    finally:
+        proc.terminate()
+        try:
+            proc.wait(timeout=10)
+        except Exception:
+            proc.kill()
+
+
+def test_mesh_contexts_move_cuda_tensors_between_processes_gpu_direct():
+    """Two nodes in two processes joined by ``MeshRemoteContext(gpu_direct=True)``: a CUDA tensor
+    payload arrives as a device tensor in the peer process (CUDA-IPC handle on the wire) and the reply
+    built from it comes back."""
+    port_a, port_b = _free_port(), _free_port()
+    peer = os.path.join(ROOT, "tests", "multi_gpu", "mesh_peer.py")
+    proc = subprocess.Popen([sys.executable, peer, str(port_b), str(port_a)], stdout=subprocess.PIPE,
+                            stderr=subprocess.PIPE, text=True)
+    try:
+        _wait_port(port_b, proc)
+        from byzpy_b200.engine.node.context import MeshRemoteContext
+
+        async def main():
+            class _Node:
+                node_id = "A"
+
+            ctx = MeshRemoteContext("127.0.0.1", port_a, {"B": ("127.0.0.1", port_b)}, gpu_direct=True)
+            await ctx.start(_Node())
+            x = torch.arange(8192, device=DEV, dtype=torch.float32)
+            torch.cuda.synchronize()
+            for _ in range(100):                                  # the peer may still be starting its side
+                try:
+                    await ctx.send_message("B", "vec", {"vector": x})
+                    break
+                except Exception:
+                    await asyncio.sleep(0.2)
+            else:
+                raise AssertionError("peer B never became reachable")
+
+            async def first():
+                async for msg in ctx.receive_messages():
+                    if msg.get("type") == "echo":
+                        return msg
+
+            msg = await asyncio.wait_for(first(), timeout=60)
+            payload = msg["payload"]
+            assert msg["from"] == "B"
+            assert payload["was_cuda"] is True and payload["pid"] != os.getpid()
+            assert payload["vector"].is_cuda and torch.equal(payload["vector"].cpu(), (x * 2).cpu())
+            await ctx.shutdown()
+
+        asyncio.run(main())
+    finally:
+        proc.terminate()
+        try:
+            proc.wait(timeout=10)
+        except Exception:
+            proc.kill()

@@ -266,3 +266,41 @@ def test_operators_through_real_pools(backend):
             await pool.shutdown()
 
     run(scenario())
+
+
+def test_ucx_transport_pools_endpoints_locks_per_peer_and_retries_once():
+    """The ``ucx://`` data plane (transports/ucx.py): one pooled endpoint per (host, port) reused across
+    exchanges, a per-peer lock, one transparent retry after the connection dropped, and namedtuple
+    payloads (Endpoint) surviving the by-value codec (reference transports/ucx.py:110-133)."""
+    from byzpy_b200.engine.actor.backends.gpu import UCXRemoteActorServer
+    from byzpy_b200.engine.actor.channels import Endpoint
+    from byzpy_b200.engine.actor.transports import ucx as ucx_t
+
+    srv = _ServerThread(UCXRemoteActorServer)
+    try:
+        async def scenario():
+            be = resolve_backend(f"ucx://127.0.0.1:{srv.port}")
+            await be.start()
+            await be.construct(Counter, args=(), kwargs={})
+            ep = await be.chan_open("box")
+            assert ep.scheme == "ucx"
+            await ucx_t.chan_put("127.0.0.1", srv.port, ep.actor_id, "box", {"ep": ep, "t": torch.ones(3)})
+            first = await ucx_t.get_endpoint("127.0.0.1", srv.port)
+            got = await ucx_t.chan_get("127.0.0.1", srv.port, ep.actor_id, "box", 2.0)
+            assert isinstance(got["ep"], Endpoint) and got["ep"] == ep and torch.equal(got["t"], torch.ones(3))
+            assert (await ucx_t.get_endpoint("127.0.0.1", srv.port)) is first          # pooled, not re-dialled
+            # concurrent exchanges with one peer are serialised by its lock (no interleaved frames)
+            await asyncio.gather(*[ucx_t.chan_put("127.0.0.1", srv.port, ep.actor_id, "box", i) for i in range(20)])
+            seen = sorted([await ucx_t.chan_get("127.0.0.1", srv.port, ep.actor_id, "box", 2.0) for _ in range(20)])
+            assert seen == list(range(20))
+            first[1].close()                                                          # the connection drops ...
+            await ucx_t.chan_put("127.0.0.1", srv.port, ep.actor_id, "box", "again")   # ... one retry re-dials
+            assert await ucx_t.chan_get("127.0.0.1", srv.port, ep.actor_id, "box", 2.0) == "again"
+            assert (await ucx_t.get_endpoint("127.0.0.1", srv.port)) is not first
+            assert await ucx_t.chan_get("127.0.0.1", srv.port, ep.actor_id, "box", 0.05) is None
+            await ucx_t.clear_pool()
+            await be.close()
+
+        run(scenario())
+    finally:
+        srv.stop()
