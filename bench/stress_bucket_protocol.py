@@ -29,6 +29,13 @@ def main():
     ap.add_argument("--d", type=int, default=1 << 16)
     ap.add_argument("--buckets", type=int, default=4)
     ap.add_argument("--mode", default="median", choices=["median", "trmean"])
+    ap.add_argument("--no-sleep", action="store_true")
+    ap.add_argument("--fixed-order", action="store_true")
+    ap.add_argument("--interleave", action="store_true",
+                    help="enqueue the ranks' bucket launches alternately instead of rank by rank")
+    ap.add_argument("--spin", type=float, default=3.0, help="flag-wait budget in seconds")
+    ap.add_argument("--sleep-after-first-rank", action="store_true",
+                    help="enqueue the late rank's spin kernel AFTER the first rank's launches (host order)")
     a = ap.parse_args()
     ext = ops.require_ext()
     dev = torch.device("cuda", 0)
@@ -49,23 +56,43 @@ def main():
         X = torch.randn(n, d, device=dev)
         torch.cuda.synchronize()
         order = [0, 1]
-        rng.shuffle(order)
-        for r in order:
-            with torch.cuda.stream(streams[r]):
-                if r == order[1] and rng.random() < 0.7:
-                    torch.cuda._sleep(int(rng.uniform(2e5, 3e6)))     # the late rank
+        if not a.fixed_order:
+            rng.shuffle(order)
+        slept = False
+        cycles = 0
+        if not a.no_sleep and rng.random() < 0.7:
+            cycles = int(rng.uniform(2e5, 3e6))
+            slept = True
+        if cycles and not a.sleep_after_first_rank:
+            with torch.cuda.stream(streams[order[1]]):
+                torch.cuda._sleep(cycles)                             # the late rank
+
+        def launch(r, k):
+            off, ln = bounds[k + 1], bounds[k] - bounds[k + 1]
+            half = (ln // 2) // 4 * 4
+            s_off = off + r * half
+            s_len = half if r == 0 else ln - half
+            ext.fused_ps_cw([X[i].data_ptr() for i in range(n)], [1.0] * n, mode, f, 0, 0, 0.0, 0.0, d,
+                            s_off, s_len, r, [t.data_ptr() for t in aggs], [p.data_ptr() for p in pads],
+                            epoch, 0, ctls[r].data_ptr(), ctls[r].data_ptr() + 4, [params[r].data_ptr()], [],
+                            0.1, 0.0, 0.0, sms, streams[r].cuda_stream, limit, off, ln, nb, k, 0, 0, a.spin)
+
+        if a.interleave:
+            for k in range(nb):
+                for r in order:
+                    launch(r, k)
+        else:
+            for r in order:
+                if cycles and a.sleep_after_first_rank and r == order[1]:
+                    with torch.cuda.stream(streams[r]):
+                        torch.cuda._sleep(cycles)
                 for k in range(nb):
-                    off, ln = bounds[k + 1], bounds[k] - bounds[k + 1]
-                    half = (ln // 2) // 4 * 4
-                    s_off = off + r * half
-                    s_len = half if r == 0 else ln - half
-                    ext.fused_ps_cw([X[i].data_ptr() for i in range(n)], [1.0] * n, mode, f, 0, 0, 0.0, 0.0, d,
-                                    s_off, s_len, r, [t.data_ptr() for t in aggs], [p.data_ptr() for p in pads],
-                                    epoch, 0, ctls[r].data_ptr(), ctls[r].data_ptr() + 4, [params[r].data_ptr()], [],
-                                    0.1, 0.0, 0.0, sms, streams[r].cuda_stream, limit, off, ln, nb, k)
+                    launch(r, k)
         torch.cuda.synchronize()
         if any(int(c[1].item()) != 0 for c in ctls):
-            print(f"epoch {epoch}: kernel status {[int(c[1].item()) for c in ctls]}")
+            print(f"epoch {epoch}: kernel status {[int(c[1].item()) for c in ctls]} order {order} slept {slept} "
+                  f"ready flags {[p[:2].tolist() for p in pads]} done flags {[p[16:18].tolist() for p in pads]} "
+                  f"counters {[int(c[0].item()) for c in ctls]} (bucket b of epoch e publishes e * {nb} + b)")
             bad += 1
             break
         exp = X.median(dim=0).values if a.mode == "median" else X.sort(dim=0).values[2:6].mean(dim=0)

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "api.h"
@@ -358,6 +359,56 @@ PYBIND11_MODULE(_C, m) {
   m.def("stem_grad_unpack", [](uint64_t gp, uint64_t g, int K, uint64_t stream) {
     check(bz_stem_grad_unpack(as_ptr<const void>(gp), as_ptr<float>(g), K, as_stream(stream)), "stem_grad_unpack");
   });
+  // segments: [(base pointer of the segment's first row, rows, row stride in bytes)], cols = row length in
+  // elements -> opaque bytes of a BzGramTmaMaps (tensor maps are plain data: cache and reuse them)
+  m.def("gram_tma_maps", [](const std::vector<std::tuple<uint64_t, int, unsigned long long>>& segments,
+                            unsigned long long cols, int n) {
+    if (segments.empty() || segments.size() > BZ_GRAM_MAXSEG) throw std::invalid_argument("1..12 segments");
+    BzGramTmaMaps tm;
+    std::memset(&tm, 0, sizeof(tm));
+    const int tile_cols = bz_gram_umma_tile_cols(n);
+    int row0 = 0;
+    for (size_t k = 0; k < segments.size(); ++k) {
+      const auto& [base, rows, stride] = segments[k];
+      if (rows < 1 || rows > 256 || (base % 16) != 0 || (stride % 16) != 0)
+        throw std::invalid_argument("segment rows must be 1..256, base and stride multiples of 16 bytes");
+      const unsigned long long st = rows > 1 ? stride : ((cols * 4 + 15) / 16 * 16);
+      int e = bz_encode_map_2d(&tm.maps[k], as_ptr<const void>(base), (unsigned long long)rows, cols, st,
+                               (unsigned)rows, (unsigned)tile_cols);
+      if (e != 0) throw std::runtime_error("cuTensorMapEncodeTiled failed (" + std::to_string(e) + ")");
+      tm.seg_row0[k] = row0;
+      tm.seg_rows[k] = rows;
+      row0 += rows;
+    }
+    if (row0 != n) throw std::invalid_argument("segments do not add up to n rows");
+    tm.nseg = (int)segments.size();
+    return py::bytes(reinterpret_cast<const char*>(&tm), sizeof(tm));
+  });
+  m.def(
+      "gram_umma_tma",
+      [](const py::bytes& maps, const std::vector<uint64_t>& rows, const std::vector<float>& scales, long long off,
+         long long len, uint64_t partials, int num_partials, uint64_t tail64, uint64_t G, uint64_t G64,
+         int sm_count, uint64_t stream) {
+        const std::string blob = maps;
+        if (blob.size() != sizeof(BzGramTmaMaps)) throw std::invalid_argument("bad tensor-map blob");
+        alignas(64) BzGramTmaMaps tm;
+        std::memcpy(&tm, blob.data(), sizeof(tm));
+        BzGramUmmaArgs a;
+        std::memset(&a, 0, sizeof(a));
+        fill_rows(a.rows, a.scales, rows, scales);
+        a.n = (int)rows.size();
+        a.off = off;
+        a.len = len;
+        a.partials = as_ptr<float>(partials);
+        a.num_partials = num_partials;
+        a.tail64 = as_ptr<const double>(tail64);
+        a.G = as_ptr<float>(G);
+        a.G64 = as_ptr<double>(G64);
+        check(bz_gram_umma_tma(&a, &tm, sm_count, as_stream(stream)), "gram_umma_tma");
+      },
+      py::arg("maps"), py::arg("rows"), py::arg("scales"), py::arg("off"), py::arg("len"), py::arg("partials"),
+      py::arg("num_partials"), py::arg("tail64"), py::arg("G"), py::arg("G64"), py::arg("sm_count"),
+      py::arg("stream"));
   m.def("gram_umma_grid", &bz_gram_umma_grid);
   m.def("gram_umma_tile_cols", &bz_gram_umma_tile_cols);
   m.def("gram_umma_partials", &bz_gram_umma_partials);

@@ -43,7 +43,8 @@ namespace {
 
 constexpr int kConvWarps = 8;                 // converter warps (also: first 4 = epilogue)
 constexpr int kConvThreads = kConvWarps * 32;
-constexpr int kThreads = 32 + kConvThreads;   // warp 0 = TMEM allocator + MMA issuer
+constexpr int kProdWarp = 1 + kConvWarps;     // warp 9: TMA producer (idle in the cp.async variant)
+constexpr int kThreads = 32 + kConvThreads + 32;   // warp 0 = TMEM allocator + MMA issuer
 constexpr int kOpCols = 32;                   // columns per operand tile (128 B swizzle row)
 constexpr int kRows = 128;                    // padded M
 constexpr int kOpStages = 3;
@@ -53,7 +54,8 @@ constexpr int kRawStages = 6;                 // cp.async ring of raw fp32 tiles
 constexpr int kChunksPerThread = kRows * 8 / kConvThreads;    // 16-byte chunks per thread per tile (4)
 constexpr int kRawStageBytes = kChunksPerThread * kConvThreads * 16;   // 16 KB
 constexpr int kTmemCols = 256;                // D_hh at column 0, D_hl at column 128
-constexpr int kSmemBytes = 1024 /*align slack*/ + kOpStages * kOpStageBytes + 256 /*barriers*/ +
+constexpr int kBarBytes = 256;                // mbarriers + TMEM slot (keeps the raw ring 128-byte aligned)
+constexpr int kSmemBytes = 1024 /*align slack*/ + kOpStages * kOpStageBytes + kBarBytes +
                            kRawStages * kRawStageBytes;
 constexpr unsigned long long kWaitBudgetCycles = 4000000000ull;  // ~2 s: trap instead of hanging
 
@@ -83,6 +85,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > kWaitBudgetCycles) __trap();
   }
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// TMA: 2-D tile global -> shared, completion (bytes) on an mbarrier.  SASS: UTMALDG.2D
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar)
+      : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -141,7 +153,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(kThreads, 1) gram_umma_kernel(const __grid_constant__ BzGramUmmaArgs a) {
+template <bool kTma>
+__device__ __forceinline__ void gram_umma_body(const BzGramUmmaArgs& a, const BzGramTmaMaps* tm) {
   extern __shared__ uint8_t smem_raw_[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment
   uint8_t* op_base = (uint8_t*)(((uintptr_t)smem_raw_ + 1023) & ~(uintptr_t)1023);   // kOpStages x (hi | lo)
@@ -149,7 +162,9 @@ __global__ void __launch_bounds__(kThreads, 1) gram_umma_kernel(const __grid_con
   uint64_t* op_full = bars;                     // [kOpStages]  converters -> MMA
   uint64_t* op_empty = bars + kOpStages;        // [kOpStages]  MMA (tcgen05.commit) -> converters
   uint64_t* acc_full = op_empty + kOpStages;    // [1]          MMA -> epilogue
-  uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
+  uint64_t* raw_full = acc_full + 1;            // [kRawStages] TMA (complete_tx) -> converters
+  uint64_t* raw_empty = raw_full + kRawStages;  // [kRawStages] converters -> TMA producer
+  uint32_t* tmem_slot = (uint32_t*)(raw_empty + kRawStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = a.n;
@@ -167,6 +182,10 @@ __global__ void __launch_bounds__(kThreads, 1) gram_umma_kernel(const __grid_con
       mbar_init(smem_u32(&op_empty[s]), 1);
     }
     mbar_init(smem_u32(acc_full), 1);
+    for (int s = 0; s < kRawStages; ++s) {
+      mbar_init(smem_u32(&raw_full[s]), 1);
+      mbar_init(smem_u32(&raw_empty[s]), kConvWarps);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // rows >= n of every operand tile stay zero for the whole kernel
@@ -207,16 +226,84 @@ __global__ void __launch_bounds__(kThreads, 1) gram_umma_kernel(const __grid_con
       }
       __syncwarp();
     }
+  } else if (warp == kProdWarp) {
+    // ================================ TMA producer (one thread) ===========================
+    if constexpr (kTma) {
+      if (lane == 0) {
+        uint8_t* raw_base = op_base + kOpStages * kOpStageBytes + kBarBytes;
+        const uint32_t row_bytes = (uint32_t)tile_cols * 4u;
+        uint32_t tile_bytes = 0;
+        for (int k = 0; k < tm->nseg; ++k) tile_bytes += (uint32_t)tm->seg_rows[k] * row_bytes;
+        for (long long t = 0; t < my_tiles; ++t) {
+          const int rs = (int)(t % kRawStages);
+          mbar_wait(smem_u32(&raw_empty[rs]), (uint32_t)(((t / kRawStages) & 1) ^ 1));
+          const long long col = a.off + ((long long)blockIdx.x + t * gridDim.x) * tile_cols;
+          const uint32_t bar = smem_u32(&raw_full[rs]);
+          mbar_expect_tx(bar, tile_bytes);
+          uint8_t* dst = raw_base + (size_t)rs * kRawStageBytes;
+          for (int k = 0; k < tm->nseg; ++k)
+            tma_load_2d(smem_u32(dst + (size_t)tm->seg_row0[k] * row_bytes), &tm->maps[k], (int)col, 0, bar);
+        }
+      }
+    }
   } else {
     // ========================= loaders / converters / epilogue ============================
+    const int ct = threadIdx.x - 32;
+    uint8_t* raw_base = op_base + kOpStages * kOpStageBytes + kBarBytes;
+    if constexpr (kTma) {
+      // The raw tile of a stage is [n rows][tile_cols] fp32, row pitch tile_cols * 4 bytes, written by
+      // the TMA.  Chunk q of a thread: data row q / (8 nblk), 16-byte chunk c = q % (8 nblk) of that row
+      // (consecutive threads read consecutive chunks: conflict-free); it belongs to column block c / 8
+      // and lands in operand row blk * n_pad + drow.
+      const int cpr = 8 * nblk;                        // 16-byte chunks per data row
+      int rows_[kChunksPerThread], cs_[kChunksPerThread], raw_off[kChunksPerThread];
+#pragma unroll
+      for (int j = 0; j < kChunksPerThread; ++j) {
+        const int q = j * kConvThreads + ct;
+        const int drow = q / cpr, c = q % cpr;
+        rows_[j] = (drow < n) ? (c >> 3) * n_pad + drow : -1;
+        cs_[j] = c & 7;
+        raw_off[j] = drow * (tile_cols * 4) + c * 16;
+      }
+      for (long long t = 0; t < my_tiles; ++t) {
+        const int os = (int)(t % kOpStages);
+        const int rs = (int)(t % kRawStages);
+        mbar_wait(smem_u32(&raw_full[rs]), (uint32_t)((t / kRawStages) & 1));
+        mbar_wait(smem_u32(&op_empty[os]), (uint32_t)(((t / kOpStages) & 1) ^ 1));
+        const uint8_t* raw = raw_base + (size_t)rs * kRawStageBytes;
+        uint8_t* hi = op_base + os * kOpStageBytes;
+        uint8_t* lo = hi + kOpTileBytes;
+#pragma unroll
+        for (int j = 0; j < kChunksPerThread; ++j) {
+          if (rows_[j] >= 0) {
+            const float4 x = *reinterpret_cast<const float4*>(raw + raw_off[j]);
+            const float xs[4] = {x.x, x.y, x.z, x.w};      // row scales are applied in the reduce
+            uint32_t hh[4], ll[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              hh[e] = to_tf32(xs[e]);
+              ll[e] = __float_as_uint(xs[e] - __uint_as_float(hh[e]));
+            }
+            const int row = rows_[j];
+            const int off = (row >> 3) * 1024 + (row & 7) * 128 + ((cs_[j] ^ (row & 7)) << 4);
+            *reinterpret_cast<uint4*>(hi + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+            *reinterpret_cast<uint4*>(lo + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+          }
+        }
+        fence_proxy_async();                         // generic-proxy writes -> async proxy (UMMA)
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(smem_u32(&raw_empty[rs]));      // this warp is done reading the raw stage
+          mbar_arrive(smem_u32(&op_full[os]));        // one arrival per converter warp
+        }
+      }
+    } else {
     // Each thread owns kChunksPerThread 16-byte chunks of every 128 x 32 tile: chunk q covers
     // row q / 8, 16-byte column group q % 8.  The raw fp32 chunks travel global (local or peer HBM)
     // -> shared memory with cp.async into a THREAD-PRIVATE slot of a kRawStages-deep ring, so the
     // bytes in flight are bounded by shared memory (80 KB / SM) instead of registers and nobody
     // else ever reads the slot (cp.async.wait_group is the only synchronisation); the owner then
     // splits hi / lo and writes the swizzled operand tiles.
-    const int ct = threadIdx.x - 32;
-    uint8_t* raw_base = op_base + kOpStages * kOpStageBytes + 256;
     int rows_[kChunksPerThread], cs_[kChunksPerThread];
     const float* src_[kChunksPerThread];
 #pragma unroll
@@ -278,6 +365,7 @@ __global__ void __launch_bounds__(kThreads, 1) gram_umma_kernel(const __grid_con
       if (lane == 0) mbar_arrive(smem_u32(&op_full[os]));   // one arrival per converter warp
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
     // ---- epilogue: TMEM -> registers -> per-CTA partials (first 4 converter warps) -------
     if (my_tiles > 0 && warp <= 4) {
       mbar_wait(smem_u32(acc_full), 0);
@@ -320,6 +408,14 @@ __global__ void __launch_bounds__(kThreads, 1) gram_umma_kernel(const __grid_con
   }
 }
 
+__global__ void __launch_bounds__(kThreads, 1) gram_umma_kernel(const __grid_constant__ BzGramUmmaArgs a) {
+  gram_umma_body<false>(a, nullptr);
+}
+__global__ void __launch_bounds__(kThreads, 1) gram_umma_tma_kernel(const __grid_constant__ BzGramUmmaArgs a,
+                                                                   const __grid_constant__ BzGramTmaMaps tm) {
+  gram_umma_body<true>(a, &tm);
+}
+
 // G_ij = s_i s_j * ( sum_c HH_c[i][j] + HL_c[i][j] + HL_c[j][i] ) + G_tail[i][j]
 __global__ void gram_umma_reduce_kernel(const float* __restrict__ partials, int num_partials, int n,
                                         ScaleTable scales, const double* __restrict__ tail64,
@@ -353,7 +449,26 @@ int bz_gram_umma_grid(int n, long long len, int sm_count) {
 
 int bz_gram_umma_partials(int n, int grid) { return grid * (kRows / bz_gram_umma_npad(n)); }
 
+static int gram_umma_launch(const BzGramUmmaArgs* args, const BzGramTmaMaps* maps, int sm_count,
+                            cudaStream_t stream);
+
 int bz_gram_umma(const BzGramUmmaArgs* args, int sm_count, cudaStream_t stream) {
+  return gram_umma_launch(args, nullptr, sm_count, stream);
+}
+
+int bz_gram_umma_tma(const BzGramUmmaArgs* args, const BzGramTmaMaps* maps, int sm_count, cudaStream_t stream) {
+  if (maps == nullptr || maps->nseg < 1 || maps->nseg > BZ_GRAM_MAXSEG) return (int)cudaErrorInvalidValue;
+  int covered = 0;
+  for (int k = 0; k < maps->nseg; ++k) {
+    if (maps->seg_row0[k] != covered || maps->seg_rows[k] < 1) return (int)cudaErrorInvalidValue;
+    covered += maps->seg_rows[k];
+  }
+  if (covered != args->n) return (int)cudaErrorInvalidValue;
+  return gram_umma_launch(args, maps, sm_count, stream);
+}
+
+static int gram_umma_launch(const BzGramUmmaArgs* args, const BzGramTmaMaps* maps, int sm_count,
+                            cudaStream_t stream) {
   const BzGramUmmaArgs& a = *args;
   if (a.n < 1 || a.n > BZ_MAXN) return (int)cudaErrorInvalidValue;
   if ((a.off % 4) != 0) return (int)cudaErrorInvalidValue;
@@ -369,10 +484,15 @@ int bz_gram_umma(const BzGramUmmaArgs* args, int sm_count, cudaStream_t stream) 
     if (!configured) {
       cudaError_t e = cudaFuncSetAttribute(gram_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            kSmemBytes);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(gram_umma_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
       if (e != cudaSuccess) return (int)e;
       configured = true;
     }
-    gram_umma_kernel<<<grid, kThreads, kSmemBytes, stream>>>(b);
+    if (maps != nullptr)
+      gram_umma_tma_kernel<<<grid, kThreads, kSmemBytes, stream>>>(b, *maps);
+    else
+      gram_umma_kernel<<<grid, kThreads, kSmemBytes, stream>>>(b);
     int e = (int)cudaGetLastError();
     if (e) return e;
   }

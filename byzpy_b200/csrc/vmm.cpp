@@ -19,6 +19,8 @@
 // fan-out loop of reference engine/parameter_server/ps.py:140-143.
 #include <cuda.h>
 #include <cuda_runtime.h>
+
+#include "gram_umma.h"
 #include <dlfcn.h>
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
@@ -56,6 +58,7 @@ struct Driver {
   BZ_DRV(cuMulticastBindMem)
   BZ_DRV(cuMulticastUnbind)
   BZ_DRV(cuMulticastGetGranularity)
+  BZ_DRV(cuTensorMapEncodeTiled)
 #undef BZ_DRV
 };
 
@@ -94,6 +97,7 @@ Driver& driver() {
     BZ_LOAD(cuMulticastBindMem, "cuMulticastBindMem")
     BZ_LOAD(cuMulticastUnbind, "cuMulticastUnbind")
     BZ_LOAD(cuMulticastGetGranularity, "cuMulticastGetGranularity")
+    BZ_LOAD(cuTensorMapEncodeTiled, "cuTensorMapEncodeTiled")
 #undef BZ_LOAD
     if (!all) {
       d.err = "missing driver symbols: " + d.err;
@@ -170,6 +174,20 @@ uint64_t map_handle(CUmemGenericAllocationHandle h, size_t size, size_t align, i
 }
 
 }  // namespace
+
+// 2-D tiled fp32 tensor map for the TMA-fed Gram kernel (gram_umma.cu); see gram_umma.h.
+int bz_encode_map_2d(CUtensorMap* out, const void* base, unsigned long long rows, unsigned long long cols,
+                     unsigned long long row_stride_bytes, unsigned box_rows, unsigned box_cols) {
+  Driver& d = driver();
+  if (!d.ok) return -1;
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)row_stride_bytes};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  const cuuint32_t estride[2] = {1, 1};
+  return (int)d.cuTensorMapEncodeTiled(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride,
+                                       box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
 
 void bz_bind_vmm(py::module_& m) {
   // {"vmm": bool, "posix_fd": bool, "multicast": bool, "reason": str}

@@ -709,9 +709,13 @@ class DeviceRound:
                          self._g_tail64.data_ptr(), self.sm, stream)
                 tail_ptr = self._g_tail64.data_ptr()
                 launches += 2
-            ext.gram_umma(self._all_rows, self._all_scales, off, main, self._umma_scratch.data_ptr(),
-                          self._umma_scratch.numel() // (2 * nt * nt), tail_ptr,
-                          self._g_local32.data_ptr(), self._g_local64.data_ptr(), self.sm, stream)
+            # TMA-fed when the table is a few matrix segments (one (L, d_pad) gradient matrix per peer GPU
+            # + the local virtual / auxiliary rows), per-thread cp.async otherwise
+            from ..ops import umma
+
+            self.gram_path = umma.launch(ext, self._all_rows, self._all_scales, off, main, self.d_pad,
+                                         self._umma_scratch, nt, tail_ptr, self._g_local32.data_ptr(),
+                                         self._g_local64.data_ptr(), self.sm, stream)
         else:
             ext.gram(self._all_rows, self._all_scales, off, ln, self._gram_scratch.data_ptr(),
                      self._gram_scratch.numel() // (nt * nt), self._g_local32.data_ptr(),

@@ -22,11 +22,10 @@ DEV = "cuda:0"
 
 
 def _chain(x: torch.Tensor, iters: int = 150) -> torch.Tensor:
-    """A dependent chain of small GEMMs: ~1-2 ms on a handful of SMs, so several chains overlap."""
-    w = torch.eye(x.shape[1], device=x.device) * 0.999
-    for _ in range(iters):
-        x = x @ w
-    return x
+    """~1.5 ms of device time in TWO launches (a spin kernel that occupies one thread, then the math):
+    the host enqueues it in microseconds, so whether branches overlap is decided on the device."""
+    torch.cuda._sleep(20_000 * iters)
+    return x * 0.5 + 1.0
 
 
 class _ChainOp:

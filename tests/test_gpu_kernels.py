@@ -660,3 +660,40 @@ def test_bert_direct_gradients_match_autograd():
     assert torch.isfinite(b).all()
     assert torch.nn.functional.cosine_similarity(a, b, dim=0).item() > 0.999
     torch.testing.assert_close(b, a, rtol=5e-2, atol=5e-3 * a.abs().max().item())
+
+
+@pytest.mark.parametrize("n", [17, 32, 33, 64, 100, 128])
+def test_gram_umma_tma_fed_matches_fp64_reference(n):
+    """tcgen05 Gram with the operand tiles brought in by the TMA (cp.async.bulk.tensor.2d, one box per
+    matrix segment per tile): a stacked (n, d) tensor is one segment, two matrices + a loose row are
+    three; the pointer-table cp.async path must give the same bits."""
+    from byzpy_b200.ops import umma
+
+    if not umma.tma_available():
+        pytest.skip("tensor-map encoder unavailable")
+    d = 32 * 1024 + 96                       # a tail that the CUDA-core kernel handles
+    g = torch.Generator().manual_seed(n)
+    X = torch.randn(n, d, generator=g).to(dev())
+    ref64 = X.double() @ X.double().T
+    G = ops.gram(list(X.unbind(0)), want64=True, impl="umma")
+    assert umma.last_path == "tma"
+    torch.testing.assert_close(G, ref64, rtol=1e-5, atol=2e-3)
+    # three segments: rows [0, a) and [a, n-1) in two separate matrices, the last row on its own
+    a = n // 2
+    A, B, c = X[:a].clone(), X[a:n - 1].clone(), X[n - 1].clone()
+    rows = list(A.unbind(0)) + list(B.unbind(0)) + [c]
+    assert len(umma.segments_of([r.data_ptr() for r in rows])) == 3
+    G3 = ops.gram(rows, want64=True, impl="umma")
+    assert umma.last_path == "tma"
+    assert torch.equal(G3, G)
+    # unrelated allocations in descending address order: no segments -> per-thread cp.async, same result
+    loose = [X[i].clone() for i in range(n)]
+    loose.sort(key=lambda t: -t.data_ptr())
+    Gl = ops.gram(loose, want64=True, impl="umma")
+    order = [next(j for j in range(n) if torch.equal(loose[i], X[j])) for i in range(n)]
+    torch.testing.assert_close(Gl, ref64[order][:, order], rtol=1e-5, atol=2e-3)
+    # scales are folded in the reduce on both paths
+    sc = [(-1.0) ** i * (1.0 + 0.1 * (i % 3)) for i in range(n)]
+    Gs = ops.gram(list(X.unbind(0)), scales=sc, want64=True, impl="umma")
+    S = torch.tensor(sc, dtype=torch.float64, device=dev())
+    torch.testing.assert_close(Gs, ref64 * S[:, None] * S[None, :], rtol=1e-5, atol=2e-3)
