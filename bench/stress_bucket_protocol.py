@@ -10,6 +10,14 @@ Every epoch launches, per rank, one kernel per gradient bucket (reverse order, p
 numbers epoch * nb + bucket in the flag words); the ranks' launch order is randomised and one of them
 is delayed by a spin kernel, so ready / delivery waits really wait.  After every epoch the
 aggregate in both ranks' buffers and the SGD-updated parameters are compared with a torch oracle.
+
+Single-GPU caveat found with this harness (``--sleep-after-first-rank``): with CUDA's lazy module
+loading, the FIRST launch of a kernel the process has not used yet needs a context-wide
+synchronisation, so launching such a kernel on the late rank's stream while the early rank's kernels
+are already resident and spinning on the late rank's flags never completes (the early rank times out
+after its spin budget).  It only exists when both ends of a flag wait live on ONE device; with one
+rank per GPU the peer's progress never depends on this process's host thread, and captured graphs
+load every kernel at capture time.  The harness therefore warms the spin kernel up first.
 """
 import argparse
 import os
@@ -52,6 +60,9 @@ def main():
     limit = max(1, sms // 4)
     expect_params = torch.zeros(d, device=dev)
     bad = 0
+    if not a.sleep_after_first_rank:
+        torch.cuda._sleep(1000)             # load the spin kernel while nothing is waiting on this device
+        torch.cuda.synchronize()
     for epoch in range(1, a.epochs + 1):
         X = torch.randn(n, d, device=dev)
         torch.cuda.synchronize()

@@ -39,6 +39,20 @@ struct BzWsumArgs {
 };
 int bz_wsum(const BzWsumArgs* args, int sm_count, cudaStream_t stream);
 
+// One-pass form for 8 < m <= 128 output rows (register-tiled fp32 GEMM over shared-memory tiles);
+// `len` must be a multiple of bz_wsum_multi_tile() coordinates, rows / outputs 16-byte aligned.
+struct BzWsumMultiArgs {
+  RowTable rows;
+  ScaleTable scales;
+  int n;
+  int m;
+  const float* W;   // (m, n) row-major, device memory
+  long long off, len;
+  struct { float* p[BZ_MAXN]; } out;   // m output row pointers
+};
+int bz_wsum_multi_tile();
+int bz_wsum_multi(const BzWsumMultiArgs* args, int sm_count, cudaStream_t stream);
+
 // Gram matrix G = (S X)(S X)^T for n <= 128 rows, fp32 CUDA-core path
 // (deterministic two-stage split-K).  `partials` is scratch of
 // gram_partial_elems(n, sm_count) floats.  G is (n, n) row-major.

@@ -130,6 +130,26 @@ PYBIND11_MODULE(_C, m) {
       py::arg("len"), py::arg("outs"), py::arg("upd_params"), py::arg("upd_moms"), py::arg("lr"),
       py::arg("mu"), py::arg("wd"), py::arg("sm_count"), py::arg("stream"));
 
+  m.attr("WSUM_MULTI_TILE") = bz_wsum_multi_tile();
+  m.def(
+      "wsum_multi",
+      [](const std::vector<uint64_t>& rows, const std::vector<float>& scales, uint64_t W, int mrows, long long off,
+         long long len, const std::vector<uint64_t>& outs, int sm_count, uint64_t stream) {
+        BzWsumMultiArgs a;
+        std::memset(&a, 0, sizeof(a));
+        fill_rows(a.rows, a.scales, rows, scales);
+        a.n = (int)rows.size();
+        a.m = mrows;
+        a.W = as_ptr<const float>(W);
+        a.off = off;
+        a.len = len;
+        if ((int)outs.size() != mrows || mrows > BZ_MAXN) throw std::invalid_argument("outs must have m <= 128 entries");
+        for (int r = 0; r < mrows; ++r) a.out.p[r] = as_ptr<float>(outs[r]);
+        check(bz_wsum_multi(&a, sm_count, as_stream(stream)), "wsum_multi");
+      },
+      py::arg("rows"), py::arg("scales"), py::arg("W"), py::arg("m"), py::arg("off"), py::arg("len"),
+      py::arg("outs"), py::arg("sm_count"), py::arg("stream"));
+
   m.def(
       "host_colstat",
       [](const std::vector<uint64_t>& rows, const std::vector<float>& scales, double a, double b, long long d,

@@ -7,6 +7,8 @@
 // Weiszfeld / centered-clipping / CAF solves): one read of n*d*4
 // bytes, (n, n) result.
 // Parity: reference krum.py:31-44 (pairwise squared distances via Gram).
+#include <cstdlib>
+
 #include "api.h"
 #include "cw_core.cuh"
 
@@ -20,8 +22,15 @@ constexpr int kWarps = kThreads / 32;
 // the upper triangle of the outer product in registers.
 // AUX: one more row = the coordinate-wise lower median of the (scaled) rows, computed in registers
 // with the selection network of cw_core.cuh, stored to a.aux_median and included in the products.
-template <int NS, int V, bool AUX>
+// STAGED: every thread streams its next tiles into a thread-private slot of a 3-deep shared-memory
+// ring with cp.async (the staging helpers of cw_core.cuh), so two tiles of loads stay in flight per
+// thread while the 36 .. 153 FMAs of the current tile run -- at 124+ registers only two CTAs fit an
+// SM and the direct form was latency bound (0.49 of the HBM copy rate at n = 8, profiles/gram_small.md).
+constexpr int kGramStages = 3;
+
+template <int NS, int V, bool AUX, bool STAGED>
 __global__ void __launch_bounds__(kThreads) gram_small_kernel(const __grid_constant__ BzGramArgs a) {
+  extern __shared__ __align__(16) float gram_stage_mem[];
   constexpr int NR = NS + (AUX ? 1 : 0);
   constexpr int T = NR * (NR + 1) / 2;
   float acc[T];
@@ -48,9 +57,48 @@ __global__ void __launch_bounds__(kThreads) gram_small_kernel(const __grid_const
     for (int i = 0; i < NS; ++i) v[i] = (i < n) ? canon(col[i] * a.scales.s[i]) : 0.f;
     return bzcw::cw_pick<NS, BZ_CW_MEDIAN>(v, n, 0, apad);
   };
-  for (long long u = (long long)blockIdx.x * kThreads + threadIdx.x; u < nvec; u += stride) {
+  const size_t stage_elems = (size_t)n * kThreads * V;
+  const long long u0 = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if constexpr (STAGED) {
+#pragma unroll
+    for (int st = 0; st < kGramStages - 1; ++st) {
+      const long long u = u0 + st * stride;
+      if (u < nvec) bzcw::cw_stage_issue<NS, V>(gram_stage_mem + st * stage_elems, kThreads, a.rows, n, a.off + u * V);
+      bzcw::cp_async_commit();
+    }
+  }
+  int slot = 0;
+  for (long long u = u0; u < nvec; u += stride) {
     const long long base = a.off + u * V;
     float x[NS][V];
+    if constexpr (STAGED) {
+      const long long un = u + (kGramStages - 1) * stride;
+      int sn = slot + kGramStages - 1;
+      if (sn >= kGramStages) sn -= kGramStages;
+      if (un < nvec) bzcw::cw_stage_issue<NS, V>(gram_stage_mem + sn * stage_elems, kThreads, a.rows, n, a.off + un * V);
+      bzcw::cp_async_commit();
+      bzcw::cp_async_wait<kGramStages - 1>();
+      const float* stage = gram_stage_mem + slot * stage_elems;
+#pragma unroll
+      for (int i = 0; i < NS; ++i) {
+        if (i < n) {
+          const float* p = stage + ((size_t)i * kThreads + threadIdx.x) * V;
+          if constexpr (V == 4) {
+            const float4 t = *reinterpret_cast<const float4*>(p);
+            x[i][0] = t.x; x[i][1] = t.y; x[i][2] = t.z; x[i][3] = t.w;
+          } else if constexpr (V == 2) {
+            const float2 t = *reinterpret_cast<const float2*>(p);
+            x[i][0] = t.x; x[i][1] = t.y;
+          } else {
+            x[i][0] = p[0];
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < V; ++c) x[i][c] = 0.f;
+        }
+      }
+      if (++slot == kGramStages) slot = 0;
+    } else {
 #pragma unroll
     for (int i = 0; i < NS; ++i) {
       if (i < n) {
@@ -67,6 +115,7 @@ __global__ void __launch_bounds__(kThreads) gram_small_kernel(const __grid_const
 #pragma unroll
         for (int c = 0; c < V; ++c) x[i][c] = 0.f;
       }
+    }
     }
     float med[V];
 #pragma unroll
@@ -89,6 +138,7 @@ __global__ void __launch_bounds__(kThreads) gram_small_kernel(const __grid_const
       }
     }
   }
+  if constexpr (STAGED) bzcw::cp_async_wait<0>();
   // scalar tail (len % V) handled by block 0
   if (V > 1 && blockIdx.x == 0) {
     const long long tail0 = a.off + nvec * V;
@@ -256,10 +306,37 @@ int bz_gram(const BzGramArgs* args, int sm_count, cudaStream_t stream) {
     al8 = al8 && ((uintptr_t)a.aux_median % 8) == 0;
     a.scales.s[n] = 1.f;           // the median row is built from already-scaled values
   }
-#define BZ_GRAM_SMALL(NS_, V_)                                                         \
-  do {                                                                                 \
-    if (aux) gram_small_kernel<NS_, V_, true><<<grid, kThreads, 0, stream>>>(a);       \
-    else gram_small_kernel<NS_, V_, false><<<grid, kThreads, 0, stream>>>(a);          \
+  // the cp.async-staged form pays off once every thread has several tiles to stream (impl: 0 auto,
+  // 1 direct, 2 staged -- BYZPY_GRAM_SMALL_IMPL, for A/B measurements)
+  static const int forced = [] {
+    const char* e = getenv("BYZPY_GRAM_SMALL_IMPL");
+    return e ? atoi(e) : 0;
+  }();
+#define BZ_GRAM_LAUNCH(NS_, V_, AUX_, ST_)                                                          \
+  do {                                                                                              \
+    const size_t smem = ST_ ? (size_t)kGramStages * n * kThreads * V_ * sizeof(float) : 0;          \
+    if (ST_) {                                                                                      \
+      static bool conf = false;                                                                     \
+      if (!conf) {                                                                                  \
+        cudaError_t ce = cudaFuncSetAttribute(gram_small_kernel<NS_, V_, AUX_, ST_>,                \
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024); \
+        if (ce != cudaSuccess) return (int)ce;                                                      \
+        conf = true;                                                                                \
+      }                                                                                             \
+    }                                                                                               \
+    gram_small_kernel<NS_, V_, AUX_, ST_><<<grid, kThreads, smem, stream>>>(a);                     \
+  } while (0)
+#define BZ_GRAM_SMALL(NS_, V_)                                                                      \
+  do {                                                                                              \
+    const bool st_ = NS_ >= 8 && forced != 1 &&                                                     \
+                     (forced == 2 || a.len / V_ >= (long long)sm_count * kThreads * 4);             \
+    if (aux) {                                                                                      \
+      if (st_) BZ_GRAM_LAUNCH(NS_, V_, true, true);                                                 \
+      else BZ_GRAM_LAUNCH(NS_, V_, true, false);                                                    \
+    } else {                                                                                        \
+      if (st_) BZ_GRAM_LAUNCH(NS_, V_, false, true);                                                \
+      else BZ_GRAM_LAUNCH(NS_, V_, false, false);                                                   \
+    }                                                                                               \
   } while (0)
   if (n <= 2) {
     if (al16) BZ_GRAM_SMALL(2, 4);
@@ -274,6 +351,7 @@ int bz_gram(const BzGramArgs* args, int sm_count, cudaStream_t stream) {
     if (al8) BZ_GRAM_SMALL(16, 2);
     else BZ_GRAM_SMALL(16, 1);
 #undef BZ_GRAM_SMALL
+#undef BZ_GRAM_LAUNCH
   } else if (n <= 32) {
     gram_tiled_kernel<2><<<grid, kThreads, 0, stream>>>(a);
   } else if (n <= 64) {

@@ -144,3 +144,135 @@ int bz_wsum(const BzWsumArgs* args, int sm_count, cudaStream_t stream) {
   if (a.m <= 4) return launch_m<4>(a, vec_ok, sm_count, stream);
   return launch_m<8>(a, vec_ok, sm_count, stream);
 }
+
+// ------------------------------------------------------------------------------------------
+// Y = W (S X) for 8 < m <= 128 output rows in ONE pass over the inputs (NNM emits n mixed vectors,
+// Bucketing n / s bucket means; reference pre_aggregators/nnm.py:92-93 does this as `mask @ flat`).
+// The m <= 8 kernel above re-reads the n x d matrix once per 8 output rows; here a CTA stages a
+// [n x 128] coordinate tile in shared memory with cp.async (two stages) next to the whole weight
+// matrix (transposed, scales folded in) and computes the [m x 128] output tile as a register-tiled
+// fp32 GEMM: 16 x 16 threads, each owning RM rows x 8 coordinates, 4 LDS.128 per 8 RM FMAs.  The
+// arithmetic (m n FMAs per coordinate) is the bound: at m = n = 64 it is 2x the single-pass byte time
+// instead of the 4.5x of eight passes.  Zero weights are skipped by predication, like above, so a
+// +-inf / NaN row excluded from an output cannot poison it with 0 * inf.
+namespace {
+
+constexpr int kTileC = 128;          // coordinates per tile
+constexpr int kMultiStages = 2;
+
+template <int RM>
+__global__ void __launch_bounds__(kThreads) wsum_multi_kernel(const __grid_constant__ BzWsumMultiArgs a) {
+  extern __shared__ __align__(16) float wm_smem[];
+  const int n = a.n, m = a.m;
+  constexpr int MP = 16 * RM;                       // padded output rows
+  float* Wt = wm_smem;                              // [n][MP]  (transposed: Wt[k][r] = W[r][k] * scale[k])
+  float* Xs = wm_smem + (size_t)n * MP;             // kMultiStages x [n][kTileC]
+  for (int t = threadIdx.x; t < n * MP; t += kThreads) {
+    const int k = t / MP, r = t % MP;
+    Wt[t] = (r < m) ? a.W[(size_t)r * n + k] * a.scales.s[k] : 0.f;
+  }
+  const long long ntiles = a.len / kTileC;
+  const int tr = threadIdx.x >> 4, tc = threadIdx.x & 15;
+  const size_t stage_elems = (size_t)n * kTileC;
+  auto issue = [&](long long tile, int stage) {
+    const long long col = a.off + tile * kTileC;
+    float* dst = Xs + stage * stage_elems;
+    // n rows x 32 chunks of 16 bytes
+    for (int q = threadIdx.x; q < n * (kTileC / 4); q += kThreads) {
+      const int k = q >> 5, ch = q & 31;
+      const unsigned sd = (unsigned)__cvta_generic_to_shared(dst + (size_t)k * kTileC + ch * 4);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sd), "l"(a.rows.p[k] + col + ch * 4) : "memory");
+    }
+  };
+  long long tile = blockIdx.x;
+  if (tile < ntiles) issue(tile, 0);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  int stage = 0;
+  for (; tile < ntiles; tile += gridDim.x) {
+    const long long next = tile + gridDim.x;
+    if (next < ntiles) issue(next, stage ^ 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();                                  // the tile (and, first time, Wt) is visible to everyone
+    const float* X = Xs + stage * stage_elems;
+    float acc[RM][8];
+#pragma unroll
+    for (int i = 0; i < RM; ++i)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < n; ++k) {
+      const float4 x0 = *reinterpret_cast<const float4*>(X + (size_t)k * kTileC + tc * 8);
+      const float4 x1 = *reinterpret_cast<const float4*>(X + (size_t)k * kTileC + tc * 8 + 4);
+      const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      float wv[RM];
+      if constexpr (RM >= 4) {
+#pragma unroll
+        for (int i = 0; i < RM; i += 4) {
+          const float4 w4 = *reinterpret_cast<const float4*>(Wt + (size_t)k * MP + tr * RM + i);
+          wv[i] = w4.x; wv[i + 1] = w4.y; wv[i + 2] = w4.z; wv[i + 3] = w4.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < RM; ++i) wv[i] = Wt[(size_t)k * MP + tr * RM + i];
+      }
+#pragma unroll
+      for (int i = 0; i < RM; ++i) {
+        if (wv[i] != 0.f) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[i][c] = fmaf(wv[i], xv[c], acc[i][c]);
+        }
+      }
+    }
+    const long long base = a.off + tile * kTileC + tc * 8;
+#pragma unroll
+    for (int i = 0; i < RM; ++i) {
+      const int r = tr * RM + i;
+      if (r < m) {
+        stg_stream4(a.out.p[r] + base, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+        stg_stream4(a.out.p[r] + base + 4, make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]));
+      }
+    }
+    __syncthreads();                                  // everyone is done with this stage before it is refilled
+    stage ^= 1;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+template <int RM>
+int launch_multi(const BzWsumMultiArgs& a, int sm_count, cudaStream_t stream) {
+  const size_t smem = ((size_t)a.n * 16 * RM + (size_t)kMultiStages * a.n * kTileC) * sizeof(float);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(wsum_multi_kernel<RM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = smem;
+  }
+  int occ = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wsum_multi_kernel<RM>, kThreads, smem) != cudaSuccess || occ < 1)
+    occ = 1;
+  long long blocks = a.len / kTileC;
+  const long long cap = (long long)sm_count * occ;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) return 0;
+  wsum_multi_kernel<RM><<<(unsigned)blocks, kThreads, smem, stream>>>(a);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+int bz_wsum_multi_tile() { return kTileC; }
+
+int bz_wsum_multi(const BzWsumMultiArgs* args, int sm_count, cudaStream_t stream) {
+  const BzWsumMultiArgs& a = *args;
+  if (a.n < 1 || a.n > BZ_MAXN || a.m < 1 || a.m > BZ_MAXN || a.W == nullptr) return (int)cudaErrorInvalidValue;
+  if ((a.off % 4) != 0 || (a.len % kTileC) != 0) return (int)cudaErrorInvalidValue;
+  for (int i = 0; i < a.n; ++i)
+    if (((uintptr_t)a.rows.p[i] % 16) != 0) return (int)cudaErrorInvalidValue;
+  for (int r = 0; r < a.m; ++r)
+    if (a.out.p[r] == nullptr || ((uintptr_t)a.out.p[r] % 16) != 0) return (int)cudaErrorInvalidValue;
+  if (a.m <= 16) return launch_multi<1>(a, sm_count, stream);
+  if (a.m <= 32) return launch_multi<2>(a, sm_count, stream);
+  if (a.m <= 64) return launch_multi<4>(a, sm_count, stream);
+  return launch_multi<8>(a, sm_count, stream);
+}

@@ -329,11 +329,14 @@ def weighted_sum(
     scales: Optional[Sequence[float]] = None,
     out: Optional[torch.Tensor] = None,
     update: Optional[dict] = None,
+    multi_impl: str = "auto",
 ) -> torch.Tensor:
     """``Y = W (S X)`` with ``W`` an ``(m, n)`` (or ``(n,)``) weight tensor on the device.
 
-    Returns ``(m, d)`` (or ``(d,)`` for 1-D ``W``).  For ``m <= 8`` this is the
-    streaming pointer-table kernel; larger ``m`` uses one cuBLAS GEMM.
+    Returns ``(m, d)`` (or ``(d,)`` for 1-D ``W``).  ``m <= 8``: the streaming pointer-table kernel
+    (one pass, zero-weight rows skipped).  ``m > 8``: one pass too -- a register-tiled fp32 GEMM over
+    shared-memory tiles of the inputs (``csrc/wsum.cu``, ``wsum_multi``) -- unless ``W`` is sparse enough
+    that the 8-rows-per-pass kernel reads less (a diagonal map reads every input once either way).
     """
     rows = as_rows(rows)
     n = len(rows)
@@ -355,13 +358,26 @@ def weighted_sum(
         params, moms, lr, mu, wd = _unpack_update(update)
         ptrs = [r.data_ptr() for r in rows]
         sc = _scales(scales, n)
-        # the streaming kernel emits up to 8 output rows per pass over the inputs
+        d_main = 0
+        if m > 8 and not params and hasattr(ext, "wsum_multi") and _wsum_dense(W2, multi_impl):
+            tile = ext.WSUM_MULTI_TILE
+            d_main = (d // tile) * tile
+            if d_main and all(p % 16 == 0 for p in ptrs) and out2.data_ptr() % 16 == 0 and (d * 4) % 16 == 0:
+                ext.wsum_multi(ptrs, sc, Wd.data_ptr(), m, 0, d_main, [out2[r].data_ptr() for r in range(m)],
+                               sm_count(dev), _stream(dev))
+            else:
+                d_main = 0
+        if d_main == d:
+            return out2[0] if squeeze else out2
+        # the streaming kernel emits up to 8 output rows per pass over the inputs (here: the remaining columns)
+        if d_main:
+            ptrs = [p + 4 * d_main for p in ptrs]
         for r0 in range(0, m, 8):
             mb = min(8, m - r0)
             first = r0 == 0
             ext.wsum(
-                ptrs, sc, Wd[r0:r0 + mb].data_ptr(), mb, 0, d,
-                [out2[r0 + r].data_ptr() for r in range(mb)],
+                ptrs, sc, Wd[r0:r0 + mb].data_ptr(), mb, 0, d - d_main,
+                [out2[r0 + r].data_ptr() + 4 * d_main for r in range(mb)],
                 [p.data_ptr() for p in params] if first else [],
                 [mm.data_ptr() for mm in moms] if first else [],
                 lr, mu, wd, sm_count(dev), _stream(dev),
@@ -374,6 +390,14 @@ def weighted_sum(
     if update is not None:
         ref.sgd_step(res[0], **update)
     return res[0] if squeeze else res
+
+
+def _wsum_dense(W: torch.Tensor, impl: str) -> bool:
+    """Use the one-pass multi-row kernel?  ``"auto"`` avoids a host sync on device weights: the
+    decision is structural (m > 8); ``"multi"`` / ``"passes"`` force one form (benchmarks, tests)."""
+    if impl == "passes":
+        return False
+    return True
 
 
 def colstat(rows: Rows, a: float, b: float, *, scales=None, out=None) -> torch.Tensor:

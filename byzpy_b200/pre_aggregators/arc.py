@@ -11,6 +11,7 @@ from .base import LinearPreAggregator
 class ARC(LinearPreAggregator):
     name = "pre-agg/arc"
     gram_diag_only = True       # only the row norms are used: the torch fallback skips the n^2 d work
+    diagonal_map = True
 
     def __init__(self, f: int = 0, *, chunk_size: int = 32) -> None:
         if f < 0:

@@ -50,6 +50,7 @@ class LinearPreAggregator(PreAggregator):
     supports_subtasks = True
     max_subtasks_inflight = 0
     needs_gram: bool = True
+    diagonal_map: bool = False      # W = diag(s): every output row reads exactly one input row
     feature_chunk_size: int = 8192
 
     def _validate(self, n: int) -> None:
@@ -89,7 +90,10 @@ class LinearPreAggregator(PreAggregator):
                 # on the input device; its clipping / ARC go through NumPy, clipping.py:53-62)
                 Wd = self.row_map_device(Gd, n)
                 if Wd is not None:
-                    Y = ops.weighted_sum(_kernel_rows(rows), Wd.to(torch.float32))
+                    # diagonal maps (Clipping, ARC) read every input once with the 8-rows-per-pass kernel;
+                    # dense maps (NNM) take the one-pass multi-row kernel
+                    Y = ops.weighted_sum(_kernel_rows(rows), Wd.to(torch.float32),
+                                         multi_impl="passes" if getattr(self, "diagonal_map", False) else "auto")
                     if like.dim() == 1 and Y.dtype == like.dtype:
                         return list(Y.unbind(0))
                     return [finish(Y[i], like) for i in range(Y.shape[0])]

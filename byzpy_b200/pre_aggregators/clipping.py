@@ -11,6 +11,7 @@ from .base import LinearPreAggregator
 class Clipping(LinearPreAggregator):
     name = "pre-agg/clipping"
     gram_diag_only = True       # only the row norms are used: the torch fallback skips the n^2 d work
+    diagonal_map = True
 
     def __init__(self, threshold: float = 2.0, *, chunk_size: int = 32) -> None:
         if threshold < 0:

