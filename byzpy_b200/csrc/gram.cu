@@ -22,10 +22,9 @@ constexpr int kWarps = kThreads / 32;
 // the upper triangle of the outer product in registers.
 // AUX: one more row = the coordinate-wise lower median of the (scaled) rows, computed in registers
 // with the selection network of cw_core.cuh, stored to a.aux_median and included in the products.
-// STAGED: every thread streams its next tiles into a thread-private slot of a 3-deep shared-memory
-// ring with cp.async (the staging helpers of cw_core.cuh), so two tiles of loads stay in flight per
-// thread while the 36 .. 153 FMAs of the current tile run -- at 124+ registers only two CTAs fit an
-// SM and the direct form was latency bound (0.49 of the HBM copy rate at n = 8, profiles/gram_small.md).
+// STAGED (experiment, BYZPY_GRAM_SMALL_IMPL=2): every thread streams its next tiles into a thread-private
+// slot of a 3-deep shared-memory ring with cp.async (the staging helpers of cw_core.cuh).  Measured slower
+// than the direct register form (profiles/gram_small.md), kept for A/B runs.
 constexpr int kGramStages = 3;
 
 template <int NS, int V, bool AUX, bool STAGED>
@@ -328,8 +327,10 @@ int bz_gram(const BzGramArgs* args, int sm_count, cudaStream_t stream) {
   } while (0)
 #define BZ_GRAM_SMALL(NS_, V_)                                                                      \
   do {                                                                                              \
-    const bool st_ = NS_ >= 8 && forced != 1 &&                                                     \
-                     (forced == 2 || a.len / V_ >= (long long)sm_count * kThreads * 4);             \
+    /* measured (profiles/gram_small.md): the staged form is SLOWER here (n = 8: 0.21 vs 0.17 ms for 537 MB, */ \
+    /* n = 16: 0.49 vs 0.38 ms) -- the extra shared-memory round trip costs more than the deeper queue wins */ \
+    /* -- so it only runs when forced */                                                                  \
+    const bool st_ = NS_ >= 8 && forced == 2;                                                       \
     if (aux) {                                                                                      \
       if (st_) BZ_GRAM_LAUNCH(NS_, V_, true, true);                                                 \
       else BZ_GRAM_LAUNCH(NS_, V_, true, false);                                                    \

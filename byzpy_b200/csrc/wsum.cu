@@ -151,7 +151,8 @@ int bz_wsum(const BzWsumArgs* args, int sm_count, cudaStream_t stream) {
 // The m <= 8 kernel above re-reads the n x d matrix once per 8 output rows; here a CTA stages a
 // [n x 128] coordinate tile in shared memory with cp.async (two stages) next to the whole weight
 // matrix (transposed, scales folded in) and computes the [m x 128] output tile as a register-tiled
-// fp32 GEMM: 16 x 16 threads, each owning RM rows x 8 coordinates, 4 LDS.128 per 8 RM FMAs.  The
+// fp32 GEMM: 16 x 16 threads, each owning RM rows x 8 coordinates (two 4-wide groups, bank-conflict
+// free), 3 LDS.128 per 8 RM FMAs.  The
 // arithmetic (m n FMAs per coordinate) is the bound: at m = n = 64 it is 2x the single-pass byte time
 // instead of the 4.5x of eight passes.  Zero weights are skipped by predication, like above, so a
 // +-inf / NaN row excluded from an output cannot poison it with 0 * inf.
@@ -202,8 +203,10 @@ __global__ void __launch_bounds__(kThreads) wsum_multi_kernel(const __grid_const
       for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
 #pragma unroll 4
     for (int k = 0; k < n; ++k) {
-      const float4 x0 = *reinterpret_cast<const float4*>(X + (size_t)k * kTileC + tc * 8);
-      const float4 x1 = *reinterpret_cast<const float4*>(X + (size_t)k * kTileC + tc * 8 + 4);
+      // coordinates tc*4 .. +3 and 64 + tc*4 .. +3: consecutive threads read consecutive 16-byte chunks
+      // (a 32-byte stride per thread would put threads 0/4/8/12 on the same banks: 4-way conflict)
+      const float4 x0 = *reinterpret_cast<const float4*>(X + (size_t)k * kTileC + tc * 4);
+      const float4 x1 = *reinterpret_cast<const float4*>(X + (size_t)k * kTileC + 64 + tc * 4);
       const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
       float wv[RM];
       if constexpr (RM >= 4) {
@@ -224,13 +227,13 @@ __global__ void __launch_bounds__(kThreads) wsum_multi_kernel(const __grid_const
         }
       }
     }
-    const long long base = a.off + tile * kTileC + tc * 8;
+    const long long base = a.off + tile * kTileC + tc * 4;
 #pragma unroll
     for (int i = 0; i < RM; ++i) {
       const int r = tr * RM + i;
       if (r < m) {
         stg_stream4(a.out.p[r] + base, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
-        stg_stream4(a.out.p[r] + base + 4, make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]));
+        stg_stream4(a.out.p[r] + base + 64, make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]));
       }
     }
     __syncthreads();                                  // everyone is done with this stage before it is refilled

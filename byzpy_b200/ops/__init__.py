@@ -393,11 +393,19 @@ def weighted_sum(
 
 
 def _wsum_dense(W: torch.Tensor, impl: str) -> bool:
-    """Use the one-pass multi-row kernel?  ``"auto"`` avoids a host sync on device weights: the
-    decision is structural (m > 8); ``"multi"`` / ``"passes"`` force one form (benchmarks, tests)."""
+    """Use the one-pass multi-row kernel?  ``"multi"`` / ``"passes"`` force one form (benchmarks, tests);
+    ``"auto"`` compares the two cost models without looking at the (device-resident) weights: the
+    8-rows-per-pass kernel moves ``ceil(m / 8) n + m`` floats per coordinate at the HBM rate, the
+    one-pass kernel issues ``m n`` FMAs per coordinate at about half the fp32 FMA peak (measured)."""
     if impl == "passes":
         return False
-    return True
+    if impl == "multi":
+        return True
+    m, n = W.shape
+    passes_s = ((m + 7) // 8 * n + m) * 4 / 6.4e12
+    eff = 0.12 if m <= 16 else (0.2 if m <= 32 else (0.4 if m <= 64 else 0.5))   # FMA efficiency by register-tile height
+    multi_s = m * n / (eff * 37.2e12)
+    return multi_s < passes_s
 
 
 def colstat(rows: Rows, a: float, b: float, *, scales=None, out=None) -> torch.Tensor:

@@ -709,13 +709,13 @@ def test_weighted_sum_one_pass_multi_row_kernel(n, m):
     W = torch.randn(m, n, generator=g).to(dev())
     W[torch.rand(m, n, generator=g).to(dev()) < 0.4] = 0.0
     rows = list(X.unbind(0))
-    Y = ops.weighted_sum(rows, W)
+    Y = ops.weighted_sum(rows, W, multi_impl="multi")
     ref64 = (W.double() @ X.double()).float()
     torch.testing.assert_close(Y, ref64, rtol=1e-5, atol=1e-4)
     Yp = ops.weighted_sum(rows, W, multi_impl="passes")
     torch.testing.assert_close(Y, Yp, rtol=1e-5, atol=1e-4)
     sc = [1.0 + 0.05 * i for i in range(n)]
-    Ys = ops.weighted_sum(rows, W, scales=sc)
+    Ys = ops.weighted_sum(rows, W, scales=sc, multi_impl="multi")
     torch.testing.assert_close(Ys, (W.double() @ (X.double() * torch.tensor(sc, device=dev(), dtype=torch.float64)[:, None])).float(),
                                rtol=1e-5, atol=1e-4)
     # an all-inf row with zero weight everywhere except one output
@@ -724,7 +724,6 @@ def test_weighted_sum_one_pass_multi_row_kernel(n, m):
     W2 = W.clone()
     W2[:, 3] = 0.0
     W2[1, 3] = 0.5
-    Y2 = ops.weighted_sum(list(X2.unbind(0)), W2)
-    assert torch.isinf(Y2[1]).all() or torch.isnan(Y2[1]).any() or True
+    Y2 = ops.weighted_sum(list(X2.unbind(0)), W2, multi_impl="multi")
     keep = [r for r in range(m) if r != 1]
     assert torch.isfinite(Y2[keep]).all()
