@@ -449,6 +449,229 @@ __global__ void __launch_bounds__(kThreads) bwd_apply_kernel(
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Single-launch forms for SMALL activations (<= 4 MB: the 14x14 and 7x7 stages of a ResNet at batch
+// 32), built on thread-block clusters.  A cluster of kClusterSize CTAs owns a group of CGC channels
+// for ALL rows: every CTA reduces its slab of rows, the per-CTA partials meet through distributed
+// shared memory (mapa + ld.shared::cluster behind one barrier.cluster), every CTA finalises the
+// group's statistics itself (identical fp64 fold, rank 0 stores them) and applies them to its slab,
+// which is still in L2.  One launch instead of two dependent ones: at these sizes a direction costs
+// ~5.5 us per dependent launch while the data streams in 1-2 us (bench/bn_layers.py).  No cross-cluster
+// synchronisation exists, so nothing depends on co-residency of the whole grid.
+constexpr int kClusterSize = 8;
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_dsmem(const float* local, uint32_t rank) {
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(local), ra;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+  return v;
+}
+
+template <int CGC, bool BWD>
+__global__ void __launch_bounds__(kThreads) bn_cluster_kernel(
+    const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ out,
+    long long R, int C, int relu, const __nv_bfloat16* __restrict__ res_or_mask, __nv_bfloat16* __restrict__ dres,
+    const Finalize fin) {
+  constexpr int NG = CGC / 8;                 // 8-channel groups per cluster
+  constexpr int LANES = kThreads / NG;        // row lanes per CTA
+  __shared__ float red[LANES * CGC * 2];      // 16 KB
+  __shared__ float part[CGC * 2];             // this CTA's partial sums, read by the whole cluster
+  __shared__ float cs[CGC * 3];               // scale, shift | P, Q, S
+  const uint32_t rank = cluster_rank();
+  const int c0 = (blockIdx.x / kClusterSize) * CGC;
+  const int g = threadIdx.x % NG, rl = threadIdx.x / NG;
+  const long long per = (R + kClusterSize - 1) / kClusterSize;
+  const long long r0 = (long long)rank * per;
+  const long long r1 = (r0 + per < R) ? r0 + per : R;
+  const int cb = c0 + g * 8;
+  float a0[8], a1[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a0[k] = a1[k] = 0.f;
+  float sc[8], sh[8], mu[8], is[8];
+  if (BWD) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      sc[k] = fin.scale[cb + k];
+      sh[k] = fin.shift[cb + k];
+      mu[k] = fin.mean[cb + k];
+      is[k] = fin.invstd[cb + k];
+    }
+  }
+  // dy' = dy masked by the ReLU of the forward output (saved output when a residual was added)
+  auto masked = [&](const float (&xf)[8], float (&df)[8], const Bf8& py) {
+    if (res_or_mask != nullptr) {
+      float yf[8];
+      unpack(py, yf);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) df[k] = yf[k] > 0.f ? df[k] : 0.f;
+    } else if (relu) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) df[k] = fmaf(xf[k], sc[k], sh[k]) > 0.f ? df[k] : 0.f;
+    }
+  };
+  constexpr int U = 4;
+  for (long long r = r0 + rl; r < r1; r += (long long)U * LANES) {
+    Bf8 bx[U], bd[U], by[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const long long rr = r + (long long)j * LANES;
+      if (rr < r1) {
+        const long long o = rr * C + cb;
+        bx[j] = ld8(x + o);
+        if (BWD) {
+          bd[j] = ld8(dy + o);
+          if (res_or_mask != nullptr) by[j] = ld8(res_or_mask + o);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      if (r + (long long)j * LANES < r1) {
+        float xf[8];
+        unpack(bx[j], xf);
+        if (!BWD) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            a0[k] += xf[k];
+            a1[k] = fmaf(xf[k], xf[k], a1[k]);
+          }
+        } else {
+          float df[8];
+          unpack(bd[j], df);
+          masked(xf, df, by[j]);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            a0[k] += df[k];
+            a1[k] = fmaf(df[k], (xf[k] - mu[k]) * is[k], a1[k]);
+          }
+        }
+      }
+    }
+  }
+  float* mine = red + ((size_t)rl * CGC + g * 8) * 2;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    mine[2 * k] = a0[k];
+    mine[2 * k + 1] = a1[k];
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < CGC * 2; t += kThreads) {
+    float s = 0.f;
+    for (int l = 0; l < LANES; ++l) s += red[(size_t)l * CGC * 2 + t];
+    part[t] = s;
+  }
+  cluster_sync_all();                          // every CTA's partial is visible cluster-wide
+  if (threadIdx.x < CGC) {
+    double s = 0.0, q = 0.0;
+#pragma unroll
+    for (uint32_t k = 0; k < (uint32_t)kClusterSize; ++k) {
+      s += (double)ld_dsmem(part + 2 * threadIdx.x, k);
+      q += (double)ld_dsmem(part + 2 * threadIdx.x + 1, k);
+    }
+    const int c = c0 + threadIdx.x;
+    if (BWD) {
+      float P_, Q_, S_;
+      fin.backward(c, C, R, s, q, P_, Q_, S_, rank == 0);
+      cs[3 * threadIdx.x] = P_;
+      cs[3 * threadIdx.x + 1] = Q_;
+      cs[3 * threadIdx.x + 2] = S_;
+    } else {
+      float sc_, sh_;
+      fin.forward(c, R, s, q, sc_, sh_, rank == 0);
+      cs[3 * threadIdx.x] = sc_;
+      cs[3 * threadIdx.x + 1] = sh_;
+    }
+  }
+  __syncthreads();
+  float k0[8], k1[8], k2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    k0[k] = cs[3 * (g * 8 + k)];
+    k1[k] = cs[3 * (g * 8 + k) + 1];
+    k2[k] = cs[3 * (g * 8 + k) + 2];
+  }
+  for (long long r = r0 + rl; r < r1; r += (long long)U * LANES) {
+    Bf8 bx[U], bd[U], by[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const long long rr = r + (long long)j * LANES;
+      if (rr < r1) {
+        const long long o = rr * C + cb;
+        bx[j] = ld8(x + o);
+        if (BWD) bd[j] = ld8(dy + o);
+        if (res_or_mask != nullptr) by[j] = ld8(res_or_mask + o);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const long long rr = r + (long long)j * LANES;
+      if (rr < r1) {
+        const long long o = rr * C + cb;
+        float xf[8];
+        unpack(bx[j], xf);
+        if (!BWD) {
+          float rf[8];
+          if (res_or_mask != nullptr) {
+            unpack(by[j], rf);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) rf[k] = 0.f;
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float v = fmaf(xf[k], k0[k], k1[k]) + rf[k];
+            xf[k] = (relu && v < 0.f) ? 0.f : v;
+          }
+          st8(out + o, pack(xf));
+        } else {
+          float df[8];
+          unpack(bd[j], df);
+          masked(xf, df, by[j]);
+          if (dres != nullptr) st8(dres + o, pack(df));
+#pragma unroll
+          for (int k = 0; k < 8; ++k) df[k] = fmaf(k0[k], df[k], fmaf(k1[k], xf[k], k2[k]));
+          st8(out + o, pack(df));
+        }
+      }
+    }
+  }
+  cluster_sync_all();                          // nobody leaves while a peer may still read its partial
+}
+
+bool cluster_mode(long long R, int C) {
+  static const bool on = [] {
+    const char* e = std::getenv("BYZPY_BN_CLUSTER");
+    return !(e && e[0] == '0');
+  }();
+  return on && (C % 16) == 0 && R * (long long)C * 2 <= (4ll << 20) && R >= kClusterSize;
+}
+
+template <int CGC, bool BWD, typename... Args>
+cudaError_t launch_cluster(int C, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(C / CGC) * kClusterSize);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kClusterSize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, bn_cluster_kernel<CGC, BWD>, args...);
+}
+
 int reduce_blocks(long long R, int sm_count) {
   // two resident CTAs per SM saturate HBM with the 8-deep unrolled 16-byte loads; more CTAs only
   // lengthen the finalize
@@ -516,6 +739,19 @@ int bz_bn_forward(const BzBnArgs* a, int sm_count, cudaStream_t stream) {
   int launches = 0;
   bool fused_fin = false;
   int nb = 0;
+  if (a->training && cluster_mode(a->R, C)) {
+    // one launch: thread-block clusters + distributed shared memory (see bn_cluster_kernel)
+    cudaError_t ce = (C <= 512 || (C % 32) != 0)
+                         ? launch_cluster<16, false>(C, stream, x, (const __nv_bfloat16*)nullptr, y, a->R, C, a->relu, res,
+                                                     (__nv_bfloat16*)nullptr, fin)
+                         : launch_cluster<32, false>(C, stream, x, (const __nv_bfloat16*)nullptr, y, a->R, C, a->relu, res,
+                                                     (__nv_bfloat16*)nullptr, fin);
+    if (ce == cudaSuccess) {
+      if (a->launches) *a->launches = 1;
+      return (int)cudaGetLastError();
+    }
+    cudaGetLastError();     // cluster launch unavailable: fall through to the two-launch path
+  }
   if (a->training) {
     fused_fin = fin_mode(a->R, C);
     nb = fused_fin ? fin_blocks(a->R) : reduce_blocks(a->R, sm_count);
@@ -562,6 +798,16 @@ int bz_bn_backward(const BzBnArgs* a, int sm_count, cudaStream_t stream) {
   const Finalize fin = make_finalize(a);
   const long long total8 = a->R * (C >> 3);
   int launches = 2;
+  if (cluster_mode(a->R, C)) {
+    cudaError_t ce = (C <= 512 || (C % 32) != 0)
+                         ? launch_cluster<16, true>(C, stream, x, dy, dx, a->R, C, a->relu, ymask, dres, fin)
+                         : launch_cluster<32, true>(C, stream, x, dy, dx, a->R, C, a->relu, ymask, dres, fin);
+    if (ce == cudaSuccess) {
+      if (a->launches) *a->launches = 1;
+      return (int)cudaGetLastError();
+    }
+    cudaGetLastError();
+  }
   reduce_partial_kernel<true><<<nb, kThreads, smem, stream>>>(x, dy, a->R, C, a->scale, a->shift, a->mean,
                                                              a->invstd, a->relu, ymask, a->partial);
   if (fused_fin) {
