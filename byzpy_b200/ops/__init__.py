@@ -403,7 +403,9 @@ def _wsum_dense(W: torch.Tensor, impl: str) -> bool:
         return True
     m, n = W.shape
     passes_s = ((m + 7) // 8 * n + m) * 4 / 6.4e12
-    eff = 0.12 if m <= 16 else (0.2 if m <= 32 else (0.4 if m <= 64 else 0.5))   # FMA efficiency by register-tile height
+    # measured fp32-FMA efficiency by register-tile height (profiles/wsum_multi.md): 13 TFMA/s at m = 32,
+    # 21 TFMA/s at m = 64 / 128 of the 37 TFMA/s peak
+    eff = 0.2 if m <= 16 else (0.35 if m <= 32 else (0.42 if m <= 64 else 0.55))
     multi_s = m * n / (eff * 37.2e12)
     return multi_s < passes_s
 
