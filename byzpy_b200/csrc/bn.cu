@@ -652,7 +652,11 @@ bool cluster_mode(long long R, int C) {
     const char* e = std::getenv("BYZPY_BN_CLUSTER");
     return !(e && e[0] == '0');
   }();
-  return on && (C % 16) == 0 && R * (long long)C * 2 <= (4ll << 20) && R >= kClusterSize;
+  static const long long limit = [] {
+    const char* e = std::getenv("BYZPY_BN_CLUSTER_MAX_MB");
+    return (long long)(e ? atof(e) * (1 << 20) : (4 << 20));
+  }();
+  return on && (C % 16) == 0 && R * (long long)C * 2 <= limit && R >= kClusterSize;
 }
 
 template <int CGC, bool BWD, typename... Args>
