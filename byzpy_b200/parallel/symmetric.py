@@ -124,14 +124,15 @@ class SymmetricBuffer:
     """
 
     def __init__(self, nbytes: int, device: torch.device, group=None, *, kind: Optional[str] = None,
-                 multicast: Optional[bool] = None):
-        ext = ops.require_ext()
+                 multicast: Optional[bool] = None, _ext=None):
+        ext = _ext if _ext is not None else ops.require_ext()     # (_ext: a fake driver, CPU protocol tests)
         self._ext = ext
         self.device = device
         self.group = group
         self.rank = dist.get_rank(group) if _dist_on() else 0
         self.world = dist.get_world_size(group) if _dist_on() else 1
-        self._dev_index = device.index if device.index is not None else torch.cuda.current_device()
+        self._dev_index = (device.index if device.index is not None
+                           else (torch.cuda.current_device() if device.type == "cuda" else 0))
         self.kind = kind or heap_kind(device, self.world)
         self.mc_base = 0
         self._closed = False
@@ -148,20 +149,21 @@ class SymmetricBuffer:
             if multicast:
                 raise RuntimeError("NVLS multicast needs the VMM symmetric heap")
             self._init_ipc(nbytes)
-        self.local = tensor_from_ptr(self._ptr, self.nbytes, device, owner=self)
+        self.local = (tensor_from_ptr(self._ptr, self.nbytes, device, owner=self) if device.type == "cuda"
+                      else torch.empty(0, dtype=torch.uint8))
 
     # ----------------------------------------------------------------- CUDA IPC heap
     def _init_ipc(self, nbytes: int) -> None:
         ext = self._ext
         self.nbytes = int((nbytes + 255) // 256 * 256)
-        with torch.cuda.device(self.device):
+        with _device_ctx(self.device):
             self._ptr = ext.raw_alloc(self.nbytes)
         self.ptrs[self.rank] = self._ptr
         if self.world > 1:
             handle = ext.ipc_export(self._ptr)
             handles: List[Optional[bytes]] = [None] * self.world
             dist.all_gather_object(handles, handle, group=self.group)
-            with torch.cuda.device(self.device):
+            with _device_ctx(self.device):
                 for r, h in enumerate(handles):
                     if r == self.rank:
                         continue
@@ -170,60 +172,192 @@ class SymmetricBuffer:
                     self._opened.append(p)
 
     # ----------------------------------------------------------------- VMM heap (+ multicast)
+    def _agree(self, ok: bool) -> bool:
+        """True when ``ok`` holds on EVERY rank.  Each set-up stage ends with exactly one of these, whether
+        or not it failed locally, so the ranks never diverge in their sequence of collectives and the
+        whole team takes the same fallback."""
+        if self.world == 1:
+            return bool(ok)
+        flags: List[Optional[bool]] = [None] * self.world
+        dist.all_gather_object(flags, bool(ok), group=self.group)
+        return all(flags)
+
     def _init_vmm(self, nbytes: int, multicast: Optional[bool]) -> None:
+        """VMM heap with the fallbacks agreed team-wide, stage by stage: no multicast support, or a
+        multicast step failing on any rank (no NVLS on this fabric, fabric manager down) -> unicast VMM
+        heap, deliveries by peer stores; allocation / fd export / import / mapping failing anywhere ->
+        the CUDA-IPC heap.  ``multicast=True`` turns the multicast fallbacks into errors."""
+        import warnings
+
         ext, dev = self._ext, self._dev_index
         sup = ext.vmm_support(dev)
-        want_mc = self.world > 1 and multicast is not False and bool(sup["multicast"])
         if multicast and self.world > 1 and not sup["multicast"]:
             raise RuntimeError("multicast=True but this device / driver reports no NVLS multicast support")
-        if self.world > 1:      # all ranks or none
-            flags: List[Optional[bool]] = [None] * self.world
-            dist.all_gather_object(flags, want_mc, group=self.group)
-            want_mc = all(flags)
-        gran = int(ext.vmm_granularity(dev, self.world, want_mc))
-        self._gran = gran
-        self.nbytes = int((nbytes + gran - 1) // gran * gran)
-        self._handle, self._ptr = ext.vmm_alloc(self.nbytes, gran, dev)
-        self.ptrs[self.rank] = self._ptr
+        want_mc = self._agree(self.world > 1 and multicast is not False and bool(sup["multicast"])) \
+            if self.world > 1 else False
         self._peer_handles: List[int] = []
         self._mc_handle = 0
-        if self.world == 1:
-            return
-        # ---- exchange the allocation handles as file descriptors
-        my_fd = ext.vmm_export_fd(self._handle)
-        fds = [my_fd]
-        if want_mc and self.rank == 0:
-            self._mc_handle = ext.mc_create(self.world, self.nbytes)
-            fds.append(ext.vmm_export_fd(self._mc_handle))
-        server = _FdServer(fds)
+        self._mc_bound = False
+        self._handle = 0
+        self._ptr = 0
+        fds: List[int] = []
+        err: Optional[BaseException] = None
+        # ---- stage A: local allocation, export, (rank 0) the multicast object
+        mc_local_ok = True
         try:
+            gran = int(ext.vmm_granularity(dev, self.world, want_mc))
+            self._gran = gran
+            self.nbytes = int((nbytes + gran - 1) // gran * gran)
+            self._handle, self._ptr = ext.vmm_alloc(self.nbytes, gran, dev)
+            self.ptrs[self.rank] = self._ptr
+            if self.world > 1:
+                fds.append(ext.vmm_export_fd(self._handle))
+                if want_mc and self.rank == 0:
+                    try:
+                        self._mc_handle = ext.mc_create(self.world, self.nbytes)
+                        fds.append(ext.vmm_export_fd(self._mc_handle))
+                    except Exception as exc:            # no multicast object: carry on unicast
+                        mc_local_ok = False
+                        err = exc
+        except Exception as exc:
+            err = exc
+            mc_local_ok = False
+        if self.world == 1:
+            if self._ptr == 0:
+                raise RuntimeError(f"VMM allocation failed: {err!r}") from err
+            return
+        if not self._agree(self._ptr != 0 and len(fds) >= 1):
+            self._vmm_teardown(fds)
+            warnings.warn(f"VMM symmetric heap unavailable on some rank ({err!r} here); using the CUDA-IPC heap")
+            self._fallback_ipc(nbytes, multicast)
+            return
+        if want_mc and not self._agree(mc_local_ok):
+            if multicast:
+                self._vmm_teardown(fds)
+                raise RuntimeError(f"multicast=True but the multicast object could not be created: {err!r}")
+            self._drop_multicast()
+            want_mc = False
+        # ---- stage B: exchange the allocation handles as file descriptors, map every peer
+        server = None
+        try:
+            try:
+                server = _FdServer(fds)
+                path: Optional[str] = server.path
+            except Exception as exc:
+                err, path = exc, None
             paths: List[Optional[str]] = [None] * self.world
-            dist.all_gather_object(paths, server.path, group=self.group)
-            for r in range(self.world):
-                if r == self.rank:
-                    continue
-                fd = _fetch_fd(paths[r], 0)
-                h = ext.vmm_import_fd(fd, dev)
-                ext.close_fd(fd)
-                p = ext.vmm_map(h, self.nbytes, gran, dev)
-                self._peer_handles.append(h)
-                self.ptrs[r] = p
-                self._opened.append(p)
+            dist.all_gather_object(paths, path, group=self.group)
+            ok = all(p is not None for p in paths)
+            if ok:
+                try:
+                    for r in range(self.world):
+                        if r == self.rank:
+                            continue
+                        fd = _fetch_fd(paths[r], 0)
+                        try:
+                            h = ext.vmm_import_fd(fd, dev)
+                        finally:
+                            ext.close_fd(fd)
+                        self._peer_handles.append(h)
+                        p = ext.vmm_map(h, self.nbytes, self._gran, dev)
+                        self.ptrs[r] = p
+                        self._opened.append(p)
+                    if want_mc and self.rank != 0:
+                        fd = _fetch_fd(paths[0], 1)
+                        try:
+                            self._mc_handle = ext.vmm_import_fd(fd, dev)
+                        finally:
+                            ext.close_fd(fd)
+                except Exception as exc:
+                    err, ok = exc, False
+            if not self._agree(ok):     # (also: nobody tears its server down while peers still fetch)
+                self._vmm_teardown(fds)
+                fds = []
+                warnings.warn(f"VMM handle exchange failed on some rank ({err!r} here); using the CUDA-IPC heap")
+                self._fallback_ipc(nbytes, multicast)
+                return
+            # ---- stage C: bind everybody's allocation to the multicast object, map its alias
             if want_mc:
-                if self.rank != 0:
-                    fd = _fetch_fd(paths[0], 1)
-                    self._mc_handle = ext.vmm_import_fd(fd, dev)
-                    ext.close_fd(fd)
-                ext.mc_add_device(self._mc_handle, dev)
-                dist.barrier(group=self.group)          # every device is part of the team before anyone binds
-                ext.mc_bind(self._mc_handle, self._handle, self.nbytes)
-                dist.barrier(group=self.group)
-                self.mc_base = ext.vmm_map(self._mc_handle, self.nbytes, gran, dev)
-            dist.barrier(group=self.group)              # nobody tears its server down while peers still fetch
+                steps = (lambda: ext.mc_add_device(self._mc_handle, dev),      # every device joins the team ...
+                         lambda: self._mc_bind(),                              # ... before anyone binds
+                         lambda: setattr(self, "mc_base", ext.vmm_map(self._mc_handle, self.nbytes, self._gran, dev)))
+                for step in steps:
+                    good = True
+                    try:
+                        step()
+                    except Exception as exc:
+                        err, good = exc, False
+                    if not self._agree(good):
+                        if multicast:
+                            self._vmm_teardown(fds)
+                            fds = []
+                            raise RuntimeError(f"multicast=True but the NVLS set-up failed: {err!r}")
+                        warnings.warn(f"NVLS multicast unavailable ({err!r} here); deliveries use peer stores")
+                        self._drop_multicast()
+                        break
         finally:
-            server.close()
+            if server is not None:
+                server.close()
             for fd in fds:
+                try:
+                    ext.close_fd(fd)
+                except Exception:
+                    pass
+
+    def _mc_bind(self) -> None:
+        self._ext.mc_bind(self._mc_handle, self._handle, self.nbytes)
+        self._mc_bound = True
+
+    def _drop_multicast(self) -> None:
+        ext = self._ext
+        try:
+            if self.mc_base:
+                ext.vmm_unmap(self.mc_base, self.nbytes)
+            if self._mc_handle:
+                if self._mc_bound:
+                    ext.mc_unbind(self._mc_handle, self._dev_index, self.nbytes)
+                ext.vmm_release(self._mc_handle)
+        except Exception:
+            pass
+        self.mc_base = 0
+        self._mc_handle = 0
+        self._mc_bound = False
+
+    def _vmm_teardown(self, fds: List[int]) -> None:
+        """Undo a partially built VMM heap (best effort) before falling back."""
+        ext = self._ext
+        self._drop_multicast()
+        for p in self._opened:
+            try:
+                ext.vmm_unmap(p, self.nbytes)
+            except Exception:
+                pass
+        for h in self._peer_handles:
+            try:
+                ext.vmm_release(h)
+            except Exception:
+                pass
+        self._opened, self._peer_handles = [], []
+        try:
+            if self._ptr:
+                ext.vmm_unmap(self._ptr, self.nbytes)
+            if self._handle:
+                ext.vmm_release(self._handle)
+        except Exception:
+            pass
+        self._ptr = self._handle = 0
+        for fd in fds:
+            try:
                 ext.close_fd(fd)
+            except Exception:
+                pass
+        self.ptrs = [0] * self.world
+
+    def _fallback_ipc(self, nbytes: int, multicast: Optional[bool]) -> None:
+        if multicast:
+            raise RuntimeError("NVLS multicast needs the VMM symmetric heap")
+        self.kind = "ipc"
+        self._init_ipc(nbytes)
 
     # ----------------------------------------------------------------- views
     def view(self, dtype: torch.dtype, numel: Optional[int] = None, offset_bytes: int = 0) -> torch.Tensor:
@@ -246,9 +380,10 @@ class SymmetricBuffer:
         if self._closed:
             return
         self._closed = True
-        torch.cuda.synchronize(self.device)
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
         ext = self._ext
-        with torch.cuda.device(self.device):
+        with _device_ctx(self.device):
             if self.world > 1 and _dist_on():
                 try:
                     dist.barrier(group=self.group)      # peers have stopped touching my memory
@@ -256,11 +391,7 @@ class SymmetricBuffer:
                     pass
             if self.kind == "vmm":
                 try:
-                    if self.mc_base:
-                        ext.vmm_unmap(self.mc_base, self.nbytes)
-                    if self._mc_handle:
-                        ext.mc_unbind(self._mc_handle, self._dev_index, self.nbytes)
-                        ext.vmm_release(self._mc_handle)
+                    self._drop_multicast()
                     for p in self._opened:
                         ext.vmm_unmap(p, self.nbytes)
                     for h in self._peer_handles:
@@ -284,6 +415,12 @@ class SymmetricBuffer:
                 ext.raw_free(self._ptr)
             except Exception:
                 pass
+
+
+def _device_ctx(device: torch.device):
+    import contextlib
+
+    return torch.cuda.device(device) if device.type == "cuda" else contextlib.nullcontext()
 
 
 def _dist_on() -> bool:
