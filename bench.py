@@ -327,8 +327,40 @@ def print_timeline(rnd, rank, world):
 
 
 # ------------------------------------------------------------------- reference: PS (2, 3)
+def _install_reference(ref_root):
+    """baseline/_ref is git-ignored, so a re-created checkout has lost it: re-do the one offline install the
+    task allows when the reference source is present.  One rank installs (file lock), the
+    others wait on the lock and find it done."""
+    import fcntl
+    import shutil
+    import subprocess
+    import tempfile
+
+    src = "/root/reference/python"
+    if not os.path.isdir(src):
+        return
+    os.makedirs(os.path.dirname(ref_root), exist_ok=True)
+    with open(os.path.join(os.path.dirname(ref_root), ".install.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if os.path.isdir(os.path.join(ref_root, "byzpy")):
+            return
+        tmp = tempfile.mkdtemp(prefix="refsrc_")
+        try:
+            shutil.copytree(src, os.path.join(tmp, "src"))          # the reference tree is read-only
+            subprocess.run([sys.executable, "-m", "pip", "install", "--no-index", "--no-build-isolation", "--no-deps",
+                            "--find-links", "/opt/wheelhouse", "--target", ref_root, os.path.join(tmp, "src")],
+                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600, check=False)
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+
+
 def _ref_imports():
     ref_root = os.path.join(REPO, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_root, "byzpy")):
+        try:
+            _install_reference(ref_root)
+        except Exception:
+            pass
     if not os.path.isdir(os.path.join(ref_root, "byzpy")):
         return "baseline/_ref/byzpy not installed"
     if ref_root not in sys.path:
