@@ -10,8 +10,11 @@ dropped before unpickling.  Protocol (server <-> worker):
     server -> {"type": "update", "round": r, "vector": agg}     (workers apply it with their own optimizer)
     server -> {"type": "done"}
 
-A round is skipped when fewer than the aggregator's minimum of gradients arrive within
-``round_timeout`` seconds (counterpart of the reference's examples/ps/remote_tcp/ps_node.py).
+A round closes when every connected worker has answered or after ``round_timeout`` seconds, and is skipped
+when fewer gradients than the aggregator needs arrived; a worker whose connection drops is removed and the
+training continues with the rest (counterpart of the reference's examples/ps/remote_tcp/ps_node.py).
+Config keys: ``server``, ``workers`` (``id``, ``role``, optional ``leave_after``), ``rounds``, ``round_timeout``,
+``lr``, ``eval_every``, ``aggregator``.
 
     python examples/ps/remote_tcp/ps_node.py server &
     for w in w0 w1 w2 w3; do python examples/ps/remote_tcp/ps_node.py worker --id $w & done; wait
@@ -77,62 +80,129 @@ def build_aggregator(spec):
 
 
 # ------------------------------------------------------------------------------ server
-async def run_server(cfg):
-    agg = build_aggregator(cfg.get("aggregator", {}))
-    expected = {str(w["id"]) for w in cfg["workers"]}
-    torch.manual_seed(0)
-    model = SmallCNN()
-    conns = {}
-    all_in = asyncio.Event()
+class ParameterServerNode:
+    """The server role: accepts workers, drives rounds, aggregates, broadcasts the update.
 
-    async def on_conn(reader, writer):
+    One receive task per worker connection feeds a per-round table, so a slow or dead worker never blocks
+    the others: a round closes when every CONNECTED worker has answered or ``round_timeout`` expires; a
+    worker whose connection drops is removed from the table (the round proceeds with the rest); a round
+    with too few gradients for the aggregator is skipped (the reference skips on a 60 s timeout,
+    reference examples/ps/remote_tcp/ps_node.py:389-394)."""
+
+    def __init__(self, cfg):
+        self.cfg = cfg
+        self.agg = build_aggregator(cfg.get("aggregator", {}))
+        self.expected = {str(w["id"]) for w in cfg["workers"]}
+        self.lr = float(cfg.get("lr", 0.05))
+        self.rounds = int(cfg.get("rounds", 5))
+        self.timeout = float(cfg.get("round_timeout", 60))
+        self.eval_every = int(cfg.get("eval_every", 1))
+        torch.manual_seed(0)
+        self.model = SmallCNN()
+        self.opt = torch.optim.SGD(self.model.parameters(), lr=self.lr)
+        self.writers = {}                  # worker id -> StreamWriter
+        self.tasks = {}                    # worker id -> receive task
+        self.round = 0
+        self.inbox = {}                    # worker id -> gradient of the current round
+        self.changed = asyncio.Event()     # a gradient arrived or a worker left
+        self.all_in = asyncio.Event()
+        self.rejected = 0
+        self._srv = None
+
+    async def start(self):
+        host, port = self.cfg["server"]["host"], int(self.cfg["server"]["port"])
+        self._srv = await asyncio.start_server(self._on_conn, host, port)
+        print(f"parameter server on {host}:{port}, waiting for {len(self.expected)} workers", flush=True)
+
+    async def _on_conn(self, reader, writer):
         try:
             hello = await recv_frame(reader)
-        except Exception as exc:  # noqa: BLE001
+            wid = str(hello["id"])
+            if hello.get("type") != "hello" or wid not in self.expected:
+                raise PermissionError(f"unexpected worker {wid!r}")
+        except Exception as exc:  # noqa: BLE001   (bad MAC, unknown id, garbage)
+            self.rejected += 1
             print("rejected connection:", exc, flush=True)
             writer.close()
             return
-        wid = str(hello["id"])
-        conns[wid] = (reader, writer)
-        await send_frame(writer, {"type": "init_model",
-                                  "state_dict": {k: v.cpu() for k, v in model.state_dict().items()}})
-        if expected <= set(conns):
-            all_in.set()
+        self.writers[wid] = writer
+        await send_frame(writer, {"type": "init_model", "round": self.round,
+                                  "state_dict": {k: v.cpu() for k, v in self.model.state_dict().items()}})
+        self.tasks[wid] = asyncio.ensure_future(self._receive(wid, reader))
+        if self.expected <= set(self.writers):
+            self.all_in.set()
 
-    srv = await asyncio.start_server(on_conn, cfg["server"]["host"], int(cfg["server"]["port"]))
-    print(f"parameter server on {cfg['server']['host']}:{cfg['server']['port']}, waiting for {len(expected)} workers",
-          flush=True)
-    await all_in.wait()
-    opt = torch.optim.SGD(model.parameters(), lr=0.05)
-    xt, yt = mnist_like(2000, train=False)
-    timeout = float(cfg.get("round_timeout", 60))
-    for r in range(1, int(cfg.get("rounds", 5)) + 1):
-        for _, w in conns.values():
-            await send_frame(w, {"type": "round", "round": r})
-
-        async def one(wid):
-            msg = await recv_frame(conns[wid][0])
-            return msg["vector"] if msg.get("round") == r else None
-
-        done, pending = await asyncio.wait([asyncio.ensure_future(one(w)) for w in conns], timeout=timeout)
-        for p in pending:
-            p.cancel()
-        grads = [d.result() for d in done if not d.exception() and d.result() is not None]
+    async def _receive(self, wid, reader):
         try:
-            vec = agg.aggregate(grads)
-        except ValueError as exc:       # not enough gradients for this aggregator
-            print(f"[round {r}] skipped ({len(grads)} gradients: {exc})", flush=True)
-            continue
-        write_vector_to_grads_(model, vec)
-        opt.step()
-        for _, w in conns.values():
-            await send_frame(w, {"type": "update", "round": r, "vector": vec})
-        loss, acc = evaluate(model, xt, yt, torch.device("cpu"))
-        print(f"[round {r}] {len(grads)} gradients  test loss={loss:.4f} acc={acc:.4f}", flush=True)
-    for _, w in conns.values():
-        await send_frame(w, {"type": "done"})
-        w.close()
-    srv.close()
+            while True:
+                msg = await recv_frame(reader)
+                if msg.get("type") == "gradient" and msg.get("round") == self.round:
+                    self.inbox[wid] = msg["vector"]
+                    self.changed.set()
+        except (asyncio.IncompleteReadError, ConnectionError, PermissionError, OSError) as exc:
+            print(f"worker {wid} left ({type(exc).__name__})", flush=True)
+        finally:
+            self.writers.pop(wid, None)
+            self.changed.set()
+
+    async def _broadcast(self, msg):
+        for wid, w in list(self.writers.items()):
+            try:
+                await send_frame(w, msg)
+            except (ConnectionError, OSError):
+                self.writers.pop(wid, None)
+
+    async def _collect(self):
+        loop = asyncio.get_running_loop()
+        deadline = loop.time() + self.timeout
+        while loop.time() < deadline and self.writers and not set(self.writers) <= set(self.inbox):
+            self.changed.clear()
+            try:
+                await asyncio.wait_for(self.changed.wait(), timeout=max(0.01, deadline - loop.time()))
+            except asyncio.TimeoutError:
+                break
+        return [self.inbox[w] for w in sorted(self.inbox)]          # deterministic row order
+
+    async def run_training(self):
+        await self.all_in.wait()
+        xt, yt = mnist_like(2000, train=False)
+        for r in range(1, self.rounds + 1):
+            self.round, self.inbox = r, {}
+            await self._broadcast({"type": "round", "round": r})
+            grads = await self._collect()
+            try:
+                vec = self.agg.aggregate(grads)
+            except ValueError as exc:       # not enough gradients for this aggregator
+                print(f"[round {r}] skipped ({len(grads)} gradients: {exc})", flush=True)
+                continue
+            write_vector_to_grads_(self.model, vec)
+            self.opt.step()
+            await self._broadcast({"type": "update", "round": r, "vector": vec})
+            if r % self.eval_every == 0 or r == self.rounds:
+                loss, acc = evaluate(self.model, xt, yt, torch.device("cpu"))
+                print(f"[round {r}] {len(grads)} gradients  test loss={loss:.4f} acc={acc:.4f}", flush=True)
+        await self._broadcast({"type": "done"})
+
+    async def shutdown(self):
+        for w in list(self.writers.values()):
+            w.close()
+        for t in self.tasks.values():
+            t.cancel()
+        if self._srv is not None:
+            self._srv.close()
+            try:        # (3.12 waits here for every accepted connection to be gone; do not hang on a stuck peer)
+                await asyncio.wait_for(self._srv.wait_closed(), timeout=2.0)
+            except asyncio.TimeoutError:
+                pass
+
+
+async def run_server(cfg):
+    node = ParameterServerNode(cfg)
+    await node.start()
+    try:
+        await node.run_training()
+    finally:
+        await node.shutdown()
 
 
 # ------------------------------------------------------------------------------ workers
@@ -151,9 +221,10 @@ async def run_worker(cfg, wid):
     init = await recv_frame(reader)
     model = SmallCNN()
     model.load_state_dict(init["state_dict"], strict=True)
-    opt = torch.optim.SGD(model.parameters(), lr=0.05)
+    opt = torch.optim.SGD(model.parameters(), lr=float(cfg.get("lr", 0.05)))
     lossf = torch.nn.CrossEntropyLoss()
     byz = entry.get("role", "honest") != "honest"
+    leave_after = entry.get("leave_after")          # drop the connection after this many rounds (failure rehearsal)
     if byz:
         me = 0
         attack = EmpireAttack(scale=-1.0)
@@ -167,6 +238,9 @@ async def run_worker(cfg, wid):
         if msg["type"] == "done":
             break
         if msg["type"] == "round":
+            if leave_after is not None and msg["round"] > int(leave_after):
+                print(f"[{wid}] leaving before round {msg['round']}", flush=True)
+                break
             xb, yb = nxt()
             model.zero_grad(set_to_none=True)
             lossf(model(xb), yb).backward()

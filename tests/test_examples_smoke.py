@@ -53,3 +53,113 @@ def test_example_actor_servers_parse_their_arguments():
         res = subprocess.run([sys.executable, script, "--help"], cwd=ROOT, capture_output=True, text=True, timeout=120,
                              env=dict(os.environ, PYTHONPATH=ROOT))
         assert res.returncode == 0 and "--gpu-direct" in res.stdout, res.stderr[-500:]
+
+
+# ------------------------------------------------------------------ remote-TCP examples (several processes each)
+def _env(**extra):
+    return dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""), CUDA_VISIBLE_DEVICES="",
+                OMP_NUM_THREADS="2", **extra)
+
+
+def _free_ports(k):
+    import socket
+
+    socks = [socket.socket() for _ in range(k)]
+    for s in socks:
+        s.bind(("127.0.0.1", 0))
+    ports = [s.getsockname()[1] for s in socks]
+    for s in socks:
+        s.close()
+    return ports
+
+
+def _finish(procs, timeout):
+    outs = []
+    for p in procs:
+        try:
+            out, _ = p.communicate(timeout=timeout)
+        except subprocess.TimeoutExpired:
+            p.kill()
+            out, _ = p.communicate()
+            out += "\n<<killed after timeout>>"
+        outs.append(out)
+    return outs
+
+
+def test_remote_tcp_parameter_server_survives_a_leaving_worker_and_rejects_a_bad_mac(tmp_path):
+    """examples/ps/remote_tcp/ps_node.py: 1 server + 4 workers (one Byzantine); worker w2 drops its connection
+    after round 2 and the training finishes with the remaining three; a client signing with the wrong secret
+    never gets in."""
+    import yaml
+
+    (port,) = _free_ports(1)
+    cfg = {"server": {"host": "127.0.0.1", "port": port}, "rounds": 4, "round_timeout": 30, "lr": 0.05,
+           "aggregator": {"name": "trimmed_mean", "f": 1},
+           "workers": [{"id": "w0", "role": "honest"}, {"id": "w1", "role": "honest"},
+                       {"id": "w2", "role": "honest", "leave_after": 2}, {"id": "w3", "role": "byzantine"}]}
+    path = tmp_path / "nodes.yaml"
+    path.write_text(yaml.safe_dump(cfg))
+    script = os.path.join("examples", "ps", "remote_tcp", "ps_node.py")
+    env = _env(BYZPY_HMAC_SECRET="rehearsal-secret")
+    popen = lambda args, e=env: subprocess.Popen([sys.executable, script] + args + ["--config", str(path)], cwd=ROOT,  # noqa: E731
+                                                 env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    server = popen(["server"])
+    intruder = popen(["worker", "--id", "w0"], _env(BYZPY_HMAC_SECRET="wrong-secret"))
+    intruder_out = _finish([intruder], 120)[0]
+    workers = [popen(["worker", "--id", w]) for w in ("w0", "w1", "w2", "w3")]
+    outs = _finish(workers + [server], 240)
+    srv_out = outs[-1]
+    assert server.returncode == 0, srv_out[-2000:]
+    assert "rejected connection: bad HMAC" in srv_out, srv_out[-2000:]
+    assert intruder.returncode != 0, intruder_out[-500:]          # the server closed the socket on it
+    assert "[round 2] 4 gradients" in srv_out and "worker w2 left" in srv_out, srv_out[-2000:]
+    assert "[round 4] 3 gradients" in srv_out, srv_out[-2000:]
+    assert "[w2] leaving before round 3" in outs[2] and all("finished" in o for o in outs[:2] + outs[3:4]), outs
+
+
+def _p2p_cfg(tmp_path, rounds=2):
+    import yaml
+
+    ports = _free_ports(5)
+    cfg = {"server": {"host": "127.0.0.1", "port": ports[4]}, "topology": "complete", "rounds": rounds,
+           "nodes": [{"id": str(i), "host": "127.0.0.1", "port": ports[i], "role": "honest" if i < 3 else "byzantine"}
+                     for i in range(4)]}
+    path = tmp_path / "nodes.yaml"
+    path.write_text(yaml.safe_dump(cfg))
+    return str(path)
+
+
+def test_remote_tcp_mesh_example_four_processes(tmp_path):
+    """examples/p2p/remote_tcp/mesh_client.py: every node is a TCP server plus clients to all peers."""
+    cfg = _p2p_cfg(tmp_path)
+    procs = [subprocess.Popen([sys.executable, "examples/p2p/remote_tcp/mesh_client.py", "--config", cfg, "--node-id", str(i)],
+                              cwd=ROOT, env=_env(), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for i in range(4)]
+    outs = _finish(procs, 240)
+    assert all(p.returncode == 0 for p in procs), [o[-800:] for o in outs]
+    finals = [ln for o in outs[:3] for ln in o.splitlines() if "round 2:" in ln]
+    assert len(finals) == 3 and all("3 neighbour vectors" in ln for ln in finals), outs
+    assert len({ln.split("|theta| = ")[1] for ln in finals}) == 1        # the honest nodes agree after aggregation
+    assert "round 2: attacked with 3 honest vectors" in outs[3], outs[3][-800:]
+
+
+def test_remote_tcp_hub_example_server_and_four_clients(tmp_path):
+    """examples/p2p/remote_tcp/server.py + client.py: hub-and-spoke relay through a RemoteNodeServer."""
+    cfg = _p2p_cfg(tmp_path)
+    hub = subprocess.Popen([sys.executable, "examples/p2p/remote_tcp/server.py", "--config", cfg], cwd=ROOT, env=_env(),
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    try:
+        import time
+
+        time.sleep(2.0)
+        procs = [subprocess.Popen([sys.executable, "examples/p2p/remote_tcp/client.py", "--config", cfg, "--node-id", str(i)],
+                                  cwd=ROOT, env=_env(), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+                 for i in range(4)]
+        outs = _finish(procs, 240)
+    finally:
+        hub.terminate()
+        hub_out = _finish([hub], 30)[0]
+    assert all(p.returncode == 0 for p in procs), [o[-800:] for o in outs] + [hub_out[-800:]]
+    finals = [ln for o in outs[:3] for ln in o.splitlines() if "round 2:" in ln]
+    assert len(finals) == 3 and all("3 neighbour vectors" in ln for ln in finals), outs
+    assert "hub listening" in hub_out
