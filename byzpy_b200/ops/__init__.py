@@ -94,6 +94,11 @@ def as_rows(x: Rows) -> List[torch.Tensor]:
             return [x]
         flat = x.reshape(x.shape[0], -1)
         return [flat[i] for i in range(flat.shape[0])]
+    if type(x) is list and x and type(x[0]) is torch.Tensor:
+        # already a list of flat tensors of one length (what the operator bases pass): one cheap scan
+        d0 = x[0].numel()
+        if all(type(r) is torch.Tensor and r.dim() == 1 and r.numel() == d0 for r in x):
+            return x
     rows = []
     for r in x:
         if not isinstance(r, torch.Tensor):

@@ -342,6 +342,9 @@ def _k_smallest_mask(D: np.ndarray, k: int) -> np.ndarray:
     if k >= n:
         return np.ones_like(D)
     thr = np.partition(D, k - 1, axis=1)[:, k - 1: k]          # the k-th smallest value of each row
+    upto = D <= thr
+    if np.all(np.count_nonzero(upto, axis=1) == k):             # no tie at the threshold (the usual case)
+        return upto.astype(np.float64)
     below = D < thr
     at = D == thr
     room = k - below.sum(axis=1, keepdims=True)                 # how many entries equal to it still fit
