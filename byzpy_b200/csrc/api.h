@@ -20,7 +20,8 @@ struct BzCwArgs {
   long long len;      // number of coordinates
   float* out;         // aggregated vector (may be nullptr when only updating)
   UpdTable upd;       // optional fused optimizer step
-  int impl;           // 0 = auto, 1 = direct register loads, 2 = cp.async-staged pipeline
+  int impl;           // 0 = auto, 1 = direct register loads, 2 = cp.async-staged pipeline,
+                      // 3 = warp-tiled pipeline (many rows; falls back to auto where it does not apply)
 };
 
 // Coordinate-wise family (median / trimmed mean / mean-of-medians / mean).

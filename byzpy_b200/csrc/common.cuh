@@ -112,16 +112,24 @@ __device__ __forceinline__ void stg_stream1(float* p, float v) {
   asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
+// The register-resident selection code below is plain arithmetic, so it is compiled for the host as
+// well: tests/test_cw_network_host.py builds it with nvcc and checks every network size, padding and
+// mode against a sort on the CPU (the box that builds the extension has no GPU).
+#define BZ_HD __host__ __device__ __forceinline__
+
 // NaN is canonicalised to +inf on load: a NaN coordinate is treated as an
 // extreme outlier (sorts last, like torch.sort) instead of poisoning min/max.
-__device__ __forceinline__ float canon(float x) { return (x != x) ? __int_as_float(0x7f800000) : x; }
+BZ_HD float canon(float x) { return (x != x) ? __builtin_huge_valf() : x; }
+// The same map in ONE alu instruction: IEEE minNum returns the numeric operand, so min(NaN, +inf) = +inf
+// and min(x, +inf) = x for every other x (FMNMX instead of FSETP + FSEL).
+BZ_HD float canon_min(float x) { return fminf(x, __builtin_huge_valf()); }
 
 // Fully unrolled bitonic sorting network over a register array (ascending).
 // All indices are compile-time after unrolling, so v[] stays in registers, and
 // the compiler dead-code-eliminates compare-exchanges whose outputs are unused
 // (e.g. when only the median slot is read).
 template <int NP>
-__device__ __forceinline__ void bitonic_sort(float (&v)[NP]) {
+BZ_HD void bitonic_sort(float (&v)[NP]) {
   // Batcher's odd-even merge sort (19 / 63 / 191 / 543 / 1471 compare-exchanges for
   // NP = 8 / 16 / 32 / 64 / 128, ~20 % fewer than the bitonic network the name recalls).
   // Every comparator sorts ascending, so each is exactly one FMNMX pair on the alu pipe.

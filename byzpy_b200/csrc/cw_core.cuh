@@ -8,11 +8,12 @@ namespace bzcw {
 
 
 constexpr int kThreads = 256;
-__device__ constexpr float kInf = __builtin_huge_valf();
+constexpr float kInf = __builtin_huge_valf();
 
-template <int NP, int MODE>
-__device__ __forceinline__ float cw_pick(float (&v)[NP], const int nt, const int f,
-                                         const int apad) {
+// PREPAD: slots nt..NP-1 already hold the -inf / +inf padding (the warp-tiled kernel keeps the pad rows
+// resident in its shared-memory tile), so the per-slot selects are skipped.
+template <int NP, int MODE, bool PREPAD = false>
+BZ_HD float cw_pick(float (&v)[NP], const int nt, const int f, const int apad) {
   if constexpr (MODE == BZ_CW_MEAN) {
     float s = 0.f;
 #pragma unroll
@@ -21,9 +22,11 @@ __device__ __forceinline__ float cw_pick(float (&v)[NP], const int nt, const int
   } else {
     // Pad: `apad` slots of -inf then +inf so that the lower median of the nt
     // real values always lands in the compile-time slot NP/2-1.
+    if constexpr (!PREPAD) {
 #pragma unroll
-    for (int i = 0; i < NP; ++i) {
-      if (i >= nt) v[i] = (i - nt < apad) ? -kInf : kInf;
+      for (int i = 0; i < NP; ++i) {
+        if (i >= nt) v[i] = (i - nt < apad) ? -kInf : kInf;
+      }
     }
     bitonic_sort<NP>(v);
     if constexpr (MODE == BZ_CW_MEDIAN) {
@@ -152,9 +155,8 @@ __device__ __forceinline__ void sgd_apply(const UpdTable& upd, long long idx, co
 
 
 // Values of V coordinates are in v[c][0..n); synthesise virtual rows, run the selection network.
-template <int NP, int V, int MODE>
-__device__ __forceinline__ void cw_finish(float (&v)[V][NP], int n, const VirtRows& virt, int f,
-                                          float (&res)[V]) {
+template <int NP, int V, int MODE, bool PREPAD = false>
+BZ_HD void cw_finish(float (&v)[V][NP], int n, const VirtRows& virt, int f, float (&res)[V]) {
   const int nv = virt.count;
   const int nt = n + nv;
   const int apad = NP / 2 - 1 - (nt - 1) / 2;
@@ -179,7 +181,7 @@ __device__ __forceinline__ void cw_finish(float (&v)[V][NP], int n, const VirtRo
         if (i >= n && i < nt) v[c][i] = canon(val);
       }
     }
-    res[c] = cw_pick<NP, MODE>(v[c], nt, f, apad);
+    res[c] = cw_pick<NP, MODE, PREPAD>(v[c], nt, f, apad);
   }
 }
 

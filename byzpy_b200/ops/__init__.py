@@ -14,6 +14,7 @@ Dispatch rule (no silent fallbacks on a GPU box):
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence, Tuple, Union
 
 import torch
@@ -149,8 +150,11 @@ def cw_select(
 ) -> torch.Tensor:
     """Coordinate-wise select over n rows.
 
-    ``impl``: ``"auto"`` | ``"direct"`` (register loads) | ``"staged"`` (cp.async pipeline); the
-    two CUDA variants are bit-identical, the knob exists for benchmarking.
+    ``impl``: ``"auto"`` | ``"direct"`` (register loads) | ``"staged"`` (thread-private cp.async pipeline) |
+    ``"tiled"`` (warp-tiled cp.async pipeline for 17..128 rows; shorter inputs and other shapes fall back to
+    ``"auto"``).  The CUDA variants are bit-identical, the knob exists for benchmarking; ``"auto"`` can be
+    redirected with ``BYZPY_CW_IMPL=tiled`` (the tiled kernel was written after the round's GPU time was spent:
+    it is opt-in until a B200 run has timed it, see profiles/cw_select.md section 4).
 
     ``virtual=(count, n_honest, a, b)`` appends ``count`` synthesised rows equal
     to ``a*mean + b*std`` of the first ``n_honest`` rows (Little / Empire).
@@ -177,7 +181,7 @@ def cw_select(
             [r.data_ptr() for r in rows], _scales(scales, n), mode, int(f), int(nv), int(nh),
             float(va), float(vb), 0, d, out.data_ptr(),
             [p.data_ptr() for p in params], [m.data_ptr() for m in moms],
-            lr, mu, wd, sm_count(dev), _stream(dev), {"auto": 0, "direct": 1, "staged": 2}[impl],
+            lr, mu, wd, sm_count(dev), _stream(dev), _CW_IMPL[_cw_impl(impl)],
         )
         return out
     res = _host_cw_select(rows, mode, f, scales, virtual, out)
@@ -189,6 +193,18 @@ def cw_select(
     if update is not None:
         ref.sgd_step(res, **update)
     return res
+
+
+_CW_IMPL = {"auto": 0, "direct": 1, "staged": 2, "tiled": 3}
+
+
+def _cw_impl(impl: str) -> str:
+    if impl not in _CW_IMPL:
+        raise ValueError(f"impl must be one of {sorted(_CW_IMPL)} (got {impl!r})")
+    if impl == "auto":
+        env = os.environ.get("BYZPY_CW_IMPL", "auto").lower()
+        return env if env in _CW_IMPL else "auto"
+    return impl
 
 
 HOST_MAX_ROWS = 1024

@@ -1,0 +1,76 @@
+"""GPU tests of kernels written AFTER the round's GPU budget was spent (they have been compiled, statically
+analysed and -- where the code is host-compilable -- checked on the CPU, but no B200 has run them yet).  The file
+name sorts last on purpose: under ``pytest -x`` a surprise here cannot hide the results of the measured kernels."""
+import pytest
+import torch
+
+from byzpy_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda", 0) if torch.cuda.is_available() else None
+
+
+def _rows(n, d, seed):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.randn(d, generator=g).to(DEV) for _ in range(n)]
+
+
+@pytest.mark.parametrize("n", [17, 32, 33, 48, 64, 65, 100, 128])
+@pytest.mark.parametrize("mode,f", [(ops.MODE_MEDIAN, 0), (ops.MODE_TRMEAN, 5), (ops.MODE_MEAMED, 6)])
+def test_warp_tiled_selection_kernel_is_bit_identical_to_the_direct_kernel(n, mode, f):
+    d = 148 * 256 * 4 + 37            # several tiles per warp, plus a tail that is not a whole tile
+    rows = _rows(n, d, seed=n)
+    want = ops.cw_select(rows, mode, f, impl="direct")
+    got = ops.cw_select(rows, mode, f, impl="tiled")
+    assert torch.equal(got, want)
+    X = torch.stack(rows).cpu()
+    if mode == ops.MODE_MEDIAN:
+        assert torch.equal(got.cpu(), X.median(dim=0).values)
+
+
+def test_warp_tiled_kernel_scales_nan_inf_virtual_rows_and_fused_update():
+    n, d = 40, 64 * 1024 + 5
+    rows = _rows(n, d, seed=7)
+    rows[3][::7] = float("nan")
+    rows[5][::11] = float("inf")
+    rows[6][::13] = float("-inf")
+    scales = [1.0] * n
+    scales[1], scales[2] = -1.0, 0.5
+    for mode, f in [(ops.MODE_MEDIAN, 0), (ops.MODE_TRMEAN, 3)]:
+        a = ops.cw_select(rows, mode, f, scales=scales, impl="direct")
+        b = ops.cw_select(rows, mode, f, scales=scales, impl="tiled")
+        assert torch.equal(torch.nan_to_num(a, nan=123.0), torch.nan_to_num(b, nan=123.0))
+    clean = _rows(n, d, seed=8)
+    virt = (3, n - 2, 1.0, -0.7)       # three Little-style rows from the first n - 2
+    a = ops.cw_select(clean, ops.MODE_MEDIAN, 0, virtual=virt, impl="direct")
+    b = ops.cw_select(clean, ops.MODE_MEDIAN, 0, virtual=virt, impl="tiled")
+    assert torch.equal(a, b)
+    # fused SGD epilogue
+    p1, p2 = torch.randn(d, device=DEV), None
+    p2 = p1.clone()
+    m1, m2 = torch.zeros(d, device=DEV), torch.zeros(d, device=DEV)
+    ops.cw_select(clean, ops.MODE_MEDIAN, 0, update=dict(params=[p1], moms=[m1], lr=0.1, momentum=0.9, weight_decay=0.0),
+                  impl="direct")
+    ops.cw_select(clean, ops.MODE_MEDIAN, 0, update=dict(params=[p2], moms=[m2], lr=0.1, momentum=0.9, weight_decay=0.0),
+                  impl="tiled")
+    assert torch.equal(p1, p2) and torch.equal(m1, m2)
+
+
+def test_warp_tiled_kernel_under_graph_capture_and_env_routing(monkeypatch):
+    rows = _rows(64, 1 << 20, seed=3)
+    out = torch.empty(1 << 20, device=DEV)
+    want = ops.cw_select(rows, ops.MODE_MEDIAN, 0, impl="direct")
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        ops.cw_select(rows, ops.MODE_MEDIAN, 0, out=out, impl="tiled")
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        ops.cw_select(rows, ops.MODE_MEDIAN, 0, out=out, impl="tiled")
+    out.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, want)
+    monkeypatch.setenv("BYZPY_CW_IMPL", "tiled")
+    assert torch.equal(ops.cw_select(rows, ops.MODE_MEDIAN, 0), want)
