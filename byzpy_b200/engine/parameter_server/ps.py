@@ -152,12 +152,13 @@ class ParameterServer:
             virtual_fold=virtual_fold, **self._device_opts)
 
     def _fused_plan(self, n_rows: int):
-        """Aggregator plan, composed in n-space with a linear pre-aggregator when present:
-        ``X' = W_p X``  =>  ``G' = W_p G W_p^T`` and final weights ``w_agg @ W_p`` -- the
-        pre-aggregated vectors are never materialised."""
+        """Aggregator plan, composed with a linear pre-aggregator when present.  Gram-family aggregator:
+        in n-space, ``X' = W_p X``  =>  ``G' = W_p G W_p^T`` and final weights ``w_agg @ W_p`` -- the
+        pre-aggregated vectors are never materialised.  Coordinate-wise aggregator: a
+        :class:`MapCwPlan` (the mixed rows exist per coordinate shard only)."""
         if self.pre is None:
             return self.agg.fused_plan(n_rows)
-        from ...parallel.device_ps import GramPlan
+        from ...parallel.device_ps import CwPlan, GramPlan, MapCwPlan
         from ...pre_aggregators.base import LinearPreAggregator
 
         if not isinstance(self.pre, LinearPreAggregator):
@@ -180,8 +181,6 @@ class ParameterServer:
         probe = pre.row_map(np.eye(n_rows) if pre.needs_gram else None, n_rows)
         m = probe.shape[0]
         inner = self.agg.fused_plan(m)
-        if not isinstance(inner, GramPlan) or inner.aux:
-            return None
         state = {"W": None}
 
         def refresh():
@@ -193,6 +192,26 @@ class ParameterServer:
                     state["W"].copy_(torch.from_numpy(Wn), non_blocking=True)
 
         device_map = type(pre).row_map_device is not LinearPreAggregator.row_map_device
+
+        if isinstance(inner, CwPlan):
+            # map -> coordinate-wise selection is not linear in n-space: the m mixed rows are produced on
+            # every rank's coordinate shard and the fused selection kernel runs over them (MapCwPlan)
+            def weights(G: Optional[torch.Tensor]) -> torch.Tensor:
+                if pre.needs_gram:
+                    Wp = pre.row_map_device(G.double(), n_rows) if (device_map and G.is_cuda) else None
+                    if Wp is None:
+                        Wp = torch.from_numpy(np.asarray(pre.row_map(G.detach().double().cpu().numpy(), n_rows),
+                                                         dtype=np.float64)).to(G.device)
+                    return Wp
+                if state["W"] is None:
+                    refresh()
+                return state["W"]
+
+            return MapCwPlan(inner, m, weights, needs_gram=bool(pre.needs_gram), name=f"{pre.name}+{self.agg.name}",
+                             capturable=device_map or not pre.needs_gram,
+                             refresh=None if pre.needs_gram else refresh)
+        if not isinstance(inner, GramPlan) or inner.aux:
+            return None
 
         def solver(G: torch.Tensor) -> torch.Tensor:
             if pre.needs_gram:

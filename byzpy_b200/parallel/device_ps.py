@@ -67,6 +67,29 @@ class GramPlan:
 
 
 @dataclass
+class MapCwPlan:
+    """A linear pre-aggregator followed by a coordinate-wise aggregator (Bucketing -> median, NNM ->
+    trimmed mean, ...).  The composition is not linear in n-space (the selection runs per coordinate
+    on the MIXED rows), so unlike :class:`GramPlan` the ``m`` pre-aggregated rows do exist -- but only
+    as each rank's coordinate shard, in local HBM: ``Y[:, shard] = W_p X[:, shard]`` is produced by
+    the weighted-sum kernels straight from the (peer) gradient rows, then the fused gather / select /
+    deliver / SGD kernel runs over those ``m`` local rows.
+
+    ``weights(G)`` returns the ``(m, n)`` map ON THE DEVICE; ``G`` is the fp64 Gram of the real rows
+    when ``needs_gram`` (Clipping / ARC / NNM: computed like in the Gram round, partials all-reduced
+    through the switch) and ``None`` otherwise (Bucketing: a constant matrix, ``refresh`` redraws it
+    on the host before the round)."""
+
+    cw: CwPlan
+    m: int
+    weights: Callable[[Optional[torch.Tensor]], torch.Tensor]
+    needs_gram: bool = False
+    name: str = "map+cw"
+    capturable: bool = True
+    refresh: Optional[Callable[[], None]] = None
+
+
+@dataclass
 class RowFold:
     """How a Byzantine row is produced without materialising it."""
 
@@ -357,7 +380,8 @@ class DeviceRound:
         self._off_ctl = self._off_pad + 256
         self._off_gslots = self._off_ctl + 256
         self.nt_max = 144                       # rows + auxiliary rows of a Gram plan
-        gram_bytes = max(2, self.world) * self.nt_max * self.nt_max * 8 if isinstance(plan, GramPlan) else 0
+        gram_bytes = (max(2, self.world) * self.nt_max * self.nt_max * 8
+                      if isinstance(plan, (GramPlan, MapCwPlan)) else 0)
         nbytes = self._off_gslots + gram_bytes
         self.sym = SymmetricBuffer(nbytes, self.device, group, multicast=multicast)
         self.grads = self.sym.view(torch.float32, L_sym * self.d_pad, self._off_grads).view(L_sym, self.d_pad)
@@ -441,6 +465,10 @@ class DeviceRound:
             self._plan_buckets(buckets, bucket_cuts, min_bucket)
         if isinstance(plan, GramPlan):
             self._setup_gram_plan()
+            if not plan.capturable:
+                self.use_cuda_graph = False
+        if isinstance(plan, MapCwPlan):
+            self._setup_mapcw_plan()
             if not plan.capturable:
                 self.use_cuda_graph = False
         if self.world > 1:
@@ -633,6 +661,8 @@ class DeviceRound:
             self.launches_per_step = self._round_launches
         elif isinstance(plan, GramPlan):
             self._launch_gram_round(stream, ctl)
+        elif isinstance(plan, MapCwPlan):
+            self._launch_mapcw_round(stream, ctl)
         else:
             raise TypeError(f"unsupported plan {plan!r}")
 
@@ -680,7 +710,9 @@ class DeviceRound:
     def _launch_gram_round(self, stream: int, ctl: int) -> None:
         ext, lay, plan = self.ext, self.layout, self.plan
         pads = [self.sym.peer_ptr(r, self._off_pad) for r in range(self.world)]
-        off, ln = self.shard_off, self.shard_len
+        # this rank's share of the coordinates among the LIVE ranks (equal to the static shard while every
+        # rank takes part; after recover() the survivors cover the dropped rank's range as well)
+        off, ln = self._shard(0, self.d_pad)
         nt = self._nt
         launches = 1
         # every rank's gradient rows must be complete before anybody reads them
@@ -739,6 +771,114 @@ class DeviceRound:
                           ctl + 8, ctl + 0, ctl + 4, self._upd_params, self._upd_moms, self.lr,
                           self.momentum, self.weight_decay, self.sm, stream, 0, 0, 0, 0, 0, self._agg_mc,
                           self.live_mask, self.spin_seconds)
+        self.launches_per_step = launches + 1
+
+    # ------------------------------------------- pre-aggregator -> coordinate-wise round
+    def _setup_mapcw_plan(self) -> None:
+        """Static buffers of the map -> coordinate-wise round."""
+        lay, dev, plan = self.layout, self.device, self.plan
+        n = lay.n_workers + lay.n_virtual
+        m = int(plan.m)
+        if n > ops.MAXN or m > ops.MAXN or n > self.nt_max:
+            raise ValueError("too many rows for the fused map + coordinate-wise round")
+        self._map_n, self._map_m = n, m
+        self._virt_buf = (torch.zeros(self.d_pad, dtype=torch.float32, device=dev) if lay.n_virtual else None)
+        rows, scales = list(self._rows), list(self._scales)
+        if lay.n_virtual:
+            rows += [self._virt_buf.data_ptr()] * lay.n_virtual
+            scales += [1.0] * lay.n_virtual
+        self._map_rows, self._map_scales = rows, scales
+        # the m mixed rows exist only over THIS rank's coordinate shard (recover() re-runs this set-up
+        # with the new live set, so the buffer follows the shard)
+        self._map_cap = padded_size(self._shard(0, self.d_pad)[1], 1024)
+        self._map_Y = torch.zeros((m, self._map_cap), dtype=torch.float32, device=dev)
+        self._map_W = torch.zeros((m, n), dtype=torch.float32, device=dev)
+        if plan.needs_gram:
+            self._g_local64 = torch.zeros((n, n), dtype=torch.float64, device=dev)
+            self._g_local32 = torch.zeros((n, n), dtype=torch.float32, device=dev)
+            self._g_tail64 = torch.zeros((n, n), dtype=torch.float64, device=dev)
+            self._g_tail32 = torch.zeros((n, n), dtype=torch.float32, device=dev)
+            self._g_total64 = torch.zeros((n, n), dtype=torch.float64, device=dev)
+            self._gram_scratch = torch.empty(self.ext.gram_partials_needed(n, self.sm), dtype=torch.float32, device=dev)
+            self._umma_scratch = torch.empty(self.sm * 8 * 2 * n * n, dtype=torch.float32, device=dev)
+
+    def _launch_mapcw_round(self, stream: int, ctl: int) -> None:
+        """flag barrier -> (virtual rows) -> (Gram pass + in-switch all-reduce -> map kernel) ->
+        ``Y = W_p X`` on my shard -> fused select / deliver / SGD over the m local rows."""
+        ext, lay, plan = self.ext, self.layout, self.plan
+        pads = [self.sym.peer_ptr(r, self._off_pad) for r in range(self.world)]
+        off, ln = self._shard(0, self.d_pad)
+        if ln > self._map_cap:
+            raise RuntimeError("coordinate shard exceeds the mixed-row buffer")
+        n, m = self._map_n, self._map_m
+        rows, scales = self._map_rows, self._map_scales
+        launches = 1
+        # every rank's gradient rows must be complete before anybody reads them (its own kernel: the passes
+        # below read the rows with non-coherent loads)
+        ext.flag_barrier(pads, self.rank, ext.PAD_READY, ctl + 8, ctl + 4, stream, 0, 0, self.live_mask,
+                         self.spin_seconds)
+        launches += 1
+        if lay.n_virtual:
+            nh = lay.n_honest
+            ext.colstat(self._rows[:nh], self._scales[:nh], float(self.virtual_fold.a), float(self.virtual_fold.b),
+                        off, ln, self._virt_buf.data_ptr(), self.sm, stream)
+            launches += 1
+        G = None
+        if plan.needs_gram:
+            tc = ext.gram_umma_tile_cols(n)
+            main = (ln // tc) * tc if n > 16 else 0
+            if main > 0:
+                tail_ptr = 0
+                if main < ln:
+                    ext.gram(rows, scales, off + main, ln - main, self._gram_scratch.data_ptr(),
+                             self._gram_scratch.numel() // (n * n), self._g_tail32.data_ptr(),
+                             self._g_tail64.data_ptr(), self.sm, stream)
+                    tail_ptr = self._g_tail64.data_ptr()
+                    launches += 2
+                from ..ops import umma
+
+                self.gram_path = umma.launch(ext, rows, scales, off, main, self.d_pad, self._umma_scratch, n, tail_ptr,
+                                             self._g_local32.data_ptr(), self._g_local64.data_ptr(), self.sm, stream)
+            else:
+                ext.gram(rows, scales, off, ln, self._gram_scratch.data_ptr(), self._gram_scratch.numel() // (n * n),
+                         self._g_local32.data_ptr(), self._g_local64.data_ptr(), self.sm, stream)
+            launches += 2
+            ext.gram_exchange(self._g_local64.data_ptr(),
+                              [self.sym.peer_ptr(r, self._off_gslots) for r in range(self.world)], pads,
+                              self.rank, n, ctl + 8, ctl + 4, self._g_total64.data_ptr(), 0, stream,
+                              self.live_mask, self.spin_seconds,
+                              self.sym.mc_ptr(self._off_gslots) if self._agg_mc else 0)
+            launches += 1
+            G = self._g_total64
+        W = plan.weights(G)
+        self._map_W.copy_(W.reshape(m, n).to(torch.float32), non_blocking=True)
+        launches += 2
+        # Y[:, 0:ln] = W X[:, off:off+ln]: the kernels index outputs with the global coordinate, so the
+        # output pointers are shifted back by the shard offset (a multiple of 4 elements: stays 16-byte aligned)
+        outs = [self._map_Y[r].data_ptr() - 4 * off for r in range(m)]
+        wptr = self._map_W.data_ptr()
+        main = 0
+        if m > 8 and hasattr(ext, "wsum_multi"):
+            tile = ext.WSUM_MULTI_TILE
+            main = (ln // tile) * tile
+            if main:
+                ext.wsum_multi(rows, scales, wptr, m, off, main, outs, self.sm, stream)
+                launches += 1
+        if main < ln:
+            for r0 in range(0, m, 8):
+                mb = min(8, m - r0)
+                ext.wsum(rows, scales, wptr + 4 * r0 * n, mb, off + main, ln - main, outs[r0:r0 + mb],
+                         [], [], 0.0, 0.0, 0.0, self.sm, stream)
+                launches += 1
+        # the fused kernel over the m LOCAL mixed rows: its ready wait is already satisfied (same sequence
+        # number as the barrier above), delivery and SGD are those of the plain coordinate-wise round
+        cw = plan.cw
+        self.ext.fused_ps_cw(
+            outs, [1.0] * m, cw.mode, cw.f, 0, 0, 0.0, 0.0, self.d_pad, off, ln, self.rank,
+            [self.sym.peer_ptr(r, self._off_agg) for r in range(self.world)], pads,
+            0, ctl + 8, ctl + 0, ctl + 4,
+            self._upd_params, self._upd_moms, self.lr, self.momentum, self.weight_decay,
+            self.sm, stream, 0, 0, self.d_pad, 1, 0, self._agg_mc, self.live_mask, self.spin_seconds, 0)
         self.launches_per_step = launches + 1
 
     def _upd_index(self) -> List[int]:
@@ -1054,6 +1194,8 @@ class DeviceRound:
             self.plan = plan
         if isinstance(self.plan, GramPlan):
             self._setup_gram_plan()
+        if isinstance(self.plan, MapCwPlan):
+            self._setup_mapcw_plan()
         self._graphs = [None, None]
         self._prefetched = [False, False]
         # fresh flag numbering: the survivors agree on a new epoch base above anything published so far
@@ -1102,5 +1244,5 @@ class DeviceRound:
         self.sym.close()
 
 
-__all__ = ["CwPlan", "GramPlan", "RowFold", "DeviceWorker", "RowLayout", "DeviceRound", "pick_bucket_offsets",
+__all__ = ["CwPlan", "GramPlan", "MapCwPlan", "RowFold", "DeviceWorker", "RowLayout", "DeviceRound", "pick_bucket_offsets",
            "bucket_bounds"]

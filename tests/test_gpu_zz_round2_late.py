@@ -74,3 +74,73 @@ def test_warp_tiled_kernel_under_graph_capture_and_env_routing(monkeypatch):
     assert torch.equal(out, want)
     monkeypatch.setenv("BYZPY_CW_IMPL", "tiled")
     assert torch.equal(ops.cw_select(rows, ops.MODE_MEDIAN, 0), want)
+
+
+# ------------------------------------------------------------- pre-aggregator -> coordinate-wise fused round
+class _TinyNet(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.a = torch.nn.Linear(20, 33)
+        self.b = torch.nn.Linear(33, 5)
+
+    def forward(self, x):
+        return self.b(torch.relu(self.a(x)))
+
+
+@pytest.mark.parametrize("pre_name", ["bucketing", "nnm", "clipping", "arc"])
+@pytest.mark.parametrize("agg_name", ["median", "trmean"])
+@pytest.mark.parametrize("graph", [False, True])
+def test_pre_aggregator_with_coordinate_wise_aggregator_runs_fused(pre_name, agg_name, graph):
+    """MapCwPlan: Y = W_p X on the coordinate shard, then the fused select / deliver / SGD kernel over the m mixed
+    rows -- compared with the host operators applied to autograd gradients of mirror models."""
+    import asyncio
+
+    from byzpy_b200.aggregators.coordinate_wise import CoordinateWiseMedian, CoordinateWiseTrimmedMean
+    from byzpy_b200.engine.node.device import DeviceHonestNode
+    from byzpy_b200.engine.parameter_server.ps import ParameterServer
+    from byzpy_b200.parallel.device_ps import MapCwPlan
+    from byzpy_b200.pre_aggregators import ARC, Bucketing, Clipping, NearestNeighborMixing
+
+    pres = {"clipping": lambda: Clipping(0.05), "arc": lambda: ARC(2), "nnm": lambda: NearestNeighborMixing(2),
+            "bucketing": lambda: Bucketing(2, perm=[5, 0, 3, 1, 7, 2, 6, 4])}
+    aggs = {"median": lambda: CoordinateWiseMedian(), "trmean": lambda: CoordinateWiseTrimmedMean(f=1)}
+    torch.manual_seed(2)
+    init = _TinyNet().state_dict()
+
+    def mk():
+        net = _TinyNet()
+        net.load_state_dict(init)
+        return net
+
+    hon = [DeviceHonestNode(mk(), lr=0.1, momentum=0.9, device=DEV) for _ in range(8)]
+    ps = ParameterServer(hon, [], aggs[agg_name](), pre_aggregator=pres[pre_name](), fused=True, amp_dtype=None,
+                         use_cuda_graph=graph)
+    rnd = ps.device_round
+    assert isinstance(rnd.plan, MapCwPlan) and rnd.plan.capturable and rnd.use_cuda_graph == graph
+    models = [mk().to(DEV) for _ in range(8)]
+    lossf = torch.nn.CrossEntropyLoss()
+    opts = None
+    for t in range(3):
+        batches = [(torch.randn(16, 20).pin_memory(), torch.randint(0, 5, (16,)).pin_memory()) for _ in range(8)]
+        ps.step(batches)
+        rows = []
+        for mdl, (x, y) in zip(models, batches):
+            mdl.zero_grad()
+            lossf(mdl(x.to(DEV)), y.to(DEV)).backward()
+            rows.append(torch.cat([p.grad.reshape(-1) for p in mdl.parameters()]).cpu())
+        expect = aggs[agg_name]().aggregate(list(pres[pre_name]().pre_aggregate(rows)))
+        rnd.read_losses()
+        torch.testing.assert_close(rnd.aggregated().cpu(), expect, rtol=2e-4, atol=2e-5)
+        for mdl in models:
+            off = 0
+            for p in mdl.parameters():
+                p.grad.copy_(expect[off:off + p.numel()].view_as(p).to(DEV))
+                off += p.numel()
+        if opts is None:
+            opts = [torch.optim.SGD(mdl.parameters(), lr=0.1, momentum=0.9) for mdl in models]
+        for o in opts:
+            o.step()
+    got = hon[0].worker.arena.flat_params[: rnd.d].cpu()
+    want = torch.cat([p.detach().reshape(-1) for p in models[0].parameters()]).cpu()
+    torch.testing.assert_close(got, want, rtol=1e-3, atol=1e-4)
+    asyncio.run(ps.shutdown())

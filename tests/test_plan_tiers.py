@@ -17,7 +17,7 @@ from byzpy_b200.aggregators.norm_wise import CAF, CenteredClipping, ComparativeG
 from byzpy_b200.attacks import (EmpireAttack, GaussianAttack, InfAttack, LittleAttack, MimicAttack,
                                 SignFlipAttack)
 from byzpy_b200.engine.parameter_server.ps import ParameterServer
-from byzpy_b200.parallel.device_ps import CwPlan, GramPlan, RowFold, RowLayout
+from byzpy_b200.parallel.device_ps import CwPlan, GramPlan, MapCwPlan, RowFold, RowLayout
 from byzpy_b200.pre_aggregators import ARC, Bucketing, Clipping, NearestNeighborMixing
 
 
@@ -115,6 +115,33 @@ def test_preaggregator_composes_in_n_space(mk_pre, mk_agg):
     assert plan.capturable == mk_agg().fused_plan(3).capturable
 
 
+CW_INNER = [lambda: CoordinateWiseMedian(), lambda: CoordinateWiseTrimmedMean(f=1), lambda: MeanOfMedians(f=1)]
+
+
+@pytest.mark.parametrize("mk_pre", PRE)
+@pytest.mark.parametrize("mk_agg", CW_INNER)
+def test_preaggregator_with_a_coordinate_wise_aggregator_gives_a_map_plan(mk_pre, mk_agg):
+    """Bucketing -> median, NNM -> trimmed mean, ...: not linear in n-space, so the plan carries the (m, n) map
+    and the coordinate-wise plan of the m mixed rows; emulated here in plain torch."""
+    vs = rows(9, 29, seed=5)
+    pre, agg = mk_pre(), mk_agg()
+    plan = _ps(agg, pre)._fused_plan(len(vs))
+    assert isinstance(plan, MapCwPlan) and isinstance(plan.cw, CwPlan) and plan.name == f"{pre.name}+{agg.name}"
+    assert plan.needs_gram == pre.needs_gram and plan.capturable
+    if plan.refresh is not None:
+        plan.refresh()
+    X = torch.stack(vs).double()
+    W = plan.weights((X @ X.T) if plan.needs_gram else None)
+    mixed = mk_pre().pre_aggregate(vs)
+    assert W.shape == (plan.m, len(vs)) and plan.m == len(mixed)
+    Y = (W.double() @ X).float()
+    torch.testing.assert_close(Y, torch.stack(list(mixed)), rtol=1e-5, atol=1e-5)
+    expect = mk_agg().aggregate(list(mixed))
+    got = ops.cw_select(list(Y.unbind(0)), plan.cw.mode, plan.cw.f)
+    torch.testing.assert_close(got, expect, rtol=1e-5, atol=1e-5)
+    assert plan.cw.mode == mk_agg().fused_plan(plan.m).mode and plan.cw.f == mk_agg().fused_plan(plan.m).f
+
+
 def test_bucketing_plan_refresh_draws_a_new_permutation_each_round():
     import random
 
@@ -145,7 +172,8 @@ def test_composition_is_refused_when_it_cannot_be_expressed():
             return list(xs)
 
     assert _ps(MultiKrum(f=1, q=1), Opaque())._fused_plan(6) is None            # not a linear map
-    assert _ps(CoordinateWiseMedian(), Clipping())._fused_plan(6) is None        # inner plan is not Gram-shaped
+    assert isinstance(_ps(CoordinateWiseMedian(), Clipping())._fused_plan(6), MapCwPlan)   # mixed rows per shard
+    assert _ps(CoordinateWiseMedian(), Opaque())._fused_plan(6) is None
     assert _ps(GeometricMedian(), Clipping())._fused_plan(6) is None             # median start row is not linear in W
     with pytest.raises(ValueError):
         _ps(MultiKrum(f=1, q=1), NearestNeighborMixing(f=6))._fused_plan(6)
