@@ -16,6 +16,7 @@ Inputs may be tensors, ndarrays, ``SharedTensorHandle`` s or handle dicts.
 """
 from __future__ import annotations
 
+import os
 from abc import ABC, abstractmethod
 from typing import Any, Iterable, List, Mapping, Optional, Sequence, Tuple
 
@@ -247,6 +248,17 @@ class GramAggregator(Aggregator):
     chunk_size: int = 8192
     gram_feature_chunk: int = 1 << 16
     _gram_chunk_elems: int = 1 << 16
+    # Conditioning of the distance matrix.  ``D_ij = G_ii + G_jj - 2 G_ij`` from an fp32-product Gram loses the
+    # distances once the gradients share a component much larger than their differences (late training:
+    # |G| ~ d * common^2, round-off ~ 1e-7 |G|, true distances far below that) -- the reference's
+    # ``flat @ flat.T`` has the same flaw.  Every solver marked ``shift_invariant`` only uses distances
+    # (or affine combinations with coefficients summing to one), so it may run on the Gram of the rows
+    # translated by ANY common vector; ``center = "median"`` translates by the coordinate-wise median (inside the
+    # honest cluster whenever a majority is honest, finite whenever a majority of the rows is), ``"row0"`` by the
+    # first row.  Off by default: it costs a median pass and a centred copy of the rows.  Instance attribute, or
+    # ``BYZPY_GRAM_CENTER=median|row0`` for the process.  The output is still ``sum_i w_i x_i`` over the ORIGINAL rows.
+    shift_invariant: bool = False
+    center: Optional[str] = None
 
     # -- hooks ---------------------------------------------------------------------
     def _validate(self, n: int) -> None:
@@ -275,11 +287,33 @@ class GramAggregator(Aggregator):
         w_np = self._solve(G.detach().cpu().numpy().astype(np.float64), n)
         return torch.from_numpy(np.asarray(w_np, dtype=np.float32)).to(all_rows[0].device)
 
+    def _centering(self) -> Optional[str]:
+        mode = self.center if self.center is not None else (os.environ.get("BYZPY_GRAM_CENTER") or None)
+        if mode in (None, "", "off", "0") or not self._is_shift_invariant():
+            return None
+        if mode not in ("median", "row0"):
+            raise ValueError("center must be None, 'median' or 'row0'")
+        return mode
+
+    def _is_shift_invariant(self) -> bool:
+        return bool(self.shift_invariant)
+
+    def _aggregate_centered(self, krows: List[torch.Tensor], n: int, like: torch.Tensor, mode: str) -> Any:
+        aux = self._aux_rows(krows)
+        c = ops.cw_median(krows) if mode == "median" else krows[0]
+        c = torch.nan_to_num(c, nan=0.0, posinf=0.0, neginf=0.0)          # a non-finite centre would poison every row
+        shifted = [r - c for r in krows] + [a - c for a in aux]
+        w = self._weights(shifted, n)
+        return finish(ops.weighted_sum(krows + aux, w.reshape(-1)), like)
+
     def aggregate(self, gradients: Sequence[Any]) -> Any:
         rows, like = prepare_rows(gradients)
         n = len(rows)
         self._validate(n)
         krows = _kernel_rows(rows)
+        mode = self._centering()
+        if mode is not None:
+            return self._aggregate_centered(krows, n, like, mode)
         fused = ops.gram_with_median(krows, want64=True) if self._fused_aux() == ("median",) else None
         if fused is not None:
             # median start point + Gram matrix in ONE pass over the rows (csrc/gram.cu, AUX variant)

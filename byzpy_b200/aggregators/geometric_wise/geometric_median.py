@@ -21,6 +21,7 @@ from ..base import GramAggregator
 
 class GeometricMedian(GramAggregator):
     name = "geometric-median"
+    shift_invariant = True       # distances only
     supports_barriered_subtasks = True
     device_solve = True
 

@@ -16,6 +16,7 @@ from ..base import GramAggregator
 
 class MultiKrum(GramAggregator):
     name = "multi-krum"
+    shift_invariant = True       # distances only
     device_solve = True
 
     def __init__(self, f: int, q: int, *, chunk_size: int = 32) -> None:

@@ -13,6 +13,7 @@ from ..base import GramAggregator
 
 class MinimumDiameterAveraging(GramAggregator):
     name = "minimum-diameter-averaging"
+    shift_invariant = True       # distances only
 
     def __init__(self, f: int, *, chunk_size: int = 256) -> None:
         if f < 0:

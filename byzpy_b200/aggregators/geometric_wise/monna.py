@@ -10,6 +10,7 @@ from ..base import GramAggregator
 
 class MoNNA(GramAggregator):
     name = "monna"
+    shift_invariant = True       # distances only
     device_solve = True
 
     def __init__(self, f: int, *, reference_index: int = 0, chunk_size: int = 32) -> None:

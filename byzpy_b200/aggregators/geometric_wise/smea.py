@@ -11,6 +11,7 @@ from ..base import GramAggregator
 
 class SMEA(GramAggregator):
     name = "smea"
+    shift_invariant = True       # distances only
 
     def __init__(self, f: int, *, chunk_size: int = 256) -> None:
         if f < 0:

@@ -22,6 +22,11 @@ class CenteredClipping(GramAggregator):
     def _fused_aux(self):
         return ("median",) if self.init == "median" else ()
 
+    def _is_shift_invariant(self) -> bool:
+        # v <- v + (1/n) sum clip(x_i - v): the coefficients of v over the rows keep summing to one when they
+        # start that way (mean / median start); the zero start is an absolute point, not an affine combination
+        return self.init != "zero"
+
     def __init__(self, *, c_tau: float, M: int = 10, eps: float = 1e-12, init: str = "mean",
                  chunk_size: int = 32) -> None:
         if c_tau < 0:
