@@ -6,7 +6,7 @@ import torch
 
 from byzpy_b200 import ops
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]     # (device-side waits have their own 20 s budgets)
 DEV = torch.device("cuda", 0) if torch.cuda.is_available() else None
 
 
