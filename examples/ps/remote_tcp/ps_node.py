@@ -52,8 +52,13 @@ async def send_frame(writer: asyncio.StreamWriter, obj) -> None:
     await writer.drain()
 
 
+MAX_FRAME = 256 << 20
+
+
 async def recv_frame(reader: asyncio.StreamReader):
     (n,) = struct.unpack(">I", await reader.readexactly(4))
+    if n > MAX_FRAME:
+        raise PermissionError(f"frame of {n} bytes exceeds the {MAX_FRAME} byte limit")
     mac = await reader.readexactly(32)
     body = await reader.readexactly(n)
     if not hmac.compare_digest(mac, hmac.new(SECRET, body, hashlib.sha256).digest()):
