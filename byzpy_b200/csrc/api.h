@@ -2,7 +2,9 @@
 // Every function enqueues work on `stream` and returns a cudaError_t as int
 // (0 == success).  No function synchronises the device.
 #pragma once
+#ifndef BZ_HOST_EMU
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 #include "common.cuh"

@@ -7,7 +7,13 @@
 //     allocations, in a flat arena, or in a *peer GPU's* HBM mapped over NVLink;
 //   * per-row scale factors (sign-flip, clipping, ...) are folded into the load.
 #pragma once
+#ifdef BZ_HOST_EMU
+// warp-lockstep host emulation of the kernels (tests/native/cuda_host_emu.h, tests/test_cw_kernels_emulated.py):
+// the CUDA runtime types, thread indices, memory-access helpers and cp.async come from the emulator
+#include "cuda_host_emu.h"
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 #define BZ_MAXN 128   // max rows handled by the register / smem resident kernels
@@ -39,6 +45,7 @@ struct VirtRows {
   float a, b;
 };
 
+#ifndef BZ_HOST_EMU
 __device__ __forceinline__ float4 ldg_stream4(const float* p) {
   float4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
@@ -112,6 +119,8 @@ __device__ __forceinline__ void stg_stream1(float* p, float v) {
   asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
+#endif  // !BZ_HOST_EMU
+
 // The register-resident selection code below is plain arithmetic, so it is compiled for the host as
 // well: tests/test_cw_network_host.py builds it with nvcc and checks every network size, padding and
 // mode against a sort on the CPU (the box that builds the extension has no GPU).
@@ -150,11 +159,14 @@ BZ_HD void bitonic_sort(float (&v)[NP]) {
   }
 }
 
+#ifndef BZ_HOST_EMU
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+
+#endif
 
 #define BZ_CUDA_CHECK(expr)                                   \
   do {                                                        \

@@ -209,6 +209,7 @@ __device__ __forceinline__ void cw_unit(const RowTable& rows, const ScaleTable& 
 // in flight per thread while the selection network of the current tile runs, at zero register
 // cost.  Slot layout [stage][row][thread][V] is bank-conflict free for both the async writes and
 // the read-back.
+#ifndef BZ_HOST_EMU      // (the emulator defers the copies to the matching wait, see cuda_host_emu.h)
 template <int BYTES>
 __device__ __forceinline__ void cp_async(void* smem, const void* gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -223,6 +224,8 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+
+#endif
 
 template <int NP, int V>
 __device__ __forceinline__ void cw_stage_issue(float* stage, int threads, const RowTable& rows, int n,
