@@ -400,3 +400,28 @@ def test_bucket_marks_fire_in_reverse_layer_order_with_complete_gradients():
     a.zero_grad()
     m(torch.randn(4, 3, 32, 32)).sum().backward()
     assert seen == []
+
+
+def test_coordinate_shards_follow_the_live_set_and_equal_the_static_split_when_nobody_was_dropped():
+    from byzpy_b200.parallel.device_ps import DeviceRound
+
+    def shard(rank, world, d_pad, live_mask=0):
+        r = object.__new__(DeviceRound)
+        r.rank, r.world, r.live_mask = rank, world, live_mask
+        return r._shard(0, d_pad)
+
+    for world in (1, 2, 3, 4, 5, 8):
+        for d_pad in (1024, 11_689_984, 25_558_016):
+            sh = d_pad // world
+            sh -= sh % 4
+            cover = 0
+            for rank in range(world):
+                static = (rank * sh, sh if rank < world - 1 else d_pad - sh * (world - 1))     # DeviceRound.__init__
+                assert shard(rank, world, d_pad) == static
+                assert static[0] % 4 == 0 and static[1] % 4 == 0
+                cover += static[1]
+            assert cover == d_pad
+    # after rank 1 of 4 was dropped the survivors split the whole vector among themselves
+    live = 0b1101
+    parts = [shard(r, 4, 4096, live) for r in (0, 2, 3)]
+    assert parts[0][0] == 0 and all(a[0] + a[1] == b[0] for a, b in zip(parts, parts[1:])) and sum(p[1] for p in parts) == 4096
