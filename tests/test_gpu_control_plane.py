@@ -62,7 +62,29 @@ def _make_branch_graph(k, stamps):
     return ComputationGraph(nodes, outputs=["out"])
 
 
+def _retry_timing(attempt, tries=3):
+    """The functional assertions inside ``attempt`` must hold every time; its device-overlap assertions are
+    measurements on a shared box, so they get a few tries (a host hiccup between two enqueues can serialise one
+    run) -- this file sorts first in the GPU suite and must not stop a ``pytest -x`` run on a fluke."""
+    last = None
+    for _ in range(tries):
+        try:
+            return attempt()
+        except _TimingMiss as exc:
+            last = exc
+            torch.cuda.synchronize()
+    raise AssertionError(f"no device overlap in {tries} attempts: {last}")
+
+
+class _TimingMiss(Exception):
+    pass
+
+
 def test_parallel_scheduler_runs_cuda_branches_concurrently_on_streams():
+    _retry_timing(_scheduler_attempt)
+
+
+def _scheduler_attempt():
     from byzpy_b200.engine.graph.parallel_scheduler import ParallelScheduler
     from byzpy_b200.engine.graph.scheduler import NodeScheduler
 
@@ -88,11 +110,11 @@ def test_parallel_scheduler_runs_cuda_branches_concurrently_on_streams():
     # ... and overlapped ON THE DEVICE: some branch started before another one finished
     iv = sorted((t1.elapsed_time(a), t1.elapsed_time(b)) for _, a, b in stamps_p.values())
     overlaps = sum(1 for i in range(k - 1) if iv[i + 1][0] < iv[i][1])
-    assert overlaps >= 1, iv
     span_p = max(e for _, e in iv) - min(s for s, _ in iv)
     iv_s = [(t0.elapsed_time(a), t0.elapsed_time(b)) for _, a, b in stamps_s.values()]
     span_s = max(e for _, e in iv_s) - min(s for s, _ in iv_s)
-    assert span_p < 0.8 * span_s, (span_p, span_s)
+    if overlaps < 1 or not span_p < 0.8 * span_s:
+        raise _TimingMiss(f"intervals {iv}, spans parallel {span_p:.3f} ms / serial {span_s:.3f} ms")
 
 
 def test_gpu_actor_backends_own_streams_overlap_and_order_after_the_caller():
@@ -129,11 +151,12 @@ def test_gpu_actor_backends_own_streams_overlap_and_order_after_the_caller():
         torch.testing.assert_close(y1, _chain(x + 1.0), rtol=0, atol=0)
         torch.testing.assert_close(y2, _chain(x + 2.0), rtol=0, atol=0)
         i1, i2 = (t0.elapsed_time(a1s), t0.elapsed_time(a1e)), (t0.elapsed_time(a2s), t0.elapsed_time(a2e))
-        assert max(i1[0], i2[0]) < min(i1[1], i2[1]), (i1, i2)          # the two actors overlapped on the device
         await b1.close()
         await b2.close()
+        if not max(i1[0], i2[0]) < min(i1[1], i2[1]):                   # the two actors overlapped on the device
+            raise _TimingMiss(f"actor intervals {i1} {i2}")
 
-    asyncio.run(main())
+    _retry_timing(lambda: asyncio.run(main()))
 
 
 def _free_port():
