@@ -224,7 +224,9 @@ class SymmetricBuffer:
             mc_local_ok = False
         if self.world == 1:
             if self._ptr == 0:
-                raise RuntimeError(f"VMM allocation failed: {err!r}") from err
+                self._vmm_teardown(fds)
+                warnings.warn(f"VMM allocation failed ({err!r}); using the CUDA-IPC heap")
+                self._fallback_ipc(nbytes, multicast)
             return
         if not self._agree(self._ptr != 0 and len(fds) >= 1):
             self._vmm_teardown(fds)

@@ -65,3 +65,16 @@ def test_explicit_multicast_request_fails_loudly_on_every_rank():
 def test_multicast_can_be_declined():
     res = _run({}, multicast="false")
     assert _uniform(res, "kind") == "vmm" and _uniform(res, "mc") is False
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_other_team_sizes(world):
+    """world 1 (the single-GPU bench: no exchange, no multicast) and world 2."""
+    res = _run({}, world=world)
+    assert _uniform(res, "kind") == "vmm" and _uniform(res, "mc") is (world > 1)
+    assert all(r["ptrs_ok"] and r["distinct"] and r["leaked_maps"] == 0 and r["leaked_handles"] == 0 for r in res), res
+
+
+def test_single_rank_allocation_failure_falls_back_to_the_ipc_heap():
+    res = _run({"vmm_alloc": [0]}, world=1)
+    assert res[0].get("kind") == "ipc" and res[0]["ptrs_ok"] and res[0]["leaked_maps"] == 0, res
