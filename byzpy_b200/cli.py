@@ -79,10 +79,33 @@ def _doctor() -> dict:
                 n = ext.device_count()
                 report["nvlink"]["peer_access"] = [[bool(i == j or ext.can_access_peer(i, j))
                                                     for j in range(n)] for i in range(n)]
+            # which symmetric heap DeviceRound / DeviceP2PRound will use on this box (parallel/symmetric.py)
+            if hasattr(ext, "vmm_support"):
+                try:
+                    sup = dict(ext.vmm_support(0))
+                except Exception as exc:  # noqa: BLE001
+                    sup = {"vmm": False, "posix_fd": False, "multicast": False, "reason": repr(exc)}
+                heap = "vmm" if (sup.get("vmm") and sup.get("posix_fd")) else "ipc"
+                report["symmetric_heap"] = {"heap": heap, "nvls_multicast": bool(sup.get("multicast")) and heap == "vmm",
+                                            "tma_tensor_maps": sup.get("reason", "") == "",
+                                            "driver": sup.get("reason") or "ok"}
         else:
             k["error"] = repr(ops._C_err)
     except Exception as exc:  # pragma: no cover
         report["kernels"]["error"] = str(exc)
+    # process-wide switches that change which code path runs (all optional; shown with their effective value)
+    import os
+
+    report["switches"] = {
+        "BYZPY_SYMM": os.environ.get("BYZPY_SYMM", "auto (vmm where supported, else ipc)"),
+        "BYZPY_CW_IMPL": os.environ.get("BYZPY_CW_IMPL", "auto (direct / staged; 'tiled' is opt-in)"),
+        "BYZPY_GRAM_TMA": os.environ.get("BYZPY_GRAM_TMA", "1"),
+        "BYZPY_GRAM_CENTER": os.environ.get("BYZPY_GRAM_CENTER", "off"),
+        "BYZPY_POOL_DISPATCH": os.environ.get("BYZPY_POOL_DISPATCH", "adaptive"),
+        "BYZPY_OVERLAP_GRID": os.environ.get("BYZPY_OVERLAP_GRID", "auto (a quarter of the SMs)"),
+        "BYZPY_BN_CLUSTER": os.environ.get("BYZPY_BN_CLUSTER", "1"),
+        "BYZPY_INTRAOP_GOVERNOR": os.environ.get("BYZPY_INTRAOP_GOVERNOR", "1"),
+    }
     return report
 
 
