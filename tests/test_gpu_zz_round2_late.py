@@ -144,3 +144,22 @@ def test_pre_aggregator_with_coordinate_wise_aggregator_runs_fused(pre_name, agg
     want = torch.cat([p.detach().reshape(-1) for p in models[0].parameters()]).cpu()
     torch.testing.assert_close(got, want, rtol=1e-3, atol=1e-4)
     asyncio.run(ps.shutdown())
+
+
+@pytest.mark.parametrize("extra", [[], ["--aggregator", "multikrum", "--pre", "nnm"],
+                                   ["--aggregator", "trmean", "--pre", "bucketing", "--timeline", "--buckets", "1"]])
+def test_device_example_runs_on_one_gpu(extra):
+    """examples/ps/device/resnet_fused.py end to end (tiny images, 6 rounds)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "examples/ps/device/resnet_fused.py", "--rounds", "6", "--image", "32", "--classes", "10",
+           "--batch", "4"] + extra
+    res = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=280,
+                         env=dict(os.environ, PYTHONPATH=root, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0")))
+    assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-1500:]
+    assert "round 5: losses" in res.stdout and "plan " in res.stdout, res.stdout[-1500:]
+    if "--timeline" in extra:
+        assert '"round_done"' in res.stdout
