@@ -56,11 +56,26 @@ class RemoteActorBackend:
         if self._writer is None:
             self._reader, self._writer = await asyncio.open_connection(self.host, self.port)
 
+    def _drop_connection(self) -> None:
+        writer, self._reader, self._writer = self._writer, None, None
+        if writer is not None:
+            try:
+                writer.close()
+            except Exception:
+                pass
+
     async def _rpc(self, msg: Dict[str, Any]) -> Any:
-        await self.start()
         async with self._lock:
-            await send_obj(self._writer, msg)
-            reply = await recv_obj(self._reader)
+            await self.start()
+            try:
+                await send_obj(self._writer, msg)
+                reply = await recv_obj(self._reader)
+            except BaseException:
+                # cancelled (a caller's wait_for timed out -- ParameterServer(node_timeout=...) does that) or
+                # broken in mid-exchange: the reply may still arrive, and the next exchange on this connection
+                # would take it for its own.  The actor lives on in the server under its id; reconnect next time.
+                self._drop_connection()
+                raise
         if not reply.get("ok", False):
             raise RuntimeError(f"remote actor error: {reply.get('error')}")
         return reply.get("payload")

@@ -28,8 +28,8 @@ from . import cuda_ipc
 
 Endpoint = Tuple[asyncio.StreamReader, asyncio.StreamWriter]
 
-_EP_CACHE: Dict[Tuple[str, int], Endpoint] = {}
-_EP_LOCKS: Dict[Tuple[str, int], asyncio.Lock] = {}
+_EP_CACHE: Dict[Tuple[int, str, int], Endpoint] = {}
+_EP_LOCKS: Dict[Tuple[int, str, int], asyncio.Lock] = {}
 _RETRYABLE = (ConnectionError, asyncio.IncompleteReadError, BrokenPipeError, EOFError, OSError)
 
 
@@ -51,8 +51,21 @@ def have_ucx() -> bool:
     return cuda_ipc.available()
 
 
-def _key(host: str, port: int) -> Tuple[str, int]:
-    return (host, int(port))
+def _key(host: str, port: int) -> Tuple[int, str, int]:
+    """Pool key: streams and locks belong to the event loop that created them, so a process that runs several
+    loops one after the other (``asyncio.run`` per call) gets one endpoint per (loop, peer)."""
+    try:
+        loop_id = id(asyncio.get_running_loop())
+    except RuntimeError:
+        loop_id = 0
+    return (loop_id, host, int(port))
+
+
+def _drop_dead_loops() -> None:
+    """Forget endpoints whose event loop is gone (their transports were closed with the loop)."""
+    for key in [k for k, (_, w) in _EP_CACHE.items() if w.is_closing()]:
+        _EP_CACHE.pop(key, None)
+        _EP_LOCKS.pop(key, None)
 
 
 def is_same_host(host: str) -> bool:
@@ -65,6 +78,8 @@ async def get_endpoint(host: str, port: int) -> Endpoint:
     ep = _EP_CACHE.get(key)
     if ep is not None and not ep[1].is_closing():
         return ep
+    if len(_EP_CACHE) > 64:
+        _drop_dead_loops()
     reader, writer = await asyncio.open_connection(host, int(port))
     _EP_CACHE[key] = (reader, writer)
     return reader, writer
@@ -80,11 +95,13 @@ def evict_endpoint(host: str, port: int) -> None:
 
 
 async def clear_pool() -> None:
+    here = _key("", 0)[0]
     for key in list(_EP_CACHE):
         _, writer = _EP_CACHE.pop(key)
         try:
             writer.close()
-            await writer.wait_closed()
+            if key[0] == here:              # (a stream of another loop cannot be awaited from this one)
+                await writer.wait_closed()
         except Exception:
             pass
     _EP_LOCKS.clear()
@@ -101,11 +118,21 @@ async def call(host: str, port: int, fn: Callable[[Endpoint], Awaitable[Any]]) -
             ep = await get_endpoint(host, port)
             return await fn(ep)
 
-    try:
-        return await _once()
-    except _RETRYABLE:
-        evict_endpoint(host, port)
-        return await _once()
+    for attempt in (0, 1):
+        try:
+            return await _once()
+        except (asyncio.TimeoutError, asyncio.CancelledError):
+            # the peer's reply is still in flight: the next exchange on this connection would read it as ITS
+            # reply, so the endpoint is not reusable (and a timeout is the caller's answer, not a broken link)
+            evict_endpoint(host, port)
+            raise
+        except _RETRYABLE:
+            evict_endpoint(host, port)
+            if attempt == 1:
+                raise
+        except BaseException:
+            evict_endpoint(host, port)
+            raise
 
 
 def pack_payload(obj: Any, *, same_host: bool = True) -> Tuple[str, bytes]:

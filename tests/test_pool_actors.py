@@ -204,6 +204,36 @@ def test_tcp_actor_server_roundtrip():
         srv.stop()
 
 
+class _Slow:
+    async def slow(self, seconds, tag):
+        await asyncio.sleep(seconds)
+        return tag
+
+    def fast(self, tag):
+        return tag
+
+
+def test_tcp_actor_call_cancelled_by_a_timeout_does_not_poison_the_next_call():
+    """``ParameterServer(node_timeout=...)`` wraps node calls in ``wait_for``: a call that times out leaves its
+    reply in flight, and the next call on the same connection must not receive it."""
+    srv = _ServerThread()
+    try:
+        async def scenario():
+            be = resolve_backend(f"tcp://127.0.0.1:{srv.port}")
+            async with ActorRef(be) as ref:
+                await be.construct(_Slow, args=(), kwargs={})
+                with pytest.raises(asyncio.TimeoutError):
+                    await asyncio.wait_for(ref.slow(0.4, "late"), timeout=0.05)
+                assert await ref.fast("mine") == "mine"            # reconnected: not the late reply
+                await asyncio.sleep(0.5)
+                assert await ref.fast("again") == "again"
+                assert await ref.slow(0.01, "ok") == "ok"
+
+        run(scenario())
+    finally:
+        srv.stop()
+
+
 def test_cross_backend_channel_matrix():
     srv = _ServerThread()
     try:
@@ -298,6 +328,15 @@ def test_ucx_transport_pools_endpoints_locks_per_peer_and_retries_once():
             assert await ucx_t.chan_get("127.0.0.1", srv.port, ep.actor_id, "box", 2.0) == "again"
             assert (await ucx_t.get_endpoint("127.0.0.1", srv.port)) is not first
             assert await ucx_t.chan_get("127.0.0.1", srv.port, ep.actor_id, "box", 0.05) is None
+            # a CLIENT-side timeout leaves the server's reply in flight: the endpoint must not be reused, or the
+            # next exchange would read that stale reply as its own
+            before = await ucx_t.get_endpoint("127.0.0.1", srv.port)
+            with pytest.raises(asyncio.TimeoutError):
+                await ucx_t.request("127.0.0.1", srv.port, {"op": "chan_get", "actor_id": ep.actor_id, "name": "idle",
+                                                            "timeout": 0.5}, timeout=0.05)
+            assert (await ucx_t.get_endpoint("127.0.0.1", srv.port)) is not before
+            await ucx_t.chan_put("127.0.0.1", srv.port, ep.actor_id, "box", "fresh")
+            assert await ucx_t.chan_get("127.0.0.1", srv.port, ep.actor_id, "box", 2.0) == "fresh"
             await ucx_t.clear_pool()
             await be.close()
 
