@@ -19,7 +19,7 @@ from typing import Any
 
 import cloudpickle
 
-from ..ipc import unwrap_payload, wrap_payload
+from ..ipc import discard_payload, unwrap_payload, wrap_payload
 from ._local import LocalMailboxBackend
 
 
@@ -146,7 +146,21 @@ class ProcessActorBackend(LocalMailboxBackend):
 
     async def _send(self, msg: dict) -> Any:
         loop = asyncio.get_running_loop()
-        return await loop.run_in_executor(None, self._roundtrip, msg)
+        fut = loop.run_in_executor(None, self._roundtrip, msg)
+        try:
+            return await asyncio.shield(fut)
+        except asyncio.CancelledError:
+            # the caller gave up (ParameterServer(node_timeout=...) wraps calls in wait_for); the round trip
+            # still completes on its thread, and its reply may hold shared-memory segments nobody will unwrap
+            def _discard(f) -> None:
+                if not f.cancelled() and f.exception() is None:
+                    try:
+                        discard_payload(f.result())
+                    except Exception:
+                        pass
+
+            fut.add_done_callback(_discard)
+            raise
 
     async def construct(self, cls_or_factory: Any, *, args: tuple, kwargs: dict) -> None:
         await self._send({"op": "construct", "cls": cloudpickle.dumps(cls_or_factory),

@@ -83,4 +83,20 @@ def unwrap_payload(obj: Any) -> Any:
     return obj
 
 
-__all__ = ["wrap_payload", "unwrap_payload"]
+def discard_payload(obj: Any) -> None:
+    """Release the shared-memory segments of a wrapped payload that nobody is going to unwrap (the reply of a
+    call whose caller was cancelled / timed out): segments are single-consumer and named, so an unread one would
+    stay in ``/dev/shm`` until the machine reboots."""
+    if isinstance(obj, tuple) and len(obj) == 2 and obj[0] == _SHM_MARK:
+        cleanup_tensor(obj[1])
+    elif isinstance(obj, tuple) and len(obj) == 4 and obj[0] == _SHM_BATCH_MARK:
+        cleanup_tensor(obj[1])
+    elif isinstance(obj, (list, tuple)):
+        for x in obj:
+            discard_payload(x)
+    elif isinstance(obj, dict):
+        for v in obj.values():
+            discard_payload(v)
+
+
+__all__ = ["wrap_payload", "unwrap_payload", "discard_payload"]

@@ -213,6 +213,37 @@ class _Slow:
         return tag
 
 
+class _SlowTensor:
+    def big(self, seconds):
+        import time
+
+        time.sleep(seconds)
+        return torch.ones(1 << 18)          # 1 MB: travels back through a shared-memory segment
+
+    def ping(self):
+        return "pong"
+
+
+def test_process_actor_reply_of_a_timed_out_call_does_not_leak_shared_memory():
+    import glob
+
+    async def scenario():
+        be = resolve_backend("process")
+        async with ActorRef(be) as ref:
+            await be.construct(_SlowTensor, args=(), kwargs={})
+            assert await ref.ping() == "pong"
+            before = set(glob.glob("/dev/shm/psm_*"))
+            with pytest.raises(asyncio.TimeoutError):
+                await asyncio.wait_for(ref.big(0.3), timeout=0.05)
+            assert await ref.ping() == "pong"          # queued behind the slow call, answered with ITS reply
+            await asyncio.sleep(0.2)
+            assert set(glob.glob("/dev/shm/psm_*")) <= before, "the abandoned reply's segment was not released"
+            out = await ref.big(0.0)
+            assert out.shape == (1 << 18,) and float(out.sum()) == float(1 << 18)
+
+    run(scenario())
+
+
 def test_tcp_actor_call_cancelled_by_a_timeout_does_not_poison_the_next_call():
     """``ParameterServer(node_timeout=...)`` wraps node calls in ``wait_for``: a call that times out leaves its
     reply in flight, and the next call on the same connection must not receive it."""
