@@ -249,7 +249,7 @@ class ActorPool:
                 return self._available.get_nowait()
             fut = asyncio.get_running_loop().create_future()
             self._waiting[None].append(fut)
-            return await fut
+            return await self._await_worker(fut)
         # rotate through the idle workers once looking for a capable one
         for _ in range(self._available.qsize()):
             w = self._available.get_nowait()
@@ -260,7 +260,18 @@ class ActorPool:
             raise RuntimeError("No actor in the pool")
         fut = asyncio.get_running_loop().create_future()
         self._waiting[affinity].append(fut)
-        return await fut
+        return await self._await_worker(fut)
+
+    async def _await_worker(self, fut: "asyncio.Future") -> _PoolWorker:
+        """Wait for ``_release`` to hand over a worker.  A waiter that is cancelled in the same loop iteration in
+        which it was handed one (the windowed runner cancels its in-flight subtasks when one of them fails) must
+        give it back, or the pool shrinks by one worker for good."""
+        try:
+            return await fut
+        except asyncio.CancelledError:
+            if fut.done() and not fut.cancelled() and fut.exception() is None:
+                await self._release(fut.result())
+            raise
 
     async def _release(self, worker: _PoolWorker) -> None:
         for key in list(worker.capabilities) + [None]:

@@ -610,3 +610,31 @@ def test_wrap_detaches_grad_tensors_and_keeps_dtype():
     x = torch.ones(3, dtype=torch.float64, requires_grad=True)
     back = unwrap_payload(wrap_payload([x * 2]))[0]
     assert back.dtype == torch.float64 and not back.requires_grad and torch.equal(back, torch.full((3,), 2.0, dtype=torch.float64))
+
+
+def test_a_waiter_cancelled_right_after_being_handed_a_worker_gives_it_back():
+    """Lost wake-up: ``_release`` resolves a waiter's future, the waiter is cancelled before it resumes (the
+    windowed runner does that when a sibling subtask fails) -- the worker must return to the pool."""
+    async def scenario():
+        pool = ActorPool([ActorPoolConfig(backend="thread", count=1)])
+        await pool.start()
+        try:
+            held = await pool._acquire(None)                     # the only worker is busy
+            waiter = asyncio.ensure_future(pool._acquire(None))
+            await asyncio.sleep(0)                               # the waiter is parked on its future
+            await pool._release(held)                            # hands the worker to the waiter's future ...
+            waiter.cancel()                                      # ... and the waiter dies before it resumes
+            with pytest.raises(asyncio.CancelledError):
+                await waiter
+            got = await asyncio.wait_for(pool._acquire(None), timeout=1.0)
+            assert got is held
+            await pool._release(got)
+            assert await asyncio.wait_for(pool.run_subtask(SubTask(fn=_add, args=(2, 3), kwargs={})), timeout=5.0) == 5
+        finally:
+            await pool.shutdown()
+
+    asyncio.run(scenario())
+
+
+def _add(a, b):
+    return a + b
