@@ -94,6 +94,37 @@ def ref_gm(rows, tol=1e-6, max_iter=256):
     return z
 
 
+def cw_variants(a):
+    """A/B of the three pipelines of csrc/cw_select.cu on the same inputs (bit-identical results are asserted):
+    ``python benchmarks/agg_sweep.py --cw-variants --n 64 --dims 1e7`` -- the measurement profiles/cw_select.md
+    section 4 is waiting for."""
+    from byzpy_b200 import ops
+
+    dev = torch.device("cuda", 0)
+    peak = peak_gbs()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    results = []
+    for ds in a.dims.split(","):
+        d = int(float(ds))
+        rows = [torch.randn(d, device=dev) for _ in range(a.n)]
+        nbytes = (a.n * d + d) * 4
+        for mode_name, mode, f in (("median", ops.MODE_MEDIAN, 0), ("trimmed_mean", ops.MODE_TRMEAN, a.f),
+                                   ("mean_of_medians", ops.MODE_MEAMED, a.f)):
+            base = ops.cw_select(rows, mode, f, impl="direct")
+            for impl in ("direct", "staged", "tiled"):
+                out = torch.empty(d, device=dev)
+                assert torch.equal(ops.cw_select(rows, mode, f, out=out, impl=impl), base), (mode_name, impl)
+                t = timeit(lambda: ops.cw_select(rows, mode, f, out=out, impl=impl), flush=flush)
+                rec = {"op": mode_name, "impl": impl, "n": a.n, "d": d, "ms": round(t, 4),
+                       "frac_of_measured_hbm_peak": round(nbytes / 1e6 / t / peak, 3)}
+                results.append(rec)
+                print(json.dumps(rec), flush=True)
+        del rows
+        torch.cuda.empty_cache()
+    os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
+    json.dump({"peak_hbm_gbs": peak, "cw_variants": results}, open(a.out, "w"), indent=1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=8)
@@ -101,7 +132,11 @@ def main():
     ap.add_argument("--dims", default="1e5,1e6,1e7,1e8")
     ap.add_argument("--out", default="gpurun_out/agg_sweep.json")
     ap.add_argument("--skip-ref-above", type=float, default=3e8)
+    ap.add_argument("--cw-variants", action="store_true",
+                    help="time the coordinate-wise kernel variants (direct / staged / tiled) instead of the operator sweep")
     a = ap.parse_args()
+    if a.cw_variants:
+        return cw_variants(a)
     dev = torch.device("cuda", 0)
     peak = peak_gbs()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
