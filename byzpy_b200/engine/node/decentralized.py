@@ -60,6 +60,7 @@ class DecentralizedNode:
         self._running = False
         self._message_task: Optional[asyncio.Task] = None
         self._autonomous_tasks: Dict[str, asyncio.Task] = {}
+        self.handler_errors: List[tuple] = []          # (message type, repr(exception)) of handlers that raised
         self._register_default_handlers()
 
     # ---- lifecycle ------------------------------------------------------------------------
@@ -87,9 +88,25 @@ class DecentralizedNode:
             async for msg in self.context.receive_messages():
                 if not self._running:
                     break
-                await self.handle_incoming_message(from_node_id=msg.get("from", "unknown"),
-                                                   message_type=msg.get("type", "unknown"),
-                                                   payload=msg.get("payload"))
+                try:
+                    await self.handle_incoming_message(from_node_id=msg.get("from", "unknown"),
+                                                       message_type=msg.get("type", "unknown"),
+                                                       payload=msg.get("payload"))
+                except asyncio.CancelledError:
+                    raise
+                except Exception as exc:  # noqa: BLE001
+                    # a raising handler must not end message processing for the node (in the reference the loop
+                    # task dies with the exception and the node goes deaf without a trace, reference
+                    # engine/node/decentralized.py:95-107): record it, say so once per message type, carry on
+                    mtype = msg.get("type", "unknown")
+                    first = not any(t == mtype for t, _ in self.handler_errors)
+                    self.handler_errors.append((mtype, repr(exc)))
+                    del self.handler_errors[:-64]
+                    if first:
+                        import warnings
+
+                        warnings.warn(f"node {self.node_id!r}: handler of {mtype!r} messages raised {exc!r}; "
+                                      "message processing continues (see node.handler_errors)")
         except asyncio.CancelledError:
             pass
 

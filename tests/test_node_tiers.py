@@ -638,3 +638,46 @@ def test_cluster_defaults_to_process_context():
         assert isinstance(node.context, ProcessContext)              # never started: nothing spawned
 
     run(go())
+
+
+def test_a_raising_message_handler_does_not_make_the_node_deaf():
+    import warnings
+
+    from byzpy_b200.engine.node.application import HonestNodeApplication
+    from byzpy_b200.engine.node.context import InProcessContext
+    from byzpy_b200.engine.node.decentralized import DecentralizedNode
+    from byzpy_b200.engine.graph.pool import ActorPoolConfig
+
+    async def scenario():
+        nodes = [DecentralizedNode(node_id=i, application=HonestNodeApplication(name=f"n{i}", actor_pool=[ActorPoolConfig(backend="thread", count=1)]),
+                                   context=InProcessContext()) for i in range(2)]
+        seen = []
+
+        async def flaky(frm, payload):
+            if payload == "boom":
+                raise ValueError("handler bug")
+            seen.append(payload)
+
+        nodes[1].register_message_handler("note", flaky)
+        for n in nodes:
+            await n.start()
+        try:
+            with warnings.catch_warnings(record=True) as caught:
+                warnings.simplefilter("always")
+                await nodes[0].send_message(1, "note", "one")
+                await nodes[0].send_message(1, "note", "boom")
+                await nodes[0].send_message(1, "note", "two")
+                await nodes[0].send_message(1, "note", "boom")
+                await nodes[0].send_message(1, "note", "three")
+                for _ in range(100):
+                    if len(seen) == 3:
+                        break
+                    await asyncio.sleep(0.02)
+            assert seen == ["one", "two", "three"]
+            assert [t for t, _ in nodes[1].handler_errors] == ["note", "note"]
+            assert sum("handler of 'note' messages raised" in str(w.message) for w in caught) == 1
+        finally:
+            for n in nodes:
+                await n.shutdown()
+
+    asyncio.run(scenario())
