@@ -38,6 +38,19 @@ def _cuda_ok() -> bool:
         return False
 
 
+def _record_stream(obj: Any, stream) -> None:
+    """``tensor.record_stream(stream)`` for every CUDA tensor in a nested result."""
+    if hasattr(obj, "is_cuda") and hasattr(obj, "record_stream"):
+        if obj.is_cuda:
+            obj.record_stream(stream)
+    elif isinstance(obj, (list, tuple)):
+        for x in obj:
+            _record_stream(x, stream)
+    elif isinstance(obj, dict):
+        for v in obj.values():
+            _record_stream(v, stream)
+
+
 class GPUActorBackend(LocalMailboxBackend):
     scheme = "gpu"
 
@@ -86,7 +99,12 @@ class GPUActorBackend(LocalMailboxBackend):
                 return out, done
 
         out, done = await loop.run_in_executor(self._pool, _run)
-        torch.cuda.current_stream(self._device).wait_event(done)   # device-side join
+        caller = torch.cuda.current_stream(self._device)
+        caller.wait_event(done)                                    # device-side join
+        # results were allocated on the ACTOR's stream and are about to be consumed on the caller's: tell the
+        # caching allocator, or a block freed by the caller could be handed to this actor's next call (by a
+        # different caller) while kernels of this caller still read it
+        _record_stream(out, caller)
         return out
 
     async def construct(self, cls_or_factory: Any, *, args: tuple, kwargs: dict) -> None:

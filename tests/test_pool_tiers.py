@@ -638,3 +638,21 @@ def test_a_waiter_cancelled_right_after_being_handed_a_worker_gives_it_back():
 
 def _add(a, b):
     return a + b
+
+
+def test_gpu_actor_results_are_recorded_on_the_callers_stream():
+    """The helper behind GPUActorBackend._on_stream, on stand-ins (no GPU here): every CUDA tensor of a nested
+    result is recorded on the consuming stream, host tensors and other objects are left alone."""
+    from byzpy_b200.engine.actor.backends.gpu import _record_stream
+
+    class FakeTensor:
+        def __init__(self, cuda):
+            self.is_cuda, self.recorded = cuda, []
+
+        def record_stream(self, s):
+            self.recorded.append(s)
+
+    a, b, c = FakeTensor(True), FakeTensor(False), FakeTensor(True)
+    _record_stream({"x": [a, (b, "text", 3)], "y": c, "z": None}, "caller-stream")
+    assert a.recorded == ["caller-stream"] and c.recorded == ["caller-stream"] and b.recorded == []
+    _record_stream(torch.ones(3), "s")       # a real CPU tensor: nothing to do, nothing raised
