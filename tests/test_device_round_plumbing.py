@@ -199,3 +199,123 @@ def test_map_round_with_virtual_little_rows():
     mixed = Bucketing(2, perm=list(range(10))).pre_aggregate(rows + [virt, virt])
     torch.testing.assert_close(r._agg_t[:d], CoordinateWiseMedian().aggregate(list(mixed)), rtol=1e-4, atol=1e-5)
     assert "colstat" in r.ext.calls
+
+
+# --------------------------------------------------------------------------- Gram round (GPU-validated) on host memory
+def _fake_gram_extras(ext):
+    """The two further kernels the Gram round launches."""
+
+    def cw_select(rows, scales, mode, f, nv, nh, va, vb, off, ln, out, upd_params, upd_moms, lr, mu, wd, sm, stream, impl=0):
+        ext.calls.append("cw_select")
+        X = torch.from_numpy(ext._rows(rows, scales, off, ln).astype(np.float32))
+        view(out + 4 * off, ln)[:] = ops.cw_select(list(X.unbind(0)), mode, f).numpy()
+
+    def fused_ps_wsum(rows, scales, W, d, shard_off, shard_len, rank, agg, pads, epoch_ptr, counter, status, upd_params,
+                      upd_moms, lr, mu, wd, sm, stream, grid_limit=0, rng_off=0, rng_len=0, seq_mul=0, seq_add=0,
+                      agg_mc=0, live_mask=0, spin_s=0.0):
+        ext.calls.append("fused_ps_wsum")
+        n = len(rows)
+        w = view(W, n).astype(np.float64)
+        view(agg[rank] + 4 * shard_off, shard_len)[:] = w @ ext._rows(rows, scales, shard_off, shard_len)
+        ext.covered = (shard_off, shard_len)
+
+    ext.cw_select, ext.fused_ps_wsum = cw_select, fused_ps_wsum
+
+
+@pytest.mark.parametrize("live_mask,world,rank", [(0, 1, 0), (0b01, 2, 0), (0, 2, 1), (0b1101, 4, 2)])
+def test_gram_round_shard_follows_the_live_set(live_mask, world, rank):
+    """``_launch_gram_round`` on host memory: with every rank alive a rank aggregates its static share; after peers
+    were dropped (``recover()``) the survivors' shares tile the whole vector (a single survivor covers all of it)."""
+    from byzpy_b200.aggregators.geometric_wise import GeometricMedian, MultiKrum
+
+    n, d = 6, 4000
+    for mk in (lambda: MultiKrum(f=1, q=3), lambda: GeometricMedian(tol=1e-7)):
+        plan = mk().fused_plan(n)
+        r = object.__new__(DeviceRound)
+        d_pad = 4096
+        r.ext = FakeExt(d_pad)
+        _fake_gram_extras(r.ext)
+        r.device = torch.device("cpu")
+        r.world, r.rank, r.live_mask = world, rank, live_mask
+        r.d, r.d_pad, r.sm, r.nt_max = d, d_pad, 8, 144
+        r.layout = RowLayout(n, 0, 0, world, [0] * n, list(range(n)))
+        r.plan, r.virtual_fold, r.spin_seconds = plan, None, 0.0
+        g = torch.Generator().manual_seed(5)
+        r._grads_t = torch.randn(n, d_pad, generator=g)
+        r._grads_t[:, d:] = 0.0
+        r._agg_t = torch.zeros(d_pad)
+        r._pad_t = torch.zeros(64, dtype=torch.int32)
+        r._gslots_t = torch.zeros(world * 144 * 144 + 144 * 144, dtype=torch.float64)
+        r._ctl_t = torch.zeros(64, dtype=torch.int32)
+        r._rows = [r._grads_t[i].data_ptr() for i in range(n)]
+        r._scales = [1.0] * n
+        r._off_pad, r._off_agg, r._off_gslots = 1, 2, 3
+        table = {1: r._pad_t.data_ptr(), 2: r._agg_t.data_ptr(), 3: r._gslots_t.data_ptr()}
+        r.sym = types.SimpleNamespace(peer_ptr=lambda rk, off: table[off], mc_ptr=lambda off: 0)
+        r._agg_mc = 0
+        r._upd_params, r._upd_moms = [], []
+        r.lr, r.momentum, r.weight_decay = 0.1, 0.0, 0.0
+        r._setup_gram_plan()
+        r._launch_gram_round(0, r._ctl_t.data_ptr())
+        off, ln = r.ext.covered
+        live = [k for k in range(world) if live_mask == 0 or (live_mask >> k) & 1]
+        share = (d_pad // len(live)) // 4 * 4
+        idx = live.index(rank)
+        assert off == idx * share and ln == (share if idx < len(live) - 1 else d_pad - share * (len(live) - 1))
+        if len(live) == 1:
+            # the lone survivor's Gram is the full Gram: its aggregate must be the operator's
+            assert (off, ln) == (0, d_pad)
+            rows = [r._grads_t[i, :d].clone() for i in range(n)]
+            torch.testing.assert_close(r._agg_t[:d], mk().aggregate(rows), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("world,live_mask", [(1, 0), (2, 0), (8, 0), (4, 0b1011), (8, 0b00010001)])
+def test_bucket_launches_of_all_ranks_tile_the_arena_exactly_once(world, live_mask):
+    """``_launch_cw_bucket`` argument plumbing: over all live ranks and all buckets the (shard_off, shard_len) ranges
+    are disjoint, 16-byte aligned and cover the padded arena; every launch of a bucket carries the bucket's range and
+    the same sequence numbering."""
+    from byzpy_b200.parallel.device_ps import CwPlan, bucket_bounds
+
+    d_pad = 11_689_984
+    bounds = bucket_bounds([6_400_000, 2_700_000, 700_000], d_pad, 1 << 16)
+    assert bounds[0] == d_pad and bounds[-1] == 0 and len(bounds) == 5
+    seen = []
+
+    class Rec:
+        PAD_READY = 0
+
+        def fused_ps_cw(self, rows, scales, mode, f, nv, nh, va, vb, d, s_off, s_len, rank, agg, pads, epoch, epoch_ptr,
+                        counter, status, up, um, lr, mu, wd, sm, stream, grid_limit, rng_off, rng_len, nb, k, agg_mc,
+                        live, spin, trace):
+            assert s_off % 4 == 0 and s_len % 4 == 0 and rng_off <= s_off and s_off + s_len <= rng_off + rng_len
+            seen.append((rank, k, nb, rng_off, rng_len, s_off, s_len, live))
+
+    live = [r for r in range(world) if live_mask == 0 or (live_mask >> r) & 1]
+    for rank in live:
+        r = object.__new__(DeviceRound)
+        r.ext = Rec()
+        r.device = torch.device("cpu")
+        r.world, r.rank, r.live_mask = world, rank, live_mask
+        r.d_pad, r.sm = d_pad, 148
+        r.plan = CwPlan(0, 0)
+        r.layout = RowLayout(8, 0, 0, world, [0] * 8, list(range(8)))
+        r.virtual_fold = None
+        r._bounds = bounds
+        r._rows, r._scales = [16 * (i + 1) for i in range(8)], [1.0] * 8
+        r._off_agg = r._off_pad = 0
+        r.sym = types.SimpleNamespace(peer_ptr=lambda rk, off: 4096 * (rk + 1))
+        r.ctl = torch.zeros(8, dtype=torch.int32)
+        r._upd_params, r._upd_moms = [], []
+        r.lr, r.momentum, r.weight_decay, r._agg_mc, r.spin_seconds, r._trace = 0.1, 0.0, 0.0, 0, 0.0, None
+        r._round_launches = 0
+        import unittest.mock as mock
+
+        with mock.patch("torch.cuda.current_stream", return_value=types.SimpleNamespace(cuda_stream=0)):
+            for k in range(len(bounds) - 1):
+                r._launch_cw_bucket(k, 37)
+    cover = np.zeros(d_pad // 4, dtype=np.int32)
+    for rank, k, nb, rng_off, rng_len, s_off, s_len, lv in seen:
+        assert nb == len(bounds) - 1 and (rng_off, rng_len) == (bounds[k + 1], bounds[k] - bounds[k + 1]) and lv == live_mask
+        cover[s_off // 4: (s_off + s_len) // 4] += 1
+    assert cover.min() == 1 and cover.max() == 1
+    assert len(seen) == len(live) * (len(bounds) - 1)
