@@ -149,13 +149,13 @@ def test_pre_aggregator_with_coordinate_wise_aggregator_runs_fused(pre_name, agg
 @pytest.mark.parametrize("extra", [[], ["--aggregator", "multikrum", "--pre", "nnm"],
                                    ["--aggregator", "trmean", "--pre", "bucketing", "--timeline", "--buckets", "1"]])
 def test_device_example_runs_on_one_gpu(extra):
-    """examples/ps/device/resnet_fused.py end to end (tiny images, 6 rounds)."""
+    """examples/ps/device/resnet_fused.py end to end (64 x 64 images -- the shape smoke() uses -- 6 rounds)."""
     import os
     import subprocess
     import sys
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    cmd = [sys.executable, "examples/ps/device/resnet_fused.py", "--rounds", "6", "--image", "32", "--classes", "10",
+    cmd = [sys.executable, "examples/ps/device/resnet_fused.py", "--rounds", "6", "--image", "64", "--classes", "10",
            "--batch", "4"] + extra
     res = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=280,
                          env=dict(os.environ, PYTHONPATH=root, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0")))
