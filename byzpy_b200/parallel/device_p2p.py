@@ -348,8 +348,11 @@ class DeviceP2PRound:
         return self.losses
 
     def read_losses(self) -> torch.Tensor:
+        """Device->host read of the round's losses (synchronises the stream).  A flag barrier that timed out
+        (a peer that stopped taking part) raises here rather than letting a training loop run on stale rows."""
         self.losses_host.copy_(self.losses, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
+        self.check_status()
         return self.losses_host
 
     def check_status(self) -> None:
