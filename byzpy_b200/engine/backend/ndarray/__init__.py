@@ -6,22 +6,25 @@ from __future__ import annotations
 from typing import Any, Sequence
 
 import numpy as np
-import torch
+# NOT ``import torch``: this package has a submodule called ``torch`` (the reference's import path
+# ``engine.backend.ndarray.torch``), and importing a submodule rebinds the attribute of the same name on the
+# package -- i.e. this module's global -- to the SUBMODULE, after which every ``torch.stack`` below would fail
+import torch as _torch
 
 
 class _TorchBackend:
     name = "torch"
 
     def asarray(self, x: Any, like: Any = None):
-        if isinstance(like, torch.Tensor):
-            return torch.as_tensor(x, dtype=like.dtype, device=like.device)
-        return torch.as_tensor(x)
+        if isinstance(like, _torch.Tensor):
+            return _torch.as_tensor(x, dtype=like.dtype, device=like.device)
+        return _torch.as_tensor(x)
 
     def stack(self, xs: Sequence[Any], axis: int = 0):
-        return torch.stack(list(xs), dim=axis)
+        return _torch.stack(list(xs), dim=axis)
 
     def median(self, x, axis: int = 0):
-        return torch.median(x, dim=axis).values
+        return _torch.median(x, dim=axis).values
 
     def mean(self, x, axis=None):
         return x.mean() if axis is None else x.mean(dim=axis)
@@ -30,22 +33,22 @@ class _TorchBackend:
         return x.sum() if axis is None else x.sum(dim=axis)
 
     def sort(self, x, axis: int = 0):
-        return torch.sort(x, dim=axis).values
+        return _torch.sort(x, dim=axis).values
 
     def argsort(self, x, axis: int = -1):
-        return torch.argsort(x, dim=axis)
+        return _torch.argsort(x, dim=axis)
 
     def sqrt(self, x):
-        return torch.sqrt(x)
+        return _torch.sqrt(x)
 
     def maximum(self, a, b):
-        return torch.maximum(a, b)
+        return _torch.maximum(a, b)
 
     def minimum(self, a, b):
-        return torch.minimum(a, b)
+        return _torch.minimum(a, b)
 
     def abs(self, x):
-        return torch.abs(x)
+        return _torch.abs(x)
 
     def reshape(self, x, shape):
         return x.reshape(shape)
@@ -57,13 +60,13 @@ class _TorchBackend:
         return a @ b
 
     def index_select(self, x, axis: int, indices):
-        return torch.index_select(x, axis, torch.as_tensor(indices, device=x.device))
+        return _torch.index_select(x, axis, _torch.as_tensor(indices, device=x.device))
 
     def max(self, x, axis=None):
-        return x.max() if axis is None else torch.amax(x, dim=axis)
+        return x.max() if axis is None else _torch.amax(x, dim=axis)
 
     def take_along_axis(self, a, indices, axis: int = 0):
-        return torch.take_along_dim(a, torch.as_tensor(indices, device=a.device), dim=axis)
+        return _torch.take_along_dim(a, _torch.as_tensor(indices, device=a.device), dim=axis)
 
 
 class _NumpyBackend:

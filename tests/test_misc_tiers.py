@@ -483,3 +483,35 @@ def test_cli_subclass_discovery_skips_abstract_and_private():
     names = [q.rsplit(".", 1)[-1] for q in qualified]
     assert qualified == sorted(qualified) and "Aggregator" not in names and "GramAggregator" not in names
     assert len(names) >= 12
+
+
+def test_ndarray_backend_module_paths_and_protocol():
+    """The reference's import paths ``engine.backend.ndarray.{base,torch}`` (reference base.py:8-27,
+    torch.py:10-71) resolve, directly and through the ``byzpy`` alias, and both implementations satisfy the
+    16-primitive protocol."""
+    import importlib
+
+    import numpy as np
+
+    from byzpy_b200.compat import install_alias
+
+    install_alias()
+    nd_base = importlib.import_module("byzpy_b200.engine.backend.ndarray.base")
+    nd_numpy = importlib.import_module("byzpy_b200.engine.backend.ndarray.numpy")
+    nd_torch = importlib.import_module("byzpy_b200.engine.backend.ndarray.torch")
+    assert importlib.import_module("byzpy.engine.backend.ndarray.base")._Backend is nd_base._Backend
+    assert importlib.import_module("byzpy.engine.backend.ndarray.torch")._TorchBackend is nd_torch._TorchBackend
+    prims = [n for n in vars(nd_base._Backend) if not n.startswith("_") and callable(getattr(nd_base._Backend, n))]
+    assert len(prims) == 16
+    for impl, make in ((nd_torch._TorchBackend(), lambda v: torch.tensor(v)), (nd_numpy._NumpyBackend(), np.asarray)):
+        assert isinstance(impl, nd_base._Backend) and all(callable(getattr(impl, p)) for p in prims)
+        x = impl.stack([make([3.0, 1.0, 2.0]), make([0.0, 5.0, 4.0])], axis=0)
+        assert [float(v) for v in impl.median(x, axis=0)] == [0.0, 1.0, 2.0]                 # lower median of two rows
+        assert [float(v) for v in impl.sum(impl.maximum(x, impl.copy(x) * 0), axis=1)] == [6.0, 9.0]
+        assert [int(v) for v in impl.argsort(make([3.0, 1.0, 2.0]))] == [1, 2, 0]
+    # importing the submodule called ``torch`` rebinds the package attribute of that name; the package's own code
+    # must keep working afterwards (it refers to the library through a private alias)
+    from byzpy_b200.engine.backend.ndarray import get_array_backend
+
+    be = get_array_backend("torch")
+    assert be.stack([torch.ones(2), torch.zeros(2)]).shape == (2, 2)
