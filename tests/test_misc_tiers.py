@@ -515,3 +515,18 @@ def test_ndarray_backend_module_paths_and_protocol():
 
     be = get_array_backend("torch")
     assert be.stack([torch.ones(2), torch.zeros(2)]).shape == (2, 2)
+
+
+def test_cli_build_and_bench_subcommands(capsys):
+    """``byzpy-b200 build`` returns the in-tree extension (already built: nothing recompiles); ``byzpy-b200 bench``
+    forwards its arguments to bench.py, which on a box without a GPU says so and exits 1."""
+    from byzpy_b200 import cli
+
+    pytest.importorskip("byzpy_b200._C")
+    assert cli.main(["build"]) == 0
+    assert "_C" in capsys.readouterr().out
+    if not torch.cuda.is_available():            # bench.py refuses politely without a device (exit code 1)
+        assert cli.main(["bench", "--", "--steps", "1", "--warmup", "0"]) == 1
+    assert cli.main(["list", "attacks"]) == 0
+    out = capsys.readouterr().out
+    assert "byzpy_b200.attacks" in out and "SignFlipAttack" in out
