@@ -12,6 +12,12 @@ Differences by design:
   its own CUDA stream taken from a small pool, ordered after its producers by CUDA events
   instead of host-side waits, so independent branches overlap ON THE DEVICE (graph nodes map to
   streams rather than to thread/process actors).  Disable with ``metadata={"cuda_streams": False}``.
+  The side stream is made current around the node's ``run`` call, and "current stream" is a property of
+  the host THREAD: an operator whose ``compute`` is a coroutine that suspends (awaits I/O, another
+  actor, a message) hands the thread -- with the side stream still current -- to whichever node the
+  event loop resumes next.  Stream dispatch is therefore meant for operators that enqueue their device
+  work synchronously (every operator of this library does); give asynchronous operators host inputs or
+  switch the streams off for that graph.
 """
 from __future__ import annotations
 
