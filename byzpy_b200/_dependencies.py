@@ -30,4 +30,20 @@ def base_requirements():
     return ["torch>=2.6", "numpy>=1.24", "cloudpickle>=2.2", "tqdm>=4.65", "pybind11>=2.11"]
 
 
-__all__ = ["preferred_device", "base_requirements"]
+# The reference's packaging hooks (reference _dependencies.py:80-97).  There: cupy / ucxx wheels are added when a
+# GPU is detected.  Here the GPU path has no extra wheels (the kernels are compiled in-tree by nvcc, CUDA tensors
+# travel as CUDA-IPC handles), so the GPU list is empty and the full list does not depend on the machine.
+def get_dependencies():
+    return list(base_requirements())
+
+
+def get_gpu_optional_dependencies():
+    return []
+
+
+def get_dev_optional_dependencies():
+    return ["pytest>=8", "pytest-timeout", "hypothesis"]
+
+
+__all__ = ["preferred_device", "base_requirements", "get_dependencies", "get_gpu_optional_dependencies",
+           "get_dev_optional_dependencies"]

@@ -135,6 +135,56 @@ async def call(host: str, port: int, fn: Callable[[Endpoint], Awaitable[Any]]) -
             raise
 
 
+async def create_endpoint(host: str, port: int) -> Endpoint:
+    """A dedicated endpoint that bypasses the pool -- for a persistent one-to-one connection with a server
+    (reference transports/ucx.py:84-93)."""
+    return await asyncio.open_connection(host, int(port))
+
+
+async def create_listener(cb: Callable[[Endpoint], Any], *, host: str, port: int):
+    """Listen on ``host:port``; ``cb(endpoint)`` (plain function or coroutine function) is invoked per accepted
+    connection with its ``(reader, writer)`` endpoint and the connection is closed when it returns (reference
+    transports/ucx.py:136-160 wraps
+    ``ucxx.create_listener``).  Returns the ``asyncio`` server; ``port=0`` picks a free port
+    (``server.sockets[0].getsockname()[1]``)."""
+
+    async def _accept(reader: asyncio.StreamReader, writer: asyncio.StreamWriter) -> None:
+        try:
+            out = cb((reader, writer))
+            if asyncio.iscoroutine(out):
+                await out
+        except (asyncio.IncompleteReadError, ConnectionError):
+            pass                                   # the peer hung up in the middle of an exchange
+        finally:
+            writer.close()                         # the connection lives as long as its handler
+
+    return await asyncio.start_server(_accept, host, int(port))
+
+
+async def send_control(ep: Endpoint, obj: Dict[str, Any]) -> None:
+    """One length-prefixed control message on an endpoint (reference transports/ucx.py:210-214)."""
+    await send_obj(ep[1], obj)
+
+
+async def recv_control(ep: Endpoint) -> Dict[str, Any]:
+    return await recv_obj(ep[0])
+
+
+async def send_payload(ep: Endpoint, tag: str, desc: Any, obj: Any = None) -> None:
+    """Send what :func:`pack_payload` produced: ``tag`` is ``"cuda"`` (``desc`` = CUDA-IPC handles: the receiver
+    maps the sender's device memory, nothing else travels) or ``"pickle"`` (``desc`` = the by-value blob).  The
+    reference sends the device buffer itself after the descriptor (transports/ucx.py:245-254); on one NVSwitch box
+    the handle IS the transfer."""
+    if not isinstance(desc, (bytes, bytearray)):
+        tag, desc = pack_payload(obj if obj is not None else desc)
+    await send_control(ep, {"ptag": tag, "desc": bytes(desc)})
+
+
+async def recv_payload(ep: Endpoint) -> Any:
+    ctrl = await recv_control(ep)
+    return unpack_payload(ctrl["desc"])
+
+
 def pack_payload(obj: Any, *, same_host: bool = True) -> Tuple[str, bytes]:
     blob = cuda_ipc.dumps(obj, same_host=same_host)
     return ("cuda" if blob[:1] == b"I" else "pickle"), blob
@@ -174,5 +224,6 @@ async def chan_get(host: str, port: int, actor_id: str, name: str, timeout: Opti
     return out
 
 
-__all__ = ["have_ucx", "pack_payload", "unpack_payload", "get_endpoint", "evict_endpoint", "clear_pool", "call",
-           "request", "chan_put", "chan_get", "is_same_host"]
+__all__ = ["have_ucx", "pack_payload", "unpack_payload", "get_endpoint", "create_endpoint", "create_listener",
+           "evict_endpoint", "clear_pool", "call", "request", "send_control", "recv_control", "send_payload",
+           "recv_payload", "chan_put", "chan_get", "is_same_host"]
