@@ -134,6 +134,10 @@ class UCXRemoteActorServer(RemoteActorServer):
     scheme = "ucx"
     gpu_direct = True
 
+    def address(self) -> str:
+        """``host:port`` the server listens on (reference backends/gpu.py:490-491)."""
+        return f"{self.host}:{self.port}"
+
 
 async def start_ucx_actor_server(host: str, port: int) -> None:
     await UCXRemoteActorServer(host, port).serve()

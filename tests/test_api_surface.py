@@ -54,6 +54,35 @@ def test_every_reference_module_and_public_name_exists_here():
     assert checked > 150 and not missing, missing
 
 
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not available")
+def test_public_methods_and_constructor_parameters_of_every_reference_class_exist_here():
+    import inspect
+
+    from byzpy_b200.compat import install_alias
+
+    install_alias()
+    missing, classes = [], 0
+    for name, path in _reference_modules():
+        mod = importlib.import_module(name)
+        for node in ast.parse(open(path, encoding="utf-8").read()).body:
+            if not isinstance(node, ast.ClassDef) or node.name.startswith("_") or not hasattr(mod, node.name):
+                continue
+            ours = getattr(mod, node.name)
+            classes += 1
+            for m in node.body:
+                if not isinstance(m, (ast.FunctionDef, ast.AsyncFunctionDef)):
+                    continue
+                if m.name == "__init__":
+                    want = [a.arg for a in m.args.args[1:]] + [a.arg for a in m.args.kwonlyargs]
+                    sig = inspect.signature(ours.__init__)
+                    if any(p.kind is p.VAR_KEYWORD for p in sig.parameters.values()):
+                        continue
+                    missing += [f"{name}.{node.name}(…{p}=)" for p in want if p not in sig.parameters]
+                elif not m.name.startswith("_") and not hasattr(ours, m.name):
+                    missing.append(f"{name}.{node.name}.{m.name}")
+    assert classes > 90 and not missing, missing
+
+
 def test_ucx_transport_listener_endpoint_control_and_payload_helpers():
     """The reference's UCX helper surface (create_listener / create_endpoint / send_control / recv_control /
     send_payload / recv_payload, reference transports/ucx.py:84-277) on stream endpoints."""
