@@ -14,8 +14,14 @@ from ..engine.backend.ndarray import get_array_backend
 _current = "torch"
 
 
-def set_backend(name: str) -> None:
+def set_backend(backend) -> None:
+    """``backend``: ``"torch"`` / ``"pytorch"`` / ``"numpy"``, or a backend object (anything with a ``name``
+    attribute naming one of them; reference configs/backend.py:12-29 takes the same two forms)."""
     global _current
+    name = backend if isinstance(backend, str) else getattr(backend, "name", None)
+    if not isinstance(name, str):
+        raise TypeError("backend must be a string or implement the _Backend protocol")
+    name = {"pytorch": "torch"}.get(name.lower(), name.lower())
     get_array_backend(name)  # validates
     _current = name
 
@@ -25,10 +31,10 @@ def get_backend():
 
 
 @contextmanager
-def use_backend(name: str) -> Iterator[None]:
+def use_backend(backend) -> Iterator[None]:
     global _current
     prev = _current
-    set_backend(name)
+    set_backend(backend)
     try:
         yield
     finally:

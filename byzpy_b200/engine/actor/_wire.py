@@ -21,14 +21,14 @@ def encode(obj: Any) -> bytes:
     return _HDR.pack(len(body)) + body
 
 
-async def send_obj(writer: asyncio.StreamWriter, obj: Any) -> None:
-    writer.write(encode(obj))
-    await writer.drain()
+async def send_obj(w: asyncio.StreamWriter, obj: Any) -> None:
+    w.write(encode(obj))
+    await w.drain()
 
 
-async def recv_obj(reader: asyncio.StreamReader) -> Any:
-    (n,) = _HDR.unpack(await reader.readexactly(_HDR.size))
-    return cloudpickle.loads(await reader.readexactly(n))
+async def recv_obj(r: asyncio.StreamReader) -> Any:
+    (n,) = _HDR.unpack(await r.readexactly(_HDR.size))
+    return cloudpickle.loads(await r.readexactly(n))
 
 
 __all__ = ["send_obj", "recv_obj", "encode"]

@@ -29,11 +29,33 @@ async def request(host: str, port: int, msg: dict, timeout: Optional[float] = No
     return reply.get("payload") if isinstance(reply, dict) else reply
 
 
-async def chan_put(host: str, port: int, actor_id: str, name: str, payload: Any) -> None:
-    await request(host, port, {"op": "chan_put", "actor_id": actor_id, "name": name, "payload": payload})
+def _target(address, port, actor_id, to_ep):
+    """(host, port, actor id) from either calling convention: ``(host, port, actor_id, ...)`` as used inside this
+    package, or the reference's ``(address, *, to_ep=..., ...)`` with ``address = "host:port"`` (reference
+    transports/tcp.py:27-67)."""
+    if port is None:
+        host, port = parse_address(address)
+    else:
+        host = address
+    if actor_id is None and to_ep is not None:
+        actor_id = to_ep["actor_id"] if isinstance(to_ep, dict) else getattr(to_ep, "actor_id")
+    if actor_id is None:
+        raise TypeError("an actor id (or to_ep) is required")
+    return host, int(port), actor_id
 
 
-async def chan_get(host: str, port: int, actor_id: str, name: str, timeout: Optional[float]) -> Any:
+async def chan_put(address: str, port: Optional[int] = None, actor_id: Optional[str] = None, name: Optional[str] = None,
+                   payload: Any = None, *, from_ep: Any = None, to_ep: Any = None) -> None:
+    host, port, actor_id = _target(address, port, actor_id, to_ep)
+    msg = {"op": "chan_put", "actor_id": actor_id, "name": name, "payload": payload}
+    if to_ep is not None and not isinstance(to_ep, dict):
+        msg["to"] = (to_ep.scheme, to_ep.address, to_ep.actor_id)
+    await request(host, port, msg)
+
+
+async def chan_get(address: str, port: Optional[int] = None, actor_id: Optional[str] = None, name: Optional[str] = None,
+                   timeout: Optional[float] = None) -> Any:
+    host, port, actor_id = _target(address, port, actor_id, None)
     return await request(host, port, {"op": "chan_get", "actor_id": actor_id, "name": name,
                                       "timeout": timeout},
                          timeout=None if timeout is None else timeout + 5.0)

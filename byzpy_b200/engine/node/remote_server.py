@@ -131,7 +131,16 @@ class RemoteNodeServer:
         out.update({f"conn-{id(w):x}": w for w in self._writers if id(w) not in named})
         return out
 
-    async def send_message_to_client(self, node_id, msg: Dict[str, Any]) -> None:
+    async def send_message_to_client(self, client_writer, from_node_id=None, message_type: Optional[str] = None,
+                                     payload: Any = None) -> None:
+        """Two calling conventions: ``(node_id, message_dict)`` -- used inside this package, the registered
+        client of that node id is looked up -- and the reference's ``(client_writer, from_node_id, message_type,
+        payload)`` with the client's ``StreamWriter`` (reference engine/node/remote_server.py:226-250)."""
+        if isinstance(client_writer, asyncio.StreamWriter) or hasattr(client_writer, "drain"):
+            await write_frame(client_writer, {"from": from_node_id, "type": message_type, "payload": payload},
+                              gpu_direct=self.gpu_direct)
+            return
+        node_id, msg = client_writer, from_node_id
         writer = self._clients.get(node_id)
         if writer is None or writer.is_closing():
             raise ValueError(f"Target node {node_id} not found on server or among clients")

@@ -126,3 +126,112 @@ def test_dependency_hooks():
 
     assert d.get_gpu_optional_dependencies() == [] and any(x.startswith("torch") for x in d.get_dependencies())
     assert any("pytest" in x for x in d.get_dev_optional_dependencies())
+
+
+def _ref_params(fn_node, drop_first):
+    a = fn_node.args
+    pos = [x.arg for x in a.posonlyargs + a.args]
+    if drop_first and pos and pos[0] in ("self", "cls"):
+        pos = pos[1:]
+    return pos, [x.arg for x in a.kwonlyargs]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not available")
+def test_parameters_of_every_public_function_and_method_of_the_reference_are_accepted_here():
+    """Every parameter NAME of the reference's public functions and methods exists here (extra parameters with
+    defaults are fine), and the shared positional parameters come in the same order."""
+    import inspect
+
+    from byzpy_b200.compat import install_alias
+
+    install_alias()
+    diffs, compared = [], 0
+
+    def compare(qual, node, ours, drop_first):
+        nonlocal compared
+        try:
+            sig = inspect.signature(ours)
+        except (TypeError, ValueError):
+            return
+        compared += 1
+        pos, kwo = _ref_params(node, drop_first)
+        ps = list(sig.parameters.values())
+        if drop_first and ps and ps[0].name in ("self", "cls"):
+            ps = ps[1:]
+        names = [p.name for p in ps]
+        var_kw = any(p.kind is p.VAR_KEYWORD for p in ps)
+        var_pos = any(p.kind is p.VAR_POSITIONAL for p in ps)
+        lacking = [p for p in pos + kwo if p not in names]
+        if lacking and not var_kw and not (var_pos and not kwo):
+            diffs.append((qual, "missing", lacking))
+            return
+        ours_pos = [p.name for p in ps if p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD)]
+        common = [p for p in pos if p in ours_pos]
+        if not var_pos and [p for p in ours_pos if p in common] != common:
+            diffs.append((qual, "order", pos, ours_pos))
+
+    for name, path in _reference_modules():
+        mod = importlib.import_module(name)
+        for node in ast.parse(open(path, encoding="utf-8").read()).body:
+            if isinstance(node, (ast.FunctionDef, ast.AsyncFunctionDef)) and not node.name.startswith("_") \
+                    and hasattr(mod, node.name):
+                compare(f"{name}.{node.name}", node, getattr(mod, node.name), False)
+            if isinstance(node, ast.ClassDef) and not node.name.startswith("_") and hasattr(mod, node.name):
+                cls = getattr(mod, node.name)
+                for m in node.body:
+                    if not isinstance(m, (ast.FunctionDef, ast.AsyncFunctionDef)) or m.name.startswith("_") \
+                            or not hasattr(cls, m.name):
+                        continue
+                    raw = inspect.getattr_static(cls, m.name)
+                    if isinstance(raw, property) or any(isinstance(d, ast.Name) and d.id == "property"
+                                                        for d in m.decorator_list):
+                        continue
+                    bound = inspect.ismethod(getattr(cls, m.name))           # classmethod: cls already bound
+                    is_static = isinstance(raw, staticmethod)
+                    ref_is_plain = not any(isinstance(d, ast.Name) and d.id in ("staticmethod",)
+                                           for d in m.decorator_list)
+                    node2 = m
+                    if ref_is_plain and (bound or is_static):
+                        node2 = ast.FunctionDef(name=m.name, args=ast.arguments(
+                            posonlyargs=[], args=m.args.args[1:], vararg=m.args.vararg, kwonlyargs=m.args.kwonlyargs,
+                            kw_defaults=m.args.kw_defaults, kwarg=m.args.kwarg, defaults=[]), body=[], decorator_list=[])
+                    compare(f"{name}.{node.name}.{m.name}", node2, getattr(cls, m.name),
+                            not (bound or is_static) and ref_is_plain)
+    assert compared > 300 and not diffs, diffs
+
+
+def test_low_level_helpers_accept_the_reference_calling_conventions():
+    import asyncio
+
+    import torch
+
+    from byzpy_b200.configs.backend import get_backend, set_backend, use_backend
+    from byzpy_b200.engine.actor.backends.remote import RemoteActorServer
+    from byzpy_b200.engine.actor.channels import Endpoint
+    from byzpy_b200.engine.actor.transports import tcp
+
+    set_backend(backend="numpy")
+    assert get_backend().name == "numpy"
+    with use_backend(backend="pytorch"):
+        assert get_backend().name == "torch"
+    set_backend(get_backend())                       # a backend object is accepted too
+    set_backend("torch")
+    with pytest.raises(ValueError):
+        set_backend("jax")
+
+    async def scenario():
+        srv = RemoteActorServer("127.0.0.1", 0)
+        await srv.start()
+        try:
+            ep = Endpoint("tcp", f"127.0.0.1:{srv.port}", "box-owner")
+            # the reference's convention: address string + keyword endpoints
+            await tcp.chan_put(f"127.0.0.1:{srv.port}", from_ep=None, to_ep=ep, name="inbox", payload={"x": torch.ones(2)})
+            got = await tcp.chan_get(f"127.0.0.1:{srv.port}", name="inbox", timeout=2.0, actor_id="box-owner")
+            assert torch.equal(got["x"], torch.ones(2))
+            # this package's convention
+            await tcp.chan_put("127.0.0.1", srv.port, "box-owner", "inbox", 5)
+            assert await tcp.chan_get("127.0.0.1", srv.port, "box-owner", "inbox", 2.0) == 5
+        finally:
+            await srv.stop()
+
+    asyncio.run(scenario())
