@@ -24,6 +24,7 @@ def _span(start: int, end: int):
 
 class GaussianAttack(Attack):
     name = "gaussian"
+    max_subtasks_inflight = 0       # 0 / None: the pool-sized default window (value of the reference class)
     uses_honest_grads = True
     supports_subtasks = True
 

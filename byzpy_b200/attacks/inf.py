@@ -18,6 +18,7 @@ def _inf_chunk(start: int, end: int, device: str):
 
 class InfAttack(Attack):
     name = "inf"
+    max_subtasks_inflight = 0       # 0 / None: the pool-sized default window (value of the reference class)
     uses_honest_grads = True
     supports_subtasks = True
 

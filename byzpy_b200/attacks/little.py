@@ -25,6 +25,7 @@ def _ndtri(p: float) -> float:
 
 class LittleAttack(ColumnStatAttack):
     name = "little"
+    max_subtasks_inflight = 0       # 0 / None: the pool-sized default window (value of the reference class)
 
     def __init__(self, f: int, N: Optional[int] = None, *, chunk_size: int = 8192) -> None:
         if f < 0:

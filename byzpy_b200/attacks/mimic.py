@@ -17,6 +17,7 @@ def _copy_chunk(vec: torch.Tensor, start: int, end: int):
 
 class MimicAttack(Attack):
     name = "mimic"
+    max_subtasks_inflight = 0       # 0 / None: the pool-sized default window (value of the reference class)
     uses_honest_grads = True
     supports_subtasks = True
 

@@ -18,6 +18,7 @@ def _scale_chunk(vec: torch.Tensor, start: int, end: int, scale: float):
 
 class SignFlipAttack(Attack):
     name = "sign-flip"
+    max_subtasks_inflight = 0       # 0 / None: the pool-sized default window (value of the reference class)
     uses_base_grad = True
     supports_subtasks = True
 

@@ -23,7 +23,7 @@ from ..engine.graph.subtask import SubTask
 
 
 class PreAggregator(Operator, ABC):
-    name = "pre-aggregator"
+    name = "pre_aggregator"
     input_key = "vectors"
 
     def compute(self, inputs: Mapping[str, Any], *, context: OpContext) -> Any:

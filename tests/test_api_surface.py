@@ -235,3 +235,42 @@ def test_low_level_helpers_accept_the_reference_calling_conventions():
             await srv.stop()
 
     asyncio.run(scenario())
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not available")
+def test_class_level_attributes_of_the_reference_exist_with_the_same_literal_values():
+    """``name``, ``supports_subtasks``, ``input_key``, ``max_subtasks_inflight`` ...: every public class attribute the
+    reference assigns in a class body exists here; where it is a literal, the value is the same."""
+    from byzpy_b200.compat import install_alias
+
+    install_alias()
+    problems, seen = [], 0
+    dataclass_fields = {("SubTask", "args"), ("SubTask", "kwargs"), ("GraphNode", "inputs")}      # default_factory fields
+    for name, path in _reference_modules():
+        mod = importlib.import_module(name)
+        for node in ast.parse(open(path, encoding="utf-8").read()).body:
+            if not isinstance(node, ast.ClassDef) or node.name.startswith("_") or not hasattr(mod, node.name):
+                continue
+            cls = getattr(mod, node.name)
+            for m in node.body:
+                if isinstance(m, ast.Assign):
+                    targets, value = [t.id for t in m.targets if isinstance(t, ast.Name)], m.value
+                elif isinstance(m, ast.AnnAssign) and isinstance(m.target, ast.Name) and m.value is not None:
+                    targets, value = [m.target.id], m.value
+                else:
+                    continue
+                for t in targets:
+                    if t.startswith("_") or (node.name, t) in dataclass_fields:
+                        continue
+                    seen += 1
+                    if not hasattr(cls, t):
+                        problems.append(f"{name}.{node.name}.{t} missing")
+                        continue
+                    try:
+                        want = ast.literal_eval(value)
+                    except (ValueError, SyntaxError):
+                        continue
+                    have = getattr(cls, t)
+                    if not callable(have) and have != want:
+                        problems.append(f"{name}.{node.name}.{t}: {have!r} != {want!r}")
+    assert seen > 80 and not problems, problems
