@@ -134,12 +134,17 @@ class UCXRemoteActorServer(RemoteActorServer):
     scheme = "ucx"
     gpu_direct = True
 
+    def __init__(self, host: str = "127.0.0.1", port: int = 0) -> None:
+        # port 0 = an ephemeral port, as in the reference (backends/gpu.py:470-480); the host default stays the
+        # loopback interface (the reference listens on 0.0.0.0 and unpickles whatever connects)
+        super().__init__(host, port)
+
     def address(self) -> str:
         """``host:port`` the server listens on (reference backends/gpu.py:490-491)."""
         return f"{self.host}:{self.port}"
 
 
-async def start_ucx_actor_server(host: str, port: int) -> None:
+async def start_ucx_actor_server(host: str = "127.0.0.1", port: int = 0) -> None:
     await UCXRemoteActorServer(host, port).serve()
 
 

@@ -18,7 +18,7 @@ def _wants_round(fn: Callable[..., Any]) -> bool:
 
 
 async def train_with_progress(ps, rounds: int, eval_callback: Optional[EvalFn] = None,
-                              eval_interval: int = 50, *, desc: str = "training") -> List[Dict[str, Any]]:
+                              eval_interval: int = 1, *, desc: str = "training") -> List[Dict[str, Any]]:
     """Run ``rounds`` rounds of ``ps`` under a progress bar.  Every ``eval_interval`` rounds
     ``eval_callback(round_number)`` (sync or async; a zero-argument callable is accepted too) is evaluated,
     its metrics dict shown on the bar and appended to the returned history as

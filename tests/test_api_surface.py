@@ -274,3 +274,62 @@ def test_class_level_attributes_of_the_reference_exist_with_the_same_literal_val
                     if not callable(have) and have != want:
                         problems.append(f"{name}.{node.name}.{t}: {have!r} != {want!r}")
     assert seen > 80 and not problems, problems
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not available")
+def test_default_argument_values_match_the_reference():
+    """Literal defaults of constructor / function / method parameters (chunk sizes, tolerances, iteration counts,
+    ``eval_interval`` ...).  One deliberate difference: servers listen on the loopback interface by default (the
+    reference binds 0.0.0.0 and unpickles whatever connects)."""
+    import inspect
+
+    from byzpy_b200.compat import install_alias
+
+    install_alias()
+    allowed = {("byzpy.engine.actor.backends.gpu.UCXRemoteActorServer.__init__", "host"),
+               ("byzpy.engine.actor.backends.gpu.start_ucx_actor_server", "host")}
+    diffs, compared = [], 0
+
+    def ref_defaults(fn):
+        a = fn.args
+        pos = a.posonlyargs + a.args
+        pairs = list(zip(pos[len(pos) - len(a.defaults):], a.defaults)) + \
+            [(k, d) for k, d in zip(a.kwonlyargs, a.kw_defaults) if d is not None]
+        out = {}
+        for arg, d in pairs:
+            try:
+                out[arg.arg] = ast.literal_eval(d)
+            except (ValueError, SyntaxError):
+                pass
+        return out
+
+    def compare(qual, node, ours):
+        nonlocal compared
+        try:
+            sig = inspect.signature(ours)
+        except (TypeError, ValueError):
+            return
+        for k, v in ref_defaults(node).items():
+            p = sig.parameters.get(k)
+            if p is None or (qual, k) in allowed:
+                continue
+            compared += 1
+            if p.default is inspect.Parameter.empty:
+                diffs.append(f"{qual}({k}): required here, default {v!r} in the reference")
+            elif p.default != v:
+                diffs.append(f"{qual}({k}={p.default!r}) != {v!r}")
+
+    for name, path in _reference_modules():
+        mod = importlib.import_module(name)
+        for node in ast.parse(open(path, encoding="utf-8").read()).body:
+            if isinstance(node, (ast.FunctionDef, ast.AsyncFunctionDef)) and not node.name.startswith("_") \
+                    and hasattr(mod, node.name):
+                compare(f"{name}.{node.name}", node, getattr(mod, node.name))
+            if isinstance(node, ast.ClassDef) and not node.name.startswith("_") and hasattr(mod, node.name):
+                cls = getattr(mod, node.name)
+                for m in node.body:
+                    if isinstance(m, (ast.FunctionDef, ast.AsyncFunctionDef)) and hasattr(cls, m.name) \
+                            and (m.name == "__init__" or not m.name.startswith("_")) \
+                            and not isinstance(inspect.getattr_static(cls, m.name), property):
+                        compare(f"{name}.{node.name}.{m.name}", m, getattr(cls, m.name))
+    assert compared > 180 and not diffs, diffs
