@@ -23,9 +23,16 @@ class _AliasLoader(importlib.abc.Loader):
         self.real_name = real_name
 
     def create_module(self, spec):
-        return importlib.import_module(self.real_name)
+        module = importlib.import_module(self.real_name)
+        self._real_spec = getattr(module, "__spec__", None)
+        return module
 
     def exec_module(self, module):  # already executed under its real name
+        # importlib has just stamped the ALIAS spec on the (shared) module object; with it, ``__spec__.parent``
+        # (``byzpy...``) no longer matches ``__package__`` (``byzpy_b200...``) and every later relative import
+        # inside the module warns (an error from Python 3.15 on).  The module keeps its own identity.
+        if self._real_spec is not None:
+            module.__spec__ = self._real_spec
         return None
 
 
