@@ -32,3 +32,25 @@ def run_async(coro):
     import asyncio
 
     return asyncio.run(coro)
+
+
+@pytest.fixture
+def byzpy_alias():
+    """``import byzpy...`` resolves to THIS package for the duration of the test, whatever earlier tests left in
+    ``sys.modules`` (the parity tests import the real reference from ``baseline/_ref`` under the same name): the
+    real modules are set aside, the alias is installed, and both are put back afterwards."""
+    from byzpy_b200 import compat
+
+    saved = {k: v for k, v in sys.modules.items() if k == "byzpy" or k.startswith("byzpy.")}
+    for k in saved:
+        del sys.modules[k]
+    had_alias = compat._finder is not None
+    compat.install_alias()
+    try:
+        yield compat
+    finally:
+        if not had_alias:
+            compat.uninstall_alias()
+        for k in [k for k in sys.modules if k == "byzpy" or k.startswith("byzpy.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)

@@ -38,10 +38,7 @@ def _public_names(path):
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not available")
-def test_every_reference_module_and_public_name_exists_here():
-    from byzpy_b200.compat import install_alias
-
-    install_alias()
+def test_every_reference_module_and_public_name_exists_here(byzpy_alias):
     modules = list(_reference_modules())
     assert len(modules) > 80
     missing, checked = [], 0
@@ -55,12 +52,9 @@ def test_every_reference_module_and_public_name_exists_here():
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not available")
-def test_public_methods_and_constructor_parameters_of_every_reference_class_exist_here():
+def test_public_methods_and_constructor_parameters_of_every_reference_class_exist_here(byzpy_alias):
     import inspect
 
-    from byzpy_b200.compat import install_alias
-
-    install_alias()
     missing, classes = [], 0
     for name, path in _reference_modules():
         mod = importlib.import_module(name)
@@ -137,14 +131,11 @@ def _ref_params(fn_node, drop_first):
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not available")
-def test_parameters_of_every_public_function_and_method_of_the_reference_are_accepted_here():
+def test_parameters_of_every_public_function_and_method_of_the_reference_are_accepted_here(byzpy_alias):
     """Every parameter NAME of the reference's public functions and methods exists here (extra parameters with
     defaults are fine), and the shared positional parameters come in the same order."""
     import inspect
 
-    from byzpy_b200.compat import install_alias
-
-    install_alias()
     diffs, compared = [], 0
 
     def compare(qual, node, ours, drop_first):
@@ -238,12 +229,9 @@ def test_low_level_helpers_accept_the_reference_calling_conventions():
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not available")
-def test_class_level_attributes_of_the_reference_exist_with_the_same_literal_values():
+def test_class_level_attributes_of_the_reference_exist_with_the_same_literal_values(byzpy_alias):
     """``name``, ``supports_subtasks``, ``input_key``, ``max_subtasks_inflight`` ...: every public class attribute the
     reference assigns in a class body exists here; where it is a literal, the value is the same."""
-    from byzpy_b200.compat import install_alias
-
-    install_alias()
     problems, seen = [], 0
     dataclass_fields = {("SubTask", "args"), ("SubTask", "kwargs"), ("GraphNode", "inputs")}      # default_factory fields
     for name, path in _reference_modules():
@@ -277,15 +265,12 @@ def test_class_level_attributes_of_the_reference_exist_with_the_same_literal_val
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not available")
-def test_default_argument_values_match_the_reference():
+def test_default_argument_values_match_the_reference(byzpy_alias):
     """Literal defaults of constructor / function / method parameters (chunk sizes, tolerances, iteration counts,
     ``eval_interval`` ...).  One deliberate difference: servers listen on the loopback interface by default (the
     reference binds 0.0.0.0 and unpickles whatever connects)."""
     import inspect
 
-    from byzpy_b200.compat import install_alias
-
-    install_alias()
     allowed = {("byzpy.engine.actor.backends.gpu.UCXRemoteActorServer.__init__", "host"),
                ("byzpy.engine.actor.backends.gpu.start_ucx_actor_server", "host")}
     diffs, compared = [], 0

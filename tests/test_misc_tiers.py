@@ -485,7 +485,7 @@ def test_cli_subclass_discovery_skips_abstract_and_private():
     assert len(names) >= 12
 
 
-def test_ndarray_backend_module_paths_and_protocol():
+def test_ndarray_backend_module_paths_and_protocol(byzpy_alias):
     """The reference's import paths ``engine.backend.ndarray.{base,torch}`` (reference base.py:8-27,
     torch.py:10-71) resolve, directly and through the ``byzpy`` alias, and both implementations satisfy the
     16-primitive protocol."""
@@ -493,9 +493,6 @@ def test_ndarray_backend_module_paths_and_protocol():
 
     import numpy as np
 
-    from byzpy_b200.compat import install_alias
-
-    install_alias()
     nd_base = importlib.import_module("byzpy_b200.engine.backend.ndarray.base")
     nd_numpy = importlib.import_module("byzpy_b200.engine.backend.ndarray.numpy")
     nd_torch = importlib.import_module("byzpy_b200.engine.backend.ndarray.torch")
