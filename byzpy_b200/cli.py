@@ -142,6 +142,12 @@ def _cmd_list(args: argparse.Namespace) -> int:
         from .pre_aggregators.base import PreAggregator as base
 
         items = _load_subclasses("byzpy_b200.pre_aggregators", base)
+    from . import compat
+
+    if compat._finder is not None:
+        # the ``byzpy`` import alias is active (``python -m byzpy.cli``, or a program that installed it): print the
+        # names the way that program can import them
+        items = sorted("byzpy" + name[len("byzpy_b200"):] for name in items)
     if args.short:
         items = sorted({name.rsplit(".", 1)[-1] for name in items})
     if args.format == "json":
