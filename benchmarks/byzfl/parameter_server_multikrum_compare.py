@@ -5,11 +5,11 @@ the "ByzFL 57 ms" column of benchmarks/README.md:23).
 
 Both arms train SmallCNN on the same in-memory MNIST-shaped tensors (real MNIST when ``--data-root``
 holds a copy, otherwise ``utils.data.mnist_like``'s synthetic stand-in -- the build image has no network),
-``--honest`` honest clients and ``--byzantine`` Byzantine ones (Empire here, SignFlipping in ByzFL), SGD with ``--lr``, for ``--rounds``
+``--num-honest`` honest clients and ``--num-byz`` Byzantine ones (Empire here, SignFlipping in ByzFL), SGD with ``--lr``, for ``--rounds``
 rounds; the report is total and per-round milliseconds.  ByzFL is not installable offline: its arm
 then reads ``unavailable``.
 
-    python benchmarks/byzfl/parameter_server_multikrum_compare.py --rounds 50 --honest 10 --byzantine 3
+    python benchmarks/byzfl/parameter_server_multikrum_compare.py --rounds 50 --num-honest 10 --num-byz 3 --f 3
 """
 from __future__ import annotations
 
@@ -39,7 +39,7 @@ async def ours(a) -> dict:
                                                    lr=a.lr))
            for i in range(a.honest)]
     byz = [await ByzantineNodeActor.spawn(DistributedPSByzNode, backend="thread") for _ in range(a.byzantine)]
-    ps = ParameterServer(hon, byz, MultiKrum(f=a.byzantine, q=a.honest - a.byzantine))
+    ps = ParameterServer(hon, byz, MultiKrum(f=a.f, q=max(1, a.honest + a.byzantine - a.f - 1)))
     await ps.round()
     t0 = time.perf_counter()
     for _ in range(a.rounds):
@@ -64,7 +64,7 @@ def theirs(a) -> dict:
               "LabelFlipping": False, "momentum": 0.0, "nb_labels": 10}
     clients = [Client({**common, "training_dataloader": ld}) for ld in loaders]
     server = Server({**common, "test_loader": None, "validation_loader": None,
-                     "aggregator_info": {"name": "MultiKrum", "parameters": {"f": a.byzantine}},
+                     "aggregator_info": {"name": "MultiKrum", "parameters": {"f": a.f}},
                      "pre_agg_list": []})
     attacker = ByzantineClient({"name": "SignFlipping", "f": a.byzantine, "parameters": {}})
 
@@ -88,14 +88,16 @@ def theirs(a) -> dict:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--rounds", type=int, default=50)
-    ap.add_argument("--honest", type=int, default=10)
-    ap.add_argument("--byzantine", type=int, default=3)
+    ap.add_argument("--num-honest", "--honest", dest="honest", type=int, default=10)
+    ap.add_argument("--num-byz", "--byzantine", dest="byzantine", type=int, default=3)
     ap.add_argument("--batch-size", type=int, default=64)
-    ap.add_argument("--lr", type=float, default=0.05)
+    ap.add_argument("--lr", type=float, default=0.1)
+    ap.add_argument("--f", type=int, default=None, help="Multi-Krum f (default: --num-byz)")
     ap.add_argument("--samples", type=int, default=6000)
-    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--data-root", default="./data")
     a = ap.parse_args()
+    a.f = a.byzantine if a.f is None else a.f
     out = {"rounds": a.rounds, "honest": a.honest, "byzantine": a.byzantine, "batch_size": a.batch_size,
            "byzpy_b200": asyncio.run(ours(a)), "byzfl": theirs(a)}
     print(json.dumps(out))

@@ -3,16 +3,43 @@ benchmarks/pytorch/_worker_args.py:6-38): a comma separated list of worker count
 which may itself be a comma separated mix, e.g. ``thread,process,tcp://host:29000``."""
 from __future__ import annotations
 
-from typing import List
+import argparse
+from typing import List, Sequence
 
 from byzpy_b200.engine.graph.pool import ActorPoolConfig
 
 
+DEFAULT_WORKER_COUNTS = (2, 4, 6)
+
+
 def parse_worker_counts(spec: str) -> List[int]:
-    out = [int(x) for x in str(spec).split(",") if x.strip()]
+    """``"2,4,6"`` / ``"2 4 6"`` -> [2, 4, 6]."""
+    try:
+        out = [int(x) for x in str(spec).replace(",", " ").split()]
+    except ValueError:
+        raise argparse.ArgumentTypeError(f"bad worker count in {spec!r}") from None
     if not out or any(k < 1 for k in out):
-        raise ValueError(f"bad --pool-workers {spec!r}")
+        raise argparse.ArgumentTypeError(f"bad --pool-workers {spec!r} (example: 2,4,6)")
     return out
+
+
+def coerce_worker_counts(value) -> List[int]:
+    """A worker specification as it may sit in a namespace -- a string, one int, or a sequence of either -- as a
+    list of ints."""
+    if isinstance(value, str):
+        return parse_worker_counts(value)
+    if isinstance(value, int):
+        return [value]
+    if isinstance(value, Sequence):
+        out: List[int] = []
+        for v in value:
+            if not isinstance(v, (int, str)):
+                raise TypeError(f"unsupported worker count entry {v!r}")
+            out.extend(coerce_worker_counts(v))
+        if not out:
+            raise ValueError("empty worker count list")
+        return out
+    raise TypeError(f"cannot read worker counts from {value!r}")
 
 
 def pool_configs(backend_spec: str, count: int) -> List[ActorPoolConfig]:

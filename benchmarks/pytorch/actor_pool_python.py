@@ -1,7 +1,11 @@
 """Pure-Python CPU-bound operator on an ActorPool: shows process-pool scaling where the thread backend
 is GIL-bound (counterpart of the reference's benchmarks/pytorch/actor_pool_python.py).
 
-    python benchmarks/pytorch/actor_pool_python.py --tasks 16 --work 200000 --pool-workers 1,2,4 --pool-backend process
+    python benchmarks/pytorch/actor_pool_python.py --tasks 5000 --inner-iters 2000 --chunk-size 250 \
+        --pool-workers 1,2,4 --pool-backend process
+
+``--tasks`` work items of ``--inner-iters`` loop iterations each, ``--chunk-size`` items per subtask (the reference's
+flags and defaults; ``--work`` is the older name of ``--inner-iters``).
 """
 from __future__ import annotations
 
@@ -9,6 +13,7 @@ import argparse
 import asyncio
 import json
 import os
+import random
 import sys
 import time
 
@@ -29,18 +34,24 @@ def burn(seed: int, work: int) -> int:
     return x
 
 
+def burn_many(seeds, work: int) -> int:
+    return sum(burn(s, work) for s in seeds)
+
+
 class BurnOp(Operator):
     name = "python-burn"
     supports_subtasks = True
 
-    def __init__(self, tasks: int, work: int):
-        self.tasks, self.work = tasks, work
+    def __init__(self, work: int, chunk_size: int = 1):
+        self.work, self.chunk_size = max(1, work), max(1, chunk_size)
 
     def compute(self, inputs, *, context: OpContext):
-        return sum(burn(i, self.work) for i in range(self.tasks))
+        return burn_many(inputs["x"], self.work)
 
     def create_subtasks(self, inputs, *, context: OpContext):
-        return [SubTask(fn=burn, args=(i, self.work), name=f"burn{i}") for i in range(self.tasks)]
+        seeds = list(inputs["x"])
+        return [SubTask(fn=burn_many, args=(seeds[i:i + self.chunk_size], self.work), name=f"burn{i}")
+                for i in range(0, len(seeds), self.chunk_size)]
 
     def reduce_subtasks(self, partials, inputs, *, context: OpContext):
         return sum(partials)
@@ -48,26 +59,32 @@ class BurnOp(Operator):
 
 async def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--tasks", type=int, default=16)
-    ap.add_argument("--work", type=int, default=200000)
-    ap.add_argument("--pool-workers", default="1,2,4")
+    ap.add_argument("--tasks", type=int, default=5000)
+    ap.add_argument("--inner-iters", "--work", dest="inner_iters", type=int, default=2000)
+    ap.add_argument("--chunk-size", type=int, default=250)
+    ap.add_argument("--pool-workers", default="2,4,6")
     ap.add_argument("--pool-backend", default="process")
-    ap.add_argument("--repeat", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--repeat", type=int, default=3)
+    ap.add_argument("--seed", type=int, default=0)
     a = ap.parse_args()
-    graph = make_single_operator_graph(node_name="burn", operator=BurnOp(a.tasks, a.work), input_keys=("x",))
-    out = {"tasks": a.tasks, "work": a.work, "backend": a.pool_backend}
+    payload = {"x": [random.Random(a.seed + i).getrandbits(31) for i in range(a.tasks)]}
+    graph = make_single_operator_graph(node_name="burn", operator=BurnOp(a.inner_iters, a.chunk_size),
+                                       input_keys=("x",))
+    out = {"tasks": a.tasks, "inner_iters": a.inner_iters, "chunk_size": a.chunk_size, "backend": a.pool_backend}
     t0 = time.perf_counter()
-    ref = (await NodeScheduler(graph, pool=None).run({"x": 0}))["burn"]
+    ref = (await NodeScheduler(graph, pool=None).run(payload))["burn"]
     out["no_pool_ms"] = round((time.perf_counter() - t0) * 1e3, 2)
     for k in parse_worker_counts(a.pool_workers):
         pool = ActorPool(pool_configs(a.pool_backend, k))
         await pool.start()
         try:
             sched = NodeScheduler(graph, pool=pool)
-            await sched.run({"x": 0})
+            for _ in range(max(1, a.warmup)):
+                await sched.run(payload)
             t0 = time.perf_counter()
             for _ in range(a.repeat):
-                got = (await sched.run({"x": 0}))["burn"]
+                got = (await sched.run(payload))["burn"]
             out[f"pool_x{k}_ms"] = round((time.perf_counter() - t0) / a.repeat * 1e3, 2)
             assert got == ref
         finally:

@@ -1,17 +1,44 @@
-"""Bar plots (speed-up over the direct call) from a profile_summary.py JSON dump.
+"""Bar plots (speed-up over the direct call) of the ActorPool benchmarks.
 
+    python benchmarks/pytorch/generate_benchmark_plots.py --output-dir benchmarks/plots     # runs the benchmarks
     python benchmarks/pytorch/profile_summary.py --out bench_summary.json
     python benchmarks/pytorch/generate_benchmark_plots.py bench_summary.json --out bench_summary.png
+
+Without a summary file the script runs the benchmarks the reference's plots show (MDA, trimmed mean, mean of medians:
+reference benchmarks/pytorch/generate_benchmark_plots.py) through profile_summary.py and writes
+``<output-dir>/actor_pool_speedups.png`` plus the JSON it was drawn from.
 """
 import argparse
 import json
+import os
+import subprocess
+import sys
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("summary")
-    ap.add_argument("--out", default="bench_summary.png")
+    ap.add_argument("summary", nargs="?", default=None)
+    ap.add_argument("--out", default=None)
+    ap.add_argument("--output-dir", default=os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                         "plots"))
+    ap.add_argument("--ops", default="mda,cwtm,meamed")
+    ap.add_argument("--workers", default="2,4,6")
+    ap.add_argument("--num-grads", type=int, default=None)
+    ap.add_argument("--grad-dim", type=int, default=None)
+    ap.add_argument("--pool-backend", default="process")
     a = ap.parse_args()
+    if a.summary is None:
+        os.makedirs(a.output_dir, exist_ok=True)
+        a.summary = os.path.join(a.output_dir, "actor_pool_speedups.json")
+        cmd = [sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "profile_summary.py"),
+               "--ops", a.ops, "--workers", a.workers, "--pool-backend", a.pool_backend, "--out", a.summary]
+        if a.num_grads is not None:
+            cmd += ["--num-grads", str(a.num_grads)]
+        if a.grad_dim is not None:
+            cmd += ["--grad-dim", str(a.grad_dim)]
+        subprocess.run(cmd, check=True)
+        a.out = a.out or os.path.join(a.output_dir, "actor_pool_speedups.png")
+    a.out = a.out or "bench_summary.png"
     rows = [r for r in json.load(open(a.summary)) if "direct_ms" in r]
     try:
         import matplotlib

@@ -4,6 +4,7 @@ line, so the summary is exact).
 
     python benchmarks/pytorch/profile_summary.py --ops median,trimmed_mean,multi_krum --num-grads 32 --grad-dim 32768
     python benchmarks/pytorch/profile_summary.py --out bench_summary.json
+    python benchmarks/pytorch/profile_summary.py --bench krum --bench median --workers 2,4
 """
 from __future__ import annotations
 
@@ -25,21 +26,28 @@ def discover():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ops", default="")
-    ap.add_argument("--num-grads", type=int, default=32)
-    ap.add_argument("--grad-dim", type=int, default=32768)
-    ap.add_argument("--pool-workers", default="2,4")
+    ap.add_argument("--bench", action="append", default=None,
+                    help="run only the benchmarks whose name contains this (repeatable; the reference's flag)")
+    ap.add_argument("--num-grads", type=int, default=None, help="default: each script's own (= the reference's)")
+    ap.add_argument("--grad-dim", type=int, default=None)
+    ap.add_argument("--pool-workers", "--workers", dest="pool_workers", default="2,4,6")
     ap.add_argument("--pool-backend", default="thread")
     ap.add_argument("--timeout", type=float, default=600)
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     ops = [o for o in a.ops.split(",") if o] or discover()
+    if a.bench:
+        ops = [o for o in ops if any(b in o or b in f"{o}_actor_pool" for b in a.bench)]
     rows = []
     for op in ops:
         script = os.path.join(HERE, f"{op}_actor_pool.py")
         if not os.path.exists(script):
             script = os.path.join(HERE, f"{op}_preagg.py")
-        cmd = [sys.executable, script, "--num-grads", str(a.num_grads), "--grad-dim", str(a.grad_dim),
-               "--pool-workers", a.pool_workers, "--pool-backend", a.pool_backend]
+        cmd = [sys.executable, script, "--pool-workers", a.pool_workers, "--pool-backend", a.pool_backend]
+        if a.num_grads is not None:
+            cmd += ["--num-grads", str(a.num_grads)]
+        if a.grad_dim is not None:
+            cmd += ["--grad-dim", str(a.grad_dim)]
         try:
             p = subprocess.run(cmd, capture_output=True, text=True, timeout=a.timeout)
             line = [l for l in p.stdout.splitlines() if l.startswith("{")][-1]

@@ -49,7 +49,8 @@ class ChannelRef:
         await self._backend.chan_put(from_ep=self._local, to_ep=to, name=self._name, payload=payload)
 
     async def recv(self, *, timeout: Optional[float] = None) -> Any:
-        """Next payload from this actor's own mailbox (``asyncio.TimeoutError`` after ``timeout``)."""
+        """Next payload from this actor's own mailbox; ``None`` when ``timeout`` seconds pass without one (the
+        reference's convention, backends/thread.py:127-137)."""
         item = await self._backend.chan_get(ep=self._local, name=self._name, timeout=timeout)
         return unwrap_payload(item)
 

@@ -18,5 +18,5 @@ sys.exit(0 if s.connect_ex(("127.0.0.1", int(sys.argv[1]))) == 0 else 1)
 PY
   done
 done
-python examples/distributed/mnist.py --servers "127.0.0.1:$PORT_A,127.0.0.1:$PORT_B" --rounds "$ROUNDS"
+python examples/distributed/mnist.py --remote-hosts "tcp://127.0.0.1:$PORT_A,tcp://127.0.0.1:$PORT_B" --rounds "$ROUNDS" --eval-interval 1
 echo "distributed parameter-server rehearsal finished"

@@ -5,14 +5,17 @@ stale against its own API at the surveyed commit; this one runs).
 Each node holds a scalar; on every ``step`` it averages the values in its inbox with its own; the
 launcher forwards every node's value to its ring neighbours between steps.
 
-    python examples/p2p/decentralized_demo.py
+    python examples/p2p/decentralized_demo.py [--transport local|tcp]
 """
+import argparse
 import os
 import sys
 
 sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..", "..")))
 
 from byzpy_b200.engine.node_cluster import NodeCluster  # noqa: E402
+from byzpy_b200.engine.transport.local import LocalTransport  # noqa: E402
+from byzpy_b200.engine.transport.tcp import TcpTransport  # noqa: E402
 
 
 def step(state: dict) -> dict:
@@ -29,8 +32,13 @@ def on_msg(state: dict, msg) -> dict:
 
 
 if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--transport", choices=["local", "tcp"], default="local",
+                    help="how the node processes exchange messages: in-process queues or loopback sockets")
+    a = ap.parse_args()
+    transport = LocalTransport() if a.transport == "local" else TcpTransport()
     n = 4
-    cluster = NodeCluster()
+    cluster = NodeCluster(transport=transport)
     for i in range(n):
         cluster.add_node(f"n{i}", step, on_msg, init_state={"value": float(10 * i)})
     cluster.start_all()
@@ -45,3 +53,5 @@ if __name__ == "__main__":
                 cluster._nodes[f"n{i}"].step()
     finally:
         cluster.stop_all()
+        if hasattr(transport, "close"):
+            transport.close()

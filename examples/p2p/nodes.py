@@ -22,8 +22,9 @@ from byzpy_b200.utils.data import batch_source, mnist_like
 
 
 class P2PHonestNode(P2PHonestMixin):
-    def __init__(self, *, indices: Sequence[int], batch_size: int = 64, device: str = "cpu", f: int = 1, seed: int = 0):
-        x, y = mnist_like(6000)
+    def __init__(self, *, indices: Sequence[int], batch_size: int = 64, device: str = "cpu", f: int = 1, seed: int = 0,
+                 data_root: str = "./data"):
+        x, y = mnist_like(6000, root=data_root)
         idx = torch.as_tensor(list(indices))
         self._next = batch_source(x[idx], y[idx], batch_size, seed=seed)
         self.device = torch.device(device)

@@ -26,6 +26,30 @@ def load_config(path: str) -> dict:
         return json.load(f)
 
 
+def add_training_flags(ap) -> None:
+    """The per-node flags of the reference's clients (examples/p2p/remote_tcp/client.py:473-521,
+    mesh_client.py): they override what the node list says."""
+    ap.add_argument("--node-type", choices=["honest", "byzantine"], default=None,
+                    help="this node's role (default: the node list's `role`, else honest)")
+    ap.add_argument("--rounds", type=int, default=None)
+    ap.add_argument("--batch-size", type=int, default=64)
+    ap.add_argument("--lr", type=float, default=0.05)
+    ap.add_argument("--data-root", default="./data")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--byz-scale", type=float, default=-1.0)
+
+
+def apply_training_flags(cfg: dict, a, node_id: str) -> dict:
+    cfg = dict(cfg)
+    if a.rounds is not None:
+        cfg["rounds"] = a.rounds
+    if a.node_type is not None:
+        cfg["nodes"] = [dict(e, role=a.node_type) if str(e["id"]) == node_id else e for e in cfg["nodes"]]
+    cfg["train"] = {"batch_size": a.batch_size, "lr": a.lr, "data_root": a.data_root, "seed": a.seed,
+                    "byz_scale": a.byz_scale, "data_shard": getattr(a, "data_shard", None)}
+    return cfg
+
+
 def topology_of(cfg: dict) -> Topology:
     n = len(cfg["nodes"])
     return Topology.complete(n) if cfg.get("topology", "complete") == "complete" else Topology.ring(n, 1)
@@ -52,6 +76,8 @@ async def gossip(node: DecentralizedNode, cfg: dict, role: str, *, settle: float
     ids: List[str] = [str(e["id"]) for e in cfg["nodes"]]
     honest_ids = [str(e["id"]) for e in cfg["nodes"] if e.get("role", "honest") == "honest"]
     rounds = int(cfg.get("rounds", 5))
+    train = cfg.get("train") or {}
+    lr = float(train.get("lr", 0.05))
     inbox, arrived = [], asyncio.Event()
 
     async def on_model(frm, payload):
@@ -76,10 +102,12 @@ async def gossip(node: DecentralizedNode, cfg: dict, role: str, *, settle: float
 
     if role == "honest":
         me = honest_ids.index(node.node_id)
-        worker = P2PHonestNode(indices=shard_indices(6000, len(honest_ids))[me], seed=me)
+        shard = me if train.get("data_shard") is None else int(train["data_shard"]) % len(honest_ids)
+        worker = P2PHonestNode(indices=shard_indices(6000, len(honest_ids))[shard], seed=int(train.get("seed", 0)) + me,
+                               batch_size=int(train.get("batch_size", 64)), data_root=train.get("data_root", "./data"))
         n_in = len(node.get_in_neighbors())
         for r in range(1, rounds + 1):
-            own = worker.p2p_half_step(0.05)
+            own = worker.p2p_half_step(lr)
             await node.broadcast_message("model", {"vector": own})
             received = await collect(n_in)
             if len(received) + 1 > 2 * worker.p2p_agg.f:
@@ -87,7 +115,7 @@ async def gossip(node: DecentralizedNode, cfg: dict, role: str, *, settle: float
             print(f"[node {node.node_id}] round {r}: {len(received)} neighbour vectors, "
                   f"|theta| = {worker.get_param_vector().norm().item():.4f}", flush=True)
     else:
-        attacker = P2PByzNode()
+        attacker = P2PByzNode(scale=float(train.get("byz_scale", -1.0)))
         n_h_in = len([i for i in node.get_in_neighbors() if str(i) in honest_ids])
         for r in range(1, rounds + 1):
             seen = await collect(n_h_in)

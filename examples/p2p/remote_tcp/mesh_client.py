@@ -2,6 +2,7 @@
 peers (``MeshRemoteContext``; dead peers are re-dialled, sends fall back outbound -> inbound).
 
     for i in 0 1 2 3; do python examples/p2p/remote_tcp/mesh_client.py --node-id $i & done; wait
+    python examples/p2p/remote_tcp/mesh_client.py --config nodes.yaml --node-id 0 --node-type honest --rounds 50 --lr 0.05
     # on one NVSwitch box add --gpu-direct to ship CUDA tensors as CUDA-IPC handles
 """
 import argparse
@@ -10,7 +11,7 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-from common import gossip, load_config, make_node  # noqa: E402
+from common import add_training_flags, apply_training_flags, gossip, load_config, make_node  # noqa: E402
 
 from byzpy_b200.engine.node.context import MeshRemoteContext  # noqa: E402
 
@@ -34,5 +35,6 @@ if __name__ == "__main__":
     ap.add_argument("--config", default=os.path.join(os.path.dirname(__file__), "nodes_example.json"))
     ap.add_argument("--node-id", required=True)
     ap.add_argument("--gpu-direct", action="store_true")
+    add_training_flags(ap)
     a = ap.parse_args()
-    asyncio.run(main(load_config(a.config), str(a.node_id), a.gpu_direct))
+    asyncio.run(main(apply_training_flags(load_config(a.config), a, str(a.node_id)), str(a.node_id), a.gpu_direct))

@@ -18,6 +18,12 @@ Config keys: ``server``, ``workers`` (``id``, ``role``, optional ``leave_after``
 
     python examples/ps/remote_tcp/ps_node.py server &
     for w in w0 w1 w2 w3; do python examples/ps/remote_tcp/ps_node.py worker --id $w & done; wait
+
+The reference's spelling works too (``--worker-id`` = an id or a position in the list; ``--worker-type``,
+``--rounds``, ``--data-root`` override the node list):
+
+    python examples/ps/remote_tcp/ps_node.py --config nodes.yaml --role server
+    python examples/ps/remote_tcp/ps_node.py --config nodes.yaml --role worker --worker-id 3 --worker-type byzantine
 """
 from __future__ import annotations
 
@@ -170,7 +176,7 @@ class ParameterServerNode:
 
     async def run_training(self):
         await self.all_in.wait()
-        xt, yt = mnist_like(2000, train=False)
+        xt, yt = mnist_like(2000, train=False, root=self.cfg.get("data_root", "./data"))
         for r in range(1, self.rounds + 1):
             self.round, self.inbox = r, {}
             await self._broadcast({"type": "round", "round": r})
@@ -211,8 +217,20 @@ async def run_server(cfg):
 
 
 # ------------------------------------------------------------------------------ workers
+def resolve_worker(cfg, wid: str) -> dict:
+    """The worker entry named ``wid``; a bare number that is nobody's id is a position in the list
+    (``--worker-id 0`` as in the reference's command lines)."""
+    for w in cfg["workers"]:
+        if str(w["id"]) == str(wid):
+            return w
+    if str(wid).isdigit() and int(wid) < len(cfg["workers"]):
+        return cfg["workers"][int(wid)]
+    raise SystemExit(f"no worker {wid!r} in the node list ({[str(w['id']) for w in cfg['workers']]})")
+
+
 async def run_worker(cfg, wid):
-    entry = next(w for w in cfg["workers"] if str(w["id"]) == wid)
+    entry = resolve_worker(cfg, wid)
+    wid = str(entry["id"])
     honest_ids = [str(w["id"]) for w in cfg["workers"] if w.get("role", "honest") == "honest"]
     for attempt in range(50):
         try:
@@ -235,7 +253,7 @@ async def run_worker(cfg, wid):
         attack = EmpireAttack(scale=-1.0)
     else:
         me = honest_ids.index(wid)
-    x, y = mnist_like(6000)
+    x, y = mnist_like(6000, root=cfg.get("data_root", "./data"))
     idx = torch.as_tensor(shard_indices(6000, max(1, len(honest_ids)))[me])
     nxt = batch_source(x[idx], y[idx], 64, seed=me)
     while True:
@@ -262,9 +280,24 @@ async def run_worker(cfg, wid):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("role", choices=["server", "worker"])
-    ap.add_argument("--id", default="w0")
+    ap.add_argument("role_pos", nargs="?", choices=["server", "worker"], default=None, metavar="role")
+    ap.add_argument("--role", choices=["server", "worker"], default=None)
+    ap.add_argument("--id", "--worker-id", dest="id", default="w0",
+                    help="worker id from the node list, or its position in it")
+    ap.add_argument("--worker-type", choices=["honest", "byzantine"], default=None,
+                    help="override this worker's role from the node list")
+    ap.add_argument("--rounds", type=int, default=None, help="override the node list's `rounds`")
+    ap.add_argument("--data-root", default=None, help="MNIST directory (synthetic stand-in when absent)")
     ap.add_argument("--config", default=os.path.join(os.path.dirname(__file__), "nodes_example.yaml"))
     a = ap.parse_args()
+    role = a.role or a.role_pos
+    if role is None:
+        ap.error("say which node this is: --role server | --role worker")
     cfg = load_config(a.config)
-    asyncio.run(run_server(cfg) if a.role == "server" else run_worker(cfg, a.id))
+    if a.rounds is not None:
+        cfg["rounds"] = a.rounds
+    if a.data_root is not None:
+        cfg["data_root"] = a.data_root
+    if role == "worker" and a.worker_type is not None:
+        resolve_worker(cfg, a.id)["role"] = a.worker_type
+    asyncio.run(run_server(cfg) if role == "server" else run_worker(cfg, a.id))

@@ -14,7 +14,8 @@ CASES = [
     (["examples/p2p/decentralized_autonomous_mnist.py", "--rounds", "1"], "'rounds': 1"),
     (["examples/ps/decentralized_demo.py"], "aggregate = [1.0, 2.0, 3.0]"),
     (["examples/p2p/decentralized_demo.py"], "round 5:"),
-    (["examples/distributed/mnist.py", "--local", "--rounds", "2"], "|aggregate|"),
+    (["examples/distributed/mnist.py", "--local", "--rounds", "2", "--num-honest", "4", "--num-byz", "1", "--f", "1",
+      "--eval-interval", "1"], "[round 0002] test loss="),
     (["benchmarks/config1_cpu_plumbing.py", "--repeat", "3"], '"pool_x4_ms"'),
     (["benchmarks/pytorch/sign_flip_actor_pool.py", "--num-grads", "8", "--grad-dim", "4096", "--pool-workers", "2",
       "--repeat", "1"], '"op": "sign-flip"'),
@@ -163,3 +164,55 @@ def test_remote_tcp_hub_example_server_and_four_clients(tmp_path):
     finals = [ln for o in outs[:3] for ln in o.splitlines() if "round 2:" in ln]
     assert len(finals) == 3 and all("3 neighbour vectors" in ln for ln in finals), outs
     assert "hub listening" in hub_out
+
+
+def test_remote_tcp_hub_example_reference_command_line():
+    """The hub example driven the way the reference's README does it: no node list, the server given --host/--port,
+    every client told the shape of the network (--server-host --total-nodes --honest-nodes --node-type ...)."""
+    import time
+
+    (port,) = _free_ports(1)
+    hub = subprocess.Popen([sys.executable, "examples/p2p/remote_tcp/server.py", "--host", "127.0.0.1", "--port", str(port)],
+                           cwd=ROOT, env=_env(), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    try:
+        time.sleep(2.0)
+        common = ["--server-host", "127.0.0.1", "--server-port", str(port), "--total-nodes", "3", "--honest-nodes", "2",
+                  "--rounds", "2", "--batch-size", "32", "--lr", "0.05", "--seed", "1"]
+        argv = [["--node-id", "0", "--node-type", "honest", "--data-shard", "0"],
+                ["--node-id", "1", "--node-type", "honest", "--data-shard", "1"],
+                ["--node-id", "2", "--node-type", "byzantine", "--byz-scale", "-2.0"]]
+        procs = [subprocess.Popen([sys.executable, "examples/p2p/remote_tcp/client.py"] + common + extra, cwd=ROOT,
+                                  env=_env(), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+                 for extra in argv]
+        outs = _finish(procs, 240)
+    finally:
+        hub.terminate()
+        hub_out = _finish([hub], 30)[0]
+    assert all(p.returncode == 0 for p in procs), [o[-800:] for o in outs] + [hub_out[-800:]]
+    finals = [ln for o in outs[:2] for ln in o.splitlines() if "round 2:" in ln]
+    assert len(finals) == 2 and all("2 neighbour vectors" in ln for ln in finals), outs
+    assert "round 2: attacked with 2 honest vectors" in outs[2], outs[2][-800:]
+
+
+def test_remote_tcp_parameter_server_reference_command_line(tmp_path):
+    """ps_node.py with the reference's spelling: --role, --worker-id as a position, --worker-type / --rounds
+    overriding the node list."""
+    import yaml
+
+    (port,) = _free_ports(1)
+    cfg = {"server": {"host": "127.0.0.1", "port": port}, "rounds": 9, "round_timeout": 30, "lr": 0.05,
+           "aggregator": {"name": "trimmed_mean", "f": 1},
+           "workers": [{"id": f"w{i}", "role": "honest"} for i in range(4)]}
+    path = tmp_path / "nodes.yaml"
+    path.write_text(yaml.safe_dump(cfg))
+    script = os.path.join("examples", "ps", "remote_tcp", "ps_node.py")
+    popen = lambda args: subprocess.Popen([sys.executable, script, "--config", str(path), "--rounds", "2"] + args,  # noqa: E731
+                                          cwd=ROOT, env=_env(BYZPY_HMAC_SECRET="s"), stdout=subprocess.PIPE,
+                                          stderr=subprocess.STDOUT, text=True)
+    server = popen(["--role", "server"])
+    workers = [popen(["--role", "worker", "--worker-id", str(i)] + (["--worker-type", "byzantine"] if i == 3 else []))
+               for i in range(4)]
+    outs = _finish(workers + [server], 240)
+    assert server.returncode == 0 and all(w.returncode == 0 for w in workers), [o[-800:] for o in outs]
+    assert "[round 2] 4 gradients" in outs[-1] and "[round 3]" not in outs[-1], outs[-1][-1500:]
+    assert all(f"[w{i}] finished" in outs[i] for i in range(4)), outs[:4]
