@@ -13,11 +13,14 @@ The round is message-driven: a node proceeds when it has one vector from every (
 in-neighbour (``recv_timeout`` bounds the wait) -- no fixed sleeps.  Node objects are reached
 directly when they live in this process (thread/gpu actor backends), otherwise through their
 actor proxy.  The default context is ``InProcessContext``; pass ``context_factory`` for
-``ProcessContext`` / ``RemoteContext`` / ``MeshRemoteContext`` deployments.
+``ProcessContext`` / ``RemoteContext`` / ``MeshRemoteContext`` deployments, or set
+``BYZPY_P2P_CONTEXT=process`` to get the reference's default (one OS process per node,
+reference peer_to_peer/runner.py:221-224) without touching the call sites.
 """
 from __future__ import annotations
 
 import asyncio
+import os
 import inspect
 from typing import Any, Callable, Dict, List, Optional
 
@@ -28,7 +31,7 @@ from ..graph.ops import CallableOp, make_single_operator_graph
 from ..graph.pool import ActorPoolConfig
 from ..node.application import ByzantineNodeApplication, HonestNodeApplication
 from ..node.cluster import DecentralizedCluster
-from ..node.context import InProcessContext, NodeContext
+from ..node.context import InProcessContext, NodeContext, ProcessContext
 from ..node.decentralized import DecentralizedNode
 from .topology import Topology
 
@@ -144,6 +147,15 @@ def _create_byzantine_node_application(actor: Any, node_id: str) -> ByzantineNod
     return app
 
 
+def _default_context() -> NodeContext:
+    kind = os.environ.get("BYZPY_P2P_CONTEXT", "inprocess").strip().lower()
+    if kind in ("process", "processcontext"):
+        return ProcessContext()
+    if kind in ("", "inprocess", "inprocesscontext"):
+        return InProcessContext()
+    raise ValueError(f"BYZPY_P2P_CONTEXT={kind!r}: expected 'inprocess' or 'process'")
+
+
 class DecentralizedPeerToPeer:
     def __init__(self, honest_nodes: List[Any], byzantine_nodes: List[Any], topology: Topology, *,
                  lr: float = 0.05, context_factory: Optional[Callable[[str, int], NodeContext]] = None,
@@ -171,7 +183,7 @@ class DecentralizedPeerToPeer:
     async def start(self) -> None:
         for idx in range(self._n()):
             node_id = str(idx)
-            context = self.context_factory(node_id, idx) if self.context_factory else InProcessContext()
+            context = self.context_factory(node_id, idx) if self.context_factory else _default_context()
             if idx < len(self.honest):
                 actor = self.honest[idx]
                 try:

@@ -8,7 +8,8 @@ a minimal stand-in for ``pytest-asyncio`` when that plugin is not installed, and
     python scripts/run_reference_tests.py --reference /path/to/byzpy/python/byzpy [-k expr] [--keep]
 
 It is a compatibility probe, not part of the regular suite: the expected residue is listed in
-docs/source/testing.md (package-name strings in CLI output, the default P2P context, UCX-only tests).
+docs/source/testing.md (UCX-only tests).  ``BYZPY_P2P_CONTEXT=process`` is set for the run: one process per P2P
+node is the reference's default and its suite asserts it; here it is opt-in.
 """
 from __future__ import annotations
 
@@ -115,6 +116,8 @@ def main() -> int:
             (stage / "pytest_asyncio.py").write_text(ASYNCIO_SHIM)
         env = dict(os.environ)
         env["PYTHONPATH"] = os.pathsep.join([str(shim), env.get("PYTHONPATH", "")]).rstrip(os.pathsep)
+        # the suite asserts the reference's defaults; the one default that differs here is switchable
+        env.setdefault("BYZPY_P2P_CONTEXT", "process")
         cmd = [sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "-W", "ignore",
                *[str(f) for f in sorted(stage.glob("*test_*.py"))]]
         try:

@@ -178,6 +178,35 @@ def test_peer_to_peer_round_writes_back_robust_aggregate():
     run(scenario())
 
 
+def test_p2p_default_context_follows_the_environment_switch(monkeypatch):
+    """``BYZPY_P2P_CONTEXT=process`` gives the reference's default (a ``ProcessContext`` per node) and the round still
+    produces the robust aggregate; unset, nodes sit in ``InProcessContext``; anything else is rejected."""
+    from byzpy_b200.engine.node.context import InProcessContext, ProcessContext
+
+    async def scenario(expect_cls):
+        hon = [await HonestNodeActor.spawn(PH, backend="thread", args=(i,)) for i in range(3)]
+        p2p = PeerToPeer(hon, [], Topology.complete(3), lr=0.1)
+        await p2p.bootstrap()
+        try:
+            assert all(isinstance(n.context, expect_cls) for n in p2p._runner._cluster.nodes.values())
+            await p2p.round()
+            halves = [PH(i).p2p_half_step(0.1) for i in range(3)]
+            exp = CoordinateWiseTrimmedMean(f=1).aggregate(halves)
+            assert torch.allclose(await hon[0].params(), exp, atol=1e-6)
+        finally:
+            await p2p.shutdown()
+            for a in hon:
+                await a.close()
+
+    monkeypatch.delenv("BYZPY_P2P_CONTEXT", raising=False)
+    run(scenario(InProcessContext))
+    monkeypatch.setenv("BYZPY_P2P_CONTEXT", "process")
+    run(scenario(ProcessContext))
+    monkeypatch.setenv("BYZPY_P2P_CONTEXT", "bogus")
+    with pytest.raises(ValueError):
+        run(scenario(InProcessContext))
+
+
 def test_decentralized_peer_to_peer_round_matches_manual_expectation():
     """``DecentralizedPeerToPeer`` over DecentralizedNodes: the round writes the robust aggregate of
     own + neighbour half-steps back into every honest model (ring topology, message-count driven)."""
