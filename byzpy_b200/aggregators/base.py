@@ -32,7 +32,27 @@ from ._chunking import select_adaptive_chunk_size
 
 
 class Aggregator(Operator, ABC):
-    """Base class of every gradient aggregator."""
+    """Base class of every gradient aggregator: ``n`` gradients in, one robust estimate out.
+
+    Subclasses implement :meth:`aggregate`.  Inputs are a sequence of same-shaped tensors (any floating dtype, CPU or
+    CUDA) or array-likes the active backend understands; the result has the shape, dtype and device of the first
+    input.  As an :class:`~byzpy_b200.engine.graph.operator.Operator` an aggregator reads its input list from
+    the key ``"gradients"`` of a computation graph, and -- when ``supports_subtasks`` is set -- can split its work
+    over an :class:`~byzpy_b200.engine.graph.pool.ActorPool` (``create_subtasks`` / ``reduce_subtasks``).
+    :meth:`fused_plan` is the hook through which the device parameter server runs the aggregator inside its fused
+    round instead of calling :meth:`aggregate`.
+
+    Examples
+    --------
+    >>> import torch
+    >>> from byzpy_b200.aggregators import Aggregator
+    >>> class Mean(Aggregator):
+    ...     name = "mean"
+    ...     def aggregate(self, gradients):
+    ...         return torch.stack(list(gradients)).mean(0)
+    >>> Mean().aggregate([torch.tensor([1.0, 2.0]), torch.tensor([3.0, 6.0])])
+    tensor([2., 4.])
+    """
 
     name = "aggregator"
     input_key = "gradients"
@@ -151,7 +171,23 @@ def _cw_chunk(packed: _Packed, start: int, end: int, mode: int, f: int):
 
 
 class CoordinateWiseAggregator(Aggregator):
-    """Per-coordinate selection over the n inputs (median / trimmed mean / meamed)."""
+    """Shared machinery of the coordinate-wise family (median, trimmed mean, mean of medians).
+
+    Each output coordinate depends only on that coordinate of the ``n`` inputs, so the work splits along the feature
+    dimension without communication: on CUDA one selection-network launch over all coordinates
+    (``ops.cw_select``); on an actor pool one subtask per feature chunk (``chunk_size`` coordinates, adapted to the
+    pool size), concatenated by ``reduce_subtasks``; in the fused parameter-server round each GPU selects over the
+    coordinate shard it owns (``CwPlan``).  Subclasses set ``_mode`` (which statistic) and ``_f`` (how many values are
+    trimmed).
+
+    Examples
+    --------
+    >>> import torch
+    >>> from byzpy_b200.aggregators.coordinate_wise import CoordinateWiseMedian
+    >>> from byzpy_b200.aggregators.base import CoordinateWiseAggregator
+    >>> isinstance(CoordinateWiseMedian(), CoordinateWiseAggregator)
+    True
+    """
 
     supports_subtasks = True
     max_subtasks_inflight = 0
@@ -237,7 +273,32 @@ def _gram_chunk(packed: _Packed, start: int, end: int, with_median: bool = False
 
 
 class GramAggregator(Aggregator):
-    """Distance/norm based aggregators: Gram pass -> n-space solve -> weighted sum."""
+    """Shared machinery of the distance / norm based aggregators: Gram pass -> small solve -> weighted sum.
+
+    Every aggregator of this family returns ``sum_i w_i x_i`` where the weights depend on the inputs only through
+    their Gram matrix ``G = X X^T`` (norms, pairwise distances, spectra of sub-blocks).  The gradients are therefore
+    read exactly twice whatever the algorithm iterates over: once to build the ``n x n`` matrix (``ops.gram``:
+    tcgen05 tensor cores in 3xTF32 or exact fp32 CUDA cores, fp64 accumulation across tiles), once for the weighted
+    sum (``ops.weighted_sum``).  Subclasses implement ``_solve`` (host, NumPy fp64) and optionally ``_solve_device``
+    (one CTA on the device Gram, which keeps the fused round free of host round trips); ``_aux_rows`` appends
+    extra rows to the Gram (a start point, a probe direction).
+
+    ``shift_invariant`` marks solvers that only use distances; they can run on a centred Gram (``center``,
+    ``BYZPY_GRAM_CENTER``) when the gradients share a component much larger than their differences.
+
+    Examples
+    --------
+    >>> import numpy as np, torch
+    >>> from byzpy_b200.aggregators.base import GramAggregator
+    >>> class NearestToOrigin(GramAggregator):
+    ...     name = "nearest-to-origin"
+    ...     def _solve(self, G, n):
+    ...         w = np.zeros(n)
+    ...         w[int(np.argmin(np.diag(G)[:n]))] = 1.0      # the row with the smallest norm
+    ...         return w
+    >>> NearestToOrigin().aggregate([torch.tensor([3.0, 4.0]), torch.tensor([0.0, 1.0]), torch.tensor([2.0, 2.0])])
+    tensor([0., 1.])
+    """
 
     supports_subtasks = True
     max_subtasks_inflight = 0

@@ -7,6 +7,30 @@ from ..base import CoordinateWiseAggregator
 
 
 class CoordinateWiseTrimmedMean(CoordinateWiseAggregator):
+    """Mean of every coordinate after dropping its ``f`` smallest and ``f`` largest values.
+
+    Parameters
+    ----------
+    f : int
+        Values trimmed from each end, per coordinate; needs ``0 <= 2 f < n``.
+    chunk_size : int, default 8192
+        Coordinates per subtask on an actor pool.
+
+    Notes
+    -----
+    CUDA inputs: full odd-even merge network per coordinate followed by a masked sum, one launch
+    (``cw_select_staged_kernel``: each thread streams its next tiles through a private cp.async ring).  ``f = 0`` is the
+    plain mean.
+
+    Examples
+    --------
+    >>> import torch
+    >>> from byzpy_b200.aggregators.coordinate_wise import CoordinateWiseTrimmedMean
+    >>> grads = [torch.tensor([v]) for v in (0.0, 1.0, 2.0, 3.0, 1000.0)]
+    >>> CoordinateWiseTrimmedMean(f=1).aggregate(grads)
+    tensor([2.])
+    """
+
     name = "coordinate-wise-trimmed-mean"
     _mode = ops.MODE_TRMEAN
 

@@ -20,6 +20,43 @@ from ..base import GramAggregator
 
 
 class GeometricMedian(GramAggregator):
+    """Geometric median: the point minimising the sum of Euclidean distances to the gradients (Weiszfeld's algorithm).
+
+    Parameters
+    ----------
+    tol : float, default 1e-6
+        Stop when two successive iterates are closer than this (Euclidean norm).
+    max_iter : int, default 256
+        Upper bound on Weiszfeld iterations.
+    eps : float, default 1e-12
+        Lower clamp on a distance before it is inverted (an iterate that lands on an input).
+    init : {"median", "mean"}, default "median"
+        Start point: coordinate-wise (lower) median or arithmetic mean of the inputs.
+    chunk_size : int, default 32
+        Rows per subtask; on an actor pool every iteration is one barriered round of subtasks.
+
+    Attributes
+    ----------
+    last_iterations : int
+        Iterations the most recent call took.
+
+    Notes
+    -----
+    Every iterate is an affine combination of the inputs and the start point, so the iteration is carried out on the
+    coefficient vector using only the Gram matrix of ``[X; start]``: one Gram pass, an ``O(n^2)`` update per
+    iteration on one CTA, one weighted-sum pass.  The gradients are read twice however many iterations it takes (the
+    reference reads them once per iteration and synchronises with the host each time).
+
+    Examples
+    --------
+    >>> import torch
+    >>> from byzpy_b200.aggregators.geometric_wise import GeometricMedian
+    >>> pts = [torch.tensor([0.0, 0.0]), torch.tensor([2.0, 0.0]), torch.tensor([1.0, 1.0]), torch.tensor([1.0, 50.0])]
+    >>> out = GeometricMedian().aggregate(pts)
+    >>> bool((out - torch.tensor([1.0, 1.0])).norm() < 1e-3)
+    True
+    """
+
     name = "geometric-median"
     shift_invariant = True       # distances only
     supports_barriered_subtasks = True

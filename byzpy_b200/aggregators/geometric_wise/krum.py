@@ -15,6 +15,35 @@ from ..base import GramAggregator
 
 
 class MultiKrum(GramAggregator):
+    """Multi-Krum: average of the ``q`` gradients with the best Krum scores.
+
+    The score of gradient ``i`` is the sum of its ``n - f - 1`` smallest squared distances to the other gradients; a
+    gradient far from every honest cluster scores badly and is left out of the average.
+
+    Parameters
+    ----------
+    f : int
+        Upper bound on the number of Byzantine inputs; ``0 <= f < n - 1``.
+    q : int
+        Number of best-scored gradients averaged; ``1 <= q <= n - f``.
+    chunk_size : int, default 32
+        Rows per subtask on an actor pool (subtasks score row blocks against all rows).
+
+    Notes
+    -----
+    Everything the operator needs is in the ``n x n`` Gram matrix: one pass over the data builds it
+    (tcgen05 3xTF32 or exact fp32, ``ops.gram``), a single CTA turns it into ``q`` selected rows, one weighted-sum pass
+    writes the result -- the gradients are read twice regardless of ``n``.  Ties in the score go to the lower index.
+
+    Examples
+    --------
+    >>> import torch
+    >>> from byzpy_b200.aggregators.geometric_wise import MultiKrum
+    >>> honest = [torch.tensor([1.0, 1.0]) + 0.01 * i for i in range(4)]
+    >>> MultiKrum(f=1, q=2).aggregate(honest + [torch.tensor([100.0, -100.0])])
+    tensor([1.0150, 1.0150])
+    """
+
     name = "multi-krum"
     shift_invariant = True       # distances only
     device_solve = True
@@ -54,6 +83,23 @@ class MultiKrum(GramAggregator):
 
 
 class Krum(MultiKrum):
+    """Krum: the single gradient with the best Krum score (``MultiKrum`` with ``q = 1``).
+
+    Parameters
+    ----------
+    f : int
+        Upper bound on the number of Byzantine inputs; ``0 <= f < n - 1``.
+    chunk_size : int, default 32
+        Rows per subtask on an actor pool.
+
+    Examples
+    --------
+    >>> import torch
+    >>> from byzpy_b200.aggregators.geometric_wise import Krum
+    >>> Krum(f=1).aggregate([torch.tensor([0.0]), torch.tensor([0.1]), torch.tensor([0.2]), torch.tensor([9.0])])
+    tensor([0.1000])
+    """
+
     name = "krum"
 
     def __init__(self, f: int, *, chunk_size: int = 32) -> None:

@@ -12,6 +12,34 @@ from ..base import GramAggregator
 
 
 class MinimumDiameterAveraging(GramAggregator):
+    """Minimum Diameter Averaging: mean of the ``n - f`` gradients that fit in the smallest ball-like set.
+
+    Among all subsets of size ``n - f`` the one with the smallest diameter (largest pairwise distance) is averaged;
+    between subsets of equal diameter the lexicographically first wins.
+
+    Parameters
+    ----------
+    f : int
+        Number of gradients left out; ``0 <= f < n``.
+    chunk_size : int, default 256
+        Subsets scored per subtask on an actor pool.
+
+    Notes
+    -----
+    The search runs on the ``n x n`` distance matrix only.  Instead of enumerating ``C(n, f)`` subsets, the diameter is
+    found by bisection over the sorted distances with a bitset clique search ("is there a set of ``n - f`` points whose
+    pairwise distances are all below t?"), which is what makes ``n = 30, f = 10`` take milliseconds; small instances
+    are searched exhaustively on the device (``csrc/nspace.cu``) so the round stays capturable in a CUDA graph.
+
+    Examples
+    --------
+    >>> import torch
+    >>> from byzpy_b200.aggregators.geometric_wise import MinimumDiameterAveraging
+    >>> grads = [torch.tensor([0.0]), torch.tensor([1.0]), torch.tensor([2.0]), torch.tensor([40.0])]
+    >>> MinimumDiameterAveraging(f=1).aggregate(grads)
+    tensor([1.])
+    """
+
     name = "minimum-diameter-averaging"
     shift_invariant = True       # distances only
 

@@ -9,6 +9,33 @@ from ..base import GramAggregator
 
 
 class MoNNA(GramAggregator):
+    """MoNNA: mean of the ``n - f`` gradients nearest to a trusted reference gradient.
+
+    Parameters
+    ----------
+    f : int
+        Number of gradients left out; ``0 <= 2 f < n``.
+    reference_index : int, default 0
+        Position of the trusted gradient in the input list (a node aggregating its neighbours passes its own vector
+        first).
+    chunk_size : int, default 32
+        Rows per subtask on an actor pool.
+
+    Notes
+    -----
+    Needs one row of the distance matrix, read off the Gram matrix; ties go to the lower index.  Because the
+    parameter server's device path keeps gradients in rank order, ``reference_index`` names the same worker every
+    round (the reference collects in completion order).
+
+    Examples
+    --------
+    >>> import torch
+    >>> from byzpy_b200.aggregators.geometric_wise import MoNNA
+    >>> grads = [torch.tensor([1.0]), torch.tensor([1.2]), torch.tensor([0.9]), torch.tensor([-30.0])]
+    >>> MoNNA(f=1).aggregate(grads)
+    tensor([1.0333])
+    """
+
     name = "monna"
     shift_invariant = True       # distances only
     device_solve = True

@@ -10,6 +10,35 @@ from ..base import GramAggregator
 
 
 class SMEA(GramAggregator):
+    """Smallest Maximum Eigenvalue Averaging: mean of the ``n - f`` gradients whose covariance is the least stretched.
+
+    For every subset of size ``n - f`` the largest eigenvalue of its empirical covariance is computed; the subset with
+    the smallest one is averaged.  A group of colluding outliers inflates the variance along one direction, which this
+    criterion sees even when every single distance looks harmless.
+
+    Parameters
+    ----------
+    f : int
+        Number of gradients left out; ``0 <= 2 f < n``.
+    chunk_size : int, default 256
+        Subsets scored per subtask on an actor pool.
+
+    Notes
+    -----
+    The non-zero spectrum of a subset's covariance equals that of its centred ``m x m`` Gram block, so after one Gram
+    pass the search is dense linear algebra on tiny matrices, batched over subsets (``numpy.linalg.eigvalsh`` on the
+    host, power iteration in ``csrc/nspace.cu`` on the device).  The number of subsets grows combinatorially: meant for
+    ``n`` up to a few tens.
+
+    Examples
+    --------
+    >>> import torch
+    >>> from byzpy_b200.aggregators.geometric_wise import SMEA
+    >>> grads = [torch.tensor([0.0, 0.0]), torch.tensor([0.2, 0.0]), torch.tensor([0.1, 0.1]), torch.tensor([9.0, -9.0])]
+    >>> SMEA(f=1).aggregate(grads)
+    tensor([0.1000, 0.0333])
+    """
+
     name = "smea"
     shift_invariant = True       # distances only
 

@@ -15,6 +15,39 @@ from ..base import GramAggregator
 
 
 class CenteredClipping(GramAggregator):
+    """Centered clipping: ``v <- v + mean_i clip(x_i - v, c_tau)`` repeated ``M`` times.
+
+    Every gradient pulls the running estimate towards itself, but by at most ``c_tau`` per round, so a far-away input
+    has bounded influence.
+
+    Parameters
+    ----------
+    c_tau : float
+        Clipping radius (``>= 0``).
+    M : int, default 10
+        Number of rounds.
+    eps : float, default 1e-12
+        Lower clamp on a norm before dividing by it.
+    init : {"mean", "median", "zero"}, default "mean"
+        Start point of ``v``.
+    chunk_size : int, default 32
+        Rows per subtask; on an actor pool every round is one barriered round of subtasks.
+
+    Notes
+    -----
+    As with the geometric median, ``v`` stays an affine combination of the inputs and the start point, so the ``M``
+    rounds run on coefficients against the Gram matrix: two passes over the gradients in total.
+
+    Examples
+    --------
+    >>> import torch
+    >>> from byzpy_b200.aggregators.norm_wise import CenteredClipping
+    >>> grads = [torch.tensor([1.0]), torch.tensor([1.1]), torch.tensor([0.9]), torch.tensor([1000.0])]
+    >>> out = CenteredClipping(c_tau=0.5, M=20, init="median").aggregate(grads)
+    >>> bool(out.item() < 5.0)
+    True
+    """
+
     name = "centered-clipping"
     supports_barriered_subtasks = True
     device_solve = True

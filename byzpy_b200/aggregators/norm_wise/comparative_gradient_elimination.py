@@ -9,6 +9,29 @@ from ..base import GramAggregator
 
 
 class ComparativeGradientElimination(GramAggregator):
+    """CGE: drop the ``f`` gradients with the largest norms and average the rest.
+
+    Parameters
+    ----------
+    f : int
+        Number of gradients eliminated; ``0 <= f < n``.
+    chunk_size : int, default 8192
+        Coordinates per subtask on an actor pool (partial squared norms, then partial sums).
+
+    Notes
+    -----
+    Only the diagonal of the Gram matrix is used: a row-norm pass and a weighted-sum pass.  Ties in the norm keep the
+    lower index.
+
+    Examples
+    --------
+    >>> import torch
+    >>> from byzpy_b200.aggregators.norm_wise import ComparativeGradientElimination
+    >>> grads = [torch.tensor([1.0, 0.0]), torch.tensor([0.0, 1.0]), torch.tensor([30.0, 30.0])]
+    >>> ComparativeGradientElimination(f=1).aggregate(grads)
+    tensor([0.5000, 0.5000])
+    """
+
     name = "comparative-gradient-elimination"
     gram_diag_only = True       # only the row norms are used: the torch fallback skips the n^2 d work
     device_solve = True

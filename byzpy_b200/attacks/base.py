@@ -22,6 +22,31 @@ from ..engine.graph.subtask import SubTask
 
 
 class Attack(Operator, ABC):
+    """Base class of attacks: an operator that produces one malicious vector for a Byzantine node to submit.
+
+    Subclasses declare what they look at through three class flags and implement :meth:`apply`:
+
+    * ``uses_base_grad`` -- the Byzantine node's own honest gradient (``base_grad``);
+    * ``uses_honest_grads`` -- the gradients of the honest nodes this round (``honest_grads``), the omniscient setting;
+    * ``uses_model_batch`` -- the node's model and a batch (``model``, ``x``, ``y``), for data-poisoning attacks.
+
+    As a graph operator the attack reads exactly the inputs its flags name.  :meth:`fold` optionally describes the
+    attack as something the fused device round can apply while it loads the rows (a per-row scale, an alias of another
+    row, or a row synthesised from column statistics), in which case the malicious vector is never written to memory.
+
+    Examples
+    --------
+    >>> import torch
+    >>> from byzpy_b200.attacks import Attack
+    >>> class Zero(Attack):
+    ...     name = "zero"
+    ...     uses_base_grad = True
+    ...     def apply(self, *, model=None, x=None, y=None, honest_grads=None, base_grad=None):
+    ...         return torch.zeros_like(base_grad)
+    >>> Zero().apply(base_grad=torch.ones(3))
+    tensor([0., 0., 0.])
+    """
+
     uses_base_grad: bool = False
     uses_model_batch: bool = False
     uses_honest_grads: bool = False
@@ -65,7 +90,23 @@ def _colstat_chunk(packed: _Packed, start: int, end: int, a: float, b: float):
 
 class ColumnStatAttack(Attack):
     """Shared machinery of the omniscient column-statistics attacks: the output is
-    ``a * mean(honest) + b * std(honest)`` per coordinate (population std)."""
+    ``a * mean(honest) + b * std(honest)`` per coordinate (population std).
+
+    Subclasses only supply ``_coeffs(n_honest) -> (a, b)``.  The direct call is one pass of the column-statistics
+    kernel (``ops.colstat``), the pool path splits the coordinates, and the fused device round synthesises the row in
+    registers from the loads the aggregation kernel makes anyway (``RowFold("virtual", a=a, b=b)``).
+
+    Examples
+    --------
+    >>> import torch
+    >>> from byzpy_b200.attacks.base import ColumnStatAttack
+    >>> class MeanPlusStd(ColumnStatAttack):
+    ...     name = "mean-plus-std"
+    ...     def _coeffs(self, n_honest):
+    ...         return 1.0, 1.0
+    >>> MeanPlusStd().apply(honest_grads=[torch.tensor([0.0]), torch.tensor([2.0])])
+    tensor([2.])
+    """
 
     uses_honest_grads = True
     supports_subtasks = True

@@ -23,6 +23,34 @@ def _span(start: int, end: int):
 
 
 class GaussianAttack(Attack):
+    """Gaussian noise: submit a vector of i.i.d. ``N(mu, sigma^2)`` samples shaped like a gradient.
+
+    Parameters
+    ----------
+    mu, sigma : float, default 0.0, 1.0
+        Mean and standard deviation of every coordinate (``sigma >= 0``).
+    seed : int, optional
+        The generator is re-seeded with it on every call, so a fixed seed submits the same vector each round; ``None``
+        draws fresh noise.
+    chunk_size : int, default 8192
+        Coordinates per subtask on an actor pool.
+
+    Notes
+    -----
+    ``honest_grads`` is only used for shape, dtype and device.  CPU inputs are sampled with
+    ``numpy.random.default_rng(seed)`` (bit-identical with the reference); CUDA inputs with a counter-based
+    Philox4x32-10 kernel on the device, which has the same distribution but not the same bits.
+
+    Examples
+    --------
+    >>> import torch
+    >>> from byzpy_b200.attacks import GaussianAttack
+    >>> a = GaussianAttack(mu=0.0, sigma=1.0, seed=7).apply(honest_grads=[torch.zeros(1000)])
+    >>> b = GaussianAttack(mu=0.0, sigma=1.0, seed=7).apply(honest_grads=[torch.zeros(1000)])
+    >>> a.shape, bool(torch.equal(a, b)), bool(abs(a.std().item() - 1.0) < 0.1)
+    (torch.Size([1000]), True, True)
+    """
+
     name = "gaussian"
     max_subtasks_inflight = 0       # 0 / None: the pool-sized default window (value of the reference class)
     uses_honest_grads = True

@@ -17,6 +17,24 @@ def _inf_chunk(start: int, end: int, device: str):
 
 
 class InfAttack(Attack):
+    """Inf attack: submit a vector of ``+inf`` shaped like a gradient.
+
+    Breaks any aggregator that averages without screening (the mean becomes ``inf``); selection-based aggregators
+    order ``+inf`` as the largest value and discard it.
+
+    Parameters
+    ----------
+    chunk_size : int, default 8192
+        Coordinates per subtask on an actor pool.
+
+    Examples
+    --------
+    >>> import torch
+    >>> from byzpy_b200.attacks import InfAttack
+    >>> InfAttack().apply(honest_grads=[torch.zeros(3)])
+    tensor([inf, inf, inf])
+    """
+
     name = "inf"
     max_subtasks_inflight = 0       # 0 / None: the pool-sized default window (value of the reference class)
     uses_honest_grads = True

@@ -18,6 +18,37 @@ from .base import Attack
 
 
 class LabelFlipAttack(Attack):
+    """Label flip (data poisoning): the gradient of the loss on a batch whose targets were remapped.
+
+    Parameters
+    ----------
+    num_classes : int, optional
+        With ``K`` classes and no ``mapping`` the targets are flipped as ``y -> K - 1 - y``.
+    mapping : dict of int to int, optional
+        Explicit remapping of classes; classes not named keep their label.  One of ``num_classes`` / ``mapping`` is
+        required.
+    loss_fn : torch.nn.Module, optional
+        Loss applied to ``model(x)`` and the corrupted targets; default mean cross entropy.
+    scale : float, default 1.0
+        Multiplier of the submitted gradient.
+
+    Notes
+    -----
+    Needs ``model``, ``x``, ``y``.  The gradient is returned flat in ``model.parameters()`` order and the model's
+    ``.grad`` buffers are cleared afterwards, so the node's optimizer state is not touched.
+
+    Examples
+    --------
+    >>> import torch
+    >>> from byzpy_b200.attacks import LabelFlipAttack
+    >>> atk = LabelFlipAttack(num_classes=10)
+    >>> atk.corrupt(torch.tensor([0, 3, 9]))
+    tensor([9, 6, 0])
+    >>> model = torch.nn.Linear(4, 10)
+    >>> atk.apply(model=model, x=torch.randn(2, 4), y=torch.tensor([1, 2])).shape
+    torch.Size([50])
+    """
+
     name = "label-flip"
     uses_model_batch = True
 

@@ -24,6 +24,38 @@ def _ndtri(p: float) -> float:
 
 
 class LittleAttack(ColumnStatAttack):
+    """"A little is enough": shift every coordinate of the honest mean by ``z`` honest standard deviations.
+
+    ``z`` is the largest shift that still leaves the malicious value among the majority a robust aggregator trusts:
+    ``z = Phi^-1((N - s) / N)`` with ``s = max(1, N // 2 + 1 - f)`` supporters needed, ``Phi`` the standard normal CDF.
+    The population standard deviation (divide by the number of honest gradients) is used.
+
+    Parameters
+    ----------
+    f : int
+        Number of Byzantine nodes.
+    N : int, optional
+        Total number of nodes; default: number of honest gradients given ``+ f``.
+    chunk_size : int, default 8192
+        Coordinates per subtask on an actor pool.
+
+    Notes
+    -----
+    Needs ``honest_grads``.  ``z`` can be negative when fewer than half of the nodes have to be convinced.  In the
+    fused device round mean and standard deviation of each coordinate come out of the aggregation kernel's own loads
+    and the row is synthesised in registers.
+
+    Examples
+    --------
+    >>> import torch
+    >>> from byzpy_b200.attacks import LittleAttack
+    >>> atk = LittleAttack(f=2)
+    >>> round(atk.z_value(8), 4)
+    0.2533
+    >>> atk.apply(honest_grads=[torch.tensor([0.0]), torch.tensor([2.0])] * 4)
+    tensor([1.2533])
+    """
+
     name = "little"
     max_subtasks_inflight = 0       # 0 / None: the pool-sized default window (value of the reference class)
 

@@ -16,6 +16,30 @@ def _copy_chunk(vec: torch.Tensor, start: int, end: int):
 
 
 class MimicAttack(Attack):
+    """Mimic: replay the gradient of honest node number ``epsilon`` unchanged.
+
+    Over-representing one honest node biases the aggregate towards that node's data when the honest data is
+    heterogeneous, without ever submitting an outlier.
+
+    Parameters
+    ----------
+    epsilon : int, default 0
+        Index of the honest gradient to copy.
+    chunk_size : int, default 8192
+        Coordinates per subtask on an actor pool.
+
+    Notes
+    -----
+    In the fused device round the Byzantine row is an alias of the victim's row (the same pointer twice): no copy.
+
+    Examples
+    --------
+    >>> import torch
+    >>> from byzpy_b200.attacks import MimicAttack
+    >>> MimicAttack(epsilon=1).apply(honest_grads=[torch.tensor([1.0]), torch.tensor([5.0])])
+    tensor([5.])
+    """
+
     name = "mimic"
     max_subtasks_inflight = 0       # 0 / None: the pool-sized default window (value of the reference class)
     uses_honest_grads = True

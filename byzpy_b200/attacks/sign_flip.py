@@ -17,6 +17,29 @@ def _scale_chunk(vec: torch.Tensor, start: int, end: int, scale: float):
 
 
 class SignFlipAttack(Attack):
+    """Sign flip: submit the node's own gradient multiplied by ``scale`` (default ``-1``).
+
+    Parameters
+    ----------
+    scale : float, default -1.0
+        Multiplier of the node's gradient.
+    chunk_size : int, default 8192
+        Coordinates per subtask on an actor pool.
+
+    Notes
+    -----
+    Needs ``base_grad`` only (not omniscient).  In the fused device round it is a per-row scale applied as the
+    aggregation kernel loads the row; this is the attack of the headline benchmark (6 honest + 2 sign-flipping
+    workers).
+
+    Examples
+    --------
+    >>> import torch
+    >>> from byzpy_b200.attacks import SignFlipAttack
+    >>> SignFlipAttack().apply(base_grad=torch.tensor([1.0, -2.0]))
+    tensor([-1.,  2.])
+    """
+
     name = "sign-flip"
     max_subtasks_inflight = 0       # 0 / None: the pool-sized default window (value of the reference class)
     uses_base_grad = True

@@ -9,6 +9,32 @@ from .base import LinearPreAggregator
 
 
 class ARC(LinearPreAggregator):
+    """Adaptive Robust Clipping: clip to a radius chosen from the data instead of a fixed threshold.
+
+    The vectors are ranked by norm; the ``floor(2 f (n - f) / n)`` largest ones are clipped to the norm of the largest
+    remaining vector.  With ``f = 0`` nothing is clipped.
+
+    Parameters
+    ----------
+    f : int, default 0
+        Expected number of Byzantine vectors; ``0 <= f <= n``.
+    chunk_size : int, default 32
+        Vectors per subtask on an actor pool.
+
+    Notes
+    -----
+    Diagonal row map like :class:`Clipping`; the threshold is found from the Gram diagonal on the device
+    (``csrc/nspace_maps.cu``), so a fused round that uses ARC needs no host round trip and stays graph-capturable.
+
+    Examples
+    --------
+    >>> import torch
+    >>> from byzpy_b200.pre_aggregators import ARC
+    >>> xs = [torch.tensor([1.0, 0.0]), torch.tensor([0.0, 2.0]), torch.tensor([3.0, 0.0]), torch.tensor([0.0, 40.0])]
+    >>> [round(x.norm().item(), 4) for x in ARC(f=1).pre_aggregate(xs)]
+    [1.0, 2.0, 3.0, 3.0]
+    """
+
     name = "pre-agg/arc"
     gram_diag_only = True       # only the row norms are used: the torch fallback skips the n^2 d work
     diagonal_map = True

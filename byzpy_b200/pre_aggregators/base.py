@@ -23,6 +23,24 @@ from ..engine.graph.subtask import SubTask
 
 
 class PreAggregator(Operator, ABC):
+    """Base class of pre-aggregators: operators that map ``n`` vectors to ``m`` (usually better behaved) vectors.
+
+    Subclasses implement :meth:`pre_aggregate`.  As an :class:`~byzpy_b200.engine.graph.operator.Operator` a
+    pre-aggregator reads its input list from the key ``"vectors"`` of a computation graph, so it can be chained
+    in front of an aggregator (``ParameterServer(..., pre_aggregator=...)``, ``GraphBuilder().input("vectors").apply(...)``).
+
+    Examples
+    --------
+    >>> import torch
+    >>> from byzpy_b200.pre_aggregators import PreAggregator
+    >>> class Halve(PreAggregator):
+    ...     name = "pre-agg/halve"
+    ...     def pre_aggregate(self, xs):
+    ...         return [0.5 * x for x in xs]
+    >>> Halve().pre_aggregate([torch.tensor([2.0]), torch.tensor([4.0])])
+    [tensor([1.]), tensor([2.])]
+    """
+
     name = "pre_aggregator"
     input_key = "vectors"
 
@@ -45,7 +63,30 @@ def _mix_chunk(packed: _Packed, start: int, end: int, W: torch.Tensor):
 
 
 class LinearPreAggregator(PreAggregator):
-    """Pre-aggregators expressible as ``X' = W X``."""
+    """Pre-aggregators expressible as a row map ``X' = W X`` with an ``m x n`` matrix that depends on the inputs only
+    through their Gram matrix (or on nothing, as for bucketing).
+
+    Subclasses implement :meth:`row_map` (host, fp64) and optionally :meth:`row_map_device`.  Exposing ``W`` is what
+    lets a pre-aggregator compose with what follows without writing the intermediate vectors: a Gram-family
+    aggregator runs on ``W G W^T`` and returns ``(w W) X``; a coordinate-wise aggregator after a diagonal map
+    takes the scales as per-row factors inside its kernel.  :meth:`pre_aggregate` materialises ``W X`` (one
+    multi-row weighted-sum pass) for callers that want the vectors.
+
+    Examples
+    --------
+    >>> import numpy as np, torch
+    >>> from byzpy_b200.pre_aggregators.base import LinearPreAggregator
+    >>> class PairMeans(LinearPreAggregator):
+    ...     name = "pre-agg/pair-means"
+    ...     needs_gram = False
+    ...     def row_map(self, G, n):
+    ...         W = np.zeros((n // 2, n))
+    ...         for k in range(n // 2):
+    ...             W[k, 2 * k] = W[k, 2 * k + 1] = 0.5
+    ...         return W
+    >>> PairMeans().pre_aggregate([torch.tensor([0.0]), torch.tensor([2.0]), torch.tensor([4.0]), torch.tensor([8.0])])
+    [tensor([1.]), tensor([6.])]
+    """
 
     supports_subtasks = True
     max_subtasks_inflight = 0

@@ -11,6 +11,37 @@ from .base import LinearPreAggregator
 
 
 class Bucketing(LinearPreAggregator):
+    """Bucketing: shuffle the vectors, cut the shuffled list into buckets of ``bucket_size`` and return the bucket means.
+
+    Averaging inside random buckets dilutes each Byzantine vector with honest ones and reduces the variance the
+    aggregator that follows has to cope with; the output has ``ceil(n / bucket_size)`` vectors.
+
+    Parameters
+    ----------
+    bucket_size : int
+        Vectors per bucket (the last bucket may be smaller).
+    feature_chunk_size : int, default 8192
+        Coordinates per subtask on an actor pool.
+    perm : iterable of int, optional
+        A fixed permutation of ``range(n)`` to use instead of shuffling.
+    rng : random.Random, optional
+        Source of the shuffle; default: a fresh OS-seeded generator per instance, so two runs differ unless ``rng`` or
+        ``perm`` is given.
+
+    Notes
+    -----
+    The row map needs no Gram matrix.  In a fused device round the permutation is drawn on the host once per round
+    (``MapCwPlan.refresh`` / the Gram plan's weight refresh) and uploaded as the mixing matrix.
+
+    Examples
+    --------
+    >>> import torch
+    >>> from byzpy_b200.pre_aggregators import Bucketing
+    >>> xs = [torch.tensor([float(i)]) for i in range(5)]
+    >>> Bucketing(bucket_size=2, perm=[0, 1, 2, 3, 4]).pre_aggregate(xs)
+    [tensor([0.5000]), tensor([2.5000]), tensor([4.])]
+    """
+
     name = "pre-agg/bucketing"
     needs_gram = False
 

@@ -9,6 +9,29 @@ from .base import LinearPreAggregator
 
 
 class Clipping(LinearPreAggregator):
+    """Static norm clipping: scale every vector whose Euclidean norm exceeds ``threshold`` back onto that radius.
+
+    Parameters
+    ----------
+    threshold : float, default 2.0
+        Maximum norm after clipping (``>= 0``).
+    chunk_size : int, default 32
+        Vectors per subtask on an actor pool.
+
+    Notes
+    -----
+    A diagonal row map: only the row norms are needed (one norm pass), then ``n`` scaled copies -- or no copy at
+    all when an aggregator follows, which then folds the scales into its own pass over the data (the fused
+    coordinate-wise kernels take per-row scales; Gram-family aggregators rescale the Gram matrix).
+
+    Examples
+    --------
+    >>> import torch
+    >>> from byzpy_b200.pre_aggregators import Clipping
+    >>> Clipping(threshold=1.0).pre_aggregate([torch.tensor([3.0, 4.0]), torch.tensor([0.3, 0.4])])
+    [tensor([0.6000, 0.8000]), tensor([0.3000, 0.4000])]
+    """
+
     name = "pre-agg/clipping"
     gram_diag_only = True       # only the row norms are used: the torch fallback skips the n^2 d work
     diagonal_map = True
