@@ -34,6 +34,19 @@ def graph_input(name: str) -> GraphInput:
 
 @dataclass(frozen=True)
 class GraphNode:
+    """One node of a :class:`ComputationGraph`: an operator and where each of its inputs comes from.
+
+    Parameters
+    ----------
+    name : str
+        Unique name; other nodes refer to this node's result by it, schedulers return results keyed by it.
+    op : Operator
+        The operator to run.
+    inputs : mapping of str to source
+        For each input key of the operator: a :func:`graph_input` (data given at run time), the name of another node
+        (an edge), or a ``MessageSource`` (a message a :class:`MessageAwareNodeScheduler` waits for).
+    """
+
     name: str
     op: Operator
     inputs: Mapping[str, Any] = field(default_factory=dict)
@@ -44,6 +57,35 @@ def _is_message_source(dep: Any) -> bool:
 
 
 class ComputationGraph:
+    """A validated directed acyclic graph of operator nodes.
+
+    Parameters
+    ----------
+    nodes : sequence of GraphNode
+        At least one; names must be unique, every edge must name an existing node, cycles are rejected
+        (``ValueError``).
+    outputs : sequence of str, optional
+        Names of the nodes whose results a scheduler returns; default: the last node in topological order.
+
+    Attributes
+    ----------
+    required_inputs : names of the :func:`graph_input` placeholders the run must be fed.
+    outputs : the output node names.
+
+    Examples
+    --------
+    >>> import torch
+    >>> from byzpy_b200.aggregators.coordinate_wise import CoordinateWiseMedian
+    >>> from byzpy_b200.pre_aggregators import Clipping
+    >>> from byzpy_b200.engine.graph.graph import ComputationGraph, GraphNode, graph_input
+    >>> g = ComputationGraph([
+    ...     GraphNode("clip", Clipping(threshold=1.0), {"vectors": graph_input("grads")}),
+    ...     GraphNode("agg", CoordinateWiseMedian(), {"gradients": "clip"}),
+    ... ])
+    >>> sorted(g.required_inputs), list(g.outputs)
+    (['grads'], ['agg'])
+    """
+
     def __init__(self, nodes: Sequence[GraphNode], *, outputs: Optional[Sequence[str]] = None) -> None:
         if not nodes:
             raise ValueError("ComputationGraph requires at least one node.")

@@ -13,6 +13,24 @@ from .operator import Operator
 
 
 class GraphBuilder:
+    """Fluent construction of a :class:`~byzpy_b200.engine.graph.graph.ComputationGraph`.
+
+    ``input(name)`` declares run-time data and returns a :class:`LazyNode`; ``LazyNode.apply(operator)`` records a node
+    fed by it and returns the next lazy node; ``build(outputs)`` validates and returns the graph.  Nothing executes
+    until the graph is given to a scheduler.
+
+    Examples
+    --------
+    >>> from byzpy_b200.aggregators.coordinate_wise import CoordinateWiseMedian
+    >>> from byzpy_b200.pre_aggregators import Clipping
+    >>> from byzpy_b200.engine.graph.lazy import GraphBuilder
+    >>> b = GraphBuilder()
+    >>> out = b.input("vectors").apply(Clipping(threshold=1.0)).apply(CoordinateWiseMedian(), name="agg")
+    >>> g = b.build(outputs=[out.key])
+    >>> [n.name for n in g.nodes_in_order()]
+    ['pre-agg/clipping_0', 'agg']
+    """
+
     def __init__(self) -> None:
         self._nodes: Dict[str, GraphNode] = {}
         self._inputs: Dict[str, GraphInput] = {}
@@ -40,6 +58,14 @@ class GraphBuilder:
 
 
 class LazyNode:
+    """Handle on a not-yet-computed value inside a :class:`GraphBuilder` (an input or a recorded node).
+
+    ``apply(operator, input_key=None, extra_inputs=None, name=None)`` wires this value into ``operator`` under
+    ``input_key`` (default: the operator's own ``input_key``, e.g. ``"gradients"`` for aggregators and ``"vectors"`` for
+    pre-aggregators), optionally with further inputs (lazy nodes or names), and returns the handle of the new node.
+    ``key`` is the node (or input) name.
+    """
+
     def __init__(self, builder: GraphBuilder, key: str, is_input: bool = False) -> None:
         self._builder = builder
         self._key = key

@@ -67,6 +67,41 @@ class _StreamPool:
 
 
 class ParallelScheduler:
+    """Dataflow scheduler: every node starts as soon as its inputs are ready, independent branches run concurrently.
+
+    Parameters
+    ----------
+    graph : ComputationGraph
+    pool : ActorPool, optional
+        Shared by all concurrently running operators.
+    metadata : mapping, optional
+        As for :class:`~byzpy_b200.engine.graph.scheduler.NodeScheduler`.
+    max_concurrent_nodes : int, optional
+        Upper bound on nodes in flight.
+    max_pending_subtasks : int, optional
+        Upper bound on subtasks in flight over all running operators; default ``8 x pool.size``.
+
+    Notes
+    -----
+    Nodes whose inputs are CUDA tensors are issued on CUDA streams taken from a per-device stream pool, ordered by
+    events instead of host synchronisation, so independent branches overlap on the GPU as well as on the host.
+
+    Examples
+    --------
+    >>> import asyncio, torch
+    >>> from byzpy_b200.aggregators.coordinate_wise import CoordinateWiseMedian, CoordinateWiseTrimmedMean
+    >>> from byzpy_b200.engine.graph.lazy import GraphBuilder
+    >>> from byzpy_b200.engine.graph.parallel_scheduler import ParallelScheduler
+    >>> b = GraphBuilder()
+    >>> x = b.input("gradients")
+    >>> med = x.apply(CoordinateWiseMedian(), name="median")
+    >>> tm = x.apply(CoordinateWiseTrimmedMean(f=1), name="trimmed")
+    >>> grads = [torch.tensor([v]) for v in (1.0, 2.0, 6.0, 100.0)]
+    >>> out = asyncio.run(ParallelScheduler(b.build(outputs=["median", "trimmed"])).run({"gradients": grads}))
+    >>> out["median"], out["trimmed"]
+    (tensor([2.]), tensor([4.]))
+    """
+
     def __init__(self, graph: ComputationGraph, *, pool=None,
                  metadata: Optional[Mapping[str, Any]] = None,
                  max_concurrent_nodes: Optional[int] = None,

@@ -34,6 +34,22 @@ def _infer_capabilities(spec: Union[str, ActorBackend]) -> Sequence[str]:
 
 @dataclass(frozen=True)
 class ActorPoolConfig:
+    """One homogeneous group of workers of an :class:`ActorPool`.
+
+    Parameters
+    ----------
+    backend : str or ActorBackend
+        ``"thread"``, ``"process"``, ``"gpu"`` / ``"gpu:<index>"`` (a CUDA-stream worker), ``"tcp://host:port"``,
+        ``"ucx://host:port"``, or a backend instance.
+    count : int, default 1
+        Number of workers of this kind.
+    capabilities : sequence of str, optional
+        Tags subtasks can ask for through ``SubTask.affinity``; default ``("gpu",)`` for GPU / ucx backends, else
+        ``("cpu",)``.
+    name : str, optional
+        Prefix of the worker labels (``<name>-<index>``; default ``actor``).
+    """
+
     backend: Union[str, ActorBackend]
     count: int = 1
     capabilities: Optional[Sequence[str]] = None
@@ -142,6 +158,39 @@ class ActorPoolChannel:
 
 
 class ActorPool:
+    """A set of worker actors that run :class:`~byzpy_b200.engine.graph.subtask.SubTask` objects.
+
+    Parameters
+    ----------
+    configs : sequence of ActorPoolConfig
+        Worker groups; a pool may mix backends (threads for cheap tasks, CUDA-stream workers for kernels, remote
+        workers on other machines) and routes by ``SubTask.affinity``.
+
+    Notes
+    -----
+    ``await pool.start()`` brings the workers up concurrently, ``await pool.shutdown()`` closes them; ``size`` is the
+    number of workers (configured count before ``start``).  ``run_subtask`` / ``run_many`` hand each task to whichever idle
+    worker has the capability it asks for; a task whose worker fails is retried up to ``max_retries`` times.
+    ``open_channel(name)`` gives the workers named mailboxes to talk to each other.
+    ``in_process`` is true when all workers share this address space, in which case operators hand views instead of
+    shared-memory copies.  The pool pickles as its configuration only.
+
+    Examples
+    --------
+    >>> import asyncio
+    >>> from byzpy_b200.engine.graph.pool import ActorPool, ActorPoolConfig
+    >>> from byzpy_b200.engine.graph.subtask import SubTask
+    >>> async def demo():
+    ...     pool = ActorPool([ActorPoolConfig("thread", count=2)])
+    ...     await pool.start()
+    ...     try:
+    ...         return await pool.run_many([SubTask(fn=pow, args=(2, k)) for k in range(4)])
+    ...     finally:
+    ...         await pool.shutdown()
+    >>> asyncio.run(demo())
+    [1, 2, 4, 8]
+    """
+
     def __init__(self, configs: Sequence[ActorPoolConfig]) -> None:
         self.configs = list(configs)
         self._workers: List[_PoolWorker] = []

@@ -35,6 +35,30 @@ class MessageSource:
 
 
 class NodeScheduler:
+    """Runs a :class:`~byzpy_b200.engine.graph.graph.ComputationGraph` node by node in topological order.
+
+    Parameters
+    ----------
+    graph : ComputationGraph
+    pool : ActorPool, optional
+        Given a pool, operators that support subtasks may fan their work out to it (``Operator.run`` decides, see
+        ``BYZPY_POOL_DISPATCH``); without one every operator computes in the calling task.
+    metadata : mapping, optional
+        Merged into every operator's ``OpContext.metadata`` (``pool_size``, ``pool_in_process`` and
+        ``worker_affinities`` are filled in from the pool).
+
+    Examples
+    --------
+    >>> import asyncio, torch
+    >>> from byzpy_b200.aggregators.coordinate_wise import CoordinateWiseMedian
+    >>> from byzpy_b200.engine.graph.ops import make_single_operator_graph
+    >>> from byzpy_b200.engine.graph.scheduler import NodeScheduler
+    >>> graph = make_single_operator_graph(node_name="agg", operator=CoordinateWiseMedian(), input_keys=("gradients",))
+    >>> grads = [torch.tensor([1.0]), torch.tensor([5.0]), torch.tensor([2.0])]
+    >>> asyncio.run(NodeScheduler(graph).run({"gradients": grads}))
+    {'agg': tensor([2.])}
+    """
+
     def __init__(self, graph: ComputationGraph, *, pool=None,
                  metadata: Optional[Mapping[str, Any]] = None) -> None:
         self.graph = graph
@@ -81,6 +105,31 @@ class NodeScheduler:
 
 
 class MessageAwareNodeScheduler(NodeScheduler):
+    """A :class:`NodeScheduler` whose graphs may take inputs from messages that arrive while the graph runs.
+
+    An input declared as ``GraphInput.from_message("gradient", field="vector", timeout=5)`` makes the node wait until
+    somebody calls ``deliver_message("gradient", payload)`` (a decentralized node's message loop does); messages that
+    arrive before anyone waits are queued per type.  ``wait_for_message`` is the same primitive for hand-written
+    pipelines.
+
+    Examples
+    --------
+    >>> import asyncio
+    >>> from byzpy_b200.engine.graph.graph import ComputationGraph, GraphInput, GraphNode
+    >>> from byzpy_b200.engine.graph.ops import CallableOp
+    >>> from byzpy_b200.engine.graph.scheduler import MessageAwareNodeScheduler
+    >>> g = ComputationGraph([GraphNode("double", CallableOp(lambda x: 2 * x, input_mapping={"x": "x"}),
+    ...                                 {"x": GraphInput.from_message("number", field="value")})])
+    >>> async def demo():
+    ...     sched = MessageAwareNodeScheduler(g)
+    ...     task = asyncio.ensure_future(sched.run({}))
+    ...     await asyncio.sleep(0)
+    ...     sched.deliver_message("number", {"value": 21})
+    ...     return await task
+    >>> asyncio.run(demo())
+    {'double': 42}
+    """
+
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
         self._message_waiters: Dict[str, List[asyncio.Future]] = {}

@@ -17,6 +17,13 @@ from .parallel_scheduler import ParallelScheduler
 
 
 class ExecutionFuture:
+    """Handle on a graph execution started with :meth:`ExecutionSession.execute_async`.
+
+    Awaitable (``await fut`` or ``await fut.wait()``) for the ``{output name: value}`` mapping; ``done()``,
+    ``cancel()``, ``cancelled()`` as on an asyncio task; ``result(timeout=None)`` returns the mapping once finished
+    (raises when it is not); ``output_keys`` names what will be returned.
+    """
+
     def __init__(self, task: "asyncio.Task[Dict[str, Any]]", output_keys) -> None:
         self._task = task
         self._output_keys = tuple(output_keys)
@@ -55,6 +62,36 @@ class ExecutionFuture:
 
 
 class ExecutionSession:
+    """Runs graphs through a :class:`~byzpy_b200.engine.graph.parallel_scheduler.ParallelScheduler`, remembering results by node name.
+
+    Parameters
+    ----------
+    pool : ActorPool, optional
+    cache_intermediate : bool, default True
+        Keep every computed node's result; a later ``execute`` skips nodes whose *name* is cached (the cache does not look
+        at input values -- give nodes fed with different data different names, or call ``clear_cache``).
+    metadata : mapping, optional
+
+    Notes
+    -----
+    Use as ``async with ExecutionSession(pool) as s: ...``; the cache is dropped on exit.  ``get_cached`` /
+    ``is_cached`` inspect it.
+
+    Examples
+    --------
+    >>> import asyncio, torch
+    >>> from byzpy_b200.aggregators.coordinate_wise import CoordinateWiseMedian
+    >>> from byzpy_b200.engine.graph.ops import make_single_operator_graph
+    >>> from byzpy_b200.engine.graph.session import ExecutionSession
+    >>> graph = make_single_operator_graph(node_name="agg", operator=CoordinateWiseMedian(), input_keys=("gradients",))
+    >>> async def demo():
+    ...     async with ExecutionSession() as s:
+    ...         first = await s.execute(graph, {"gradients": [torch.tensor([1.0]), torch.tensor([3.0]), torch.tensor([2.0])]})
+    ...         return first, s.is_cached("agg")
+    >>> asyncio.run(demo())
+    ({'agg': tensor([2.])}, True)
+    """
+
     def __init__(self, pool=None, cache_intermediate: bool = True,
                  metadata: Optional[Mapping[str, Any]] = None) -> None:
         self.pool = pool

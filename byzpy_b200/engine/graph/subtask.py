@@ -14,6 +14,31 @@ from typing import Any, Callable, Mapping, Optional, Sequence
 
 @dataclass(frozen=True)
 class SubTask:
+    """A unit of work an operator hands to an :class:`~byzpy_b200.engine.graph.pool.ActorPool`.
+
+    Parameters
+    ----------
+    fn : callable
+        Runs on a worker as ``fn(*args, **kwargs)``.  It is shipped by value (cloudpickle) to process and remote
+        workers, so it must not close over unpicklable state.
+    args, kwargs :
+        Arguments.  Tensors travel through shared memory to process workers and as CUDA-IPC handles to ``ucx://``
+        workers; thread and GPU-stream workers receive the objects themselves.
+    name : str, optional
+        Label used in traces and error messages.
+    affinity : str, optional
+        Capability a worker must have: ``"cpu"``, ``"gpu"``, or one specific worker ``"worker::<pool-name>-<index>"``.
+    max_retries : int, default 0
+        How many times the pool re-runs the task on another worker after a worker failure.
+
+    Examples
+    --------
+    >>> from byzpy_b200.engine.graph.subtask import SubTask
+    >>> t = SubTask(fn=pow, args=(2, 10), name="pow")
+    >>> t.run(), t.pinned_to("cpu").affinity
+    (1024, 'cpu')
+    """
+
     fn: Callable[..., Any]
     args: Sequence[Any] = field(default_factory=tuple)
     kwargs: Mapping[str, Any] = field(default_factory=dict)
