@@ -18,6 +18,9 @@ from ..graph.scheduler import NodeScheduler
 
 @dataclass(frozen=True)
 class NodePipeline:
+    """A registered pipeline of a :class:`NodeApplication`: the computation graph and the metadata merged into each run.
+    """
+
     graph: ComputationGraph
     metadata: Optional[Mapping[str, Any]] = None
 
@@ -32,6 +35,46 @@ def _run_blocking(coro_fn):
 
 
 class NodeApplication:
+    """What a node can compute: an :class:`~byzpy_b200.engine.graph.pool.ActorPool` of its own plus named pipelines.
+
+    A pipeline is a :class:`~byzpy_b200.engine.graph.graph.ComputationGraph` registered under a name and run on
+    demand on the node's pool.  Decentralized nodes (:class:`~byzpy_b200.engine.node.decentralized.DecentralizedNode`)
+    execute their training logic through these pipelines.
+
+    Parameters
+    ----------
+    name : str
+        Node name (appears in scheduler metadata and error messages).
+    actor_pool : ActorPool or sequence of ActorPoolConfig
+        The node's private pool, or the configuration to build one from.
+    metadata : mapping, optional
+        Merged into every pipeline run's metadata.
+
+    Notes
+    -----
+    ``register_pipeline(name, graph, metadata=None)``; ``await run_pipeline(name, inputs)`` returns the graph's outputs
+    by node name; ``run_pipeline_sync`` does the same from synchronous code (it refuses to run inside a running event
+    loop); ``has_pipeline`` / ``list_pipelines``; ``await shutdown()`` closes the pool.
+
+    Examples
+    --------
+    >>> import asyncio, torch
+    >>> from byzpy_b200.aggregators.coordinate_wise import CoordinateWiseMedian
+    >>> from byzpy_b200.engine.graph.ops import make_single_operator_graph
+    >>> from byzpy_b200.engine.graph.pool import ActorPoolConfig
+    >>> from byzpy_b200.engine.node.application import NodeApplication
+    >>> app = NodeApplication(name="n0", actor_pool=[ActorPoolConfig("thread", count=1)])
+    >>> app.register_pipeline("robust", make_single_operator_graph(node_name="agg", operator=CoordinateWiseMedian(),
+    ...                                                              input_keys=("gradients",)))
+    >>> async def demo():
+    ...     try:
+    ...         return await app.run_pipeline("robust", {"gradients": [torch.tensor([1.0]), torch.tensor([9.0]), torch.tensor([2.0])]})
+    ...     finally:
+    ...         await app.shutdown()
+    >>> asyncio.run(demo())
+    {'agg': tensor([2.])}
+    """
+
     def __init__(self, *, name: str, actor_pool: Union[ActorPool, Sequence[ActorPoolConfig]],
                  metadata: Optional[Mapping[str, Any]] = None) -> None:
         self.name = name
@@ -89,6 +132,13 @@ class NodeApplication:
 
 
 class HonestNodeApplication(NodeApplication):
+    """A :class:`NodeApplication` with the two pipelines an honest node is expected to have.
+
+    ``"aggregate"`` (input ``gradients``) is run by :meth:`aggregate`; ``"honest_gradient"`` by :meth:`honest_gradient`.
+    Both return the single output of the pipeline; the ``*_sync`` variants are for synchronous callers.  Calling one
+    whose pipeline was never registered raises ``KeyError``.
+    """
+
     AGGREGATION_PIPELINE = "aggregate"
     GRADIENT_PIPELINE = "honest_gradient"
 
@@ -110,6 +160,11 @@ class HonestNodeApplication(NodeApplication):
 
 
 class ByzantineNodeApplication(NodeApplication):
+    """A :class:`NodeApplication` with the ``"attack"`` pipeline a Byzantine node is expected to have, run by
+    :meth:`run_attack` / :meth:`run_attack_sync` with whatever inputs the attack operator reads (``honest_grads``,
+    ``base_grad``, ``model`` / ``x`` / ``y``).
+    """
+
     ATTACK_PIPELINE = "attack"
 
     async def run_attack(self, *, inputs: Mapping[str, Any], metadata=None) -> Any:

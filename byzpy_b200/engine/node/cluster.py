@@ -13,6 +13,14 @@ NodeId = Union[int, str]
 
 
 class DecentralizedCluster:
+    """A set of :class:`~byzpy_b200.engine.node.decentralized.DecentralizedNode` objects managed together.
+
+    ``await add_node(node_id, application, topology=None, context=None, metadata=None)`` creates a node (default context:
+    a :class:`~byzpy_b200.engine.node.context.ProcessContext`) and returns it; the order of insertion defines the
+    topology index of each id.  ``await start_all()``, ``await shutdown_all()``, ``get_node(id)``,
+    ``await remove_node(id)``; ``nodes`` maps ids to nodes.
+    """
+
     def __init__(self) -> None:
         self.nodes: Dict[NodeId, DecentralizedNode] = {}
         self._node_id_map: Dict[int, NodeId] = {}

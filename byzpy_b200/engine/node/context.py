@@ -36,6 +36,15 @@ class PeerUnreachableError(ConnectionError, RuntimeError):
 
 
 class NodeContext(ABC):
+    """Where a decentralized node lives and how its messages travel: the transport contract.
+
+    Four methods: ``await start(node)`` attaches the context to its :class:`~byzpy_b200.engine.node.decentralized.
+    DecentralizedNode`; ``await send_message(to_node_id, message_type, payload)``; ``receive_messages()`` is an async
+    iterator of ``{"from", "type", "payload"}`` dicts that ends when the context shuts down; ``await shutdown()``.
+    Implementations: :class:`InProcessContext`, :class:`ProcessContext`, :class:`RemoteContext`,
+    :class:`MeshRemoteContext`.
+    """
+
     @abstractmethod
     async def start(self, node: "DecentralizedNode") -> None:
         ...
@@ -66,6 +75,38 @@ async def _drain(queue: "asyncio.Queue", is_running, idle: float = 0.1) -> Async
 
 # ------------------------------------------------------------------------------- in-process
 class InProcessContext(NodeContext):
+    """All nodes in one Python process: a class-level registry of asyncio queues.
+
+    Payloads are handed over by reference -- a CUDA tensor sent between two device-resident nodes is not copied.
+    Sending to an id that never started raises ``ValueError``.  The cheapest context; the default of
+    :class:`~byzpy_b200.engine.peer_to_peer.train.PeerToPeer` here.
+
+    Examples
+    --------
+    >>> import asyncio
+    >>> from byzpy_b200.engine.graph.pool import ActorPoolConfig
+    >>> from byzpy_b200.engine.node.application import NodeApplication
+    >>> from byzpy_b200.engine.node.context import InProcessContext
+    >>> from byzpy_b200.engine.node.decentralized import DecentralizedNode
+    >>> async def demo():
+    ...     nodes = [DecentralizedNode(node_id=i, application=NodeApplication(name=i, actor_pool=[ActorPoolConfig("thread")]),
+    ...                                context=InProcessContext()) for i in ("a", "b")]
+    ...     got = asyncio.get_running_loop().create_future()
+    ...     async def on_ping(sender, payload):
+    ...         got.set_result((sender, payload))
+    ...     nodes[1].register_message_handler("ping", on_ping)
+    ...     for n in nodes:
+    ...         await n.start()
+    ...     try:
+    ...         await nodes[0].send_message("b", "ping", {"x": 1})
+    ...         return await asyncio.wait_for(got, 5)
+    ...     finally:
+    ...         for n in nodes:
+    ...             await n.shutdown()
+    >>> asyncio.run(demo())
+    ('a', {'x': 1})
+    """
+
     _registry: Dict[Any, "InProcessContext"] = {}
 
     def __init__(self) -> None:
@@ -129,6 +170,24 @@ class _PipeReader(threading.Thread):
 
 
 class ProcessContext(NodeContext):
+    """One OS process per node: the node is mirrored inside a spawned child and runs there.
+
+    The child builds its own :class:`~byzpy_b200.engine.node.decentralized.DecentralizedNode` around the pickled
+    application (an ``init_callback`` registered on the node runs in the child, so models and data loaders can be
+    created where they are used), executes pipelines and autonomous tasks there, and talks to the parent over a duplex
+    pipe; the parent relays child-to-child messages.  Reader threads wake the event loops directly -- no polling.
+
+    Parameters
+    ----------
+    start_timeout : float, default 60.0
+        Seconds to wait for the child to report ready (a fresh interpreter importing torch takes a few).
+
+    Notes
+    -----
+    The reference's default context; here it is the default of ``DecentralizedCluster.add_node`` and selectable for
+    ``PeerToPeer`` with ``context_factory=lambda node_id, index: ProcessContext()`` or ``BYZPY_P2P_CONTEXT=process``.
+    """
+
     _registry: Dict[Any, "ProcessContext"] = {}
 
     def __init__(self, *, start_timeout: float = 60.0) -> None:
@@ -380,6 +439,17 @@ def _process_node_main(config_blob: bytes, conn) -> None:
 
 # ------------------------------------------------------------------------------------ remote
 class RemoteContext(NodeContext):
+    """Client of a :class:`~byzpy_b200.engine.node.remote_server.RemoteNodeServer` hub: every message goes to the
+    hub, which forwards it to the addressee's connection.
+
+    Parameters
+    ----------
+    host, port :
+        Address of the hub.
+    gpu_direct : bool, default False
+        Ship CUDA tensors as CUDA-IPC handles (hub and nodes on one machine) instead of staging them through the host.
+    """
+
     def __init__(self, host: str, port: int, *, gpu_direct: bool = False):
         self.host, self.port = host, int(port)
         self.gpu_direct = gpu_direct
@@ -431,6 +501,26 @@ class RemoteContext(NodeContext):
 
 # -------------------------------------------------------------------------------------- mesh
 class MeshRemoteContext(NodeContext):
+    """Full mesh over TCP: every node listens on its own address and dials every peer.
+
+    Parameters
+    ----------
+    local_host, local_port :
+        Where this node listens.
+    peer_addresses : dict
+        ``{node id: (host, port)}`` of the other nodes.
+    connect_timeout : float, default 5.0
+    reconnect_interval : float, default 2.0
+        Peers that are down are re-dialled this often in the background; nodes may start in any order.
+    gpu_direct : bool, default False
+        Ship CUDA tensors as CUDA-IPC handles between processes of one machine.
+
+    Notes
+    -----
+    A send uses the outbound connection to the peer and falls back to the connection the peer opened to us; when
+    neither exists it raises :class:`PeerUnreachableError`.
+    """
+
     def __init__(self, local_host: str, local_port: int, peer_addresses: Dict[Any, Tuple[str, int]],
                  connect_timeout: float = 5.0, reconnect_interval: float = 2.0, *,
                  gpu_direct: bool = False):

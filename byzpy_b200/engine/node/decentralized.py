@@ -40,6 +40,32 @@ async def _cancel(task: Optional[asyncio.Task], timeout: float = 1.0) -> None:
 
 
 class DecentralizedNode:
+    """One autonomous participant: an application (pool + pipelines), a message-aware scheduler, a router and a context.
+
+    Parameters
+    ----------
+    node_id : int or str
+    application : NodeApplication
+        What the node can compute.
+    context : NodeContext
+        Where it lives and how its messages travel.
+    topology : Topology, optional
+        Restricts whom it may talk to (``None``: anybody, and broadcasts reach nobody).
+    metadata : mapping, optional
+    node_id_map : dict, optional
+        Topology index -> node id, when ids are strings.
+
+    Notes
+    -----
+    ``await start()`` / ``await shutdown()``.  Outbound: ``send_message``, ``broadcast_message`` (out-neighbours),
+    ``multicast_message``.  Inbound messages wake pipelines waiting on that message type and are passed to the handler
+    registered with ``register_message_handler(type, async_fn(sender, payload))``; a handler that raises is recorded
+    in ``handler_errors`` and does not stop message processing.  ``await execute_pipeline(name, inputs)`` runs one of
+    the application's pipelines on the node's scheduler; ``await start_autonomous_task(coro, name)`` parks a background
+    task (a training loop) that is cancelled on shutdown.  See :class:`~byzpy_b200.engine.node.context.InProcessContext`
+    for a runnable example.
+    """
+
     def __init__(self, *, node_id: NodeId, application: NodeApplication, context: NodeContext,
                  topology: Optional[Any] = None, metadata: Optional[Mapping[str, Any]] = None,
                  node_id_map: Optional[Dict[int, str]] = None):

@@ -32,6 +32,21 @@ Tensor = torch.Tensor
 
 
 class P2PHonestMixin:
+    """The honest side of a gossip round, for nodes that keep a ``torch.nn.Module``.
+
+    Mix it into a node class that provides ``model``, ``device``, ``criterion``, ``next_batch()``, a robust aggregator
+    ``p2p_agg`` and optionally a pre-aggregator ``p2p_pre``.  A round is two calls:
+
+    * :meth:`p2p_half_step` ``(lr)`` -- one local SGD step on the next batch; returns the flat parameter vector to
+      broadcast;
+    * :meth:`p2p_aggregate_and_set` ``(own, neighbour_vectors)`` -- robustly aggregate own and received vectors and
+      load the result into the model.
+
+    :meth:`get_param_vector` / :meth:`set_param_vector` expose the model as one flat vector.  When the node holds a
+    :class:`~byzpy_b200.parallel.arena.ParamArena` over its model (attribute ``arena``), all four work on the arena's
+    flat buffers without per-parameter copies.
+    """
+
     model: nn.Module
     device: torch.device
     criterion: nn.Module
@@ -88,6 +103,11 @@ class P2PHonestMixin:
 
 
 class P2PByzantineMixin:
+    """The Byzantine side of a gossip round: :meth:`p2p_broadcast_vector` hands the vectors received from honest
+    neighbours to ``self.attack`` (as ``honest_grads``) and returns the crafted vector, cast to the dtype and device of
+    ``like``.
+    """
+
     device: torch.device
     attack: Attack
 

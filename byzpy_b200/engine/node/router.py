@@ -14,6 +14,26 @@ NodeId = Union[int, str]
 
 
 class MessageRouter:
+    """Sends a node's outgoing messages through its context, as far as the topology allows.
+
+    All ``route_*`` methods are coroutines taking the message type, the payload and the
+    :class:`~byzpy_b200.engine.node.context.NodeContext` to send through: ``route_direct(target, ...)`` refuses
+    self-sends and targets that are not out-neighbours (``ValueError``), ``route_broadcast(...)`` sends to the
+    de-duplicated out-neighbours and carries on past individual failures, ``route_multicast(targets, ...)`` validates
+    every target before sending, ``route_reply(original_message, ...)`` answers its sender.  ``get_out_neighbors`` /
+    ``get_in_neighbors`` / ``can_send_to`` answer questions about the neighbourhood.  Ids can be topology integers
+    or strings translated through ``node_id_map``; without a topology everything is allowed and a broadcast reaches
+    nobody.
+
+    Examples
+    --------
+    >>> from byzpy_b200.engine.node.router import MessageRouter
+    >>> from byzpy_b200.engine.peer_to_peer.topology import Topology
+    >>> r = MessageRouter(topology=Topology.ring(4, 1), node_id="n0", node_id_map={i: f"n{i}" for i in range(4)})
+    >>> r.get_out_neighbors(), r.can_send_to("n2")
+    (['n1', 'n3'], False)
+    """
+
     def __init__(self, *, topology: Optional[Any] = None, node_id: NodeId,
                  node_id_map: Optional[Dict[int, str]] = None):
         self.topology = topology

@@ -48,6 +48,74 @@ def _is_device_node(node: Any) -> bool:
 
 
 class ParameterServer:
+    """Synchronous robust training with a central aggregator.
+
+    One :meth:`round`: every honest node computes a gradient on its next batch; every Byzantine node produces its vector
+    after seeing the honest ones (omniscient adversary); the optional pre-aggregator and then the aggregator reduce the
+    ``n`` vectors to one; the result is sent back to the honest nodes (and to the Byzantine ones when
+    ``update_byzantines``), which apply it with their own optimizer.
+
+    Parameters
+    ----------
+    honest_nodes, byzantine_nodes : list
+        Node objects or node actors (:class:`~byzpy_b200.engine.node.actors.HonestNodeActor` /
+        ``ByzantineNodeActor``); on the multi-GPU device path each process passes the nodes it hosts.
+    aggregator : Aggregator
+    pre_aggregator : PreAggregator, optional
+    update_byzantines : bool, default False
+    actor_pool : ActorPool, optional
+        Run the aggregation through a :class:`~byzpy_b200.engine.graph.scheduler.NodeScheduler` on this pool
+        (generic path only).
+    scheduler_metadata : dict, optional
+    node_timeout : float, optional
+        Seconds a node may take to answer before it counts as failed for the round.
+    tolerate_failures : bool, default False
+        Skip nodes that raise or time out (recorded in ``failed`` as ``(round, "honest:<i>", reason)``) instead of
+        propagating the error.
+    fused : bool, optional
+        ``None``: use the fused device round when every node is a device node on CUDA; ``True``: require it;
+        ``False``: always take the generic, actor-driven path.
+    layout, process_group, lr, momentum, weight_decay, amp_dtype, use_cuda_graph, worker_streams, direct_grads,
+    overlap_wgrad, branch_streams, buckets, multicast, device_options :
+        Device-path configuration, see :class:`byzpy_b200.parallel.device_ps.DeviceRound` and
+        ``docs/source/device_path.md``.  ``layout=RowLayout(...)`` says which worker rows each GPU hosts;
+        ``buckets`` cuts the gradient into buckets that are aggregated while backward is still running;
+        ``multicast`` selects NVLS multicast delivery of the aggregate.
+
+    Notes
+    -----
+    Device path: all replicas of a GPU train in one captured graph, gradients land in a symmetric-memory arena, and
+    aggregation, the attack's row folds, the optimizer step and the delivery of the update happen in one kernel per
+    bucket reading peer memory over NVLink (``csrc/fused_ps.cu``).  :meth:`step` enqueues a round without waiting,
+    :meth:`round` additionally returns the aggregate, :meth:`recover` drops a rank that stopped answering and carries
+    on with the rest.  Generic path: gradients are collected in node order (the reference: completion order), so
+    order-sensitive operators see the same worker in the same row every round.
+
+    Examples
+    --------
+    >>> import asyncio, torch
+    >>> from byzpy_b200.aggregators.coordinate_wise import CoordinateWiseMedian
+    >>> from byzpy_b200.engine.parameter_server.ps import ParameterServer
+    >>> class Honest:
+    ...     def __init__(self, g):
+    ...         self.g, self.seen = torch.tensor(g), None
+    ...     def honest_gradient_for_next_batch(self):
+    ...         return self.g
+    ...     def apply_server_gradient(self, g):
+    ...         self.seen = g
+    >>> class Liar:
+    ...     def byzantine_gradient_for_next_batch(self, honest_grads=None):
+    ...         return -100.0 * torch.stack(list(honest_grads)).mean(0)
+    ...     def apply_server_gradient(self, g):
+    ...         pass
+    >>> honest = [Honest([1.0, 1.0]), Honest([2.0, 0.0]), Honest([3.0, 2.0])]
+    >>> ps = ParameterServer(honest, [Liar()], CoordinateWiseMedian())
+    >>> asyncio.run(ps.round())
+    tensor([1., 0.])
+    >>> honest[0].seen
+    tensor([1., 0.])
+    """
+
     def __init__(self, honest_nodes: List[Any], byzantine_nodes: List[Any], aggregator: Aggregator,
                  pre_aggregator: Optional[PreAggregator] = None, update_byzantines: bool = False, *,
                  actor_pool=None, scheduler_metadata: Optional[dict] = None, layout=None,

@@ -26,6 +26,31 @@ def _unique(seq: List[int]) -> List[int]:
 
 
 class Topology:
+    """Directed communication graph over nodes ``0 .. n-1``: who sends its model to whom in a gossip round.
+
+    Parameters
+    ----------
+    n_nodes : int
+    edges : iterable of (int, int)
+        Directed edges ``(source, destination)``; an undirected link is two edges.
+
+    Notes
+    -----
+    ``Topology.complete(n)`` links every ordered pair, ``Topology.ring(n, k=1)`` every node with its ``k`` nearest
+    neighbours on both sides.  ``out_neighbors(i)`` / ``in_neighbors(i)`` list a node's peers (duplicates removed unless
+    ``unique=False``), ``edges()`` all edges, ``out`` / ``in_`` the raw adjacency lists.
+
+    Examples
+    --------
+    >>> from byzpy_b200.engine.peer_to_peer.topology import Topology
+    >>> Topology.ring(5, 1).out_neighbors(0)
+    [1, 4]
+    >>> Topology.complete(3).in_neighbors(2)
+    [0, 1]
+    >>> Topology(3, [(0, 1), (1, 2)]).edges()
+    [Edge(u=0, v=1), Edge(u=1, v=2)]
+    """
+
     def __init__(self, n_nodes: int, edges: Iterable[Tuple[int, int]]):
         self.n = n = int(n_nodes)
         self.out: Dict[int, List[int]] = {i: [] for i in range(n)}
