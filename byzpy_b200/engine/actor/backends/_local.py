@@ -87,6 +87,15 @@ intra_op_governor = IntraOpGovernor()
 
 
 class LocalMailboxBackend:
+    """Mailbox and addressing half of every in-host backend (thread, process, gpu).
+
+    Keeps one asyncio queue per channel name, registers the actor with the process-wide
+    :class:`~byzpy_b200.engine.actor.router.ChannelRouter`, and implements ``chan_open`` / ``chan_put`` / ``chan_get``:
+    a put to an actor of this process goes straight onto its queue, a put to a ``tcp://`` / ``ucx://`` endpoint goes
+    through the transport, tensors bound for another process are parked in shared memory first.  Subclasses add where
+    the hosted object runs (``construct`` / ``call`` / ``close``).
+    """
+
     scheme = "thread"
 
     def __init__(self) -> None:

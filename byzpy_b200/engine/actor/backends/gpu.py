@@ -52,6 +52,19 @@ def _record_stream(obj: Any, stream) -> None:
 
 
 class GPUActorBackend(LocalMailboxBackend):
+    """Hosts the object on a worker thread bound to one CUDA device and stream (``"gpu"`` / ``"gpu:<index>"``).
+
+    Every call runs with the actor's stream current, so kernels launched by different GPU actors overlap on the
+    device; results are handed to the caller ordered by an event on that stream (and ``record_stream`` keeps the
+    allocator from recycling them early) rather than by a device synchronisation.  Without CUDA it degrades to a thread
+    actor.
+
+    Parameters
+    ----------
+    device : int, optional
+        CUDA device index; default: round-robin over the visible devices.
+    """
+
     scheme = "gpu"
 
     def __init__(self, device: Optional[int] = None) -> None:
@@ -131,6 +144,17 @@ class UCXRemoteActorBackend(RemoteActorBackend):
 
 
 class UCXRemoteActorServer(RemoteActorServer):
+    """Actor server for ``ucx://host:port`` clients: like :class:`~byzpy_b200.engine.actor.backends.remote.RemoteActorServer`,
+    but CUDA tensors in calls, results and channel messages cross the process boundary as CUDA-IPC handles (the
+    receiver maps the sender's memory; same machine only) instead of being staged through the host.
+
+    Parameters
+    ----------
+    host : str, default "127.0.0.1"
+    port : int, default 0
+        0 picks a free port; ``address()`` tells which.
+    """
+
     scheme = "ucx"
     gpu_direct = True
 

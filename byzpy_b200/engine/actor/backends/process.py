@@ -109,6 +109,14 @@ def _thread_share() -> int:
 
 
 class ProcessActorBackend(LocalMailboxBackend):
+    """Hosts the object in a child process of its own (``"process"``).
+
+    The class and every call travel over a duplex pipe (cloudpickle); tensors in arguments and results are parked in POSIX
+    shared memory instead of being pickled, and released when the call is over -- also when it is cancelled.  Children
+    are started with the ``forkserver`` method (``BYZPY_MP_START=spawn`` to change it) and share the host's cores: each
+    call tells the child how many intra-op threads it may use.
+    """
+
     scheme = "process"
 
     def __init__(self) -> None:

@@ -27,6 +27,18 @@ def _is_local(host: str) -> bool:
 
 
 class RemoteActorBackend:
+    """Client side of an actor hosted by a :class:`RemoteActorServer` on another machine (``"tcp://host:port"``).
+
+    One TCP connection per backend; ``construct`` ships the class by value, calls are request/response frames
+    (length-prefixed pickles) serialised by a lock.  If a call is cancelled or fails mid-exchange the connection is
+    dropped and re-opened on the next call, so a late reply can never be mistaken for the answer to a later request.
+
+    Parameters
+    ----------
+    host, port :
+        Address of the server.
+    """
+
     scheme = "tcp"
     gpu_direct = False
 
@@ -138,6 +150,25 @@ class RemoteActorBackend:
 
 
 class RemoteActorServer:
+    """Hosts actors for remote clients: ``await RemoteActorServer(host, port).serve()``.
+
+    Each client connection may construct actors, call them, open their mailboxes and post to them.  Frames are
+    unpickled, so whoever can reach the port can run code in this process: the default binds the loopback interface;
+    pass ``host="0.0.0.0"`` explicitly on a trusted network.
+
+    Parameters
+    ----------
+    host : str, default "127.0.0.1"
+    port : int, default 29000
+        0 picks a free port (``port`` holds it after ``start()``).
+
+    Notes
+    -----
+    ``await start()`` binds without blocking, ``await serve()`` binds and serves until cancelled, ``await stop()``
+    closes the listener.  :func:`start_actor_server` is ``serve()`` as a one-liner for scripts
+    (``examples/distributed/server.py``).
+    """
+
     scheme = "tcp"
     gpu_direct = False
 

@@ -11,6 +11,27 @@ from ._local import LocalMailboxBackend, intra_op_governor
 
 
 class ThreadActorBackend(LocalMailboxBackend):
+    """Hosts the object on a dedicated single-thread executor of this process (``"thread"``).
+
+    Method calls are serialised on that thread, so the object needs no locking of its own, and arguments and results are
+    passed by reference (no pickling, CUDA tensors stay where they are).  When several thread actors compute at once
+    the host's intra-op threads are divided between them (``BYZPY_INTRAOP_GOVERNOR=0`` disables that).
+
+    Examples
+    --------
+    >>> import asyncio
+    >>> from byzpy_b200.engine.actor.base import ActorRef
+    >>> from byzpy_b200.engine.actor.backends.thread import ThreadActorBackend
+    >>> async def demo():
+    ...     be = ThreadActorBackend()
+    ...     async with ActorRef(be) as ref:
+    ...         await be.construct(list, args=([3, 1, 2],), kwargs={})
+    ...         await ref.sort()
+    ...         return await ref.copy()
+    >>> asyncio.run(demo())
+    [1, 2, 3]
+    """
+
     scheme = "thread"
 
     def __init__(self) -> None:

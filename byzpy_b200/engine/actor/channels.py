@@ -14,6 +14,20 @@ from .ipc import unwrap_payload
 
 
 class Endpoint(NamedTuple):
+    """Global address of an actor: ``(scheme, address, actor_id)``.
+
+    ``scheme`` is the kind of backend hosting it (``"thread"``, ``"process"``, ``"gpu"``, ``"tcp"``, ``"ucx"``),
+    ``address`` the ``host:port`` its server listens on (empty for in-host schemes), ``actor_id`` a unique id there.
+    A plain named tuple: it pickles and travels inside messages, which is how actors introduce each other.
+
+    Examples
+    --------
+    >>> from byzpy_b200.engine.actor.channels import Endpoint
+    >>> ep = Endpoint("tcp", "10.0.0.5:29000", "abc")
+    >>> str(ep), ep.is_remote()
+    ('tcp://10.0.0.5:29000/abc', True)
+    """
+
     scheme: str      # "thread" | "process" | "gpu" | "tcp" | "ucx"
     address: str     # "host:port" for tcp / ucx, "" otherwise
     actor_id: str
@@ -27,6 +41,15 @@ class Endpoint(NamedTuple):
 
 
 class ChannelRef:
+    """A local actor's handle on one of its named mailboxes.
+
+    ``await ch.send(endpoint, payload)`` posts to the same-named mailbox of the actor at ``endpoint`` (whatever backend
+    hosts it -- delivery is in-process when possible, else shared memory, TCP or CUDA-IPC); ``await ch.recv(timeout=None)``
+    takes the next payload from its own mailbox (``None`` on timeout); ``ch.endpoint`` is the address to give peers.
+    Obtained from ``await ActorRef.open_channel(name)`` / :func:`open_channel`; a runnable tour is in
+    ``examples/actor_demo/actor_demo.py``.
+    """
+
     __slots__ = ("_backend", "_local", "_name")
 
     def __init__(self, backend, local_ep: Endpoint, name: str):

@@ -10,12 +10,31 @@ from typing import Any, Dict, Optional, Tuple
 
 @dataclass(frozen=True)
 class BackendRecord:
+    """One row of the :class:`ChannelRouter` table: which backend object hosts actor ``actor_id`` of ``scheme``.
+    """
+
     scheme: str
     actor_id: str
     backend: Any
 
 
 class ChannelRouter:
+    """Process-wide registry of the actor backends living in this process.
+
+    Backends register themselves under ``(scheme, actor_id)``; when one of them must deliver a channel message to an
+    endpoint, ``resolve`` tells it whether the addressee is in this process (then the payload is put on its asyncio
+    queue directly) or has to be reached through a transport.  Thread safe.  The module-level ``channel_router`` is the
+    instance everybody uses.
+
+    Examples
+    --------
+    >>> from byzpy_b200.engine.actor.router import ChannelRouter
+    >>> r = ChannelRouter()
+    >>> r.register("thread", "a1", backend := object())
+    >>> r.resolve("thread", "a1") is backend, r.resolve("thread", "nobody")
+    (True, None)
+    """
+
     def __init__(self) -> None:
         self._lock = threading.Lock()
         self._table: Dict[Tuple[str, str], BackendRecord] = {}

@@ -17,6 +17,14 @@ MessageFn = Callable[[dict, Any], dict]
 
 
 class NodeCluster:
+    """Named :class:`~byzpy_b200.engine.node_runner.NodeRunner` processes plus an optional message transport (legacy).
+
+    ``add_node(node_id, step_fn, msg_handler, init_state=None)``, ``start_all()``, ``stop_all()``, ``send(node_id, msg)``,
+    ``state(node_id)``.  With ``transport=LocalTransport()`` or ``TcpTransport()`` messages go through the transport (the
+    same script then runs in-process or over loopback sockets); without one they are written to the runner's pipe.
+    ``examples/p2p/decentralized_demo.py`` is a complete program.
+    """
+
     def __init__(self, transport=None) -> None:
         self._transport = transport
         self._nodes: Dict[str, NodeRunner] = {}

@@ -70,6 +70,25 @@ def _runner_main(cmd_conn, inbox_conn, blob: bytes) -> None:
 
 
 class NodeRunner:
+    """A blocking, process-per-node state machine (legacy building block, kept for parity with the reference).
+
+    The child process holds a ``state`` dict and two user functions: ``step_fn(state) -> state`` and
+    ``msg_handler(state, msg) -> state``.  The parent drives it with commands.
+
+    Parameters
+    ----------
+    step_fn : callable
+    msg_handler : callable
+    init_state : dict, optional
+
+    Notes
+    -----
+    ``start()`` spawns the child and waits for its handshake; ``step()`` runs one step (the inbox is drained first);
+    ``start_auto(interval)`` / ``stop_auto()`` step periodically; ``send_message(msg)`` posts into the inbox;
+    ``state()`` fetches a copy of the state; ``stop()`` ends the process.  New code should use
+    :class:`~byzpy_b200.engine.node.decentralized.DecentralizedNode`.
+    """
+
     def __init__(self, step_fn: Callable[[dict], dict], msg_handler: Callable[[dict, Any], dict], *,
                  init_state: Optional[dict] = None) -> None:
         ctx = process_context()      # fork-server with torch preloaded ("spawn" semantics, fast start)

@@ -11,6 +11,18 @@ from typing import Any, Callable, Dict, Iterable
 
 
 class LocalTransport:
+    """Same-process :class:`~byzpy_b200.engine.transport.base.Transport`: ``send`` calls the registered handler on the
+    caller's thread.  ``delivered`` counts deliveries per node; sending to an unknown node raises ``KeyError``.
+
+    Examples
+    --------
+    >>> from byzpy_b200.engine.transport.local import LocalTransport
+    >>> t, seen = LocalTransport(), []
+    >>> t.register("n0", seen.append)
+    >>> t.send("n0", {"x": 1}); seen, t.delivered["n0"]
+    ([{'x': 1}], 1)
+    """
+
     def __init__(self) -> None:
         self._lock = threading.Lock()
         self._deliver: Dict[str, Callable[[Any], None]] = {}

@@ -17,6 +17,16 @@ class _Route(NamedTuple):
 
 
 class TcpTransport:
+    """Loopback-socket :class:`~byzpy_b200.engine.transport.base.Transport`: every registered node gets a
+    :class:`~byzpy_b200.engine.transport.tcp_simple.TcpMailbox` on a free port and a pump thread that feeds its handler;
+    ``send`` connects to the addressee's port and writes one length-prefixed pickle.  ``close()`` stops the pumps and
+    the listeners.
+
+    Parameters
+    ----------
+    host : str, default "127.0.0.1"
+    """
+
     def __init__(self, host: str = "127.0.0.1") -> None:
         self._host = host
         self._routes: Dict[str, _Route] = {}

@@ -51,6 +51,22 @@ class _Server(socketserver.ThreadingTCPServer):
 
 
 class TcpMailbox:
+    """A listening socket with a queue behind it: the smallest possible TCP inbox.
+
+    Each accepted connection delivers one length-prefixed pickled payload.  ``recv(timeout=None)`` returns the next one
+    (``queue.Empty`` on timeout), ``host`` / ``port`` say where to send (``port=0`` picks a free one), ``close()`` stops the
+    server thread.  Payloads are unpickled: loopback or trusted networks only.
+
+    Examples
+    --------
+    >>> from byzpy_b200.engine.transport.tcp_simple import TcpMailbox, send_message
+    >>> box = TcpMailbox()
+    >>> send_message((box.host, box.port), {"hello": 1})
+    >>> box.recv(timeout=5)
+    {'hello': 1}
+    >>> box.close()
+    """
+
     def __init__(self, host: str = "127.0.0.1", port: int = 0) -> None:
         self._srv = _Server((host, port), _FrameHandler)
         self._srv.inbox = queue.Queue()  # type: ignore[attr-defined]
