@@ -26,6 +26,30 @@ BatchSource = Callable[[], Tuple[torch.Tensor, torch.Tensor]]
 
 
 class DeviceHonestNode(HonestNode):
+    """An honest worker that lives on a GPU: model, loss, optimizer state and data source.
+
+    With nodes of this kind :class:`~byzpy_b200.engine.parameter_server.ps.ParameterServer` takes its fused device path:
+    all replicas of a GPU run forward and backward in one captured CUDA graph and write their gradients into rows of a
+    symmetric-memory arena, where the fused kernels aggregate them.  The same object also satisfies the generic node
+    contract (``next_batch`` / ``honest_gradient`` / ``apply_server_gradient``), so it works through actors on any
+    backend, CPU included.
+
+    Parameters
+    ----------
+    model : torch.nn.Module
+    loss_fn : callable, optional
+        Default cross entropy.
+    data : callable, optional
+        ``() -> (inputs, targets)``; may return host tensors (pinned memory makes the copy asynchronous).
+    lr, momentum, weight_decay : float
+        SGD hyper-parameters applied by the fused optimizer step (or by ``ensure_optimizer()`` on the generic path).
+    device : str, optional
+        Default ``"cuda"`` when available.
+    preprocess : callable, optional
+        Applied to the inputs on the device (normalisation, layout change) inside the captured graph.
+    name : str
+    """
+
     def __init__(self, model: nn.Module, loss_fn: Optional[Callable] = None, *,
                  data: Optional[BatchSource] = None, lr: float = 0.05, momentum: float = 0.9,
                  weight_decay: float = 0.0, device: Optional[str] = None,
@@ -169,6 +193,16 @@ class DeviceP2PHonestNode(P2PHonestMixin):
 
 
 class DeviceP2PByzantineNode(P2PByzantineMixin):
+    """Byzantine gossip node for the device path: holds the :class:`~byzpy_b200.attacks.base.Attack` the fused P2P
+    round folds into its kernels (or applies through ``p2p_broadcast_vector`` on the generic path).
+
+    Parameters
+    ----------
+    attack : Attack
+    device : str, optional
+    name : str
+    """
+
     def __init__(self, attack: Attack, *, device: Optional[str] = None, name: str = "p2p-byz"):
         self.device = torch.device(device or ("cuda" if torch.cuda.is_available() else "cpu"))
         self.attack = attack

@@ -44,6 +44,26 @@ class _DistributedNodeBase:
 
 
 class DistributedHonestNode(_DistributedNodeBase, HonestNode):
+    """Base class of honest nodes whose gradient and aggregation work runs as pipelines on the node's own actor pool.
+
+    Subclass it, implement ``local_honest_gradient(*, x, y)`` plus ``next_batch`` / ``apply_server_gradient``; the
+    constructor registers the ``"honest_gradient"`` and ``"aggregate"`` pipelines.  ``honest_gradient(x, y)`` then runs
+    the gradient pipeline, ``await aggregate(gradients)`` / ``aggregate_sync`` the node's aggregator.
+
+    Parameters
+    ----------
+    actor_pool : ActorPool or sequence of ActorPoolConfig
+    aggregator : Aggregator
+        Used when this node aggregates (P2P) -- the parameter server has its own.
+    metadata : mapping, optional
+    name : str, optional
+
+    Notes
+    -----
+    ``examples/ps/nodes.py`` (``DistributedPSHonestNode``) is the canonical subclass; ``await shutdown_distributed()``
+    closes the pool.
+    """
+
     def __init__(self, *, actor_pool: PoolSpec, aggregator: Aggregator,
                  metadata: Optional[Mapping[str, object]] = None, name: Optional[str] = None) -> None:
         self._aggregator = aggregator
@@ -73,6 +93,21 @@ class DistributedHonestNode(_DistributedNodeBase, HonestNode):
 
 
 class DistributedByzantineNode(_DistributedNodeBase, ByzantineNode):
+    """Base class of Byzantine nodes whose attack runs as the ``"attack"`` pipeline on the node's own actor pool.
+
+    Either pass an :class:`~byzpy_b200.attacks.base.Attack` (its ``uses_*`` flags decide which of ``honest_grads`` /
+    ``base_grad`` / ``model, x, y`` it is given), or override ``byzantine_gradient`` in the subclass -- the override is
+    shipped to the pool as the body of the pipeline and the public ``byzantine_gradient(x, y, honest_grads)`` keeps the
+    calling convention orchestrators use.
+
+    Parameters
+    ----------
+    actor_pool : ActorPool or sequence of ActorPoolConfig
+    attack : Attack, optional
+    metadata : mapping, optional
+    name : str, optional
+    """
+
     _distributed_user_bz = None
 
     def __init_subclass__(cls, **kwargs):

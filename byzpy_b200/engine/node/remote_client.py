@@ -45,6 +45,19 @@ async def read_frame(reader: asyncio.StreamReader) -> Dict[str, Any]:
 
 
 class RemoteNodeClient:
+    """One TCP connection to a :class:`~byzpy_b200.engine.node.remote_server.RemoteNodeServer`.
+
+    ``await connect(timeout=5.0)``; ``await register_node(node_id)`` announces an id this client owns;
+    ``await send_message(to, type, payload)``; ``await receive_message(timeout=None)`` returns the next message the
+    server forwarded (``None`` on timeout); ``is_connected()``; ``await disconnect()``.  Used by :class:`~byzpy_b200.engine.node.context.RemoteContext`; frames are written under a
+    lock so concurrent senders cannot interleave.
+
+    Parameters
+    ----------
+    host, port :
+    gpu_direct : bool, default False
+    """
+
     def __init__(self, host: str, port: int, *, gpu_direct: bool = False):
         self.host, self.port = host, int(port)
         self.gpu_direct = gpu_direct

@@ -16,6 +16,11 @@ from .remote_client import read_frame, write_frame
 
 
 class ServerNodeContext(NodeContext):
+    """Context of a node hosted *on* a :class:`RemoteNodeServer`: peers registered on the same server are reached
+    through the in-process registry, everybody else through the server's connection to the client that announced that
+    id.
+    """
+
     def __init__(self, server: "RemoteNodeServer", in_process_context: InProcessContext):
         self.server = server
         self.inner = in_process_context
@@ -42,6 +47,25 @@ class ServerNodeContext(NodeContext):
 
 
 class RemoteNodeServer:
+    """Hub of the hub-and-spoke deployment: relays messages between
+    :class:`~byzpy_b200.engine.node.context.RemoteContext` clients, and can host nodes itself.
+
+    Parameters
+    ----------
+    host : str, default "localhost"
+    port : int, default 8888
+        0 picks a free port (``port`` holds it after ``start()``).
+    gpu_direct : bool, default False
+        Forward CUDA tensors as CUDA-IPC handles (all clients on this machine).
+
+    Notes
+    -----
+    ``await start()`` binds, ``await serve()`` serves until cancelled, ``await shutdown()`` closes every connection,
+    ``await register_node(node)`` hosts a :class:`~byzpy_b200.engine.node.decentralized.DecentralizedNode` on the
+    server.  A client announces the node ids it owns with a ``_register_node`` frame; frames are length-prefixed
+    pickles, so expose the port on trusted networks only.  ``examples/p2p/remote_tcp/server.py`` runs one.
+    """
+
     def __init__(self, host: str = "localhost", port: int = 8888, *, gpu_direct: bool = False):
         self.host, self.port = host, int(port)
         self.gpu_direct = gpu_direct

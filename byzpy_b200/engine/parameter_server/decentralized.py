@@ -21,6 +21,25 @@ def _grad_reader(node) -> Callable[[], torch.Tensor]:
 
 
 class DecentralizedParameterServer:
+    """Async facade over the process-per-node :class:`~byzpy_b200.engine.parameter_server.runner.ParameterServerRunner`
+    (kept for scripts written against the reference's prototype).
+
+    Parameters
+    ----------
+    honest_nodes : list
+        Objects exposing the gradient to submit as ``.grad``.
+    byzantine_nodes : list, optional
+        Accepted for signature compatibility; the prototype does not simulate them.
+    aggregator : callable
+        ``sequence of tensors -> tensor``.
+
+    Notes
+    -----
+    ``await bootstrap()`` starts the processes, ``await round()`` returns the aggregate of one round,
+    ``await shutdown()`` stops them.  For real training use
+    :class:`~byzpy_b200.engine.parameter_server.ps.ParameterServer`.
+    """
+
     def __init__(self, honest_nodes: List, byzantine_nodes: Optional[List], aggregator: Aggregate) -> None:
         self._honest = list(honest_nodes)
         self._byz = list(byzantine_nodes or [])

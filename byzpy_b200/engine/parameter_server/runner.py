@@ -64,6 +64,26 @@ class _Server:
 
 
 class ParameterServerRunner:
+    """A prototype parameter server built from blocking :class:`~byzpy_b200.engine.node_runner.NodeRunner` processes.
+
+    One server process and one process per worker.  ``run_round()`` steps every worker (each calls its gradient
+    function), forwards the gradients to the server, steps the server (which aggregates its inbox) and returns the
+    result.
+
+    Parameters
+    ----------
+    worker_grad_fns : list of callables
+        One ``() -> tensor`` per worker (shipped to the worker process by value).
+    aggregator : callable, optional
+        ``sequence of tensors -> tensor``; default :func:`mean_aggregate`.
+    transport : Transport, optional
+        ``LocalTransport()`` / ``TcpTransport()`` to route messages through a transport instead of the runners' pipes.
+
+    Notes
+    -----
+    ``start()`` / ``stop()`` bracket the rounds.  ``examples/ps/decentralized_demo.py`` is a complete program.
+    """
+
     def __init__(self, worker_grad_fns: List[GradFn], aggregator: Optional[AggFn] = None, *,
                  transport=None) -> None:
         self.cluster = NodeCluster(transport=transport)

@@ -157,6 +157,35 @@ def _default_context() -> NodeContext:
 
 
 class DecentralizedPeerToPeer:
+    """Message-driven gossip training over :class:`~byzpy_b200.engine.node.decentralized.DecentralizedNode` objects.
+
+    Every node (honest first, then Byzantine; ids ``"0" .. "n-1"`` in that order, matching the topology indices) gets a
+    decentralized node with ``half_step`` / ``aggregate`` (honest) or ``broadcast`` (Byzantine) pipelines wrapped around
+    the user's node object.  A round: honest nodes take a local half step and send the resulting parameter vector to
+    their out-neighbours; Byzantine nodes wait for their honest in-neighbours' vectors, craft one vector from them and
+    broadcast it; every honest node robustly aggregates its own and the received vectors and loads the result.
+
+    Parameters
+    ----------
+    honest_nodes, byzantine_nodes : list
+        Node objects or node actors implementing the P2P mixin methods (``p2p_half_step`` + ``p2p_aggregate_and_set`` or
+        just ``p2p_aggregate``; ``p2p_broadcast_vector``).
+    topology : Topology
+    lr : float, default 0.05
+    context_factory : callable, optional
+        ``(node_id, index) -> NodeContext``; default :class:`~byzpy_b200.engine.node.context.InProcessContext` (or
+        ``ProcessContext`` with ``BYZPY_P2P_CONTEXT=process``).
+    recv_timeout : float, default 30.0
+        Longest a node waits for its neighbours' vectors before going on with what it has.
+
+    Notes
+    -----
+    ``await start()``, ``await run_round_async()`` (``run_round()`` from synchronous code), ``await stop()``;
+    ``rounds`` counts completed rounds, ``cluster`` is the underlying
+    :class:`~byzpy_b200.engine.node.cluster.DecentralizedCluster`.  Usually reached through
+    :class:`~byzpy_b200.engine.peer_to_peer.train.PeerToPeer`.
+    """
+
     def __init__(self, honest_nodes: List[Any], byzantine_nodes: List[Any], topology: Topology, *,
                  lr: float = 0.05, context_factory: Optional[Callable[[str, int], NodeContext]] = None,
                  recv_timeout: float = 30.0) -> None:

@@ -26,6 +26,22 @@ import torch
 
 @dataclass(frozen=True)
 class SharedTensorHandle:
+    """Name, shape and dtype of an array living in a POSIX shared-memory segment.
+
+    Small and picklable: this is what crosses a process boundary instead of the data.  Operators accept handles (or the
+    equivalent ``{"name", "shape", "dtype"}`` dict) wherever they accept tensors.
+
+    Examples
+    --------
+    >>> import torch
+    >>> from byzpy_b200.engine.storage.shared_store import cleanup_tensor, open_tensor, register_tensor
+    >>> h = register_tensor(torch.arange(6.0).reshape(2, 3))
+    >>> with open_tensor(h) as view:
+    ...     print(h.shape, h.dtype, float(view.sum()))
+    (2, 3) float32 15.0
+    >>> cleanup_tensor(h)
+    """
+
     name: str
     shape: Tuple[int, ...]
     dtype: str
@@ -44,11 +60,14 @@ def _coerce(handle: SharedHandleLike) -> SharedTensorHandle:
 
 
 def is_handle(obj: Any) -> bool:
+    """True for a :class:`SharedTensorHandle` or a dict with its three keys."""
     return isinstance(obj, SharedTensorHandle) or (
         isinstance(obj, dict) and {"name", "shape", "dtype"} <= set(obj.keys()))
 
 
 def register_tensor(array: Any) -> SharedTensorHandle:
+    """Copy a tensor / array into a fresh shared-memory segment and return its handle.  The caller owns the
+    segment: :func:`cleanup_tensor` unlinks it."""
     if isinstance(array, torch.Tensor):
         array = array.detach().cpu().numpy()
     arr = np.ascontiguousarray(array)
@@ -106,6 +125,7 @@ def attach_cached(handle: SharedHandleLike) -> np.ndarray:
 
 @contextmanager
 def open_tensor(handle: SharedHandleLike) -> Iterator[np.ndarray]:
+    """Context manager mapping a segment as a NumPy array (a view, not a copy; do not keep it past the block)."""
     h = _coerce(handle)
     seg = shared_memory.SharedMemory(name=h.name)
     try:
@@ -115,6 +135,7 @@ def open_tensor(handle: SharedHandleLike) -> Iterator[np.ndarray]:
 
 
 def cleanup_tensor(handle: SharedHandleLike) -> None:
+    """Unlink the segment (idempotent); the memory is freed once the last mapping is closed."""
     h = _coerce(handle)
     try:
         seg = shared_memory.SharedMemory(name=h.name)

@@ -16,6 +16,13 @@ _REGISTRY = {
 
 
 def build_model(name: str, **kw):
+    """Model by name: ``smallcnn``, ``resnet18`` / ``34`` / ``50``, ``bert-base``; keyword arguments go to the
+    constructor.
+
+    >>> from byzpy_b200.models import build_model
+    >>> type(build_model("smallcnn")).__name__
+    'SmallCNN'
+    """
     try:
         return _REGISTRY[name.lower()](**kw)
     except KeyError as exc:

@@ -20,6 +20,10 @@ import torch.nn.functional as F
 
 @dataclass
 class BertConfig:
+    """Sizes of a BERT encoder; the defaults are BERT-base (12 layers, hidden 768, 12 heads, FFN 3072, vocabulary
+    30 522, 512 positions).  ``dropout`` defaults to 0 so that a captured training step is deterministic.
+    """
+
     vocab_size: int = 30522
     hidden: int = 768
     layers: int = 12
@@ -52,6 +56,14 @@ class _Block(nn.Module):
 
 
 class BertEncoder(nn.Module):
+    """BERT encoder stack: token + position + type embeddings, LayerNorm, then ``config.layers`` post-LN transformer
+    blocks (fused QKV projection, ``scaled_dot_product_attention``, GELU FFN).
+
+    ``forward(ids, attention_mask=None)`` takes ``(batch, seq)`` token ids and an optional ``(batch, seq)`` 0/1 mask and
+    returns ``(batch, seq, hidden)`` states.  The linear layers are arena-aware: inside a device worker their weight
+    gradients are written straight into the node's gradient arena.
+    """
+
     def __init__(self, config: BertConfig | None = None):
         super().__init__()
         c = config or BertConfig()
@@ -102,4 +114,6 @@ class BertForMaskedLM(nn.Module):
 
 
 def bert_base(**overrides) -> BertForMaskedLM:
+    """BERT-base with a masked-language-model head (110 M parameters); keyword arguments override
+    :class:`BertConfig` fields, e.g. ``bert_base(layers=2, hidden=128, heads=2, ffn=512)`` for tests."""
     return BertForMaskedLM(BertConfig(**overrides))

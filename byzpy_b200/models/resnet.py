@@ -68,6 +68,11 @@ def _join(idt: torch.Tensor, fork) -> torch.Tensor:
 
 
 class BasicBlock(nn.Module):
+    """Two 3 x 3 convolutions with an identity (or 1 x 1 projection) shortcut -- the ResNet-18 / 34 block.  BatchNorm,
+    ReLU and the residual add are fused (one kernel per BatchNorm), and the projection shortcut runs on a side stream
+    when the model is captured with branch streams.
+    """
+
     expansion = 1
     supports_branch_stream = True
 
@@ -87,6 +92,10 @@ class BasicBlock(nn.Module):
 
 
 class Bottleneck(nn.Module):
+    """1 x 1 reduce, 3 x 3, 1 x 1 expand (x 4) with a shortcut -- the ResNet-50 block; same fusions as
+    :class:`BasicBlock`.
+    """
+
     expansion = 4
     supports_branch_stream = True
 
@@ -109,6 +118,34 @@ class Bottleneck(nn.Module):
 
 
 class ResNet(nn.Module):
+    """ResNet v1 (torchvision layout and parameter names) built from fused layers.
+
+    Parameters
+    ----------
+    block : BasicBlock or Bottleneck
+    depths : sequence of 4 ints
+        Blocks per stage.
+    num_classes : int, default 1000
+    in_channels : int, default 3
+    small_input : bool, default False
+        CIFAR-style stem (3 x 3 convolution, no max-pool) for 32 x 32 inputs.
+
+    Notes
+    -----
+    On sm_100a the 7 x 7 / stride-2 stem runs as a space-to-depth 4 x 4 convolution, BatchNorm + ReLU (+ residual) are
+    single kernels (one launch per activation through thread-block clusters when it fits, ``csrc/bn.cu``), and weight
+    gradients can be written directly into a gradient arena.  On CPU every fused layer falls back to the equivalent
+    ``torch.nn`` computation, with the same parameters.
+
+    Examples
+    --------
+    >>> import torch
+    >>> from byzpy_b200.models import resnet18
+    >>> net = resnet18(num_classes=10, small_input=True).eval()
+    >>> net(torch.zeros(1, 3, 32, 32)).shape, sum(p.numel() for p in net.parameters())
+    (torch.Size([1, 10]), 11173962)
+    """
+
     def __init__(self, block: Type[Union[BasicBlock, Bottleneck]], depths: Sequence[int],
                  num_classes: int = 1000, in_channels: int = 3, small_input: bool = False):
         super().__init__()
@@ -156,12 +193,15 @@ class ResNet(nn.Module):
 
 
 def resnet18(num_classes: int = 1000, **kw) -> ResNet:
+    """ResNet-18 (11.7 M parameters at 1000 classes): the model of the headline benchmark."""
     return ResNet(BasicBlock, (2, 2, 2, 2), num_classes, **kw)
 
 
 def resnet34(num_classes: int = 1000, **kw) -> ResNet:
+    """ResNet-34 (21.8 M parameters at 1000 classes)."""
     return ResNet(BasicBlock, (3, 4, 6, 3), num_classes, **kw)
 
 
 def resnet50(num_classes: int = 1000, **kw) -> ResNet:
+    """ResNet-50 (25.6 M parameters at 1000 classes), bottleneck blocks."""
     return ResNet(Bottleneck, (3, 4, 6, 3), num_classes, **kw)

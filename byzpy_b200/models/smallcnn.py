@@ -11,6 +11,26 @@ import torch.nn.functional as F
 
 
 class SmallCNN(nn.Module):
+    """The MNIST network of the reference's examples and of its published parameter-server benchmark.
+
+    ``conv(in, 32, 3) - relu - pool - conv(32, 64, 3) - relu - pool - fc(3136, 128) - relu - fc(128, classes)`` for
+    28 x 28 inputs; 421 642 parameters with the defaults.  Parameter names match the reference's class, so state dicts
+    interchange.
+
+    Parameters
+    ----------
+    in_channels : int, default 1
+    num_classes : int, default 10
+
+    Examples
+    --------
+    >>> import torch
+    >>> from byzpy_b200.models import SmallCNN
+    >>> net = SmallCNN()
+    >>> net(torch.zeros(2, 1, 28, 28)).shape, sum(p.numel() for p in net.parameters())
+    (torch.Size([2, 10]), 421642)
+    """
+
     def __init__(self, in_channels: int = 1, num_classes: int = 10):
         super().__init__()
         self.conv1 = nn.Conv2d(in_channels, 32, 3, padding=1)
