@@ -25,6 +25,7 @@ ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
 def ext_path() -> Path:
+    """Where the built kernel library lives: ``byzpy_b200/_C<EXT_SUFFIX>`` inside the source tree."""
     suffix = sysconfig.get_config_var("EXT_SUFFIX") or ".so"
     return PKG_DIR / f"_C{suffix}"
 
@@ -37,6 +38,7 @@ def _nvcc() -> str:
 
 
 def sources() -> list[Path]:
+    """Every ``.cu`` / ``.cpp`` file under ``csrc/``, sorted."""
     return sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cpp")))
 
 

@@ -12,6 +12,9 @@ def _flag(name: str) -> bool:
 
 
 def preferred_device() -> str:
+    """``"cuda"`` when a CUDA device is usable, else ``"cpu"``; ``BYZPY_FORCE_CPU`` / ``BYZPY_FORCE_GPU`` override (the latter
+    raises when there is no device).
+    """
     if _flag("BYZPY_FORCE_CPU"):
         return "cpu"
     try:
@@ -27,6 +30,7 @@ def preferred_device() -> str:
 
 
 def base_requirements():
+    """Run-time requirements of the package."""
     return ["torch>=2.6", "numpy>=1.24", "cloudpickle>=2.2", "tqdm>=4.65", "pybind11>=2.11"]
 
 
@@ -34,14 +38,17 @@ def base_requirements():
 # GPU is detected.  Here the GPU path has no extra wheels (the kernels are compiled in-tree by nvcc, CUDA tensors
 # travel as CUDA-IPC handles), so the GPU list is empty and the full list does not depend on the machine.
 def get_dependencies():
+    """Requirements to install on this machine (the same everywhere: no per-platform GPU wheels)."""
     return list(base_requirements())
 
 
 def get_gpu_optional_dependencies():
+    """Extra wheels of the GPU path: none, the kernels are compiled in-tree."""
     return []
 
 
 def get_dev_optional_dependencies():
+    """Requirements of the test-suite."""
     return ["pytest>=8", "pytest-timeout", "hypothesis"]
 
 

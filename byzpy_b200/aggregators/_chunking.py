@@ -42,6 +42,13 @@ def _ceil_div(a: int, b: int) -> int:
 def select_adaptive_chunk_size(total_items: int, configured_chunk: int, *,
                                pool_size: Optional[int] = None, min_chunks_per_worker: int = 4,
                                max_shrink_factor: int = 8, allow_small_chunks: bool = False) -> int:
+    """Subtask granularity for ``total_items`` items on a pool of ``pool_size`` workers.
+
+    Starts from the operator's configured chunk and shrinks it (by at most ``max_shrink_factor``) until every worker has
+    about ``min_chunks_per_worker`` chunks to steal from; small inputs keep the configured chunk unless
+    ``allow_small_chunks``.  ``BYZPY_CHUNK_MIN_PER_WORKER`` / ``BYZPY_CHUNK_MAX_SHRINK`` / ``BYZPY_CHUNK_TARGET_FACTOR`` tune it
+    (same names as the reference, aggregators/_chunking.py).
+    """
     if total_items <= 0:
         return 0
     base = min(max(1, int(configured_chunk)), total_items)

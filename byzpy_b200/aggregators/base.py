@@ -111,6 +111,7 @@ def _kernel_rows(rows: List[torch.Tensor]) -> List[torch.Tensor]:
 
 
 def pool_size_of(context: Optional[OpContext]) -> int:
+    """Number of pool workers the running scheduler announced in the operator context (0: no pool)."""
     meta = (context.metadata if context is not None else None) or {}
     return int(meta.get("pool_size") or 0)
 
@@ -159,6 +160,7 @@ class _Packed:
 
 
 def feature_chunks(d: int, chunk: int) -> Iterable[Tuple[int, int]]:
+    """``(start, end)`` pairs cutting ``range(d)`` into pieces of at most ``chunk`` coordinates."""
     for s in range(0, d, chunk):
         yield s, min(d, s + chunk)
 

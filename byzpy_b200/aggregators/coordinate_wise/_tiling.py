@@ -11,6 +11,7 @@ from ...engine.storage.shared_store import materialize
 
 
 def flatten_gradients(gradients: Sequence[Any]) -> Tuple[Tuple[int, ...], np.ndarray]:
+    """``(feature shape, (n, d) float array)`` of a gradient list (tensors, arrays or shared-memory handles)."""
     arrays = [materialize(g).detach().cpu().numpy() for g in gradients]
     stacked = np.stack(arrays, axis=0)
     return tuple(stacked.shape[1:]), stacked.reshape(stacked.shape[0], -1)

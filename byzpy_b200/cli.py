@@ -177,6 +177,9 @@ def _cmd_bench(args: argparse.Namespace) -> int:
 
 
 def build_parser() -> argparse.ArgumentParser:
+    """The ``byzpy-b200`` argument parser: ``version``, ``doctor``, ``list``, ``build``, ``bench`` (the first three as in the
+    reference's CLI, reference cli.py).
+    """
     parser = argparse.ArgumentParser(prog="byzpy-b200",
                                      description="Utilities for inspecting byzpy_b200 installations.")
     sub = parser.add_subparsers(dest="command", required=True)
@@ -200,6 +203,7 @@ def build_parser() -> argparse.ArgumentParser:
 
 
 def main(argv: Optional[Sequence[str]] = None) -> int:
+    """Entry point of the ``byzpy-b200`` console script; returns the exit status (``argv`` defaults to ``sys.argv[1:]``)."""
     args = build_parser().parse_args(argv)
     if getattr(args, "rest", None) and args.rest and args.rest[0] == "--":
         args.rest = args.rest[1:]

@@ -55,6 +55,9 @@ _finder = None
 
 
 def install_alias() -> None:
+    """Make ``import byzpy`` (and every ``byzpy.x.y``) resolve to ``byzpy_b200`` (``byzpy_b200.x.y``) from now on, through a
+    meta-path finder; idempotent.  Both names then refer to the SAME module objects.
+    """
     global _finder
     if _finder is None:
         _finder = _AliasFinder()
@@ -62,6 +65,7 @@ def install_alias() -> None:
 
 
 def uninstall_alias() -> None:
+    """Remove the finder and the ``byzpy*`` aliases it created from ``sys.modules``."""
     global _finder
     if _finder is not None:
         sys.meta_path.remove(_finder)

@@ -27,11 +27,13 @@ def set_backend(backend) -> None:
 
 
 def get_backend():
+    """The array backend object currently selected for this process."""
     return get_array_backend(_current)
 
 
 @contextmanager
 def use_backend(backend) -> Iterator[None]:
+    """Context manager: select array backend ``backend`` (``"torch"`` / ``"numpy"``) inside the block."""
     global _current
     prev = _current
     set_backend(backend)

@@ -15,6 +15,7 @@ MAX_FRAME = (1 << 32) - 1
 
 
 def encode(obj: Any) -> bytes:
+    """``obj`` as one frame: 4-byte big-endian length + cloudpickle body."""
     body = cloudpickle.dumps(obj, protocol=pickle.HIGHEST_PROTOCOL)
     if len(body) > MAX_FRAME:
         raise ValueError("frame too large")
@@ -22,11 +23,13 @@ def encode(obj: Any) -> bytes:
 
 
 async def send_obj(w: asyncio.StreamWriter, obj: Any) -> None:
+    """Write ``obj`` as one frame to the stream writer ``w`` and drain."""
     w.write(encode(obj))
     await w.drain()
 
 
 async def recv_obj(r: asyncio.StreamReader) -> Any:
+    """Read one frame from the stream reader ``r`` and unpickle it."""
     (n,) = _HDR.unpack(await r.readexactly(_HDR.size))
     return cloudpickle.loads(await r.readexactly(n))
 

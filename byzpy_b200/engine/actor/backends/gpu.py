@@ -169,6 +169,7 @@ class UCXRemoteActorServer(RemoteActorServer):
 
 
 async def start_ucx_actor_server(host: str = "127.0.0.1", port: int = 0) -> None:
+    """Serve a :class:`UCXRemoteActorServer` on ``host:port`` until cancelled."""
     await UCXRemoteActorServer(host, port).serve()
 
 

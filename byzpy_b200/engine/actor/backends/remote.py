@@ -284,6 +284,7 @@ class RemoteActorServer:
 
 
 async def start_actor_server(host: str, port: int) -> None:
+    """Serve a :class:`RemoteActorServer` on ``host:port`` until cancelled."""
     await RemoteActorServer(host, port).serve()
 
 

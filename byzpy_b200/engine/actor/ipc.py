@@ -35,6 +35,9 @@ def _batchable(seq) -> bool:
 
 
 def wrap_payload(obj: Any) -> Any:
+    """Replace every tensor / array in a nested payload by a tagged shared-memory handle (lists of equally shaped CPU
+    tensors share one segment) so the payload can cross a process boundary without pickling the data.
+    """
     if isinstance(obj, torch.Tensor):
         return (_SHM_MARK, register_tensor(obj.detach().cpu().numpy()))
     if isinstance(obj, np.ndarray):
@@ -68,6 +71,7 @@ def _take(handle: SharedTensorHandle) -> torch.Tensor:
 
 
 def unwrap_payload(obj: Any) -> Any:
+    """Inverse of :func:`wrap_payload`: copy the data out of shared memory and unlink the segments (single consumer)."""
     if isinstance(obj, tuple) and len(obj) == 2 and obj[0] == _SHM_MARK:
         return _take(obj[1])
     if isinstance(obj, tuple) and len(obj) == 4 and obj[0] == _SHM_BATCH_MARK:

@@ -21,6 +21,7 @@ import torch
 
 
 def available() -> bool:
+    """CUDA-IPC payloads need a CUDA device in this process."""
     return torch.cuda.is_available()
 
 
@@ -76,6 +77,9 @@ def _ensure_context() -> None:
 
 
 def loads(data: bytes) -> Any:
+    """Rebuild a payload written by :func:`dumps`: ``b"I"`` frames map the sender's device memory (CUDA-IPC handles),
+    ``b"V"`` frames carry host copies.
+    """
     tag, body = data[:1], data[1:]
     if tag == b"I":
         _ensure_context()

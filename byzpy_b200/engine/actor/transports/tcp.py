@@ -9,11 +9,15 @@ from .._wire import recv_obj, send_obj
 
 
 def parse_address(address: str) -> Tuple[str, int]:
+    """``"host:port"`` -> ``(host, port)``."""
     host, port = address.rsplit(":", 1)
     return host, int(port)
 
 
 async def request(host: str, port: int, msg: dict, timeout: Optional[float] = None) -> Any:
+    """One request/response exchange with the actor server at ``host:port`` over a fresh connection; raises what the
+    server reports.
+    """
     reader, writer = await asyncio.open_connection(host, port)
     try:
         await send_obj(writer, msg)
@@ -46,6 +50,9 @@ def _target(address, port, actor_id, to_ep):
 
 async def chan_put(address: str, port: Optional[int] = None, actor_id: Optional[str] = None, name: Optional[str] = None,
                    payload: Any = None, *, from_ep: Any = None, to_ep: Any = None) -> None:
+    """Post ``payload`` to mailbox ``name`` of a remote actor.  Accepts ``(host, port, actor_id, name, payload)`` and the
+    reference's ``(address, to_ep=..., name=..., payload=...)`` calling convention.
+    """
     host, port, actor_id = _target(address, port, actor_id, to_ep)
     msg = {"op": "chan_put", "actor_id": actor_id, "name": name, "payload": payload}
     if to_ep is not None and not isinstance(to_ep, dict):
@@ -55,6 +62,9 @@ async def chan_put(address: str, port: Optional[int] = None, actor_id: Optional[
 
 async def chan_get(address: str, port: Optional[int] = None, actor_id: Optional[str] = None, name: Optional[str] = None,
                    timeout: Optional[float] = None) -> Any:
+    """Take the next payload from mailbox ``name`` of a remote actor (``None`` on timeout); both calling conventions of
+    :func:`chan_put`.
+    """
     host, port, actor_id = _target(address, port, actor_id, None)
     return await request(host, port, {"op": "chan_get", "actor_id": actor_id, "name": name,
                                       "timeout": timeout},

@@ -69,6 +69,7 @@ def _drop_dead_loops() -> None:
 
 
 def is_same_host(host: str) -> bool:
+    """True for loopback addresses: CUDA-IPC handles are only meaningful on the machine that exported them."""
     return host in ("127.0.0.1", "localhost", "0.0.0.0", "::1")
 
 
@@ -86,6 +87,7 @@ async def get_endpoint(host: str, port: int) -> Endpoint:
 
 
 def evict_endpoint(host: str, port: int) -> None:
+    """Close and forget the pooled connection to ``host:port`` (the next use re-opens it)."""
     ep = _EP_CACHE.pop(_key(host, port), None)
     if ep is not None:
         try:
@@ -95,6 +97,7 @@ def evict_endpoint(host: str, port: int) -> None:
 
 
 async def clear_pool() -> None:
+    """Close every pooled connection of this process."""
     here = _key("", 0)[0]
     for key in list(_EP_CACHE):
         _, writer = _EP_CACHE.pop(key)
@@ -167,6 +170,7 @@ async def send_control(ep: Endpoint, obj: Dict[str, Any]) -> None:
 
 
 async def recv_control(ep: Endpoint) -> Dict[str, Any]:
+    """Read one control frame (a dict) from the endpoint."""
     return await recv_obj(ep[0])
 
 
@@ -181,16 +185,19 @@ async def send_payload(ep: Endpoint, tag: str, desc: Any, obj: Any = None) -> No
 
 
 async def recv_payload(ep: Endpoint) -> Any:
+    """Read one payload written by :func:`send_payload` and rebuild it (CUDA tensors arrive as mapped device memory)."""
     ctrl = await recv_control(ep)
     return unpack_payload(ctrl["desc"])
 
 
 def pack_payload(obj: Any, *, same_host: bool = True) -> Tuple[str, bytes]:
+    """``(tag, bytes)`` of a payload: CUDA-IPC handles when ``same_host``, host copies otherwise."""
     blob = cuda_ipc.dumps(obj, same_host=same_host)
     return ("cuda" if blob[:1] == b"I" else "pickle"), blob
 
 
 def unpack_payload(blob: bytes) -> Any:
+    """Inverse of :func:`pack_payload`."""
     return cuda_ipc.loads(blob)
 
 
@@ -217,6 +224,7 @@ async def chan_put(host: str, port: int, actor_id: str, name: str, payload: Any)
 
 
 async def chan_get(host: str, port: int, actor_id: str, name: str, timeout: Optional[float]) -> Any:
+    """Take the next payload from mailbox ``name`` of actor ``actor_id`` hosted at ``host:port`` (``None`` on timeout)."""
     out = await request(host, port, {"op": "chan_get", "actor_id": actor_id, "name": name, "timeout": timeout},
                         timeout=None if timeout is None else timeout + 5.0)
     if isinstance(out, dict) and "__cuda_ipc__" in out:

@@ -129,6 +129,9 @@ _BACKENDS = {"torch": _TorchBackend, "numpy": _NumpyBackend}
 
 
 def get_array_backend(name: str = "torch"):
+    """Array backend by name: ``"torch"`` or ``"numpy"`` (the small array API operators written against the backend
+    protocol use; ``configs.backend.set_backend`` selects the process default).
+    """
     try:
         return _BACKENDS[name]()
     except KeyError:

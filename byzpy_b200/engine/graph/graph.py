@@ -29,6 +29,7 @@ class GraphInput:
 
 
 def graph_input(name: str) -> GraphInput:
+    """Placeholder for data handed to the scheduler at run time under ``name``."""
     return GraphInput(name)
 
 

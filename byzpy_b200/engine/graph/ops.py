@@ -60,6 +60,7 @@ class RemoteCallableOp(Operator):
 
 def make_single_operator_graph(*, node_name: str, operator: Operator,
                                input_keys: Sequence[str]) -> ComputationGraph:
+    """The one-node graph ``operator(input_keys...) -> node_name``: every input key becomes a run-time graph input."""
     node = GraphNode(name=node_name, op=operator, inputs={k: graph_input(k) for k in input_keys})
     return ComputationGraph([node], outputs=[node_name])
 

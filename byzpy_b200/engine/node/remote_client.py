@@ -19,12 +19,16 @@ _LEN = struct.Struct(">I")
 
 
 def serialize_message(msg: Dict[str, Any], *, gpu_direct: bool = False) -> bytes:
+    """Message dict -> bytes: ``b"G"`` + CUDA-IPC pickle when ``gpu_direct`` (tensors stay on the device), else ``b"P"`` +
+    cloudpickle with tensors moved to the host.
+    """
     if gpu_direct and cuda_ipc.available():
         return b"G" + cuda_ipc.dumps(msg, same_host=True)
     return b"P" + cloudpickle.dumps(cuda_ipc._to_host(msg))
 
 
 def deserialize_message(data: bytes) -> Dict[str, Any]:
+    """Inverse of :func:`serialize_message` (untagged frames are read as plain cloudpickle)."""
     tag, body = data[:1], data[1:]
     if tag == b"G":
         return cuda_ipc.loads(body)
@@ -34,12 +38,14 @@ def deserialize_message(data: bytes) -> Dict[str, Any]:
 
 
 async def write_frame(writer: asyncio.StreamWriter, msg: Dict[str, Any], *, gpu_direct: bool = False) -> None:
+    """Write one length-prefixed message to the stream and drain it."""
     body = serialize_message(msg, gpu_direct=gpu_direct)
     writer.write(_LEN.pack(len(body)) + body)
     await writer.drain()
 
 
 async def read_frame(reader: asyncio.StreamReader) -> Dict[str, Any]:
+    """Read one length-prefixed message from the stream."""
     (n,) = _LEN.unpack(await reader.readexactly(_LEN.size))
     return deserialize_message(await reader.readexactly(n))
 

@@ -25,6 +25,7 @@ SERVER = "server"
 
 
 def mean_aggregate(grads: Sequence[torch.Tensor]) -> torch.Tensor:
+    """Arithmetic mean of the gradients: the default (non-robust) aggregator of the prototype runner."""
     total = grads[0].clone()
     for g in grads[1:]:
         total += g

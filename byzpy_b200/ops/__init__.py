@@ -49,18 +49,22 @@ _LAUNCHES = [0]
 
 
 def count_launch(k: int = 1) -> None:
+    """Record ``k`` launches of this library's kernels made from a Python-side layer wrapper."""
     _LAUNCHES[0] += k
 
 
 def launches() -> int:
+    """Kernel launches recorded so far by :func:`count_launch` (``bench.py`` reports the per-step difference)."""
     return _LAUNCHES[0]
 
 
 def extension_available() -> bool:
+    """True when the compiled sm_100a kernel library (``byzpy_b200._C``) can be imported."""
     return _load_ext() is not None
 
 
 def require_ext():
+    """The kernel library module, or ``RuntimeError`` when it is not built: CUDA inputs never fall back to PyTorch silently."""
     ext = _load_ext()
     if ext is None:
         raise RuntimeError(
@@ -75,6 +79,7 @@ _SM_COUNT: dict = {}
 
 
 def sm_count(device: torch.device) -> int:
+    """Number of SMs of ``device`` (cached); the persistent kernels size their grids from it."""
     idx = device.index if device.index is not None else torch.cuda.current_device()
     if idx not in _SM_COUNT:
         _SM_COUNT[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
@@ -243,18 +248,23 @@ def _unpack_update(update: Optional[dict]):
 
 
 def cw_median(rows: Rows, **kw) -> torch.Tensor:
+    """Coordinate-wise (lower) median of the rows; keyword arguments as for :func:`cw_select`."""
     return cw_select(rows, MODE_MEDIAN, 0, **kw)
 
 
 def cw_trimmed_mean(rows: Rows, f: int, **kw) -> torch.Tensor:
+    """Coordinate-wise mean after trimming the ``f`` smallest and ``f`` largest values; see :func:`cw_select`."""
     return cw_select(rows, MODE_TRMEAN, f, **kw)
 
 
 def cw_meamed(rows: Rows, f: int, **kw) -> torch.Tensor:
+    """Coordinate-wise mean of the ``n - f`` values closest to the median; see :func:`cw_select`."""
     return cw_select(rows, MODE_MEAMED, f, **kw)
 
 
 def cw_mean(rows: Rows, **kw) -> torch.Tensor:
+    """Coordinate-wise mean through the selection kernel's load path (same row handling: scales, synthesised rows); see
+    :func:`cw_select`."""
     return cw_select(rows, MODE_MEAN, 0, **kw)
 
 
@@ -467,6 +477,9 @@ def colstat(rows: Rows, a: float, b: float, *, scales=None, out=None) -> torch.T
 # element-wise helpers
 # ----------------------------------------------------------------------------
 def scale_copy(src: torch.Tensor, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``out = scale * src`` in one pass (a grid-stride kernel for fp32 CUDA tensors, PyTorch otherwise); ``out`` is
+    allocated when not given.
+    """
     flat = src.reshape(-1)
     if flat.is_cuda and flat.dtype == torch.float32:
         ext = require_ext()
@@ -484,6 +497,7 @@ def scale_copy(src: torch.Tensor, scale: float, out: Optional[torch.Tensor] = No
 
 
 def fill_(dst: torch.Tensor, value: float) -> torch.Tensor:
+    """Fill ``dst`` with ``value`` in place (kernel for contiguous fp32 CUDA tensors) and return it."""
     if dst.is_cuda and dst.dtype == torch.float32 and dst.is_contiguous():
         ext = require_ext()
         ext.fill(dst.data_ptr(), float(value), dst.numel(), sm_count(dst.device),

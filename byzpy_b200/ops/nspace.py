@@ -53,6 +53,7 @@ def _stable_smallest(values: np.ndarray, k: int) -> np.ndarray:
 
 # ----------------------------------------------------------------------- selection
 def krum_scores(G: np.ndarray, f: int) -> np.ndarray:
+    """Krum score of every row: sum of its ``n - f - 1`` smallest squared distances to the other rows."""
     D = sqdist(G)
     n = D.shape[0]
     S = np.sort(D, axis=1)
@@ -60,6 +61,7 @@ def krum_scores(G: np.ndarray, f: int) -> np.ndarray:
 
 
 def krum_weights(G: np.ndarray, f: int, q: int) -> np.ndarray:
+    """Multi-Krum weights: ``1/q`` on the ``q`` best-scored rows (ties to the lower index), 0 elsewhere."""
     n = G.shape[0]
     if not (0 <= f < n - 1):
         raise ValueError(f"f must satisfy 0 <= f < n-1 (got n={n}, f={f})")
@@ -72,6 +74,7 @@ def krum_weights(G: np.ndarray, f: int, q: int) -> np.ndarray:
 
 
 def monna_weights(G: np.ndarray, f: int, reference_index: int = 0) -> np.ndarray:
+    """MoNNA weights: ``1/(n-f)`` on the ``n - f`` rows nearest to row ``reference_index`` (itself included)."""
     n = G.shape[0]
     if not (0 <= 2 * f < n):
         raise ValueError(f"2f must be < n (got n={n}, f={f})")
@@ -86,6 +89,7 @@ def monna_weights(G: np.ndarray, f: int, reference_index: int = 0) -> np.ndarray
 
 
 def cge_weights(G: np.ndarray, f: int) -> np.ndarray:
+    """CGE weights: ``1/(n-f)`` on the ``n - f`` rows with the smallest norms (NaN norms count as infinite)."""
     n = G.shape[0]
     if not (0 <= f < n):
         raise ValueError(f"f must satisfy 0 <= f < n (got n={n}, f={f})")
@@ -256,6 +260,7 @@ def mda_subset(D: np.ndarray, m: int) -> Tuple[int, ...]:
 
 
 def mda_weights(G: np.ndarray, f: int) -> np.ndarray:
+    """MDA weights: ``1/(n-f)`` on the lexicographically first ``(n-f)``-subset of minimum diameter."""
     n = G.shape[0]
     if not (0 <= f < n):
         raise ValueError(f"f must satisfy 0 <= f < n (got n={n}, f={f})")
@@ -297,6 +302,7 @@ def smea_subset(G: np.ndarray, m: int, batch: int = 32768) -> Tuple[int, ...]:
 
 
 def smea_weights(G: np.ndarray, f: int) -> np.ndarray:
+    """SMEA weights: ``1/(n-f)`` on the ``(n-f)``-subset whose covariance has the smallest top eigenvalue."""
     n = G.shape[0]
     if not (0 <= 2 * f < n):
         raise ValueError(f"2f must be < n (got n={n}, f={f})")
@@ -308,11 +314,13 @@ def smea_weights(G: np.ndarray, f: int) -> np.ndarray:
 
 # ------------------------------------------------------------------- pre-aggregators
 def clip_scales(G: np.ndarray, threshold: float) -> np.ndarray:
+    """Per-row factors of static clipping: ``min(1, threshold / max(norm, 1e-12))`` from the Gram diagonal."""
     norms = np.sqrt(np.maximum(np.diag(np.asarray(G, dtype=np.float64)), 0.0))
     return np.minimum(1.0, threshold / np.maximum(norms, 1e-12))
 
 
 def arc_scales(G: np.ndarray, f: int) -> np.ndarray:
+    """Per-row factors of adaptive robust clipping (the ``floor(2f(n-f)/n)`` largest norms are clipped to the next one)."""
     G = np.asarray(G, dtype=np.float64)
     n = G.shape[0]
     norms = np.sqrt(np.maximum(np.diag(G), 0.0))

@@ -43,6 +43,9 @@ def _ready(G: torch.Tensor, name: str):
 
 
 def krum_weights(G: torch.Tensor, f: int, q: int) -> Optional[torch.Tensor]:
+    """Multi-Krum weights from the device Gram matrix, by one single-CTA kernel (no host round trip); ``None`` when the
+    kernel library lacks it or ``n > 128``.
+    """
     ext = _ready(G, "nspace_krum")
     if ext is None:
         return None
@@ -55,6 +58,9 @@ def krum_weights(G: torch.Tensor, f: int, q: int) -> Optional[torch.Tensor]:
 
 def weiszfeld_coeffs(G: torch.Tensor, n_real: int, a0: np.ndarray, *, tol: float, max_iter: int,
                      eps: float) -> Optional[torch.Tensor]:
+    """Coefficients of the geometric median over ``[rows; start point]`` from the device Gram matrix: the whole Weiszfeld
+    iteration runs inside one single-CTA kernel (fp64); ``None`` when unavailable.
+    """
     ext = _ready(G, "nspace_weiszfeld")
     if ext is None:
         return None
@@ -70,6 +76,9 @@ def weiszfeld_coeffs(G: torch.Tensor, n_real: int, a0: np.ndarray, *, tol: float
 
 def centered_clip_coeffs(G: torch.Tensor, n_real: int, a0: np.ndarray, *, c_tau: float, M: int,
                          eps: float) -> Optional[torch.Tensor]:
+    """Coefficients of ``M`` centered-clipping rounds from the device Gram matrix (one single-CTA kernel, fp64);
+    ``None`` when unavailable.
+    """
     ext = _ready(G, "nspace_cclip")
     if ext is None:
         return None

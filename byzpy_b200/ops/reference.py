@@ -150,6 +150,7 @@ def gram(rows, *, scales=None, want64: bool = False, diag_only: bool = False) ->
 
 
 def weighted_sum(rows, W: torch.Tensor, *, scales=None) -> torch.Tensor:
+    """Plain PyTorch ``Y = W X`` over the rows (with optional per-row scales): the CPU path and the oracle of the CUDA kernels."""
     if W.dim() == 1 or W.shape[0] == 1:
         # one output row: accumulate the non-zero rows directly (no (n, d) stack, and rows with zero
         # weight -- possibly holding inf -- are never touched)
@@ -210,6 +211,7 @@ def _all_finite(X: torch.Tensor) -> bool:
 
 
 def colstat(rows, a: float, b: float, *, scales=None) -> torch.Tensor:
+    """Plain PyTorch ``a * mean + b * std`` per coordinate (population std) over the rows."""
     X = _stack(rows, scales)
     mean = X.mean(dim=0)
     out = a * mean
@@ -220,6 +222,7 @@ def colstat(rows, a: float, b: float, *, scales=None) -> torch.Tensor:
 
 def sgd_step(grad: torch.Tensor, *, params, moms=None, lr: float, momentum: float = 0.0,
              weight_decay: float = 0.0) -> None:
+    """Plain PyTorch SGD(+momentum, weight decay) update of flat parameter / momentum buffers with the flat gradient ``grad``."""
     with torch.no_grad():
         for r, p in enumerate(params):
             g = grad.reshape(p.shape).to(p.dtype)

@@ -29,6 +29,7 @@ def _partials(dev: torch.device, n: int, slots: int) -> torch.Tensor:
 
 
 def supported(rows: Sequence[torch.Tensor]) -> bool:
+    """The tcgen05 Gram kernel stages rows with 16-byte copies: every row must start on a 16-byte boundary."""
     return all(r.data_ptr() % 16 == 0 for r in rows)
 
 
@@ -115,6 +116,12 @@ def launch(ext, ptrs: Sequence[int], scales, off: int, main: int, row_len: int, 
 
 def gram_umma(rows: List[torch.Tensor], scales: List[float], G: torch.Tensor,
               G64: Optional[torch.Tensor]) -> None:
+    """Gram matrix of ``rows`` (each scaled by ``scales[i]``) on the 5th-generation tensor cores.
+
+    fp32 operands are split into three TF32 terms (3xTF32) so the products carry fp32 accuracy; accumulators live in
+    TMEM, tiles arrive by TMA (``cp.async`` staging when the rows are not one strided matrix), split-K partials are
+    reduced in fp64.  Writes the fp32 result into ``G`` and, when given, the fp64 one into ``G64``.
+    """
     ext = require_ext()
     n = len(rows)
     d = rows[0].numel()

@@ -20,10 +20,12 @@ PAD = 1024  # arenas are padded to a multiple of this many elements (vector widt
 
 
 def flat_size(module: nn.Module) -> int:
+    """Total number of parameters of ``module``."""
     return sum(p.numel() for p in module.parameters())
 
 
 def padded_size(d: int, pad: int = PAD) -> int:
+    """``d`` rounded up to a multiple of ``pad`` (arenas are padded so that every rank's shard is vector aligned)."""
     return (d + pad - 1) // pad * pad
 
 
@@ -101,10 +103,12 @@ def flatten_grads(module: nn.Module) -> torch.Tensor:
 
 
 def flatten_params(module: nn.Module) -> torch.Tensor:
+    """The parameters of ``module`` as one flat vector (a copy, ``module.parameters()`` order)."""
     return torch.cat([p.detach().reshape(-1) for p in module.parameters()])
 
 
 def write_vector_to_params_(module: nn.Module, vec: torch.Tensor) -> None:
+    """Load a flat vector into the parameters of ``module`` in place."""
     off = 0
     with torch.no_grad():
         for p in module.parameters():
@@ -114,6 +118,7 @@ def write_vector_to_params_(module: nn.Module, vec: torch.Tensor) -> None:
 
 
 def write_vector_to_grads_(module: nn.Module, vec: torch.Tensor) -> None:
+    """Load a flat vector into the ``.grad`` buffers of ``module`` (allocating them when absent), ready for ``optimizer.step()``."""
     off = 0
     for p in module.parameters():
         n = p.numel()

@@ -84,6 +84,33 @@ class PeerLayout:
 
 
 class DeviceP2PRound:
+    """Fused gossip round on GPUs: the device path of :class:`~byzpy_b200.engine.peer_to_peer.train.PeerToPeer`.
+
+    Every peer's published vector lives in a row of a symmetric-memory arena.  A round on a rank: the local half steps
+    of its honest peers (forward, backward, flat SGD, publish); a device-side flag barrier; every remote in-neighbour's
+    row is pulled over NVLink ONCE into local staging rows (a multi-pass aggregator run for several local peers would
+    otherwise fetch each remote byte many times); the attack kernels of local Byzantine peers (column statistics or an
+    alias copy over the honest rows) and a second barrier; then, per local honest peer, the robust aggregate of its
+    own and its in-neighbours' rows is written into its parameter arena -- the topology only selects which rows a
+    kernel loads.  Synchronisation is by release/acquire flags in device memory and the whole round is one CUDA
+    graph when every aggregator's small solve runs on the device.
+
+    Parameters
+    ----------
+    peers : sequence of DevicePeer
+        This rank's peers (honest first).
+    layout : PeerLayout
+        Which global peer ids each rank hosts.
+    topology : Topology
+    lr : float
+    device, group, amp_dtype, use_cuda_graph :
+        As for :class:`byzpy_b200.parallel.device_ps.DeviceRound`.
+
+    Notes
+    -----
+    ``step()`` enqueues one round; ``read_losses()`` waits for it and raises when a rank stopped answering
+    (``check_status``); ``close()`` releases the symmetric memory.
+    """
     def __init__(self, peers: Sequence[DevicePeer], layout: PeerLayout, topology, *, lr: float,
                  device: Optional[torch.device] = None, group=None,
                  amp_dtype: Optional[torch.dtype] = torch.bfloat16, use_cuda_graph: bool = True):

@@ -64,6 +64,9 @@ def _node_records(ps) -> List[Dict[str, Any]]:
 
 
 def save_checkpoint(path: str, ps, *, round_index: Optional[int] = None, extra: Optional[dict] = None) -> None:
+    """Write models, momentum / optimizer state and RNG state of every node of the parameter server ``ps`` to ``path``
+    (one ``torch.save`` blob that :func:`load_checkpoint` reads with the restricted unpickler).
+    """
     if torch.cuda.is_available():
         torch.cuda.synchronize()
     blob = {"format": FORMAT, "round": int(round_index if round_index is not None else getattr(ps, "rounds", 0)),

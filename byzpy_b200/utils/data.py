@@ -30,6 +30,7 @@ def mnist_like(n: int = 6000, *, train: bool = True, root: str = "./data", seed:
 
 
 def shard_indices(n_items: int, n_shards: int) -> List[List[int]]:
+    """Round-robin split of ``range(n_items)`` into ``n_shards`` index lists (shard ``i`` gets ``i, i + n_shards, ...``)."""
     return [list(range(i, n_items, n_shards)) for i in range(n_shards)]
 
 
@@ -58,6 +59,7 @@ def batch_source(x: torch.Tensor, y: torch.Tensor, batch_size: int, *, seed: int
 
 @torch.no_grad()
 def evaluate(model: torch.nn.Module, x: torch.Tensor, y: torch.Tensor, device, batch: int = 1024):
+    """``(mean loss, accuracy)`` of ``model`` on the tensors ``x, y``, evaluated in batches of ``batch`` on ``device``."""
     model.eval()
     loss_sum, correct = 0.0, 0
     for i in range(0, x.shape[0], batch):

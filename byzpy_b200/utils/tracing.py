@@ -18,6 +18,7 @@ import torch
 
 @contextlib.contextmanager
 def nvtx_range(name: str):
+    """Context manager pushing an NVTX range (visible in Nsight timelines); a no-op without CUDA."""
     pushed = False
     if torch.cuda.is_available():
         try:
@@ -33,6 +34,10 @@ def nvtx_range(name: str):
 
 
 class Tracer:
+    """Lightweight span recorder: ``with tracer.span("name", **tags):`` measures host time and, on CUDA, device time
+    between two events on the current stream (no synchronisation until ``finalize()``).  ``summary()`` aggregates calls,
+    host and device milliseconds per span name; every span is also an NVTX range.
+    """
     def __init__(self, cuda: Optional[bool] = None) -> None:
         self.cuda = torch.cuda.is_available() if cuda is None else cuda
         self.records: List[Dict[str, Any]] = []

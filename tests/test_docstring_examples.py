@@ -59,3 +59,24 @@ def test_every_operator_class_is_documented():
                 without_example.append(f"{name}.{cls_name}")
     assert not undocumented, undocumented
     assert not without_example, without_example
+
+
+def test_every_public_definition_has_a_docstring():
+    """Every public top-level class and function of the package carries a docstring (what autodoc renders in
+    docs/source/api_reference.md)."""
+    import ast
+    import os
+
+    root = os.path.dirname(byzpy_b200.__file__)
+    missing = []
+    for base, dirs, files in os.walk(root):
+        dirs[:] = [d for d in dirs if d not in ("__pycache__", "csrc")]
+        for f in files:
+            if not f.endswith(".py"):
+                continue
+            path = os.path.join(base, f)
+            for node in ast.parse(open(path).read()).body:
+                if isinstance(node, (ast.ClassDef, ast.FunctionDef, ast.AsyncFunctionDef)) \
+                        and not node.name.startswith("_") and not ast.get_docstring(node):
+                    missing.append(f"{os.path.relpath(path, root)}:{node.lineno} {node.name}")
+    assert not missing, missing
