@@ -58,6 +58,7 @@ class Aggregator(Operator, ABC):
     input_key = "gradients"
 
     def compute(self, inputs: Mapping[str, Any], *, context: OpContext) -> Any:
+        """Graph entry point: aggregate the sequence found under ``inputs["gradients"]``."""
         if self.input_key not in inputs:
             raise KeyError(f"{self.name} expects input key {self.input_key!r}")
         grads = inputs[self.input_key]
@@ -67,7 +68,7 @@ class Aggregator(Operator, ABC):
 
     @abstractmethod
     def aggregate(self, gradients: Sequence[Any]) -> Any:
-        ...
+        """Reduce the gradients to one tensor of the same shape, dtype and device as the first of them."""
 
     def fused_plan(self, n: int):
         """Plan object for :class:`byzpy_b200.parallel.device_ps.DeviceRound` (or None)."""

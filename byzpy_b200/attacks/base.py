@@ -55,13 +55,16 @@ class Attack(Operator, ABC):
     supports_subtasks = False
 
     def compute(self, inputs: Mapping[str, Any], *, context: OpContext) -> Any:
+        """Graph entry point: pick the inputs the attack's ``uses_*`` flags name out of ``inputs`` and call :meth:`apply`."""
         return self.apply(**self._collect_inputs(inputs))
 
     @abstractmethod
     def apply(self, *, model: Optional[nn.Module] = None, x: Optional[torch.Tensor] = None,
               y: Optional[torch.Tensor] = None, honest_grads: Optional[List[Any]] = None,
               base_grad: Optional[Any] = None) -> Any:
-        ...
+        """Return the malicious vector.  Only the keyword arguments the attack declared through its ``uses_*`` flags are
+        required: ``base_grad``; ``honest_grads``; ``model`` with a batch ``x``, ``y``.
+        """
 
     def fold(self, n_honest: int):
         """Row-fold description for the fused device round (None = must be materialised)."""

@@ -139,6 +139,7 @@ class ComputationGraph:
         return order
 
     def nodes_in_order(self) -> Iterable[GraphNode]:
+        """The nodes in a topological order (dependencies first)."""
         for name in self._order:
             yield self._nodes[name]
 
@@ -146,6 +147,7 @@ class ComputationGraph:
         return self._nodes[name]
 
     def dependencies(self, name: str) -> List[str]:
+        """Names of the nodes ``name`` takes inputs from."""
         return list(self._edges[name])
 
     def __len__(self) -> int:

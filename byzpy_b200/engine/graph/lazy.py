@@ -37,10 +37,12 @@ class GraphBuilder:
         self._node_counter = 0
 
     def input(self, name: str) -> "LazyNode":
+        """Declare run-time data called ``name`` and return its lazy handle."""
         self._inputs.setdefault(name, GraphInput(name))
         return LazyNode(builder=self, key=name, is_input=True)
 
     def build(self, outputs: Sequence[str]) -> ComputationGraph:
+        """Validate what was recorded and return the graph whose results are the nodes named in ``outputs``."""
         if not self._nodes:
             raise ValueError("GraphBuilder requires at least one node")
         for name in outputs:
@@ -78,6 +80,9 @@ class LazyNode:
     def apply(self, operator: Operator, *, input_key: Optional[str] = None,
               extra_inputs: Optional[Dict[str, Union["LazyNode", str]]] = None,
               name: Optional[str] = None) -> "LazyNode":
+        """Record ``operator`` fed by this value (under ``input_key``, default the operator's own) plus ``extra_inputs``
+        (lazy nodes or node names); returns the handle of the new node, named ``name`` or ``"<operator.name>_<k>"``.
+        """
         if not isinstance(operator, Operator):
             raise TypeError(f"operator must be an Operator instance, got {type(operator).__name__}")
         b = self._builder

@@ -133,22 +133,36 @@ class Operator:
 
     # -- to be provided by subclasses -------------------------------------------------
     def compute(self, inputs: Mapping[str, Any], *, context: OpContext) -> Any:
+        """The operator's result for ``inputs`` (a mapping of input key to value), computed in the calling task.
+        ``context`` carries the node name and scheduler metadata (pool size, worker affinities).
+        """
         raise NotImplementedError
 
     def create_subtasks(self, inputs: Mapping[str, Any], *, context: OpContext) -> Iterable[SubTask]:
+        """Split the work for ``inputs`` into :class:`SubTask` objects for a pool; an empty result means "compute directly".
+        Only consulted when ``supports_subtasks`` is set.
+        """
         return []
 
     def reduce_subtasks(self, partials: Sequence[Any], inputs: Mapping[str, Any], *,
                         context: OpContext) -> Any:
+        """Combine the subtask results (``partials``, in submission order) into the operator's result."""
         raise RuntimeError(f"Operator {self.name} does not implement reduce_subtasks().")
 
     async def run_barriered_subtasks(self, inputs: Mapping[str, Any], *, context: OpContext,
                                      pool: "ActorPool") -> Any:
+        """Iterative operators (``supports_barriered_subtasks``): run several rounds of subtasks on ``pool`` with a reduction
+        between rounds and return the result.
+        """
         raise RuntimeError(f"Operator {self.name} does not implement barriered subtasks.")
 
     # -- dispatch ------------------------------------------------------------------------
     async def run(self, inputs: Mapping[str, Any], *, context: OpContext,
                   pool: Optional["ActorPool"]) -> Any:
+        """Execute the operator the way a scheduler does: through the pool's subtask (or barriered) path when that is
+        supported and pays off, otherwise :meth:`compute`.  With ``BYZPY_POOL_DISPATCH`` unset the choice is measured per
+        (operator, input shape, pool); see :meth:`dispatch_report`.
+        """
         barriered = pool is not None and self.supports_barriered_subtasks
         if barriered or (pool is not None and self.supports_subtasks and pool.size > 1):
             key = self._dispatch_key(inputs, pool) if _adaptive_dispatch() else None

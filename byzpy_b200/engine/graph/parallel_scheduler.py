@@ -178,6 +178,9 @@ class ParallelScheduler:
         return node_name, result
 
     async def run(self, inputs: Mapping[str, Any]) -> Dict[str, Any]:
+        """Execute the graph on ``inputs`` with every ready node in flight at once; returns ``{output node name: value}``.
+        A failing node cancels the rest and its exception propagates.
+        """
         missing = [name for name in self.graph.required_inputs if name not in inputs]
         if missing:
             raise ValueError(f"Missing graph inputs: {missing}")

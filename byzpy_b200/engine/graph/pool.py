@@ -219,9 +219,11 @@ class ActorPool:
                    for c in self.configs)
 
     def worker_affinities(self) -> Sequence[str]:
+        """The ``worker::<label>`` tag of every worker, for pinning subtasks to one of them."""
         return tuple(self._worker_affinity_caps)
 
     async def start(self) -> None:
+        """Create and start the workers (idempotent); they come up concurrently."""
         if self._started:
             return
         fresh = []
@@ -242,6 +244,7 @@ class ActorPool:
         self._started = True
 
     async def shutdown(self) -> None:
+        """Close every worker; the pool can be started again afterwards."""
         for w in self._workers:
             await w.close()
         self._workers.clear()
@@ -258,6 +261,9 @@ class ActorPool:
         self._waiting.clear()
 
     async def open_channel(self, name: str) -> ActorPoolChannel:
+        """A named mailbox on every worker: returns an :class:`ActorPoolChannel` through which workers (and the caller)
+        exchange messages addressed by worker label.
+        """
         await self.start()
         cached = self._channel_cache.get(name)
         if cached is not None:
@@ -268,12 +274,16 @@ class ActorPool:
         return self._channel_cache[name]
 
     async def run_many(self, subtasks: Sequence[SubTask]) -> List[Any]:
+        """Run the subtasks concurrently (as far as workers are free) and return their results in the order given."""
         await self.start()
         if not subtasks:
             return []
         return list(await asyncio.gather(*[self._run_subtask(st) for st in subtasks]))
 
     async def run_subtask(self, subtask: SubTask) -> Any:
+        """Run one subtask on an idle worker that has the capability ``subtask.affinity`` asks for; retries on another
+        worker up to ``subtask.max_retries`` times when the worker raises.
+        """
         await self.start()
         return await self._run_subtask(subtask)
 

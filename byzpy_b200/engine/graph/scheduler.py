@@ -90,6 +90,9 @@ class NodeScheduler:
         return bound
 
     async def run(self, inputs: Mapping[str, Any]) -> Dict[str, Any]:
+        """Execute the graph on ``inputs`` (a mapping covering ``graph.required_inputs``) and return
+        ``{output node name: value}``.  Raises ``ValueError`` when an input is missing.
+        """
         self._check_inputs(inputs)
         cache: Dict[str, Any] = dict(inputs)
         tracer = self.metadata.get("tracer")
@@ -136,6 +139,9 @@ class MessageAwareNodeScheduler(NodeScheduler):
         self._message_cache: Dict[str, List[Any]] = defaultdict(list)
 
     async def wait_for_message(self, message_type: str, *, timeout: Optional[float] = None) -> Any:
+        """Next message of ``message_type``: a queued one if any, else wait up to ``timeout`` seconds
+        (``asyncio.TimeoutError``).
+        """
         queued = self._message_cache.get(message_type)
         if queued:
             return queued.pop(0)
@@ -150,6 +156,9 @@ class MessageAwareNodeScheduler(NodeScheduler):
             raise
 
     def deliver_message(self, message_type: str, payload: Any) -> None:
+        """Hand a message to the scheduler: wakes every task waiting for ``message_type`` and queues the payload for later
+        waiters.
+        """
         for fut in self._message_waiters.pop(message_type, []):
             if not fut.done():
                 fut.set_result(payload)

@@ -106,6 +106,7 @@ class ExecutionSession:
         self._result_cache.clear()
 
     async def execute(self, graph: ComputationGraph, inputs: Mapping[str, Any]) -> Dict[str, Any]:
+        """Run ``graph`` on ``inputs``; nodes whose names are cached are not recomputed.  Returns ``{output: value}``."""
         if not self.cache_intermediate:
             return await ParallelScheduler(graph, pool=self.pool, metadata=self.metadata).run(inputs)
         pruned, cached = self._prune_cached_nodes(graph)
@@ -120,6 +121,7 @@ class ExecutionSession:
         return {name: self._result_cache[name] for name in graph.outputs}
 
     def execute_async(self, graph: ComputationGraph, inputs: Mapping[str, Any]) -> ExecutionFuture:
+        """Start :meth:`execute` in the background and return an :class:`ExecutionFuture`."""
         task = asyncio.ensure_future(self.execute(graph, inputs))
         return ExecutionFuture(task, output_keys=graph.outputs)
 
@@ -145,14 +147,17 @@ class ExecutionSession:
         return ComputationGraph(keep, outputs=outs), cached
 
     def clear_cache(self) -> None:
+        """Forget every cached node result."""
         self._result_cache.clear()
 
     def get_cached(self, key: str) -> Any:
+        """Cached result of node ``key`` (``KeyError`` when absent)."""
         if key not in self._result_cache:
             raise KeyError(f"No cached result for {key!r}")
         return self._result_cache[key]
 
     def is_cached(self, key: str) -> bool:
+        """Whether node ``key`` has a cached result."""
         return key in self._result_cache
 
 

@@ -84,18 +84,22 @@ class NodeApplication:
 
     @property
     def pool(self) -> ActorPool:
+        """The node's actor pool."""
         return self._pool
 
     def register_pipeline(self, name: str, graph: ComputationGraph, *,
                           metadata: Optional[Mapping[str, Any]] = None) -> None:
+        """Register ``graph`` under ``name`` (``ValueError`` when the name is taken); ``metadata`` is merged into each run."""
         if name in self._pipelines:
             raise ValueError(f"Pipeline {name!r} already registered for node {self.name!r}.")
         self._pipelines[name] = NodePipeline(graph=graph, metadata=dict(metadata or {}))
 
     def has_pipeline(self, name: str) -> bool:
+        """Whether a pipeline called ``name`` is registered."""
         return name in self._pipelines
 
     def list_pipelines(self) -> Iterable[str]:
+        """Names of the registered pipelines."""
         return self._pipelines.keys()
 
     def _pipeline(self, name: str) -> NodePipeline:
@@ -106,6 +110,7 @@ class NodeApplication:
 
     async def run_pipeline(self, name: str, inputs: Mapping[str, Any], *,
                            metadata: Optional[Mapping[str, Any]] = None) -> Dict[str, Any]:
+        """Run pipeline ``name`` on the node's pool; returns ``{output node name: value}`` (``KeyError`` for an unknown name)."""
         pipe = self._pipeline(name)
         meta: Dict[str, Any] = {"node": self.name, "pipeline": name}
         meta.update(self._base_metadata)
@@ -115,6 +120,7 @@ class NodeApplication:
 
     def run_pipeline_sync(self, name: str, inputs: Mapping[str, Any], *,
                           metadata: Optional[Mapping[str, Any]] = None) -> Dict[str, Any]:
+        """:meth:`run_pipeline` for synchronous callers; raises ``RuntimeError`` inside a running event loop."""
         return _run_blocking(lambda: self.run_pipeline(name, inputs, metadata=metadata))
 
     async def _single(self, name: str, inputs, metadata, missing_msg: str) -> Any:
@@ -128,6 +134,7 @@ class NodeApplication:
         return next(iter(self.run_pipeline_sync(name, inputs, metadata=metadata).values()))
 
     async def shutdown(self) -> None:
+        """Shut the node's pool down."""
         await self._pool.shutdown()
 
 
@@ -143,18 +150,22 @@ class HonestNodeApplication(NodeApplication):
     GRADIENT_PIPELINE = "honest_gradient"
 
     async def aggregate(self, *, gradients: Sequence[Any], metadata=None) -> Any:
+        """Result of the ``"aggregate"`` pipeline on ``gradients``."""
         return await self._single(self.AGGREGATION_PIPELINE, {"gradients": gradients}, metadata,
                                   f"No aggregation pipeline registered on node {self.name!r}.")
 
     def aggregate_sync(self, *, gradients: Sequence[Any], metadata=None) -> Any:
+        """Synchronous :meth:`aggregate`."""
         return self._single_sync(self.AGGREGATION_PIPELINE, {"gradients": gradients}, metadata,
                                  f"No aggregation pipeline registered on node {self.name!r}.")
 
     async def honest_gradient(self, inputs: Mapping[str, Any], *, metadata=None) -> Any:
+        """Result of the ``"honest_gradient"`` pipeline on ``inputs`` (usually ``{"x": ..., "y": ...}``)."""
         return await self._single(self.GRADIENT_PIPELINE, inputs, metadata,
                                   f"No honest gradient pipeline registered on node {self.name!r}.")
 
     def honest_gradient_sync(self, inputs: Mapping[str, Any], *, metadata=None) -> Any:
+        """Synchronous :meth:`honest_gradient`."""
         return self._single_sync(self.GRADIENT_PIPELINE, inputs, metadata,
                                  f"No honest gradient pipeline registered on node {self.name!r}.")
 
@@ -168,10 +179,12 @@ class ByzantineNodeApplication(NodeApplication):
     ATTACK_PIPELINE = "attack"
 
     async def run_attack(self, *, inputs: Mapping[str, Any], metadata=None) -> Any:
+        """Result of the ``"attack"`` pipeline on ``inputs``."""
         return await self._single(self.ATTACK_PIPELINE, inputs, metadata,
                                   f"No attack pipeline registered on node {self.name!r}.")
 
     def run_attack_sync(self, *, inputs: Mapping[str, Any], metadata=None) -> Any:
+        """Synchronous :meth:`run_attack`."""
         return self._single_sync(self.ATTACK_PIPELINE, inputs, metadata,
                                  f"No attack pipeline registered on node {self.name!r}.")
 

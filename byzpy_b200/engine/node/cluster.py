@@ -28,6 +28,9 @@ class DecentralizedCluster:
     async def add_node(self, node_id: NodeId, application: NodeApplication, topology: Any = None,
                        context: Optional[NodeContext] = None,
                        metadata: Optional[Mapping[str, Any]] = None) -> DecentralizedNode:
+        """Create a node (context default: a fresh :class:`ProcessContext`) and register it; returns the node.
+        ``ValueError`` when the id exists.
+        """
         if node_id in self.nodes:
             raise ValueError(f"Node {node_id!r} already exists in cluster")
         if context is None:
@@ -50,20 +53,24 @@ class DecentralizedCluster:
             r._reverse_id_map = {v: k for k, v in snapshot.items()}
 
     async def start_all(self) -> None:
+        """Start every node, in insertion order."""
         self._update_node_id_maps()
         for node in self.nodes.values():
             await node.start()
 
     async def shutdown_all(self) -> None:
+        """Shut every node down and forget them."""
         for node in list(self.nodes.values()):
             await node.shutdown()
         self.nodes.clear()
         self._node_id_map.clear()
 
     def get_node(self, node_id: NodeId) -> Optional[DecentralizedNode]:
+        """The node with this id, or ``None``."""
         return self.nodes.get(node_id)
 
     async def remove_node(self, node_id: NodeId) -> None:
+        """Shut one node down and remove it (unknown ids are ignored); the remaining nodes are re-indexed."""
         node = self.nodes.pop(node_id, None)
         if node is None:
             return

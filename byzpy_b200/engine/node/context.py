@@ -47,19 +47,19 @@ class NodeContext(ABC):
 
     @abstractmethod
     async def start(self, node: "DecentralizedNode") -> None:
-        ...
+        """Attach to ``node`` and become able to send and receive."""
 
     @abstractmethod
     async def send_message(self, to_node_id: Any, message_type: str, payload: Any) -> None:
-        ...
+        """Deliver ``{"from": this node, "type": message_type, "payload": payload}`` to ``to_node_id``."""
 
     @abstractmethod
     def receive_messages(self) -> AsyncIterator[Any]:
-        ...
+        """Async iterator over incoming message dicts; ends when the context is shut down."""
 
     @abstractmethod
     async def shutdown(self) -> None:
-        ...
+        """Stop receiving and release the transport."""
 
 
 async def _drain(queue: "asyncio.Queue", is_running, idle: float = 0.1) -> AsyncIterator[Any]:

@@ -91,6 +91,7 @@ class DecentralizedNode:
 
     # ---- lifecycle ------------------------------------------------------------------------
     async def start(self) -> None:
+        """Attach the context and start processing incoming messages (idempotent)."""
         if self._running:
             return
         self._running = True
@@ -98,6 +99,7 @@ class DecentralizedNode:
         self._message_task = asyncio.ensure_future(self._message_processing_loop())
 
     async def shutdown(self) -> None:
+        """Cancel autonomous tasks and message processing, shut the context and the application's pool down."""
         if not self._running:
             return
         self._running = False
@@ -137,6 +139,7 @@ class DecentralizedNode:
             pass
 
     async def handle_incoming_message(self, from_node_id: str, message_type: str, payload: Any) -> None:
+        """Deliver one message: wake pipelines waiting for ``message_type``, then call the registered handler."""
         self.scheduler.deliver_message(message_type, payload)
         handler = self._message_handlers.get(message_type)
         if handler is not None:
@@ -144,6 +147,9 @@ class DecentralizedNode:
 
     def register_message_handler(self, message_type: str,
                                  handler: Callable[[str, Any], Awaitable[None]]) -> None:
+        """``await handler(sender_id, payload)`` will be called for every incoming message of ``message_type`` (one handler
+        per type; a later registration replaces the earlier one).
+        """
         self._message_handlers[message_type] = handler
 
     def _register_default_handlers(self) -> None:
@@ -155,28 +161,36 @@ class DecentralizedNode:
             raise RuntimeError("Node not started")
 
     async def send_message(self, to_node_id: NodeId, message_type: str, payload: Any) -> None:
+        """Send to one out-neighbour (``ValueError`` when the topology does not allow it, ``RuntimeError`` before ``start``)."""
         self._require_running()
         if not self.message_router.can_send_to(to_node_id):
             raise ValueError(f"Cannot send to {to_node_id} (not a neighbor)")
         await self.message_router.route_direct(to_node_id, message_type, payload, self.context)
 
     async def broadcast_message(self, message_type: str, payload: Any) -> None:
+        """Send to every out-neighbour; unreachable peers are skipped."""
         self._require_running()
         await self.message_router.route_broadcast(message_type, payload, self.context)
 
     async def multicast_message(self, to_node_ids: List[NodeId], message_type: str, payload: Any) -> None:
+        """Send to the listed nodes, all of which must be out-neighbours."""
         self._require_running()
         await self.message_router.route_multicast(to_node_ids, message_type, payload, self.context)
 
     def get_neighbors(self) -> List[NodeId]:
+        """Ids of the nodes this node may send to."""
         return self.message_router.get_out_neighbors()
 
     def get_in_neighbors(self) -> List[NodeId]:
+        """Ids of the nodes that may send to this node."""
         return self.message_router.get_in_neighbors()
 
     # ---- pipelines ----------------------------------------------------------------------------
     async def execute_pipeline(self, pipeline_name: str, inputs: Mapping[str, Any], *,
                                triggered_by: Optional[str] = None) -> Dict[str, Any]:
+        """Run the application's pipeline ``pipeline_name`` on this node's message-aware scheduler and pool; returns
+        ``{output node name: value}``.  Inputs declared as message sources are filled from incoming messages.
+        """
         self._require_running()
         pipeline = self.application._pipelines.get(pipeline_name)
         if pipeline is None:
@@ -186,6 +200,7 @@ class DecentralizedNode:
         return await self.scheduler.run(inputs)
 
     async def start_autonomous_task(self, task_coro: Awaitable[Any], name: str = "autonomous_task") -> asyncio.Task:
+        """Schedule ``task_coro`` as a named background task of the node (cancelled on shutdown); names are unique."""
         if not self._running:
             raise RuntimeError("Node must be started before starting autonomous tasks")
         if name in self._autonomous_tasks:

@@ -344,6 +344,9 @@ class ParameterServer:
         return [g for g in got if g is not None]
 
     async def round(self) -> torch.Tensor:
+        """One training round; returns the aggregated gradient (device path: the device tensor of the aggregate after
+        enqueuing the round).
+        """
         if self.device_round is not None:
             self.step()
             return self.device_round.aggregated()
@@ -366,9 +369,11 @@ class ParameterServer:
         return g
 
     def round_sync(self) -> torch.Tensor:
+        """:meth:`round` for synchronous callers (spins an event loop)."""
         return asyncio.run(self.round())
 
     async def shutdown(self) -> None:
+        """Release the device round's symmetric memory and close the node actors' backends."""
         if self.device_round is not None:
             self.device_round.close()
             self.device_round = None

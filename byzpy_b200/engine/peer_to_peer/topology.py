@@ -78,12 +78,15 @@ class Topology:
 
     # -- queries ----------------------------------------------------------------------------
     def edges(self) -> List[Edge]:
+        """All directed edges, grouped by source in insertion order."""
         return [Edge(u, v) for u, targets in self.out.items() for v in targets]
 
     def in_neighbors(self, i: int, unique: bool = True) -> List[int]:
+        """Nodes that send to ``i`` (duplicates removed unless ``unique=False``)."""
         return _unique(self.in_[i]) if unique else list(self.in_[i])
 
     def out_neighbors(self, i: int, unique: bool = True) -> List[int]:
+        """Nodes ``i`` sends to (duplicates removed unless ``unique=False``)."""
         return _unique(self.out[i]) if unique else list(self.out[i])
 
 

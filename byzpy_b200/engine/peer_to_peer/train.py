@@ -77,9 +77,11 @@ class PeerToPeer:
 
     @property
     def runner(self) -> DecentralizedPeerToPeer:
+        """The message-driven runner behind the generic path (``None`` on the fused device path)."""
         return self._runner
 
     async def bootstrap(self) -> None:
+        """Create and start the decentralized nodes (generic path); a no-op on the device path.  Call once before :meth:`round`."""
         if self._runner is not None:
             await self._runner.start()
 
@@ -90,12 +92,16 @@ class PeerToPeer:
         return self.device_round.step(batches)
 
     async def round(self) -> None:
+        """One gossip round: every honest node takes a local half step, exchanges models with its neighbours and robustly
+        aggregates what it received.
+        """
         if self.device_round is not None:
             self.device_round.step()
             return
         await self._runner.run_round_async()
 
     async def shutdown(self) -> None:
+        """Stop the nodes / release the device round."""
         if self.device_round is not None:
             self.device_round.close()
             self.device_round = None

@@ -45,6 +45,7 @@ class PreAggregator(Operator, ABC):
     input_key = "vectors"
 
     def compute(self, inputs: Mapping[str, Any], *, context: OpContext) -> Any:
+        """Graph entry point: pre-aggregate the sequence found under ``inputs["vectors"]``."""
         if self.input_key not in inputs:
             raise KeyError(f"{self.name} expects input key {self.input_key!r}")
         xs = inputs[self.input_key]
@@ -54,7 +55,7 @@ class PreAggregator(Operator, ABC):
 
     @abstractmethod
     def pre_aggregate(self, xs: Sequence[Any]) -> List[Any]:
-        ...
+        """Map the ``n`` input vectors to a list of (possibly fewer) vectors of the same shape, dtype and device."""
 
 
 def _mix_chunk(packed: _Packed, start: int, end: int, W: torch.Tensor):
