@@ -201,10 +201,15 @@ class DecentralizedNode:
 
     async def start_autonomous_task(self, task_coro: Awaitable[Any], name: str = "autonomous_task") -> asyncio.Task:
         """Schedule ``task_coro`` as a named background task of the node (cancelled on shutdown); names are unique."""
+        refused = None
         if not self._running:
-            raise RuntimeError("Node must be started before starting autonomous tasks")
-        if name in self._autonomous_tasks:
-            raise ValueError(f"Autonomous task with name '{name}' already exists")
+            refused = RuntimeError("Node must be started before starting autonomous tasks")
+        elif name in self._autonomous_tasks:
+            refused = ValueError(f"Autonomous task with name '{name}' already exists")
+        if refused is not None:
+            if asyncio.iscoroutine(task_coro):
+                task_coro.close()       # a coroutine object we will never run: do not leave it to warn at GC
+            raise refused
         task = asyncio.ensure_future(task_coro)
         self._autonomous_tasks[name] = task
         return task
