@@ -131,6 +131,11 @@ class ColumnStatAttack(Attack):
         a, b = self._coeffs(n_honest)
         return RowFold("virtual", a=a, b=b)
 
+    def _subtask_feature_chunk(self, d: int, n_rows: int, context) -> int:
+        """Coordinates per subtask; ``chunk_size`` counts coordinates for this family unless a subclass says
+        otherwise."""
+        return select_adaptive_chunk_size(d, self.chunk_size, pool_size=pool_size_of(context))
+
     def create_subtasks(self, inputs, *, context):
         grads = inputs.get("honest_grads")
         if not isinstance(grads, Sequence) or not grads:
@@ -138,7 +143,7 @@ class ColumnStatAttack(Attack):
         rows, _ = prepare_rows(grads, "honest_grads")
         d = rows[0].numel()
         a, b = self._coeffs(len(rows))
-        chunk = select_adaptive_chunk_size(d, self.chunk_size, pool_size=pool_size_of(context))
+        chunk = self._subtask_feature_chunk(d, len(rows), context)
         packed = _Packed.pack(rows, in_process=pool_in_process(context))
         _hold_packed(self, inputs, packed)
         return [SubTask(fn=_colstat_chunk, args=(packed, s, e, a, b), name=f"{self.name}_chunk_{k}")

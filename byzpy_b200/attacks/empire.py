@@ -2,6 +2,8 @@
 (reference attacks/empire.py:23-187)."""
 from __future__ import annotations
 
+from ..aggregators._chunking import select_adaptive_chunk_size
+from ..aggregators.base import pool_size_of
 from .base import ColumnStatAttack
 
 
@@ -42,6 +44,19 @@ class EmpireAttack(ColumnStatAttack):
 
     def _coeffs(self, n_honest: int):
         return self.scale, 0.0
+
+    def _subtask_feature_chunk(self, d: int, n_rows: int, context) -> int:
+        # ``chunk_size`` counts GRADIENTS per subtask (reference attacks/empire.py:108-120: partial sums over row
+        # blocks).  The column-statistics kernel splits coordinates instead, so the setting is honoured as a number
+        # of subtasks: as many as the reference would create, but at least one per worker once there is enough
+        # data for that.  (Read as a coordinate count, the default of 8 would mean d / 8 subtasks.)
+        pool = pool_size_of(context)
+        rows_chunk = max(1, select_adaptive_chunk_size(n_rows, self.chunk_size, pool_size=pool))
+        pieces = -(-n_rows // rows_chunk)
+        if d >= 4096 * max(1, pool):
+            pieces = max(pieces, pool)
+        per = -(-d // max(1, pieces))
+        return max(64, -(-per // 64) * 64)
 
 
 __all__ = ["EmpireAttack"]
