@@ -236,6 +236,64 @@ def test_decentralized_peer_to_peer_round_matches_manual_expectation():
     run(scenario())
 
 
+class _DuckAggregateOnly:
+    """An honest gossip node from before the mixins: ``p2p_half_step`` and ``p2p_aggregate(vectors)`` only."""
+
+    def __init__(self, start):
+        self.theta = torch.tensor([float(start), float(start)])
+        self.seen = None
+
+    def p2p_half_step(self, lr):
+        self.theta = self.theta - lr
+        return self.theta.clone()
+
+    def p2p_aggregate(self, vectors):
+        self.seen = len(vectors)
+        self.theta = torch.stack(list(vectors)).median(0).values
+        return self.theta
+
+
+class _DuckBare:
+    """A node with neither aggregation hook: the runner aggregates with a coordinate-wise median and loads the
+    result through ``set_param_vector``."""
+
+    def __init__(self, start):
+        self.theta = torch.tensor([float(start), float(start)])
+
+    def p2p_half_step(self, lr):
+        return self.theta.clone()
+
+    def set_param_vector(self, vec):
+        self.theta = torch.as_tensor(vec).clone()
+
+
+class _DuckBroken(_DuckAggregateOnly):
+    def p2p_aggregate(self, vectors):
+        return self.no_such_attribute          # an AttributeError raised INSIDE the hook must not be mistaken for "no hook"
+
+
+def test_decentralized_peer_to_peer_accepts_duck_typed_nodes():
+    from byzpy_b200.engine.peer_to_peer.runner import DecentralizedPeerToPeer
+
+    async def scenario(nodes):
+        p2p = DecentralizedPeerToPeer(nodes, [], Topology.complete(len(nodes)), lr=1.0, recv_timeout=5.0)
+        await p2p.start()
+        try:
+            await p2p.run_round_async()
+        finally:
+            await p2p.stop()
+
+    old = [_DuckAggregateOnly(s) for s in (1.0, 5.0, 9.0)]
+    run(scenario(old))
+    assert all(n.seen == 3 for n in old)                                   # own + two neighbours
+    assert all(torch.equal(n.theta, torch.tensor([4.0, 4.0])) for n in old)   # median of (0, 4, 8)
+    bare = [_DuckBare(s) for s in (1.0, 5.0, 9.0)]
+    run(scenario(bare))
+    assert all(torch.equal(n.theta, torch.tensor([5.0, 5.0])) for n in bare)
+    with pytest.raises(AttributeError):
+        run(scenario([_DuckBroken(s) for s in (1.0, 2.0, 3.0)]))
+
+
 def test_gram_family_subtasks_chunk_the_feature_dimension_coarsely():
     """Regression: the reference's row-chunk default (chunk_size=32) must not be used as a FEATURE
     chunk -- a 1.2 M-parameter gradient became 37 500 subtasks."""
@@ -402,6 +460,49 @@ def test_checkpoint_roundtrip_generic_nodes(tmp_path):
     blob = torch.load(path, weights_only=False)
     # the per-node snapshot is exactly the reference's dump_state_dict() mapping
     nn.Linear(6, 3).load_state_dict(blob["nodes"][0]["state_dict"], strict=True)
+
+
+def test_checkpoint_resume_continues_the_same_trajectory_and_rejects_mismatches(tmp_path):
+    """Training 2 rounds, checkpoint, 2 more rounds == restoring the checkpoint into fresh nodes and training 2 rounds:
+    momentum buffers and the RNG stream are part of the checkpoint.  Files of another format or with a different
+    number of nodes are refused."""
+    from byzpy_b200.utils.checkpoint import FORMAT, load_checkpoint, load_reference_state_dict, save_checkpoint
+
+    def build(k=3):
+        torch.manual_seed(0)
+        hon = [DeviceHonestNode(nn.Linear(6, 3), data=lambda: (torch.randn(8, 6), torch.randint(0, 3, (8,))), lr=0.1,
+                                momentum=0.9, device="cpu") for _ in range(k)]
+        return ParameterServer(hon, [], CoordinateWiseMedian())
+
+    ps = build()
+    for _ in range(2):
+        ps.round_sync()
+    path = str(tmp_path / "ck.pt")
+    save_checkpoint(path, ps, extra={"note": "after two rounds"})
+    for _ in range(2):
+        ps.round_sync()
+    want = [flatten_params(n.model).clone() for n in ps.hon]
+
+    resumed = build()
+    torch.manual_seed(12345)                           # a different stream until the checkpoint restores the saved one
+    assert load_checkpoint(path, resumed) == 2
+    for _ in range(2):
+        resumed.round_sync()
+    assert resumed.rounds == 4
+    for a, b in zip(want, [flatten_params(n.model) for n in resumed.hon]):
+        assert torch.allclose(a, b, atol=1e-6)
+
+    assert torch.load(path, weights_only=True)["extra"] == {"note": "after two rounds"}
+    with pytest.raises(ValueError):
+        load_checkpoint(path, build(k=2))                                   # fewer nodes than the file
+    bad = str(tmp_path / "bad.pt")
+    torch.save({"format": "something-else", "nodes": []}, bad)
+    with pytest.raises(ValueError):
+        load_checkpoint(bad, build())
+    assert FORMAT.startswith("byzpy_b200.ckpt")
+    fresh = nn.Linear(6, 3)
+    load_reference_state_dict(fresh, ps.hon[0].dump_state_dict())
+    assert torch.equal(flatten_params(fresh), flatten_params(ps.hon[0].model))
 
 
 def test_tracer_records_graph_nodes():

@@ -374,3 +374,46 @@ def test_ucx_transport_pools_endpoints_locks_per_peer_and_retries_once():
         run(scenario())
     finally:
         srv.stop()
+
+
+def test_channels_between_local_actors_and_a_ucx_actor_server():
+    """Mailboxes across the ``ucx://`` scheme from both sides: a thread actor posts to an actor hosted by a
+    ``UCXRemoteActorServer`` and reads that actor's mailbox remotely; the hosted actor answers through its own backend.
+    On a CPU-only box the CUDA-IPC codec carries host copies, the routing is the same."""
+    from byzpy_b200.engine.actor.backends.gpu import UCXRemoteActorServer
+    from byzpy_b200.engine.actor.transports import ucx as ucx_t
+
+    srv = _ServerThread(UCXRemoteActorServer)
+    try:
+        async def scenario():
+            local = resolve_backend("thread")
+            remote = resolve_backend(f"ucx://127.0.0.1:{srv.port}")
+            for be in (local, remote):
+                await be.start()
+                await be.construct(Counter, args=(), kwargs={})
+            lref, rref = ActorRef(local), ActorRef(remote)
+            lch, rch = await lref.open_channel("m"), await rref.open_channel("m")
+            lep, rep = await lref.endpoint(), await rref.endpoint()
+            assert rep.scheme == "ucx" and rep.is_remote() and not lep.is_remote()
+            # local -> remote mailbox, read back by the remote actor's own handle
+            await lch.send(rep, {"k": 1, "t": torch.arange(4.0)})
+            got = await rch.recv(timeout=2.0)
+            assert got["k"] == 1 and torch.equal(got["t"], torch.arange(4.0))
+            # ... and read REMOTELY by the local backend (chan_get on a foreign endpoint)
+            await lch.send(rep, "second")
+            assert await local.chan_get(ep=rep, name="m", timeout=2.0) == "second"
+            assert await local.chan_get(ep=rep, name="m", timeout=0.05) is None
+            # an endpoint nobody can route to
+            from byzpy_b200.engine.actor.channels import Endpoint
+
+            with pytest.raises(RuntimeError):
+                await local.chan_put(from_ep=lep, to_ep=Endpoint("carrier-pigeon", "", "x"), name="m", payload=1)
+            with pytest.raises(RuntimeError):
+                await local.chan_get(ep=Endpoint("carrier-pigeon", "", "x"), name="m", timeout=0.01)
+            await ucx_t.clear_pool()
+            for be in (local, remote):
+                await be.close()
+
+        run(scenario())
+    finally:
+        srv.stop()
