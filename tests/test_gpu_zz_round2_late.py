@@ -1,12 +1,20 @@
 """GPU tests of kernels written AFTER the round's GPU budget was spent (they have been compiled, statically
 analysed and -- where the code is host-compilable -- checked on the CPU, but no B200 has run them yet).  The file
-name sorts last on purpose: under ``pytest -x`` a surprise here cannot hide the results of the measured kernels."""
+name sorts last on purpose: under ``pytest -x`` a surprise here cannot hide the results of the measured kernels.
+
+Everything exercised here is OPT-IN (``impl="tiled"`` / ``BYZPY_CW_IMPL=tiled``, a pre-aggregator in front of a
+coordinate-wise aggregator on the fused path, the example's non-default flags); no default path depends on it.  For
+that reason the tests are marked ``xfail(strict=False)``: the first B200 run reports them as XPASS (verified) or XFAIL
+(the opt-in feature needs work) without turning the tier of the measured kernels red.  Remove the mark once a run has
+shown XPASS."""
 import pytest
 import torch
 
 from byzpy_b200 import ops
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]     # (device-side waits have their own 20 s budgets)
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),     # (device-side waits have their own 20 s budgets)
+              pytest.mark.xfail(strict=False, reason="opt-in code written after the GPU budget was spent: never "
+                                                     "executed on a B200 (see the module docstring)")]
 DEV = torch.device("cuda", 0) if torch.cuda.is_available() else None
 
 
