@@ -45,7 +45,7 @@ def test_installation_alias_block_runs(byzpy_alias):
 
 def _doc_files():
     out = [os.path.join("docs", "source", f) for f in sorted(os.listdir(DOCS)) if f.endswith(".md")]
-    out += [f for f in ("README.md", "DESIGN.md", "ROUND2.md", "CHANGELOG.md", "CONTRIBUTING.md", "benchmarks/README.md",
+    out += [f for f in ("README.md", "DESIGN.md", "ROUND2.md", "COMPONENTS.md", "CHANGELOG.md", "CONTRIBUTING.md", "benchmarks/README.md",
                         "docs/BUILDING.md", "docs/README.md") if os.path.exists(os.path.join(ROOT, f))]
     for sub in ("profiles", "examples"):
         for base, _, files in os.walk(os.path.join(ROOT, sub)):
