@@ -15,3 +15,10 @@ def __getattr__(name):
 
 
 __all__ = ["run_operator", "OperatorExecutor", "__version__"]
+
+# Library logging convention: everything logs under "byzpy_b200" and stays silent unless the application configures
+# logging (failure detection, dropped peers and refused frames are reported at WARNING).
+import logging as _logging  # noqa: E402
+
+_logging.getLogger("byzpy_b200").addHandler(_logging.NullHandler())
+

@@ -28,6 +28,7 @@ import time
 from dataclasses import dataclass
 from typing import TYPE_CHECKING, Any, Iterable, Iterator, List, Mapping, Optional, Sequence
 
+from ...utils import metrics
 from .subtask import SubTask
 
 if TYPE_CHECKING:  # pragma: no cover
@@ -239,6 +240,8 @@ class Operator:
         return other if st["calls"] % self._REEXPLORE == self._REEXPLORE - 1 else best
 
     def _dispatch_record(self, key: Optional[tuple], route: str, seconds: float) -> None:
+        if metrics.REGISTRY.enabled:
+            metrics.inc("byzpy_operator_runs_total", labels={"op": self.name, "route": route})
         if key is None:
             return
         stats = self.__dict__.setdefault("_dispatch_stats", {})

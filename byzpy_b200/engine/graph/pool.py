@@ -18,6 +18,7 @@ from typing import Any, Callable, Deque, Dict, List, Mapping, Optional, Sequence
 
 import cloudpickle
 
+from ...utils import metrics
 from ..actor.base import ActorBackend, ActorRef
 from ..actor.channels import ChannelRef, Endpoint
 from ..actor.factory import resolve_backend
@@ -292,11 +293,14 @@ class ActorPool:
         while True:
             worker = await self._acquire(subtask.affinity)
             try:
-                return await worker.run(subtask)
+                out = await worker.run(subtask)
+                metrics.inc("byzpy_pool_subtasks_total")
+                return out
             except Exception:
                 attempts_left -= 1
                 if attempts_left <= 0:
                     raise
+                metrics.inc("byzpy_pool_subtask_retries_total")
             finally:
                 await self._release(worker)
 

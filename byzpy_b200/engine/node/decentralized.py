@@ -12,6 +12,7 @@ from __future__ import annotations
 import asyncio
 from typing import Any, Awaitable, Callable, Dict, List, Mapping, Optional, Union
 
+from ...utils import metrics
 from ..graph.graph import ComputationGraph, GraphNode
 from ..graph.operator import Operator
 from ..graph.scheduler import MessageAwareNodeScheduler
@@ -129,6 +130,7 @@ class DecentralizedNode:
                     mtype = msg.get("type", "unknown")
                     first = not any(t == mtype for t, _ in self.handler_errors)
                     self.handler_errors.append((mtype, repr(exc)))
+                    metrics.inc("byzpy_node_handler_errors_total", labels={"type": mtype})
                     del self.handler_errors[:-64]
                     if first:
                         import warnings

@@ -24,12 +24,15 @@ from __future__ import annotations
 
 import asyncio
 import inspect
+import logging
+import time
 from typing import Any, List, Optional, Sequence
 
 import torch
 
 from ...aggregators.base import Aggregator
 from ...pre_aggregators.base import PreAggregator
+from ...utils import metrics
 
 
 async def _call(obj: Any, method: str, *args, **kwargs) -> Any:
@@ -37,6 +40,9 @@ async def _call(obj: Any, method: str, *args, **kwargs) -> Any:
     if inspect.isawaitable(res):
         res = await res
     return res
+
+
+_log = logging.getLogger(__name__)
 
 
 def _is_device_node(node: Any) -> bool:
@@ -307,6 +313,7 @@ class ParameterServer:
         if self.device_round is None:
             raise RuntimeError("step() is only available on the fused device path; use round()")
         self.rounds += 1
+        metrics.inc("byzpy_ps_rounds_total", labels={"path": "device"})
         return self.device_round.step(batches)
 
     def recover(self) -> List[int]:
@@ -329,6 +336,8 @@ class ParameterServer:
             if not self.tolerate_failures:
                 raise
             self.failed.append((self.rounds, f"{kind}:{idx}", repr(exc)))
+            metrics.inc("byzpy_ps_node_failures_total", labels={"kind": kind})
+            _log.warning("round %d: %s node %d skipped (%r)", self.rounds, kind, idx, exc)
             return None
 
     async def _gather_honest(self) -> List[torch.Tensor]:
@@ -350,6 +359,7 @@ class ParameterServer:
         if self.device_round is not None:
             self.step()
             return self.device_round.aggregated()
+        t_round = time.perf_counter()
         grads = await self._gather_honest()
         grads += await self._gather_byzantine(tuple(grads))
         if not grads:
@@ -366,6 +376,8 @@ class ParameterServer:
         await asyncio.gather(*[self._guarded("apply", i, n, "apply_server_gradient", g)
                                for i, n in enumerate(targets)])
         self.rounds += 1
+        metrics.inc("byzpy_ps_rounds_total", labels={"path": "generic"})
+        metrics.observe("byzpy_ps_round_seconds", time.perf_counter() - t_round)
         return g
 
     def round_sync(self) -> torch.Tensor:

@@ -27,6 +27,7 @@ from typing import Any, Callable, Dict, List, Optional
 import torch
 
 from ...aggregators.coordinate_wise.median import CoordinateWiseMedian
+from ...utils import metrics
 from ..graph.ops import CallableOp, make_single_operator_graph
 from ..graph.pool import ActorPoolConfig
 from ..node.application import ByzantineNodeApplication, HonestNodeApplication
@@ -308,6 +309,7 @@ class DecentralizedPeerToPeer:
         for j in range(n_h, self._n()):
             self._gradient_cache[str(j)] = []
         self.rounds += 1
+        metrics.inc("byzpy_p2p_rounds_total")
 
     def run_round(self) -> None:
         asyncio.run(self.run_round_async())
