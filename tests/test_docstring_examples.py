@@ -75,7 +75,9 @@ def test_every_public_definition_has_a_docstring():
             if not f.endswith(".py"):
                 continue
             path = os.path.join(base, f)
-            for node in ast.parse(open(path).read()).body:
+            with open(path) as fh:
+                tree = ast.parse(fh.read())
+            for node in tree.body:
                 if isinstance(node, (ast.ClassDef, ast.FunctionDef, ast.AsyncFunctionDef)) \
                         and not node.name.startswith("_") and not ast.get_docstring(node):
                     missing.append(f"{os.path.relpath(path, root)}:{node.lineno} {node.name}")
