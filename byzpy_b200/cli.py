@@ -99,6 +99,7 @@ def _doctor() -> dict:
     report["switches"] = {
         "BYZPY_SYMM": os.environ.get("BYZPY_SYMM", "auto (vmm where supported, else ipc)"),
         "BYZPY_CW_IMPL": os.environ.get("BYZPY_CW_IMPL", "auto (direct / staged; 'tiled' is opt-in)"),
+        "BYZPY_FUSED_MAPCW": os.environ.get("BYZPY_FUSED_MAPCW", "0 (pre-aggregator -> coordinate-wise fused round on fused=True only)"),
         "BYZPY_GRAM_TMA": os.environ.get("BYZPY_GRAM_TMA", "1"),
         "BYZPY_GRAM_CENTER": os.environ.get("BYZPY_GRAM_CENTER", "off"),
         "BYZPY_POOL_DISPATCH": os.environ.get("BYZPY_POOL_DISPATCH", "adaptive"),

@@ -25,6 +25,7 @@ from __future__ import annotations
 import asyncio
 import inspect
 import logging
+import os
 import time
 from typing import Any, List, Optional, Sequence
 
@@ -161,6 +162,9 @@ class ParameterServer:
             self.scheduler = NodeScheduler(graph, pool=actor_pool, metadata=scheduler_metadata)
         self.device_round = None
         want_fused = fused if fused is not None else True
+        # the pre-aggregator -> coordinate-wise fused round has not been timed on hardware yet: automatic selection
+        # (fused=None) keeps to the measured plans, fused=True or BYZPY_FUSED_MAPCW=1 asks for it explicitly
+        self._allow_mapcw = bool(fused) or os.environ.get("BYZPY_FUSED_MAPCW", "0") not in ("", "0")
         if want_fused and actor_pool is None:
             self.device_round = self._try_build_device_round(
                 layout, process_group, lr, momentum, weight_decay, amp_dtype, use_cuda_graph,
@@ -268,6 +272,8 @@ class ParameterServer:
         device_map = type(pre).row_map_device is not LinearPreAggregator.row_map_device
 
         if isinstance(inner, CwPlan):
+            if not getattr(self, "_allow_mapcw", True):
+                return None
             # map -> coordinate-wise selection is not linear in n-space: the m mixed rows are produced on
             # every rank's coordinate shard and the fused selection kernel runs over them (MapCwPlan)
             def weights(G: Optional[torch.Tensor]) -> torch.Tensor:

@@ -165,6 +165,7 @@ PRES = {"bucketing": lambda: Bucketing(2, perm=[5, 0, 3, 1, 7, 2, 6, 4, 9, 8]), 
 def test_map_round_plumbing_against_host_operators(pre_name, n, agg_name, d):
     mk_agg = {"median": CoordinateWiseMedian, "trmean": lambda: CoordinateWiseTrimmedMean(f=1)}[agg_name]
     ps = ParameterServer([_Dev()], [], mk_agg(), pre_aggregator=PRES[pre_name](), fused=None)
+    ps._allow_mapcw = True
     plan = ps._fused_plan(n)
     assert isinstance(plan, MapCwPlan)
     if plan.refresh is not None:
@@ -188,6 +189,7 @@ def test_map_round_plumbing_against_host_operators(pre_name, n, agg_name, d):
 def test_map_round_with_virtual_little_rows():
     n_workers, n_virtual, d = 8, 2, 2500
     ps = ParameterServer([_Dev()], [], CoordinateWiseMedian(), pre_aggregator=Bucketing(2, perm=list(range(10))), fused=None)
+    ps._allow_mapcw = True
     plan = ps._fused_plan(n_workers + n_virtual)
     plan.refresh()
     fold = RowFold("virtual", a=1.0, b=-0.8)

@@ -88,8 +88,10 @@ class _Dev:
     device = torch.device("cpu")
 
 
-def _ps(agg, pre):
-    return ParameterServer([_Dev()], [], agg, pre_aggregator=pre, fused=None)
+def _ps(agg, pre, mapcw=True):
+    ps = ParameterServer([_Dev()], [], agg, pre_aggregator=pre, fused=None)
+    ps._allow_mapcw = mapcw          # what fused=True / BYZPY_FUSED_MAPCW=1 grant on a GPU box
+    return ps
 
 
 PRE = [lambda: Clipping(threshold=3.0), lambda: ARC(f=2), lambda: NearestNeighborMixing(f=2),
@@ -173,6 +175,8 @@ def test_composition_is_refused_when_it_cannot_be_expressed():
 
     assert _ps(MultiKrum(f=1, q=1), Opaque())._fused_plan(6) is None            # not a linear map
     assert isinstance(_ps(CoordinateWiseMedian(), Clipping())._fused_plan(6), MapCwPlan)   # mixed rows per shard
+    # ... only on request: automatic selection keeps to the plans that have been timed on hardware
+    assert _ps(CoordinateWiseMedian(), Clipping(), mapcw=False)._fused_plan(6) is None
     assert _ps(CoordinateWiseMedian(), Opaque())._fused_plan(6) is None
     assert _ps(GeometricMedian(), Clipping())._fused_plan(6) is None             # median start row is not linear in W
     with pytest.raises(ValueError):
