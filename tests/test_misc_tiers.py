@@ -424,7 +424,7 @@ class _InlinePool:
 
 @pytest.mark.parametrize("mk,inputs", [
     (lambda: SignFlipAttack(scale=-3.0, chunk_size=7), lambda vs: {"base_grad": vs[0]}),
-    (lambda: EmpireAttack(scale=-1.0, chunk_size=7), lambda vs: {"honest_grads": vs}),
+    (lambda: EmpireAttack(scale=-1.0, chunk_size=2), lambda vs: {"honest_grads": vs}),   # (gradients per subtask)
     (lambda: LittleAttack(f=1, chunk_size=7), lambda vs: {"honest_grads": vs}),
     (lambda: InfAttack(chunk_size=7), lambda vs: {"honest_grads": vs}),
     (lambda: MimicAttack(epsilon=1, chunk_size=7), lambda vs: {"honest_grads": vs}),
@@ -432,7 +432,7 @@ class _InlinePool:
 ])
 def test_attack_subtask_path_equals_direct(mk, inputs):
     g = torch.Generator().manual_seed(0)
-    vs = [torch.randn(50, generator=g) for _ in range(5)]
+    vs = [torch.randn(200, generator=g) for _ in range(5)]
     ctx = OpContext("n", metadata={"pool_size": 4})
     atk = mk()
     direct = atk.compute(inputs(vs), context=ctx)
