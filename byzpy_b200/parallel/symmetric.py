@@ -26,6 +26,7 @@ import os
 import socket
 import tempfile
 import threading
+import time
 import uuid
 from typing import List, Optional
 
@@ -61,9 +62,15 @@ class _FdServer:
 
     def __init__(self, fds: List[int]):
         self.fds = list(fds)
-        self.path = os.path.join(tempfile.gettempdir(), f"byzpy_b200_fd_{uuid.uuid4().hex}.sock")
+        # Linux abstract namespace (leading NUL): no file, so neither a full / read-only / very long temp
+        # directory nor a stale path can make the exchange -- and with it the VMM heap -- fail
+        self.path = f"\0byzpy_b200_fd_{os.getpid()}_{uuid.uuid4().hex}"
         self._sock = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
-        self._sock.bind(self.path)
+        try:
+            self._sock.bind(self.path)
+        except OSError:                                    # (a kernel without the abstract namespace)
+            self.path = os.path.join(tempfile.gettempdir(), f"byzpy_b200_fd_{uuid.uuid4().hex}.sock")
+            self._sock.bind(self.path)
         self._sock.listen(64)
         self._stop = False
         self._thr = threading.Thread(target=self._serve, daemon=True)
@@ -88,20 +95,31 @@ class _FdServer:
         try:
             self._sock.close()
         finally:
-            try:
-                os.unlink(self.path)
-            except OSError:
-                pass
+            if not self.path.startswith("\0"):
+                try:
+                    os.unlink(self.path)
+                except OSError:
+                    pass
 
 
-def _fetch_fd(path: str, index: int = 0) -> int:
-    with socket.socket(socket.AF_UNIX, socket.SOCK_STREAM) as s:
-        s.connect(path)
-        s.sendall(bytes([index]))
-        _, fds, _, _ = socket.recv_fds(s, 1, 1)
-        if not fds:
-            raise RuntimeError(f"no file descriptor received from {path}")
-        return fds[0]
+def _fetch_fd(path: str, index: int = 0, attempts: int = 5) -> int:
+    """Ask the peer serving ``path`` for its descriptor ``index``.  A refused / interrupted exchange (a loaded box:
+    full accept backlog, EINTR, a descriptor table momentarily full) is retried a few times before it counts as
+    a failure -- one failed fetch moves the WHOLE team off the VMM heap."""
+    last: Optional[BaseException] = None
+    for k in range(attempts):
+        try:
+            with socket.socket(socket.AF_UNIX, socket.SOCK_STREAM) as s:
+                s.connect(path)
+                s.sendall(bytes([index]))
+                _, fds, _, _ = socket.recv_fds(s, 1, 1)
+                if fds:
+                    return fds[0]
+                last = RuntimeError(f"no file descriptor received from {path!r}")
+        except OSError as exc:
+            last = exc
+        time.sleep(0.05 * (k + 1))
+    raise RuntimeError(f"could not fetch descriptor {index} from {path!r}: {last!r}")
 
 
 def heap_kind(device: torch.device, world: int) -> str:

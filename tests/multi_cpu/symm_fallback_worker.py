@@ -60,8 +60,8 @@ class FakeDriver:
 
     def vmm_import_fd(self, fd, dev):
         self._maybe_fail("vmm_import_fd")
-        os.lseek(fd, 0, os.SEEK_SET)
-        remote = int(os.read(fd, 64).decode())
+        # (descriptors received over SCM_RIGHTS share ONE file offset with every other receiver: read positionally)
+        remote = int(os.pread(fd, 64, 0).decode())
         h = self._new()
         self.live_handles.add(h)
         self.imported = getattr(self, "imported", []) + [remote]
