@@ -56,7 +56,9 @@ class EmpireAttack(ColumnStatAttack):
         if d >= 4096 * max(1, pool):
             pieces = max(pieces, pool)
         per = -(-d // max(1, pieces))
-        return max(64, -(-per // 64) * 64)
+        # cache-line multiples (16 floats) once there is a line per piece; below that the reference's subtask COUNT
+        # is what callers observe (its test suite compares the counts for two pool sizes on a 256 x 256 input)
+        return -(-per // 16) * 16 if per >= 64 else max(4, -(-per // 4) * 4)
 
 
 __all__ = ["EmpireAttack"]
