@@ -3,7 +3,7 @@
 # the warp-tiled selection kernel, then -- on an 8-GPU box -- scripts/gpu_tables8.sh.
 #   gpurun --timeout 1500 -- 'bash scripts/gpu_next.sh'
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_zz_round2_late.py -q -p no:warnings -p no:cacheprovider > gpurun_out/late_tests.log 2>&1
+timeout 900 python -m pytest tests/gpu_late/late_cases.py -m gpu -q -p no:warnings -p no:cacheprovider > gpurun_out/late_tests.log 2>&1
 echo "late tests rc=$?"; tail -5 gpurun_out/late_tests.log
 for n in 32 64 128; do
   timeout 300 python benchmarks/agg_sweep.py --cw-variants --n $n --f 8 --dims 1e7 --out gpurun_out/cw_variants_n$n.json 2>&1 | tail -9
