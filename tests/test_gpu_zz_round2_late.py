@@ -15,7 +15,7 @@ import warnings
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIMIT_S = 1500
+LIMIT_S = 600
 
 
 @pytest.mark.gpu
